@@ -1,0 +1,157 @@
+/* b2sv.h -- C ABI of the B200 statevector engine that sits behind unitaria's simulate seam.
+ *
+ * The reference (tequilahub/unitaria v0.2.0, pure Python) has no FFI of its own; its only seam to a
+ * simulator is the Python call
+ *     tq.simulate(padded, initial_state=wfn, backend="qulacs").to_array(LSB)
+ * made from Circuit.simulate (src/unitaria/circuit.py:62-70), followed by Subspace.project and the
+ * normalization factor in Node.simulate / Node.simulate_norm (src/unitaria/nodes/node.py:363-403,
+ * src/unitaria/subspace.py:297-335).  Each entry point below names the piece of that path it
+ * replaces.  The ctypes binding a maintainer would add is shown in INTEGRATION.md and shipped as
+ * unitaria_b200/cabi.py.
+ *
+ * Conventions
+ *   - amplitudes are little-endian in the qubit index ("LSB", circuit.py:63-70): bit q of an
+ *     amplitude's index is the state of qubit q.
+ *   - host amplitude buffers are always complex128 (interleaved re,im doubles), whatever the
+ *     device storage dtype is; they are borrowed for the duration of the call only.
+ *   - every function returns 0 on success or a negative B2SV_E* code; b2sv_last_error() gives the
+ *     message for the calling thread.  Nothing throws across the ABI, there are no callbacks.
+ *   - a handle is not thread-safe; different handles may be used from different threads.
+ *   - there is no CPU fallback: without a usable CUDA device every compute entry point fails with
+ *     B2SV_ENODEV.
+ */
+#ifndef B2SV_H
+#define B2SV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2SV_ABI_VERSION 1
+
+typedef struct b2sv b2sv_t;
+
+enum {
+    B2SV_OK = 0,
+    B2SV_EINVAL = -1,  /* bad argument */
+    B2SV_ENODEV = -2,  /* no CUDA device / CUDA runtime failure at start-up */
+    B2SV_ENOMEM = -3,  /* device or host allocation failed */
+    B2SV_ECUDA = -4,   /* a CUDA call or kernel failed */
+    B2SV_ESTATE = -5   /* call not valid in the handle's current state */
+};
+
+enum { B2SV_C128 = 0, B2SV_C64 = 1 }; /* device storage dtype of the amplitudes */
+
+/* Lowered gate alphabet.  unitaria_b200/lowering.py maps the tequila gates unitaria emits
+ * (I X Y Z H Rx Ry Rz Phase GlobalPhase SWAP, any control set) onto these. */
+enum {
+    B2SV_OP_MAT1 = 0,  /* dense 2x2 on t0: m = {m00,m01,m10,m11} as (re,im) pairs, row-major      */
+    B2SV_OP_DIAG1 = 1, /* diag(d0,d1) on t0: m[0..1] = d0, m[2..3] = d1                            */
+    B2SV_OP_X = 2,     /* bit flip of t0 -- exact data movement, no arithmetic on the amplitudes    */
+    B2SV_OP_SWAP = 3,  /* exchange qubits t0,t1 -- exact data movement                              */
+    B2SV_OP_PHASE = 4  /* no target: multiply the controlled block by m[0..1] (GlobalPhase)         */
+};
+
+/* One lowered gate; applied iff all bits of ctrl_mask are 1 in the amplitude's index. */
+typedef struct b2sv_gate {
+    uint8_t op;
+    uint8_t n_targets; /* 0 (PHASE), 1, or 2 (SWAP) */
+    uint8_t t0, t1;
+    uint32_t reserved;
+    uint64_t ctrl_mask;
+    double m[8];
+} b2sv_gate;
+
+/* Planner / execution options for b2sv_apply (NULL = defaults). */
+typedef struct b2sv_plan_opts {
+    int32_t fuse;         /* 0: one kernel launch per gate (qulacs-like schedule); 1: fused sweeps (default) */
+    int32_t tile_qubits;  /* qubits per shared-memory tile of a fused sweep; 0 = default             */
+    int32_t perm_runs;    /* 1: runs of X/SWAP gates become one index-map sweep (default); 0: off    */
+    int32_t timing;       /* 1: bracket every launch with CUDA events and accumulate per-class times */
+    int32_t lookahead;    /* commutation-aware lookahead window in gates; 0 = default                 */
+    int32_t reserved[3];
+} b2sv_plan_opts;
+
+/* Flattened Subspace program (restates Subspace.test_basis, subspace.py:297-323).
+ * A subspace is a run of `count` consecutive factor nodes starting at `first`, least-significant
+ * factor first.  kind 0 = ZeroQubitSubspace (1 qubit, must be 0).  kind 1 = ControlledSubspace:
+ * its top qubit selects child 0 (case_zero) or child 1 (case_one) for its lower nbits-1 qubits.
+ * Node 0..root_count-1 of the array passed to b2sv_project_* form the root subspace. */
+typedef struct b2sv_subnode {
+    int32_t kind;
+    int32_t nbits;            /* qubits this factor spans */
+    uint64_t dim;             /* dimension of this factor */
+    uint64_t dim0;            /* dimension of case_zero (kind 1) */
+    int32_t child_first[2];   /* first factor node of case_zero / case_one */
+    int32_t child_count[2];   /* number of factor nodes of case_zero / case_one */
+} b2sv_subnode;
+
+/* Counters filled by b2sv_stats (accumulated since creation or the last b2sv_stats_reset). */
+typedef struct b2sv_stats_t {
+    uint64_t gates_in;        /* lowered gates handed to b2sv_apply                                   */
+    uint64_t gates_live;      /* ... of which not exact no-ops                                        */
+    uint64_t launches;        /* kernel launches made by b2sv_apply                                   */
+    uint64_t launches_by_class[8]; /* 0 gate1q, 1 tile sweep, 2 perm run, 3 scale, 4 project, 5 init/convert, 6 swap pack */
+    double alg_bytes_by_class[8];  /* algorithmic bytes (2*B*M per sweep)                */
+    double ms_by_class[8];         /* CUDA-event time per class (only with opts.timing)                */
+    double apply_ms;               /* CUDA-event time of whole b2sv_apply calls (always measured)      */
+} b2sv_stats_t;
+
+/* ---- lifetime ---------------------------------------------------------------------------------- */
+
+/* State of `n_qubits` qubits (2^n amplitudes) on CUDA device `device`.  Replaces the
+ * QubitWaveFunction + qulacs QuantumState that tq.simulate allocates per call (circuit.py:62-69). */
+int b2sv_create(int n_qubits, int dtype, int device, b2sv_t** out);
+int b2sv_destroy(b2sv_t* sv);
+
+/* ---- state I/O (circuit.py:62-65: from_basis_state / from_array; :70: to_array) ---------------- */
+int b2sv_set_basis(b2sv_t* sv, uint64_t index);
+int b2sv_upload(b2sv_t* sv, const void* host_amps_c128);
+int b2sv_download(b2sv_t* sv, void* host_out_c128);
+
+/* ---- the simulate call itself (circuit.py:69, tq.simulate -> qulacs update_quantum_state) ------ */
+int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_plan_opts* opts);
+
+/* ---- fused post-processing (node.py:379 project*normalization, node.py:402 norm) --------------- */
+/* sum of |psi_i|^2 over i in the subspace on the low `target_qubits` qubits with every higher
+ * (ancilla) qubit 0. */
+int b2sv_project_norm2(b2sv_t* sv, const b2sv_subnode* prog, int n_nodes, int root_count, int target_qubits,
+                       double* out);
+/* host_out[rank(i)] = (scale_re + i*scale_im) * psi_i for the members i, in ascending-index order
+ * (= Subspace.enumerate_basis order, subspace.py:325-329); `dim` must equal the subspace dimension. */
+int b2sv_project_gather(b2sv_t* sv, const b2sv_subnode* prog, int n_nodes, int root_count, int target_qubits,
+                        double scale_re, double scale_im, void* host_out_c128, uint64_t dim);
+/* Same predicate on the host-visible side of enumerate_basis: writes the member indices (int64). */
+int b2sv_enumerate_basis(b2sv_t* sv, const b2sv_subnode* prog, int n_nodes, int root_count, int target_qubits,
+                         int64_t* host_out, uint64_t dim);
+
+/* ---- device-resident hand-off and the pieces the distributed layer drives ----------------------- */
+int b2sv_device_ptr(b2sv_t* sv, void** amps, uint64_t* bytes);
+int b2sv_sync(b2sv_t* sv);
+/* Exchange support for global<->local qubit swaps (unitaria_b200/distributed.py): pack the half of
+ * the shard whose local qubit `q` differs from `keep_bit` into `staging` (contiguous), and the
+ * inverse. */
+int b2sv_swap_pack(b2sv_t* sv, int q, int keep_bit, void* staging_dev);
+int b2sv_swap_unpack(b2sv_t* sv, int q, int keep_bit, const void* staging_dev);
+
+/* ---- planner introspection (no GPU needed): how would `gates` be executed? ---------------------- */
+/* Writes up to `cap` int64 words describing the plan: for each segment
+ *   {class, n_gates, tile_mask, gate_index_0, ..., gate_index_{n_gates-1}}
+ * and returns the number of words needed in *n_words. */
+int b2sv_plan_describe(int n_qubits, int dtype, const b2sv_gate* gates, size_t n_gates, const b2sv_plan_opts* opts,
+                       int64_t* out_words, size_t cap, size_t* n_words);
+
+/* ---- bookkeeping ------------------------------------------------------------------------------- */
+int b2sv_stats(b2sv_t* sv, b2sv_stats_t* out);
+int b2sv_stats_reset(b2sv_t* sv);
+int b2sv_abi_version(void);
+int b2sv_device_count(void);
+const char* b2sv_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2SV_H */

@@ -1,0 +1,217 @@
+"""Drop-in backend: the B200 engine behind unitaria's ``Circuit.simulate`` / ``Node.simulate``.
+
+``install()`` replaces ``unitaria.circuit.Circuit.simulate`` (/root/reference/src/unitaria/circuit.py:42-70)
+and adds fused fast paths for ``Node.simulate`` and ``Node.simulate_norm``
+(/root/reference/src/unitaria/nodes/node.py:363-403).  Everything above the seam -- the Node algebra,
+``circuit()``, ``toarray()``, ``normalization``, ``Subspace`` and the tequila circuit objects -- is
+untouched.  The functions below can also be used directly on any tequila-like circuit object
+(an object with ``.gates``), which is how the GPU tests drive them.
+
+Preserved quirks: Q1 the "no qubit touched" early return that drops global
+phases, Q2 register width ``max(1, n_qubits)`` and complex128 results, Q3 ``np.integer`` inputs and
+dense-vector inputs, Q7 ``backend="qulacs"`` accepted and ignored.
+"""
+
+from __future__ import annotations
+
+import weakref
+
+import numpy as np
+
+from .cabi import PlanOpts
+from .engine import StateVector
+from .lowering import lower_gates, touches_any_qubit
+from .subspace_prog import SubspaceProgram
+
+_DEFAULTS = {"dtype": "complex128", "device": 0, "opts": None}
+# lowered gate lists, keyed by the identity of the tequila circuit object and its gate count
+_LOWERED: dict = {}
+# one resident statevector per (n_qubits, dtype, device): verify-style workloads call simulate
+# thousands of times on the same register size
+_STATES: dict = {}
+
+
+def configure(dtype=None, device=None, opts: PlanOpts | None = None) -> None:
+    """Engine options for the patched entry points (``dtype``: "complex128" | "complex64")."""
+    if dtype is not None:
+        _DEFAULTS["dtype"] = dtype
+    if device is not None:
+        _DEFAULTS["device"] = int(device)
+    _DEFAULTS["opts"] = opts
+
+
+def clear_caches() -> None:
+    _LOWERED.clear()
+    for sv in _STATES.values():
+        sv.close()
+    _STATES.clear()
+
+
+def _state(n_qubits: int) -> StateVector:
+    key = (max(1, int(n_qubits)), str(_DEFAULTS["dtype"]), _DEFAULTS["device"])
+    sv = _STATES.get(key)
+    if sv is None:
+        # keep device memory bounded: drop other resident registers before allocating a big one
+        if key[0] >= 26:
+            clear_states = [k for k in _STATES if k != key]
+            for k in clear_states:
+                _STATES.pop(k).close()
+        sv = StateVector(key[0], dtype=_DEFAULTS["dtype"], device=_DEFAULTS["device"])
+        _STATES[key] = sv
+    return sv
+
+
+def _lowered(tq_circuit, n_qubits: int) -> np.ndarray:
+    gates = tq_circuit.gates
+    key = id(tq_circuit)
+    hit = _LOWERED.get(key)
+    if hit is not None and hit[0]() is tq_circuit and hit[1] == len(gates) and hit[2] == n_qubits:
+        return hit[3]
+    low = lower_gates(gates, n_qubits)
+    try:
+        ref = weakref.ref(tq_circuit, lambda _r, k=key: _LOWERED.pop(k, None))
+        _LOWERED[key] = (ref, len(gates), n_qubits, low)
+    except TypeError:  # object cannot be weakly referenced: do not cache
+        pass
+    return low
+
+
+def _run(tq_circuit, n_qubits: int, input) -> StateVector:
+    sv = _state(n_qubits)
+    if isinstance(input, np.ndarray):
+        if input.size != sv.size:
+            raise ValueError(f"input has {input.size} amplitudes, circuit register has {sv.size}")
+        sv.upload(input)
+    elif isinstance(input, (int, np.integer)):
+        sv.set_basis(int(input))
+    else:
+        raise TypeError(f"input must be an int or an ndarray, not {type(input).__name__}")
+    sv.apply_lowered(_lowered(tq_circuit, n_qubits), _DEFAULTS["opts"])
+    return sv
+
+
+def simulate_circuit(tq_circuit, n_qubits: int, input=0, **kwargs) -> np.ndarray:
+    """Same contract as ``Circuit.simulate`` (circuit.py:42-70); ``kwargs`` (``backend=...``) are ignored."""
+    if not touches_any_qubit(tq_circuit.gates):  # circuit.py:54-61, including the dropped global phase
+        if isinstance(input, np.ndarray):
+            return input
+        assert isinstance(input, (int, np.integer))
+        result = np.zeros(2**n_qubits, dtype=complex)
+        result[input] = 1
+        return result
+    return _run(tq_circuit, n_qubits, input).download()
+
+
+def simulate_projected(tq_circuit, n_qubits: int, subspace_out, normalization, input=0) -> np.ndarray:
+    """``normalization * subspace_out.project(circuit.simulate(input))`` (node.py:378-379), with the
+    projection gathered on the device so only ``dimension_out`` amplitudes cross PCIe."""
+    prog = subspace_out if isinstance(subspace_out, SubspaceProgram) else SubspaceProgram(subspace_out)
+    if not touches_any_qubit(tq_circuit.gates):
+        wavefunction = simulate_circuit(tq_circuit, n_qubits, input)
+        return normalization * _host_project(prog, wavefunction)
+    return _run(tq_circuit, n_qubits, input).project(prog, scale=normalization)
+
+
+def simulate_norm(tq_circuit, n_qubits: int, subspace_out, normalization, input=0) -> float:
+    """``norm(normalization * project(simulate(input)))`` (node.py:390-403) as one device reduction."""
+    prog = subspace_out if isinstance(subspace_out, SubspaceProgram) else SubspaceProgram(subspace_out)
+    if not touches_any_qubit(tq_circuit.gates):
+        return float(np.linalg.norm(simulate_projected(tq_circuit, n_qubits, prog, normalization, input)))
+    return float(abs(normalization) * np.sqrt(_run(tq_circuit, n_qubits, input).project_norm2(prog)))
+
+
+def _host_project(prog: SubspaceProgram, vector: np.ndarray) -> np.ndarray:
+    # only reached for circuits that touch no qubit (tiny registers): index list from the device
+    sv = _state(max(1, prog.total_qubits))
+    return vector[sv.enumerate_basis(prog)]
+
+
+# ---------------------------------------------------------------------------------------------
+# monkey patches
+# ---------------------------------------------------------------------------------------------
+
+_ORIGINALS: dict = {}
+
+
+def install(dtype="complex128", device: int = 0, opts: PlanOpts | None = None, patch_nodes: bool = True):
+    """Route unitaria's simulation through the B200 engine.  Returns the patched module."""
+    import unitaria.circuit as ucircuit
+
+    configure(dtype=dtype, device=device, opts=opts)
+    Circuit = ucircuit.Circuit
+    if "Circuit.simulate" not in _ORIGINALS:
+        _ORIGINALS["Circuit.simulate"] = Circuit.simulate
+
+    def simulate(self, input=0, **kwargs):
+        return simulate_circuit(self._tq_circuit, self.n_qubits, input, **kwargs)
+
+    simulate.__doc__ = _ORIGINALS["Circuit.simulate"].__doc__
+    Circuit.simulate = simulate
+
+    if patch_nodes:
+        import unitaria.nodes.node as unode
+
+        Node = unode.Node
+        if "Node.simulate" not in _ORIGINALS:
+            _ORIGINALS["Node.simulate"] = Node.simulate
+            _ORIGINALS["Node.simulate_norm"] = Node.simulate_norm
+
+        def node_simulate(self, input=None):
+            if self.is_vector() and input is None:
+                input = 0
+            circuit = self.circuit()
+            prog = _subspace_program(self.subspace_out)
+            if input is not None:
+                return simulate_projected(circuit._tq_circuit, circuit.n_qubits, prog, self.normalization, input)
+            # matrix case (node.py:381-388): one lowered plan, one resident register, dimension_in runs
+            basis_in = _state(max(1, self.subspace_in.total_qubits)).enumerate_basis(_subspace_program(self.subspace_in))
+            output = np.zeros((self.dimension_out, self.dimension_in), dtype=np.complex128)
+            for i, b in enumerate(basis_in):
+                output[:, i] = simulate_projected(circuit._tq_circuit, circuit.n_qubits, prog, self.normalization, int(b))
+            return output
+
+        def node_simulate_norm(self, input=None):
+            if input is None and not self.is_vector():
+                raise ValueError("Cannot simulate norm, since node is a matrix and no input was given")
+            if self.is_vector() and input is None:
+                input = 0
+            circuit = self.circuit()
+            prog = _subspace_program(self.subspace_out)
+            return simulate_norm(circuit._tq_circuit, circuit.n_qubits, prog, self.normalization, input)
+
+        node_simulate.__doc__ = _ORIGINALS["Node.simulate"].__doc__
+        node_simulate_norm.__doc__ = _ORIGINALS["Node.simulate_norm"].__doc__
+        Node.simulate = node_simulate
+        Node.simulate_norm = node_simulate_norm
+    return ucircuit
+
+
+def uninstall() -> None:
+    if "Circuit.simulate" in _ORIGINALS:
+        import unitaria.circuit as ucircuit
+
+        ucircuit.Circuit.simulate = _ORIGINALS.pop("Circuit.simulate")
+    if "Node.simulate" in _ORIGINALS:
+        import unitaria.nodes.node as unode
+
+        unode.Node.simulate = _ORIGINALS.pop("Node.simulate")
+        unode.Node.simulate_norm = _ORIGINALS.pop("Node.simulate_norm")
+    clear_caches()
+
+
+_PROGRAMS: dict = {}
+
+
+def _subspace_program(subspace) -> SubspaceProgram:
+    """Subspaces are immutable and hashable in unitaria (frozen factors); cache their programs."""
+    try:
+        key = subspace
+        hit = _PROGRAMS.get(key)
+    except TypeError:
+        return SubspaceProgram(subspace)
+    if hit is None:
+        hit = SubspaceProgram(subspace)
+        if len(_PROGRAMS) > 256:
+            _PROGRAMS.clear()
+        _PROGRAMS[key] = hit
+    return hit

@@ -1,0 +1,555 @@
+// kernels.cuh -- hand-written sm_100a kernels of the B200 statevector engine.
+//
+// Every kernel here works on amplitudes in LSB order (bit q of the index = qubit q), the layout
+// Circuit.simulate returns (/root/reference/src/unitaria/circuit.py:63-70).  All of them are
+// HBM-bound integer/indexing + complex-FMA work (<= 14 flops per amplitude per gate); none is
+// GEMM-shaped, so none uses the tensor cores.  The levers are the ones that matter for such
+// kernels on B200: 16-byte accesses, long contiguous runs per request (bulk-async / TMA copies of
+// whole tile chunks), grids that are multiples of the SM count, and as few sweeps as possible.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b2sv.h"
+
+namespace b2svk {
+
+constexpr int kMaxFixed = 24;
+constexpr int kThreads = 256;
+
+struct ExpandArgs {
+    int m;
+    uint8_t pos[kMaxFixed];  // ascending bit positions at which a 0 is inserted
+};
+
+__host__ __device__ __forceinline__ uint64_t insert_zero(uint64_t k, int p) {
+    const uint64_t lo = k & ((1ull << p) - 1);
+    return ((k >> p) << (p + 1)) | lo;
+}
+
+__device__ __forceinline__ uint64_t expand_bits(uint64_t k, const ExpandArgs& e) {
+    for (int i = 0; i < e.m; ++i) k = insert_zero(k, e.pos[i]);
+    return k;
+}
+
+// ---- amplitude access: storage type A (double2 = complex128, float2 = complex64), math in fp64 ----
+
+__device__ __forceinline__ double2 to_c128(double2 v) { return v; }
+__device__ __forceinline__ double2 to_c128(float2 v) { return make_double2((double)v.x, (double)v.y); }
+template <typename A>
+__device__ __forceinline__ A from_c128(double2 v);
+template <>
+__device__ __forceinline__ double2 from_c128<double2>(double2 v) {
+    return v;
+}
+template <>
+__device__ __forceinline__ float2 from_c128<float2>(double2 v) {
+    return make_float2((float)v.x, (float)v.y);
+}
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {  // a*b + c
+    return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
+}
+
+// ===================================================================================================
+// 1. Stand-alone multi-controlled gate: visits only the 2^(n-c[-1]) amplitudes selected by the
+//    control bits (the schedule of one qulacs update, but with all controls handled in the index).
+// ===================================================================================================
+
+struct Gate1Args {
+    ExpandArgs ex;      // fixed positions = controls + target(s)
+    uint64_t ctrl;      // OR-ed into every expanded index
+    uint64_t bit0, bit1;
+    uint64_t count;     // number of (pairs of) amplitudes to visit
+    int op;
+    double m[8];
+};
+
+template <typename A>
+__global__ void __launch_bounds__(kThreads) k_gate1(A* __restrict__ psi, const Gate1Args a) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a.count; k += stride) {
+        const uint64_t i0 = expand_bits(k, a.ex) | a.ctrl;
+        switch (a.op) {
+            case B2SV_OP_X: {
+                const uint64_t i1 = i0 | a.bit0;
+                const A v0 = psi[i0], v1 = psi[i1];
+                psi[i0] = v1;
+                psi[i1] = v0;
+            } break;
+            case B2SV_OP_SWAP: {
+                const uint64_t ia = i0 | a.bit0, ib = i0 | a.bit1;
+                const A va = psi[ia], vb = psi[ib];
+                psi[ia] = vb;
+                psi[ib] = va;
+            } break;
+            case B2SV_OP_MAT1: {
+                const uint64_t i1 = i0 | a.bit0;
+                const double2 v0 = to_c128(psi[i0]), v1 = to_c128(psi[i1]);
+                const double2 m00 = make_double2(a.m[0], a.m[1]), m01 = make_double2(a.m[2], a.m[3]);
+                const double2 m10 = make_double2(a.m[4], a.m[5]), m11 = make_double2(a.m[6], a.m[7]);
+                psi[i0] = from_c128<A>(cfma(m01, v1, cmul(m00, v0)));
+                psi[i1] = from_c128<A>(cfma(m11, v1, cmul(m10, v0)));
+            } break;
+            case B2SV_OP_DIAG1: {
+                const uint64_t i1 = i0 | a.bit0;
+                const double2 d0 = make_double2(a.m[0], a.m[1]), d1 = make_double2(a.m[2], a.m[3]);
+                if (!(d0.x == 1.0 && d0.y == 0.0)) psi[i0] = from_c128<A>(cmul(d0, to_c128(psi[i0])));
+                if (!(d1.x == 1.0 && d1.y == 0.0)) psi[i1] = from_c128<A>(cmul(d1, to_c128(psi[i1])));
+            } break;
+            default: {  // B2SV_OP_PHASE
+                const double2 w = make_double2(a.m[0], a.m[1]);
+                psi[i0] = from_c128<A>(cmul(w, to_c128(psi[i0])));
+            } break;
+        }
+    }
+}
+
+// ===================================================================================================
+// 2. Fused tile sweep.  A CTA owns one tile = all 2^k combinations of the tile qubits T for one
+//    setting of the other n-k qubits.  T always contains the low `lc` qubits, so the tile is
+//    2^(k-lc) contiguous chunks of 2^lc amplitudes; each chunk moves with ONE bulk-async (TMA engine)
+//    copy global->shared, completion tracked by an mbarrier, and one bulk copy back.  In between,
+//    the gates of the sweep are applied to the tile in shared memory: targets are tile-local bit
+//    positions, controls inside the tile are per-element predicates, controls outside the tile are
+//    CTA-uniform (the whole CTA skips the gate).  Algorithmic traffic: 2 * sizeof(A) * 2^n per sweep.
+// ===================================================================================================
+
+struct __align__(16) TileOp {
+    uint8_t op;
+    uint8_t tpos, tpos2;  // tile-local target positions (0xFF: DIAG1 target outside the tile)
+    uint8_t nfix;         // number of fixed tile-local positions while enumerating
+    uint32_t lctrl;       // tile-local control mask
+    uint64_t fixpos;      // nfix ascending tile-local positions, 4 bits each
+    uint64_t ext_ctrl;    // controls outside the tile (global index bits)
+    uint64_t ext_tbit;    // DIAG1 whose target is outside the tile: that global bit
+    double m[8];
+};
+static_assert(sizeof(TileOp) == 96, "TileOp layout");
+
+struct TileArgs {
+    ExpandArgs tile_ex;   // the k tile-qubit positions (ascending)
+    int k, lc;
+    int n_ops;
+    const TileOp* ops;
+};
+
+__device__ __forceinline__ uint32_t expand_local(uint32_t p, uint64_t fixpos, int nfix) {
+    for (int i = 0; i < nfix; ++i) {
+        const int pos = (int)((fixpos >> (4 * i)) & 15);
+        const uint32_t lo = p & ((1u << pos) - 1);
+        p = ((p >> pos) << (pos + 1)) | lo;
+    }
+    return p;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "B2SV_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra B2SV_DONE_%=;\n"
+        "bra B2SV_WAIT_%=;\n"
+        "B2SV_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+template <typename A>
+__device__ __forceinline__ void tile_apply_op(A* tile, const TileOp& op, int k, uint64_t base) {
+    const int tid = threadIdx.x;
+    switch (op.op) {
+        case B2SV_OP_X: {
+            const uint32_t cnt = 1u << (k - op.nfix), bt = 1u << op.tpos;
+            for (uint32_t p = tid; p < cnt; p += kThreads) {
+                const uint32_t l0 = expand_local(p, op.fixpos, op.nfix) | op.lctrl;
+                const A v0 = tile[l0], v1 = tile[l0 | bt];
+                tile[l0] = v1;
+                tile[l0 | bt] = v0;
+            }
+        } break;
+        case B2SV_OP_SWAP: {
+            const uint32_t cnt = 1u << (k - op.nfix), ba = 1u << op.tpos, bb = 1u << op.tpos2;
+            for (uint32_t p = tid; p < cnt; p += kThreads) {
+                const uint32_t l = expand_local(p, op.fixpos, op.nfix) | op.lctrl;
+                const A va = tile[l | ba], vb = tile[l | bb];
+                tile[l | ba] = vb;
+                tile[l | bb] = va;
+            }
+        } break;
+        case B2SV_OP_MAT1: {
+            const uint32_t cnt = 1u << (k - op.nfix), bt = 1u << op.tpos;
+            const double2 m00 = make_double2(op.m[0], op.m[1]), m01 = make_double2(op.m[2], op.m[3]);
+            const double2 m10 = make_double2(op.m[4], op.m[5]), m11 = make_double2(op.m[6], op.m[7]);
+            for (uint32_t p = tid; p < cnt; p += kThreads) {
+                const uint32_t l0 = expand_local(p, op.fixpos, op.nfix) | op.lctrl;
+                const double2 v0 = to_c128(tile[l0]), v1 = to_c128(tile[l0 | bt]);
+                tile[l0] = from_c128<A>(cfma(m01, v1, cmul(m00, v0)));
+                tile[l0 | bt] = from_c128<A>(cfma(m11, v1, cmul(m10, v0)));
+            }
+        } break;
+        case B2SV_OP_DIAG1: {
+            const double2 d0 = make_double2(op.m[0], op.m[1]), d1 = make_double2(op.m[2], op.m[3]);
+            if (op.tpos == 0xFF) {  // target outside the tile: one CTA-uniform factor
+                const double2 d = (base & op.ext_tbit) ? d1 : d0;
+                if (d.x == 1.0 && d.y == 0.0) break;
+                const uint32_t cnt = 1u << (k - op.nfix);
+                for (uint32_t p = tid; p < cnt; p += kThreads) {
+                    const uint32_t l = expand_local(p, op.fixpos, op.nfix) | op.lctrl;
+                    tile[l] = from_c128<A>(cmul(d, to_c128(tile[l])));
+                }
+            } else {
+                const uint32_t cnt = 1u << (k - op.nfix), bt = 1u << op.tpos;
+                const bool one0 = (d0.x == 1.0 && d0.y == 0.0), one1 = (d1.x == 1.0 && d1.y == 0.0);
+                for (uint32_t p = tid; p < cnt; p += kThreads) {
+                    const uint32_t l0 = expand_local(p, op.fixpos, op.nfix) | op.lctrl;
+                    if (!one0) tile[l0] = from_c128<A>(cmul(d0, to_c128(tile[l0])));
+                    if (!one1) tile[l0 | bt] = from_c128<A>(cmul(d1, to_c128(tile[l0 | bt])));
+                }
+            }
+        } break;
+        default: {  // PHASE
+            const double2 w = make_double2(op.m[0], op.m[1]);
+            const uint32_t cnt = 1u << (k - op.nfix);
+            for (uint32_t p = tid; p < cnt; p += kThreads) {
+                const uint32_t l = expand_local(p, op.fixpos, op.nfix) | op.lctrl;
+                tile[l] = from_c128<A>(cmul(w, to_c128(tile[l])));
+            }
+        } break;
+    }
+}
+
+// global offset (in amplitudes, relative to the tile base) of chunk j of the tile
+__device__ __forceinline__ uint64_t chunk_offset(uint32_t j, const ExpandArgs& ex, int k, int lc) {
+    uint64_t off = 0;
+    for (int i = lc; i < k; ++i)
+        if ((j >> (i - lc)) & 1) off |= 1ull << ex.pos[i];
+    return off;
+}
+
+template <typename A, bool BULK>
+__global__ void __launch_bounds__(kThreads) k_tile(A* __restrict__ psi, const TileArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    A* tile = reinterpret_cast<A*>(smem_raw);
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x;
+    const int k = a.k, lc = a.lc;
+    const uint32_t n_chunks = 1u << (k - lc), chunk_elems = 1u << lc;
+    const uint32_t chunk_bytes = chunk_elems * (uint32_t)sizeof(A);
+    const uint64_t base = expand_bits((uint64_t)blockIdx.x, a.tile_ex);
+
+    if (BULK) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) mbar_expect_tx(&bar, chunk_bytes * n_chunks);
+        __syncthreads();
+        for (uint32_t j = tid; j < n_chunks; j += kThreads)
+            bulk_g2s(tile + (size_t)j * chunk_elems, psi + (base | chunk_offset(j, a.tile_ex, k, lc)), chunk_bytes, &bar);
+        mbar_wait(&bar, 0);
+    } else {
+        const uint32_t elems = 1u << k;
+        for (uint32_t l = tid; l < elems; l += kThreads) {
+            const uint64_t g = base | chunk_offset(l >> lc, a.tile_ex, k, lc) | (l & (chunk_elems - 1));
+            tile[l] = psi[g];
+        }
+        __syncthreads();
+    }
+
+    for (int o = 0; o < a.n_ops; ++o) {
+        const TileOp& op = a.ops[o];
+        if ((base & op.ext_ctrl) != op.ext_ctrl) continue;  // CTA-uniform: gate not active on this tile
+        tile_apply_op<A>(tile, op, k, base);
+        __syncthreads();
+    }
+
+    if (BULK) {
+        // generic-proxy writes to shared memory must be visible to the async proxy before the copy out
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        for (uint32_t j = tid; j < n_chunks; j += kThreads)
+            bulk_s2g(psi + (base | chunk_offset(j, a.tile_ex, k, lc)), tile + (size_t)j * chunk_elems, chunk_bytes);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    } else {
+        const uint32_t elems = 1u << k;
+        for (uint32_t l = tid; l < elems; l += kThreads) {
+            const uint64_t g = base | chunk_offset(l >> lc, a.tile_ex, k, lc) | (l & (chunk_elems - 1));
+            psi[g] = tile[l];
+        }
+    }
+}
+
+// ===================================================================================================
+// 3. Permutation run: a run of X / multi-controlled X / (controlled) SWAP gates is a bijection f on
+//    amplitude indices.  One out-of-place sweep computes out[j] = in[f^-1(j)] (writes coalesced).
+//    f^-1 is evaluated bit-sliced: a thread owns 32 output indices; word q holds bit q of all 32, so
+//    an MCX is "W[t] ^= W[c0] & W[c1] & ..." -- one pass of word ops per gate for 32 amplitudes.
+//    Words live in shared memory (a register file cannot be indexed by a run-time qubit number); the
+//    gate program is read through the constant cache so it does not compete with shared memory.
+// ===================================================================================================
+
+constexpr int kPermMaxOps = 7680;          // 60 KiB of constant memory
+constexpr int kPermThreads = 256;
+constexpr int kPermRowBytes = kPermThreads * 4;
+
+// 8-byte op.  Row numbers are qubit indices; row `n` is the all-ones row (an unused control slot).
+// kind 0: X     W[a] ^= acc & W[b] & W[c] & W[d]
+// kind 1: SWAP  m = acc & W[c] & W[d] & (W[a]^W[b]); W[a]^=m; W[b]^=m
+// kind 2: ACC   acc = W[a] & W[b] & W[c] & W[d]            (starts a long control chain)
+// kind 3: ACC&  acc &= W[a] & W[b] & W[c] & W[d]
+// After a kind 0/1 op acc is reset to all ones.
+struct PermOp {
+    uint8_t kind, a, b, c, d, pad[3];
+};
+static_assert(sizeof(PermOp) == 8, "PermOp layout");
+
+__constant__ uint2 c_perm_ops[kPermMaxOps];
+
+template <typename A>
+__global__ void __launch_bounds__(kPermThreads) k_perm(const A* __restrict__ in, A* __restrict__ out, int n, int n_ops) {
+    extern __shared__ __align__(16) uint32_t W[];  // (n + 1) rows of kPermThreads words
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint64_t warp_global = (uint64_t)blockIdx.x * (kPermThreads / 32) + (tid >> 5);
+    const uint64_t warp_base = warp_global << 10;  // 1024 outputs per warp: j = warp_base + b*32 + lane
+    // initial words: bit b of word q = bit q of (warp_base + b*32 + lane)
+    for (int q = 0; q < n; ++q) {
+        uint32_t w;
+        if (q < 5) w = ((lane >> q) & 1) ? 0xFFFFFFFFu : 0u;
+        else if (q == 5) w = 0xAAAAAAAAu;
+        else if (q == 6) w = 0xCCCCCCCCu;
+        else if (q == 7) w = 0xF0F0F0F0u;
+        else if (q == 8) w = 0xFF00FF00u;
+        else if (q == 9) w = 0xFFFF0000u;
+        else w = ((warp_global >> (q - 10)) & 1) ? 0xFFFFFFFFu : 0u;
+        W[q * kPermThreads + tid] = w;
+    }
+    W[n * kPermThreads + tid] = 0xFFFFFFFFu;
+    uint32_t acc = 0xFFFFFFFFu;
+    uint32_t* Wt = W + tid;
+    for (int o = 0; o < n_ops; ++o) {
+        const uint2 raw = c_perm_ops[o];
+        const uint32_t kind = raw.x & 0xFF;
+        const uint32_t ra = (raw.x >> 8) & 0xFF, rb = (raw.x >> 16) & 0xFF, rc = raw.x >> 24, rd = raw.y & 0xFF;
+        const uint32_t wc = Wt[rc * kPermThreads], wd = Wt[rd * kPermThreads];
+        if (kind == 0) {
+            const uint32_t m = acc & Wt[rb * kPermThreads] & wc & wd;
+            Wt[ra * kPermThreads] ^= m;
+            acc = 0xFFFFFFFFu;
+        } else if (kind == 1) {
+            const uint32_t wa = Wt[ra * kPermThreads], wb = Wt[rb * kPermThreads];
+            const uint32_t m = acc & wc & wd & (wa ^ wb);
+            Wt[ra * kPermThreads] = wa ^ m;
+            Wt[rb * kPermThreads] = wb ^ m;
+            acc = 0xFFFFFFFFu;
+        } else {
+            const uint32_t m = Wt[ra * kPermThreads] & Wt[rb * kPermThreads] & wc & wd;
+            acc = (kind == 2) ? m : (acc & m);
+        }
+    }
+    // un-slice: source index of output b, then move the amplitudes (8 loads in flight per thread)
+#pragma unroll 1
+    for (int b0 = 0; b0 < 32; b0 += 8) {
+        uint64_t src[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) src[u] = 0;
+        for (int q = 0; q < n; ++q) {
+            const uint32_t w = Wt[q * kPermThreads] >> b0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) src[u] |= (uint64_t)((w >> u) & 1u) << q;
+        }
+        A v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = in[src[u]];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) out[warp_base + (uint64_t)(b0 + u) * 32 + lane] = v[u];
+    }
+}
+
+// ===================================================================================================
+// 4. Projection onto a Subspace with all ancillae 0 (Subspace.test_basis / enumerate_basis / project,
+//    /root/reference/src/unitaria/subspace.py:297-335) fused with the norm (nodes/node.py:390-403).
+// ===================================================================================================
+
+constexpr int kMaxSubNodes = 1 << 16;  // program lives in global memory (per-thread divergent reads)
+
+// member test + rank (position in ascending-index order) of index `bits`.
+__device__ __forceinline__ bool sub_member_rank(const b2sv_subnode* __restrict__ c_sub, uint64_t bits, int root_count,
+                                                uint64_t& rank_out) {
+    struct Frame {
+        int cur, end;
+        uint64_t bits, rank, radix, add;
+    };
+    Frame st[66];
+    int sp = 0;
+    st[0] = {0, root_count, bits, 0, 1, 0};
+    uint64_t ret = 0;
+    bool returning = false;
+    while (true) {
+        Frame& f = st[sp];
+        if (returning) {
+            // child finished with rank `ret`: fold into the factor that spawned it
+            const b2sv_subnode nd = c_sub[f.cur];
+            f.rank += (ret + f.add) * f.radix;
+            f.radix *= nd.dim;
+            f.cur++;
+            returning = false;
+        }
+        if (f.cur == f.end) {
+            if (sp == 0) {
+                rank_out = f.rank;
+                return true;
+            }
+            ret = f.rank;
+            --sp;
+            returning = true;
+            continue;
+        }
+        const b2sv_subnode nd = c_sub[f.cur];
+        if (nd.kind == 0) {
+            if (f.bits & 1) return false;
+            f.bits >>= 1;
+            f.cur++;
+            continue;
+        }
+        const int nb = nd.nbits - 1;
+        const uint64_t low = f.bits & ((nb >= 64) ? ~0ull : ((1ull << nb) - 1));
+        const int top = (int)((f.bits >> nb) & 1);
+        f.bits >>= (nb + 1);
+        if (nd.child_count[top] == 0) {  // child is the zero-qubit (empty) subspace: rank 0, dim 1
+            f.rank += (top ? nd.dim0 : 0) * f.radix;
+            f.radix *= nd.dim;
+            f.cur++;
+            continue;
+        }
+        f.add = top ? nd.dim0 : 0;
+        ++sp;
+        st[sp] = {nd.child_first[top], nd.child_first[top] + nd.child_count[top], low, 0, 1, 0};
+    }
+}
+
+template <typename A>
+__global__ void __launch_bounds__(kThreads) k_project_norm2(const A* __restrict__ psi, const b2sv_subnode* __restrict__ sub,
+                                                            uint64_t count, int root_count,
+                                                            double* __restrict__ partial) {
+    double acc = 0.0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        uint64_t r;
+        if (sub_member_rank(sub, i, root_count, r)) {
+            const double2 v = to_c128(psi[i]);
+            acc = fma(v.x, v.x, fma(v.y, v.y, acc));
+        }
+    }
+    __shared__ double red[kThreads / 32];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < kThreads / 32 ? red[threadIdx.x] : 0.0;
+        for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) partial[blockIdx.x] = v;
+    }
+}
+
+// deterministic final reduction of the per-block partial sums (one block)
+__global__ void __launch_bounds__(kThreads) k_reduce_partials(const double* __restrict__ partial, int n, double* out) {
+    __shared__ double red[kThreads];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += kThreads) acc += partial[i];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = kThreads / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = red[0];
+}
+
+template <typename A>
+__global__ void __launch_bounds__(kThreads) k_project_gather(const A* __restrict__ psi, const b2sv_subnode* __restrict__ sub,
+                                                             uint64_t count, int root_count,
+                                                             double2 scale, double2* __restrict__ out, uint64_t dim) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        uint64_t r;
+        if (sub_member_rank(sub, i, root_count, r) && r < dim) out[r] = cmul(scale, to_c128(psi[i]));
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_enumerate_basis(const b2sv_subnode* __restrict__ sub, uint64_t count, int root_count,
+                                                              long long* __restrict__ out,
+                                                              uint64_t dim) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        uint64_t r;
+        if (sub_member_rank(sub, i, root_count, r) && r < dim) out[r] = (long long)i;
+    }
+}
+
+// ===================================================================================================
+// 5. State initialisation, dtype conversion, scaling, global<->local swap packing.
+// ===================================================================================================
+
+template <typename A>
+__global__ void __launch_bounds__(kThreads) k_set_basis(A* __restrict__ psi, uint64_t count, uint64_t index) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        psi[i] = from_c128<A>(make_double2(i == index ? 1.0 : 0.0, 0.0));
+}
+
+template <typename A>
+__global__ void __launch_bounds__(kThreads) k_scale(A* __restrict__ psi, uint64_t count, double2 s) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        psi[i] = from_c128<A>(cmul(s, to_c128(psi[i])));
+}
+
+// dst[i] = convert(src[i]); used for complex64 storage <-> complex128 host buffers
+template <typename D, typename S>
+__global__ void __launch_bounds__(kThreads) k_convert(D* __restrict__ dst, const S* __restrict__ src, uint64_t count) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        dst[i] = from_c128<D>(to_c128(src[i]));
+}
+
+// staging[k] = psi[i] (pack) or psi[i] = staging[k] (unpack) for the half of the shard whose bit q
+// equals `sel`; k enumerates that half in ascending index order.
+template <typename A, bool PACK>
+__global__ void __launch_bounds__(kThreads) k_swap_pack(A* __restrict__ psi, A* __restrict__ staging, uint64_t half,
+                                                        int q, uint64_t sel_bit) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < half; k += stride) {
+        const uint64_t i = insert_zero(k, q) | sel_bit;
+        if (PACK) staging[k] = psi[i];
+        else psi[i] = staging[k];
+    }
+}
+
+}  // namespace b2svk

@@ -1,0 +1,308 @@
+// planner.hpp -- host-side fusion planner of the B200 statevector engine (no CUDA in this file).
+//
+// Input: the lowered gate list handed to b2sv_apply -- one entry per tequila gate of the circuit
+// that unitaria's Circuit.simulate would have passed to tq.simulate
+// (/root/reference/src/unitaria/circuit.py:62-70).  The reference's simulator (qulacs) makes one
+// memory sweep per gate; the planner's job is to make as few sweeps as possible:
+//
+//   * exact no-ops are dropped (I pads, zero angles, X.X pairs from
+//     nodes/basic/modify_control.py:70-78), uncontrolled global phases fold into one scalar;
+//   * long runs of X / multi-controlled X / (controlled) SWAP gates -- the ripple-carry arithmetic
+//     of circuits/arithmetic.py -- become ONE out-of-place index-map sweep (SEG_PERM);
+//   * everything else is packed greedily, with a commutation-aware look-ahead, into shared-memory
+//     tile sweeps (SEG_TILE): a sweep owns a set T of `tile_qubits` qubits (always containing the
+//     low `chunk_bits` qubits so every global access is a long contiguous run); a gate can ride in
+//     the sweep when its non-diagonal targets are in T.  Controls are free (tile predicates) and
+//     diagonal gates ride anywhere;
+//   * a sweep that would touch only a small fraction of the state (few, heavily controlled gates)
+//     is issued as stand-alone gate kernels instead (SEG_GATE1Q) which only visit the 2^(n-c)
+//     controlled amplitudes.
+//
+// The plan never reorders two gates unless they commute by the rule "on every shared qubit both
+// gates act diagonally (as a control or as a diagonal target)".
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../include/b2sv.h"
+
+namespace b2svk {
+
+enum SegClass { SEG_GATE1Q = 0, SEG_TILE = 1, SEG_PERM = 2 };
+
+struct PGate {
+    uint8_t op;
+    uint8_t t0, t1;
+    uint64_t ctrl;
+    uint64_t tmask;   // targets that must be tile-resident (non-diagonal action)
+    uint64_t qmask;   // every qubit the gate touches
+    double m[8];
+    int src;          // index in the caller's list
+    bool is_perm() const { return op == B2SV_OP_X || op == B2SV_OP_SWAP; }
+};
+
+struct Segment {
+    int cls;
+    uint64_t tile_mask;  // SEG_TILE only
+    std::vector<int> gates;  // indices into Plan::gates, execution order
+};
+
+struct PlanConfig {
+    int n = 1;
+    int amp_bytes = 16;
+    bool fuse = true;
+    bool perm_runs = true;
+    int tile_qubits = 12;
+    int chunk_bits = 7;
+    int lookahead = 96;
+    int perm_min = 12;          // shortest run worth an out-of-place sweep
+    double perm_gate_cost = 1.0 / 300.0;  // cost of one perm gate in units of one full sweep
+    bool always_tile_below = true;        // small states: prefer the fewest launches
+};
+
+struct Plan {
+    std::vector<PGate> gates;
+    std::vector<Segment> segs;
+    double scalar_re = 1.0, scalar_im = 0.0;  // folded uncontrolled global phases
+    uint64_t gates_in = 0, gates_live = 0;
+};
+
+inline int popcount64(uint64_t x) { return __builtin_popcountll(x); }
+inline uint64_t low_mask(int b) { return b >= 64 ? ~0ull : ((1ull << b) - 1); }
+
+inline PlanConfig default_config(int n, int dtype, const b2sv_plan_opts* o) {
+    PlanConfig c;
+    c.n = n;
+    c.amp_bytes = dtype == B2SV_C64 ? 8 : 16;
+    c.tile_qubits = dtype == B2SV_C64 ? 13 : 12;  // 64 KiB of shared memory either way
+    c.chunk_bits = dtype == B2SV_C64 ? 8 : 7;     // 2 KiB contiguous per bulk copy
+    if (o) {
+        c.fuse = o->fuse != 0;
+        c.perm_runs = o->perm_runs != 0;
+        if (o->tile_qubits > 0) c.tile_qubits = o->tile_qubits;
+        if (o->lookahead > 0) c.lookahead = o->lookahead;
+    }
+    if (c.tile_qubits > 13 && c.amp_bytes == 16) c.tile_qubits = 13;
+    if (c.tile_qubits > 14) c.tile_qubits = 14;
+    if (c.tile_qubits < 3) c.tile_qubits = 3;
+    if (c.tile_qubits > n) c.tile_qubits = n;
+    if (c.chunk_bits > c.tile_qubits - 2) c.chunk_bits = std::max(0, c.tile_qubits - 2);
+    if (c.amp_bytes << c.chunk_bits < 16) c.chunk_bits = c.amp_bytes == 8 ? 1 : 0;  // bulk copies need 16 B
+    if (c.chunk_bits > c.tile_qubits) c.chunk_bits = c.tile_qubits;
+    return c;
+}
+
+// ---- normalisation ----------------------------------------------------------------------------
+
+inline bool is_one(double re, double im) { return re == 1.0 && im == 0.0; }
+inline bool is_zero(double re, double im) { return re == 0.0 && im == 0.0; }
+
+// Returns false when the gate is an exact no-op.
+inline bool normalise_gate(const b2sv_gate& g, int src, PGate& out, double& sre, double& sim) {
+    out.op = g.op;
+    out.t0 = g.t0;
+    out.t1 = g.t1;
+    out.ctrl = g.ctrl_mask;
+    out.src = src;
+    std::memcpy(out.m, g.m, sizeof(out.m));
+    if (out.op == B2SV_OP_MAT1) {
+        const double* m = out.m;
+        if (is_zero(m[2], m[3]) && is_zero(m[4], m[5])) {
+            out.op = B2SV_OP_DIAG1;  // {d0, d1} = {m00, m11}
+            out.m[2] = m[6];
+            out.m[3] = m[7];
+        } else if (is_zero(m[0], m[1]) && is_zero(m[6], m[7]) && is_one(m[2], m[3]) && is_one(m[4], m[5])) {
+            out.op = B2SV_OP_X;
+        }
+    }
+    if (out.op == B2SV_OP_DIAG1) {
+        if (is_one(out.m[0], out.m[1]) && is_one(out.m[2], out.m[3])) return false;
+        if (out.m[0] == out.m[2] && out.m[1] == out.m[3]) {  // scalar on the controlled block
+            out.op = B2SV_OP_PHASE;
+        } else if (is_one(out.m[0], out.m[1])) {  // diag(1, w): a phase on the block where the target is 1 too
+            out.op = B2SV_OP_PHASE;
+            out.ctrl |= 1ull << out.t0;
+            out.m[0] = out.m[2];
+            out.m[1] = out.m[3];
+        }
+    }
+    if (out.op == B2SV_OP_PHASE) {
+        if (is_one(out.m[0], out.m[1])) return false;
+        if (out.ctrl == 0) {  // uncontrolled global phase: fold
+            double r = sre * out.m[0] - sim * out.m[1];
+            double i = sre * out.m[1] + sim * out.m[0];
+            sre = r;
+            sim = i;
+            return false;
+        }
+        out.t0 = out.t1 = 0;
+        out.tmask = 0;
+        out.qmask = out.ctrl;
+        return true;
+    }
+    if (out.op == B2SV_OP_SWAP) {
+        if (out.t0 == out.t1) return false;
+        out.tmask = (1ull << out.t0) | (1ull << out.t1);
+    } else if (out.op == B2SV_OP_DIAG1) {
+        out.tmask = 0;
+    } else {
+        out.tmask = 1ull << out.t0;
+    }
+    out.qmask = out.ctrl | (1ull << out.t0);
+    if (out.op == B2SV_OP_SWAP) out.qmask |= 1ull << out.t1;
+    return true;
+}
+
+inline bool same_perm_gate(const PGate& a, const PGate& b) {
+    if (a.op != b.op || a.ctrl != b.ctrl) return false;
+    if (a.op == B2SV_OP_X) return a.t0 == b.t0;
+    return (a.t0 == b.t0 && a.t1 == b.t1) || (a.t0 == b.t1 && a.t1 == b.t0);
+}
+
+// ---- tile packing -----------------------------------------------------------------------------
+
+inline double gate_sweep_fraction(const PGate& g) {
+    int c = popcount64(g.ctrl);
+    if (g.op == B2SV_OP_SWAP) c += 1;
+    return std::ldexp(1.0, -c);
+}
+
+inline void plan_tiles(const std::vector<PGate>& G, const std::vector<int>& idx, const PlanConfig& cfg,
+                       std::vector<Segment>& out) {
+    const int n = cfg.n, k = cfg.tile_qubits;
+    std::vector<char> done(idx.size(), 0);
+    size_t head = 0;
+    const uint64_t base = low_mask(std::min(cfg.chunk_bits, n));
+    while (head < idx.size()) {
+        if (done[head]) {
+            ++head;
+            continue;
+        }
+        Segment seg;
+        seg.cls = SEG_TILE;
+        uint64_t T = base;
+        uint64_t blocked_any = 0, blocked_nd = 0;
+        int scanned = 0;
+        for (size_t p = head; p < idx.size() && scanned < cfg.lookahead; ++p) {
+            if (done[p]) continue;
+            ++scanned;
+            const PGate& g = G[idx[p]];
+            const bool commutes = ((g.tmask & blocked_any) == 0) && ((g.qmask & blocked_nd) == 0);
+            const bool fits = popcount64(T | g.tmask) <= k;
+            if (commutes && fits) {
+                T |= g.tmask;
+                seg.gates.push_back(idx[p]);
+                done[p] = 1;
+            } else {
+                blocked_any |= g.qmask;
+                blocked_nd |= g.tmask;
+                if (p == head) break;  // cannot happen (k >= chunk_bits + 2), but never spin
+            }
+        }
+        if (seg.gates.empty()) {  // defensive: issue the head gate alone
+            seg.gates.push_back(idx[head]);
+            done[head] = 1;
+            T |= G[idx[head]].tmask;
+        }
+        for (int q = 0; q < n && popcount64(T) < k; ++q) T |= 1ull << q;  // pad with the lowest qubits
+        seg.tile_mask = T;
+        // A sweep that touches little of the state is cheaper as stand-alone controlled kernels.
+        double frac = 0;
+        for (int gi : seg.gates) frac += gate_sweep_fraction(G[gi]);
+        const bool small_state = cfg.always_tile_below && n <= 16;
+        if (!small_state && frac <= 0.55 && seg.gates.size() <= 8) {
+            for (int gi : seg.gates) {
+                Segment one;
+                one.cls = SEG_GATE1Q;
+                one.tile_mask = 0;
+                one.gates.push_back(gi);
+                out.push_back(std::move(one));
+            }
+        } else {
+            out.push_back(std::move(seg));
+        }
+    }
+}
+
+// ---- whole plan -------------------------------------------------------------------------------
+
+inline Plan make_plan(const b2sv_gate* gates, size_t n_gates, const PlanConfig& cfg, bool scratch_available) {
+    Plan plan;
+    plan.gates_in = n_gates;
+    plan.gates.reserve(n_gates);
+    for (size_t j = 0; j < n_gates; ++j) {
+        PGate g;
+        if (!normalise_gate(gates[j], (int)j, g, plan.scalar_re, plan.scalar_im)) continue;
+        // adjacent self-inverse pairs cancel (X.X, SWAP.SWAP with identical controls)
+        if (g.is_perm() && !plan.gates.empty() && same_perm_gate(plan.gates.back(), g)) {
+            plan.gates.pop_back();
+            continue;
+        }
+        plan.gates.push_back(g);
+    }
+    plan.gates_live = plan.gates.size();
+    const std::vector<PGate>& G = plan.gates;
+    if (!cfg.fuse) {
+        for (size_t j = 0; j < G.size(); ++j) {
+            Segment s;
+            s.cls = SEG_GATE1Q;
+            s.tile_mask = 0;
+            s.gates.push_back((int)j);
+            plan.segs.push_back(std::move(s));
+        }
+        return plan;
+    }
+    // split into stretches at long permutation runs
+    std::vector<int> stretch;
+    auto flush_stretch = [&]() {
+        if (!stretch.empty()) {
+            plan_tiles(G, stretch, cfg, plan.segs);
+            stretch.clear();
+        }
+    };
+    size_t j = 0;
+    while (j < G.size()) {
+        if (G[j].is_perm() && cfg.perm_runs && scratch_available) {
+            size_t e = j;
+            while (e < G.size() && G[e].is_perm()) ++e;
+            const size_t len = e - j;
+            bool use_perm = false;
+            if ((int)len >= cfg.perm_min) {
+                std::vector<int> run(len);
+                for (size_t q = 0; q < len; ++q) run[q] = (int)(j + q);
+                std::vector<Segment> alt;
+                plan_tiles(G, run, cfg, alt);
+                double tile_cost = 0;
+                for (const Segment& s : alt) {
+                    if (s.cls == SEG_TILE) tile_cost += 1.0;
+                    else tile_cost += gate_sweep_fraction(G[s.gates[0]]);
+                }
+                const double perm_cost = 1.0 + cfg.perm_gate_cost * (double)len;
+                use_perm = perm_cost < tile_cost;
+                if (cfg.n <= 16) use_perm = alt.size() > 1;  // launch-bound regime: fewest launches
+            }
+            if (use_perm) {
+                flush_stretch();
+                Segment s;
+                s.cls = SEG_PERM;
+                s.tile_mask = 0;
+                for (size_t q = j; q < e; ++q) s.gates.push_back((int)q);
+                plan.segs.push_back(std::move(s));
+            } else {
+                for (size_t q = j; q < e; ++q) stretch.push_back((int)q);
+            }
+            j = e;
+        } else {
+            stretch.push_back((int)j);
+            ++j;
+        }
+    }
+    flush_stretch();
+    return plan;
+}
+
+}  // namespace b2svk
