@@ -131,6 +131,10 @@ int b2sv_enumerate_basis(b2sv_t* sv, const b2sv_subnode* prog, int n_nodes, int 
 /* ---- device-resident hand-off and the pieces the distributed layer drives ----------------------- */
 int b2sv_device_ptr(b2sv_t* sv, void** amps, uint64_t* bytes);
 int b2sv_sync(b2sv_t* sv);
+/* CUDA-event stopwatch on the handle's stream (slots 0..7): b2sv_mark records an event after all work
+ * enqueued so far; b2sv_elapsed_ms synchronises and returns the device time between two marks. */
+int b2sv_mark(b2sv_t* sv, int slot);
+int b2sv_elapsed_ms(b2sv_t* sv, int slot_a, int slot_b, double* ms);
 /* Exchange support for global<->local qubit swaps (unitaria_b200/distributed.py): pack the half of
  * the shard whose local qubit `q` differs from `keep_bit` into `staging` (contiguous), and the
  * inverse. */

@@ -98,3 +98,18 @@ def random_circuit(n, m, rng, kinds=None, max_controls=3):
 def random_state(n, rng):
     psi = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
     return psi / np.linalg.norm(psi)
+
+
+def dagger_gates(gates):
+    """Inverse circuit of a list of GateRecords (what ``QCircuit.dagger()`` does gate by gate)."""
+    from unitaria_b200.fixtures import GateRecord
+
+    out = []
+    for g in reversed(list(gates)):
+        name = g.name.upper()
+        if name in ("RX", "RY", "RZ", "PHASE", "GLOBALPHASE"):
+            out.append(GateRecord(g.name, g.target, g.control, -g.parameter, 1.0))
+        else:
+            p = g.power if g.power == 1 else -g.power
+            out.append(GateRecord(g.name, g.target, g.control, p, p))
+    return out

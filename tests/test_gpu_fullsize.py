@@ -1,0 +1,102 @@
+"""BASELINE.json configs at FULL size on one B200, checked through size-independent properties
+(no oracle array of 2^29 amplitudes is ever built on the host)."""
+
+import numpy as np
+import pytest
+
+from tests.helpers import dagger_gates, load_golden
+from unitaria_b200 import PlanOpts, StateVector, SubspaceProgram, cabi, lower_gates
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _require_gpu():
+    if cabi.device_count() == 0:
+        pytest.fail("tests marked gpu need a CUDA device; the engine has no CPU fallback")
+
+
+def test_cfg2_laplace_n26_columns_are_the_periodic_laplacian():
+    """Config 2: 1-D Laplace block encoding, bits=26 (29 qubits, complex128, 8 GiB).
+    A = -2 I + C + C^T with C the cyclic increment, so column j is -2 e_j + e_{j+1} + e_{j-1}."""
+    case = load_golden("cfg2_laplace_n26")
+    n, norm = case.n_qubits, case.meta["normalization"]
+    assert n == 29 and len(case.gates) == 1450
+    prog = SubspaceProgram(case.meta["subspace_out"])
+    dim = prog.dimension
+    assert dim == 2**26
+    low = lower_gates(case.gates, n)
+    with StateVector(n, "complex128") as sv:
+        for j in (0, 1, 12345678, dim - 1):
+            sv.set_basis(j)  # subspace_in is "00" + 26 free qubits: basis index j is the j-th input
+            sv.apply_lowered(low)
+            assert abs(norm * np.sqrt(sv.project_norm2(prog)) - np.sqrt(6.0)) < 1e-11
+            col = sv.project(prog, scale=norm)
+            want = {j: -2.0, (j + 1) % dim: 1.0, (j - 1) % dim: 1.0}
+            nz = np.flatnonzero(np.abs(col) > 1e-12)
+            assert sorted(nz) == sorted(want)
+            for i, v in want.items():
+                assert abs(col[i] - v) < 1e-12
+        st = sv.stats()
+        assert st["launches_by_class"]["perm"] >= 4 and st["launches_by_class"]["tile"] >= 4
+
+
+def test_cfg2_tiles_only_equals_perm_path_on_dense_input():
+    """Same circuit family at 23 qubits with a dense random state: both execution plans agree to 1e-12."""
+    case = load_golden("laplace_n20")
+    n = case.n_qubits
+    rng = np.random.default_rng(0)
+    psi = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    psi /= np.linalg.norm(psi)
+    low = lower_gates(case.gates, n)
+    with StateVector(n) as sv:
+        sv.upload(psi)
+        sv.apply_lowered(low)
+        a = sv.download()
+        sv.upload(psi)
+        sv.apply_lowered(low, PlanOpts.make(perm_runs=False))
+        b = sv.download()
+    assert np.abs(a - b).max() < 1e-13
+    assert abs(np.linalg.norm(a) - 1.0) < 1e-12
+
+
+def test_cfg3_gaussian_28q_complex64_matches_convolution():
+    """Config 3: Gaussian convolution block encoding at 28 qubits, complex64 storage.
+    The encoded matrix is a convolution with the kernel (tests/test_gaussian_conv.py:18-22)."""
+    case = load_golden("cfg3_gaussian_s3_t21")
+    n, norm = case.n_qubits, case.meta["normalization"]
+    assert n == 28
+    prog_in = SubspaceProgram(case.meta["subspace_in"])
+    prog_out = SubspaceProgram(case.meta["subspace_out"])
+    dim = prog_out.dimension
+    assert dim == 2**20
+    kernel = np.exp(-((np.arange(-3, 4) / 4) ** 2))
+    x = np.linspace(0.0, 1.0, dim)
+    x /= np.linalg.norm(x)
+    low = lower_gates(case.gates, n)
+    with StateVector(n, "complex64") as sv:
+        basis_in = sv.enumerate_basis(prog_in)
+        psi = np.zeros(2**n, dtype=np.complex128)
+        psi[basis_in] = x
+        sv.upload(psi)
+        del psi
+        sv.apply_lowered(low)
+        got = sv.project(prog_out, scale=norm)
+    want = np.convolve(x, kernel, mode="same")
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max() * 4
+
+
+def test_cfg4_bpx_L8_norm_and_dagger_roundtrip():
+    """Config 4 (BPX preconditioned 2-D Laplacian, L=8, 29 qubits): unitarity + inverse round trip."""
+    case = load_golden("cfg4_bpx_L8")
+    n = case.n_qubits
+    low = lower_gates(case.gates, n)
+    inv_low = lower_gates(dagger_gates(case.gates), n)
+    with StateVector(n) as sv:
+        sv.set_basis(0)
+        sv.apply_lowered(low)
+        full = SubspaceProgram("#" * n)
+        assert abs(sv.project_norm2(full) - 1.0) < 1e-11
+        sv.apply_lowered(inv_low)
+        out = sv.project(SubspaceProgram("0" * (n - 4) + "####"))
+        assert abs(out[0] - 1.0) < 1e-11 and np.abs(out[1:]).max() < 1e-11

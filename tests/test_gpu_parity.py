@@ -1,0 +1,235 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the reference goldens.
+
+Needs a B200 (``-m gpu``).  Tolerances are the north-star's: 1e-12 relative for complex128 storage,
+1e-5 for complex64; permutation circuits and basis-state indexing bit-exact.
+"""
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, np_oracle
+from tests.helpers import expected_column, golden_inputs, golden_names, load_golden, random_circuit, random_state
+from unitaria_b200 import PlanOpts, StateVector, SubspaceProgram, cabi, lower_gates
+from unitaria_b200 import adapter
+
+pytestmark = pytest.mark.gpu
+
+# execution variants: every one must give the same answer
+VARIANTS = {
+    "fused": dict(),
+    "unfused": dict(fuse=False),
+    "tiles_only": dict(perm_runs=False),
+    "tiles_plain_io": dict(perm_runs=False, plain_tile_io=True),
+    "small_tiles": dict(tile_qubits=5, lookahead=4),
+}
+
+
+def tol(dtype, n_gates):
+    base = 1e-12 if dtype == "complex128" else 1e-5
+    return base * max(1.0, n_gates / 200.0)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _require_gpu():
+    if cabi.device_count() == 0:
+        pytest.fail("tests marked gpu need a CUDA device; the engine has no CPU fallback")
+    yield
+    adapter.clear_caches()
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+@pytest.mark.parametrize("name", golden_names(with_expected=True, max_qubits=16))
+def test_goldens_complex128(name, variant):
+    """normalization * project(simulate(b)) == reference toarray()[:, col]  (verifier.py:115-126)."""
+    case = load_golden(name)
+    if variant != "fused" and len(case.gates) > 5000:
+        pytest.skip("long circuit: fused variant only")
+    n, norm = case.n_qubits, case.meta["normalization"]
+    prog = SubspaceProgram(case.meta["subspace_out"])
+    low = lower_gates(case.gates, n)
+    opts = PlanOpts.make(**VARIANTS[variant])
+    with StateVector(n, "complex128") as sv:
+        for col, b in golden_inputs(case, limit=4 if len(case.gates) > 5000 else 12):
+            sv.set_basis(b)
+            sv.apply_lowered(low, opts)
+            got = sv.project(prog, scale=norm)
+            want = expected_column(case, col)
+            scale = max(1.0, float(np.abs(want).max()))
+            assert np.abs(got - want).max() <= tol("complex128", len(case.gates)) * scale, (name, variant, col)
+            n2 = sv.project_norm2(prog)
+            assert abs(abs(norm) * np.sqrt(n2) - np.linalg.norm(want)) <= 1e-11 * max(1.0, np.linalg.norm(want))
+
+
+@pytest.mark.parametrize("name", golden_names(with_expected=True, max_qubits=16))
+def test_goldens_complex64(name):
+    case = load_golden(name)
+    n, norm = case.n_qubits, case.meta["normalization"]
+    prog = SubspaceProgram(case.meta["subspace_out"])
+    low = lower_gates(case.gates, n)
+    with StateVector(n, "complex64") as sv:
+        for col, b in golden_inputs(case, limit=4):
+            sv.set_basis(b)
+            sv.apply_lowered(low)
+            got = sv.project(prog, scale=norm)
+            want = expected_column(case, col)
+            scale = max(1.0, float(np.abs(want).max()))
+            assert np.abs(got - want).max() <= tol("complex64", len(case.gates)) * scale, (name, col)
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 6, 9, 12, 13, 15])
+def test_random_circuits_full_state(n, variant):
+    rng = np.random.default_rng(1000 + n)
+    circuit = random_circuit(n, 300, rng, max_controls=min(4, max(0, n - 2)))
+    psi0 = random_state(n, rng)
+    want = c_oracle.simulate_gates(circuit.gates, n, psi0)
+    with StateVector(n, "complex128") as sv:
+        sv.upload(psi0)
+        sv.apply(circuit.gates, PlanOpts.make(**VARIANTS[variant]))
+        got = sv.download()
+    assert np.abs(got - want).max() <= 1e-12, (n, variant)
+    with StateVector(n, "complex64") as sv:
+        sv.upload(psi0)
+        sv.apply(circuit.gates, PlanOpts.make(**VARIANTS[variant]))
+        got = sv.download()
+    assert np.abs(got - want).max() <= 1e-5, (n, variant)
+
+
+@pytest.mark.parametrize("variant", ["fused", "tiles_only", "unfused"])
+@pytest.mark.parametrize("n", [13, 14, 17])
+def test_permutation_circuits_are_bit_exact(n, variant):
+    """X / CNOT / Toffoli / SWAP circuits move amplitudes without arithmetic (subspace.py:426-431)."""
+    rng = np.random.default_rng(n)
+    circuit = random_circuit(n, 500, rng, kinds=["X", "CNOT", "Toffoli", "SWAP"], max_controls=5)
+    psi0 = random_state(n, rng)
+    want = c_oracle.simulate_gates(circuit.gates, n, psi0)
+    for dtype, ref in (("complex128", want), ("complex64", want.astype(np.complex64).astype(np.complex128))):
+        with StateVector(n, dtype) as sv:
+            sv.upload(psi0)
+            sv.apply(circuit.gates, PlanOpts.make(**VARIANTS[variant]))
+            got = sv.download()
+        assert np.array_equal(got, ref), (n, variant, dtype)
+    with StateVector(n) as sv:
+        sv.set_basis(5)
+        sv.apply(circuit.gates, PlanOpts.make(**VARIANTS[variant]))
+        got = sv.download()
+    assert np.count_nonzero(got) == 1 and got[np.flatnonzero(got)[0]] == 1
+
+
+@pytest.mark.parametrize("name", ["laplace_n12", "laplace_n16", "laplace_n20", "gaussian_s3_t13", "bpx_L4", "bpx_L5", "cfg5_bits13"])
+def test_mid_size_configs_against_c_oracle(name):
+    """The BASELINE.json circuit families at sizes the CPU oracle finishes in seconds: full state."""
+    case = load_golden(name)
+    n = case.n_qubits
+    rng = np.random.default_rng(3)
+    psi0 = random_state(n, rng)
+    want = c_oracle.simulate_gates(case.gates, n, psi0)
+    low = lower_gates(case.gates, n)
+    with StateVector(n, "complex128") as sv:
+        sv.upload(psi0)
+        sv.apply_lowered(low)
+        got = sv.download()
+        assert np.abs(got - want).max() <= 1e-12, name
+        sv.upload(psi0)
+        sv.apply_lowered(low, PlanOpts.make(perm_runs=False))
+        got2 = sv.download()
+        assert np.abs(got2 - want).max() <= 1e-12, name
+    with StateVector(n, "complex64") as sv:
+        sv.upload(psi0)
+        sv.apply_lowered(low)
+        got = sv.download()
+        assert np.abs(got - want).max() <= 1e-5, name
+
+
+@pytest.mark.parametrize("name", ["laplace_readme_n8", "bpx_L3", "pinv_bpx_L2", "cfg5_bits13", "laplace_n16"])
+@pytest.mark.parametrize("which", ["subspace_in", "subspace_out"])
+def test_device_enumerate_basis_and_projection_order(name, which):
+    """Device predicate + rank == Subspace.enumerate_basis order (subspace.py:325-329), bit-exact."""
+    case = load_golden(name)
+    spec = case.meta[which]
+    prog = SubspaceProgram(spec)
+    if prog.total_qubits > 22:
+        pytest.skip("oracle enumeration too large")
+    want = np_oracle.enumerate_basis(spec)
+    n = case.n_qubits
+    rng = np.random.default_rng(11)
+    psi = random_state(n, rng)
+    with StateVector(n) as sv:
+        got = sv.enumerate_basis(prog)
+        assert np.array_equal(got, want)
+        sv.upload(psi)
+        assert np.array_equal(sv.project(prog, scale=2.5 - 1j), (2.5 - 1j) * psi[want])
+        assert abs(sv.project_norm2(prog) - float(np.sum(np.abs(psi[want]) ** 2))) < 1e-13
+
+
+def test_adapter_simulate_circuit_contract():
+    """Circuit.simulate's contract (circuit.py:42-70) incl. quirks Q1-Q3, Q7 of SURVEY.md App. D."""
+    import tequila as tq
+
+    c = tq.gates.Ry(1.854590436003224, 0)  # README.md:20-24: encodes (3,4)/5
+    out = adapter.simulate_circuit(c, 1, 0, backend="qulacs")
+    assert out.dtype == np.complex128 and out.shape == (2,)
+    assert np.allclose(out, [0.6, 0.8], atol=1e-15)
+    # np.integer input, dense input, register wider than the used qubits
+    c2 = tq.gates.X(0) + tq.gates.CNOT(0, 2)
+    assert adapter.simulate_circuit(c2, 4, np.int64(0))[5] == 1
+    vec = np.zeros(16, dtype=complex)
+    vec[2] = 1j
+    assert adapter.simulate_circuit(c2, 4, vec)[2 | 1 | 4] == 1j
+    # no qubit touched: returns input / one-hot and DROPS the global phase
+    g = tq.gates.GlobalPhase(0.9)
+    assert adapter.simulate_circuit(g, 2, 1)[1] == 1
+    assert adapter.simulate_circuit(g, 2, vec[:4]) is not None
+    # controlled global phase is NOT dropped
+    cg = tq.gates.X(0) + tq.gates.GlobalPhase(0.9).add_controls([0])
+    assert abs(adapter.simulate_circuit(cg, 1, 0)[1] - np.exp(0.9j)) < 1e-15
+    # uncontrolled global phase next to real gates is applied
+    cg2 = tq.gates.GlobalPhase(0.4) + tq.gates.X(1)
+    assert abs(adapter.simulate_circuit(cg2, 2, 0)[2] - np.exp(0.4j)) < 1e-15
+
+
+def test_adapter_projected_and_norm_match_oracle():
+    case = load_golden("laplace_n3")  # BASELINE config 1
+
+    class C:
+        gates = case.gates
+
+    n, norm, spec = case.n_qubits, case.meta["normalization"], case.meta["subspace_out"]
+    for col, b in golden_inputs(case):
+        got = adapter.simulate_projected(C, n, spec, norm, b)
+        assert np.abs(got - expected_column(case, col)).max() < 1e-13
+        nrm = adapter.simulate_norm(C, n, spec, norm, b)
+        assert abs(nrm - np.linalg.norm(expected_column(case, col))) < 1e-13
+        full = adapter.simulate_circuit(C, n, b)
+        assert np.abs(full - np_oracle.simulate_gates(case.gates, n, b)).max() < 1e-14
+
+
+def test_dagger_roundtrip_restores_state():
+    """encode -> inverse round trip at a size no oracle array is stored for."""
+    import tequila as tq
+
+    n = 22
+    rng = np.random.default_rng(4)
+    circuit = random_circuit(n, 200, rng, max_controls=3)
+    both = tq.QCircuit(circuit.gates) + circuit.dagger()
+    psi0 = random_state(n, rng)
+    with StateVector(n) as sv:
+        sv.upload(psi0)
+        sv.apply(both.gates)
+        got = sv.download()
+    assert np.abs(got - psi0).max() < 1e-12
+
+
+def test_bad_arguments_are_rejected():
+    with StateVector(3) as sv:
+        with pytest.raises(cabi.B2svError):
+            sv.set_basis(8)
+        with pytest.raises(ValueError):
+            sv.upload(np.zeros(4, dtype=complex))
+        bad = np.zeros(1, dtype=cabi.GATE_DTYPE)
+        bad["op"][0] = cabi.OP_X
+        bad["t0"][0] = 5
+        with pytest.raises(cabi.B2svError):
+            sv.apply_lowered(bad)
+        with pytest.raises(cabi.B2svError):
+            sv.project_norm2("#####")  # a 5-qubit subspace on a 3-qubit register

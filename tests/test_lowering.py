@@ -1,0 +1,144 @@
+"""Host logic: gate lowering and the Subspace program (CPU only)."""
+
+import numpy as np
+import pytest
+import tequila as tq
+
+from oracle import np_oracle
+from tests.helpers import golden_names, load_golden, random_circuit
+from unitaria_b200 import cabi
+from unitaria_b200.lowering import LoweringError, lower_gates, touches_any_qubit
+from unitaria_b200.subspace_prog import SubspaceProgram, to_spec
+
+
+def lowered_matrix(rec):
+    """2x2 unitary a lowered single-target gate stands for."""
+    m = rec["m"]
+    c = lambda i: complex(m[2 * i], m[2 * i + 1])  # noqa: E731
+    op = int(rec["op"])
+    if op == cabi.OP_MAT1:
+        return np.array([[c(0), c(1)], [c(2), c(3)]])
+    if op == cabi.OP_DIAG1:
+        return np.array([[c(0), 0], [0, c(1)]])
+    if op == cabi.OP_X:
+        return np.array([[0, 1], [1, 0]], dtype=complex)
+    raise AssertionError(op)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_lowered_gates_match_oracle_unitaries(seed):
+    rng = np.random.default_rng(seed)
+    circuit = random_circuit(6, 300, rng)
+    gates = [g for g in circuit.gates if g.name != "I"]
+    low = lower_gates(gates, 6)
+    assert len(low) == len(gates)
+    for g, rec in zip(gates, low):
+        mask = sum(1 << c for c in g.control)
+        assert int(rec["ctrl_mask"]) == mask
+        if g.name == "GlobalPhase":
+            assert rec["op"] == cabi.OP_PHASE
+            assert abs(complex(rec["m"][0], rec["m"][1]) - np.exp(1j * g.parameter)) < 1e-15
+        elif g.name == "SWAP":
+            assert rec["op"] == cabi.OP_SWAP and {int(rec["t0"]), int(rec["t1"])} == set(g.target)
+        else:
+            assert int(rec["t0"]) == g.target[0]
+            want = np_oracle.gate_unitary(g.name, getattr(g, "parameter", None), getattr(g, "power", 1))
+            assert np.abs(lowered_matrix(rec) - want).max() < 1e-15, g
+
+
+def test_x_is_lowered_to_exact_data_movement_and_noops_are_exact():
+    c = tq.gates.X(0) + tq.gates.CNOT(1, 0) + tq.gates.Toffoli(0, 1, 2) + tq.gates.I(3)
+    low = lower_gates(c.gates, 4)
+    assert list(low["op"]) == [cabi.OP_X] * 3
+    zero = tq.gates.Ry(0.0, 1) + tq.gates.Rz(0.0, 1) + tq.gates.Phase(1, angle=0.0) + tq.gates.GlobalPhase(0.0) + tq.gates.Z(0, power=2)
+    for rec in lower_gates(zero.gates, 2):
+        m = rec["m"]
+        if rec["op"] == cabi.OP_MAT1:
+            assert list(m) == [1, 0, 0, 0, 0, 0, 1, 0]
+        elif rec["op"] == cabi.OP_DIAG1:
+            assert list(m[:4]) == [1, 0, 1, 0]
+        else:
+            assert list(m[:2]) == [1, 0]
+    z = lower_gates(tq.gates.Z(0).gates, 1)[0]
+    assert list(z["m"][:4]) == [1, 0, -1, 0]
+
+
+def test_lowering_rejects_bad_gates():
+    class G:
+        name, target, control, parameter, power = "CCZZ", (0,), (), 0.0, 1
+
+    with pytest.raises(LoweringError):
+        lower_gates([G()], 2)
+    with pytest.raises(LoweringError):
+        lower_gates(tq.gates.X(5).gates, 3)
+
+
+def test_touches_any_qubit():
+    assert not touches_any_qubit(tq.gates.GlobalPhase(0.3).gates)
+    assert touches_any_qubit(tq.gates.GlobalPhase(0.3).add_controls([1]).gates)
+    assert touches_any_qubit(tq.gates.I(0).gates)
+
+
+def test_golden_fixture_roundtrip_through_lowering():
+    for name in golden_names(max_qubits=20)[:12]:
+        case = load_golden(name)
+        low = lower_gates(case.gates, case.n_qubits)
+        assert len(low) == sum(1 for g in case.gates if g.name != "I")
+
+
+# -- Subspace program: a Python mirror of the device walk (kernels.cuh sub_member_rank) ------------
+
+
+def walk(prog: SubspaceProgram, bits: int):
+    nodes = prog.nodes
+
+    def sub(first, count, bits):
+        rank, radix = 0, 1
+        for i in range(first, first + count):
+            nd = nodes[i]
+            if nd["kind"] == 0:
+                if bits & 1:
+                    return None
+                bits >>= 1
+                continue
+            nb = int(nd["nbits"]) - 1
+            low, top = bits & ((1 << nb) - 1), (bits >> nb) & 1
+            bits >>= nb + 1
+            if nd["child_count"][top] == 0:
+                r = 0
+            else:
+                r = sub(int(nd["child_first"][top]), int(nd["child_count"][top]), low)
+                if r is None:
+                    return None
+            if top:
+                r += int(nd["dim0"])
+            rank += r * radix
+            radix *= int(nd["dim"])
+        return rank
+
+    return sub(0, prog.root_count, bits)
+
+
+@pytest.mark.parametrize("name", ["laplace_n3", "laplace_readme_n8", "bpx_L3", "bpx_L2", "pinv_bpx_L2", "gaussian_s3_t4", "cfg5_bits5"])
+@pytest.mark.parametrize("which", ["subspace_in", "subspace_out"])
+def test_subspace_program_reproduces_enumerate_basis_order(name, which):
+    case = load_golden(name)
+    spec = case.meta[which]
+    prog = SubspaceProgram(spec)
+    want = np_oracle.enumerate_basis(spec)
+    assert prog.dimension == len(want) and prog.total_qubits == np_oracle.spec_total_qubits(spec)
+    got = {}
+    for i in range(2**prog.total_qubits):
+        r = walk(prog, i)
+        if r is not None:
+            got[r] = i
+    assert sorted(got) == list(range(len(want)))
+    assert [got[r] for r in range(len(want))] == list(want)
+
+
+def test_subspace_string_form():
+    # subspace.py:114-125: leftmost character is the most significant qubit
+    assert to_spec("0#") == [[[], []], 0]
+    p = SubspaceProgram("00###")
+    assert p.total_qubits == 5 and p.dimension == 8
+    assert [walk(p, i) for i in range(9)] == [0, 1, 2, 3, 4, 5, 6, 7, None]

@@ -114,6 +114,8 @@ SYMBOLS = {
     "b2sv_enumerate_basis": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, ctypes.c_uint64]),
     "b2sv_device_ptr": (ctypes.c_int, [_P, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_uint64)]),
     "b2sv_sync": (ctypes.c_int, [_P]),
+    "b2sv_mark": (ctypes.c_int, [_P, ctypes.c_int]),
+    "b2sv_elapsed_ms": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
     "b2sv_swap_pack": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P]),
     "b2sv_swap_unpack": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P]),
     "b2sv_plan_describe": (

@@ -73,6 +73,7 @@ struct b2sv {
     std::vector<TimedLaunch> timed;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> apply_events;
     std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t marks[8] = {};
 };
 
 namespace {
@@ -543,6 +544,8 @@ int b2sv_destroy(b2sv_t* sv) {
         cudaEventDestroy(p.second);
     }
     for (auto e : sv->event_pool) cudaEventDestroy(e);
+    for (auto e : sv->marks)
+        if (e) cudaEventDestroy(e);
     cudaFree(sv->amps);
     cudaFree(sv->scratch);
     cudaFree(sv->d_ops);
@@ -807,6 +810,28 @@ int b2sv_sync(b2sv_t* sv) {
     if (int rc = check(sv)) return rc;
     CU(cudaSetDevice(sv->device));
     CU(cudaStreamSynchronize(sv->stream));
+    return B2SV_OK;
+}
+
+int b2sv_mark(b2sv_t* sv, int slot) {
+    if (int rc = check(sv)) return rc;
+    if (slot < 0 || slot >= 8) return fail(B2SV_EINVAL, "mark slot %d outside [0,8)", slot);
+    CU(cudaSetDevice(sv->device));
+    if (!sv->marks[slot]) CU(cudaEventCreate(&sv->marks[slot]));
+    CU(cudaEventRecord(sv->marks[slot], sv->stream));
+    return B2SV_OK;
+}
+
+int b2sv_elapsed_ms(b2sv_t* sv, int slot_a, int slot_b, double* ms) {
+    if (int rc = check(sv)) return rc;
+    if (!ms) return fail(B2SV_EINVAL, "ms is null");
+    if (slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8 || !sv->marks[slot_a] || !sv->marks[slot_b])
+        return fail(B2SV_ESTATE, "marks %d/%d were not recorded", slot_a, slot_b);
+    CU(cudaSetDevice(sv->device));
+    CU(cudaEventSynchronize(sv->marks[slot_b]));
+    float f = 0;
+    CU(cudaEventElapsedTime(&f, sv->marks[slot_a], sv->marks[slot_b]));
+    *ms = f;
     return B2SV_OK;
 }
 

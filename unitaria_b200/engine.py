@@ -154,6 +154,15 @@ class StateVector:
     def sync(self) -> None:
         cabi.check(self._lib.b2sv_sync(self._h))
 
+    def mark(self, slot: int) -> None:
+        """Record a CUDA event on the engine's stream (stopwatch slot 0..7)."""
+        cabi.check(self._lib.b2sv_mark(self._h, int(slot)))
+
+    def elapsed_ms(self, slot_a: int, slot_b: int) -> float:
+        ms = ctypes.c_double(0.0)
+        cabi.check(self._lib.b2sv_elapsed_ms(self._h, int(slot_a), int(slot_b), ctypes.byref(ms)))
+        return float(ms.value)
+
     def stats(self) -> dict:
         st = Stats()
         cabi.check(self._lib.b2sv_stats(self._h, ctypes.byref(st)))
