@@ -72,29 +72,38 @@ typedef struct b2sv_plan_opts {
     int32_t perm_runs;    /* 1: runs of X/SWAP gates become one index-map sweep (default); 0: off    */
     int32_t timing;       /* 1: bracket every launch with CUDA events and accumulate per-class times */
     int32_t lookahead;    /* commutation-aware lookahead window in gates; 0 = default                 */
-    int32_t reserved[3];
+    int32_t tile_io;      /* 0: bulk-async (TMA engine) tile copies (default); 1: plain ld/st (debug aid)   */
+    int32_t jit;          /* permutation runs: 0 = specialise with NVRTC in the background after first use
+                             (default), 1 = never (generic kernel only), 2 = compile synchronously       */
+    int32_t reserved;
 } b2sv_plan_opts;
 
-/* Flattened Subspace program (restates Subspace.test_basis, subspace.py:297-323).
- * A subspace is a run of `count` consecutive factor nodes starting at `first`, least-significant
- * factor first.  kind 0 = ZeroQubitSubspace (1 qubit, must be 0).  kind 1 = ControlledSubspace:
- * its top qubit selects child 0 (case_zero) or child 1 (case_one) for its lower nbits-1 qubits.
- * Node 0..root_count-1 of the array passed to b2sv_project_* form the root subspace. */
-typedef struct b2sv_subnode {
-    int32_t kind;
-    int32_t nbits;            /* qubits this factor spans */
-    uint64_t dim;             /* dimension of this factor */
-    uint64_t dim0;            /* dimension of case_zero (kind 1) */
-    int32_t child_first[2];   /* first factor node of case_zero / case_one */
-    int32_t child_count[2];   /* number of factor nodes of case_zero / case_one */
-} b2sv_subnode;
+/* Subspace program (restates Subspace.test_basis / enumerate_basis,
+ * subspace.py:297-329).  unitaria's Subspace is a tree of tensor factors; because it is a tree, the
+ * absolute bit position and the mixed-radix rank weight of every factor are static, so the host
+ * (unitaria_b200/subspace_prog.py) compiles it into a stack-free decision program:
+ *   B2SV_SUB_END     accept; the accumulated rank is the index's position in enumerate_basis order
+ *   B2SV_SUB_ZEROS   reject unless bits [pos, pos+len) are all 0              (ZeroQubitSubspace run)
+ *   B2SV_SUB_FREE    rank += field(pos, len) * weight                          (run of free qubits)
+ *   B2SV_SUB_BRANCH  bit `pos` (the top qubit of a ControlledSubspace) picks next1 (and rank += add)
+ *                    or next0
+ * Evaluation starts at instruction `entry`; ZEROS/FREE continue at next0. */
+enum { B2SV_SUB_END = 0, B2SV_SUB_ZEROS = 1, B2SV_SUB_FREE = 2, B2SV_SUB_BRANCH = 3 };
+
+typedef struct b2sv_subinstr {
+    uint8_t op, pos, len, pad;
+    uint16_t next0, next1;
+    uint64_t weight;
+    uint64_t add;
+    uint64_t reserved;
+} b2sv_subinstr;
 
 /* Counters filled by b2sv_stats (accumulated since creation or the last b2sv_stats_reset). */
 typedef struct b2sv_stats_t {
     uint64_t gates_in;        /* lowered gates handed to b2sv_apply                                   */
     uint64_t gates_live;      /* ... of which not exact no-ops                                        */
     uint64_t launches;        /* kernel launches made by b2sv_apply                                   */
-    uint64_t launches_by_class[8]; /* 0 gate1q, 1 tile sweep, 2 perm run, 3 scale, 4 project, 5 init/convert, 6 swap pack */
+    uint64_t launches_by_class[8]; /* 0 gate1q, 1 tile sweep, 2 perm run, 3 scale, 4 project, 5 init/convert, 6 swap pack, 7 perm run (NVRTC-specialised) */
     double alg_bytes_by_class[8];  /* algorithmic bytes (2*B*M per sweep)                */
     double ms_by_class[8];         /* CUDA-event time per class (only with opts.timing)                */
     double apply_ms;               /* CUDA-event time of whole b2sv_apply calls (always measured)      */
@@ -118,19 +127,23 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
 /* ---- fused post-processing (node.py:379 project*normalization, node.py:402 norm) --------------- */
 /* sum of |psi_i|^2 over i in the subspace on the low `target_qubits` qubits with every higher
  * (ancilla) qubit 0. */
-int b2sv_project_norm2(b2sv_t* sv, const b2sv_subnode* prog, int n_nodes, int root_count, int target_qubits,
+int b2sv_project_norm2(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
                        double* out);
 /* host_out[rank(i)] = (scale_re + i*scale_im) * psi_i for the members i, in ascending-index order
  * (= Subspace.enumerate_basis order, subspace.py:325-329); `dim` must equal the subspace dimension. */
-int b2sv_project_gather(b2sv_t* sv, const b2sv_subnode* prog, int n_nodes, int root_count, int target_qubits,
+int b2sv_project_gather(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
                         double scale_re, double scale_im, void* host_out_c128, uint64_t dim);
 /* Same predicate on the host-visible side of enumerate_basis: writes the member indices (int64). */
-int b2sv_enumerate_basis(b2sv_t* sv, const b2sv_subnode* prog, int n_nodes, int root_count, int target_qubits,
+int b2sv_enumerate_basis(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
                          int64_t* host_out, uint64_t dim);
 
 /* ---- device-resident hand-off and the pieces the distributed layer drives ----------------------- */
 int b2sv_device_ptr(b2sv_t* sv, void** amps, uint64_t* bytes);
 int b2sv_sync(b2sv_t* sv);
+/* Page-locked host memory for results that cross PCIe (cudaHostAlloc / cudaFreeHost): D2H into such a
+ * buffer runs at link speed instead of being staged through the driver's bounce buffers. */
+int b2sv_host_alloc(size_t bytes, void** out);
+int b2sv_host_free(void* ptr);
 /* CUDA-event stopwatch on the handle's stream (slots 0..7): b2sv_mark records an event after all work
  * enqueued so far; b2sv_elapsed_ms synchronises and returns the device time between two marks. */
 int b2sv_mark(b2sv_t* sv, int slot);
@@ -147,6 +160,10 @@ int b2sv_swap_unpack(b2sv_t* sv, int q, int keep_bit, const void* staging_dev);
  * and returns the number of words needed in *n_words. */
 int b2sv_plan_describe(int n_qubits, int dtype, const b2sv_gate* gates, size_t n_gates, const b2sv_plan_opts* opts,
                        int64_t* out_words, size_t cap, size_t* n_words);
+
+/* Host-only check of the run-time specialisation: generates the CUDA source of the permutation-run
+ * kernel for `gates` (all X / SWAP), compiles it with NVRTC for sm_100a and returns the cubin size. */
+int b2sv_perm_jit_compile_check(int n_qubits, int dtype, const b2sv_gate* gates, size_t n_gates, size_t* cubin_bytes);
 
 /* ---- bookkeeping ------------------------------------------------------------------------------- */
 int b2sv_stats(b2sv_t* sv, b2sv_stats_t* out);

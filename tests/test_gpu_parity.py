@@ -21,6 +21,8 @@ VARIANTS = {
     "tiles_only": dict(perm_runs=False),
     "tiles_plain_io": dict(perm_runs=False, plain_tile_io=True),
     "small_tiles": dict(tile_qubits=5, lookahead=4),
+    "jit_sync": dict(jit="sync"),
+    "jit_off": dict(jit="off"),
 }
 
 
@@ -95,8 +97,8 @@ def test_random_circuits_full_state(n, variant):
     assert np.abs(got - want).max() <= 1e-5, (n, variant)
 
 
-@pytest.mark.parametrize("variant", ["fused", "tiles_only", "unfused"])
-@pytest.mark.parametrize("n", [13, 14, 17])
+@pytest.mark.parametrize("variant", ["fused", "tiles_only", "unfused", "jit_sync", "jit_off"])
+@pytest.mark.parametrize("n", [13, 14, 17, 21])
 def test_permutation_circuits_are_bit_exact(n, variant):
     """X / CNOT / Toffoli / SWAP circuits move amplitudes without arithmetic (subspace.py:426-431)."""
     rng = np.random.default_rng(n)
@@ -130,10 +132,11 @@ def test_mid_size_configs_against_c_oracle(name):
         sv.apply_lowered(low)
         got = sv.download()
         assert np.abs(got - want).max() <= 1e-12, name
-        sv.upload(psi0)
-        sv.apply_lowered(low, PlanOpts.make(perm_runs=False))
-        got2 = sv.download()
-        assert np.abs(got2 - want).max() <= 1e-12, name
+        for variant in ("tiles_only", "jit_sync", "jit_off"):
+            sv.upload(psi0)
+            sv.apply_lowered(low, PlanOpts.make(**VARIANTS[variant]))
+            got2 = sv.download()
+            assert np.abs(got2 - want).max() <= 1e-12, (name, variant)
     with StateVector(n, "complex64") as sv:
         sv.upload(psi0)
         sv.apply_lowered(low)

@@ -90,33 +90,28 @@ def test_golden_fixture_roundtrip_through_lowering():
 
 
 def walk(prog: SubspaceProgram, bits: int):
-    nodes = prog.nodes
-
-    def sub(first, count, bits):
-        rank, radix = 0, 1
-        for i in range(first, first + count):
-            nd = nodes[i]
-            if nd["kind"] == 0:
-                if bits & 1:
-                    return None
-                bits >>= 1
-                continue
-            nb = int(nd["nbits"]) - 1
-            low, top = bits & ((1 << nb) - 1), (bits >> nb) & 1
-            bits >>= nb + 1
-            if nd["child_count"][top] == 0:
-                r = 0
+    ins = prog.instrs
+    pc, rank = prog.entry, 0
+    for _ in range(len(ins) + 1):
+        i = ins[pc]
+        op, pos, ln = int(i["op"]), int(i["pos"]), int(i["len"])
+        field = (bits >> pos) & ((1 << ln) - 1)
+        if op == cabi.SUB_END:
+            return rank
+        if op == cabi.SUB_ZEROS:
+            if field:
+                return None
+            pc = int(i["next0"])
+        elif op == cabi.SUB_FREE:
+            rank += field * int(i["weight"])
+            pc = int(i["next0"])
+        else:
+            if (bits >> pos) & 1:
+                rank += int(i["add"])
+                pc = int(i["next1"])
             else:
-                r = sub(int(nd["child_first"][top]), int(nd["child_count"][top]), low)
-                if r is None:
-                    return None
-            if top:
-                r += int(nd["dim0"])
-            rank += r * radix
-            radix *= int(nd["dim"])
-        return rank
-
-    return sub(0, prog.root_count, bits)
+                pc = int(i["next0"])
+    raise AssertionError("program did not terminate")
 
 
 @pytest.mark.parametrize("name", ["laplace_n3", "laplace_readme_n8", "bpx_L3", "bpx_L2", "pinv_bpx_L2", "gaussian_s3_t4", "cfg5_bits5"])
@@ -141,4 +136,5 @@ def test_subspace_string_form():
     assert to_spec("0#") == [[[], []], 0]
     p = SubspaceProgram("00###")
     assert p.total_qubits == 5 and p.dimension == 8
+    assert len(p.instrs) == 3  # END, ZEROS(3,2), FREE(0,3): runs are merged
     assert [walk(p, i) for i in range(9)] == [0, 1, 2, 3, 4, 5, 6, 7, None]

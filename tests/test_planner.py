@@ -112,3 +112,25 @@ def test_noops_and_xx_pairs_are_dropped():
     planned = [gi for _c, _m, idx in segs for gi in idx]
     assert planned == [len(live) - 1]
     assert abs(scalar - np.exp(0.5j)) < 1e-15
+
+
+def test_permutation_run_specialisation_compiles_with_nvrtc():
+    """The run-time specialised kernel source for config 2's 1434-gate run compiles for sm_100a
+    (NVRTC needs no GPU)."""
+    import ctypes
+
+    case = load_golden("cfg2_laplace_n26")
+    low = lower_gates(case.gates, case.n_qubits)
+    perm = low[(low["op"] == cabi.OP_X) | (low["op"] == cabi.OP_SWAP)].copy()
+    size = ctypes.c_size_t()
+    lib = cabi.load()
+    for dtype in (cabi.B2SV_C128, cabi.B2SV_C64):
+        rc = lib.b2sv_perm_jit_compile_check(case.n_qubits, dtype, perm.ctypes.data, len(perm), ctypes.byref(size))
+        assert rc == 0, lib.b2sv_last_error()
+        assert size.value > 10000
+    # wide registers (sharded runs): 34 qubits
+    case = load_golden("cfg5_bits27")
+    low = lower_gates(case.gates, case.n_qubits)
+    perm = low[(low["op"] == cabi.OP_X) | (low["op"] == cabi.OP_SWAP)].copy()
+    rc = lib.b2sv_perm_jit_compile_check(case.n_qubits, cabi.B2SV_C128, perm.ctypes.data, len(perm), ctypes.byref(size))
+    assert rc == 0, lib.b2sv_last_error()

@@ -45,6 +45,9 @@ def clear_caches() -> None:
     for sv in _STATES.values():
         sv.close()
     _STATES.clear()
+    from .engine import PINNED
+
+    PINNED.clear()
 
 
 def _state(n_qubits: int) -> StateVector:

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libunitaria_b200.so")
 B2SV_C128, B2SV_C64 = 0, 1
 OP_MAT1, OP_DIAG1, OP_X, OP_SWAP, OP_PHASE = 0, 1, 2, 3, 4
 SEG_GATE1Q, SEG_TILE, SEG_PERM = 0, 1, 2
-CLASS_NAMES = ("gate1q", "tile", "perm", "scale", "project", "init", "swap", "unused")
+CLASS_NAMES = ("gate1q", "tile", "perm", "scale", "project", "init", "swap", "perm_jit")
 
 # struct b2sv_gate (80 bytes)
 GATE_DTYPE = np.dtype(
@@ -31,13 +31,14 @@ GATE_DTYPE = np.dtype(
     }
 )
 
-# struct b2sv_subnode (40 bytes)
-SUBNODE_DTYPE = np.dtype(
+# struct b2sv_subinstr (32 bytes)
+SUB_END, SUB_ZEROS, SUB_FREE, SUB_BRANCH = 0, 1, 2, 3
+SUBINSTR_DTYPE = np.dtype(
     {
-        "names": ["kind", "nbits", "dim", "dim0", "child_first", "child_count"],
-        "formats": [np.int32, np.int32, np.uint64, np.uint64, (np.int32, 2), (np.int32, 2)],
-        "offsets": [0, 4, 8, 16, 24, 32],
-        "itemsize": 40,
+        "names": ["op", "pos", "len", "pad", "next0", "next1", "weight", "add", "reserved"],
+        "formats": [np.uint8, np.uint8, np.uint8, np.uint8, np.uint16, np.uint16, np.uint64, np.uint64, np.uint64],
+        "offsets": [0, 1, 2, 3, 4, 6, 8, 16, 24],
+        "itemsize": 32,
     }
 )
 
@@ -49,18 +50,21 @@ class PlanOpts(ctypes.Structure):
         ("perm_runs", ctypes.c_int32),
         ("timing", ctypes.c_int32),
         ("lookahead", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 3),
+        ("tile_io", ctypes.c_int32),
+        ("jit", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
     @classmethod
-    def make(cls, fuse=True, tile_qubits=0, perm_runs=True, timing=False, lookahead=0, plain_tile_io=False):
+    def make(cls, fuse=True, tile_qubits=0, perm_runs=True, timing=False, lookahead=0, plain_tile_io=False, jit="auto"):
         o = cls()
         o.fuse = int(bool(fuse))
         o.tile_qubits = int(tile_qubits)
         o.perm_runs = int(bool(perm_runs))
         o.timing = int(bool(timing))
         o.lookahead = int(lookahead)
-        o.reserved[0] = 1 if plain_tile_io else 0
+        o.tile_io = 1 if plain_tile_io else 0
+        o.jit = {"auto": 0, "off": 1, "sync": 2}[jit]
         return o
 
 
@@ -80,9 +84,9 @@ class Stats(ctypes.Structure):
             "gates_in": int(self.gates_in),
             "gates_live": int(self.gates_live),
             "launches": int(self.launches),
-            "launches_by_class": {CLASS_NAMES[i]: int(self.launches_by_class[i]) for i in range(7)},
-            "alg_bytes_by_class": {CLASS_NAMES[i]: float(self.alg_bytes_by_class[i]) for i in range(7)},
-            "ms_by_class": {CLASS_NAMES[i]: float(self.ms_by_class[i]) for i in range(7)},
+            "launches_by_class": {CLASS_NAMES[i]: int(self.launches_by_class[i]) for i in range(8)},
+            "alg_bytes_by_class": {CLASS_NAMES[i]: float(self.alg_bytes_by_class[i]) for i in range(8)},
+            "ms_by_class": {CLASS_NAMES[i]: float(self.ms_by_class[i]) for i in range(8)},
             "apply_ms": float(self.apply_ms),
         }
 
@@ -114,6 +118,8 @@ SYMBOLS = {
     "b2sv_enumerate_basis": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, ctypes.c_uint64]),
     "b2sv_device_ptr": (ctypes.c_int, [_P, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_uint64)]),
     "b2sv_sync": (ctypes.c_int, [_P]),
+    "b2sv_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(_P)]),
+    "b2sv_host_free": (ctypes.c_int, [_P]),
     "b2sv_mark": (ctypes.c_int, [_P, ctypes.c_int]),
     "b2sv_elapsed_ms": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
     "b2sv_swap_pack": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P]),
@@ -122,6 +128,7 @@ SYMBOLS = {
         ctypes.c_int,
         [ctypes.c_int, ctypes.c_int, _P, ctypes.c_size_t, ctypes.POINTER(PlanOpts), _P, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)],
     ),
+    "b2sv_perm_jit_compile_check": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _P, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
     "b2sv_stats": (ctypes.c_int, [_P, ctypes.POINTER(Stats)]),
     "b2sv_stats_reset": (ctypes.c_int, [_P]),
     "b2sv_abi_version": (ctypes.c_int, []),

@@ -10,7 +10,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <memory>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <type_traits>
 #include <utility>
@@ -19,6 +22,7 @@
 #include "../../include/b2sv.h"
 #include "kernels.cuh"
 #include "planner.hpp"
+#include "perm_jit.hpp"
 
 namespace {
 
@@ -42,7 +46,7 @@ int fail(int code, const char* fmt, ...) {
                         cudaGetErrorString(e_), __FILE__, __LINE__);                               \
     } while (0)
 
-enum { CLS_GATE1 = 0, CLS_TILE = 1, CLS_PERM = 2, CLS_SCALE = 3, CLS_PROJECT = 4, CLS_INIT = 5, CLS_SWAP = 6, CLS_N = 8 };
+enum { CLS_GATE1 = 0, CLS_TILE = 1, CLS_PERM = 2, CLS_SCALE = 3, CLS_PROJECT = 4, CLS_INIT = 5, CLS_SWAP = 6, CLS_PERM_JIT = 7, CLS_N = 8 };
 
 struct TimedLaunch {
     cudaEvent_t a, b;
@@ -61,10 +65,13 @@ struct b2sv {
     void* amps = nullptr;
     void* scratch = nullptr;       // second state-sized buffer for out-of-place permutation sweeps
     bool scratch_failed = false;
+    bool timing_on = false;        // last b2sv_apply asked for per-launch timing: time init/project too
     double sre = 1.0, sim = 0.0;   // pending global scalar (folded uncontrolled global phases)
     void* d_ops = nullptr;         // device copy of the tile ops of the current apply
     size_t d_ops_cap = 0;
-    b2sv_subnode* d_sub = nullptr; // device copy of the current subspace program
+    void* d_gather = nullptr;      // device-side result buffer of project_gather / enumerate_basis
+    size_t d_gather_cap = 0;
+    b2sv_subinstr* d_sub = nullptr; // device copy of the current subspace program
     int d_sub_cap = 0;
     double* d_partial = nullptr;   // projection partial sums (+1 slot for the result)
     int n_partial = 0;
@@ -166,6 +173,17 @@ template <typename F>
 int dispatch_dtype(const b2sv* sv, F&& f) {
     if (sv->dtype == B2SV_C128) return f((double2*)nullptr);
     return f((float2*)nullptr);
+}
+
+int ensure_gather(b2sv* sv, size_t bytes) {
+    if (bytes <= sv->d_gather_cap) return B2SV_OK;
+    CU(cudaStreamSynchronize(sv->stream));
+    cudaFree(sv->d_gather);
+    sv->d_gather = nullptr;
+    sv->d_gather_cap = 0;
+    CU(cudaMalloc(&sv->d_gather, bytes));
+    sv->d_gather_cap = bytes;
+    return B2SV_OK;
 }
 
 int ensure_scratch(b2sv* sv) {
@@ -331,53 +349,146 @@ int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, co
     });
 }
 
-// Encode a permutation run (execution order gates[first..last)) as the REVERSED word program of its
-// inverse map; returns false if it does not fit `cap` ops.
-void encode_perm_gate(const PGate& g, int n, std::vector<PermOp>& out) {
-    std::vector<uint8_t> ctrls;
+// Encode one permutation gate as word ops (see kernels.cuh), in EXECUTION order.
+void encode_perm_gate(const PGate& g, int n, std::vector<uint4>& out) {
+    auto row = [](int r) { return (uint32_t)r * (uint32_t)kPermRowBytes; };
+    const uint32_t ones = row(n);
+    std::vector<int> ctrls;
     for (int q = 0; q < 64; ++q)
-        if ((g.ctrl >> q) & 1) ctrls.push_back((uint8_t)q);
-    const uint8_t ones = (uint8_t)n;
-    const size_t direct = g.op == B2SV_OP_X ? 3 : 2;  // control slots of the final op
-    size_t used = 0;
-    // long control lists: leading ACC ops take 4 controls each
-    bool first_acc = true;
-    while (ctrls.size() - used > direct) {
-        PermOp op{};
-        op.kind = first_acc ? 2 : 3;
-        first_acc = false;
-        uint8_t slot[4] = {ones, ones, ones, ones};
-        for (int s = 0; s < 4 && ctrls.size() - used > direct; ++s) slot[s] = ctrls[used++];
-        op.a = slot[0];
-        op.b = slot[1];
-        op.c = slot[2];
-        op.d = slot[3];
-        out.push_back(op);
+        if ((g.ctrl >> q) & 1) ctrls.push_back(q);
+    const size_t direct = g.op == B2SV_OP_X ? 3 : 2;  // control slots left in the final op(s)
+    // Long control lists: fold controls into temporaries T1 (and T2 for very long lists):
+    //   T1 ^= c0&c1&c2 ; [T2 ^= T1&c3&c4 ; T1' ...] -- kept simple: chain through two temporaries.
+    std::vector<uint4> prologue;
+    std::vector<int> eff(ctrls.begin(), ctrls.end());  // effective control rows of the final op
+    int next_temp = n + 1;
+    while (eff.size() > direct) {
+        // take three controls, AND them into a fresh temporary, replace them by the temporary
+        const int t = next_temp++;
+        uint4 op;
+        op.x = row(t);
+        op.y = row(eff[0]);
+        op.z = row(eff[1]);
+        op.w = row(eff[2]);
+        prologue.push_back(op);
+        eff.erase(eff.begin(), eff.begin() + 3);
+        eff.insert(eff.begin(), t);
     }
-    uint8_t rest[3] = {ones, ones, ones};
-    for (size_t s = 0; used < ctrls.size(); ++s) rest[s] = ctrls[used++];
-    PermOp op{};
+    for (const uint4& op : prologue) out.push_back(op);
+    auto ctl = [&](size_t i) { return i < eff.size() ? row(eff[i]) : ones; };
     if (g.op == B2SV_OP_X) {
-        op.kind = 0;
-        op.a = g.t0;
-        op.b = rest[0];
-        op.c = rest[1];
-        op.d = rest[2];
+        out.push_back(make_uint4(row(g.t0), ctl(0), ctl(1), ctl(2)));
     } else {
-        op.kind = 1;
-        op.a = g.t0;
-        op.b = g.t1;
-        op.c = rest[0];
-        op.d = rest[1];
+        out.push_back(make_uint4(row(g.t1), row(g.t0), ctl(0), ctl(1)));
+        out.push_back(make_uint4(row(g.t0), row(g.t1), ctl(0), ctl(1)));
+        out.push_back(make_uint4(row(g.t1), row(g.t0), ctl(0), ctl(1)));
     }
-    out.push_back(op);
+    for (size_t i = prologue.size(); i-- > 0;) out.push_back(prologue[i]);  // un-compute the temporaries
 }
 
-int launch_perm(b2sv* sv, const Plan& plan, const Segment& seg, bool timing) {
+static_assert(kPermMaxCtrlX == 3 + 2 * kPermTemps && kPermMaxCtrlSwap == 2 + 2 * kPermTemps,
+              "planner's control limits must match the scratch rows of k_perm");
+
+// ---- run-time specialised permutation kernels (perm_jit.hpp) -------------------------------------
+
+struct JitEntry {
+    std::mutex mu;
+    int state = 0;  // 0 compiling, 1 cubin ready, -1 failed
+    std::vector<char> cubin;
+    std::string log;
+    std::map<int, std::pair<cudaLibrary_t, cudaKernel_t>> loaded;  // per device
+    uint64_t uses = 0;
+};
+std::mutex g_jit_mutex;
+std::map<std::string, std::shared_ptr<JitEntry>> g_jit;
+
+std::string perm_key(const std::vector<PGate>& gates, int n, int dtype) {
+    std::string k;
+    k.reserve(gates.size() * 11 + 8);
+    k.push_back((char)n);
+    k.push_back((char)dtype);
+    for (const PGate& g : gates) {
+        k.push_back((char)g.op);
+        k.push_back((char)g.t0);
+        k.push_back((char)(g.op == B2SV_OP_SWAP ? g.t1 : 0));
+        k.append(reinterpret_cast<const char*>(&g.ctrl), 8);
+    }
+    return k;
+}
+
+void jit_compile_into(const std::shared_ptr<JitEntry>& e, std::vector<PGate> gates, int n, int dtype) {
+    std::vector<char> cubin;
+    std::string log;
+    const bool ok = nvrtc_compile(perm_jit_source(gates, n, dtype), cubin, log);
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->cubin = std::move(cubin);
+    e->log = std::move(log);
+    e->state = ok ? 1 : -1;
+}
+
+// Returns the specialised kernel for this run if it is ready (loading it on first use), else null.
+cudaKernel_t jit_lookup(b2sv* sv, const std::vector<PGate>& gates, int jit_mode) {
+    if (jit_mode == 1 || !nvrtc_api().ok) return nullptr;
+    std::shared_ptr<JitEntry> e;
+    {
+        std::lock_guard<std::mutex> lk(g_jit_mutex);
+        std::string key = perm_key(gates, sv->n, sv->dtype);
+        auto it = g_jit.find(key);
+        if (it == g_jit.end()) {
+            e = std::make_shared<JitEntry>();
+            g_jit.emplace(std::move(key), e);
+            if (jit_mode == 2) {
+                jit_compile_into(e, gates, sv->n, sv->dtype);
+            } else {
+                std::thread(jit_compile_into, e, gates, sv->n, sv->dtype).detach();
+                return nullptr;  // first sighting: the generic kernel runs while NVRTC works
+            }
+        } else {
+            e = it->second;
+        }
+    }
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->uses++;
+    if (e->state != 1) return nullptr;
+    auto it = e->loaded.find(sv->device);
+    if (it == e->loaded.end()) {
+        cudaLibrary_t lib = nullptr;
+        cudaKernel_t k = nullptr;
+        if (cudaLibraryLoadData(&lib, e->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
+            cudaLibraryGetKernel(&k, lib, "b2sv_perm_jit") != cudaSuccess) {
+            cudaGetLastError();
+            e->state = -1;
+            e->log = "loading the specialised kernel failed";
+            return nullptr;
+        }
+        it = e->loaded.emplace(sv->device, std::make_pair(lib, k)).first;
+    }
+    return it->second.second;
+}
+
+int launch_perm(b2sv* sv, const Plan& plan, const Segment& seg, bool timing, int jit_mode) {
+    // long runs on big registers: straight-line register code from NVRTC once it is ready
+    if (jit_mode == 2 || (seg.gates.size() >= 64 && sv->n >= 20)) {
+        std::vector<PGate> gates;
+        gates.reserve(seg.gates.size());
+        for (int gi : seg.gates) gates.push_back(plan.gates[gi]);
+        if (cudaKernel_t k = jit_lookup(sv, gates, jit_mode)) {
+            const void* in = sv->amps;
+            void* out = sv->scratch;
+            void* args[] = {(void*)&in, (void*)&out};
+            const uint64_t blocks = sv->count / (uint64_t)(kPermThreads * 32);
+            {
+                LaunchTimer lt(sv, timing, CLS_PERM_JIT, 2.0 * sv->amp_bytes * (double)sv->count);
+                CU(cudaLaunchKernel((const void*)k, dim3((unsigned)blocks), dim3(kPermThreads), args, 0, sv->stream));
+            }
+            std::swap(sv->amps, sv->scratch);
+            return B2SV_OK;
+        }
+    }
     // split the run so that each chunk's program fits constant memory
     size_t pos = 0;
     while (pos < seg.gates.size()) {
-        std::vector<PermOp> fwd;  // ops in execution order, gate by gate
+        std::vector<uint4> fwd;  // ops in execution order, gate by gate
         std::vector<size_t> gate_end;
         size_t e = pos;
         while (e < seg.gates.size()) {
@@ -391,18 +502,15 @@ int launch_perm(b2sv* sv, const Plan& plan, const Segment& seg, bool timing) {
             ++e;
         }
         if (e == pos) return fail(B2SV_EINVAL, "permutation gate too large");
-        // reverse gate order, keeping each gate's ACC ops in front of its final op
-        std::vector<PermOp> prog;
-        prog.reserve(fwd.size());
-        for (size_t gi = gate_end.size(); gi-- > 0;) {
-            const size_t b = gi == 0 ? 0 : gate_end[gi - 1];
-            for (size_t q = b; q < gate_end[gi]; ++q) prog.push_back(fwd[q]);
-        }
+        // The sweep gathers: out[j] = in[f^-1(j)], and f^-1 applies the (self-inverse) gates in reverse
+        // order.  Each gate's op group is a palindrome (compute temporaries, act, un-compute), so
+        // reversing the whole op list reverses the gates and keeps every group valid.
+        std::vector<uint4> prog(fwd.rbegin(), fwd.rend());
+        // SWAP groups (b^=a, a^=b, b^=a) are palindromes too.
         ConstGuard guard(sv);
-        CU(cudaMemcpyToSymbolAsync(c_perm_ops, prog.data(), prog.size() * sizeof(PermOp), 0, cudaMemcpyHostToDevice,
+        CU(cudaMemcpyToSymbolAsync(c_perm_ops, prog.data(), prog.size() * sizeof(uint4), 0, cudaMemcpyHostToDevice,
                                    sv->stream));
-        // the host vector dies at the end of this iteration: pageable copies are staged synchronously
-        const size_t smem = (size_t)(sv->n + 1) * kPermRowBytes;
+        const size_t smem = (size_t)(sv->n + 1 + kPermTemps) * kPermRowBytes;
         const uint64_t blocks = sv->count / (uint64_t)(kPermThreads * 32);
         int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
             using A = std::remove_pointer_t<decltype(tag)>;
@@ -429,32 +537,48 @@ int check(const b2sv* sv) {
     return B2SV_OK;
 }
 
-int upload_subprog(b2sv* sv, const b2sv_subnode* prog, int n_nodes, int root_count, int target_qubits) {
-    if (!prog && n_nodes > 0) return fail(B2SV_EINVAL, "null subspace program");
-    if (n_nodes < 0 || n_nodes > kMaxSubNodes) return fail(B2SV_EINVAL, "subspace program has %d nodes (max %d)", n_nodes, kMaxSubNodes);
-    if (root_count < 0 || root_count > n_nodes) return fail(B2SV_EINVAL, "bad root_count");
+// Validates and uploads a subspace program; *count_bits = number of low index bits that can be
+// non-zero in a member (top ZEROS runs reachable from `entry` shrink the scan range).
+int upload_subprog(b2sv* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits, int* count_bits) {
+    if (!prog || n_instr <= 0) return fail(B2SV_EINVAL, "empty subspace program");
+    if (n_instr > kMaxSubInstr) return fail(B2SV_EINVAL, "subspace program has %d instructions (max %d)", n_instr, kMaxSubInstr);
+    if (entry < 0 || entry >= n_instr) return fail(B2SV_EINVAL, "bad entry %d", entry);
     if (target_qubits < 0 || target_qubits > sv->n) return fail(B2SV_EINVAL, "target_qubits %d outside [0,%d]", target_qubits, sv->n);
-    int bits = 0;
-    for (int i = 0; i < root_count; ++i) bits += prog[i].nbits;
-    if (bits != target_qubits) return fail(B2SV_EINVAL, "subspace spans %d qubits, target_qubits is %d", bits, target_qubits);
-    for (int i = 0; i < n_nodes; ++i) {
-        const b2sv_subnode& nd = prog[i];
-        if (nd.kind != 0 && nd.kind != 1) return fail(B2SV_EINVAL, "bad subspace node kind");
-        if (nd.kind == 1)
-            for (int c = 0; c < 2; ++c)
-                if (nd.child_count[c] < 0 || nd.child_first[c] < 0 || nd.child_first[c] + nd.child_count[c] > n_nodes)
-                    return fail(B2SV_EINVAL, "subspace node %d has children out of range", i);
+    uint64_t covered = 0;
+    for (int i = 0; i < n_instr; ++i) {
+        const b2sv_subinstr& in = prog[i];
+        if (in.op > B2SV_SUB_BRANCH) return fail(B2SV_EINVAL, "subspace instruction %d: bad op %d", i, (int)in.op);
+        if (in.op == B2SV_SUB_END) continue;
+        const int len = in.op == B2SV_SUB_BRANCH ? 1 : in.len;
+        if (len < 1 || in.pos + len > target_qubits) return fail(B2SV_EINVAL, "subspace instruction %d: bits [%d,%d) outside the %d target qubits", i, (int)in.pos, in.pos + len, target_qubits);
+        if (in.next0 >= n_instr || (in.op == B2SV_SUB_BRANCH && in.next1 >= n_instr))
+            return fail(B2SV_EINVAL, "subspace instruction %d: jump out of range", i);
+        covered |= (len >= 64 ? ~0ull : ((1ull << len) - 1)) << in.pos;
     }
-    if (n_nodes > sv->d_sub_cap) {
+    const uint64_t all = target_qubits >= 64 ? ~0ull : ((1ull << target_qubits) - 1);
+    if ((covered & all) != all) return fail(B2SV_EINVAL, "subspace program does not constrain all %d target qubits", target_qubits);
+    // shrink the scan range by the ZEROS runs at the top of the index that every path goes through:
+    // conservative version -- follow the entry chain while it is made of ZEROS instructions.
+    int bits = target_qubits;
+    {
+        uint64_t zero_mask = 0;
+        int pc = entry;
+        for (int guard = 0; guard < n_instr && prog[pc].op == B2SV_SUB_ZEROS; ++guard) {
+            zero_mask |= (prog[pc].len >= 64 ? ~0ull : ((1ull << prog[pc].len) - 1)) << prog[pc].pos;
+            pc = prog[pc].next0;
+        }
+        while (bits > 0 && ((zero_mask >> (bits - 1)) & 1)) --bits;
+    }
+    if (count_bits) *count_bits = bits;
+    if (n_instr > sv->d_sub_cap) {
         CU(cudaStreamSynchronize(sv->stream));
         cudaFree(sv->d_sub);
         sv->d_sub = nullptr;
         sv->d_sub_cap = 0;
-        CU(cudaMalloc(&sv->d_sub, sizeof(b2sv_subnode) * (size_t)(n_nodes + 64)));
-        sv->d_sub_cap = n_nodes + 64;
+        CU(cudaMalloc(&sv->d_sub, sizeof(b2sv_subinstr) * (size_t)(n_instr + 64)));
+        sv->d_sub_cap = n_instr + 64;
     }
-    if (n_nodes > 0)
-        CU(cudaMemcpyAsync(sv->d_sub, prog, (size_t)n_nodes * sizeof(b2sv_subnode), cudaMemcpyHostToDevice, sv->stream));
+    CU(cudaMemcpyAsync(sv->d_sub, prog, (size_t)n_instr * sizeof(b2sv_subinstr), cudaMemcpyHostToDevice, sv->stream));
     return B2SV_OK;
 }
 
@@ -551,6 +675,7 @@ int b2sv_destroy(b2sv_t* sv) {
     cudaFree(sv->d_ops);
     cudaFree(sv->d_partial);
     cudaFree(sv->d_sub);
+    cudaFree(sv->d_gather);
     cudaStreamDestroy(sv->stream);
     cudaGetLastError();
     delete sv;
@@ -565,7 +690,7 @@ int b2sv_set_basis(b2sv_t* sv, uint64_t index) {
     sv->sim = 0.0;
     int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
         using A = std::remove_pointer_t<decltype(tag)>;
-        LaunchTimer lt(sv, false, CLS_INIT, (double)sv->amp_bytes * (double)sv->count);
+        LaunchTimer lt(sv, sv->timing_on, CLS_INIT, (double)sv->amp_bytes * (double)sv->count);
         k_set_basis<A><<<grid_for(sv, sv->count), kThreads, 0, sv->stream>>>((A*)sv->amps, sv->count, index);
         return B2SV_OK;
     });
@@ -653,7 +778,9 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
     }
     PlanConfig cfg = default_config(sv->n, sv->dtype, opts);
     const bool timing = opts && opts->timing;
-    const bool bulk = !(opts && opts->reserved[0] == 1);  // reserved[0] == 1: plain ld/st tile I/O (debug aid)
+    sv->timing_on = timing;
+    const bool bulk = !(opts && opts->tile_io == 1);
+    const int jit_mode = opts ? opts->jit : 0;
     bool scratch_ok = false;
     if (cfg.fuse && cfg.perm_runs && sv->n >= 13) {
         // only pay for the second buffer if the circuit has a run that wants it
@@ -711,7 +838,7 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
         } else if (seg.cls == SEG_TILE) {
             rc = launch_tile(sv, seg, (const TileOp*)sv->d_ops + seg_first[s], (int)seg.gates.size(), cfg, bulk, timing);
         } else {
-            rc = launch_perm(sv, plan, seg, timing);
+            rc = launch_perm(sv, plan, seg, timing, jit_mode);
         }
         if (rc) return rc;
         CU(cudaGetLastError());
@@ -725,17 +852,18 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
     return B2SV_OK;
 }
 
-int b2sv_project_norm2(b2sv_t* sv, const b2sv_subnode* prog, int n_nodes, int root_count, int target_qubits, double* out) {
+int b2sv_project_norm2(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits, double* out) {
     if (int rc = check(sv)) return rc;
     if (!out) return fail(B2SV_EINVAL, "out is null");
     CU(cudaSetDevice(sv->device));
-    if (int rc = upload_subprog(sv, prog, n_nodes, root_count, target_qubits)) return rc;
-    const uint64_t cnt = 1ull << target_qubits;
+    int count_bits = 0;
+    if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits)) return rc;
+    const uint64_t cnt = 1ull << count_bits;
     const int grid = grid_for(sv, cnt);
     int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
         using A = std::remove_pointer_t<decltype(tag)>;
-        LaunchTimer lt(sv, false, CLS_PROJECT, (double)sv->amp_bytes * (double)cnt);
-        k_project_norm2<A><<<grid, kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, root_count, sv->d_partial);
+        LaunchTimer lt(sv, sv->timing_on, CLS_PROJECT, (double)sv->amp_bytes * (double)cnt);
+        k_project_norm2<A><<<grid, kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, sv->d_partial);
         k_reduce_partials<<<1, kThreads, 0, sv->stream>>>(sv->d_partial, grid, sv->d_partial + sv->n_partial);
         return B2SV_OK;
     });
@@ -748,50 +876,50 @@ int b2sv_project_norm2(b2sv_t* sv, const b2sv_subnode* prog, int n_nodes, int ro
     return B2SV_OK;
 }
 
-int b2sv_project_gather(b2sv_t* sv, const b2sv_subnode* prog, int n_nodes, int root_count, int target_qubits,
+int b2sv_project_gather(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
                         double scale_re, double scale_im, void* host_out, uint64_t dim) {
     if (int rc = check(sv)) return rc;
     if (!host_out && dim > 0) return fail(B2SV_EINVAL, "host_out is null");
     CU(cudaSetDevice(sv->device));
-    if (int rc = upload_subprog(sv, prog, n_nodes, root_count, target_qubits)) return rc;
+    int count_bits = 0;
+    if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits)) return rc;
     if (dim == 0) return B2SV_OK;
-    const uint64_t cnt = 1ull << target_qubits;
-    double2* d_out = nullptr;
-    CU(cudaMalloc(&d_out, dim * 16));
+    const uint64_t cnt = 1ull << count_bits;
+    if (int rc = ensure_gather(sv, dim * 16)) return rc;
+    double2* d_out = (double2*)sv->d_gather;
     cudaMemsetAsync(d_out, 0, dim * 16, sv->stream);
     // the pending global scalar rides along in the scale factor
     const double2 s = make_double2(scale_re * sv->sre - scale_im * sv->sim, scale_re * sv->sim + scale_im * sv->sre);
     dispatch_dtype(sv, [&](auto* tag) -> int {
         using A = std::remove_pointer_t<decltype(tag)>;
-        LaunchTimer lt(sv, false, CLS_PROJECT, (double)sv->amp_bytes * (double)cnt + 16.0 * (double)dim);
-        k_project_gather<A><<<grid_for(sv, cnt), kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, root_count, s, d_out, dim);
+        LaunchTimer lt(sv, sv->timing_on, CLS_PROJECT, (double)sv->amp_bytes * (double)cnt + 16.0 * (double)dim);
+        k_project_gather<A><<<grid_for(sv, cnt), kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, s, d_out, dim);
         return B2SV_OK;
     });
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, d_out, dim * 16, cudaMemcpyDeviceToHost, sv->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(sv->stream);
-    cudaFree(d_out);
     if (e != cudaSuccess) return fail(B2SV_ECUDA, "project_gather failed: %s", cudaGetErrorString(e));
     return B2SV_OK;
 }
 
-int b2sv_enumerate_basis(b2sv_t* sv, const b2sv_subnode* prog, int n_nodes, int root_count, int target_qubits,
+int b2sv_enumerate_basis(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
                          int64_t* host_out, uint64_t dim) {
     if (int rc = check(sv)) return rc;
     if (!host_out && dim > 0) return fail(B2SV_EINVAL, "host_out is null");
     CU(cudaSetDevice(sv->device));
-    if (int rc = upload_subprog(sv, prog, n_nodes, root_count, target_qubits)) return rc;
+    int count_bits = 0;
+    if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits)) return rc;
     if (dim == 0) return B2SV_OK;
-    const uint64_t cnt = 1ull << target_qubits;
-    long long* d_out = nullptr;
-    CU(cudaMalloc(&d_out, dim * 8));
+    const uint64_t cnt = 1ull << count_bits;
+    if (int rc = ensure_gather(sv, dim * 8)) return rc;
+    long long* d_out = (long long*)sv->d_gather;
     cudaMemsetAsync(d_out, 0xFF, dim * 8, sv->stream);
     sv->stats.launches_by_class[CLS_PROJECT]++;
-    k_enumerate_basis<<<grid_for(sv, cnt), kThreads, 0, sv->stream>>>(sv->d_sub, cnt, root_count, d_out, dim);
+    k_enumerate_basis<<<grid_for(sv, cnt), kThreads, 0, sv->stream>>>(sv->d_sub, cnt, entry, n_instr + 1, d_out, dim);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, d_out, dim * 8, cudaMemcpyDeviceToHost, sv->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(sv->stream);
-    cudaFree(d_out);
     if (e != cudaSuccess) return fail(B2SV_ECUDA, "enumerate_basis failed: %s", cudaGetErrorString(e));
     return B2SV_OK;
 }
@@ -810,6 +938,30 @@ int b2sv_sync(b2sv_t* sv) {
     if (int rc = check(sv)) return rc;
     CU(cudaSetDevice(sv->device));
     CU(cudaStreamSynchronize(sv->stream));
+    return B2SV_OK;
+}
+
+int b2sv_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(B2SV_EINVAL, "out is null");
+    *out = nullptr;
+    if (bytes == 0) return fail(B2SV_EINVAL, "zero-size allocation");
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return fail(e == cudaErrorMemoryAllocation ? B2SV_ENOMEM : B2SV_ENODEV, "cudaHostAlloc(%zu) failed: %s", bytes,
+                    cudaGetErrorString(e));
+    }
+    return B2SV_OK;
+}
+
+int b2sv_host_free(void* ptr) {
+    if (!ptr) return B2SV_OK;
+    cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B2SV_ECUDA, "cudaFreeHost failed: %s", cudaGetErrorString(e));
+    }
     return B2SV_OK;
 }
 
@@ -891,6 +1043,24 @@ int b2sv_plan_describe(int n_qubits, int dtype, const b2sv_gate* gates, size_t n
         put(im_bits);
     }
     if (n_words) *n_words = w;
+    return B2SV_OK;
+}
+
+int b2sv_perm_jit_compile_check(int n_qubits, int dtype, const b2sv_gate* gates, size_t n_gates, size_t* cubin_bytes) {
+    if (n_qubits < 13 || n_qubits > 40) return fail(B2SV_EINVAL, "n_qubits %d outside [13,40]", n_qubits);
+    if (n_gates > 0 && !gates) return fail(B2SV_EINVAL, "gates is null");
+    std::vector<PGate> pg;
+    double sre = 1, sim = 0;
+    for (size_t j = 0; j < n_gates; ++j) {
+        PGate g;
+        if (!normalise_gate(gates[j], (int)j, g, sre, sim)) continue;
+        if (!g.is_perm()) return fail(B2SV_EINVAL, "gate %zu is not a permutation gate", j);
+        pg.push_back(g);
+    }
+    std::vector<char> cubin;
+    std::string log;
+    if (!nvrtc_compile(perm_jit_source(pg, n_qubits, dtype), cubin, log)) return fail(B2SV_ESTATE, "NVRTC: %s", log.c_str());
+    if (cubin_bytes) *cubin_bytes = cubin.size();
     return B2SV_OK;
 }
 

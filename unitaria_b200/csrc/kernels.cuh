@@ -315,26 +315,38 @@ __global__ void __launch_bounds__(kThreads) k_tile(A* __restrict__ psi, const Ti
 //    gate program is read through the constant cache so it does not compete with shared memory.
 // ===================================================================================================
 
-constexpr int kPermMaxOps = 7680;          // 60 KiB of constant memory
+constexpr int kPermMaxOps = 3840;          // 60 KiB of constant memory, 16 bytes per op
 constexpr int kPermThreads = 256;
 constexpr int kPermRowBytes = kPermThreads * 4;
+constexpr int kPermTemps = 2;              // scratch rows for control lists longer than three
 
-// 8-byte op.  Row numbers are qubit indices; row `n` is the all-ones row (an unused control slot).
-// kind 0: X     W[a] ^= acc & W[b] & W[c] & W[d]
-// kind 1: SWAP  m = acc & W[c] & W[d] & (W[a]^W[b]); W[a]^=m; W[b]^=m
-// kind 2: ACC   acc = W[a] & W[b] & W[c] & W[d]            (starts a long control chain)
-// kind 3: ACC&  acc &= W[a] & W[b] & W[c] & W[d]
-// After a kind 0/1 op acc is reset to all ones.
-struct PermOp {
-    uint8_t kind, a, b, c, d, pad[3];
-};
-static_assert(sizeof(PermOp) == 8, "PermOp layout");
+// One word op: W[t] ^= W[c0] & W[c1] & W[c2], every field a row BYTE offset (row * kPermRowBytes).
+// Row n is all ones (unused control slots), rows n+1.. are zero-initialised temporaries.
+//   X(t; c...)        -> one op (<= 3 controls); longer lists AND into a temporary first, use it as a
+//                        control and un-compute it afterwards
+//   SWAP(a,b; c...)   -> three ops: b ^= a&c, a ^= b&c, b ^= a&c
+__constant__ uint4 c_perm_ops[kPermMaxOps];
 
-__constant__ uint2 c_perm_ops[kPermMaxOps];
+// 32x32 bit-matrix transpose, LSB convention: out[b] bit q == in[q] bit b.
+__device__ __forceinline__ void transpose32(uint32_t (&a)[32]) {
+    uint32_t m = 0x0000FFFFu;
+#pragma unroll
+    for (int j = 16; j != 0; j >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            if ((k & j) == 0) {
+                const uint32_t t = ((a[k] >> j) ^ a[k + j]) & m;
+                a[k] ^= t << j;
+                a[k + j] ^= t;
+            }
+        }
+        m ^= m << (j >> 1);
+    }
+}
 
 template <typename A>
 __global__ void __launch_bounds__(kPermThreads) k_perm(const A* __restrict__ in, A* __restrict__ out, int n, int n_ops) {
-    extern __shared__ __align__(16) uint32_t W[];  // (n + 1) rows of kPermThreads words
+    extern __shared__ __align__(16) uint32_t W[];  // (n + 1 + kPermTemps) rows of kPermThreads words
     const int tid = threadIdx.x, lane = tid & 31;
     const uint64_t warp_global = (uint64_t)blockIdx.x * (kPermThreads / 32) + (tid >> 5);
     const uint64_t warp_base = warp_global << 10;  // 1024 outputs per warp: j = warp_base + b*32 + lane
@@ -351,36 +363,27 @@ __global__ void __launch_bounds__(kPermThreads) k_perm(const A* __restrict__ in,
         W[q * kPermThreads + tid] = w;
     }
     W[n * kPermThreads + tid] = 0xFFFFFFFFu;
-    uint32_t acc = 0xFFFFFFFFu;
-    uint32_t* Wt = W + tid;
+    for (int r = 1; r <= kPermTemps; ++r) W[(n + r) * kPermThreads + tid] = 0u;
+    unsigned char* col = reinterpret_cast<unsigned char*>(W + tid);  // this thread's column
+#pragma unroll 4
     for (int o = 0; o < n_ops; ++o) {
-        const uint2 raw = c_perm_ops[o];
-        const uint32_t kind = raw.x & 0xFF;
-        const uint32_t ra = (raw.x >> 8) & 0xFF, rb = (raw.x >> 16) & 0xFF, rc = raw.x >> 24, rd = raw.y & 0xFF;
-        const uint32_t wc = Wt[rc * kPermThreads], wd = Wt[rd * kPermThreads];
-        if (kind == 0) {
-            const uint32_t m = acc & Wt[rb * kPermThreads] & wc & wd;
-            Wt[ra * kPermThreads] ^= m;
-            acc = 0xFFFFFFFFu;
-        } else if (kind == 1) {
-            const uint32_t wa = Wt[ra * kPermThreads], wb = Wt[rb * kPermThreads];
-            const uint32_t m = acc & wc & wd & (wa ^ wb);
-            Wt[ra * kPermThreads] = wa ^ m;
-            Wt[rb * kPermThreads] = wb ^ m;
-            acc = 0xFFFFFFFFu;
-        } else {
-            const uint32_t m = Wt[ra * kPermThreads] & Wt[rb * kPermThreads] & wc & wd;
-            acc = (kind == 2) ? m : (acc & m);
-        }
+        const uint4 op = c_perm_ops[o];
+        const uint32_t m = *reinterpret_cast<uint32_t*>(col + op.y) & *reinterpret_cast<uint32_t*>(col + op.z) &
+                           *reinterpret_cast<uint32_t*>(col + op.w);
+        *reinterpret_cast<uint32_t*>(col + op.x) ^= m;
     }
-    // un-slice: source index of output b, then move the amplitudes (8 loads in flight per thread)
-#pragma unroll 1
+    // un-slice with a register bit-matrix transpose: src[b] = source index of output b
+    uint32_t lo[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) lo[q] = q < n ? W[q * kPermThreads + tid] : 0u;
+    transpose32(lo);
+#pragma unroll
     for (int b0 = 0; b0 < 32; b0 += 8) {
         uint64_t src[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) src[u] = 0;
-        for (int q = 0; q < n; ++q) {
-            const uint32_t w = Wt[q * kPermThreads] >> b0;
+        for (int u = 0; u < 8; ++u) src[u] = lo[b0 + u];
+        for (int q = 32; q < n; ++q) {  // registers wider than 32 qubits (sharded / 33-34 qubit runs)
+            const uint32_t w = W[q * kPermThreads + tid] >> b0;
 #pragma unroll
             for (int u = 0; u < 8; ++u) src[u] |= (uint64_t)((w >> u) & 1u) << q;
         }
@@ -397,72 +400,50 @@ __global__ void __launch_bounds__(kPermThreads) k_perm(const A* __restrict__ in,
 //    /root/reference/src/unitaria/subspace.py:297-335) fused with the norm (nodes/node.py:390-403).
 // ===================================================================================================
 
-constexpr int kMaxSubNodes = 1 << 16;  // program lives in global memory (per-thread divergent reads)
+constexpr int kMaxSubInstr = 65535;  // program lives in global memory (per-thread divergent reads)
 
-// member test + rank (position in ascending-index order) of index `bits`.
-__device__ __forceinline__ bool sub_member_rank(const b2sv_subnode* __restrict__ c_sub, uint64_t bits, int root_count,
-                                                uint64_t& rank_out) {
-    struct Frame {
-        int cur, end;
-        uint64_t bits, rank, radix, add;
-    };
-    Frame st[66];
-    int sp = 0;
-    st[0] = {0, root_count, bits, 0, 1, 0};
-    uint64_t ret = 0;
-    bool returning = false;
-    while (true) {
-        Frame& f = st[sp];
-        if (returning) {
-            // child finished with rank `ret`: fold into the factor that spawned it
-            const b2sv_subnode nd = c_sub[f.cur];
-            f.rank += (ret + f.add) * f.radix;
-            f.radix *= nd.dim;
-            f.cur++;
-            returning = false;
+// member test + rank (position in ascending-index order) of index `bits`: a stack-free walk of the
+// decision program (see include/b2sv.h).  `max_steps` bounds the walk so that a malformed program
+// cannot hang the device.
+__device__ __forceinline__ bool sub_member_rank(const b2sv_subinstr* __restrict__ prog, int entry, int max_steps,
+                                                uint64_t bits, uint64_t& rank_out) {
+    uint64_t r = 0;
+    int pc = entry;
+    for (int step = 0; step < max_steps; ++step) {
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(prog + pc));
+        const uint32_t op = h.x & 0xFFu, pos = (h.x >> 8) & 0xFFu, len = (h.x >> 16) & 0xFFu;
+        const uint64_t field = (bits >> pos) & (len >= 64 ? ~0ull : ((1ull << len) - 1ull));
+        if (op == B2SV_SUB_END) {
+            rank_out = r;
+            return true;
         }
-        if (f.cur == f.end) {
-            if (sp == 0) {
-                rank_out = f.rank;
-                return true;
+        if (op == B2SV_SUB_ZEROS) {
+            if (field) return false;
+            pc = (int)(h.y & 0xFFFFu);
+        } else if (op == B2SV_SUB_FREE) {
+            r += field * ((uint64_t)h.z | ((uint64_t)h.w << 32));
+            pc = (int)(h.y & 0xFFFFu);
+        } else {  // BRANCH on bit `pos`
+            if ((bits >> pos) & 1ull) {
+                r += __ldg(&prog[pc].add);
+                pc = (int)(h.y >> 16);
+            } else {
+                pc = (int)(h.y & 0xFFFFu);
             }
-            ret = f.rank;
-            --sp;
-            returning = true;
-            continue;
         }
-        const b2sv_subnode nd = c_sub[f.cur];
-        if (nd.kind == 0) {
-            if (f.bits & 1) return false;
-            f.bits >>= 1;
-            f.cur++;
-            continue;
-        }
-        const int nb = nd.nbits - 1;
-        const uint64_t low = f.bits & ((nb >= 64) ? ~0ull : ((1ull << nb) - 1));
-        const int top = (int)((f.bits >> nb) & 1);
-        f.bits >>= (nb + 1);
-        if (nd.child_count[top] == 0) {  // child is the zero-qubit (empty) subspace: rank 0, dim 1
-            f.rank += (top ? nd.dim0 : 0) * f.radix;
-            f.radix *= nd.dim;
-            f.cur++;
-            continue;
-        }
-        f.add = top ? nd.dim0 : 0;
-        ++sp;
-        st[sp] = {nd.child_first[top], nd.child_first[top] + nd.child_count[top], low, 0, 1, 0};
     }
+    return false;
 }
 
 template <typename A>
-__global__ void __launch_bounds__(kThreads) k_project_norm2(const A* __restrict__ psi, const b2sv_subnode* __restrict__ sub,
-                                                            uint64_t count, int root_count,
+__global__ void __launch_bounds__(kThreads) k_project_norm2(const A* __restrict__ psi, const b2sv_subinstr* __restrict__ sub,
+                                                            uint64_t count, int entry, int max_steps,
                                                             double* __restrict__ partial) {
     double acc = 0.0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
         uint64_t r;
-        if (sub_member_rank(sub, i, root_count, r)) {
+        if (sub_member_rank(sub, entry, max_steps, i, r)) {
             const double2 v = to_c128(psi[i]);
             acc = fma(v.x, v.x, fma(v.y, v.y, acc));
         }
@@ -493,23 +474,23 @@ __global__ void __launch_bounds__(kThreads) k_reduce_partials(const double* __re
 }
 
 template <typename A>
-__global__ void __launch_bounds__(kThreads) k_project_gather(const A* __restrict__ psi, const b2sv_subnode* __restrict__ sub,
-                                                             uint64_t count, int root_count,
+__global__ void __launch_bounds__(kThreads) k_project_gather(const A* __restrict__ psi, const b2sv_subinstr* __restrict__ sub,
+                                                             uint64_t count, int entry, int max_steps,
                                                              double2 scale, double2* __restrict__ out, uint64_t dim) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
         uint64_t r;
-        if (sub_member_rank(sub, i, root_count, r) && r < dim) out[r] = cmul(scale, to_c128(psi[i]));
+        if (sub_member_rank(sub, entry, max_steps, i, r) && r < dim) out[r] = cmul(scale, to_c128(psi[i]));
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_enumerate_basis(const b2sv_subnode* __restrict__ sub, uint64_t count, int root_count,
+__global__ void __launch_bounds__(kThreads) k_enumerate_basis(const b2sv_subinstr* __restrict__ sub, uint64_t count, int entry, int max_steps,
                                                               long long* __restrict__ out,
                                                               uint64_t dim) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
         uint64_t r;
-        if (sub_member_rank(sub, i, root_count, r) && r < dim) out[r] = (long long)i;
+        if (sub_member_rank(sub, entry, max_steps, i, r) && r < dim) out[r] = (long long)i;
     }
 }
 

@@ -1,0 +1,180 @@
+// perm_jit.hpp -- run-time specialisation of the permutation-run sweep (host side, no CUDA here).
+//
+// The generic kernel k_perm (kernels.cuh) interprets the word program out of shared memory because
+// a register file cannot be indexed by a run-time qubit number; it is bound by shared-memory
+// wavefronts (5 per gate per 1024 amplitudes), ~5x the HBM time for the 1434-gate ripple-carry run
+// of BASELINE config 2.  For a program that is applied again and again (every input of
+// Node.simulate's matrix case, every step of a benchmark) the engine therefore emits the SAME
+// kernel with the gate loop unrolled into straight-line register code -- one LOP3 per gate for 32
+// amplitudes -- compiles it with NVRTC for sm_100a on a background thread, and switches to it when
+// ready.  Prologue (bit-sliced index words) and epilogue (register bit-matrix transpose, coalesced
+// 16-byte gather/scatter) are textually the ones of k_perm.
+#pragma once
+
+#include <dlfcn.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "planner.hpp"
+
+namespace b2svk {
+
+inline std::string perm_jit_source(const std::vector<PGate>& exec_order, int n, int dtype) {
+    std::string s;
+    s.reserve(exec_order.size() * 40 + 8192);
+    char buf[256];
+    s += dtype == B2SV_C64 ? "typedef float2 amp_t;\n" : "typedef double2 amp_t;\n";
+    s += "extern \"C\" __global__ void __launch_bounds__(256) b2sv_perm_jit(const amp_t* __restrict__ in, amp_t* __restrict__ out) {\n";
+    s += "  const unsigned tid = threadIdx.x, lane = tid & 31u;\n";
+    s += "  const unsigned long long wg = (unsigned long long)blockIdx.x * 8ull + (tid >> 5);\n";
+    s += "  const unsigned long long warp_base = wg << 10;\n";
+    static const char* pat[5] = {"0xAAAAAAAAu", "0xCCCCCCCCu", "0xF0F0F0F0u", "0xFF00FF00u", "0xFFFF0000u"};
+    for (int q = 0; q < n; ++q) {
+        if (q < 5) snprintf(buf, sizeof(buf), "  unsigned w%d = ((lane >> %d) & 1u) ? 0xFFFFFFFFu : 0u;\n", q, q);
+        else if (q < 10) snprintf(buf, sizeof(buf), "  unsigned w%d = %s;\n", q, pat[q - 5]);
+        else snprintf(buf, sizeof(buf), "  unsigned w%d = ((wg >> %d) & 1ull) ? 0xFFFFFFFFu : 0u;\n", q, q - 10);
+        s += buf;
+    }
+    // the sweep gathers out[j] = in[f^-1(j)]: apply the self-inverse gates in reverse order
+    for (size_t gi = exec_order.size(); gi-- > 0;) {
+        const PGate& g = exec_order[gi];
+        std::string m;
+        for (int q = 0; q < 64; ++q)
+            if ((g.ctrl >> q) & 1) {
+                snprintf(buf, sizeof(buf), "%sw%d", m.empty() ? "" : " & ", q);
+                m += buf;
+            }
+        if (g.op == B2SV_OP_X) {
+            if (m.empty()) snprintf(buf, sizeof(buf), "  w%d = ~w%d;\n", (int)g.t0, (int)g.t0);
+            else snprintf(buf, sizeof(buf), "  w%d ^= %s;\n", (int)g.t0, m.c_str());
+            s += buf;
+        } else {
+            if (m.empty()) snprintf(buf, sizeof(buf), "  { const unsigned d = w%d ^ w%d; w%d ^= d; w%d ^= d; }\n", (int)g.t0, (int)g.t1, (int)g.t0, (int)g.t1);
+            else
+                snprintf(buf, sizeof(buf), "  { const unsigned d = (w%d ^ w%d) & %s; w%d ^= d; w%d ^= d; }\n", (int)g.t0, (int)g.t1,
+                         m.c_str(), (int)g.t0, (int)g.t1);
+            s += buf;
+        }
+    }
+    s += "  unsigned a[32] = {";
+    for (int q = 0; q < 32; ++q) {
+        if (q < n) snprintf(buf, sizeof(buf), "w%d%s", q, q == 31 ? "" : ", ");
+        else snprintf(buf, sizeof(buf), "0u%s", q == 31 ? "" : ", ");
+        s += buf;
+    }
+    s += "};\n";
+    s += "  unsigned m = 0x0000FFFFu;\n"
+         "  #pragma unroll\n"
+         "  for (int j = 16; j != 0; j >>= 1) {\n"
+         "    #pragma unroll\n"
+         "    for (int k = 0; k < 32; ++k) {\n"
+         "      if ((k & j) == 0) { const unsigned t = ((a[k] >> j) ^ a[k + j]) & m; a[k] ^= t << j; a[k + j] ^= t; }\n"
+         "    }\n"
+         "    m ^= m << (j >> 1);\n"
+         "  }\n";
+    s += "  #pragma unroll\n"
+         "  for (int b0 = 0; b0 < 32; b0 += 8) {\n"
+         "    unsigned long long src[8];\n"
+         "    #pragma unroll\n"
+         "    for (int u = 0; u < 8; ++u) src[u] = a[b0 + u];\n";
+    for (int q = 32; q < n; ++q) {
+        snprintf(buf, sizeof(buf),
+                 "    #pragma unroll\n    for (int u = 0; u < 8; ++u) src[u] |= (unsigned long long)((w%d >> (b0 + u)) & 1u) << %d;\n", q, q);
+        s += buf;
+    }
+    s += "    amp_t v[8];\n"
+         "    #pragma unroll\n"
+         "    for (int u = 0; u < 8; ++u) v[u] = in[src[u]];\n"
+         "    #pragma unroll\n"
+         "    for (int u = 0; u < 8; ++u) out[warp_base + (unsigned long long)(b0 + u) * 32ull + lane] = v[u];\n"
+         "  }\n"
+         "}\n";
+    return s;
+}
+
+// ---- NVRTC through dlopen: the library keeps no link-time dependency on it --------------------------
+
+struct NvrtcApi {
+    void* handle = nullptr;
+    int (*CreateProgram)(void**, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    int (*CompileProgram)(void*, int, const char* const*) = nullptr;
+    int (*GetCUBINSize)(void*, size_t*) = nullptr;
+    int (*GetCUBIN)(void*, char*) = nullptr;
+    int (*GetProgramLogSize)(void*, size_t*) = nullptr;
+    int (*GetProgramLog)(void*, char*) = nullptr;
+    int (*DestroyProgram)(void**) = nullptr;
+    bool ok = false;
+};
+
+inline const NvrtcApi& nvrtc_api() {
+    static NvrtcApi api = [] {
+        NvrtcApi a;
+        const char* names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so",
+                               "/usr/local/cuda/lib64/libnvrtc.so"};
+        for (const char* nm : names) {
+            a.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+            if (a.handle) break;
+        }
+        if (!a.handle) return a;
+        auto sym = [&](const char* n) { return dlsym(a.handle, n); };
+        a.CreateProgram = (decltype(a.CreateProgram))sym("nvrtcCreateProgram");
+        a.CompileProgram = (decltype(a.CompileProgram))sym("nvrtcCompileProgram");
+        a.GetCUBINSize = (decltype(a.GetCUBINSize))sym("nvrtcGetCUBINSize");
+        a.GetCUBIN = (decltype(a.GetCUBIN))sym("nvrtcGetCUBIN");
+        a.GetProgramLogSize = (decltype(a.GetProgramLogSize))sym("nvrtcGetProgramLogSize");
+        a.GetProgramLog = (decltype(a.GetProgramLog))sym("nvrtcGetProgramLog");
+        a.DestroyProgram = (decltype(a.DestroyProgram))sym("nvrtcDestroyProgram");
+        a.ok = a.CreateProgram && a.CompileProgram && a.GetCUBINSize && a.GetCUBIN && a.GetProgramLogSize &&
+               a.GetProgramLog && a.DestroyProgram;
+        return a;
+    }();
+    return api;
+}
+
+// Compile `src` for sm_100a; returns true and fills `cubin` on success, else fills `log`.
+inline bool nvrtc_compile(const std::string& src, std::vector<char>& cubin, std::string& log) {
+    const NvrtcApi& api = nvrtc_api();
+    if (!api.ok) {
+        log = "libnvrtc not available";
+        return false;
+    }
+    void* prog = nullptr;
+    if (api.CreateProgram(&prog, src.c_str(), "b2sv_perm_jit.cu", 0, nullptr, nullptr) != 0) {
+        log = "nvrtcCreateProgram failed";
+        return false;
+    }
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-lineinfo"};
+    const int rc = api.CompileProgram(prog, 2, opts);
+    if (rc != 0) {
+        size_t n = 0;
+        api.GetProgramLogSize(prog, &n);
+        log.resize(n);
+        if (n) api.GetProgramLog(prog, &log[0]);
+        api.DestroyProgram(&prog);
+        return false;
+    }
+    size_t n = 0;
+    api.GetCUBINSize(prog, &n);
+    cubin.resize(n);
+    const bool ok = n > 0 && api.GetCUBIN(prog, cubin.data()) == 0;
+    api.DestroyProgram(&prog);
+    if (const char* dump = getenv("B2SV_JIT_DUMP")) {  // debugging aid: keep the last source + cubin
+        std::string base(dump);
+        if (FILE* f = fopen((base + ".cu").c_str(), "w")) {
+            fwrite(src.data(), 1, src.size(), f);
+            fclose(f);
+        }
+        if (FILE* f = fopen((base + ".cubin").c_str(), "wb")) {
+            fwrite(cubin.data(), 1, cubin.size(), f);
+            fclose(f);
+        }
+    }
+    if (!ok) log = "nvrtcGetCUBIN failed";
+    return ok;
+}
+
+}  // namespace b2svk

@@ -33,6 +33,7 @@
 namespace b2svk {
 
 enum SegClass { SEG_GATE1Q = 0, SEG_TILE = 1, SEG_PERM = 2 };
+constexpr int kPermMaxCtrlX = 7, kPermMaxCtrlSwap = 6;
 
 struct PGate {
     uint8_t op;
@@ -43,6 +44,12 @@ struct PGate {
     double m[8];
     int src;          // index in the caller's list
     bool is_perm() const { return op == B2SV_OP_X || op == B2SV_OP_SWAP; }
+    // fits the word-op encoding of the permutation-run kernel (3 direct control slots, 2 for SWAP,
+    // plus two per scratch row)
+    bool perm_ok() const {
+        const int c = __builtin_popcountll(ctrl);
+        return (op == B2SV_OP_X && c <= kPermMaxCtrlX) || (op == B2SV_OP_SWAP && c <= kPermMaxCtrlSwap);
+    }
 };
 
 struct Segment {
@@ -266,9 +273,9 @@ inline Plan make_plan(const b2sv_gate* gates, size_t n_gates, const PlanConfig& 
     };
     size_t j = 0;
     while (j < G.size()) {
-        if (G[j].is_perm() && cfg.perm_runs && scratch_available) {
+        if (G[j].perm_ok() && cfg.perm_runs && scratch_available) {
             size_t e = j;
-            while (e < G.size() && G[e].is_perm()) ++e;
+            while (e < G.size() && G[e].perm_ok()) ++e;
             const size_t len = e - j;
             bool use_perm = false;
             if ((int)len >= cfg.perm_min) {

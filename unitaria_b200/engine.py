@@ -3,6 +3,7 @@
 from __future__ import annotations
 
 import ctypes
+import weakref
 
 import numpy as np
 
@@ -19,6 +20,62 @@ _DTYPES = {
     "c64": B2SV_C64,
     np.complex64: B2SV_C64,
 }
+
+
+class _PinnedPool:
+    """Recycles page-locked host buffers for results that cross PCIe.
+
+    ``cudaHostAlloc`` is slow (it pins pages), so buffers are handed out as numpy arrays and come
+    back to the pool when the last array (or view) on them is garbage-collected.  A caller that
+    keeps a result alive simply keeps its buffer; nothing is ever overwritten behind its back.
+    """
+
+    MIN_BYTES = 1 << 20
+    MAX_CACHED = 6 << 30
+
+    def __init__(self):
+        self.free: dict = {}
+        self.cached = 0
+
+    def array(self, count: int, dtype) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        nbytes = int(count) * dtype.itemsize
+        if nbytes < self.MIN_BYTES:
+            return np.empty(count, dtype=dtype)
+        lib = cabi.load()
+        bucket = self.free.get(nbytes)
+        if bucket:
+            ptr = bucket.pop()
+            self.cached -= nbytes
+        else:
+            p = ctypes.c_void_p()
+            if lib.b2sv_host_alloc(nbytes, ctypes.byref(p)) != 0:
+                return np.empty(count, dtype=dtype)  # pinning failed: pageable memory still works
+            ptr = p.value
+        buf = (ctypes.c_char * nbytes).from_address(ptr)
+        weakref.finalize(buf, self._release, ptr, nbytes)
+        return np.frombuffer(buf, dtype=dtype, count=count)
+
+    def _release(self, ptr: int, nbytes: int) -> None:
+        if self.cached + nbytes <= self.MAX_CACHED:
+            self.free.setdefault(nbytes, []).append(ptr)
+            self.cached += nbytes
+        else:
+            try:
+                cabi.load().b2sv_host_free(ctypes.c_void_p(ptr))
+            except Exception:
+                pass
+
+    def clear(self) -> None:
+        lib = cabi.load()
+        for bucket in self.free.values():
+            for ptr in bucket:
+                lib.b2sv_host_free(ctypes.c_void_p(ptr))
+        self.free.clear()
+        self.cached = 0
+
+
+PINNED = _PinnedPool()
 
 
 def _dtype_code(dtype) -> int:
@@ -85,7 +142,7 @@ class StateVector:
 
     def download(self, out: np.ndarray | None = None) -> np.ndarray:
         if out is None:
-            out = np.empty(self.size, dtype=np.complex128)
+            out = PINNED.array(self.size, np.complex128)
         assert out.dtype == np.complex128 and out.flags.c_contiguous and out.size == self.size
         cabi.check(self._lib.b2sv_download(self._h, out.ctypes.data))
         return out
@@ -119,18 +176,18 @@ class StateVector:
         p = self._program(subspace)
         out = ctypes.c_double(0.0)
         cabi.check(
-            self._lib.b2sv_project_norm2(self._h, p.nodes.ctypes.data, len(p.nodes), p.root_count, p.total_qubits, ctypes.byref(out))
+            self._lib.b2sv_project_norm2(self._h, p.instrs.ctypes.data, len(p.instrs), p.entry, p.total_qubits, ctypes.byref(out))
         )
         return float(out.value)
 
     def project(self, subspace, scale: complex = 1.0) -> np.ndarray:
         """``scale * Subspace.project(psi)`` (subspace.py:331-335) gathered on the device."""
         p = self._program(subspace)
-        out = np.empty(p.dimension, dtype=np.complex128)
+        out = PINNED.array(p.dimension, np.complex128)
         s = complex(scale)
         cabi.check(
             self._lib.b2sv_project_gather(
-                self._h, p.nodes.ctypes.data, len(p.nodes), p.root_count, p.total_qubits, s.real, s.imag, out.ctypes.data, p.dimension
+                self._h, p.instrs.ctypes.data, len(p.instrs), p.entry, p.total_qubits, s.real, s.imag, out.ctypes.data, p.dimension
             )
         )
         return out
@@ -140,7 +197,7 @@ class StateVector:
         p = self._program(subspace)
         out = np.empty(p.dimension, dtype=np.int64)
         cabi.check(
-            self._lib.b2sv_enumerate_basis(self._h, p.nodes.ctypes.data, len(p.nodes), p.root_count, p.total_qubits, out.ctypes.data, p.dimension)
+            self._lib.b2sv_enumerate_basis(self._h, p.instrs.ctypes.data, len(p.instrs), p.entry, p.total_qubits, out.ctypes.data, p.dimension)
         )
         return out
 

@@ -1,11 +1,11 @@
-"""Subspace -> flat device program (``b2sv_subnode[]``), SURVEY.md App. C.
+"""Subspace -> stack-free device program (``b2sv_subinstr[]``), SURVEY.md App. C.
 
 A unitaria ``Subspace`` (/root/reference/src/unitaria/subspace.py) is a tensor product of factors,
 least-significant first (:117-125): ``ZeroQubitSubspace`` (one qubit fixed to 0) or
 ``ControlledSubspace(case_zero, case_one)`` whose top qubit picks which sub-subspace constrains the
-lower qubits (:523-560).  ``test_basis`` (:297-323) walks those factors; the device does the same
-walk on the flattened tree, plus the mixed-radix rank that reproduces ``enumerate_basis`` order
-(:325-329) without enumerating.
+lower qubits (:523-560).  ``test_basis`` (:297-323) walks those factors; the device runs the same
+walk as a compiled decision program, plus the mixed-radix rank that reproduces ``enumerate_basis``
+order (:325-329) without enumerating.
 
 Accepted inputs: a unitaria ``Subspace`` (duck-typed via ``tensor_factors`` / ``case_zero`` /
 ``case_one``), a string such as ``"0##"`` (most significant qubit first, subspace.py:114-125) or the
@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .cabi import SUBNODE_DTYPE
+from .cabi import SUB_BRANCH, SUB_END, SUB_FREE, SUB_ZEROS, SUBINSTR_DTYPE
 
 
 def to_spec(subspace) -> list:
@@ -61,32 +61,73 @@ def spec_dimension(spec) -> int:
 
 
 class SubspaceProgram:
-    """Flattened subspace: ``nodes`` (SUBNODE_DTYPE), ``root_count``, ``total_qubits``, ``dimension``."""
+    """Compiled subspace: ``instrs`` (SUBINSTR_DTYPE), ``entry``, ``total_qubits``, ``dimension``.
+
+    Because a Subspace is a tree, every factor has a static absolute bit position and a static
+    mixed-radix weight (product of the dimensions of all lower factors), so the
+    walk of ``test_basis`` compiles to a stack-free decision program (include/b2sv.h).
+    """
 
     def __init__(self, subspace):
         self.spec = to_spec(subspace)
         self.total_qubits = spec_total_qubits(self.spec)
         self.dimension = spec_dimension(self.spec)
-        records: list = []
-        self.root_count = len(self.spec)
-        self._emit(self.spec, records)
-        self.nodes = np.zeros(len(records), dtype=SUBNODE_DTYPE)
-        for i, r in enumerate(records):
-            self.nodes[i] = r
+        if self.total_qubits > 64:
+            raise ValueError("subspaces wider than 64 qubits are not supported")
+        self._ins: list = [dict(op=SUB_END, pos=0, len=0, next0=0, next1=0, weight=0, add=0)]
+        self.entry = self._emit_list(self.spec, 0, 1, 0)
+        if len(self._ins) > 65535:
+            raise ValueError("subspace program too long")
+        self.instrs = np.zeros(len(self._ins), dtype=SUBINSTR_DTYPE)
+        for i, r in enumerate(self._ins):
+            for k, v in r.items():
+                self.instrs[k][i] = v
+        del self._ins
 
-    def _emit(self, spec, records) -> int:
-        """Lay out the factors of ``spec`` contiguously; children follow later.  Returns first index."""
-        first = len(records)
-        records.extend([None] * len(spec))
-        for j, f in enumerate(spec):
+    def _push(self, **fields) -> int:
+        self._ins.append(fields)
+        return len(self._ins) - 1
+
+    def _emit_list(self, spec, pos: int, weight: int, cont: int) -> int:
+        """Emit the program of the factor list ``spec`` whose lowest qubit sits at absolute bit ``pos``
+        and whose rank is scaled by ``weight``; when the list is done control goes to ``cont``.
+        Returns the entry instruction.  Built back to front so every jump target already exists."""
+        positions, weights = [], []
+        p, w = pos, weight
+        for f in spec:
+            positions.append(p)
+            weights.append(w)
             if f == 0:
-                records[first + j] = (0, 1, 1, 0, (0, 0), (0, 0))
-                continue
-            s0, s1 = f
-            if spec_total_qubits(s0) != spec_total_qubits(s1):
-                raise ValueError("ControlledSubspace cases span different qubit counts")
-            d0, d1 = spec_dimension(s0), spec_dimension(s1)
-            c0 = self._emit(s0, records) if len(s0) else 0
-            c1 = self._emit(s1, records) if len(s1) else 0
-            records[first + j] = (1, 1 + spec_total_qubits(s0), d0 + d1, d0, (c0, c1), (len(s0), len(s1)))
-        return first
+                p += 1
+            else:
+                if spec_total_qubits(f[0]) != spec_total_qubits(f[1]):
+                    raise ValueError("ControlledSubspace cases span different qubit counts")
+                p += 1 + spec_total_qubits(f[0])
+                w *= spec_dimension(f[0]) + spec_dimension(f[1])
+        nxt = cont
+        for j in range(len(spec) - 1, -1, -1):
+            f, fp, fw = spec[j], positions[j], weights[j]
+            if fw >= 2**64:
+                raise ValueError("subspace dimension exceeds 64 bits")
+            head = self._ins[nxt]
+            if f == 0:
+                if head["op"] == SUB_ZEROS and head["pos"] == fp + 1 and nxt != cont:
+                    head["pos"], head["len"] = fp, head["len"] + 1  # extend the run downwards
+                else:
+                    nxt = self._push(op=SUB_ZEROS, pos=fp, len=1, next0=nxt, next1=0, weight=0, add=0)
+            elif len(f[0]) == 0 and len(f[1]) == 0:  # free qubit
+                if head["op"] == SUB_FREE and head["pos"] == fp + 1 and head["weight"] == 2 * fw and nxt != cont:
+                    head["pos"], head["len"], head["weight"] = fp, head["len"] + 1, fw
+                else:
+                    nxt = self._push(op=SUB_FREE, pos=fp, len=1, next0=nxt, next1=0, weight=fw, add=0)
+            else:
+                nb = spec_total_qubits(f[0])
+                e0 = self._emit_list(f[0], fp, fw, nxt)
+                e1 = self._emit_list(f[1], fp, fw, nxt)
+                nxt = self._push(op=SUB_BRANCH, pos=fp + nb, len=1, next0=e0, next1=e1, weight=0, add=spec_dimension(f[0]) * fw)
+        return nxt
+
+    # kept for callers that want the flat arrays under their C names
+    @property
+    def nodes(self):
+        return self.instrs
