@@ -70,11 +70,12 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         self.index = index
+        self.window = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                 stdout=subprocess.PIPE,
                 stderr=subprocess.DEVNULL,
                 text=True,
@@ -86,7 +87,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
@@ -98,7 +99,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for t, r in self.rows if self.window is None or self.window[0] <= t <= self.window[1]]
+        scope = "timed region"
+        if len(rows) < 2:  # timed region shorter than the sampling period: use every sample under load
+            rows, scope = [r for _t, r in self.rows], "warm-up + timed region"
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 smax.append(float(r[1]))
@@ -109,7 +114,7 @@ class ClockSampler:
                 continue
         if not sm:
             return None
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -254,16 +259,18 @@ def run_single(args):
         sv.apply_lowered(lowered, opts)
         return abs(norm) * np.sqrt(sv.project_norm2(prog))
 
+    clocks = ClockSampler()
+    clocks.start()
     for j in inputs[: args.warmup]:
         step(j)
     sv.stats_reset()
-    clocks = ClockSampler()
-    clocks.start()
     sv.sync()
+    t_begin = time.perf_counter()
     sv.mark(0)
     norms = [step(j) for j in inputs[args.warmup :]]
     sv.mark(1)
     sv.sync()
+    clocks.window = (t_begin, time.perf_counter())
     ms = sv.elapsed_ms(0, 1)
     st = sv.stats()
     gates_live = st["gates_live"] // max(1, args.steps)
@@ -314,8 +321,9 @@ def run_single(args):
         gates = case.gates
 
     adapter.configure(dtype="complex128" if dtype == "c128" else "complex64", opts=PlanOpts.make(jit=args.jit))
-    e2e_steps = max(1, min(args.steps, 5))
-    out = adapter.simulate_projected(Circuit, n, prog, norm, inputs[0])  # warm: lowering cache, register, scratch
+    e2e_steps = max(1, min(args.steps, 20))
+    for j in inputs[: min(3, len(inputs))]:  # warm: lowering cache, resident register, pinned result buffers
+        out = adapter.simulate_projected(Circuit, n, prog, norm, j)
     t0 = time.perf_counter()
     for j in inputs[args.warmup : args.warmup + e2e_steps]:
         out = adapter.simulate_projected(Circuit, n, prog, norm, j)
@@ -362,8 +370,8 @@ def run_single(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, help="fixture name under tests/golden (default: BASELINE config for --gpus)")
     ap.add_argument("--dtype", default="c128", choices=["c128", "c64"])

@@ -38,7 +38,9 @@ def test_cfg2_laplace_n26_columns_are_the_periodic_laplacian():
             for i, v in want.items():
                 assert abs(col[i] - v) < 1e-12
         st = sv.stats()
-        assert st["launches_by_class"]["perm"] >= 4 and st["launches_by_class"]["tile"] >= 4
+        # one permutation-run sweep per apply (generic kernel until the NVRTC-specialised one is ready)
+        assert st["launches_by_class"]["perm"] + st["launches_by_class"]["perm_jit"] == 4
+        assert st["launches_by_class"]["tile"] == 8 and st["launches_by_class"]["gate1q"] == 0
 
 
 def test_cfg2_tiles_only_equals_perm_path_on_dense_input():
