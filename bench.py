@@ -235,7 +235,7 @@ def run_single(args):
         raise SystemExit("bench.py needs a CUDA device: unitaria_b200 has no CPU fallback")
     case = load_workload(args.workload or workload_for(1))
     dtype = args.dtype
-    n = max(1, case.n_qubits)
+    n = max(1, case.n_qubits, args.qubits or 0)  # --qubits pads the register with idle high qubits (A (x) Identity)
     norm = case.meta["normalization"]
     prog = SubspaceProgram(case.meta["subspace_out"])
     prog_in = SubspaceProgram(case.meta["subspace_in"])
@@ -322,22 +322,24 @@ def run_single(args):
 
     adapter.configure(dtype="complex128" if dtype == "c128" else "complex64", opts=PlanOpts.make(jit=args.jit))
     e2e_steps = max(1, min(args.steps, 20))
-    for j in inputs[: min(3, len(inputs))]:  # warm: lowering cache, resident register, pinned result buffers
-        out = adapter.simulate_projected(Circuit, n, prog, norm, j)
-    t0 = time.perf_counter()
-    for j in inputs[args.warmup : args.warmup + e2e_steps]:
-        out = adapter.simulate_projected(Circuit, n, prog, norm, j)
-    e2e_s = time.perf_counter() - t0
-    e2e = {
-        "value": gates_live * e2e_steps / e2e_s,
-        "unit": "gates/s",
-        "h2d_bytes_per_step": int(lowered.nbytes + 96 * len(lowered)),
-        "d2h_bytes_per_step": int(out.nbytes),
-        "steps": e2e_steps,
-        "ms_per_step": 1e3 * e2e_s / e2e_steps,
-        "call": "unitaria_b200.simulate_projected(circuit, n_qubits, subspace_out, normalization, j) -> host complex128[dim_out] "
-        "(= Node.simulate(j)); H2D = lowered gate program, D2H = projected vector",
-    }
+    e2e = None
+    if not args.no_e2e:
+        for j in inputs[: min(3, len(inputs))]:  # warm: lowering cache, resident register, pinned result buffers
+            out = adapter.simulate_projected(Circuit, n, prog, norm, j)
+        t0 = time.perf_counter()
+        for j in inputs[args.warmup : args.warmup + e2e_steps]:
+            out = adapter.simulate_projected(Circuit, n, prog, norm, j)
+        e2e_s = time.perf_counter() - t0
+        e2e = {
+            "value": gates_live * e2e_steps / e2e_s,
+            "unit": "gates/s",
+            "h2d_bytes_per_step": int(lowered.nbytes + 96 * len(lowered)),
+            "d2h_bytes_per_step": int(out.nbytes),
+            "steps": e2e_steps,
+            "ms_per_step": 1e3 * e2e_s / e2e_steps,
+            "call": "unitaria_b200.simulate_projected(circuit, n_qubits, subspace_out, normalization, j) -> host complex128[dim_out] "
+            "(= Node.simulate(j)); H2D = lowered gate program, D2H = projected vector",
+        }
     adapter.clear_caches()
 
     cpu = None if args.no_cpu_baseline else cpu_sample(case, budget_s=args.cpu_seconds)
@@ -375,6 +377,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, help="fixture name under tests/golden (default: BASELINE config for --gpus)")
     ap.add_argument("--dtype", default="c128", choices=["c128", "c64"])
+    ap.add_argument("--qubits", type=int, default=None, help="pad the register to this many qubits (idle high qubits)")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--jit", default="sync", choices=["sync", "auto", "off"], help="permutation-run kernel specialisation")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

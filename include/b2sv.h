@@ -118,6 +118,7 @@ int b2sv_destroy(b2sv_t* sv);
 
 /* ---- state I/O (circuit.py:62-65: from_basis_state / from_array; :70: to_array) ---------------- */
 int b2sv_set_basis(b2sv_t* sv, uint64_t index);
+int b2sv_set_zero(b2sv_t* sv); /* all amplitudes 0: a shard that does not own the basis state */
 int b2sv_upload(b2sv_t* sv, const void* host_amps_c128);
 int b2sv_download(b2sv_t* sv, void* host_out_c128);
 
@@ -129,6 +130,11 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
  * (ancilla) qubit 0. */
 int b2sv_project_norm2(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
                        double* out);
+/* Sharded form: this handle holds the amplitudes index_base | i (i < 2^n_qubits, index_base's low
+ * n_qubits bits clear) of a wider register; the subspace program spans `target_qubits` (<= 64) qubits
+ * of the WIDE index.  The caller sums the per-shard results (unitaria_b200/distributed.py). */
+int b2sv_project_norm2_at(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
+                          uint64_t index_base, double* out);
 /* host_out[rank(i)] = (scale_re + i*scale_im) * psi_i for the members i, in ascending-index order
  * (= Subspace.enumerate_basis order, subspace.py:325-329); `dim` must equal the subspace dimension. */
 int b2sv_project_gather(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,

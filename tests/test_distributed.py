@@ -1,0 +1,154 @@
+"""Host logic of the distributed layer on CPU: world_size-2 and -4 ``gloo`` runs.
+
+The shard backend here is a TEST DOUBLE built on the CPU oracle (tests may use the oracle; the
+product backend is the CUDA engine, exercised on GPUs by tests/test_gpu_distributed.py).  What is
+under test is everything above it: layout tracking, gate localisation, rank relabels, swap
+planning, the pack/exchange/unpack order and the global reduction.
+"""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import np_oracle
+from tests.helpers import load_golden, random_circuit
+from unitaria_b200.distributed import Layout, ShardedStateVector, TorchComm, localise_gate
+from unitaria_b200.fixtures import GateRecord
+from unitaria_b200.subspace_prog import SubspaceProgram, to_spec
+
+
+class NumpyShard:
+    def __init__(self, n_local):
+        self.n = n_local
+        self.psi = np.zeros(2**n_local, dtype=np.complex128)
+        self.send = np.zeros(2 ** (n_local - 1), dtype=np.complex128)
+        self.recv = np.zeros(2 ** (n_local - 1), dtype=np.complex128)
+
+    def set_basis(self, index):
+        self.psi[:] = 0
+        self.psi[index] = 1
+
+    def clear(self):
+        self.psi[:] = 0
+
+    def apply(self, gates, opts=None):
+        for g in gates:
+            np_oracle.apply_gate(self.psi, self.n, g)
+
+    def _half(self, q, keep_bit):
+        idx = np.arange(2**self.n)
+        return idx[((idx >> q) & 1) != keep_bit]
+
+    def pack(self, q, keep_bit):
+        self.send[:] = self.psi[self._half(q, keep_bit)]
+        return torch.from_numpy(self.send.view(np.float64)), torch.from_numpy(self.recv.view(np.float64))
+
+    def unpack(self, q, keep_bit):
+        self.psi[self._half(q, keep_bit)] = self.recv
+
+    def norm2_at(self, prog, index_base):
+        t = prog.total_qubits
+        if index_base >> t:
+            return 0.0
+        mask = np_oracle.member_mask(prog.spec)
+        idx = index_base | np.arange(min(2**self.n, 2**t))
+        idx = idx[idx < 2**t]
+        sel = mask[idx]
+        return float(np.sum(np.abs(self.psi[: len(idx)][sel]) ** 2))
+
+    def download(self):
+        return self.psi.copy()
+
+    def close(self):
+        pass
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, case_name, seed, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        if case_name.startswith("random"):
+            n = int(case_name.split("_")[1])
+            rng = np.random.default_rng(seed)
+            gates = random_circuit(n, 160, rng, max_controls=3).gates
+            spec = to_spec("0" + "#" * (n - 1))
+            basis = int(rng.integers(0, 2 ** (n - 1)))
+        else:
+            case = load_golden(case_name)
+            n, gates, spec = case.n_qubits, case.gates, case.meta["subspace_out"]
+            basis = 3
+        sv = ShardedStateVector(n, TorchComm(), NumpyShard)
+        sv.set_basis(basis)
+        sv.apply(gates)
+        swaps_before_restore = sv.stats["swaps"]
+        norm2 = sv.project_norm2(SubspaceProgram(spec))
+        local = sv.local_amplitudes()
+        np.save(os.path.join(out_dir, f"shard{rank}.npy"), local)
+        if rank == 0:
+            np.save(os.path.join(out_dir, "meta.npy"), np.array([norm2, swaps_before_restore, sv.stats["swaps"]]))
+    finally:
+        dist.destroy_process_group()
+
+
+def run_case(tmp_path, world, case_name, seed=0):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, case_name, seed, str(tmp_path)), nprocs=world, join=True)
+    full = np.concatenate([np.load(tmp_path / f"shard{r}.npy") for r in range(world)])
+    meta = np.load(tmp_path / "meta.npy")
+    return full, meta
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("case_name", ["laplace_n4", "cfg5_bits5", "bpx_L2"])
+def test_sharded_matches_single_register_goldens(tmp_path, world, case_name):
+    case = load_golden(case_name)
+    full, meta = run_case(tmp_path, world, case_name)
+    want = np_oracle.simulate_gates(case.gates, case.n_qubits, 3)
+    assert np.abs(full - want).max() < 1e-12
+    basis = np_oracle.enumerate_basis(case.meta["subspace_out"])
+    assert abs(meta[0] - np.sum(np.abs(want[basis]) ** 2)) < 1e-12
+
+
+@pytest.mark.parametrize("world,n,seed", [(2, 6, 1), (4, 7, 2), (2, 9, 3)])
+def test_sharded_matches_single_register_random(tmp_path, world, n, seed):
+    """Every gate kind, controls on global qubits, rank relabels (uncontrolled X on a global qubit),
+    diagonal gates on global targets, global<->local swaps."""
+    full, meta = run_case(tmp_path, world, f"random_{n}", seed)
+    rng = np.random.default_rng(seed)
+    gates = random_circuit(n, 160, rng, max_controls=3).gates
+    basis = int(rng.integers(0, 2 ** (n - 1)))
+    want = np_oracle.simulate_gates(gates, n, basis)
+    assert np.abs(full - want).max() < 1e-12
+    member = np_oracle.enumerate_basis(to_spec("0" + "#" * (n - 1)))
+    assert abs(meta[0] - np.sum(np.abs(want[member]) ** 2)) < 1e-12
+    assert meta[1] > 0  # the circuit did need global<->local swaps
+
+
+def test_localise_gate_rules():
+    lay = Layout(6, 2)  # qubits 4,5 global
+    # control on a global qubit: dropped on ranks where it is 1, gate skipped where it is 0
+    g = GateRecord("X", (0,), (1, 5), 1.0, 1.0)
+    assert localise_gate(g, lay, rank=0) is None
+    lg = localise_gate(g, lay, rank=2)
+    assert lg.target == (0,) and lg.control == (1,)
+    # diagonal gate on a global target: per-rank scalar on the remaining controls
+    rz = GateRecord("Rz", (4,), (2,), 0.6, 1.0)
+    a, b = localise_gate(rz, lay, 0), localise_gate(rz, lay, 1)
+    assert a.name == "GlobalPhase" and a.control == (2,) and abs(a.parameter + 0.3) < 1e-15 and abs(b.parameter - 0.3) < 1e-15
+    ph = GateRecord("Phase", (5,), (), 0.4, 1.0)
+    assert localise_gate(ph, lay, 0) is None and localise_gate(ph, lay, 2).parameter == 0.4
+    # rank relabel: flip flag inverts the meaning of the rank bit
+    lay.flip[lay.pos[5]] = 1
+    assert localise_gate(g, lay, rank=0) is not None and localise_gate(g, lay, rank=2) is None

@@ -107,10 +107,15 @@ SYMBOLS = {
     "b2sv_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_P)]),
     "b2sv_destroy": (ctypes.c_int, [_P]),
     "b2sv_set_basis": (ctypes.c_int, [_P, ctypes.c_uint64]),
+    "b2sv_set_zero": (ctypes.c_int, [_P]),
     "b2sv_upload": (ctypes.c_int, [_P, _P]),
     "b2sv_download": (ctypes.c_int, [_P, _P]),
     "b2sv_apply": (ctypes.c_int, [_P, _P, ctypes.c_size_t, ctypes.POINTER(PlanOpts)]),
     "b2sv_project_norm2": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
+    "b2sv_project_norm2_at": (
+        ctypes.c_int,
+        [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(ctypes.c_double)],
+    ),
     "b2sv_project_gather": (
         ctypes.c_int,
         [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, _P, ctypes.c_uint64],

@@ -335,7 +335,8 @@ int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, co
     a.n_ops = n_ops;
     a.ops = d_ops;
     const uint64_t n_tiles = 1ull << (sv->n - a.k);
-    const size_t smem = (size_t)sv->amp_bytes << a.k;
+    if (n_ops > kTileMaxOps) return fail(B2SV_EINVAL, "tile sweep with %d ops (max %d)", n_ops, kTileMaxOps);
+    const size_t smem = ((size_t)sv->amp_bytes << a.k) + (size_t)kTileMaxOps * sizeof(TileOp);
     return dispatch_dtype(sv, [&](auto* tag) -> int {
         using A = std::remove_pointer_t<decltype(tag)>;
         int rc = set_tile_smem<A>(smem);
@@ -386,6 +387,7 @@ void encode_perm_gate(const PGate& g, int n, std::vector<uint4>& out) {
     for (size_t i = prologue.size(); i-- > 0;) out.push_back(prologue[i]);  // un-compute the temporaries
 }
 
+static_assert(kPlanMaxTileOps == kTileMaxOps, "planner and kernel disagree on the ops per tile sweep");
 static_assert(kPermMaxCtrlX == 3 + 2 * kPermTemps && kPermMaxCtrlSwap == 2 + 2 * kPermTemps,
               "planner's control limits must match the scratch rows of k_perm");
 
@@ -539,11 +541,14 @@ int check(const b2sv* sv) {
 
 // Validates and uploads a subspace program; *count_bits = number of low index bits that can be
 // non-zero in a member (top ZEROS runs reachable from `entry` shrink the scan range).
-int upload_subprog(b2sv* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits, int* count_bits) {
+int upload_subprog(b2sv* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits, int* count_bits,
+                   int max_target_qubits = -1) {
+    if (max_target_qubits < 0) max_target_qubits = sv->n;
     if (!prog || n_instr <= 0) return fail(B2SV_EINVAL, "empty subspace program");
     if (n_instr > kMaxSubInstr) return fail(B2SV_EINVAL, "subspace program has %d instructions (max %d)", n_instr, kMaxSubInstr);
     if (entry < 0 || entry >= n_instr) return fail(B2SV_EINVAL, "bad entry %d", entry);
-    if (target_qubits < 0 || target_qubits > sv->n) return fail(B2SV_EINVAL, "target_qubits %d outside [0,%d]", target_qubits, sv->n);
+    if (target_qubits < 0 || target_qubits > max_target_qubits)
+        return fail(B2SV_EINVAL, "target_qubits %d outside [0,%d]", target_qubits, max_target_qubits);
     uint64_t covered = 0;
     for (int i = 0; i < n_instr; ++i) {
         const b2sv_subinstr& in = prog[i];
@@ -696,6 +701,16 @@ int b2sv_set_basis(b2sv_t* sv, uint64_t index) {
     });
     CU(cudaGetLastError());
     return rc;
+}
+
+int b2sv_set_zero(b2sv_t* sv) {
+    if (int rc = check(sv)) return rc;
+    CU(cudaSetDevice(sv->device));
+    sv->sre = 1.0;
+    sv->sim = 0.0;
+    sv->stats.launches_by_class[CLS_INIT]++;
+    CU(cudaMemsetAsync(sv->amps, 0, sv->count * sv->amp_bytes, sv->stream));
+    return B2SV_OK;
 }
 
 // Host buffers are complex128.  complex64 states convert through a bounded device staging buffer.
@@ -852,18 +867,26 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
     return B2SV_OK;
 }
 
-int b2sv_project_norm2(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits, double* out) {
+int b2sv_project_norm2_at(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
+                          uint64_t index_base, double* out) {
     if (int rc = check(sv)) return rc;
     if (!out) return fail(B2SV_EINVAL, "out is null");
     CU(cudaSetDevice(sv->device));
+    if (index_base & (sv->count - 1)) return fail(B2SV_EINVAL, "index_base must have its low %d bits clear", sv->n);
     int count_bits = 0;
-    if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits)) return rc;
+    if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits, 64)) return rc;
+    if (target_qubits < 64 && (index_base >> target_qubits) != 0) {  // this shard holds ancilla != 0 only
+        *out = 0.0;
+        return B2SV_OK;
+    }
+    if (count_bits > sv->n) count_bits = sv->n;
     const uint64_t cnt = 1ull << count_bits;
     const int grid = grid_for(sv, cnt);
     int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
         using A = std::remove_pointer_t<decltype(tag)>;
         LaunchTimer lt(sv, sv->timing_on, CLS_PROJECT, (double)sv->amp_bytes * (double)cnt);
-        k_project_norm2<A><<<grid, kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, sv->d_partial);
+        k_project_norm2<A><<<grid, kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, index_base,
+                                                             sv->d_partial);
         k_reduce_partials<<<1, kThreads, 0, sv->stream>>>(sv->d_partial, grid, sv->d_partial + sv->n_partial);
         return B2SV_OK;
     });
@@ -874,6 +897,12 @@ int b2sv_project_norm2(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int e
     CU(cudaStreamSynchronize(sv->stream));
     *out = v * (sv->sre * sv->sre + sv->sim * sv->sim);
     return B2SV_OK;
+}
+
+int b2sv_project_norm2(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits, double* out) {
+    if (int rc = check(sv)) return rc;
+    if (target_qubits > sv->n) return fail(B2SV_EINVAL, "target_qubits %d outside [0,%d]", target_qubits, sv->n);
+    return b2sv_project_norm2_at(sv, prog, n_instr, entry, target_qubits, 0, out);
 }
 
 int b2sv_project_gather(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,

@@ -179,66 +179,134 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
                  : "memory");
 }
 
+constexpr int kTileMaxOps = 112;  // ops of one sweep are staged in shared memory (10.5 KiB)
+
+// Enumerate the tile-local indices with the fixed positions cleared, UNROLL at a time, so that a
+// thread has UNROLL independent shared-memory round trips in flight (the tile phase is latency-
+// bound otherwise: 8 warps per CTA, a dependent LDS -> DFMA -> STS chain per element).
+template <int UNROLL, typename F>
+__device__ __forceinline__ void tile_for_each(uint32_t cnt, uint64_t fixpos, int nfix, uint32_t lctrl, F&& body) {
+    uint32_t p = threadIdx.x;
+    for (; p + (UNROLL - 1) * kThreads < cnt; p += UNROLL * kThreads) {
+        uint32_t l[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) l[u] = expand_local(p + u * kThreads, fixpos, nfix) | lctrl;
+        body(l, UNROLL);
+    }
+    for (; p < cnt; p += kThreads) {
+        uint32_t l[UNROLL];
+        l[0] = expand_local(p, fixpos, nfix) | lctrl;
+        body(l, 1);
+    }
+}
+
 template <typename A>
 __device__ __forceinline__ void tile_apply_op(A* tile, const TileOp& op, int k, uint64_t base) {
-    const int tid = threadIdx.x;
+    const uint32_t cnt = 1u << (k - op.nfix);
+    const uint64_t fixpos = op.fixpos;
+    const int nfix = op.nfix;
+    const uint32_t lctrl = op.lctrl;
     switch (op.op) {
         case B2SV_OP_X: {
-            const uint32_t cnt = 1u << (k - op.nfix), bt = 1u << op.tpos;
-            for (uint32_t p = tid; p < cnt; p += kThreads) {
-                const uint32_t l0 = expand_local(p, op.fixpos, op.nfix) | op.lctrl;
-                const A v0 = tile[l0], v1 = tile[l0 | bt];
-                tile[l0] = v1;
-                tile[l0 | bt] = v0;
-            }
+            const uint32_t bt = 1u << op.tpos;
+            tile_for_each<4>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
+                A v0[4], v1[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (u < m) {
+                        v0[u] = tile[l[u]];
+                        v1[u] = tile[l[u] | bt];
+                    }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (u < m) {
+                        tile[l[u]] = v1[u];
+                        tile[l[u] | bt] = v0[u];
+                    }
+            });
         } break;
         case B2SV_OP_SWAP: {
-            const uint32_t cnt = 1u << (k - op.nfix), ba = 1u << op.tpos, bb = 1u << op.tpos2;
-            for (uint32_t p = tid; p < cnt; p += kThreads) {
-                const uint32_t l = expand_local(p, op.fixpos, op.nfix) | op.lctrl;
-                const A va = tile[l | ba], vb = tile[l | bb];
-                tile[l | ba] = vb;
-                tile[l | bb] = va;
-            }
+            const uint32_t ba = 1u << op.tpos, bb = 1u << op.tpos2;
+            tile_for_each<4>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
+                A va[4], vb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (u < m) {
+                        va[u] = tile[l[u] | ba];
+                        vb[u] = tile[l[u] | bb];
+                    }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (u < m) {
+                        tile[l[u] | ba] = vb[u];
+                        tile[l[u] | bb] = va[u];
+                    }
+            });
         } break;
         case B2SV_OP_MAT1: {
-            const uint32_t cnt = 1u << (k - op.nfix), bt = 1u << op.tpos;
+            const uint32_t bt = 1u << op.tpos;
             const double2 m00 = make_double2(op.m[0], op.m[1]), m01 = make_double2(op.m[2], op.m[3]);
             const double2 m10 = make_double2(op.m[4], op.m[5]), m11 = make_double2(op.m[6], op.m[7]);
-            for (uint32_t p = tid; p < cnt; p += kThreads) {
-                const uint32_t l0 = expand_local(p, op.fixpos, op.nfix) | op.lctrl;
-                const double2 v0 = to_c128(tile[l0]), v1 = to_c128(tile[l0 | bt]);
-                tile[l0] = from_c128<A>(cfma(m01, v1, cmul(m00, v0)));
-                tile[l0 | bt] = from_c128<A>(cfma(m11, v1, cmul(m10, v0)));
-            }
+            tile_for_each<2>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
+                double2 v0[2], v1[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    if (u < m) {
+                        v0[u] = to_c128(tile[l[u]]);
+                        v1[u] = to_c128(tile[l[u] | bt]);
+                    }
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    if (u < m) {
+                        tile[l[u]] = from_c128<A>(cfma(m01, v1[u], cmul(m00, v0[u])));
+                        tile[l[u] | bt] = from_c128<A>(cfma(m11, v1[u], cmul(m10, v0[u])));
+                    }
+            });
         } break;
         case B2SV_OP_DIAG1: {
             const double2 d0 = make_double2(op.m[0], op.m[1]), d1 = make_double2(op.m[2], op.m[3]);
             if (op.tpos == 0xFF) {  // target outside the tile: one CTA-uniform factor
                 const double2 d = (base & op.ext_tbit) ? d1 : d0;
                 if (d.x == 1.0 && d.y == 0.0) break;
-                const uint32_t cnt = 1u << (k - op.nfix);
-                for (uint32_t p = tid; p < cnt; p += kThreads) {
-                    const uint32_t l = expand_local(p, op.fixpos, op.nfix) | op.lctrl;
-                    tile[l] = from_c128<A>(cmul(d, to_c128(tile[l])));
-                }
+                tile_for_each<4>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
+                    double2 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (u < m) v[u] = to_c128(tile[l[u]]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (u < m) tile[l[u]] = from_c128<A>(cmul(d, v[u]));
+                });
             } else {
-                const uint32_t cnt = 1u << (k - op.nfix), bt = 1u << op.tpos;
-                const bool one0 = (d0.x == 1.0 && d0.y == 0.0), one1 = (d1.x == 1.0 && d1.y == 0.0);
-                for (uint32_t p = tid; p < cnt; p += kThreads) {
-                    const uint32_t l0 = expand_local(p, op.fixpos, op.nfix) | op.lctrl;
-                    if (!one0) tile[l0] = from_c128<A>(cmul(d0, to_c128(tile[l0])));
-                    if (!one1) tile[l0 | bt] = from_c128<A>(cmul(d1, to_c128(tile[l0 | bt])));
-                }
+                const uint32_t bt = 1u << op.tpos;
+                tile_for_each<2>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
+                    double2 v0[2], v1[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+                        if (u < m) {
+                            v0[u] = to_c128(tile[l[u]]);
+                            v1[u] = to_c128(tile[l[u] | bt]);
+                        }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+                        if (u < m) {
+                            tile[l[u]] = from_c128<A>(cmul(d0, v0[u]));
+                            tile[l[u] | bt] = from_c128<A>(cmul(d1, v1[u]));
+                        }
+                });
             }
         } break;
         default: {  // PHASE
             const double2 w = make_double2(op.m[0], op.m[1]);
-            const uint32_t cnt = 1u << (k - op.nfix);
-            for (uint32_t p = tid; p < cnt; p += kThreads) {
-                const uint32_t l = expand_local(p, op.fixpos, op.nfix) | op.lctrl;
-                tile[l] = from_c128<A>(cmul(w, to_c128(tile[l])));
-            }
+            tile_for_each<4>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
+                double2 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (u < m) v[u] = to_c128(tile[l[u]]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (u < m) tile[l[u]] = from_c128<A>(cmul(w, v[u]));
+            });
         } break;
     }
 }
@@ -255,9 +323,11 @@ template <typename A, bool BULK>
 __global__ void __launch_bounds__(kThreads) k_tile(A* __restrict__ psi, const TileArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     A* tile = reinterpret_cast<A*>(smem_raw);
+    const int k = a.k, lc = a.lc;
+    // the sweep's ops live behind the tile: fetched once, coalesced, while the tile is in flight
+    TileOp* s_ops = reinterpret_cast<TileOp*>(smem_raw + ((size_t)sizeof(A) << k));
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
-    const int k = a.k, lc = a.lc;
     const uint32_t n_chunks = 1u << (k - lc), chunk_elems = 1u << lc;
     const uint32_t chunk_bytes = chunk_elems * (uint32_t)sizeof(A);
     const uint64_t base = expand_bits((uint64_t)blockIdx.x, a.tile_ex);
@@ -272,6 +342,14 @@ __global__ void __launch_bounds__(kThreads) k_tile(A* __restrict__ psi, const Ti
         __syncthreads();
         for (uint32_t j = tid; j < n_chunks; j += kThreads)
             bulk_g2s(tile + (size_t)j * chunk_elems, psi + (base | chunk_offset(j, a.tile_ex, k, lc)), chunk_bytes, &bar);
+    }
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.ops);
+        uint4* dst = reinterpret_cast<uint4*>(s_ops);
+        const int n16 = a.n_ops * (int)(sizeof(TileOp) / 16);
+        for (int i = tid; i < n16; i += kThreads) dst[i] = __ldg(src + i);
+    }
+    if (BULK) {
         mbar_wait(&bar, 0);
     } else {
         const uint32_t elems = 1u << k;
@@ -279,11 +357,11 @@ __global__ void __launch_bounds__(kThreads) k_tile(A* __restrict__ psi, const Ti
             const uint64_t g = base | chunk_offset(l >> lc, a.tile_ex, k, lc) | (l & (chunk_elems - 1));
             tile[l] = psi[g];
         }
-        __syncthreads();
     }
+    __syncthreads();
 
     for (int o = 0; o < a.n_ops; ++o) {
-        const TileOp& op = a.ops[o];
+        const TileOp& op = s_ops[o];
         if ((base & op.ext_ctrl) != op.ext_ctrl) continue;  // CTA-uniform: gate not active on this tile
         tile_apply_op<A>(tile, op, k, base);
         __syncthreads();
@@ -437,13 +515,13 @@ __device__ __forceinline__ bool sub_member_rank(const b2sv_subinstr* __restrict_
 
 template <typename A>
 __global__ void __launch_bounds__(kThreads) k_project_norm2(const A* __restrict__ psi, const b2sv_subinstr* __restrict__ sub,
-                                                            uint64_t count, int entry, int max_steps,
+                                                            uint64_t count, int entry, int max_steps, uint64_t index_base,
                                                             double* __restrict__ partial) {
     double acc = 0.0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
         uint64_t r;
-        if (sub_member_rank(sub, entry, max_steps, i, r)) {
+        if (sub_member_rank(sub, entry, max_steps, index_base | i, r)) {
             const double2 v = to_c128(psi[i]);
             acc = fma(v.x, v.x, fma(v.y, v.y, acc));
         }

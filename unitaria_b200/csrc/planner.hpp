@@ -34,6 +34,7 @@ namespace b2svk {
 
 enum SegClass { SEG_GATE1Q = 0, SEG_TILE = 1, SEG_PERM = 2 };
 constexpr int kPermMaxCtrlX = 7, kPermMaxCtrlSwap = 6;
+constexpr int kPlanMaxTileOps = 112;  // gates per tile sweep (their ops are staged in shared memory)
 
 struct PGate {
     uint8_t op;
@@ -194,7 +195,7 @@ inline void plan_tiles(const std::vector<PGate>& G, const std::vector<int>& idx,
         uint64_t T = base;
         uint64_t blocked_any = 0, blocked_nd = 0;
         int scanned = 0;
-        for (size_t p = head; p < idx.size() && scanned < cfg.lookahead; ++p) {
+        for (size_t p = head; p < idx.size() && scanned < cfg.lookahead && (int)seg.gates.size() < kPlanMaxTileOps; ++p) {
             if (done[p]) continue;
             ++scanned;
             const PGate& g = G[idx[p]];

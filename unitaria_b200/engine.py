@@ -134,6 +134,9 @@ class StateVector:
     def set_basis(self, index: int) -> None:
         cabi.check(self._lib.b2sv_set_basis(self._h, int(index)))
 
+    def set_zero(self) -> None:
+        cabi.check(self._lib.b2sv_set_zero(self._h))
+
     def upload(self, amplitudes: np.ndarray) -> None:
         a = np.ascontiguousarray(amplitudes, dtype=np.complex128).reshape(-1)
         if a.size != self.size:
@@ -177,6 +180,17 @@ class StateVector:
         out = ctypes.c_double(0.0)
         cabi.check(
             self._lib.b2sv_project_norm2(self._h, p.instrs.ctypes.data, len(p.instrs), p.entry, p.total_qubits, ctypes.byref(out))
+        )
+        return float(out.value)
+
+    def project_norm2_at(self, subspace, index_base: int) -> float:
+        """Shard form of :meth:`project_norm2`: this register holds indices ``index_base | i`` of a wider one."""
+        p = self._program(subspace)
+        out = ctypes.c_double(0.0)
+        cabi.check(
+            self._lib.b2sv_project_norm2_at(
+                self._h, p.instrs.ctypes.data, len(p.instrs), p.entry, p.total_qubits, int(index_base), ctypes.byref(out)
+            )
         )
         return float(out.value)
 
