@@ -75,7 +75,7 @@ typedef struct b2sv_plan_opts {
     int32_t tile_io;      /* 0: bulk-async (TMA engine) tile copies (default); 1: plain ld/st (debug aid)   */
     int32_t jit;          /* permutation runs: 0 = specialise with NVRTC in the background after first use
                              (default), 1 = never (generic kernel only), 2 = compile synchronously       */
-    int32_t reserved;
+    int32_t reserved;     /* 1: no same-target multiplexor fusion (A/B switch); else 0                     */
 } b2sv_plan_opts;
 
 /* Subspace program (restates Subspace.test_basis / enumerate_basis,

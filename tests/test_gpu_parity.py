@@ -23,6 +23,7 @@ VARIANTS = {
     "small_tiles": dict(tile_qubits=5, lookahead=4),
     "jit_sync": dict(jit="sync"),
     "jit_off": dict(jit="off"),
+    "no_mux": dict(mux=False),
 }
 
 

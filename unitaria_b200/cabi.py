@@ -56,7 +56,7 @@ class PlanOpts(ctypes.Structure):
     ]
 
     @classmethod
-    def make(cls, fuse=True, tile_qubits=0, perm_runs=True, timing=False, lookahead=0, plain_tile_io=False, jit="auto"):
+    def make(cls, fuse=True, tile_qubits=0, perm_runs=True, timing=False, lookahead=0, plain_tile_io=False, jit="auto", mux=True):
         o = cls()
         o.fuse = int(bool(fuse))
         o.tile_qubits = int(tile_qubits)
@@ -65,6 +65,7 @@ class PlanOpts(ctypes.Structure):
         o.lookahead = int(lookahead)
         o.tile_io = 1 if plain_tile_io else 0
         o.jit = {"auto": 0, "off": 1, "sync": 2}[jit]
+        o.reserved = 0 if mux else 1
         return o
 
 

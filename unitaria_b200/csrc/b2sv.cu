@@ -69,6 +69,8 @@ struct b2sv {
     double sre = 1.0, sim = 0.0;   // pending global scalar (folded uncontrolled global phases)
     void* d_ops = nullptr;         // device copy of the tile ops of the current apply
     size_t d_ops_cap = 0;
+    void* d_tables = nullptr;      // device copy of the multiplexor tables of the current apply
+    size_t d_tables_cap = 0;
     void* d_gather = nullptr;      // device-side result buffer of project_gather / enumerate_basis
     size_t d_gather_cap = 0;
     b2sv_subinstr* d_sub = nullptr; // device copy of the current subspace program
@@ -256,7 +258,7 @@ int launch_gate1(b2sv* sv, const PGate& g, bool timing) {
 }
 
 // Translate a planned gate into a tile-local op for the tile with (ascending) qubit positions `ex`.
-TileOp make_tile_op(const PGate& g, uint64_t tile_mask, const ExpandArgs& ex) {
+TileOp make_tile_op(const Plan& plan, const PGate& g, uint64_t tile_mask, const ExpandArgs& ex) {
     TileOp op{};
     auto local_pos = [&](int q) -> int {
         for (int i = 0; i < ex.m; ++i)
@@ -303,6 +305,19 @@ TileOp make_tile_op(const PGate& g, uint64_t tile_mask, const ExpandArgs& ex) {
             op.nfix++;
         }
     std::memcpy(op.m, g.m, sizeof(op.m));
+    if (g.op == B2SV_OP_MUX) {
+        const MuxInfo& mi = plan.mux[g.mux];
+        op.mux.table_off = mi.table_off;
+        op.mux.nmux = (uint8_t)mi.nbits;
+        int j = 0;
+        for (int q = 0; q < 64 && j < mi.nbits; ++q)
+            if ((mi.ctrl_mask >> q) & 1) {
+                const int lp = local_pos(q);
+                op.mux.mpos[j] = lp < 0 ? 0xFF : (uint8_t)lp;
+                op.mux.mq[j] = (uint8_t)q;
+                ++j;
+            }
+    }
     return op;
 }
 
@@ -334,6 +349,7 @@ int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, co
     a.lc = lc;
     a.n_ops = n_ops;
     a.ops = d_ops;
+    a.tables = (const double2*)sv->d_tables;
     const uint64_t n_tiles = 1ull << (sv->n - a.k);
     if (n_ops > kTileMaxOps) return fail(B2SV_EINVAL, "tile sweep with %d ops (max %d)", n_ops, kTileMaxOps);
     const size_t smem = ((size_t)sv->amp_bytes << a.k) + (size_t)kTileMaxOps * sizeof(TileOp);
@@ -678,6 +694,7 @@ int b2sv_destroy(b2sv_t* sv) {
     cudaFree(sv->amps);
     cudaFree(sv->scratch);
     cudaFree(sv->d_ops);
+    cudaFree(sv->d_tables);
     cudaFree(sv->d_partial);
     cudaFree(sv->d_sub);
     cudaFree(sv->d_gather);
@@ -780,6 +797,7 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
     for (size_t j = 0; j < n_gates; ++j) {
         const b2sv_gate& g = gates[j];
         if (g.op > B2SV_OP_PHASE) return fail(B2SV_EINVAL, "gate %zu: unknown op %d", j, (int)g.op);
+        if (g.op == B2SV_OP_SWAP && g.t0 == g.t1) return fail(B2SV_EINVAL, "gate %zu: SWAP of a qubit with itself", j);
         const uint64_t all = sv->n >= 64 ? ~0ull : ((1ull << sv->n) - 1);
         if (g.ctrl_mask & ~all) return fail(B2SV_EINVAL, "gate %zu: control outside the %d-qubit register", j, sv->n);
         if (g.op != B2SV_OP_PHASE) {
@@ -825,7 +843,7 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
         ExpandArgs ex;
         fill_expand(ex, seg.tile_mask);
         seg_first[s] = host_ops.size();
-        for (int gi : seg.gates) host_ops.push_back(make_tile_op(plan.gates[gi], seg.tile_mask, ex));
+        for (int gi : seg.gates) host_ops.push_back(make_tile_op(plan, plan.gates[gi], seg.tile_mask, ex));
     }
     if (!host_ops.empty()) {
         const size_t bytes = host_ops.size() * sizeof(TileOp);
@@ -833,12 +851,25 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
             // a previous apply may still be reading the old buffer
             CU(cudaStreamSynchronize(sv->stream));
             cudaFree(sv->d_ops);
+    cudaFree(sv->d_tables);
             sv->d_ops = nullptr;
             sv->d_ops_cap = 0;
             CU(cudaMalloc(&sv->d_ops, bytes * 2));
             sv->d_ops_cap = bytes * 2;
         }
         CU(cudaMemcpyAsync(sv->d_ops, host_ops.data(), bytes, cudaMemcpyHostToDevice, sv->stream));
+    }
+    if (!plan.mux_tables.empty()) {
+        const size_t bytes = plan.mux_tables.size() * sizeof(double);
+        if (bytes > sv->d_tables_cap) {
+            CU(cudaStreamSynchronize(sv->stream));
+            cudaFree(sv->d_tables);
+            sv->d_tables = nullptr;
+            sv->d_tables_cap = 0;
+            CU(cudaMalloc(&sv->d_tables, bytes * 2));
+            sv->d_tables_cap = bytes * 2;
+        }
+        CU(cudaMemcpyAsync(sv->d_tables, plan.mux_tables.data(), bytes, cudaMemcpyHostToDevice, sv->stream));
     }
     cudaEvent_t ev_a = get_event(sv), ev_b = get_event(sv);
     CU(cudaEventRecord(ev_a, sv->stream));
@@ -1057,10 +1088,17 @@ int b2sv_plan_describe(int n_qubits, int dtype, const b2sv_gate* gates, size_t n
         ++w;
     };
     for (const Segment& seg : plan.segs) {
+        size_t n_src = 0;
+        for (int gi : seg.gates) n_src += plan.gates[gi].mux >= 0 ? plan.mux[plan.gates[gi].mux].sources.size() : 1;
         put(seg.cls);
-        put((int64_t)seg.gates.size());
+        put((int64_t)n_src);
         put((int64_t)seg.tile_mask);
-        for (int gi : seg.gates) put(plan.gates[gi].src);
+        for (int gi : seg.gates) {
+            if (plan.gates[gi].mux >= 0)
+                for (int sidx : plan.mux[plan.gates[gi].mux].sources) put(sidx);
+            else
+                put(plan.gates[gi].src);
+        }
     }
     {  // trailer: the folded global scalar, as raw IEEE bits
         int64_t re_bits, im_bits;

@@ -126,8 +126,17 @@ struct __align__(16) TileOp {
     uint64_t fixpos;      // nfix ascending tile-local positions, 4 bits each
     uint64_t ext_ctrl;    // controls outside the tile (global index bits)
     uint64_t ext_tbit;    // DIAG1 whose target is outside the tile: that global bit
-    double m[8];
+    union {
+        double m[8];
+        struct {               // op == kOpMux: table of 2x2 matrices indexed by control bits
+            uint64_t table_off;    // first entry (4 double2 per entry) in TileArgs::tables
+            uint8_t nmux;
+            uint8_t mpos[7];       // per index bit: tile-local position, or 0xFF when outside the tile
+            uint8_t mq[8];         // per index bit: global qubit
+        } mux;
+    };
 };
+constexpr int kOpMux = 5;
 static_assert(sizeof(TileOp) == 96, "TileOp layout");
 
 struct TileArgs {
@@ -135,6 +144,7 @@ struct TileArgs {
     int k, lc;
     int n_ops;
     const TileOp* ops;
+    const double2* tables;  // multiplexor tables of this apply
 };
 
 __device__ __forceinline__ uint32_t expand_local(uint32_t p, uint64_t fixpos, int nfix) {
@@ -201,7 +211,8 @@ __device__ __forceinline__ void tile_for_each(uint32_t cnt, uint64_t fixpos, int
 }
 
 template <typename A>
-__device__ __forceinline__ void tile_apply_op(A* tile, const TileOp& op, int k, uint64_t base) {
+__device__ __forceinline__ void tile_apply_op(A* tile, const TileOp& op, int k, uint64_t base,
+                                              const double2* __restrict__ tables) {
     const uint32_t cnt = 1u << (k - op.nfix);
     const uint64_t fixpos = op.fixpos;
     const int nfix = op.nfix;
@@ -296,6 +307,45 @@ __device__ __forceinline__ void tile_apply_op(A* tile, const TileOp& op, int k, 
                 });
             }
         } break;
+        case kOpMux: {
+            // one pass over all pairs of the target; the 2x2 matrix of a pair is looked up by the
+            // pair's control bits (tile-local ones per element, outside ones CTA-uniform)
+            const uint32_t bt = 1u << op.tpos;
+            const int nmux = op.mux.nmux;
+            uint32_t idx_ext = 0, lsel = 0;
+            uint8_t lp[7];
+            int nl = 0, ljb[7];
+            for (int j = 0; j < nmux; ++j) {
+                if (op.mux.mpos[j] == 0xFF) idx_ext |= (uint32_t)((base >> op.mux.mq[j]) & 1ull) << j;
+                else {
+                    lp[nl] = op.mux.mpos[j];
+                    ljb[nl] = j;
+                    ++nl;
+                }
+            }
+            (void)lsel;
+            const double2* __restrict__ tab = tables + op.mux.table_off * 4;
+            tile_for_each<2>(cnt, fixpos, nfix, 0u, [&](const uint32_t* l, int m) {
+                double2 v0[2], v1[2];
+                const double2* M[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    if (u < m) {
+                        uint32_t idx = idx_ext;
+                        for (int j = 0; j < nl; ++j) idx |= ((l[u] >> lp[j]) & 1u) << ljb[j];
+                        M[u] = tab + (size_t)idx * 4;
+                        v0[u] = to_c128(tile[l[u]]);
+                        v1[u] = to_c128(tile[l[u] | bt]);
+                    }
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    if (u < m) {
+                        const double2 m00 = __ldg(M[u]), m01 = __ldg(M[u] + 1), m10 = __ldg(M[u] + 2), m11 = __ldg(M[u] + 3);
+                        tile[l[u]] = from_c128<A>(cfma(m01, v1[u], cmul(m00, v0[u])));
+                        tile[l[u] | bt] = from_c128<A>(cfma(m11, v1[u], cmul(m10, v0[u])));
+                    }
+            });
+        } break;
         default: {  // PHASE
             const double2 w = make_double2(op.m[0], op.m[1]);
             tile_for_each<4>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
@@ -363,7 +413,7 @@ __global__ void __launch_bounds__(kThreads) k_tile(A* __restrict__ psi, const Ti
     for (int o = 0; o < a.n_ops; ++o) {
         const TileOp& op = s_ops[o];
         if ((base & op.ext_ctrl) != op.ext_ctrl) continue;  // CTA-uniform: gate not active on this tile
-        tile_apply_op<A>(tile, op, k, base);
+        tile_apply_op<A>(tile, op, k, base, a.tables);
         __syncthreads();
     }
 

@@ -34,6 +34,8 @@ namespace b2svk {
 
 enum SegClass { SEG_GATE1Q = 0, SEG_TILE = 1, SEG_PERM = 2 };
 constexpr int kPermMaxCtrlX = 7, kPermMaxCtrlSwap = 6;
+constexpr int B2SV_OP_MUX = 5;        // internal: fused same-target run, a table of 2x2 matrices indexed by control bits
+constexpr int kMuxMaxCtrl = 6;        // table of at most 64 matrices (4 KiB)
 constexpr int kPlanMaxTileOps = 112;  // gates per tile sweep (their ops are staged in shared memory)
 
 struct PGate {
@@ -44,6 +46,7 @@ struct PGate {
     uint64_t qmask;   // every qubit the gate touches
     double m[8];
     int src;          // index in the caller's list
+    int mux = -1;     // B2SV_OP_MUX: index into Plan::mux
     bool is_perm() const { return op == B2SV_OP_X || op == B2SV_OP_SWAP; }
     // fits the word-op encoding of the permutation-run kernel (3 direct control slots, 2 for SWAP,
     // plus two per scratch row)
@@ -70,9 +73,23 @@ struct PlanConfig {
     int perm_min = 12;          // shortest run worth an out-of-place sweep
     double perm_gate_cost = 1.0 / 300.0;  // cost of one perm gate in units of one full sweep
     bool always_tile_below = true;        // small states: prefer the fewest launches
+    bool mux = true;                      // fuse same-target runs into multiplexed 2x2 ops
+};
+
+// A run of consecutive gates on ONE target whose other qubits are only controls multiplies out to
+// sum_c |c><c| (x) M_c: one 2x2 matrix per value c of the union of the control qubits.  This is what
+// Moettoenen state preparation emits (circuits/multiplexed_rot.py:8-77: Ry/Rz interleaved with CNOTs
+// onto the same target) and what LCU / cosine-sine rotations look like after add_controls.
+struct MuxInfo {
+    uint64_t ctrl_mask = 0;      // union of the controls, table index = those bits in ascending order
+    int nbits = 0;
+    size_t table_off = 0;        // first entry in Plan::mux_tables (8 doubles per entry)
+    std::vector<int> sources;    // caller's gate indices, execution order
 };
 
 struct Plan {
+    std::vector<MuxInfo> mux;
+    std::vector<double> mux_tables;
     std::vector<PGate> gates;
     std::vector<Segment> segs;
     double scalar_re = 1.0, scalar_im = 0.0;  // folded uncontrolled global phases
@@ -93,6 +110,7 @@ inline PlanConfig default_config(int n, int dtype, const b2sv_plan_opts* o) {
         c.perm_runs = o->perm_runs != 0;
         if (o->tile_qubits > 0) c.tile_qubits = o->tile_qubits;
         if (o->lookahead > 0) c.lookahead = o->lookahead;
+        c.mux = o->reserved != 1;  // reserved == 1: no multiplexor fusion (A/B switch for tests and profiling)
     }
     if (c.tile_qubits > 13 && c.amp_bytes == 16) c.tile_qubits = 13;
     if (c.tile_qubits > 14) c.tile_qubits = 14;
@@ -171,6 +189,110 @@ inline bool same_perm_gate(const PGate& a, const PGate& b) {
     return (a.t0 == b.t0 && a.t1 == b.t1) || (a.t0 == b.t1 && a.t1 == b.t0);
 }
 
+// ---- same-target multiplexor fusion -------------------------------------------------------------
+
+inline bool single_target_gate(const PGate& g) {
+    return g.op == B2SV_OP_MAT1 || g.op == B2SV_OP_DIAG1 || g.op == B2SV_OP_X;
+}
+
+inline void gate_matrix2(const PGate& g, double m[8]) {
+    for (int i = 0; i < 8; ++i) m[i] = 0.0;
+    if (g.op == B2SV_OP_MAT1) {
+        for (int i = 0; i < 8; ++i) m[i] = g.m[i];
+    } else if (g.op == B2SV_OP_DIAG1) {
+        m[0] = g.m[0];
+        m[1] = g.m[1];
+        m[6] = g.m[2];
+        m[7] = g.m[3];
+    } else {  // X
+        m[2] = 1.0;
+        m[4] = 1.0;
+    }
+}
+
+// c = a * b (2x2 complex, row-major, (re,im) pairs)
+inline void matmul2(const double a[8], const double b[8], double c[8]) {
+    for (int r = 0; r < 2; ++r)
+        for (int col = 0; col < 2; ++col) {
+            double re = 0, im = 0;
+            for (int k = 0; k < 2; ++k) {
+                const double ar = a[2 * (2 * r + k)], ai = a[2 * (2 * r + k) + 1];
+                const double br = b[2 * (2 * k + col)], bi = b[2 * (2 * k + col) + 1];
+                re += ar * br - ai * bi;
+                im += ar * bi + ai * br;
+            }
+            c[2 * (2 * r + col)] = re;
+            c[2 * (2 * r + col) + 1] = im;
+        }
+}
+
+inline void fuse_multiplexors(Plan& plan) {
+    std::vector<PGate> out;
+    out.reserve(plan.gates.size());
+    const std::vector<PGate>& G = plan.gates;
+    size_t i = 0;
+    while (i < G.size()) {
+        const PGate& g = G[i];
+        if (!single_target_gate(g) || popcount64(g.ctrl) > kMuxMaxCtrl) {
+            out.push_back(g);
+            ++i;
+            continue;
+        }
+        uint64_t C = g.ctrl;
+        bool nonperm = !g.is_perm();
+        size_t j = i + 1;
+        while (j < G.size() && single_target_gate(G[j]) && G[j].t0 == g.t0 && popcount64(C | G[j].ctrl) <= kMuxMaxCtrl) {
+            C |= G[j].ctrl;
+            nonperm |= !G[j].is_perm();
+            ++j;
+        }
+        const size_t len = j - i;
+        const bool worth = nonperm && (len >= 3 || (len == 2 && C == 0));
+        if (!worth) {
+            out.push_back(g);
+            ++i;
+            continue;
+        }
+        MuxInfo info;
+        info.ctrl_mask = C;
+        info.nbits = popcount64(C);
+        info.table_off = plan.mux_tables.size() / 8;
+        int cpos[kMuxMaxCtrl];
+        int nb = 0;
+        for (int q = 0; q < 64; ++q)
+            if ((C >> q) & 1) cpos[nb++] = q;
+        for (uint32_t c = 0; c < (1u << nb); ++c) {
+            uint64_t pattern = 0;
+            for (int b = 0; b < nb; ++b)
+                if ((c >> b) & 1) pattern |= 1ull << cpos[b];
+            double M[8] = {1, 0, 0, 0, 0, 0, 1, 0};
+            for (size_t q = i; q < j; ++q) {
+                if ((G[q].ctrl & pattern) != G[q].ctrl) continue;
+                double U[8], R[8];
+                gate_matrix2(G[q], U);
+                matmul2(U, M, R);
+                for (int e = 0; e < 8; ++e) M[e] = R[e];
+            }
+            plan.mux_tables.insert(plan.mux_tables.end(), M, M + 8);
+        }
+        for (size_t q = i; q < j; ++q) info.sources.push_back(G[q].src);
+        PGate f;
+        f.op = B2SV_OP_MUX;
+        f.t0 = g.t0;
+        f.t1 = 0;
+        f.ctrl = 0;  // no predicate: every amplitude pair is touched, the table entry depends on the control bits
+        f.tmask = 1ull << g.t0;
+        f.qmask = C | f.tmask;
+        for (int e = 0; e < 8; ++e) f.m[e] = 0;
+        f.src = g.src;
+        f.mux = (int)plan.mux.size();
+        plan.mux.push_back(std::move(info));
+        out.push_back(f);
+        i = j;
+    }
+    plan.gates.swap(out);
+}
+
 // ---- tile packing -----------------------------------------------------------------------------
 
 inline double gate_sweep_fraction(const PGate& g) {
@@ -222,7 +344,9 @@ inline void plan_tiles(const std::vector<PGate>& G, const std::vector<int>& idx,
         double frac = 0;
         for (int gi : seg.gates) frac += gate_sweep_fraction(G[gi]);
         const bool small_state = cfg.always_tile_below && n <= 16;
-        if (!small_state && frac <= 0.55 && seg.gates.size() <= 8) {
+        bool has_mux = false;
+        for (int gi : seg.gates) has_mux |= G[gi].op == B2SV_OP_MUX;
+        if (!small_state && !has_mux && frac <= 0.55 && seg.gates.size() <= 8) {
             for (int gi : seg.gates) {
                 Segment one;
                 one.cls = SEG_GATE1Q;
@@ -253,6 +377,7 @@ inline Plan make_plan(const b2sv_gate* gates, size_t n_gates, const PlanConfig& 
         plan.gates.push_back(g);
     }
     plan.gates_live = plan.gates.size();
+    if (cfg.fuse && cfg.mux) fuse_multiplexors(plan);
     const std::vector<PGate>& G = plan.gates;
     if (!cfg.fuse) {
         for (size_t j = 0; j < G.size(); ++j) {
