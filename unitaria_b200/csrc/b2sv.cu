@@ -851,7 +851,6 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
             // a previous apply may still be reading the old buffer
             CU(cudaStreamSynchronize(sv->stream));
             cudaFree(sv->d_ops);
-    cudaFree(sv->d_tables);
             sv->d_ops = nullptr;
             sv->d_ops_cap = 0;
             CU(cudaMalloc(&sv->d_ops, bytes * 2));
