@@ -134,3 +134,25 @@ def test_permutation_run_specialisation_compiles_with_nvrtc():
     perm = low[(low["op"] == cabi.OP_X) | (low["op"] == cabi.OP_SWAP)].copy()
     rc = lib.b2sv_perm_jit_compile_check(case.n_qubits, cabi.B2SV_C128, perm.ctypes.data, len(perm), ctypes.byref(size))
     assert rc == 0, lib.b2sv_last_error()
+
+
+@pytest.mark.parametrize("name", ["cfg4_bpx_L8", "bpx_L4", "pinv_bpx_L2"])
+def test_common_controls_restrict_tile_sweeps(name):
+    """Block-encoding circuits keep whole stretches under selector controls: a tile sweep whose gates
+    all share controls outside its tile only launches the tiles where they are 1."""
+    case = load_golden(name)
+    n = case.n_qubits
+    live = [g for g in case.gates if g.name != "I"]
+    low = lower_gates(live, n)
+    segs, _scalar, common = cabi.plan_describe(n, cabi.B2SV_C128, low, cabi.PlanOpts.make(mux=False), with_common=True)
+    restricted = 0
+    for (cls, mask, idx), com in zip(segs, common):
+        if cls != cabi.SEG_TILE:
+            assert com == 0
+            continue
+        assert com & mask == 0
+        for gi in idx:
+            assert int(low[gi]["ctrl_mask"]) & com == com, (name, gi)
+        restricted += com != 0
+    if n >= 17:
+        assert restricted > 0

@@ -177,7 +177,7 @@ def device_count() -> int:
     return int(load().b2sv_device_count())
 
 
-def plan_describe(n_qubits: int, dtype: int, gates: np.ndarray, opts: PlanOpts | None = None):
+def plan_describe(n_qubits: int, dtype: int, gates: np.ndarray, opts: PlanOpts | None = None, with_common: bool = False):
     """Planner introspection (host only, needs no GPU): list of (class, tile_mask, [gate indices]) and
     the folded global scalar."""
     lib = load()
@@ -190,14 +190,18 @@ def plan_describe(n_qubits: int, dtype: int, gates: np.ndarray, opts: PlanOpts |
     segs = []
     scalar = 1.0 + 0.0j
     i = 0
+    common = []
     while i < len(words):
-        cls, cnt, mask = int(words[i]), int(words[i + 1]), int(words[i + 2])
+        cls, cnt, mask, com = int(words[i]), int(words[i + 1]), int(words[i + 2]), int(words[i + 3])
         if cls == -1:
-            re = np.array([words[i + 2]], dtype=np.int64).view(np.float64)[0]
-            im = np.array([words[i + 3]], dtype=np.int64).view(np.float64)[0]
+            re = np.array([words[i + 4]], dtype=np.int64).view(np.float64)[0]
+            im = np.array([words[i + 5]], dtype=np.int64).view(np.float64)[0]
             scalar = complex(re, im)
-            i += 4
+            i += 6
             continue
-        segs.append((cls, mask & 0xFFFFFFFFFFFFFFFF, [int(w) for w in words[i + 3 : i + 3 + cnt]]))
-        i += 3 + cnt
+        segs.append((cls, mask & 0xFFFFFFFFFFFFFFFF, [int(w) for w in words[i + 4 : i + 4 + cnt]]))
+        common.append(com & 0xFFFFFFFFFFFFFFFF)
+        i += 4 + cnt
+    if with_common:
+        return segs, scalar, common
     return segs, scalar

@@ -307,6 +307,7 @@ TileOp make_tile_op(const Plan& plan, const PGate& g, uint64_t tile_mask, const 
     std::memcpy(op.m, g.m, sizeof(op.m));
     if (g.op == B2SV_OP_MUX) {
         const MuxInfo& mi = plan.mux[g.mux];
+        // g.ctrl (the run's common controls) is already a predicate in lctrl / ext_ctrl
         op.mux.table_off = mi.table_off;
         op.mux.nmux = (uint8_t)mi.nbits;
         int j = 0;
@@ -341,6 +342,9 @@ int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, co
                 bool timing) {
     TileArgs a{};
     fill_expand(a.tile_ex, seg.tile_mask);
+    if (popcount64(seg.tile_mask | seg.common_ctrl) > kMaxFixed) return fail(B2SV_EINVAL, "tile + common controls exceed %d qubits", kMaxFixed);
+    fill_expand(a.cta_ex, seg.tile_mask | seg.common_ctrl);
+    a.cta_or = seg.common_ctrl;
     a.k = a.tile_ex.m;
     int lc = 0;
     while (lc < a.k && a.tile_ex.pos[lc] == lc) ++lc;  // contiguous low run of the tile
@@ -350,14 +354,14 @@ int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, co
     a.n_ops = n_ops;
     a.ops = d_ops;
     a.tables = (const double2*)sv->d_tables;
-    const uint64_t n_tiles = 1ull << (sv->n - a.k);
+    const uint64_t n_tiles = 1ull << (sv->n - a.cta_ex.m);
     if (n_ops > kTileMaxOps) return fail(B2SV_EINVAL, "tile sweep with %d ops (max %d)", n_ops, kTileMaxOps);
     const size_t smem = ((size_t)sv->amp_bytes << a.k) + (size_t)kTileMaxOps * sizeof(TileOp);
     return dispatch_dtype(sv, [&](auto* tag) -> int {
         using A = std::remove_pointer_t<decltype(tag)>;
         int rc = set_tile_smem<A>(smem);
         if (rc) return rc;
-        LaunchTimer lt(sv, timing, CLS_TILE, 2.0 * sv->amp_bytes * (double)sv->count);
+        LaunchTimer lt(sv, timing, CLS_TILE, 2.0 * sv->amp_bytes * (double)(n_tiles << a.k));
         if (bulk)
             k_tile<A, true><<<(unsigned)n_tiles, kThreads, smem, sv->stream>>>((A*)sv->amps, a);
         else
@@ -1092,6 +1096,7 @@ int b2sv_plan_describe(int n_qubits, int dtype, const b2sv_gate* gates, size_t n
         put(seg.cls);
         put((int64_t)n_src);
         put((int64_t)seg.tile_mask);
+        put((int64_t)seg.common_ctrl);
         for (int gi : seg.gates) {
             if (plan.gates[gi].mux >= 0)
                 for (int sidx : plan.mux[plan.gates[gi].mux].sources) put(sidx);
@@ -1105,6 +1110,8 @@ int b2sv_plan_describe(int n_qubits, int dtype, const b2sv_gate* gates, size_t n
         std::memcpy(&im_bits, &plan.scalar_im, 8);
         put(-1);
         put(2);
+        put(0);
+        put(0);
         put(re_bits);
         put(im_bits);
     }

@@ -140,6 +140,8 @@ constexpr int kOpMux = 5;
 static_assert(sizeof(TileOp) == 96, "TileOp layout");
 
 struct TileArgs {
+    ExpandArgs cta_ex;    // tile qubits + the sweep's common outside controls: block index -> tile base
+    uint64_t cta_or;      // the common outside controls (set in every launched tile's base)
     ExpandArgs tile_ex;   // the k tile-qubit positions (ascending)
     int k, lc;
     int n_ops;
@@ -325,7 +327,7 @@ __device__ __forceinline__ void tile_apply_op(A* tile, const TileOp& op, int k, 
             }
             (void)lsel;
             const double2* __restrict__ tab = tables + op.mux.table_off * 4;
-            tile_for_each<2>(cnt, fixpos, nfix, 0u, [&](const uint32_t* l, int m) {
+            tile_for_each<2>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
                 double2 v0[2], v1[2];
                 const double2* M[2];
 #pragma unroll
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__(kThreads) k_tile(A* __restrict__ psi, const Ti
     const int tid = threadIdx.x;
     const uint32_t n_chunks = 1u << (k - lc), chunk_elems = 1u << lc;
     const uint32_t chunk_bytes = chunk_elems * (uint32_t)sizeof(A);
-    const uint64_t base = expand_bits((uint64_t)blockIdx.x, a.tile_ex);
+    const uint64_t base = expand_bits((uint64_t)blockIdx.x, a.cta_ex) | a.cta_or;
 
     if (BULK) {
         if (tid == 0) {

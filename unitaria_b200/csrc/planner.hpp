@@ -59,6 +59,8 @@ struct PGate {
 struct Segment {
     int cls;
     uint64_t tile_mask;  // SEG_TILE only
+    uint64_t common_ctrl = 0;  // SEG_TILE: controls shared by EVERY gate of the sweep that lie outside the
+                               // tile -- only the 2^-|common| tiles with those bits set are launched
     std::vector<int> gates;  // indices into Plan::gates, execution order
 };
 
@@ -189,6 +191,12 @@ inline bool same_perm_gate(const PGate& a, const PGate& b) {
     return (a.t0 == b.t0 && a.t1 == b.t1) || (a.t0 == b.t1 && a.t1 == b.t0);
 }
 
+inline double gate_sweep_fraction(const PGate& g) {
+    int c = popcount64(g.ctrl);
+    if (g.op == B2SV_OP_SWAP) c += 1;
+    return std::ldexp(1.0, -c);
+}
+
 // ---- same-target multiplexor fusion -------------------------------------------------------------
 
 inline bool single_target_gate(const PGate& g) {
@@ -226,6 +234,19 @@ inline void matmul2(const double a[8], const double b[8], double c[8]) {
         }
 }
 
+// Returns false when the gate is an exact no-op (same contract as normalise_gate) -- used to
+// re-normalise the product of a fused run.
+inline bool renormalise(PGate& g, double& sre, double& sim) {
+    b2sv_gate raw{};
+    raw.op = g.op;
+    raw.t0 = g.t0;
+    raw.t1 = g.t1;
+    raw.ctrl_mask = g.ctrl;
+    std::memcpy(raw.m, g.m, sizeof(raw.m));
+    const int src = g.src;
+    return normalise_gate(raw, src, g, sre, sim);
+}
+
 inline void fuse_multiplexors(Plan& plan) {
     std::vector<PGate> out;
     out.reserve(plan.gates.size());
@@ -233,58 +254,83 @@ inline void fuse_multiplexors(Plan& plan) {
     size_t i = 0;
     while (i < G.size()) {
         const PGate& g = G[i];
-        if (!single_target_gate(g) || popcount64(g.ctrl) > kMuxMaxCtrl) {
+        if (!single_target_gate(g)) {
             out.push_back(g);
             ++i;
             continue;
         }
-        uint64_t C = g.ctrl;
+        uint64_t U = g.ctrl, K = g.ctrl;  // union / intersection of the controls of the run
         bool nonperm = !g.is_perm();
+        double separate = gate_sweep_fraction(g);
         size_t j = i + 1;
-        while (j < G.size() && single_target_gate(G[j]) && G[j].t0 == g.t0 && popcount64(C | G[j].ctrl) <= kMuxMaxCtrl) {
-            C |= G[j].ctrl;
+        while (j < G.size() && single_target_gate(G[j]) && G[j].t0 == g.t0 &&
+               popcount64((U | G[j].ctrl) & ~(K & G[j].ctrl)) <= kMuxMaxCtrl) {
+            U |= G[j].ctrl;
+            K &= G[j].ctrl;
             nonperm |= !G[j].is_perm();
+            separate += gate_sweep_fraction(G[j]);
             ++j;
         }
         const size_t len = j - i;
-        const bool worth = nonperm && (len >= 3 || (len == 2 && C == 0));
+        const uint64_t C = U & ~K;  // the table is indexed by the non-common controls only
+        const double scale = std::ldexp(1.0, -popcount64(K));
+        // one table-driven pass over the K-controlled block costs about 2.5 plain passes; a product
+        // with a single entry is just another 2x2 gate
+        const bool worth = nonperm && len >= 2 && (C == 0 ? true : (len >= 3 && separate > 2.5 * scale));
         if (!worth) {
             out.push_back(g);
             ++i;
             continue;
         }
-        MuxInfo info;
-        info.ctrl_mask = C;
-        info.nbits = popcount64(C);
-        info.table_off = plan.mux_tables.size() / 8;
         int cpos[kMuxMaxCtrl];
         int nb = 0;
         for (int q = 0; q < 64; ++q)
             if ((C >> q) & 1) cpos[nb++] = q;
+        std::vector<double> table;
+        table.reserve((size_t)8 << nb);
         for (uint32_t c = 0; c < (1u << nb); ++c) {
-            uint64_t pattern = 0;
+            uint64_t pattern = K;
             for (int b = 0; b < nb; ++b)
                 if ((c >> b) & 1) pattern |= 1ull << cpos[b];
             double M[8] = {1, 0, 0, 0, 0, 0, 1, 0};
             for (size_t q = i; q < j; ++q) {
                 if ((G[q].ctrl & pattern) != G[q].ctrl) continue;
-                double U[8], R[8];
-                gate_matrix2(G[q], U);
-                matmul2(U, M, R);
+                double Ug[8], R[8];
+                gate_matrix2(G[q], Ug);
+                matmul2(Ug, M, R);
                 for (int e = 0; e < 8; ++e) M[e] = R[e];
             }
-            plan.mux_tables.insert(plan.mux_tables.end(), M, M + 8);
+            table.insert(table.end(), M, M + 8);
         }
-        for (size_t q = i; q < j; ++q) info.sources.push_back(G[q].src);
         PGate f;
-        f.op = B2SV_OP_MUX;
         f.t0 = g.t0;
         f.t1 = 0;
-        f.ctrl = 0;  // no predicate: every amplitude pair is touched, the table entry depends on the control bits
-        f.tmask = 1ull << g.t0;
-        f.qmask = C | f.tmask;
-        for (int e = 0; e < 8; ++e) f.m[e] = 0;
+        f.ctrl = K;  // a real predicate: only the K-controlled block is touched
         f.src = g.src;
+        MuxInfo info;
+        for (size_t q = i; q < j; ++q) info.sources.push_back(G[q].src);
+        if (nb == 0) {
+            // plain product: still one gate, but remember what it stands for
+            f.op = B2SV_OP_MAT1;
+            for (int e = 0; e < 8; ++e) f.m[e] = table[e];
+            if (renormalise(f, plan.scalar_re, plan.scalar_im)) {
+                info.ctrl_mask = 0;
+                info.nbits = -1;  // marks "sources only"
+                f.mux = (int)plan.mux.size();
+                plan.mux.push_back(std::move(info));
+                out.push_back(f);
+            }
+            i = j;
+            continue;
+        }
+        info.ctrl_mask = C;
+        info.nbits = nb;
+        info.table_off = plan.mux_tables.size() / 8;
+        plan.mux_tables.insert(plan.mux_tables.end(), table.begin(), table.end());
+        f.op = B2SV_OP_MUX;
+        f.tmask = 1ull << g.t0;
+        f.qmask = U | f.tmask;
+        for (int e = 0; e < 8; ++e) f.m[e] = 0;
         f.mux = (int)plan.mux.size();
         plan.mux.push_back(std::move(info));
         out.push_back(f);
@@ -295,11 +341,8 @@ inline void fuse_multiplexors(Plan& plan) {
 
 // ---- tile packing -----------------------------------------------------------------------------
 
-inline double gate_sweep_fraction(const PGate& g) {
-    int c = popcount64(g.ctrl);
-    if (g.op == B2SV_OP_SWAP) c += 1;
-    return std::ldexp(1.0, -c);
-}
+// Cost of a sweep in units of one full pass over the state.
+inline double sweep_cost(uint64_t common_outside) { return std::ldexp(1.0, -popcount64(common_outside)); }
 
 inline void plan_tiles(const std::vector<PGate>& G, const std::vector<int>& idx, const PlanConfig& cfg,
                        std::vector<Segment>& out) {
@@ -315,6 +358,7 @@ inline void plan_tiles(const std::vector<PGate>& G, const std::vector<int>& idx,
         Segment seg;
         seg.cls = SEG_TILE;
         uint64_t T = base;
+        uint64_t K = ~0ull;  // controls common to every gate taken so far
         uint64_t blocked_any = 0, blocked_nd = 0;
         int scanned = 0;
         for (size_t p = head; p < idx.size() && scanned < cfg.lookahead && (int)seg.gates.size() < kPlanMaxTileOps; ++p) {
@@ -322,9 +366,22 @@ inline void plan_tiles(const std::vector<PGate>& G, const std::vector<int>& idx,
             ++scanned;
             const PGate& g = G[idx[p]];
             const bool commutes = ((g.tmask & blocked_any) == 0) && ((g.qmask & blocked_nd) == 0);
-            const bool fits = popcount64(T | g.tmask) <= k;
-            if (commutes && fits) {
-                T |= g.tmask;
+            const uint64_t T2 = T | g.tmask;
+            const bool fits = popcount64(T2) <= k;
+            // Block-encoding circuits put whole stretches under the same selector controls
+            // (BlockDiagonal / LCU / QSVT flag qubits).  A sweep whose gates ALL share controls outside
+            // the tile only has to visit the tiles where those bits are 1, so do not let one gate
+            // with fewer controls make everybody else's sweep bigger.
+            bool cheap = true;
+            if (!seg.gates.empty()) {
+                const double now = sweep_cost(K & ~T2);
+                const double joined = sweep_cost(K & g.ctrl & ~T2);
+                const double alone = sweep_cost(g.ctrl & ~(base | g.tmask));
+                cheap = joined <= now + 0.5 * alone;
+            }
+            if (commutes && fits && cheap) {
+                T = T2;
+                K &= g.ctrl;
                 seg.gates.push_back(idx[p]);
                 done[p] = 1;
             } else {
@@ -337,16 +394,21 @@ inline void plan_tiles(const std::vector<PGate>& G, const std::vector<int>& idx,
             seg.gates.push_back(idx[head]);
             done[head] = 1;
             T |= G[idx[head]].tmask;
+            K = G[idx[head]].ctrl;
         }
-        for (int q = 0; q < n && popcount64(T) < k; ++q) T |= 1ull << q;  // pad with the lowest qubits
+        // pad with the lowest qubits that are not common controls (a bit fixed to 1 is wasted in a tile)
+        for (int q = 0; q < n && popcount64(T) < k; ++q)
+            if (!((K >> q) & 1)) T |= 1ull << q;
+        for (int q = 0; q < n && popcount64(T) < k; ++q) T |= 1ull << q;
         seg.tile_mask = T;
+        seg.common_ctrl = K & ~T;
         // A sweep that touches little of the state is cheaper as stand-alone controlled kernels.
         double frac = 0;
         for (int gi : seg.gates) frac += gate_sweep_fraction(G[gi]);
         const bool small_state = cfg.always_tile_below && n <= 16;
         bool has_mux = false;
         for (int gi : seg.gates) has_mux |= G[gi].op == B2SV_OP_MUX;
-        if (!small_state && !has_mux && frac <= 0.55 && seg.gates.size() <= 8) {
+        if (!small_state && !has_mux && frac <= 0.55 * sweep_cost(seg.common_ctrl) && seg.gates.size() <= 8) {
             for (int gi : seg.gates) {
                 Segment one;
                 one.cls = SEG_GATE1Q;
@@ -411,7 +473,7 @@ inline Plan make_plan(const b2sv_gate* gates, size_t n_gates, const PlanConfig& 
                 plan_tiles(G, run, cfg, alt);
                 double tile_cost = 0;
                 for (const Segment& s : alt) {
-                    if (s.cls == SEG_TILE) tile_cost += 1.0;
+                    if (s.cls == SEG_TILE) tile_cost += sweep_cost(s.common_ctrl);
                     else tile_cost += gate_sweep_fraction(G[s.gates[0]]);
                 }
                 const double perm_cost = 1.0 + cfg.perm_gate_cost * (double)len;
