@@ -292,6 +292,10 @@ TileOp make_tile_op(const Plan& plan, const PGate& g, uint64_t tile_mask, const 
             op.tpos2 = (uint8_t)local_pos(g.t1);
             fixed |= (1u << op.tpos) | (1u << op.tpos2);
             break;
+        case B2SV_OP_BLOCK: {
+            const BlockInfo& bi = plan.blocks[g.blk];
+            for (int i = 0; i < bi.kb; ++i) fixed |= 1u << local_pos(bi.q[i]);
+        } break;
         default:
             op.tpos = (uint8_t)local_pos(g.t0);
             fixed |= 1u << op.tpos;
@@ -305,6 +309,12 @@ TileOp make_tile_op(const Plan& plan, const PGate& g, uint64_t tile_mask, const 
             op.nfix++;
         }
     std::memcpy(op.m, g.m, sizeof(op.m));
+    if (g.op == B2SV_OP_BLOCK) {
+        const BlockInfo& bi = plan.blocks[g.blk];
+        op.blk.mat_off = bi.mat_off;
+        op.blk.kb = (uint8_t)bi.kb;
+        for (int i = 0; i < bi.kb; ++i) op.blk.bpos[i] = (uint8_t)local_pos(bi.q[i]);
+    }
     if (g.op == B2SV_OP_MUX) {
         const MuxInfo& mi = plan.mux[g.mux];
         // g.ctrl (the run's common controls) is already a predicate in lctrl / ext_ctrl
@@ -1091,18 +1101,13 @@ int b2sv_plan_describe(int n_qubits, int dtype, const b2sv_gate* gates, size_t n
         ++w;
     };
     for (const Segment& seg : plan.segs) {
-        size_t n_src = 0;
-        for (int gi : seg.gates) n_src += plan.gates[gi].mux >= 0 ? plan.mux[plan.gates[gi].mux].sources.size() : 1;
+        std::vector<int> srcs;
+        for (int gi : seg.gates) gate_sources(plan, plan.gates[gi], srcs);
         put(seg.cls);
-        put((int64_t)n_src);
+        put((int64_t)srcs.size());
         put((int64_t)seg.tile_mask);
         put((int64_t)seg.common_ctrl);
-        for (int gi : seg.gates) {
-            if (plan.gates[gi].mux >= 0)
-                for (int sidx : plan.mux[plan.gates[gi].mux].sources) put(sidx);
-            else
-                put(plan.gates[gi].src);
-        }
+        for (int sidx : srcs) put(sidx);
     }
     {  // trailer: the folded global scalar, as raw IEEE bits
         int64_t re_bits, im_bits;

@@ -15,7 +15,7 @@
 
 namespace b2svk {
 
-constexpr int kMaxFixed = 24;
+constexpr int kMaxFixed = 40;
 constexpr int kThreads = 256;
 
 struct ExpandArgs {
@@ -134,9 +134,15 @@ struct __align__(16) TileOp {
             uint8_t mpos[7];       // per index bit: tile-local position, or 0xFF when outside the tile
             uint8_t mq[8];         // per index bit: global qubit
         } mux;
+        struct {               // op == kOpBlock: dense 2^kb x 2^kb matrix on kb <= 3 tile qubits
+            uint64_t mat_off;      // first double2 of the row-major matrix in TileArgs::tables
+            uint8_t kb;
+            uint8_t bpos[3];       // tile-local positions of the block qubits (matrix index bit i)
+        } blk;
     };
 };
 constexpr int kOpMux = 5;
+constexpr int kOpBlock = 6;
 static_assert(sizeof(TileOp) == 96, "TileOp layout");
 
 struct TileArgs {
@@ -347,6 +353,48 @@ __device__ __forceinline__ void tile_apply_op(A* tile, const TileOp& op, int k, 
                         tile[l[u] | bt] = from_c128<A>(cfma(m11, v1[u], cmul(m10, v0[u])));
                     }
             });
+        } break;
+        case kOpBlock: {
+            // every group of 2^kb amplitudes (block bits free, predicate bits set) is multiplied by one
+            // dense matrix; the matrix is read through the read-only path at warp-uniform addresses
+            const double2* __restrict__ U = tables + op.blk.mat_off;
+            if (op.blk.kb == 3) {
+                const uint32_t b0 = 1u << op.blk.bpos[0], b1 = 1u << op.blk.bpos[1], b2 = 1u << op.blk.bpos[2];
+                tile_for_each<1>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int) {
+                    uint32_t off[8];
+                    double2 v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        off[j] = l[0] | ((j & 1) ? b0 : 0u) | ((j & 2) ? b1 : 0u) | ((j & 4) ? b2 : 0u);
+                        v[j] = to_c128(tile[off[j]]);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        double2 acc = cmul(__ldg(U + r * 8), v[0]);
+#pragma unroll
+                        for (int c = 1; c < 8; ++c) acc = cfma(__ldg(U + r * 8 + c), v[c], acc);
+                        tile[off[r]] = from_c128<A>(acc);
+                    }
+                });
+            } else {  // kb == 2
+                const uint32_t b0 = 1u << op.blk.bpos[0], b1 = 1u << op.blk.bpos[1];
+                tile_for_each<1>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int) {
+                    uint32_t off[4];
+                    double2 v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        off[j] = l[0] | ((j & 1) ? b0 : 0u) | ((j & 2) ? b1 : 0u);
+                        v[j] = to_c128(tile[off[j]]);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        double2 acc = cmul(__ldg(U + r * 4), v[0]);
+#pragma unroll
+                        for (int c = 1; c < 4; ++c) acc = cfma(__ldg(U + r * 4 + c), v[c], acc);
+                        tile[off[r]] = from_c128<A>(acc);
+                    }
+                });
+            }
         } break;
         default: {  // PHASE
             const double2 w = make_double2(op.m[0], op.m[1]);

@@ -36,6 +36,8 @@ enum SegClass { SEG_GATE1Q = 0, SEG_TILE = 1, SEG_PERM = 2 };
 constexpr int kPermMaxCtrlX = 7, kPermMaxCtrlSwap = 6;
 constexpr int B2SV_OP_MUX = 5;        // internal: fused same-target run, a table of 2x2 matrices indexed by control bits
 constexpr int kMuxMaxCtrl = 6;        // table of at most 64 matrices (4 KiB)
+constexpr int B2SV_OP_BLOCK = 6;      // internal: fused run on <= 3 qubits, one dense 2^kb x 2^kb matrix
+constexpr int kBlockMaxQubits = 3;
 constexpr int kPlanMaxTileOps = 112;  // gates per tile sweep (their ops are staged in shared memory)
 
 struct PGate {
@@ -47,6 +49,7 @@ struct PGate {
     double m[8];
     int src;          // index in the caller's list
     int mux = -1;     // B2SV_OP_MUX: index into Plan::mux
+    int blk = -1;     // B2SV_OP_BLOCK: index into Plan::blocks
     bool is_perm() const { return op == B2SV_OP_X || op == B2SV_OP_SWAP; }
     // fits the word-op encoding of the permutation-run kernel (3 direct control slots, 2 for SWAP,
     // plus two per scratch row)
@@ -89,7 +92,18 @@ struct MuxInfo {
     std::vector<int> sources;    // caller's gate indices, execution order
 };
 
+// A run of consecutive gates confined to <= 3 qubits (apart from controls they ALL share) is one
+// dense 2^kb x 2^kb matrix on those qubits under the shared controls: the cosine-sine two-qubit
+// unitaries of circuits/generic_unitary.py, LCU rotations with their X sandwiches, ...
+struct BlockInfo {
+    int kb = 0;
+    uint8_t q[kBlockMaxQubits] = {0, 0, 0};  // block qubits, ascending; matrix index bit i <-> q[i]
+    size_t mat_off = 0;                      // first double2 of the row-major matrix in Plan::mux_tables
+    std::vector<int> sources;
+};
+
 struct Plan {
+    std::vector<BlockInfo> blocks;
     std::vector<MuxInfo> mux;
     std::vector<double> mux_tables;
     std::vector<PGate> gates;
@@ -339,6 +353,145 @@ inline void fuse_multiplexors(Plan& plan) {
     plan.gates.swap(out);
 }
 
+// ---- dense few-qubit block fusion ---------------------------------------------------------------
+
+inline bool blockable_gate(const PGate& g) {
+    return g.op == B2SV_OP_MAT1 || g.op == B2SV_OP_DIAG1 || g.op == B2SV_OP_X || g.op == B2SV_OP_SWAP || g.op == B2SV_OP_PHASE;
+}
+
+inline uint64_t gate_targets(const PGate& g) {
+    if (g.op == B2SV_OP_PHASE) return 0;
+    uint64_t t = 1ull << g.t0;
+    if (g.op == B2SV_OP_SWAP) t |= 1ull << g.t1;
+    return t;
+}
+
+// Apply gate g to a 2^kb vector (interleaved re,im) whose bit i stands for qubit q[i]; controls in
+// `common` are assumed satisfied.
+inline void block_apply_gate(double* v, int kb, const uint8_t* q, const PGate& g, uint64_t common) {
+    auto local = [&](int qubit) {
+        for (int i = 0; i < kb; ++i)
+            if (q[i] == qubit) return i;
+        return -1;
+    };
+    uint32_t lc = 0;
+    for (int b = 0; b < 64; ++b)
+        if (((g.ctrl & ~common) >> b) & 1) lc |= 1u << local(b);
+    const uint32_t dim = 1u << kb;
+    if (g.op == B2SV_OP_PHASE) {
+        for (uint32_t i = 0; i < dim; ++i)
+            if ((i & lc) == lc) {
+                const double re = v[2 * i] * g.m[0] - v[2 * i + 1] * g.m[1];
+                const double im = v[2 * i] * g.m[1] + v[2 * i + 1] * g.m[0];
+                v[2 * i] = re;
+                v[2 * i + 1] = im;
+            }
+        return;
+    }
+    if (g.op == B2SV_OP_SWAP) {
+        const uint32_t ba = 1u << local(g.t0), bb = 1u << local(g.t1);
+        for (uint32_t i = 0; i < dim; ++i)
+            if ((i & lc) == lc && (i & ba) && !(i & bb)) {
+                const uint32_t j = i ^ ba ^ bb;
+                std::swap(v[2 * i], v[2 * j]);
+                std::swap(v[2 * i + 1], v[2 * j + 1]);
+            }
+        return;
+    }
+    double U[8];
+    gate_matrix2(g, U);
+    const uint32_t bt = 1u << local(g.t0);
+    for (uint32_t i = 0; i < dim; ++i)
+        if ((i & lc) == lc && !(i & bt)) {
+            const double a0r = v[2 * i], a0i = v[2 * i + 1], a1r = v[2 * (i | bt)], a1i = v[2 * (i | bt) + 1];
+            v[2 * i] = U[0] * a0r - U[1] * a0i + U[2] * a1r - U[3] * a1i;
+            v[2 * i + 1] = U[0] * a0i + U[1] * a0r + U[2] * a1i + U[3] * a1r;
+            v[2 * (i | bt)] = U[4] * a0r - U[5] * a0i + U[6] * a1r - U[7] * a1i;
+            v[2 * (i | bt) + 1] = U[4] * a0i + U[5] * a0r + U[6] * a1i + U[7] * a1r;
+        }
+}
+
+inline void gate_sources(const Plan& plan, const PGate& g, std::vector<int>& out) {
+    if (g.mux >= 0) out.insert(out.end(), plan.mux[g.mux].sources.begin(), plan.mux[g.mux].sources.end());
+    else if (g.blk >= 0) out.insert(out.end(), plan.blocks[g.blk].sources.begin(), plan.blocks[g.blk].sources.end());
+    else out.push_back(g.src);
+}
+
+inline void fuse_blocks(Plan& plan) {
+    std::vector<PGate> out;
+    out.reserve(plan.gates.size());
+    const std::vector<PGate>& G = plan.gates;
+    size_t i = 0;
+    while (i < G.size()) {
+        const PGate& g = G[i];
+        if (!blockable_gate(g)) {
+            out.push_back(g);
+            ++i;
+            continue;
+        }
+        uint64_t K = g.ctrl, T = gate_targets(g), U = g.ctrl;
+        bool nonperm = !g.is_perm();
+        double separate = gate_sweep_fraction(g);
+        size_t j = i + 1;
+        while (j < G.size() && blockable_gate(G[j])) {
+            const uint64_t K2 = K & G[j].ctrl, T2 = T | gate_targets(G[j]), U2 = U | G[j].ctrl;
+            const uint64_t B2 = T2 | (U2 & ~K2);
+            if (popcount64(B2) > kBlockMaxQubits || (T2 & K2) != 0) break;
+            K = K2;
+            T = T2;
+            U = U2;
+            nonperm |= !G[j].is_perm();
+            separate += gate_sweep_fraction(G[j]);
+            ++j;
+        }
+        const size_t len = j - i;
+        const uint64_t B = T | (U & ~K);
+        const int kb = popcount64(B);
+        static const double block_cost[4] = {0.6, 1.0, 1.3, 2.4};  // one pass in units of a plain full-touch gate
+        const double scale = std::ldexp(1.0, -popcount64(K));
+        const bool worth = nonperm && kb >= 2 && len >= 3 && separate > block_cost[kb] * scale;
+        if (!worth) {
+            out.push_back(g);
+            ++i;
+            continue;
+        }
+        BlockInfo info;
+        info.kb = kb;
+        int nb = 0;
+        for (int b = 0; b < 64; ++b)
+            if ((B >> b) & 1) info.q[nb++] = (uint8_t)b;
+        const uint32_t dim = 1u << kb;
+        std::vector<double> mat((size_t)2 * dim * dim, 0.0);  // row-major, (re,im)
+        for (uint32_t col = 0; col < dim; ++col) {
+            double v[2 * 8] = {0};
+            v[2 * col] = 1.0;
+            for (size_t qg = i; qg < j; ++qg) block_apply_gate(v, kb, info.q, G[qg], K);
+            for (uint32_t row = 0; row < dim; ++row) {
+                mat[2 * ((size_t)row * dim + col)] = v[2 * row];
+                mat[2 * ((size_t)row * dim + col) + 1] = v[2 * row + 1];
+            }
+        }
+        while (plan.mux_tables.size() % 8) plan.mux_tables.push_back(0.0);  // keep multiplexor entries aligned
+        info.mat_off = plan.mux_tables.size() / 2;
+        plan.mux_tables.insert(plan.mux_tables.end(), mat.begin(), mat.end());
+        for (size_t qg = i; qg < j; ++qg) gate_sources(plan, G[qg], info.sources);
+        PGate f;
+        f.op = B2SV_OP_BLOCK;
+        f.t0 = info.q[0];
+        f.t1 = 0;
+        f.ctrl = K;
+        f.tmask = B;
+        f.qmask = B | K;
+        for (int e = 0; e < 8; ++e) f.m[e] = 0;
+        f.src = g.src;
+        f.blk = (int)plan.blocks.size();
+        plan.blocks.push_back(std::move(info));
+        out.push_back(f);
+        i = j;
+    }
+    plan.gates.swap(out);
+}
+
 // ---- tile packing -----------------------------------------------------------------------------
 
 // Cost of a sweep in units of one full pass over the state.
@@ -407,7 +560,7 @@ inline void plan_tiles(const std::vector<PGate>& G, const std::vector<int>& idx,
         for (int gi : seg.gates) frac += gate_sweep_fraction(G[gi]);
         const bool small_state = cfg.always_tile_below && n <= 16;
         bool has_mux = false;
-        for (int gi : seg.gates) has_mux |= G[gi].op == B2SV_OP_MUX;
+        for (int gi : seg.gates) has_mux |= G[gi].op == B2SV_OP_MUX || G[gi].op == B2SV_OP_BLOCK;
         if (!small_state && !has_mux && frac <= 0.55 * sweep_cost(seg.common_ctrl) && seg.gates.size() <= 8) {
             for (int gi : seg.gates) {
                 Segment one;
@@ -439,7 +592,10 @@ inline Plan make_plan(const b2sv_gate* gates, size_t n_gates, const PlanConfig& 
         plan.gates.push_back(g);
     }
     plan.gates_live = plan.gates.size();
-    if (cfg.fuse && cfg.mux) fuse_multiplexors(plan);
+    if (cfg.fuse && cfg.mux) {
+        fuse_multiplexors(plan);
+        fuse_blocks(plan);
+    }
     const std::vector<PGate>& G = plan.gates;
     if (!cfg.fuse) {
         for (size_t j = 0; j < G.size(); ++j) {
