@@ -162,9 +162,10 @@ int b2sv_swap_unpack(b2sv_t* sv, int q, int keep_bit, const void* staging_dev);
 
 /* ---- planner introspection (no GPU needed): how would `gates` be executed? ---------------------- */
 /* Writes up to `cap` int64 words describing the plan: for each segment
- *   {class, n_gates, tile_mask, common_ctrl, gate_index_0, ..., gate_index_{n_gates-1}}
+ *   {class, n_gates, tile_mask, common_ctrl, n_ops, gate_index_0, ..., gate_index_{n_gates-1}}
  * (a fused gate lists every caller gate it stands for; common_ctrl = controls shared by all gates
- * of a tile sweep outside its tile), then the trailer {-1, 2, 0, 0, bits(scalar_re), bits(scalar_im)},
+ * of a tile sweep outside its tile; n_ops = device ops after fusion), then the trailer
+ * {-1, 2, 0, 0, 0, bits(scalar_re), bits(scalar_im)},
  * and returns the number of words needed in *n_words. */
 int b2sv_plan_describe(int n_qubits, int dtype, const b2sv_gate* gates, size_t n_gates, const b2sv_plan_opts* opts,
                        int64_t* out_words, size_t cap, size_t* n_words);

@@ -146,7 +146,7 @@ def test_common_controls_restrict_tile_sweeps(name):
     low = lower_gates(live, n)
     segs, _scalar, common = cabi.plan_describe(n, cabi.B2SV_C128, low, cabi.PlanOpts.make(mux=False), with_common=True)
     restricted = 0
-    for (cls, mask, idx), com in zip(segs, common):
+    for (cls, mask, idx), (com, _n_ops) in zip(segs, common):
         if cls != cabi.SEG_TILE:
             assert com == 0
             continue

@@ -192,16 +192,16 @@ def plan_describe(n_qubits: int, dtype: int, gates: np.ndarray, opts: PlanOpts |
     i = 0
     common = []
     while i < len(words):
-        cls, cnt, mask, com = int(words[i]), int(words[i + 1]), int(words[i + 2]), int(words[i + 3])
+        cls, cnt, mask, com, n_ops = (int(words[i + k]) for k in range(5))
         if cls == -1:
-            re = np.array([words[i + 4]], dtype=np.int64).view(np.float64)[0]
-            im = np.array([words[i + 5]], dtype=np.int64).view(np.float64)[0]
+            re = np.array([words[i + 5]], dtype=np.int64).view(np.float64)[0]
+            im = np.array([words[i + 6]], dtype=np.int64).view(np.float64)[0]
             scalar = complex(re, im)
-            i += 6
+            i += 7
             continue
-        segs.append((cls, mask & 0xFFFFFFFFFFFFFFFF, [int(w) for w in words[i + 4 : i + 4 + cnt]]))
-        common.append(com & 0xFFFFFFFFFFFFFFFF)
-        i += 4 + cnt
+        segs.append((cls, mask & 0xFFFFFFFFFFFFFFFF, [int(w) for w in words[i + 5 : i + 5 + cnt]]))
+        common.append((com & 0xFFFFFFFFFFFFFFFF, n_ops))
+        i += 5 + cnt
     if with_common:
         return segs, scalar, common
     return segs, scalar

@@ -65,6 +65,8 @@ struct b2sv {
     void* amps = nullptr;
     void* scratch = nullptr;       // second state-sized buffer for out-of-place permutation sweeps
     bool scratch_failed = false;
+    bool pending_basis = false;    // |basis_index> has been requested but not written yet (lazy init)
+    uint64_t basis_index = 0;
     bool timing_on = false;        // last b2sv_apply asked for per-launch timing: time init/project too
     double sre = 1.0, sim = 0.0;   // pending global scalar (folded uncontrolled global phases)
     void* d_ops = nullptr;         // device copy of the tile ops of the current apply
@@ -216,6 +218,21 @@ int flush_scalar(b2sv* sv, bool timing) {
     return rc;
 }
 
+// Write the lazily requested basis state out (every reader of the amplitudes calls this first).
+int materialise(b2sv* sv) {
+    if (!sv->pending_basis) return B2SV_OK;
+    sv->pending_basis = false;
+    const uint64_t index = sv->basis_index;
+    int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
+        using A = std::remove_pointer_t<decltype(tag)>;
+        LaunchTimer lt(sv, sv->timing_on, CLS_INIT, (double)sv->amp_bytes * (double)sv->count);
+        k_set_basis<A><<<grid_for(sv, sv->count), kThreads, 0, sv->stream>>>((A*)sv->amps, sv->count, index);
+        return B2SV_OK;
+    });
+    CU(cudaGetLastError());
+    return rc;
+}
+
 // ---- launch helpers ---------------------------------------------------------------------------
 
 void fill_expand(ExpandArgs& ex, uint64_t mask) {
@@ -334,22 +351,19 @@ TileOp make_tile_op(const Plan& plan, const PGate& g, uint64_t tile_mask, const 
 
 template <typename A>
 int set_tile_smem(size_t bytes) {
-    static size_t configured[2] = {0, 0};
-    if (bytes > 48 * 1024) {
-        if (configured[0] < bytes) {
-            CU(cudaFuncSetAttribute(k_tile<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-            configured[0] = bytes;
-        }
-        if (configured[1] < bytes) {
-            CU(cudaFuncSetAttribute(k_tile<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-            configured[1] = bytes;
-        }
+    static size_t configured = 0;
+    if (bytes > 48 * 1024 && configured < bytes) {
+        CU(cudaFuncSetAttribute(k_tile<A, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        CU(cudaFuncSetAttribute(k_tile<A, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        CU(cudaFuncSetAttribute(k_tile<A, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        CU(cudaFuncSetAttribute(k_tile<A, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured = bytes;
     }
     return B2SV_OK;
 }
 
 int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, const PlanConfig& cfg, bool bulk,
-                bool timing) {
+                bool fused_ops, bool timing, bool lazy_init) {
     TileArgs a{};
     fill_expand(a.tile_ex, seg.tile_mask);
     if (popcount64(seg.tile_mask | seg.common_ctrl) > kMaxFixed) return fail(B2SV_EINVAL, "tile + common controls exceed %d qubits", kMaxFixed);
@@ -364,6 +378,9 @@ int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, co
     a.n_ops = n_ops;
     a.ops = d_ops;
     a.tables = (const double2*)sv->d_tables;
+    a.init_mode = lazy_init ? 1 : 0;
+    a.init_index = sv->basis_index;
+    a.tile_mask = seg.tile_mask;
     const uint64_t n_tiles = 1ull << (sv->n - a.cta_ex.m);
     if (n_ops > kTileMaxOps) return fail(B2SV_EINVAL, "tile sweep with %d ops (max %d)", n_ops, kTileMaxOps);
     const size_t smem = ((size_t)sv->amp_bytes << a.k) + (size_t)kTileMaxOps * sizeof(TileOp);
@@ -371,11 +388,15 @@ int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, co
         using A = std::remove_pointer_t<decltype(tag)>;
         int rc = set_tile_smem<A>(smem);
         if (rc) return rc;
-        LaunchTimer lt(sv, timing, CLS_TILE, 2.0 * sv->amp_bytes * (double)(n_tiles << a.k));
-        if (bulk)
-            k_tile<A, true><<<(unsigned)n_tiles, kThreads, smem, sv->stream>>>((A*)sv->amps, a);
+        LaunchTimer lt(sv, timing, CLS_TILE, (lazy_init ? 1.0 : 2.0) * sv->amp_bytes * (double)(n_tiles << a.k));
+        if (bulk && fused_ops)
+            k_tile<A, true, true><<<(unsigned)n_tiles, kThreads, smem, sv->stream>>>((A*)sv->amps, a);
+        else if (bulk)
+            k_tile<A, true, false><<<(unsigned)n_tiles, kThreads, smem, sv->stream>>>((A*)sv->amps, a);
+        else if (fused_ops)
+            k_tile<A, false, true><<<(unsigned)n_tiles, kThreads, smem, sv->stream>>>((A*)sv->amps, a);
         else
-            k_tile<A, false><<<(unsigned)n_tiles, kThreads, smem, sv->stream>>>((A*)sv->amps, a);
+            k_tile<A, false, false><<<(unsigned)n_tiles, kThreads, smem, sv->stream>>>((A*)sv->amps, a);
         return B2SV_OK;
     });
 }
@@ -721,17 +742,13 @@ int b2sv_destroy(b2sv_t* sv) {
 int b2sv_set_basis(b2sv_t* sv, uint64_t index) {
     if (int rc = check(sv)) return rc;
     if (index >= sv->count) return fail(B2SV_EINVAL, "basis index %llu >= 2^%d", (unsigned long long)index, sv->n);
-    CU(cudaSetDevice(sv->device));
     sv->sre = 1.0;
     sv->sim = 0.0;
-    int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
-        using A = std::remove_pointer_t<decltype(tag)>;
-        LaunchTimer lt(sv, sv->timing_on, CLS_INIT, (double)sv->amp_bytes * (double)sv->count);
-        k_set_basis<A><<<grid_for(sv, sv->count), kThreads, 0, sv->stream>>>((A*)sv->amps, sv->count, index);
-        return B2SV_OK;
-    });
-    CU(cudaGetLastError());
-    return rc;
+    // lazy: the first full tile sweep of the next b2sv_apply generates the state in shared memory;
+    // any other reader materialises it first
+    sv->pending_basis = true;
+    sv->basis_index = index;
+    return B2SV_OK;
 }
 
 int b2sv_set_zero(b2sv_t* sv) {
@@ -739,6 +756,7 @@ int b2sv_set_zero(b2sv_t* sv) {
     CU(cudaSetDevice(sv->device));
     sv->sre = 1.0;
     sv->sim = 0.0;
+    sv->pending_basis = false;
     sv->stats.launches_by_class[CLS_INIT]++;
     CU(cudaMemsetAsync(sv->amps, 0, sv->count * sv->amp_bytes, sv->stream));
     return B2SV_OK;
@@ -753,6 +771,7 @@ int b2sv_upload(b2sv_t* sv, const void* host) {
     CU(cudaSetDevice(sv->device));
     sv->sre = 1.0;
     sv->sim = 0.0;
+    sv->pending_basis = false;
     if (sv->dtype == B2SV_C128) {
         CU(cudaMemcpyAsync(sv->amps, host, sv->count * 16, cudaMemcpyHostToDevice, sv->stream));
         CU(cudaStreamSynchronize(sv->stream));
@@ -781,6 +800,7 @@ int b2sv_download(b2sv_t* sv, void* host) {
     if (int rc = check(sv)) return rc;
     if (!host) return fail(B2SV_EINVAL, "host buffer is null");
     CU(cudaSetDevice(sv->device));
+    if (int rc = materialise(sv)) return rc;
     if (int rc = flush_scalar(sv, false)) return rc;
     if (sv->dtype == B2SV_C128) {
         CU(cudaMemcpyAsync(host, sv->amps, sv->count * 16, cudaMemcpyDeviceToHost, sv->stream));
@@ -889,13 +909,22 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
     for (size_t s = 0; s < plan.segs.size(); ++s) {
         const Segment& seg = plan.segs[s];
         int rc = B2SV_OK;
+        // a pending basis state is generated by the first sweep if that sweep visits every tile
+        const bool lazy_init = sv->pending_basis && seg.cls == SEG_TILE && seg.common_ctrl == 0;
+        if (sv->pending_basis && !lazy_init) {
+            rc = materialise(sv);
+            if (rc) return rc;
+        }
         if (seg.cls == SEG_GATE1Q) {
             for (int gi : seg.gates) {
                 rc = launch_gate1(sv, plan.gates[gi], timing);
                 if (rc) break;
             }
         } else if (seg.cls == SEG_TILE) {
-            rc = launch_tile(sv, seg, (const TileOp*)sv->d_ops + seg_first[s], (int)seg.gates.size(), cfg, bulk, timing);
+            bool fused_ops = false;
+            for (int gi : seg.gates) fused_ops |= plan.gates[gi].op == B2SV_OP_MUX || plan.gates[gi].op == B2SV_OP_BLOCK;
+            rc = launch_tile(sv, seg, (const TileOp*)sv->d_ops + seg_first[s], (int)seg.gates.size(), cfg, bulk, fused_ops, timing, lazy_init);
+            if (lazy_init) sv->pending_basis = false;
         } else {
             rc = launch_perm(sv, plan, seg, timing, jit_mode);
         }
@@ -917,6 +946,7 @@ int b2sv_project_norm2_at(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, in
     if (!out) return fail(B2SV_EINVAL, "out is null");
     CU(cudaSetDevice(sv->device));
     if (index_base & (sv->count - 1)) return fail(B2SV_EINVAL, "index_base must have its low %d bits clear", sv->n);
+    if (int rc = materialise(sv)) return rc;
     int count_bits = 0;
     if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits, 64)) return rc;
     if (target_qubits < 64 && (index_base >> target_qubits) != 0) {  // this shard holds ancilla != 0 only
@@ -954,6 +984,7 @@ int b2sv_project_gather(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int 
     if (int rc = check(sv)) return rc;
     if (!host_out && dim > 0) return fail(B2SV_EINVAL, "host_out is null");
     CU(cudaSetDevice(sv->device));
+    if (int rc = materialise(sv)) return rc;
     int count_bits = 0;
     if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits)) return rc;
     if (dim == 0) return B2SV_OK;
@@ -1000,6 +1031,7 @@ int b2sv_enumerate_basis(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int
 int b2sv_device_ptr(b2sv_t* sv, void** amps, uint64_t* bytes) {
     if (int rc = check(sv)) return rc;
     CU(cudaSetDevice(sv->device));
+    if (int rc = materialise(sv)) return rc;
     if (int rc = flush_scalar(sv, false)) return rc;
     CU(cudaStreamSynchronize(sv->stream));
     if (amps) *amps = sv->amps;
@@ -1065,6 +1097,7 @@ static int swap_pack_impl(b2sv_t* sv, int q, int keep_bit, void* staging, bool p
     if (q < 0 || q >= sv->n) return fail(B2SV_EINVAL, "qubit %d outside the shard", q);
     if (!staging) return fail(B2SV_EINVAL, "staging is null");
     CU(cudaSetDevice(sv->device));
+    if (int rc = materialise(sv)) return rc;
     if (int rc = flush_scalar(sv, false)) return rc;
     const uint64_t half = sv->count >> 1;
     const uint64_t sel = keep_bit ? 0ull : (1ull << q);  // move the half whose bit differs from keep_bit
@@ -1107,6 +1140,7 @@ int b2sv_plan_describe(int n_qubits, int dtype, const b2sv_gate* gates, size_t n
         put((int64_t)srcs.size());
         put((int64_t)seg.tile_mask);
         put((int64_t)seg.common_ctrl);
+        put((int64_t)seg.gates.size());
         for (int sidx : srcs) put(sidx);
     }
     {  // trailer: the folded global scalar, as raw IEEE bits
@@ -1115,6 +1149,7 @@ int b2sv_plan_describe(int n_qubits, int dtype, const b2sv_gate* gates, size_t n
         std::memcpy(&im_bits, &plan.scalar_im, 8);
         put(-1);
         put(2);
+        put(0);
         put(0);
         put(0);
         put(re_bits);

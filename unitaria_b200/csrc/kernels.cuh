@@ -153,6 +153,12 @@ struct TileArgs {
     int n_ops;
     const TileOp* ops;
     const double2* tables;  // multiplexor tables of this apply
+    // init_mode 1: the register is the (not yet materialised) basis state |init_index>: the tile is
+    // generated in shared memory instead of being read -- the first sweep after b2sv_set_basis costs
+    // one write of the state and no read, and the separate initialisation kernel disappears.
+    int init_mode;
+    uint64_t init_index;
+    uint64_t tile_mask;
 };
 
 __device__ __forceinline__ uint32_t expand_local(uint32_t p, uint64_t fixpos, int nfix) {
@@ -218,7 +224,9 @@ __device__ __forceinline__ void tile_for_each(uint32_t cnt, uint64_t fixpos, int
     }
 }
 
-template <typename A>
+// FUSED = false compiles the light variant (no table-driven ops): fewer registers for sweeps that
+// only hold plain gates.
+template <typename A, bool FUSED>
 __device__ __forceinline__ void tile_apply_op(A* tile, const TileOp& op, int k, uint64_t base,
                                               const double2* __restrict__ tables) {
     const uint32_t cnt = 1u << (k - op.nfix);
@@ -315,7 +323,7 @@ __device__ __forceinline__ void tile_apply_op(A* tile, const TileOp& op, int k, 
                 });
             }
         } break;
-        case kOpMux: {
+        case kOpMux: if constexpr (FUSED) {
             // one pass over all pairs of the target; the 2x2 matrix of a pair is looked up by the
             // pair's control bits (tile-local ones per element, outside ones CTA-uniform)
             const uint32_t bt = 1u << op.tpos;
@@ -354,7 +362,7 @@ __device__ __forceinline__ void tile_apply_op(A* tile, const TileOp& op, int k, 
                     }
             });
         } break;
-        case kOpBlock: {
+        case kOpBlock: if constexpr (FUSED) {
             // every group of 2^kb amplitudes (block bits free, predicate bits set) is multiplied by one
             // dense matrix; the matrix is read through the read-only path at warp-uniform addresses
             const double2* __restrict__ U = tables + op.blk.mat_off;
@@ -368,31 +376,38 @@ __device__ __forceinline__ void tile_apply_op(A* tile, const TileOp& op, int k, 
                         off[j] = l[0] | ((j & 1) ? b0 : 0u) | ((j & 2) ? b1 : 0u) | ((j & 4) ? b2 : 0u);
                         v[j] = to_c128(tile[off[j]]);
                     }
+                    // four rows at a time: four independent accumulation chains hide the DFMA latency
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        double2 acc = cmul(__ldg(U + r * 8), v[0]);
+                    for (int r0 = 0; r0 < 8; r0 += 4) {
+                        double2 acc[4];
 #pragma unroll
-                        for (int c = 1; c < 8; ++c) acc = cfma(__ldg(U + r * 8 + c), v[c], acc);
-                        tile[off[r]] = from_c128<A>(acc);
+                        for (int r = 0; r < 4; ++r) acc[r] = cmul(__ldg(U + (r0 + r) * 8), v[0]);
+#pragma unroll
+                        for (int c = 1; c < 8; ++c)
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) acc[r] = cfma(__ldg(U + (r0 + r) * 8 + c), v[c], acc[r]);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) tile[off[r0 + r]] = from_c128<A>(acc[r]);
                     }
                 });
             } else {  // kb == 2
                 const uint32_t b0 = 1u << op.blk.bpos[0], b1 = 1u << op.blk.bpos[1];
                 tile_for_each<1>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int) {
                     uint32_t off[4];
-                    double2 v[4];
+                    double2 v[4], acc[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         off[j] = l[0] | ((j & 1) ? b0 : 0u) | ((j & 2) ? b1 : 0u);
                         v[j] = to_c128(tile[off[j]]);
                     }
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        double2 acc = cmul(__ldg(U + r * 4), v[0]);
+                    for (int r = 0; r < 4; ++r) acc[r] = cmul(__ldg(U + r * 4), v[0]);
 #pragma unroll
-                        for (int c = 1; c < 4; ++c) acc = cfma(__ldg(U + r * 4 + c), v[c], acc);
-                        tile[off[r]] = from_c128<A>(acc);
-                    }
+                    for (int c = 1; c < 4; ++c)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) acc[r] = cfma(__ldg(U + r * 4 + c), v[c], acc[r]);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) tile[off[r]] = from_c128<A>(acc[r]);
                 });
             }
         } break;
@@ -419,7 +434,7 @@ __device__ __forceinline__ uint64_t chunk_offset(uint32_t j, const ExpandArgs& e
     return off;
 }
 
-template <typename A, bool BULK>
+template <typename A, bool BULK, bool FUSED>
 __global__ void __launch_bounds__(kThreads) k_tile(A* __restrict__ psi, const TileArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     A* tile = reinterpret_cast<A*>(smem_raw);
@@ -432,7 +447,8 @@ __global__ void __launch_bounds__(kThreads) k_tile(A* __restrict__ psi, const Ti
     const uint32_t chunk_bytes = chunk_elems * (uint32_t)sizeof(A);
     const uint64_t base = expand_bits((uint64_t)blockIdx.x, a.cta_ex) | a.cta_or;
 
-    if (BULK) {
+    const bool load = a.init_mode == 0;
+    if (BULK && load) {
         if (tid == 0) {
             mbar_init(&bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -449,7 +465,17 @@ __global__ void __launch_bounds__(kThreads) k_tile(A* __restrict__ psi, const Ti
         const int n16 = a.n_ops * (int)(sizeof(TileOp) / 16);
         for (int i = tid; i < n16; i += kThreads) dst[i] = __ldg(src + i);
     }
-    if (BULK) {
+    if (!load) {
+        const uint32_t elems = 1u << k;
+        const A zero = from_c128<A>(make_double2(0.0, 0.0));
+        for (uint32_t l = tid; l < elems; l += kThreads) tile[l] = zero;
+        __syncthreads();
+        if (tid == 0 && (a.init_index & ~a.tile_mask) == base) {
+            uint32_t l = 0;
+            for (int i = 0; i < k; ++i) l |= (uint32_t)((a.init_index >> a.tile_ex.pos[i]) & 1ull) << i;
+            tile[l] = from_c128<A>(make_double2(1.0, 0.0));
+        }
+    } else if (BULK) {
         mbar_wait(&bar, 0);
     } else {
         const uint32_t elems = 1u << k;
@@ -463,7 +489,7 @@ __global__ void __launch_bounds__(kThreads) k_tile(A* __restrict__ psi, const Ti
     for (int o = 0; o < a.n_ops; ++o) {
         const TileOp& op = s_ops[o];
         if ((base & op.ext_ctrl) != op.ext_ctrl) continue;  // CTA-uniform: gate not active on this tile
-        tile_apply_op<A>(tile, op, k, base, a.tables);
+        tile_apply_op<A, FUSED>(tile, op, k, base, a.tables);
         __syncthreads();
     }
 

@@ -290,7 +290,7 @@ inline void fuse_multiplexors(Plan& plan) {
         const double scale = std::ldexp(1.0, -popcount64(K));
         // one table-driven pass over the K-controlled block costs about 2.5 plain passes; a product
         // with a single entry is just another 2x2 gate
-        const bool worth = nonperm && len >= 2 && (C == 0 ? true : (len >= 3 && separate > 2.5 * scale));
+        const bool worth = nonperm && len >= 2 && (C == 0 ? true : (len >= 3 && separate > 1.8 * scale));
         if (!worth) {
             out.push_back(g);
             ++i;
@@ -447,9 +447,12 @@ inline void fuse_blocks(Plan& plan) {
         const size_t len = j - i;
         const uint64_t B = T | (U & ~K);
         const int kb = popcount64(B);
-        static const double block_cost[4] = {0.6, 1.0, 1.3, 2.4};  // one pass in units of a plain full-touch gate
+        // measured on B200 (scripts/microbench_tile.py, 26 qubits): one block pass in units of a plain
+        // full-touch 2x2 gate: kb=2 ~1.5, kb=3 ~5 (DFMA-bound); a table-driven multiplexor pass ~1.7
+        static const double block_cost[4] = {0.6, 1.0, 1.6, 5.0};
         const double scale = std::ldexp(1.0, -popcount64(K));
-        const bool worth = nonperm && kb >= 2 && len >= 3 && separate > block_cost[kb] * scale;
+        // a light sweep hides ~4 plain passes behind its HBM time, so only fuse when the win is clear
+        const bool worth = nonperm && kb >= 2 && len >= 3 && separate > 2.5 * block_cost[kb] * scale;
         if (!worth) {
             out.push_back(g);
             ++i;
