@@ -87,8 +87,10 @@ typedef struct b2sv_plan_opts {
  *   B2SV_SUB_FREE    rank += field(pos, len) * weight                          (run of free qubits)
  *   B2SV_SUB_BRANCH  bit `pos` (the top qubit of a ControlledSubspace) picks next1 (and rank += add)
  *                    or next0
+ *   B2SV_SUB_REJECT  reject (used by per-rank specialised programs of the distributed layer, where a
+ *                    bit that lives in the rank number is known on the host)
  * Evaluation starts at instruction `entry`; ZEROS/FREE continue at next0. */
-enum { B2SV_SUB_END = 0, B2SV_SUB_ZEROS = 1, B2SV_SUB_FREE = 2, B2SV_SUB_BRANCH = 3 };
+enum { B2SV_SUB_END = 0, B2SV_SUB_ZEROS = 1, B2SV_SUB_FREE = 2, B2SV_SUB_BRANCH = 3, B2SV_SUB_REJECT = 4 };
 
 typedef struct b2sv_subinstr {
     uint8_t op, pos, len, pad;

@@ -17,6 +17,7 @@ import torch.multiprocessing as mp
 
 from oracle import np_oracle
 from tests.helpers import load_golden, random_circuit
+from unitaria_b200 import cabi
 from unitaria_b200.distributed import Layout, ShardedStateVector, TorchComm, localise_gate
 from unitaria_b200.fixtures import GateRecord
 from unitaria_b200.subspace_prog import SubspaceProgram, to_spec
@@ -51,15 +52,35 @@ class NumpyShard:
     def unpack(self, q, keep_bit):
         self.psi[self._half(q, keep_bit)] = self.recv
 
-    def norm2_at(self, prog, index_base):
-        t = prog.total_qubits
-        if index_base >> t:
-            return 0.0
-        mask = np_oracle.member_mask(prog.spec)
-        idx = index_base | np.arange(min(2**self.n, 2**t))
-        idx = idx[idx < 2**t]
-        sel = mask[idx]
-        return float(np.sum(np.abs(self.psi[: len(idx)][sel]) ** 2))
+    def norm2_shard(self, sp):
+        """Python mirror of the device walk over a per-rank specialised membership program."""
+        ins = sp.instrs
+        total = 0.0
+        for i in range(2**self.n):
+            pc = sp.entry
+            ok = None
+            for _ in range(len(ins) + 1):
+                op, pos, ln = int(ins["op"][pc]), int(ins["pos"][pc]), int(ins["len"][pc])
+                field = (i >> pos) & ((1 << ln) - 1)
+                if op == cabi.SUB_END:
+                    ok = True
+                    break
+                if op == cabi.SUB_REJECT:
+                    ok = False
+                    break
+                if op == cabi.SUB_ZEROS:
+                    if field:
+                        ok = False
+                        break
+                    pc = int(ins["next0"][pc])
+                elif op == cabi.SUB_FREE:
+                    pc = int(ins["next0"][pc])
+                else:
+                    pc = int(ins["next1"][pc]) if (i >> pos) & 1 else int(ins["next0"][pc])
+            assert ok is not None
+            if ok:
+                total += abs(self.psi[i]) ** 2
+        return total
 
     def download(self):
         return self.psi.copy()
@@ -92,8 +113,8 @@ def _worker(rank, world, port, case_name, seed, out_dir):
         sv = ShardedStateVector(n, TorchComm(), NumpyShard)
         sv.set_basis(basis)
         sv.apply(gates)
-        swaps_before_restore = sv.stats["swaps"]
         norm2 = sv.project_norm2(SubspaceProgram(spec))
+        swaps_before_restore = sv.stats["swaps"]  # the projection itself must not move data
         local = sv.local_amplitudes()
         np.save(os.path.join(out_dir, f"shard{rank}.npy"), local)
         if rank == 0:

@@ -32,7 +32,7 @@ GATE_DTYPE = np.dtype(
 )
 
 # struct b2sv_subinstr (32 bytes)
-SUB_END, SUB_ZEROS, SUB_FREE, SUB_BRANCH = 0, 1, 2, 3
+SUB_END, SUB_ZEROS, SUB_FREE, SUB_BRANCH, SUB_REJECT = 0, 1, 2, 3, 4
 SUBINSTR_DTYPE = np.dtype(
     {
         "names": ["op", "pos", "len", "pad", "next0", "next1", "weight", "add", "reserved"],

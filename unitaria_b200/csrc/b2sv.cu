@@ -603,8 +603,8 @@ int upload_subprog(b2sv* sv, const b2sv_subinstr* prog, int n_instr, int entry, 
     uint64_t covered = 0;
     for (int i = 0; i < n_instr; ++i) {
         const b2sv_subinstr& in = prog[i];
-        if (in.op > B2SV_SUB_BRANCH) return fail(B2SV_EINVAL, "subspace instruction %d: bad op %d", i, (int)in.op);
-        if (in.op == B2SV_SUB_END) continue;
+        if (in.op > B2SV_SUB_REJECT) return fail(B2SV_EINVAL, "subspace instruction %d: bad op %d", i, (int)in.op);
+        if (in.op == B2SV_SUB_END || in.op == B2SV_SUB_REJECT) continue;
         const int len = in.op == B2SV_SUB_BRANCH ? 1 : in.len;
         if (len < 1 || in.pos + len > target_qubits) return fail(B2SV_EINVAL, "subspace instruction %d: bits [%d,%d) outside the %d target qubits", i, (int)in.pos, in.pos + len, target_qubits);
         if (in.next0 >= n_instr || (in.op == B2SV_SUB_BRANCH && in.next1 >= n_instr))
@@ -612,7 +612,10 @@ int upload_subprog(b2sv* sv, const b2sv_subinstr* prog, int n_instr, int entry, 
         covered |= (len >= 64 ? ~0ull : ((1ull << len) - 1)) << in.pos;
     }
     const uint64_t all = target_qubits >= 64 ? ~0ull : ((1ull << target_qubits) - 1);
-    if ((covered & all) != all) return fail(B2SV_EINVAL, "subspace program does not constrain all %d target qubits", target_qubits);
+    // single-register programs mention every target qubit; per-rank specialised programs (sharded
+    // form, max_target_qubits == 64) have had their rank bits resolved on the host
+    if (max_target_qubits != 64 && (covered & all) != all)
+        return fail(B2SV_EINVAL, "subspace program does not constrain all %d target qubits", target_qubits);
     // shrink the scan range by the ZEROS runs at the top of the index that every path goes through:
     // conservative version -- follow the entry chain while it is made of ZEROS instructions.
     int bits = target_qubits;

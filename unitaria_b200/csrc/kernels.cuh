@@ -621,6 +621,7 @@ __device__ __forceinline__ bool sub_member_rank(const b2sv_subinstr* __restrict_
             rank_out = r;
             return true;
         }
+        if (op == B2SV_SUB_REJECT) return false;
         if (op == B2SV_SUB_ZEROS) {
             if (field) return false;
             pc = (int)(h.y & 0xFFFFu);

@@ -186,8 +186,8 @@ class GpuShard:
     def unpack(self, q: int, keep_bit: int):
         self.sv.swap_unpack(q, keep_bit, self.recv.data_ptr())
 
-    def norm2_at(self, prog, index_base: int) -> float:
-        return self.sv.project_norm2_at(prog, index_base)
+    def norm2_shard(self, shard_prog) -> float:
+        return self.sv.project_norm2_shard(shard_prog)
 
     def download(self) -> np.ndarray:
         return self.sv.download()
@@ -321,13 +321,18 @@ class ShardedStateVector:
 
     # -- results ----------------------------------------------------------------------------------
     def project_norm2(self, subspace) -> float:
-        """Global sum of |psi_i|^2 over the subspace with all higher qubits 0 (nodes/node.py:379,402)."""
-        from .subspace_prog import SubspaceProgram
+        """Global sum of |psi_i|^2 over the subspace with all higher qubits 0 (nodes/node.py:379,402).
+
+        No data moves: every rank evaluates a membership program specialised to the current layout
+        (qubits that sit in the rank number are resolved on the host) and the partial sums are
+        all-reduced."""
+        from .subspace_prog import ShardProgram, SubspaceProgram
 
         prog = subspace if isinstance(subspace, SubspaceProgram) else SubspaceProgram(subspace)
-        self.restore_identity_layout()
-        base = self.rank << self.layout.n_local
-        local = self.shard.norm2_at(prog, base)
+        lay = self.layout
+        rank_value = lambda p: ((self.rank >> (p - lay.n_local)) & 1) ^ lay.flip[p]  # noqa: E731
+        sp = ShardProgram(prog, lay.pos, lay.n_local, rank_value, self.n)
+        local = 0.0 if sp.rejects_all else self.shard.norm2_shard(sp)
         return self.comm.allreduce_sum(local)
 
     def local_amplitudes(self) -> np.ndarray:

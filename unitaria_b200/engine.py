@@ -194,6 +194,18 @@ class StateVector:
         )
         return float(out.value)
 
+    def project_norm2_shard(self, shard_prog) -> float:
+        """Norm over a per-rank specialised membership program (subspace_prog.ShardProgram)."""
+        if shard_prog.rejects_all:
+            return 0.0
+        out = ctypes.c_double(0.0)
+        cabi.check(
+            self._lib.b2sv_project_norm2_at(
+                self._h, shard_prog.instrs.ctypes.data, len(shard_prog.instrs), shard_prog.entry, self.n_qubits, 0, ctypes.byref(out)
+            )
+        )
+        return float(out.value)
+
     def project(self, subspace, scale: complex = 1.0) -> np.ndarray:
         """``scale * Subspace.project(psi)`` (subspace.py:331-335) gathered on the device."""
         p = self._program(subspace)

@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .cabi import SUB_BRANCH, SUB_END, SUB_FREE, SUB_ZEROS, SUBINSTR_DTYPE
+from .cabi import SUB_BRANCH, SUB_END, SUB_FREE, SUB_REJECT, SUB_ZEROS, SUBINSTR_DTYPE
 
 
 def to_spec(subspace) -> list:
@@ -131,3 +131,83 @@ class SubspaceProgram:
     @property
     def nodes(self):
         return self.instrs
+
+
+class ShardProgram:
+    """Membership program of a subspace for ONE shard of a sharded register (norm only: no ranks).
+
+    The logical index bits of the subspace program are relabelled to where the qubits physically
+    sit (``position[q]``); bits that live in the rank number (``position >= n_local``) are known on the
+    host -- ``rank_value(position)`` gives the logical value on this rank -- so their instructions are
+    resolved here: a ZEROS on a 1 becomes REJECT, a BRANCH becomes a jump.  The device evaluates what
+    is left on the local index alone, so the projection needs no global<->local swaps.
+    """
+
+    def __init__(self, prog: SubspaceProgram, position, n_local: int, rank_value, n_total: int | None = None):
+        src = prog.instrs
+        out = []
+
+        def emit(**f):
+            out.append(f)
+            return len(out) - 1
+
+        # every source instruction becomes a chain of single-bit instructions; first pass allocates the
+        # head index of each chain so that jumps can be resolved
+        heads, chains = {}, {}
+        for i, ins in enumerate(src):
+            op, pos, ln = int(ins["op"]), int(ins["pos"]), int(ins["len"])
+            if op in (SUB_END, SUB_REJECT):
+                chains[i] = [(op, 0)]
+            elif op == SUB_BRANCH:
+                chains[i] = [(op, pos)]
+            elif op == SUB_ZEROS:
+                chains[i] = [(op, pos + b) for b in range(ln)]
+            else:  # FREE only matters for the rank of a member: a no-op for the norm
+                chains[i] = [(SUB_FREE, -1)]
+        cursor = 0
+        for i in range(len(src)):
+            heads[i] = cursor
+            cursor += len(chains[i])
+        for i, ins in enumerate(src):
+            n0, n1 = heads[int(ins["next0"])], heads[int(ins["next1"])]
+            chain = chains[i]
+            for j, (op, bit) in enumerate(chain):
+                nxt = heads[i] + j + 1 if j + 1 < len(chain) else n0
+                if op in (SUB_END, SUB_REJECT):
+                    emit(op=op, pos=0, len=0, next0=0, next1=0, weight=0, add=0)
+                elif op == SUB_FREE:
+                    emit(op=SUB_FREE, pos=0, len=1, next0=nxt, next1=0, weight=0, add=0)
+                elif op == SUB_ZEROS:
+                    p = position[bit]
+                    if p < n_local:
+                        emit(op=SUB_ZEROS, pos=p, len=1, next0=nxt, next1=0, weight=0, add=0)
+                    elif rank_value(p):
+                        emit(op=SUB_REJECT, pos=0, len=0, next0=0, next1=0, weight=0, add=0)
+                    else:
+                        emit(op=SUB_FREE, pos=0, len=1, next0=nxt, next1=0, weight=0, add=0)
+                else:  # BRANCH
+                    p = position[bit]
+                    if p < n_local:
+                        emit(op=SUB_BRANCH, pos=p, len=1, next0=n0, next1=n1, weight=0, add=0)
+                    else:
+                        emit(op=SUB_FREE, pos=0, len=1, next0=(n1 if rank_value(p) else n0), next1=0, weight=0, add=0)
+        entry = heads[prog.entry]
+        # qubits above the subspace's own (clean / borrowed ancillae) are post-selected on 0
+        # (Subspace.project only enumerates the subspace's qubits, nodes/node.py:379)
+        n_total = len(position) if n_total is None else n_total
+        for q in range(prog.total_qubits, n_total):
+            p = position[q]
+            if p < n_local:
+                entry = emit(op=SUB_ZEROS, pos=p, len=1, next0=entry, next1=0, weight=0, add=0)
+            elif rank_value(p):
+                entry = emit(op=SUB_REJECT, pos=0, len=0, next0=0, next1=0, weight=0, add=0)
+        if len(out) > 65535:
+            raise ValueError("subspace program too long")
+        self.instrs = np.zeros(len(out), dtype=SUBINSTR_DTYPE)
+        for i, r in enumerate(out):
+            for k, v in r.items():
+                self.instrs[k][i] = v
+        self.entry = entry
+        self.total_qubits = prog.total_qubits
+        self.n_local = n_local
+        self.rejects_all = int(self.instrs["op"][entry]) == SUB_REJECT
