@@ -25,7 +25,7 @@ case $s in
   rest)    run t_rest 1200 python -m pytest tests/test_gpu_parity.py -q -m gpu ;;
   full)    run t_full 1200 python -m pytest tests/test_gpu_fullsize.py -q -m gpu ;;
   smoke)   run t_smoke 300 python -c "import __graft_entry__ as g; g.smoke()" ;;
-  bench)   run bench 900 python bench.py --steps 5 --warmup 3 ;;
+  bench)   run bench 900 python bench.py ;;
   benchref) run benchref 600 python bench.py --impl reference --steps 2 --warmup 1 ;;
 esac
 done

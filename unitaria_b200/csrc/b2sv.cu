@@ -80,6 +80,12 @@ struct b2sv {
     double* d_partial = nullptr;   // projection partial sums (+1 slot for the result)
     int n_partial = 0;
     int sm_count = 148;
+    // the plan of the last b2sv_apply (verify-style callers apply one circuit to many inputs)
+    bool plan_valid = false;
+    uint64_t plan_key = 0, plan_key2 = 0;
+    size_t plan_ngates = 0;
+    b2svk::Plan plan;
+    std::vector<size_t> plan_seg_first;
     b2sv_stats_t stats{};
     std::vector<TimedLaunch> timed;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> apply_events;
@@ -831,38 +837,98 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
     if (int rc = check(sv)) return rc;
     if (n_gates > 0 && !gates) return fail(B2SV_EINVAL, "gates is null");
     CU(cudaSetDevice(sv->device));
-    for (size_t j = 0; j < n_gates; ++j) {
-        const b2sv_gate& g = gates[j];
-        if (g.op > B2SV_OP_PHASE) return fail(B2SV_EINVAL, "gate %zu: unknown op %d", j, (int)g.op);
-        if (g.op == B2SV_OP_SWAP && g.t0 == g.t1) return fail(B2SV_EINVAL, "gate %zu: SWAP of a qubit with itself", j);
-        const uint64_t all = sv->n >= 64 ? ~0ull : ((1ull << sv->n) - 1);
-        if (g.ctrl_mask & ~all) return fail(B2SV_EINVAL, "gate %zu: control outside the %d-qubit register", j, sv->n);
-        if (g.op != B2SV_OP_PHASE) {
-            if (g.t0 >= sv->n) return fail(B2SV_EINVAL, "gate %zu: target %d outside the register", j, (int)g.t0);
-            if ((g.ctrl_mask >> g.t0) & 1) return fail(B2SV_EINVAL, "gate %zu: target %d is also a control", j, (int)g.t0);
-        }
-        if (g.op == B2SV_OP_SWAP) {
-            if (g.t1 >= sv->n) return fail(B2SV_EINVAL, "gate %zu: target %d outside the register", j, (int)g.t1);
-            if ((g.ctrl_mask >> g.t1) & 1) return fail(B2SV_EINVAL, "gate %zu: target %d is also a control", j, (int)g.t1);
-        }
-    }
     PlanConfig cfg = default_config(sv->n, sv->dtype, opts);
     const bool timing = opts && opts->timing;
     sv->timing_on = timing;
     const bool bulk = !(opts && opts->tile_io == 1);
     const int jit_mode = opts ? opts->jit : 0;
-    bool scratch_ok = false;
-    if (cfg.fuse && cfg.perm_runs && sv->n >= 13) {
-        // only pay for the second buffer if the circuit has a run that wants it
-        size_t run = 0, best = 0;
-        for (size_t j = 0; j < n_gates; ++j) {
-            if (gates[j].op == B2SV_OP_X || gates[j].op == B2SV_OP_SWAP) best = std::max(best, ++run);
-            else run = 0;
-        }
-        if ((int)best >= cfg.perm_min) scratch_ok = ensure_scratch(sv) == B2SV_OK;
-    }
     if (sv->n < 13) cfg.perm_runs = false;
-    Plan plan = make_plan(gates, n_gates, cfg, scratch_ok);
+    // same gate list and planner options as last time: reuse the plan and what is already on the device
+    uint64_t key = 1469598103934665603ull, key2 = 0;
+    {
+        const uint64_t* w = reinterpret_cast<const uint64_t*>(gates);
+        const size_t nw = n_gates * sizeof(b2sv_gate) / 8;
+        for (size_t i = 0; i < nw; ++i) {
+            key = (key ^ w[i]) * 1099511628211ull;
+            key2 += w[i] * (2 * i + 1);
+        }
+        const uint64_t o = (uint64_t)cfg.fuse | ((uint64_t)cfg.perm_runs << 1) | ((uint64_t)cfg.mux << 2) |
+                           ((uint64_t)cfg.tile_qubits << 8) | ((uint64_t)cfg.lookahead << 16) | ((uint64_t)sv->scratch_failed << 40);
+        key = (key ^ o) * 1099511628211ull;
+    }
+    const bool reuse = sv->plan_valid && sv->plan_key == key && sv->plan_key2 == key2 && sv->plan_ngates == n_gates;
+    if (!reuse) {
+        for (size_t j = 0; j < n_gates; ++j) {
+            const b2sv_gate& g = gates[j];
+            if (g.op > B2SV_OP_PHASE) return fail(B2SV_EINVAL, "gate %zu: unknown op %d", j, (int)g.op);
+            if (g.op == B2SV_OP_SWAP && g.t0 == g.t1) return fail(B2SV_EINVAL, "gate %zu: SWAP of a qubit with itself", j);
+            const uint64_t all = sv->n >= 64 ? ~0ull : ((1ull << sv->n) - 1);
+            if (g.ctrl_mask & ~all) return fail(B2SV_EINVAL, "gate %zu: control outside the %d-qubit register", j, sv->n);
+            if (g.op != B2SV_OP_PHASE) {
+                if (g.t0 >= sv->n) return fail(B2SV_EINVAL, "gate %zu: target %d outside the register", j, (int)g.t0);
+                if ((g.ctrl_mask >> g.t0) & 1) return fail(B2SV_EINVAL, "gate %zu: target %d is also a control", j, (int)g.t0);
+            }
+            if (g.op == B2SV_OP_SWAP) {
+                if (g.t1 >= sv->n) return fail(B2SV_EINVAL, "gate %zu: target %d outside the register", j, (int)g.t1);
+                if ((g.ctrl_mask >> g.t1) & 1) return fail(B2SV_EINVAL, "gate %zu: target %d is also a control", j, (int)g.t1);
+            }
+        }
+        sv->plan_valid = false;
+        bool scratch_ok = false;
+        if (cfg.fuse && cfg.perm_runs) {
+            // only pay for the second buffer if the circuit has a run that wants it
+            size_t run = 0, best = 0;
+            for (size_t j = 0; j < n_gates; ++j) {
+                if (gates[j].op == B2SV_OP_X || gates[j].op == B2SV_OP_SWAP) best = std::max(best, ++run);
+                else run = 0;
+            }
+            if ((int)best >= cfg.perm_min) scratch_ok = ensure_scratch(sv) == B2SV_OK;
+        }
+        sv->plan = make_plan(gates, n_gates, cfg, scratch_ok);
+        const Plan& np = sv->plan;
+        // tile ops of all tile segments, one upload
+        std::vector<TileOp> host_ops;
+        sv->plan_seg_first.assign(np.segs.size(), 0);
+        for (size_t s = 0; s < np.segs.size(); ++s) {
+            const Segment& seg = np.segs[s];
+            if (seg.cls != SEG_TILE) continue;
+            ExpandArgs ex;
+            fill_expand(ex, seg.tile_mask);
+            sv->plan_seg_first[s] = host_ops.size();
+            for (int gi : seg.gates) host_ops.push_back(make_tile_op(np, np.gates[gi], seg.tile_mask, ex));
+        }
+        if (!host_ops.empty()) {
+            const size_t bytes = host_ops.size() * sizeof(TileOp);
+            if (bytes > sv->d_ops_cap) {
+                CU(cudaStreamSynchronize(sv->stream));
+                cudaFree(sv->d_ops);
+                sv->d_ops = nullptr;
+                sv->d_ops_cap = 0;
+                CU(cudaMalloc(&sv->d_ops, bytes * 2));
+                sv->d_ops_cap = bytes * 2;
+            }
+            CU(cudaMemcpyAsync(sv->d_ops, host_ops.data(), bytes, cudaMemcpyHostToDevice, sv->stream));
+        }
+        if (!np.mux_tables.empty()) {
+            const size_t bytes = np.mux_tables.size() * sizeof(double);
+            if (bytes > sv->d_tables_cap) {
+                CU(cudaStreamSynchronize(sv->stream));
+                cudaFree(sv->d_tables);
+                sv->d_tables = nullptr;
+                sv->d_tables_cap = 0;
+                CU(cudaMalloc(&sv->d_tables, bytes * 2));
+                sv->d_tables_cap = bytes * 2;
+            }
+            CU(cudaMemcpyAsync(sv->d_tables, np.mux_tables.data(), bytes, cudaMemcpyHostToDevice, sv->stream));
+        }
+        // pageable uploads are staged before cudaMemcpyAsync returns, so host_ops may die here
+        sv->plan_key = key;
+        sv->plan_key2 = key2;
+        sv->plan_ngates = n_gates;
+        sv->plan_valid = true;
+    }
+    const Plan& plan = sv->plan;
+    const std::vector<size_t>& seg_first = sv->plan_seg_first;
     sv->stats.gates_in += plan.gates_in;
     sv->stats.gates_live += plan.gates_live;
     {  // fold the plan's scalar into the pending one
@@ -870,42 +936,6 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
         const double i = sv->sre * plan.scalar_im + sv->sim * plan.scalar_re;
         sv->sre = r;
         sv->sim = i;
-    }
-    // tile ops of all tile segments, one upload
-    std::vector<TileOp> host_ops;
-    std::vector<size_t> seg_first(plan.segs.size(), 0);
-    for (size_t s = 0; s < plan.segs.size(); ++s) {
-        const Segment& seg = plan.segs[s];
-        if (seg.cls != SEG_TILE) continue;
-        ExpandArgs ex;
-        fill_expand(ex, seg.tile_mask);
-        seg_first[s] = host_ops.size();
-        for (int gi : seg.gates) host_ops.push_back(make_tile_op(plan, plan.gates[gi], seg.tile_mask, ex));
-    }
-    if (!host_ops.empty()) {
-        const size_t bytes = host_ops.size() * sizeof(TileOp);
-        if (bytes > sv->d_ops_cap) {
-            // a previous apply may still be reading the old buffer
-            CU(cudaStreamSynchronize(sv->stream));
-            cudaFree(sv->d_ops);
-            sv->d_ops = nullptr;
-            sv->d_ops_cap = 0;
-            CU(cudaMalloc(&sv->d_ops, bytes * 2));
-            sv->d_ops_cap = bytes * 2;
-        }
-        CU(cudaMemcpyAsync(sv->d_ops, host_ops.data(), bytes, cudaMemcpyHostToDevice, sv->stream));
-    }
-    if (!plan.mux_tables.empty()) {
-        const size_t bytes = plan.mux_tables.size() * sizeof(double);
-        if (bytes > sv->d_tables_cap) {
-            CU(cudaStreamSynchronize(sv->stream));
-            cudaFree(sv->d_tables);
-            sv->d_tables = nullptr;
-            sv->d_tables_cap = 0;
-            CU(cudaMalloc(&sv->d_tables, bytes * 2));
-            sv->d_tables_cap = bytes * 2;
-        }
-        CU(cudaMemcpyAsync(sv->d_tables, plan.mux_tables.data(), bytes, cudaMemcpyHostToDevice, sv->stream));
     }
     cudaEvent_t ev_a = get_event(sv), ev_b = get_event(sv);
     CU(cudaEventRecord(ev_a, sv->stream));
