@@ -72,7 +72,9 @@ typedef struct b2sv_plan_opts {
     int32_t perm_runs;    /* 1: runs of X/SWAP gates become one index-map sweep (default); 0: off    */
     int32_t timing;       /* 1: bracket every launch with CUDA events and accumulate per-class times */
     int32_t lookahead;    /* commutation-aware lookahead window in gates; 0 = default                 */
-    int32_t tile_io;      /* 0: bulk-async (TMA engine) tile copies (default); 1: plain ld/st (debug aid)   */
+    int32_t tile_io;      /* tile sweeps: 0 = one tile per CTA, bulk-async (TMA engine) copies, 3 CTAs/SM (default);
+                             1 = same with plain ld/st (debug aid); 3 = experimental persistent 3-stage
+                             pipeline, one CTA per SM (slower in round 1: only one load in flight per SM) */
     int32_t jit;          /* permutation runs: 0 = specialise with NVRTC in the background after first use
                              (default), 1 = never (generic kernel only), 2 = compile synchronously       */
     int32_t reserved;     /* 1: no same-target multiplexor fusion (A/B switch); else 0                     */

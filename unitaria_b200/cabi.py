@@ -56,14 +56,14 @@ class PlanOpts(ctypes.Structure):
     ]
 
     @classmethod
-    def make(cls, fuse=True, tile_qubits=0, perm_runs=True, timing=False, lookahead=0, plain_tile_io=False, jit="auto", mux=True):
+    def make(cls, fuse=True, tile_qubits=0, perm_runs=True, timing=False, lookahead=0, plain_tile_io=False, jit="auto", mux=True, tile_io=None):
         o = cls()
         o.fuse = int(bool(fuse))
         o.tile_qubits = int(tile_qubits)
         o.perm_runs = int(bool(perm_runs))
         o.timing = int(bool(timing))
         o.lookahead = int(lookahead)
-        o.tile_io = 1 if plain_tile_io else 0
+        o.tile_io = (1 if plain_tile_io else 0) if tile_io is None else int(tile_io)
         o.jit = {"auto": 0, "off": 1, "sync": 2}[jit]
         o.reserved = 0 if mux else 1
         return o

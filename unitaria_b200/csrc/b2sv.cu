@@ -368,8 +368,20 @@ int set_tile_smem(size_t bytes) {
     return B2SV_OK;
 }
 
-int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, const PlanConfig& cfg, bool bulk,
+template <typename A>
+int set_pipe_smem(size_t bytes) {
+    static size_t configured = 0;
+    if (bytes > 48 * 1024 && configured < bytes) {
+        CU(cudaFuncSetAttribute(k_tile_pipe<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        CU(cudaFuncSetAttribute(k_tile_pipe<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured = bytes;
+    }
+    return B2SV_OK;
+}
+
+int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, const PlanConfig& cfg, int tile_io,
                 bool fused_ops, bool timing, bool lazy_init) {
+    const bool bulk = tile_io != 1;
     TileArgs a{};
     fill_expand(a.tile_ex, seg.tile_mask);
     if (popcount64(seg.tile_mask | seg.common_ctrl) > kMaxFixed) return fail(B2SV_EINVAL, "tile + common controls exceed %d qubits", kMaxFixed);
@@ -390,6 +402,21 @@ int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, co
     const uint64_t n_tiles = 1ull << (sv->n - a.cta_ex.m);
     if (n_ops > kTileMaxOps) return fail(B2SV_EINVAL, "tile sweep with %d ops (max %d)", n_ops, kTileMaxOps);
     const size_t smem = ((size_t)sv->amp_bytes << a.k) + (size_t)kTileMaxOps * sizeof(TileOp);
+    if (tile_io == 3) {  // experimental: persistent three-stage pipeline, one CTA per SM (measured slower)
+        const size_t pipe_smem = (((size_t)sv->amp_bytes << a.k) * kPipeStages) + (size_t)kTileMaxOps * sizeof(TileOp);
+        const uint64_t grid = n_tiles < (uint64_t)sv->sm_count ? n_tiles : (uint64_t)sv->sm_count;
+        return dispatch_dtype(sv, [&](auto* tag) -> int {
+            using A = std::remove_pointer_t<decltype(tag)>;
+            int rc = set_pipe_smem<A>(pipe_smem);
+            if (rc) return rc;
+            LaunchTimer lt(sv, timing, CLS_TILE, (lazy_init ? 1.0 : 2.0) * sv->amp_bytes * (double)(n_tiles << a.k));
+            if (fused_ops)
+                k_tile_pipe<A, true><<<(unsigned)grid, kPipeThreads, pipe_smem, sv->stream>>>((A*)sv->amps, a, (uint32_t)n_tiles);
+            else
+                k_tile_pipe<A, false><<<(unsigned)grid, kPipeThreads, pipe_smem, sv->stream>>>((A*)sv->amps, a, (uint32_t)n_tiles);
+            return B2SV_OK;
+        });
+    }
     return dispatch_dtype(sv, [&](auto* tag) -> int {
         using A = std::remove_pointer_t<decltype(tag)>;
         int rc = set_tile_smem<A>(smem);
@@ -840,7 +867,7 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
     PlanConfig cfg = default_config(sv->n, sv->dtype, opts);
     const bool timing = opts && opts->timing;
     sv->timing_on = timing;
-    const bool bulk = !(opts && opts->tile_io == 1);
+    const int tile_io = opts ? opts->tile_io : 0;
     const int jit_mode = opts ? opts->jit : 0;
     if (sv->n < 13) cfg.perm_runs = false;
     // same gate list and planner options as last time: reuse the plan and what is already on the device
@@ -956,7 +983,7 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
         } else if (seg.cls == SEG_TILE) {
             bool fused_ops = false;
             for (int gi : seg.gates) fused_ops |= plan.gates[gi].op == B2SV_OP_MUX || plan.gates[gi].op == B2SV_OP_BLOCK;
-            rc = launch_tile(sv, seg, (const TileOp*)sv->d_ops + seg_first[s], (int)seg.gates.size(), cfg, bulk, fused_ops, timing, lazy_init);
+            rc = launch_tile(sv, seg, (const TileOp*)sv->d_ops + seg_first[s], (int)seg.gates.size(), cfg, tile_io, fused_ops, timing, lazy_init);
             if (lazy_init) sv->pending_basis = false;
         } else {
             rc = launch_perm(sv, plan, seg, timing, jit_mode);

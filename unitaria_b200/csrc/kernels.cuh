@@ -211,13 +211,14 @@ constexpr int kTileMaxOps = 112;  // ops of one sweep are staged in shared memor
 template <int UNROLL, typename F>
 __device__ __forceinline__ void tile_for_each(uint32_t cnt, uint64_t fixpos, int nfix, uint32_t lctrl, F&& body) {
     uint32_t p = threadIdx.x;
-    for (; p + (UNROLL - 1) * kThreads < cnt; p += UNROLL * kThreads) {
+    const uint32_t nt = blockDim.x;
+    for (; p + (UNROLL - 1) * nt < cnt; p += UNROLL * nt) {
         uint32_t l[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) l[u] = expand_local(p + u * kThreads, fixpos, nfix) | lctrl;
+        for (int u = 0; u < UNROLL; ++u) l[u] = expand_local(p + u * nt, fixpos, nfix) | lctrl;
         body(l, UNROLL);
     }
-    for (; p < cnt; p += kThreads) {
+    for (; p < cnt; p += nt) {
         uint32_t l[UNROLL];
         l[0] = expand_local(p, fixpos, nfix) | lctrl;
         body(l, 1);
@@ -508,6 +509,99 @@ __global__ void __launch_bounds__(kThreads) k_tile(A* __restrict__ psi, const Ti
             psi[g] = tile[l];
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Persistent, pipelined form of the tile sweep: ONE CTA per SM walks over its tiles with a ring of
+// three shared-memory stages, so that at any time one tile is arriving (bulk-async copies tracked by
+// an mbarrier), one is being worked on by all threads, and one is leaving (bulk-async stores).  The
+// TMA engine keeps HBM busy while every thread computes, which is what lets a sweep carry several
+// full-touch gates at the copy roofline (the one-tile-per-CTA kernel above only overlaps through
+// occupancy: 3 CTAs/SM, each idle on memory half of the time).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kPipeThreads = 512;
+constexpr int kPipeStages = 3;
+
+template <typename A, bool FUSED>
+__global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(A* __restrict__ psi, const TileArgs a, uint32_t n_tiles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int k = a.k, lc = a.lc;
+    const size_t tile_bytes = (size_t)sizeof(A) << k;
+    TileOp* s_ops = reinterpret_cast<TileOp*>(smem_raw + kPipeStages * tile_bytes);
+    __shared__ __align__(8) uint64_t full[kPipeStages];
+    const int tid = threadIdx.x;
+    const uint32_t n_chunks = 1u << (k - lc), chunk_elems = 1u << lc;
+    const uint32_t chunk_bytes = chunk_elems * (uint32_t)sizeof(A);
+    const bool load = a.init_mode == 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < kPipeStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.ops);
+        uint4* dst = reinterpret_cast<uint4*>(s_ops);
+        const int n16 = a.n_ops * (int)(sizeof(TileOp) / 16);
+        for (int i = tid; i < n16; i += kPipeThreads) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+
+    // the first min(n_chunks, 32) threads own the bulk copies: thread j moves chunks j, j+32, ...
+    // (bulk-store groups are per thread, so the thread that stored a stage is the one that waits for it)
+    auto issue_load = [&](uint32_t tile_id, int stage) {
+        A* tile = reinterpret_cast<A*>(smem_raw + stage * tile_bytes);
+        const uint64_t base = expand_bits((uint64_t)tile_id, a.cta_ex) | a.cta_or;
+        if (tid == 0) mbar_expect_tx(&full[stage], chunk_bytes * n_chunks);
+        __syncwarp();
+        for (uint32_t j = tid; j < n_chunks; j += 32)
+            bulk_g2s(tile + (size_t)j * chunk_elems, psi + (base | chunk_offset(j, a.tile_ex, k, lc)), chunk_bytes, &full[stage]);
+    };
+
+    uint32_t it = 0;
+    if (load && tid < 32 && blockIdx.x < n_tiles) issue_load(blockIdx.x, 0);
+    for (uint32_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x, ++it) {
+        const int stage = (int)(it % kPipeStages);
+        A* tile = reinterpret_cast<A*>(smem_raw + stage * tile_bytes);
+        const uint64_t base = expand_bits((uint64_t)tile_id, a.cta_ex) | a.cta_or;
+        // prefetch the next tile into the stage that held tile it-2: its store must have drained
+        const uint32_t next_id = tile_id + gridDim.x;
+        if (tid < 32) {
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (load && next_id < n_tiles) issue_load(next_id, (int)((it + 1) % kPipeStages));
+        }
+        if (load) {
+            mbar_wait(&full[stage], (it / kPipeStages) & 1u);
+        } else {
+            // not-yet-materialised basis state: generate the tile; the stage may still be draining
+            // (stores of tile it-3) -- the wait_group above only covers it-2, so wait for all but one
+            if (tid < 32) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncthreads();
+            const uint32_t elems = 1u << k;
+            const A zero = from_c128<A>(make_double2(0.0, 0.0));
+            for (uint32_t l = tid; l < elems; l += kPipeThreads) tile[l] = zero;
+            __syncthreads();
+            if (tid == 0 && (a.init_index & ~a.tile_mask) == base) {
+                uint32_t l = 0;
+                for (int i = 0; i < k; ++i) l |= (uint32_t)((a.init_index >> a.tile_ex.pos[i]) & 1ull) << i;
+                tile[l] = from_c128<A>(make_double2(1.0, 0.0));
+            }
+            __syncthreads();
+        }
+        for (int o = 0; o < a.n_ops; ++o) {
+            const TileOp& op = s_ops[o];
+            if ((base & op.ext_ctrl) != op.ext_ctrl) continue;
+            tile_apply_op<A, FUSED>(tile, op, k, base, a.tables);
+            __syncthreads();
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid < 32) {
+            for (uint32_t j = tid; j < n_chunks; j += 32)
+                bulk_s2g(psi + (base | chunk_offset(j, a.tile_ex, k, lc)), tile + (size_t)j * chunk_elems, chunk_bytes);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (tid < 32) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // ===================================================================================================
