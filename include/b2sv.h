@@ -163,6 +163,10 @@ int b2sv_elapsed_ms(b2sv_t* sv, int slot_a, int slot_b, double* ms);
  * inverse. */
 int b2sv_swap_pack(b2sv_t* sv, int q, int keep_bit, void* staging_dev);
 int b2sv_swap_unpack(b2sv_t* sv, int q, int keep_bit, const void* staging_dev);
+/* The same on packed amplitudes [first, first+count) only (staging is still indexed from 0), so that the
+ * caller can pipeline pack / exchange / unpack in chunks. */
+int b2sv_swap_pack_range(b2sv_t* sv, int q, int keep_bit, void* staging_dev, uint64_t first, uint64_t count);
+int b2sv_swap_unpack_range(b2sv_t* sv, int q, int keep_bit, const void* staging_dev, uint64_t first, uint64_t count);
 
 /* ---- planner introspection (no GPU needed): how would `gates` be executed? ---------------------- */
 /* Writes up to `cap` int64 words describing the plan: for each segment

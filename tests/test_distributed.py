@@ -45,12 +45,22 @@ class NumpyShard:
         idx = np.arange(2**self.n)
         return idx[((idx >> q) & 1) != keep_bit]
 
-    def pack(self, q, keep_bit):
-        self.send[:] = self.psi[self._half(q, keep_bit)]
-        return torch.from_numpy(self.send.view(np.float64)), torch.from_numpy(self.recv.view(np.float64))
+    chunks = 2  # exercise the pipelined pack / exchange / unpack path of ShardedStateVector._swap
 
-    def unpack(self, q, keep_bit):
-        self.psi[self._half(q, keep_bit)] = self.recv
+    @property
+    def half(self):
+        return self.psi.size // 2
+
+    def pack(self, q, keep_bit, first=0, count=None):
+        count = self.half - first if count is None else count
+        self.send[first : first + count] = self.psi[self._half(q, keep_bit)[first : first + count]]
+        s = torch.from_numpy(self.send.view(np.float64))[2 * first : 2 * (first + count)]
+        r = torch.from_numpy(self.recv.view(np.float64))[2 * first : 2 * (first + count)]
+        return s, r
+
+    def unpack(self, q, keep_bit, first=0, count=None):
+        count = self.half - first if count is None else count
+        self.psi[self._half(q, keep_bit)[first : first + count]] = self.recv[first : first + count]
 
     def norm2_shard(self, sp):
         """Python mirror of the device walk over a per-rank specialised membership program."""

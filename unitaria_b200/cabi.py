@@ -130,6 +130,8 @@ SYMBOLS = {
     "b2sv_elapsed_ms": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
     "b2sv_swap_pack": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P]),
     "b2sv_swap_unpack": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P]),
+    "b2sv_swap_pack_range": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P, ctypes.c_uint64, ctypes.c_uint64]),
+    "b2sv_swap_unpack_range": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P, ctypes.c_uint64, ctypes.c_uint64]),
     "b2sv_plan_describe": (
         ctypes.c_int,
         [ctypes.c_int, ctypes.c_int, _P, ctypes.c_size_t, ctypes.POINTER(PlanOpts), _P, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)],

@@ -1152,22 +1152,25 @@ int b2sv_elapsed_ms(b2sv_t* sv, int slot_a, int slot_b, double* ms) {
     return B2SV_OK;
 }
 
-static int swap_pack_impl(b2sv_t* sv, int q, int keep_bit, void* staging, bool pack) {
+static int swap_pack_impl(b2sv_t* sv, int q, int keep_bit, void* staging, bool pack, uint64_t first, uint64_t count) {
     if (int rc = check(sv)) return rc;
     if (q < 0 || q >= sv->n) return fail(B2SV_EINVAL, "qubit %d outside the shard", q);
     if (!staging) return fail(B2SV_EINVAL, "staging is null");
+    const uint64_t half = sv->count >> 1;
+    if (first > half || count > half - first) return fail(B2SV_EINVAL, "range [%llu, +%llu) outside the %llu packed amplitudes",
+                                                          (unsigned long long)first, (unsigned long long)count, (unsigned long long)half);
     CU(cudaSetDevice(sv->device));
     if (int rc = materialise(sv)) return rc;
     if (int rc = flush_scalar(sv, false)) return rc;
-    const uint64_t half = sv->count >> 1;
+    if (count == 0) return B2SV_OK;
     const uint64_t sel = keep_bit ? 0ull : (1ull << q);  // move the half whose bit differs from keep_bit
     int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
         using A = std::remove_pointer_t<decltype(tag)>;
-        LaunchTimer lt(sv, false, CLS_SWAP, 2.0 * sv->amp_bytes * (double)half);
+        LaunchTimer lt(sv, false, CLS_SWAP, 2.0 * sv->amp_bytes * (double)count);
         if (pack)
-            k_swap_pack<A, true><<<grid_for(sv, half), kThreads, 0, sv->stream>>>((A*)sv->amps, (A*)staging, half, q, sel);
+            k_swap_pack<A, true><<<grid_for(sv, count), kThreads, 0, sv->stream>>>((A*)sv->amps, (A*)staging, first, first + count, q, sel);
         else
-            k_swap_pack<A, false><<<grid_for(sv, half), kThreads, 0, sv->stream>>>((A*)sv->amps, (A*)staging, half, q, sel);
+            k_swap_pack<A, false><<<grid_for(sv, count), kThreads, 0, sv->stream>>>((A*)sv->amps, (A*)staging, first, first + count, q, sel);
         return B2SV_OK;
     });
     if (rc) return rc;
@@ -1176,9 +1179,19 @@ static int swap_pack_impl(b2sv_t* sv, int q, int keep_bit, void* staging, bool p
     return B2SV_OK;
 }
 
-int b2sv_swap_pack(b2sv_t* sv, int q, int keep_bit, void* staging_dev) { return swap_pack_impl(sv, q, keep_bit, staging_dev, true); }
+int b2sv_swap_pack(b2sv_t* sv, int q, int keep_bit, void* staging_dev) {
+    if (int rc = check(sv)) return rc;
+    return swap_pack_impl(sv, q, keep_bit, staging_dev, true, 0, sv->count >> 1);
+}
 int b2sv_swap_unpack(b2sv_t* sv, int q, int keep_bit, const void* staging_dev) {
-    return swap_pack_impl(sv, q, keep_bit, const_cast<void*>(staging_dev), false);
+    if (int rc = check(sv)) return rc;
+    return swap_pack_impl(sv, q, keep_bit, const_cast<void*>(staging_dev), false, 0, sv->count >> 1);
+}
+int b2sv_swap_pack_range(b2sv_t* sv, int q, int keep_bit, void* staging_dev, uint64_t first, uint64_t count) {
+    return swap_pack_impl(sv, q, keep_bit, staging_dev, true, first, count);
+}
+int b2sv_swap_unpack_range(b2sv_t* sv, int q, int keep_bit, const void* staging_dev, uint64_t first, uint64_t count) {
+    return swap_pack_impl(sv, q, keep_bit, const_cast<void*>(staging_dev), false, first, count);
 }
 
 int b2sv_plan_describe(int n_qubits, int dtype, const b2sv_gate* gates, size_t n_gates, const b2sv_plan_opts* opts,

@@ -822,10 +822,10 @@ __global__ void __launch_bounds__(kThreads) k_convert(D* __restrict__ dst, const
 // staging[k] = psi[i] (pack) or psi[i] = staging[k] (unpack) for the half of the shard whose bit q
 // equals `sel`; k enumerates that half in ascending index order.
 template <typename A, bool PACK>
-__global__ void __launch_bounds__(kThreads) k_swap_pack(A* __restrict__ psi, A* __restrict__ staging, uint64_t half,
-                                                        int q, uint64_t sel_bit) {
+__global__ void __launch_bounds__(kThreads) k_swap_pack(A* __restrict__ psi, A* __restrict__ staging, uint64_t first,
+                                                        uint64_t half, int q, uint64_t sel_bit) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < half; k += stride) {
+    for (uint64_t k = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < half; k += stride) {
         const uint64_t i = insert_zero(k, q) | sel_bit;
         if (PACK) staging[k] = psi[i];
         else psi[i] = staging[k];

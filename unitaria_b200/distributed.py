@@ -125,14 +125,20 @@ class TorchComm:
         self.device = device
 
     def exchange(self, send, recv, partner: int) -> None:
+        self.wait(self.start_exchange(send, recv, partner), send)
+
+    def start_exchange(self, send, recv, partner: int):
+        """Grouped send/recv with one peer (the pairwise case of an all-to-all); returns without waiting."""
         dist = self.dist
-        reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, send, partner), dist.P2POp(dist.irecv, recv, partner)])
+        return dist.batch_isend_irecv([dist.P2POp(dist.isend, send, partner), dist.P2POp(dist.irecv, recv, partner)])
+
+    def wait(self, reqs, tensor) -> None:
         for r in reqs:
             r.wait()
-        if send.is_cuda:
+        if tensor.is_cuda:
             import torch
 
-            torch.cuda.synchronize(send.device)
+            torch.cuda.synchronize(tensor.device)
 
     def allreduce_sum(self, value: float) -> float:
         import torch
@@ -179,12 +185,24 @@ class GpuShard:
         if gates:
             self.sv.apply(gates, opts)
 
-    def pack(self, q: int, keep_bit: int):
-        self.sv.swap_pack(q, keep_bit, self.send.data_ptr())
-        return self.send, self.recv
+    chunks = 8  # pack / exchange / unpack are pipelined over this many pieces of the half shard
+    min_chunk = 1 << 16
 
-    def unpack(self, q: int, keep_bit: int):
-        self.sv.swap_unpack(q, keep_bit, self.recv.data_ptr())
+    def pack(self, q: int, keep_bit: int, first: int = 0, count: int | None = None):
+        """Pack amplitudes [first, first+count) of the moving half; returns the matching views of the
+        send / receive buffers (bytes)."""
+        half = self.sv.size >> 1
+        count = half - first if count is None else count
+        self.sv.swap_pack(q, keep_bit, self.send.data_ptr(), first, count)
+        b = self.sv.amp_bytes
+        return self.send[first * b : (first + count) * b], self.recv[first * b : (first + count) * b]
+
+    def unpack(self, q: int, keep_bit: int, first: int = 0, count: int | None = None):
+        self.sv.swap_unpack(q, keep_bit, self.recv.data_ptr(), first, count)
+
+    @property
+    def half(self) -> int:
+        return self.sv.size >> 1
 
     def norm2_shard(self, shard_prog) -> float:
         return self.sv.project_norm2_shard(shard_prog)
@@ -277,9 +295,33 @@ class ShardedStateVector:
         bit = pg - lay.n_local
         my_bit = (self.rank >> bit) & 1  # PHYSICAL rank bit: data placement ignores the flip flag
         t0 = time.perf_counter()
-        send, recv = self.shard.pack(pl, my_bit)
-        self.comm.exchange(send, recv, self.rank ^ (1 << bit))
-        self.shard.unpack(pl, my_bit)
+        partner = self.rank ^ (1 << bit)
+        chunks = getattr(self.shard, "chunks", 1)
+        if chunks > 1 and hasattr(self.comm, "start_exchange") and self.shard.half >= chunks * getattr(self.shard, "min_chunk", 1):
+            # software pipeline: while NCCL moves piece c, the engine packs piece c+1 and unpacks c-1
+            half = self.shard.half
+            step = half // chunks
+            sent = 0
+            inflight = []
+            for c in range(chunks):
+                first = c * step
+                count = step if c + 1 < chunks else half - first
+                send, recv = self.shard.pack(pl, my_bit, first, count)
+                inflight.append((self.comm.start_exchange(send, recv, partner), send, first, count))
+                sent += int(send.numel() * send.element_size())
+                if len(inflight) > 1:
+                    reqs, tensor, f0, n0 = inflight.pop(0)
+                    self.comm.wait(reqs, tensor)
+                    self.shard.unpack(pl, my_bit, f0, n0)
+            for reqs, tensor, f0, n0 in inflight:
+                self.comm.wait(reqs, tensor)
+                self.shard.unpack(pl, my_bit, f0, n0)
+            send_bytes = sent
+        else:
+            send, recv = self.shard.pack(pl, my_bit)
+            self.comm.exchange(send, recv, partner)
+            self.shard.unpack(pl, my_bit)
+            send_bytes = int(send.numel() * send.element_size())
         # the local position now carries the former global qubit with the global position's flip
         # flag folded into it: physical bit value = logical ^ flip  ->  restore with a local X
         if lay.flip[pg]:
@@ -287,7 +329,7 @@ class ShardedStateVector:
             lay.flip[pg] = 0
         lay.swap_positions(pg, pl)
         self.stats["swaps"] += 1
-        self.stats["swap_bytes"] += int(send.numel() * send.element_size())
+        self.stats["swap_bytes"] += send_bytes
         self.stats["swap_s"] += time.perf_counter() - t0
 
     def restore_identity_layout(self) -> None:

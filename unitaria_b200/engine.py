@@ -254,8 +254,10 @@ class StateVector:
     def stats_reset(self) -> None:
         cabi.check(self._lib.b2sv_stats_reset(self._h))
 
-    def swap_pack(self, qubit: int, keep_bit: int, staging_ptr: int) -> None:
-        cabi.check(self._lib.b2sv_swap_pack(self._h, int(qubit), int(keep_bit), ctypes.c_void_p(staging_ptr)))
+    def swap_pack(self, qubit: int, keep_bit: int, staging_ptr: int, first: int = 0, count: int | None = None) -> None:
+        count = (self.size >> 1) - first if count is None else count
+        cabi.check(self._lib.b2sv_swap_pack_range(self._h, int(qubit), int(keep_bit), ctypes.c_void_p(staging_ptr), int(first), int(count)))
 
-    def swap_unpack(self, qubit: int, keep_bit: int, staging_ptr: int) -> None:
-        cabi.check(self._lib.b2sv_swap_unpack(self._h, int(qubit), int(keep_bit), ctypes.c_void_p(staging_ptr)))
+    def swap_unpack(self, qubit: int, keep_bit: int, staging_ptr: int, first: int = 0, count: int | None = None) -> None:
+        count = (self.size >> 1) - first if count is None else count
+        cabi.check(self._lib.b2sv_swap_unpack_range(self._h, int(qubit), int(keep_bit), ctypes.c_void_p(staging_ptr), int(first), int(count)))
