@@ -138,7 +138,9 @@ class TorchComm:
         if tensor.is_cuda:
             import torch
 
-            torch.cuda.synchronize(tensor.device)
+            # r.wait() only makes torch's current stream wait for the transfer; block the host on that
+            # stream (not the whole device: later pieces of a pipelined exchange are still in flight)
+            torch.cuda.current_stream(tensor.device).synchronize()
 
     def allreduce_sum(self, value: float) -> float:
         import torch
@@ -432,6 +434,9 @@ def bench_main(args, case, config_dict, cpu_sample, ClockSampler, measured_peak)
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
     torch.cuda.set_device(local_rank)
+    # the exchanges are big pairwise send/recv: give NCCL enough point-to-point channels to fill NVLink 5
+    os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "32")
+    os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     comm = TorchComm(device=torch.device(f"cuda:{local_rank}"))
     dtype = "complex128" if args.dtype == "c128" else "complex64"
