@@ -380,6 +380,7 @@ def main():
     ap.add_argument("--qubits", type=int, default=None, help="pad the register to this many qubits (idle high qubits)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-mux", action="store_true", help="A/B switch: disable same-target multiplexor fusion")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU swap transport")
     ap.add_argument("--tile-qubits", type=int, default=0)
     ap.add_argument("--tile-io", type=int, default=0, help="0 one tile per CTA with bulk-async copies (default), 1 plain ld/st, 3 experimental persistent pipeline")
     ap.add_argument("--lookahead", type=int, default=0)

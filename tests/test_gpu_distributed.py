@@ -27,14 +27,17 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, case_name, dtype, basis, out_dir):
+def _worker(rank, world, port, case_name, dtype, basis, out_dir, peer):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
     try:
         case = load_golden(case_name)
-        sv = ShardedStateVector(case.n_qubits, TorchComm(device=torch.device(f"cuda:{rank}")), make_gpu_shard_factory(dtype, rank))
+        comm = TorchComm(device=torch.device(f"cuda:{rank}"))
+        sv = ShardedStateVector(case.n_qubits, comm, make_gpu_shard_factory(dtype, rank))
+        if peer:
+            assert comm.enable_peer_pull(sv.shard.send), getattr(comm, "peer_error", "peer mapping failed")
         sv.set_basis(basis)
         sv.apply(case.gates)
         swaps = sv.stats["swaps"]
@@ -62,10 +65,10 @@ def test_sharded_gpu_matches_oracle(tmp_path, case_name, dtype, tol):
     want = c_oracle.simulate_gates(case.gates, case.n_qubits, basis)
     members = np_oracle.enumerate_basis(case.meta["subspace_out"])
     want_norm2 = float(np.sum(np.abs(want[members]) ** 2))
-    for world in worlds:
-        out = tmp_path / f"w{world}"
+    for world, peer in [(w, p) for w in worlds for p in (False, True)]:
+        out = tmp_path / f"w{world}_{int(peer)}"
         out.mkdir()
-        mp.spawn(_worker, args=(world, _free_port(), case_name, dtype, basis, str(out)), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), case_name, dtype, basis, str(out), peer), nprocs=world, join=True)
         full = np.concatenate([np.load(out / f"shard{r}.npy") for r in range(world)])
         meta = np.load(out / "meta.npy")
         assert np.abs(full - want).max() <= tol, (case_name, world)
