@@ -158,7 +158,7 @@ class TorchComm:
                 if r == self.rank:
                     continue
                 storage = torch.UntypedStorage._new_shared_cuda(*h)
-                self.peer_send[r] = torch.empty(0, dtype=torch.uint8, device=send_tensor.device).set_(storage, off, (n,))
+                self.peer_send[r] = torch.empty(0, dtype=torch.uint8, device=storage.device).set_(storage, off, (n,))
             ok = 1.0
         except Exception as exc:  # pragma: no cover - depends on the platform
             self.peer_error = repr(exc)
@@ -449,6 +449,10 @@ class ShardedStateVector:
         return self.shard.download()
 
     def close(self):
+        if getattr(self.comm, "peer_send", None):
+            self.comm.barrier()
+            self.comm.peer_send = {}  # drop the IPC mappings before the owners free their buffers
+            self.comm.barrier()
         self.shard.close()
 
 
