@@ -1161,16 +1161,23 @@ static int swap_pack_impl(b2sv_t* sv, int q, int keep_bit, void* staging, bool p
                                                           (unsigned long long)first, (unsigned long long)count, (unsigned long long)half);
     CU(cudaSetDevice(sv->device));
     if (int rc = materialise(sv)) return rc;
-    if (int rc = flush_scalar(sv, false)) return rc;
     if (count == 0) return B2SV_OK;
     const uint64_t sel = keep_bit ? 0ull : (1ull << q);  // move the half whose bit differs from keep_bit
+    // The shard's lazy global scalar stays pending for the half that does not move: outgoing amplitudes
+    // are multiplied by it on the way out, incoming ones by its conjugate (|s| = 1) on the way in.
+    const bool scale = !(sv->sre == 1.0 && sv->sim == 0.0);
+    const double2 sc = pack ? make_double2(sv->sre, sv->sim) : make_double2(sv->sre, -sv->sim);
     int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
         using A = std::remove_pointer_t<decltype(tag)>;
         LaunchTimer lt(sv, false, CLS_SWAP, 2.0 * sv->amp_bytes * (double)count);
-        if (pack)
-            k_swap_pack<A, true><<<grid_for(sv, count), kThreads, 0, sv->stream>>>((A*)sv->amps, (A*)staging, first, first + count, q, sel);
-        else
-            k_swap_pack<A, false><<<grid_for(sv, count), kThreads, 0, sv->stream>>>((A*)sv->amps, (A*)staging, first, first + count, q, sel);
+        const int grid = grid_for(sv, (count + 3) / 4, 16);
+        A* amps = (A*)sv->amps;
+        A* st = (A*)staging;
+        const uint64_t end = first + count;
+        if (pack && scale) k_swap_pack<A, true, true><<<grid, kThreads, 0, sv->stream>>>(amps, st, first, end, q, sel, sc);
+        else if (pack) k_swap_pack<A, true, false><<<grid, kThreads, 0, sv->stream>>>(amps, st, first, end, q, sel, sc);
+        else if (scale) k_swap_pack<A, false, true><<<grid, kThreads, 0, sv->stream>>>(amps, st, first, end, q, sel, sc);
+        else k_swap_pack<A, false, false><<<grid, kThreads, 0, sv->stream>>>(amps, st, first, end, q, sel, sc);
         return B2SV_OK;
     });
     if (rc) return rc;

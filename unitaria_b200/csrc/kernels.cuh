@@ -819,16 +819,30 @@ __global__ void __launch_bounds__(kThreads) k_convert(D* __restrict__ dst, const
         dst[i] = from_c128<D>(to_c128(src[i]));
 }
 
-// staging[k] = psi[i] (pack) or psi[i] = staging[k] (unpack) for the half of the shard whose bit q
-// equals `sel`; k enumerates that half in ascending index order.
-template <typename A, bool PACK>
+// staging[k] = s * psi[i] (pack) or psi[i] = s * staging[k] (unpack) for the half of the shard whose
+// bit q equals `sel`; k enumerates that half in ascending index order.  `s` carries the shard's lazy
+// global scalar across the exchange (pack: s, unpack: conj(s)) so that no separate scaling pass over the
+// whole shard is needed; SCALE = false is the exact data-movement form used when s == 1.
+template <typename A, bool PACK, bool SCALE>
 __global__ void __launch_bounds__(kThreads) k_swap_pack(A* __restrict__ psi, A* __restrict__ staging, uint64_t first,
-                                                        uint64_t half, int q, uint64_t sel_bit) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t k = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < half; k += stride) {
-        const uint64_t i = insert_zero(k, q) | sel_bit;
-        if (PACK) staging[k] = psi[i];
-        else psi[i] = staging[k];
+                                                        uint64_t half, int q, uint64_t sel_bit, double2 s) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
+    for (uint64_t k0 = first + ((uint64_t)blockIdx.x * blockDim.x * 4) + threadIdx.x; k0 < half; k0 += stride) {
+        A v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t k = k0 + (uint64_t)u * blockDim.x;
+            if (k < half) v[u] = PACK ? psi[insert_zero(k, q) | sel_bit] : staging[k];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t k = k0 + (uint64_t)u * blockDim.x;
+            if (k < half) {
+                const A w = SCALE ? from_c128<A>(cmul(s, to_c128(v[u]))) : v[u];
+                if (PACK) staging[k] = w;
+                else psi[insert_zero(k, q) | sel_bit] = w;
+            }
+        }
     }
 }
 

@@ -355,13 +355,21 @@ class ShardedStateVector:
             # the partner's HBM -- one device-to-device copy over NVLink, no NCCL channel kernels
             half = self.shard.half
             b = self.shard.amp_bytes
+            ta = time.perf_counter()
             self.shard.pack(pl, my_bit)
-            self.comm.barrier()                       # the partner's send buffer is complete
+            tb = time.perf_counter()
+            self.comm.allreduce_sum(0.0)              # light barrier: the partner's send buffer is complete
+            tc = time.perf_counter()
             _s, recv = self.shard.views(0, half)
             self.comm.pull(recv, partner, 0)
             self.comm.stream_sync(recv)
+            td = time.perf_counter()
             self.shard.unpack(pl, my_bit)
-            self.comm.barrier()                       # nobody re-packs while a peer is still reading
+            te = time.perf_counter()
+            self.comm.allreduce_sum(0.0)              # nobody re-packs while a peer is still reading
+            tf = time.perf_counter()
+            for key, dt in (("pack_s", tb - ta), ("barrier_s", tc - tb + tf - te), ("transfer_s", td - tc), ("unpack_s", te - td)):
+                self.stats[key] = self.stats.get(key, 0.0) + dt
             send_bytes = half * b
         elif chunks > 1 and hasattr(self.comm, "start_exchange") and self.shard.half >= chunks * getattr(self.shard, "min_chunk", 1):
             # software pipeline: while NCCL moves piece c, the engine packs piece c+1 and unpacks c-1
@@ -593,6 +601,7 @@ def bench_main(args, case, config_dict, cpu_sample, ClockSampler, measured_peak)
                 "achieved_GBps_per_direction": (swap_bytes / swap_s / 1e9) if swap_s > 0 else None,
                 "nvlink_peak_GBps_per_direction": 770.0,
                 "path": exchange,
+                "breakdown_s_per_step_rank0": {k: sv.stats[k] / args.steps for k in ("pack_s", "barrier_s", "transfer_s", "unpack_s") if k in sv.stats},
                 "note": "seconds include pack + transfer + unpack",
             },
             "kernels_rank0": {c: {"launches": st["launches_by_class"][c], "ms": st["ms_by_class"][c]} for c in st["ms_by_class"] if st["launches_by_class"][c]},
