@@ -169,9 +169,15 @@ class TorchComm:
         return all_ok
 
     def pull(self, recv_view, partner: int, first_byte: int) -> None:
-        """recv_view <- partner's send buffer [first_byte, +len(recv_view)); asynchronous on torch's stream."""
+        """recv_view <- partner's send buffer [first_byte, +len(recv_view)) and wait for it.  torch runs a
+        cross-device copy on the SOURCE device's stream (of this process), so both devices are synchronised."""
+        import torch
+
         n = recv_view.numel()
-        recv_view.copy_(self.peer_send[partner][first_byte : first_byte + n], non_blocking=True)
+        src = self.peer_send[partner][first_byte : first_byte + n]
+        recv_view.copy_(src, non_blocking=True)
+        torch.cuda.synchronize(src.device)
+        torch.cuda.synchronize(recv_view.device)
 
     def stream_sync(self, tensor) -> None:
         import torch
@@ -362,7 +368,6 @@ class ShardedStateVector:
             tc = time.perf_counter()
             _s, recv = self.shard.views(0, half)
             self.comm.pull(recv, partner, 0)
-            self.comm.stream_sync(recv)
             td = time.perf_counter()
             self.shard.unpack(pl, my_bit)
             te = time.perf_counter()
