@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -290,7 +291,9 @@ inline void fuse_multiplexors(Plan& plan) {
         const double scale = std::ldexp(1.0, -popcount64(K));
         // one table-driven pass over the K-controlled block costs about 2.5 plain passes; a product
         // with a single entry is just another 2x2 gate
-        const bool worth = nonperm && len >= 2 && (C == 0 ? true : (len >= 3 && separate > 1.8 * scale));
+        // measured (profiles/fusion_r1.txt): the table-driven pass only pays for long multiplexor runs
+        // (state preparation); short controlled runs are cheaper as plain gates
+        const bool worth = nonperm && len >= 2 && (C == 0 ? true : (len >= 6 && separate > 1.8 * scale));
         if (!worth) {
             out.push_back(g);
             ++i;
@@ -351,6 +354,17 @@ inline void fuse_multiplexors(Plan& plan) {
         i = j;
     }
     plan.gates.swap(out);
+}
+
+// How much more the separate gates must cost than the fused op before fusing (tunable for experiments
+// through B2SV_FUSE_MARGIN; the default comes from the sweep in profiles/fusion_r1.txt).
+inline double fuse_margin() {
+    static const double v = [] {
+        const char* e = std::getenv("B2SV_FUSE_MARGIN");
+        const double x = e ? std::atof(e) : 0.0;
+        return x > 0.0 ? x : 1.0;
+    }();
+    return v;
 }
 
 // ---- dense few-qubit block fusion ---------------------------------------------------------------
@@ -452,7 +466,7 @@ inline void fuse_blocks(Plan& plan) {
         static const double block_cost[4] = {0.6, 1.0, 1.6, 5.0};
         const double scale = std::ldexp(1.0, -popcount64(K));
         // a light sweep hides ~4 plain passes behind its HBM time, so only fuse when the win is clear
-        const bool worth = nonperm && kb >= 2 && len >= 3 && separate > 2.5 * block_cost[kb] * scale;
+        const bool worth = nonperm && kb >= 2 && len >= 3 && separate > fuse_margin() * block_cost[kb] * scale;
         if (!worth) {
             out.push_back(g);
             ++i;
