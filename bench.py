@@ -244,7 +244,7 @@ def run_single(args):
     rng = np.random.default_rng(0)
     # permutation runs: compile the NVRTC-specialised kernel in the first warm-up step instead of in
     # the background, so that every timed step runs the same kernels
-    opts = PlanOpts.make(timing=True, jit=args.jit, mux=not args.no_mux, tile_qubits=args.tile_qubits, lookahead=args.lookahead, tile_io=args.tile_io)
+    opts = PlanOpts.make(timing=True, jit=args.jit, mux=not args.no_mux, phases=not args.no_phases, tile_qubits=args.tile_qubits, lookahead=args.lookahead, tile_io=args.tile_io)
 
     sv = StateVector(n, "complex128" if dtype == "c128" else "complex64")
     n_inputs = args.steps + args.warmup
@@ -380,6 +380,7 @@ def main():
     ap.add_argument("--qubits", type=int, default=None, help="pad the register to this many qubits (idle high qubits)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-mux", action="store_true", help="A/B switch: disable same-target multiplexor fusion")
+    ap.add_argument("--no-phases", action="store_true", help="A/B switch: disable register phases in tile sweeps")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU swap transport")
     ap.add_argument("--tile-qubits", type=int, default=0)
     ap.add_argument("--tile-io", type=int, default=0, help="0 one tile per CTA with bulk-async copies (default), 1 plain ld/st, 3 experimental persistent pipeline")

@@ -77,7 +77,7 @@ typedef struct b2sv_plan_opts {
                              pipeline, one CTA per SM (slower in round 1: only one load in flight per SM) */
     int32_t jit;          /* permutation runs: 0 = specialise with NVRTC in the background after first use
                              (default), 1 = never (generic kernel only), 2 = compile synchronously       */
-    int32_t reserved;     /* 1: no same-target multiplexor fusion (A/B switch); else 0                     */
+    int32_t reserved;     /* A/B switches: bit 0 = no multiplexor / block fusion, bit 1 = no register phases  */
 } b2sv_plan_opts;
 
 /* Subspace program (restates Subspace.test_basis / enumerate_basis,

@@ -24,6 +24,8 @@ VARIANTS = {
     "jit_sync": dict(jit="sync"),
     "jit_off": dict(jit="off"),
     "no_mux": dict(mux=False),
+    "no_phases": dict(phases=False),
+    "no_phases_no_mux": dict(phases=False, mux=False),
     "tile_pipelined": dict(tile_io=3),
     "tile_pipelined_tiles_only": dict(tile_io=3, perm_runs=False),
 }

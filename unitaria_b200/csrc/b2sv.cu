@@ -86,6 +86,7 @@ struct b2sv {
     size_t plan_ngates = 0;
     b2svk::Plan plan;
     std::vector<size_t> plan_seg_first;
+    std::vector<int> plan_seg_nops;
     b2sv_stats_t stats{};
     std::vector<TimedLaunch> timed;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> apply_events;
@@ -355,6 +356,55 @@ TileOp make_tile_op(const Plan& plan, const PGate& g, uint64_t tile_mask, const 
     return op;
 }
 
+// Group the ops of one tile sweep into register phases (kernels.cuh: tile_apply_phase): maximal runs of
+// consecutive plain gates whose targets fall on at most three tile-local positions.
+void append_with_phases(const std::vector<TileOp>& ops, int k, bool enable, std::vector<TileOp>& out) {
+    auto plain = [](const TileOp& o) {
+        return o.op == B2SV_OP_MAT1 || o.op == B2SV_OP_DIAG1 || o.op == B2SV_OP_X || o.op == B2SV_OP_SWAP || o.op == B2SV_OP_PHASE;
+    };
+    auto targets = [](const TileOp& o) -> uint32_t {
+        uint32_t t = 0;
+        if (o.op == B2SV_OP_PHASE) return 0;
+        if (o.tpos != 0xFF) t |= 1u << o.tpos;
+        if (o.op == B2SV_OP_SWAP) t |= 1u << o.tpos2;
+        return t;
+    };
+    size_t i = 0;
+    while (i < ops.size()) {
+        if (!enable || k < 3 || !plain(ops[i])) {
+            out.push_back(ops[i++]);
+            continue;
+        }
+        uint32_t R = targets(ops[i]);
+        size_t j = i + 1;
+        while (j < ops.size() && plain(ops[j]) && __builtin_popcount(R | targets(ops[j])) <= 3 && j - i < 60000) {
+            R |= targets(ops[j]);
+            ++j;
+        }
+        if (j - i < 2) {
+            out.push_back(ops[i++]);
+            continue;
+        }
+        // pad R to three positions with the HIGHEST free tile positions: a thread's eight amplitudes
+        // then sit far apart and neighbouring lanes read neighbouring addresses (no bank conflicts)
+        for (int p = k - 1; p >= 0 && __builtin_popcount(R) < 3; --p)
+            if (!((R >> p) & 1)) R |= 1u << p;
+        TileOp h{};
+        h.op = kOpPhase;
+        h.nfix = 3;
+        h.ph.count = (uint16_t)(j - i);
+        int nr = 0;
+        for (int p = 0; p < k; ++p)
+            if ((R >> p) & 1) {
+                h.fixpos |= (uint64_t)p << (4 * nr);
+                h.ph.rpos[nr++] = (uint8_t)p;
+            }
+        out.push_back(h);
+        for (size_t q = i; q < j; ++q) out.push_back(ops[q]);
+        i = j;
+    }
+}
+
 template <typename A>
 int set_tile_smem(size_t bytes) {
     static size_t configured = 0;
@@ -471,7 +521,7 @@ void encode_perm_gate(const PGate& g, int n, std::vector<uint4>& out) {
     for (size_t i = prologue.size(); i-- > 0;) out.push_back(prologue[i]);  // un-compute the temporaries
 }
 
-static_assert(kPlanMaxTileOps == kTileMaxOps, "planner and kernel disagree on the ops per tile sweep");
+static_assert(kPlanMaxTileOps + (kPlanMaxTileOps + 1) / 2 <= kTileMaxOps, "planner and kernel disagree on the ops per tile sweep");
 static_assert(kPermMaxCtrlX == 3 + 2 * kPermTemps && kPermMaxCtrlSwap == 2 + 2 * kPermTemps,
               "planner's control limits must match the scratch rows of k_perm");
 
@@ -879,7 +929,7 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
             key = (key ^ w[i]) * 1099511628211ull;
             key2 += w[i] * (2 * i + 1);
         }
-        const uint64_t o = (uint64_t)cfg.fuse | ((uint64_t)cfg.perm_runs << 1) | ((uint64_t)cfg.mux << 2) |
+        const uint64_t o = (uint64_t)cfg.fuse | ((uint64_t)cfg.perm_runs << 1) | ((uint64_t)cfg.mux << 2) | ((uint64_t)cfg.phases << 3) |
                            ((uint64_t)cfg.tile_qubits << 8) | ((uint64_t)cfg.lookahead << 16) | ((uint64_t)sv->scratch_failed << 40);
         key = (key ^ o) * 1099511628211ull;
     }
@@ -916,13 +966,17 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
         // tile ops of all tile segments, one upload
         std::vector<TileOp> host_ops;
         sv->plan_seg_first.assign(np.segs.size(), 0);
+        sv->plan_seg_nops.assign(np.segs.size(), 0);
         for (size_t s = 0; s < np.segs.size(); ++s) {
             const Segment& seg = np.segs[s];
             if (seg.cls != SEG_TILE) continue;
             ExpandArgs ex;
             fill_expand(ex, seg.tile_mask);
             sv->plan_seg_first[s] = host_ops.size();
-            for (int gi : seg.gates) host_ops.push_back(make_tile_op(np, np.gates[gi], seg.tile_mask, ex));
+            std::vector<TileOp> seg_ops;
+            for (int gi : seg.gates) seg_ops.push_back(make_tile_op(np, np.gates[gi], seg.tile_mask, ex));
+            append_with_phases(seg_ops, ex.m, cfg.phases, host_ops);
+            sv->plan_seg_nops[s] = (int)(host_ops.size() - sv->plan_seg_first[s]);
         }
         if (!host_ops.empty()) {
             const size_t bytes = host_ops.size() * sizeof(TileOp);
@@ -983,7 +1037,7 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
         } else if (seg.cls == SEG_TILE) {
             bool fused_ops = false;
             for (int gi : seg.gates) fused_ops |= plan.gates[gi].op == B2SV_OP_MUX || plan.gates[gi].op == B2SV_OP_BLOCK;
-            rc = launch_tile(sv, seg, (const TileOp*)sv->d_ops + seg_first[s], (int)seg.gates.size(), cfg, tile_io, fused_ops, timing, lazy_init);
+            rc = launch_tile(sv, seg, (const TileOp*)sv->d_ops + seg_first[s], sv->plan_seg_nops[s], cfg, tile_io, fused_ops, timing, lazy_init);
             if (lazy_init) sv->pending_basis = false;
         } else {
             rc = launch_perm(sv, plan, seg, timing, jit_mode);

@@ -139,10 +139,15 @@ struct __align__(16) TileOp {
             uint8_t kb;
             uint8_t bpos[3];       // tile-local positions of the block qubits (matrix index bit i)
         } blk;
+        struct {               // op == kOpPhase: header of a register phase, `count` member ops follow
+            uint16_t count;
+            uint8_t rpos[3];       // the three tile-local positions held in registers (ascending)
+        } ph;
     };
 };
 constexpr int kOpMux = 5;
 constexpr int kOpBlock = 6;
+constexpr int kOpPhase = 7;
 static_assert(sizeof(TileOp) == 96, "TileOp layout");
 
 struct TileArgs {
@@ -427,6 +432,112 @@ __device__ __forceinline__ void tile_apply_op(A* tile, const TileOp& op, int k, 
     }
 }
 
+// Register phase: consecutive plain gates whose targets fall on at most three tile qubits R are applied
+// WITHOUT going back to shared memory in between: a thread loads the 8 amplitudes of one R-group,
+// runs every gate of the phase on them in registers (targets are static register pairs, controls are
+// predicates: outside the tile CTA-uniform, inside the tile but outside R per group, inside R per
+// element) and stores them once.  One shared-memory round trip and one barrier per phase instead of
+// one per gate; X and SWAP stay exact register moves.
+#define B2SV_PAIRS(RP, F)                                   \
+    switch (RP) {                                           \
+        case 0: F(0, 1) F(2, 3) F(4, 5) F(6, 7) break;      \
+        case 1: F(0, 2) F(1, 3) F(4, 6) F(5, 7) break;      \
+        default: F(0, 4) F(1, 5) F(2, 6) F(3, 7) break;     \
+    }
+
+template <typename A>
+__device__ __forceinline__ void tile_apply_phase(A* tile, const TileOp& hdr, const TileOp* ops, int k, uint64_t base) {
+    const uint32_t r0 = hdr.ph.rpos[0], r1 = hdr.ph.rpos[1], r2 = hdr.ph.rpos[2];
+    const uint32_t b0 = 1u << r0, b1 = 1u << r1, b2 = 1u << r2, rmask = b0 | b1 | b2;
+    const int count = hdr.ph.count;
+    const uint32_t cnt = 1u << (k - 3);
+    for (uint32_t g = threadIdx.x; g < cnt; g += blockDim.x) {
+        const uint32_t l = expand_local(g, hdr.fixpos, 3);
+        uint32_t off[8];
+        double2 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            off[j] = l | ((j & 1) ? b0 : 0u) | ((j & 2) ? b1 : 0u) | ((j & 4) ? b2 : 0u);
+            v[j] = to_c128(tile[off[j]]);
+        }
+        for (int mi = 0; mi < count; ++mi) {
+            const TileOp& op = ops[mi];
+            if ((base & op.ext_ctrl) != op.ext_ctrl) continue;
+            const uint32_t lc = op.lctrl;
+            if ((l & lc & ~rmask) != (lc & ~rmask)) continue;
+            uint32_t ok = 0xFFu;  // bit j: element j of the group satisfies the controls that lie in R
+            if ((lc >> r0) & 1u) ok &= 0xAAu;
+            if ((lc >> r1) & 1u) ok &= 0xCCu;
+            if ((lc >> r2) & 1u) ok &= 0xF0u;
+            const int rp = op.tpos == r0 ? 0 : (op.tpos == r1 ? 1 : 2);
+            switch (op.op) {
+                case B2SV_OP_X: {
+#define B2SV_F(a, b)                       \
+    if ((ok >> a) & 1u) {                  \
+        const double2 t_ = v[a];           \
+        v[a] = v[b];                       \
+        v[b] = t_;                         \
+    }
+                    B2SV_PAIRS(rp, B2SV_F)
+#undef B2SV_F
+                } break;
+                case B2SV_OP_MAT1: {
+                    const double2 m00 = make_double2(op.m[0], op.m[1]), m01 = make_double2(op.m[2], op.m[3]);
+                    const double2 m10 = make_double2(op.m[4], op.m[5]), m11 = make_double2(op.m[6], op.m[7]);
+#define B2SV_F(a, b)                                   \
+    if ((ok >> a) & 1u) {                              \
+        const double2 x_ = v[a], y_ = v[b];            \
+        v[a] = cfma(m01, y_, cmul(m00, x_));           \
+        v[b] = cfma(m11, y_, cmul(m10, x_));           \
+    }
+                    B2SV_PAIRS(rp, B2SV_F)
+#undef B2SV_F
+                } break;
+                case B2SV_OP_DIAG1: {
+                    const double2 d0 = make_double2(op.m[0], op.m[1]), d1 = make_double2(op.m[2], op.m[3]);
+                    if (op.tpos == 0xFF) {
+                        const double2 d = (base & op.ext_tbit) ? d1 : d0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if ((ok >> j) & 1u) v[j] = cmul(d, v[j]);
+                    } else {
+#define B2SV_F(a, b)                   \
+    if ((ok >> a) & 1u) {              \
+        v[a] = cmul(d0, v[a]);         \
+        v[b] = cmul(d1, v[b]);         \
+    }
+                        B2SV_PAIRS(rp, B2SV_F)
+#undef B2SV_F
+                    }
+                } break;
+                case B2SV_OP_SWAP: {
+                    const int rq = op.tpos2 == r0 ? 0 : (op.tpos2 == r1 ? 1 : 2);
+                    const int pair = rp + rq;  // {0,1} -> 1, {0,2} -> 2, {1,2} -> 3
+#define B2SV_S(a, b)                       \
+    if ((ok >> a) & 1u) {                  \
+        const double2 t_ = v[a];           \
+        v[a] = v[b];                       \
+        v[b] = t_;                         \
+    }
+                    if (pair == 1) { B2SV_S(1, 2) B2SV_S(5, 6) }
+                    else if (pair == 2) { B2SV_S(1, 4) B2SV_S(3, 6) }
+                    else { B2SV_S(2, 4) B2SV_S(3, 5) }
+#undef B2SV_S
+                } break;
+                default: {  // PHASE
+                    const double2 w = make_double2(op.m[0], op.m[1]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if ((ok >> j) & 1u) v[j] = cmul(w, v[j]);
+                } break;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tile[off[j]] = from_c128<A>(v[j]);
+    }
+}
+#undef B2SV_PAIRS
+
 // global offset (in amplitudes, relative to the tile base) of chunk j of the tile
 __device__ __forceinline__ uint64_t chunk_offset(uint32_t j, const ExpandArgs& ex, int k, int lc) {
     uint64_t off = 0;
@@ -436,7 +547,7 @@ __device__ __forceinline__ uint64_t chunk_offset(uint32_t j, const ExpandArgs& e
 }
 
 template <typename A, bool BULK, bool FUSED>
-__global__ void __launch_bounds__(kThreads) k_tile(A* __restrict__ psi, const TileArgs a) {
+__global__ void __launch_bounds__(kThreads, 3) k_tile(A* __restrict__ psi, const TileArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     A* tile = reinterpret_cast<A*>(smem_raw);
     const int k = a.k, lc = a.lc;
@@ -489,6 +600,12 @@ __global__ void __launch_bounds__(kThreads) k_tile(A* __restrict__ psi, const Ti
 
     for (int o = 0; o < a.n_ops; ++o) {
         const TileOp& op = s_ops[o];
+        if (op.op == kOpPhase) {
+            tile_apply_phase<A>(tile, op, s_ops + o + 1, k, base);
+            __syncthreads();
+            o += op.ph.count;
+            continue;
+        }
         if ((base & op.ext_ctrl) != op.ext_ctrl) continue;  // CTA-uniform: gate not active on this tile
         tile_apply_op<A, FUSED>(tile, op, k, base, a.tables);
         __syncthreads();
@@ -589,6 +706,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(A* __restrict__ p
         }
         for (int o = 0; o < a.n_ops; ++o) {
             const TileOp& op = s_ops[o];
+            if (op.op == kOpPhase) {
+                tile_apply_phase<A>(tile, op, s_ops + o + 1, k, base);
+                __syncthreads();
+                o += op.ph.count;
+                continue;
+            }
             if ((base & op.ext_ctrl) != op.ext_ctrl) continue;
             tile_apply_op<A, FUSED>(tile, op, k, base, a.tables);
             __syncthreads();

@@ -39,7 +39,8 @@ constexpr int B2SV_OP_MUX = 5;        // internal: fused same-target run, a tabl
 constexpr int kMuxMaxCtrl = 6;        // table of at most 64 matrices (4 KiB)
 constexpr int B2SV_OP_BLOCK = 6;      // internal: fused run on <= 3 qubits, one dense 2^kb x 2^kb matrix
 constexpr int kBlockMaxQubits = 3;
-constexpr int kPlanMaxTileOps = 112;  // gates per tile sweep (their ops are staged in shared memory)
+constexpr int kPlanMaxTileOps = 74;   // gates per tile sweep: with one register-phase header per two gates
+                                      // they still fit the 112 op slots staged in shared memory
 
 struct PGate {
     uint8_t op;
@@ -80,6 +81,7 @@ struct PlanConfig {
     double perm_gate_cost = 1.0 / 300.0;  // cost of one perm gate in units of one full sweep
     bool always_tile_below = true;        // small states: prefer the fewest launches
     bool mux = true;                      // fuse same-target runs into multiplexed 2x2 ops
+    bool phases = true;                   // group plain gates of a sweep into register phases
 };
 
 // A run of consecutive gates on ONE target whose other qubits are only controls multiplies out to
@@ -127,7 +129,8 @@ inline PlanConfig default_config(int n, int dtype, const b2sv_plan_opts* o) {
         c.perm_runs = o->perm_runs != 0;
         if (o->tile_qubits > 0) c.tile_qubits = o->tile_qubits;
         if (o->lookahead > 0) c.lookahead = o->lookahead;
-        c.mux = o->reserved != 1;  // reserved == 1: no multiplexor fusion (A/B switch for tests and profiling)
+        c.mux = !(o->reserved & 1);     // reserved bit 0: no multiplexor / block fusion (A/B switch)
+        c.phases = !(o->reserved & 2);  // reserved bit 1: no register phases (A/B switch)
     }
     if (c.tile_qubits > 13 && c.amp_bytes == 16) c.tile_qubits = 13;
     if (c.tile_qubits > 14) c.tile_qubits = 14;
