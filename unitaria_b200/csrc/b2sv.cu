@@ -376,28 +376,44 @@ void append_with_phases(const std::vector<TileOp>& ops, int k, bool enable, std:
             continue;
         }
         uint32_t R = targets(ops[i]);
+        uint32_t K = ops[i].lctrl;  // tile-local controls shared by every gate taken so far
         size_t j = i + 1;
-        while (j < ops.size() && plain(ops[j]) && __builtin_popcount(R | targets(ops[j])) <= 3 && j - i < 60000) {
-            R |= targets(ops[j]);
+        auto pass_cost = [](uint32_t common_outside_r) { return std::ldexp(1.0, -__builtin_popcount(common_outside_r)); };
+        while (j < ops.size() && plain(ops[j]) && j - i < 60000) {
+            const uint32_t R2 = R | targets(ops[j]);
+            if (__builtin_popcount(R2) > 3) break;
+            // like the sweeps themselves: do not let one lightly controlled gate make a heavily
+            // controlled stretch walk over the whole tile
+            const double now = pass_cost(K & ~R2), joined = pass_cost(K & ops[j].lctrl & ~R2), alone = pass_cost(ops[j].lctrl & ~R2);
+            if (joined > now + 0.5 * alone) break;
+            R = R2;
+            K &= ops[j].lctrl;
             ++j;
         }
         if (j - i < 2) {
             out.push_back(ops[i++]);
             continue;
         }
-        // pad R to three positions with the HIGHEST free tile positions: a thread's eight amplitudes
-        // then sit far apart and neighbouring lanes read neighbouring addresses (no bank conflicts)
+        // pad R to three positions with the HIGHEST free tile positions that are not shared controls:
+        // a thread's eight amplitudes then sit far apart and neighbouring lanes read neighbouring
+        // addresses (no bank conflicts)
+        for (int p = k - 1; p >= 0 && __builtin_popcount(R) < 3; --p)
+            if (!((R >> p) & 1) && !((K >> p) & 1)) R |= 1u << p;
         for (int p = k - 1; p >= 0 && __builtin_popcount(R) < 3; --p)
             if (!((R >> p) & 1)) R |= 1u << p;
+        K &= ~R;
         TileOp h{};
         h.op = kOpPhase;
-        h.nfix = 3;
+        h.lctrl = K;
         h.ph.count = (uint16_t)(j - i);
         int nr = 0;
         for (int p = 0; p < k; ++p)
-            if ((R >> p) & 1) {
-                h.fixpos |= (uint64_t)p << (4 * nr);
-                h.ph.rpos[nr++] = (uint8_t)p;
+            if ((R >> p) & 1) h.ph.rpos[nr++] = (uint8_t)p;
+        h.nfix = 0;
+        for (int p = 0; p < k; ++p)
+            if (((R | K) >> p) & 1) {
+                h.fixpos |= (uint64_t)p << (4 * h.nfix);
+                h.nfix++;
             }
         out.push_back(h);
         for (size_t q = i; q < j; ++q) out.push_back(ops[q]);

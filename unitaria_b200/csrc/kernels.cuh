@@ -450,9 +450,11 @@ __device__ __forceinline__ void tile_apply_phase(A* tile, const TileOp& hdr, con
     const uint32_t r0 = hdr.ph.rpos[0], r1 = hdr.ph.rpos[1], r2 = hdr.ph.rpos[2];
     const uint32_t b0 = 1u << r0, b1 = 1u << r1, b2 = 1u << r2, rmask = b0 | b1 | b2;
     const int count = hdr.ph.count;
-    const uint32_t cnt = 1u << (k - 3);
+    // groups are enumerated over the tile bits that are neither register bits nor controls shared by
+    // every gate of the phase (hdr.lctrl): heavily controlled stretches only touch their own corner
+    const uint32_t cnt = 1u << (k - hdr.nfix);
     for (uint32_t g = threadIdx.x; g < cnt; g += blockDim.x) {
-        const uint32_t l = expand_local(g, hdr.fixpos, 3);
+        const uint32_t l = expand_local(g, hdr.fixpos, hdr.nfix) | hdr.lctrl;
         uint32_t off[8];
         double2 v[8];
 #pragma unroll
@@ -601,8 +603,12 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile(A* __restrict__ psi, const
     for (int o = 0; o < a.n_ops; ++o) {
         const TileOp& op = s_ops[o];
         if (op.op == kOpPhase) {
-            tile_apply_phase<A>(tile, op, s_ops + o + 1, k, base);
-            __syncthreads();
+            bool any = false;  // CTA-uniform: is any gate of the phase active on this tile?
+            for (int mi = 1; mi <= op.ph.count; ++mi) any |= (base & s_ops[o + mi].ext_ctrl) == s_ops[o + mi].ext_ctrl;
+            if (any) {
+                tile_apply_phase<A>(tile, op, s_ops + o + 1, k, base);
+                __syncthreads();
+            }
             o += op.ph.count;
             continue;
         }
@@ -707,8 +713,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(A* __restrict__ p
         for (int o = 0; o < a.n_ops; ++o) {
             const TileOp& op = s_ops[o];
             if (op.op == kOpPhase) {
-                tile_apply_phase<A>(tile, op, s_ops + o + 1, k, base);
-                __syncthreads();
+                bool any = false;
+                for (int mi = 1; mi <= op.ph.count; ++mi) any |= (base & s_ops[o + mi].ext_ctrl) == s_ops[o + mi].ext_ctrl;
+                if (any) {
+                    tile_apply_phase<A>(tile, op, s_ops + o + 1, k, base);
+                    __syncthreads();
+                }
                 o += op.ph.count;
                 continue;
             }
