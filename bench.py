@@ -277,7 +277,7 @@ def run_single(args):
     value = gates_live * args.steps / (ms * 1e-3)
 
     # dominant kernel class by device time
-    cls = max(("tile", "perm", "perm_jit", "gate1q"), key=lambda c: st["ms_by_class"][c])
+    cls = max(("tile", "perm", "perm_jit", "gate1q", "low6"), key=lambda c: st["ms_by_class"][c])
     launches = st["launches_by_class"][cls]
     peak, peak_src = measured_peak()
     per_launch_bytes = st["alg_bytes_by_class"][cls] / max(1, launches)
@@ -290,6 +290,7 @@ def run_single(args):
             "perm": "k_perm (permutation-run sweep, generic)",
             "perm_jit": "b2sv_perm_jit (permutation-run sweep, NVRTC-specialised)",
             "gate1q": "k_gate1",
+            "low6": "k_low6 (low-qubit warp-shuffle sweep)",
         }[cls],
         "achieved": achieved,
         "peak": peak,
@@ -302,7 +303,7 @@ def run_single(args):
         "traffic": recorded_traffic(cls),
     }
     kernels = {}
-    for c in ("tile", "perm", "perm_jit", "gate1q", "project", "init", "scale"):
+    for c in ("tile", "low6", "perm", "perm_jit", "gate1q", "project", "init", "scale"):
         L = st["launches_by_class"][c]
         if L:
             t = st["ms_by_class"][c]

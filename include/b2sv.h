@@ -77,7 +77,8 @@ typedef struct b2sv_plan_opts {
                              pipeline, one CTA per SM (slower in round 1: only one load in flight per SM) */
     int32_t jit;          /* permutation runs: 0 = specialise with NVRTC in the background after first use
                              (default), 1 = never (generic kernel only), 2 = compile synchronously       */
-    int32_t reserved;     /* A/B switches: bit 0 = no multiplexor / block fusion, bit 1 = no register phases  */
+    int32_t reserved;     /* A/B switches: bit 0 = no multiplexor / block fusion, bit 1 = no register phases,
+                             bit 2 = no warp-shuffle low-qubit sweeps */
 } b2sv_plan_opts;
 
 /* Subspace program (restates Subspace.test_basis / enumerate_basis,
@@ -107,9 +108,10 @@ typedef struct b2sv_stats_t {
     uint64_t gates_in;        /* lowered gates handed to b2sv_apply                                   */
     uint64_t gates_live;      /* ... of which not exact no-ops                                        */
     uint64_t launches;        /* kernel launches made by b2sv_apply                                   */
-    uint64_t launches_by_class[8]; /* 0 gate1q, 1 tile sweep, 2 perm run, 3 scale, 4 project, 5 init/convert, 6 swap pack, 7 perm run (NVRTC-specialised) */
-    double alg_bytes_by_class[8];  /* algorithmic bytes (2*B*M per sweep)                */
-    double ms_by_class[8];         /* CUDA-event time per class (only with opts.timing)                */
+    uint64_t launches_by_class[12]; /* 0 gate1q, 1 tile sweep, 2 perm run, 3 scale, 4 project, 5 init/convert, 6 swap pack,
+                                      7 perm run (NVRTC-specialised), 8 low-qubit warp-shuffle sweep */
+    double alg_bytes_by_class[12];  /* algorithmic bytes (2*B*M per sweep)                */
+    double ms_by_class[12];        /* CUDA-event time per class (only with opts.timing)                */
     double apply_ms;               /* CUDA-event time of whole b2sv_apply calls (always measured)      */
 } b2sv_stats_t;
 

@@ -33,7 +33,7 @@ def test_abi_version_and_struct_layouts():
     assert lib.b2sv_abi_version() == 1
     assert cabi.GATE_DTYPE.itemsize == 80 and cabi.SUBINSTR_DTYPE.itemsize == 32
     assert ctypes.sizeof(cabi.PlanOpts) == 32
-    assert ctypes.sizeof(cabi.Stats) == 8 * 3 + 8 * 8 * 3 + 8
+    assert ctypes.sizeof(cabi.Stats) == 8 * 3 + 8 * 12 * 3 + 8
 
 
 def test_no_gpu_fails_loudly_not_silently():

@@ -25,6 +25,7 @@ VARIANTS = {
     "jit_off": dict(jit="off"),
     "no_mux": dict(mux=False),
     "no_phases": dict(phases=False),
+    "no_low6": dict(low6=False),
     "no_phases_no_mux": dict(phases=False, mux=False),
     "tile_pipelined": dict(tile_io=3),
     "tile_pipelined_tiles_only": dict(tile_io=3, perm_runs=False),

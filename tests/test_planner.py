@@ -63,9 +63,11 @@ def test_plan_structure(name):
     k = 12
     seen = set()
     for cls, mask, idx in segs:
-        assert cls in (cabi.SEG_GATE1Q, cabi.SEG_TILE, cabi.SEG_PERM)
+        assert cls in (cabi.SEG_GATE1Q, cabi.SEG_TILE, cabi.SEG_PERM, cabi.SEG_LOW6)
         assert idx and not (set(idx) & seen)
         seen.update(idx)
+        if cls == cabi.SEG_LOW6:
+            assert mask == 0x3F
         if cls == cabi.SEG_TILE:
             assert popcount(mask) == min(k, n) and mask < (1 << n)
             for gi in idx:

@@ -18,8 +18,8 @@ LIB_PATH = os.path.join(_HERE, "libunitaria_b200.so")
 
 B2SV_C128, B2SV_C64 = 0, 1
 OP_MAT1, OP_DIAG1, OP_X, OP_SWAP, OP_PHASE = 0, 1, 2, 3, 4
-SEG_GATE1Q, SEG_TILE, SEG_PERM = 0, 1, 2
-CLASS_NAMES = ("gate1q", "tile", "perm", "scale", "project", "init", "swap", "perm_jit")
+SEG_GATE1Q, SEG_TILE, SEG_PERM, SEG_LOW6 = 0, 1, 2, 3
+CLASS_NAMES = ("gate1q", "tile", "perm", "scale", "project", "init", "swap", "perm_jit", "low6")
 
 # struct b2sv_gate (80 bytes)
 GATE_DTYPE = np.dtype(
@@ -56,7 +56,7 @@ class PlanOpts(ctypes.Structure):
     ]
 
     @classmethod
-    def make(cls, fuse=True, tile_qubits=0, perm_runs=True, timing=False, lookahead=0, plain_tile_io=False, jit="auto", mux=True, tile_io=None, phases=True):
+    def make(cls, fuse=True, tile_qubits=0, perm_runs=True, timing=False, lookahead=0, plain_tile_io=False, jit="auto", mux=True, tile_io=None, phases=True, low6=True):
         o = cls()
         o.fuse = int(bool(fuse))
         o.tile_qubits = int(tile_qubits)
@@ -65,7 +65,7 @@ class PlanOpts(ctypes.Structure):
         o.lookahead = int(lookahead)
         o.tile_io = (1 if plain_tile_io else 0) if tile_io is None else int(tile_io)
         o.jit = {"auto": 0, "off": 1, "sync": 2}[jit]
-        o.reserved = (0 if mux else 1) | (0 if phases else 2)
+        o.reserved = (0 if mux else 1) | (0 if phases else 2) | (0 if low6 else 4)
         return o
 
 
@@ -74,9 +74,9 @@ class Stats(ctypes.Structure):
         ("gates_in", ctypes.c_uint64),
         ("gates_live", ctypes.c_uint64),
         ("launches", ctypes.c_uint64),
-        ("launches_by_class", ctypes.c_uint64 * 8),
-        ("alg_bytes_by_class", ctypes.c_double * 8),
-        ("ms_by_class", ctypes.c_double * 8),
+        ("launches_by_class", ctypes.c_uint64 * 12),
+        ("alg_bytes_by_class", ctypes.c_double * 12),
+        ("ms_by_class", ctypes.c_double * 12),
         ("apply_ms", ctypes.c_double),
     ]
 
@@ -85,9 +85,9 @@ class Stats(ctypes.Structure):
             "gates_in": int(self.gates_in),
             "gates_live": int(self.gates_live),
             "launches": int(self.launches),
-            "launches_by_class": {CLASS_NAMES[i]: int(self.launches_by_class[i]) for i in range(8)},
-            "alg_bytes_by_class": {CLASS_NAMES[i]: float(self.alg_bytes_by_class[i]) for i in range(8)},
-            "ms_by_class": {CLASS_NAMES[i]: float(self.ms_by_class[i]) for i in range(8)},
+            "launches_by_class": {CLASS_NAMES[i]: int(self.launches_by_class[i]) for i in range(9)},
+            "alg_bytes_by_class": {CLASS_NAMES[i]: float(self.alg_bytes_by_class[i]) for i in range(9)},
+            "ms_by_class": {CLASS_NAMES[i]: float(self.ms_by_class[i]) for i in range(9)},
             "apply_ms": float(self.apply_ms),
         }
 

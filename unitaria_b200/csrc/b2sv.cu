@@ -46,7 +46,7 @@ int fail(int code, const char* fmt, ...) {
                         cudaGetErrorString(e_), __FILE__, __LINE__);                               \
     } while (0)
 
-enum { CLS_GATE1 = 0, CLS_TILE = 1, CLS_PERM = 2, CLS_SCALE = 3, CLS_PROJECT = 4, CLS_INIT = 5, CLS_SWAP = 6, CLS_PERM_JIT = 7, CLS_N = 8 };
+enum { CLS_GATE1 = 0, CLS_TILE = 1, CLS_PERM = 2, CLS_SCALE = 3, CLS_PROJECT = 4, CLS_INIT = 5, CLS_SWAP = 6, CLS_PERM_JIT = 7, CLS_LOW6 = 8, CLS_N = 12 };
 
 struct TimedLaunch {
     cudaEvent_t a, b;
@@ -500,6 +500,31 @@ int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, co
     });
 }
 
+int launch_low6(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, bool timing, bool lazy_init) {
+    if (n_ops > kTileMaxOps) return fail(B2SV_EINVAL, "low-qubit sweep with %d ops (max %d)", n_ops, kTileMaxOps);
+    Low6Args a{};
+    const uint64_t fixed = seg.tile_mask | seg.common_ctrl;
+    if (popcount64(fixed) > kMaxFixed) return fail(B2SV_EINVAL, "block + common controls exceed %d qubits", kMaxFixed);
+    fill_expand(a.blk_ex, fixed);
+    a.blk_or = seg.common_ctrl;
+    a.n_blocks = 1ull << (sv->n - a.blk_ex.m);
+    a.n_ops = n_ops;
+    a.ops = d_ops;
+    a.tables = (const double2*)sv->d_tables;
+    a.init_mode = lazy_init ? 1 : 0;
+    a.init_index = sv->basis_index;
+    const size_t smem = (size_t)kTileMaxOps * sizeof(TileOp);
+    const uint64_t want = (a.n_blocks + (kThreads / 32) - 1) / (kThreads / 32);
+    const uint64_t cap = (uint64_t)sv->sm_count * 8;
+    const unsigned grid = (unsigned)(want < cap ? (want ? want : 1) : cap);
+    return dispatch_dtype(sv, [&](auto* tag) -> int {
+        using A = std::remove_pointer_t<decltype(tag)>;
+        LaunchTimer lt(sv, timing, CLS_LOW6, (lazy_init ? 1.0 : 2.0) * sv->amp_bytes * (double)(a.n_blocks << kLowBits));
+        k_low6<A><<<grid, kThreads, smem, sv->stream>>>((A*)sv->amps, a);
+        return B2SV_OK;
+    });
+}
+
 // Encode one permutation gate as word ops (see kernels.cuh), in EXECUTION order.
 void encode_perm_gate(const PGate& g, int n, std::vector<uint4>& out) {
     auto row = [](int r) { return (uint32_t)r * (uint32_t)kPermRowBytes; };
@@ -945,7 +970,7 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
             key = (key ^ w[i]) * 1099511628211ull;
             key2 += w[i] * (2 * i + 1);
         }
-        const uint64_t o = (uint64_t)cfg.fuse | ((uint64_t)cfg.perm_runs << 1) | ((uint64_t)cfg.mux << 2) | ((uint64_t)cfg.phases << 3) |
+        const uint64_t o = (uint64_t)cfg.fuse | ((uint64_t)cfg.perm_runs << 1) | ((uint64_t)cfg.mux << 2) | ((uint64_t)cfg.phases << 3) | ((uint64_t)cfg.low6 << 4) |
                            ((uint64_t)cfg.tile_qubits << 8) | ((uint64_t)cfg.lookahead << 16) | ((uint64_t)sv->scratch_failed << 40);
         key = (key ^ o) * 1099511628211ull;
     }
@@ -985,13 +1010,13 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
         sv->plan_seg_nops.assign(np.segs.size(), 0);
         for (size_t s = 0; s < np.segs.size(); ++s) {
             const Segment& seg = np.segs[s];
-            if (seg.cls != SEG_TILE) continue;
+            if (seg.cls != SEG_TILE && seg.cls != SEG_LOW6) continue;
             ExpandArgs ex;
             fill_expand(ex, seg.tile_mask);
             sv->plan_seg_first[s] = host_ops.size();
             std::vector<TileOp> seg_ops;
             for (int gi : seg.gates) seg_ops.push_back(make_tile_op(np, np.gates[gi], seg.tile_mask, ex));
-            append_with_phases(seg_ops, ex.m, cfg.phases, host_ops);
+            append_with_phases(seg_ops, ex.m, cfg.phases && seg.cls == SEG_TILE, host_ops);
             sv->plan_seg_nops[s] = (int)(host_ops.size() - sv->plan_seg_first[s]);
         }
         if (!host_ops.empty()) {
@@ -1040,7 +1065,7 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
         const Segment& seg = plan.segs[s];
         int rc = B2SV_OK;
         // a pending basis state is generated by the first sweep if that sweep visits every tile
-        const bool lazy_init = sv->pending_basis && seg.cls == SEG_TILE && seg.common_ctrl == 0;
+        const bool lazy_init = sv->pending_basis && (seg.cls == SEG_TILE || seg.cls == SEG_LOW6) && seg.common_ctrl == 0;
         if (sv->pending_basis && !lazy_init) {
             rc = materialise(sv);
             if (rc) return rc;
@@ -1054,6 +1079,9 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
             bool fused_ops = false;
             for (int gi : seg.gates) fused_ops |= plan.gates[gi].op == B2SV_OP_MUX || plan.gates[gi].op == B2SV_OP_BLOCK;
             rc = launch_tile(sv, seg, (const TileOp*)sv->d_ops + seg_first[s], sv->plan_seg_nops[s], cfg, tile_io, fused_ops, timing, lazy_init);
+            if (lazy_init) sv->pending_basis = false;
+        } else if (seg.cls == SEG_LOW6) {
+            rc = launch_low6(sv, seg, (const TileOp*)sv->d_ops + seg_first[s], sv->plan_seg_nops[s], timing, lazy_init);
             if (lazy_init) sv->pending_basis = false;
         } else {
             rc = launch_perm(sv, plan, seg, timing, jit_mode);

@@ -737,6 +737,145 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(A* __restrict__ p
     if (tid < 32) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Low-qubit warp-shuffle sweep.  When every target of a sweep lies in the low six qubits (state
+// preparation on the low register: circuits/state_prep.py emits 2*2^k gates per target there), the
+// 64 amplitudes that interact are one contiguous, aligned 1 KiB block.  A warp holds such a block in
+// registers -- lane i owns amplitudes i and i+32 -- so qubit 5 is an in-thread pair and qubits 0..4
+// are butterfly exchanges with lane ^ (1 << q) by warp shuffle.  All gates of the sweep run back to
+// back on the registers; global memory is touched once in, once out, fully coalesced, and no shared
+// memory is involved.  Controls above the block are warp-uniform predicates.
+// ---------------------------------------------------------------------------------------------------
+struct Low6Args {
+    ExpandArgs blk_ex;   // low 6 bits + the sweep's common outside controls: block number -> base index
+    uint64_t blk_or;
+    uint64_t n_blocks;
+    int n_ops;
+    const TileOp* ops;   // built against the pseudo tile {0..5}: tile-local position == qubit
+    const double2* tables;
+    int init_mode;       // 1: generate the pending basis state |init_index> instead of loading
+    uint64_t init_index;
+};
+
+__device__ __forceinline__ double2 shfl_xor_c128(double2 v, int lane_mask) {
+    return make_double2(__shfl_xor_sync(0xffffffffu, v.x, lane_mask), __shfl_xor_sync(0xffffffffu, v.y, lane_mask));
+}
+
+// apply the 2x2 matrix (m00..m11) on `target` to the two amplitudes a lane owns (e0 = lane, e1 = lane|32);
+// ok0/ok1: the element satisfies the gate's in-block controls.  All 32 lanes must call this together.
+__device__ __forceinline__ void low6_apply_2x2(double2& v0, double2& v1, int lane, int target, bool ok0, bool ok1,
+                                               double2 m00, double2 m01, double2 m10, double2 m11) {
+    if (target == 5) {
+        const double2 n0 = cfma(m01, v1, cmul(m00, v0)), n1 = cfma(m11, v1, cmul(m10, v0));
+        if (ok0) {
+            v0 = n0;
+            v1 = n1;
+        }
+    } else {
+        const double2 p0 = shfl_xor_c128(v0, 1 << target), p1 = shfl_xor_c128(v1, 1 << target);
+        const bool hi = (lane >> target) & 1;
+        const double2 a = hi ? m11 : m00, b = hi ? m10 : m01;  // new = a * mine + b * partner
+        if (ok0) v0 = cfma(b, p0, cmul(a, v0));
+        if (ok1) v1 = cfma(b, p1, cmul(a, v1));
+    }
+}
+
+template <typename A>
+__global__ void __launch_bounds__(kThreads) k_low6(A* __restrict__ psi, const Low6Args a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TileOp* s_ops = reinterpret_cast<TileOp*>(smem_raw);
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.ops);
+        uint4* dst = reinterpret_cast<uint4*>(s_ops);
+        const int n16 = a.n_ops * (int)(sizeof(TileOp) / 16);
+        for (int i = threadIdx.x; i < n16; i += kThreads) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t e0 = lane, e1 = lane | 32;
+    const uint64_t warps = (uint64_t)gridDim.x * (kThreads / 32);
+    for (uint64_t b = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); b < a.n_blocks; b += warps) {
+        const uint64_t base = expand_bits(b, a.blk_ex) | a.blk_or;
+        double2 v0, v1;
+        if (a.init_mode) {
+            v0 = make_double2((base | e0) == a.init_index ? 1.0 : 0.0, 0.0);
+            v1 = make_double2((base | e1) == a.init_index ? 1.0 : 0.0, 0.0);
+        } else {
+            v0 = to_c128(psi[base + e0]);
+            v1 = to_c128(psi[base + e1]);
+        }
+        for (int o = 0; o < a.n_ops; ++o) {
+            const TileOp& op = s_ops[o];
+            if ((base & op.ext_ctrl) != op.ext_ctrl) continue;  // warp-uniform
+            const uint32_t lc = op.lctrl;
+            const bool ok0 = (e0 & lc) == lc, ok1 = (e1 & lc) == lc;
+            switch (op.op) {
+                case B2SV_OP_X:  // exact data movement: take the partner's amplitude, no arithmetic
+                    if (op.tpos == 5) {
+                        if (ok0) {
+                            const double2 t = v0;
+                            v0 = v1;
+                            v1 = t;
+                        }
+                    } else {
+                        const double2 p0 = shfl_xor_c128(v0, 1 << op.tpos), p1 = shfl_xor_c128(v1, 1 << op.tpos);
+                        if (ok0) v0 = p0;
+                        if (ok1) v1 = p1;
+                    }
+                    break;
+                case B2SV_OP_MAT1:
+                    low6_apply_2x2(v0, v1, lane, op.tpos, ok0, ok1, make_double2(op.m[0], op.m[1]), make_double2(op.m[2], op.m[3]),
+                                   make_double2(op.m[4], op.m[5]), make_double2(op.m[6], op.m[7]));
+                    break;
+                case B2SV_OP_DIAG1: {
+                    const double2 d0 = make_double2(op.m[0], op.m[1]), d1 = make_double2(op.m[2], op.m[3]);
+                    if (op.tpos == 0xFF) {
+                        const double2 d = (base & op.ext_tbit) ? d1 : d0;
+                        if (ok0) v0 = cmul(d, v0);
+                        if (ok1) v1 = cmul(d, v1);
+                    } else {
+                        if (ok0) v0 = cmul(((e0 >> op.tpos) & 1u) ? d1 : d0, v0);
+                        if (ok1) v1 = cmul(((e1 >> op.tpos) & 1u) ? d1 : d0, v1);
+                    }
+                } break;
+                case kOpMux: {
+                    uint32_t i0 = 0, i1 = 0;
+                    for (int j = 0; j < op.mux.nmux; ++j) {
+                        if (op.mux.mpos[j] == 0xFF) {
+                            const uint32_t bit = (uint32_t)((base >> op.mux.mq[j]) & 1ull) << j;
+                            i0 |= bit;
+                            i1 |= bit;
+                        } else {
+                            i0 |= ((e0 >> op.mux.mpos[j]) & 1u) << j;
+                            i1 |= ((e1 >> op.mux.mpos[j]) & 1u) << j;
+                        }
+                    }
+                    const double2* T0 = a.tables + (op.mux.table_off + i0) * 4;
+                    if (op.tpos == 5) {  // in-thread pair: both elements share the control bits, so i0 == i1
+                        low6_apply_2x2(v0, v1, lane, 5, ok0, ok1, __ldg(T0), __ldg(T0 + 1), __ldg(T0 + 2), __ldg(T0 + 3));
+                    } else {
+                        // the two elements of a lane may select different matrices (bit 5 can be a control)
+                        const double2* T1 = a.tables + (op.mux.table_off + i1) * 4;
+                        const bool hi = (lane >> op.tpos) & 1;
+                        const double2 p0 = shfl_xor_c128(v0, 1 << op.tpos), p1 = shfl_xor_c128(v1, 1 << op.tpos);
+                        const double2 a0 = __ldg(T0 + (hi ? 3 : 0)), b0 = __ldg(T0 + (hi ? 2 : 1));
+                        const double2 a1 = __ldg(T1 + (hi ? 3 : 0)), b1 = __ldg(T1 + (hi ? 2 : 1));
+                        if (ok0) v0 = cfma(b0, p0, cmul(a0, v0));
+                        if (ok1) v1 = cfma(b1, p1, cmul(a1, v1));
+                    }
+                } break;
+                default: {  // PHASE
+                    const double2 w = make_double2(op.m[0], op.m[1]);
+                    if (ok0) v0 = cmul(w, v0);
+                    if (ok1) v1 = cmul(w, v1);
+                } break;
+            }
+        }
+        psi[base + e0] = from_c128<A>(v0);
+        psi[base + e1] = from_c128<A>(v1);
+    }
+}
+
 // ===================================================================================================
 // 3. Permutation run: a run of X / multi-controlled X / (controlled) SWAP gates is a bijection f on
 //    amplitude indices.  One out-of-place sweep computes out[j] = in[f^-1(j)] (writes coalesced).

@@ -33,7 +33,8 @@
 
 namespace b2svk {
 
-enum SegClass { SEG_GATE1Q = 0, SEG_TILE = 1, SEG_PERM = 2 };
+enum SegClass { SEG_GATE1Q = 0, SEG_TILE = 1, SEG_PERM = 2, SEG_LOW6 = 3 };
+constexpr int kLowBits = 6;           // SEG_LOW6: every target within the low 6 qubits -> warp-shuffle sweep
 constexpr int kPermMaxCtrlX = 7, kPermMaxCtrlSwap = 6;
 constexpr int B2SV_OP_MUX = 5;        // internal: fused same-target run, a table of 2x2 matrices indexed by control bits
 constexpr int kMuxMaxCtrl = 6;        // table of at most 64 matrices (4 KiB)
@@ -82,6 +83,7 @@ struct PlanConfig {
     bool always_tile_below = true;        // small states: prefer the fewest launches
     bool mux = true;                      // fuse same-target runs into multiplexed 2x2 ops
     bool phases = true;                   // group plain gates of a sweep into register phases
+    bool low6 = true;                     // sweeps confined to the low 6 qubits use the warp-shuffle kernel
 };
 
 // A run of consecutive gates on ONE target whose other qubits are only controls multiplies out to
@@ -131,6 +133,7 @@ inline PlanConfig default_config(int n, int dtype, const b2sv_plan_opts* o) {
         if (o->lookahead > 0) c.lookahead = o->lookahead;
         c.mux = !(o->reserved & 1);     // reserved bit 0: no multiplexor / block fusion (A/B switch)
         c.phases = !(o->reserved & 2);  // reserved bit 1: no register phases (A/B switch)
+        c.low6 = !(o->reserved & 4);    // reserved bit 2: no warp-shuffle low-qubit sweeps (A/B switch)
     }
     if (c.tile_qubits > 13 && c.amp_bytes == 16) c.tile_qubits = 13;
     if (c.tile_qubits > 14) c.tile_qubits = 14;
@@ -590,6 +593,20 @@ inline void plan_tiles(const std::vector<PGate>& G, const std::vector<int>& idx,
                 out.push_back(std::move(one));
             }
         } else {
+            // state-preparation style sweeps: every (non-diagonal) target sits in the low kLowBits qubits,
+            // i.e. inside one 64-amplitude block a warp can hold in registers and exchange by shuffles
+            bool low = cfg.low6 && n >= kLowBits + 1;
+            for (int gi : seg.gates) {
+                const PGate& g = G[gi];
+                low = low && (g.tmask >> kLowBits) == 0 && g.op != B2SV_OP_SWAP && g.op != B2SV_OP_BLOCK;
+            }
+            if (low) {
+                seg.cls = SEG_LOW6;
+                seg.tile_mask = low_mask(kLowBits);
+                uint64_t Kc = ~0ull;
+                for (int gi : seg.gates) Kc &= G[gi].ctrl;
+                seg.common_ctrl = Kc & ~seg.tile_mask;
+            }
             out.push_back(std::move(seg));
         }
     }
@@ -649,7 +666,7 @@ inline Plan make_plan(const b2sv_gate* gates, size_t n_gates, const PlanConfig& 
                 plan_tiles(G, run, cfg, alt);
                 double tile_cost = 0;
                 for (const Segment& s : alt) {
-                    if (s.cls == SEG_TILE) tile_cost += sweep_cost(s.common_ctrl);
+                    if (s.cls == SEG_TILE || s.cls == SEG_LOW6) tile_cost += sweep_cost(s.common_ctrl);
                     else tile_cost += gate_sweep_fraction(G[s.gates[0]]);
                 }
                 const double perm_cost = 1.0 + cfg.perm_gate_cost * (double)len;

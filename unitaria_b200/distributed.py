@@ -565,7 +565,7 @@ def bench_main(args, case, config_dict, cpu_sample, ClockSampler, measured_peak)
         clk = clocks.stop()
         gates_live = len(live)
         peak, peak_src = measured_peak()
-        cls = max(("tile", "perm", "perm_jit", "gate1q"), key=lambda c: st["ms_by_class"][c])
+        cls = max(("tile", "low6", "perm", "perm_jit", "gate1q"), key=lambda c: st["ms_by_class"][c])
         L = max(1, st["launches_by_class"][cls])
         per_ms = st["ms_by_class"][cls] / L
         per_bytes = st["alg_bytes_by_class"][cls] / L
