@@ -122,23 +122,34 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 
 
-def cpu_sample(case, budget_s=20.0, stride=8):
+class CpuState:
+    """The CPU port's full-width complex128 register, allocated once (8 GiB for 29 qubits)."""
+
+    def __init__(self, case):
+        from oracle import c_oracle
+
+        self.n = max(1, case.n_qubits)
+        while True:
+            try:
+                self.psi = np.empty(2**self.n, dtype=np.complex128)
+                break
+            except MemoryError:
+                self.n -= 1  # host RAM too small for the full register: shrink and say so
+        c_oracle.lib().orc_set_basis(self.psi.ctypes.data, self.n, 0)
+        live = [g for g in case.gates if g.name.upper() != "I"]
+        self.live = len(live)
+        self.keep = [g for g in live if all(q < self.n for q in tuple(g.target) + tuple(g.control))]
+
+
+def cpu_sample(case, budget_s=20.0, stride=4, state=None):
     """Time the CPU port on a bounded sample of the workload: every `stride`-th live gate of the
     circuit applied to the FULL-width complex128 state (per-gate cost does not depend on the
     amplitudes' values).  Returns gates/s over the sample."""
     from oracle import c_oracle
 
-    n = max(1, case.n_qubits)
-    live = [g for g in case.gates if g.name.upper() != "I"]
-    while True:
-        try:
-            psi = np.empty(2**n, dtype=np.complex128)
-            break
-        except MemoryError:
-            n -= 1  # host RAM too small for the full register: shrink and say so
-    c_oracle.lib().orc_set_basis(psi.ctypes.data, n, 0)
-    keep = [g for g in live if all(q < n for q in tuple(g.target) + tuple(g.control))]
-    sample = keep[::stride]
+    st = state or CpuState(case)
+    n, psi = st.n, st.psi
+    sample = st.keep[::stride]
     enc = c_oracle.encode_gates(sample)
     c_oracle.apply_encoded(psi, n, enc[:2])  # touch pages / warm up
     done, t0 = 0, time.perf_counter()
@@ -154,7 +165,7 @@ def cpu_sample(case, budget_s=20.0, stride=8):
         "unit": "gates/s",
         "cores": c_oracle.max_threads(),
         "kind": "port",
-        "sample": f"{done} gates (every {stride}th live gate of {len(live)}) on the full {n}-qubit complex128 state, "
+        "sample": f"{done} gates (every {stride}th live gate of {st.live}) on the full {n}-qubit complex128 state, "
         f"{dt:.1f} s; reference-algorithm CPU restatement (one OpenMP sweep per gate, no fusion), not qulacs",
         "seconds": dt,
         "qubits": n,
@@ -166,13 +177,14 @@ def run_reference_arm(args):
     if rank != 0:
         return
     case = load_workload(args.workload or workload_for(args.gpus))
-    per_step_budget = max(2.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
+    per_step_budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    state = CpuState(case)
     for _ in range(args.warmup):
-        cpu_sample(case, budget_s=per_step_budget / 2)
+        cpu_sample(case, budget_s=per_step_budget / 2, state=state)
     vals, last = [], None
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        last = cpu_sample(case, budget_s=per_step_budget)
+        last = cpu_sample(case, budget_s=per_step_budget, state=state)
         vals.append(last["value"])
     total = time.perf_counter() - t0
     value = float(np.mean(vals))
@@ -390,6 +402,7 @@ def main():
     ap.add_argument("--jit", default="sync", choices=["sync", "auto", "off"], help="permutation-run kernel specialisation")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
+    args.family_n1 = None
     if args.warmup < 3 and args.impl == "ours" and not args.workload:
         args.warmup = max(args.warmup, 3)  # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
@@ -399,6 +412,8 @@ def main():
     else:
         from unitaria_b200 import distributed
 
+        if not args.workload:  # N = 1 member of the scaling family: same amplitudes per GPU
+            args.family_n1 = load_workload("cfg5_bits24")
         distributed.bench_main(args, load_workload(args.workload or workload_for(args.gpus)), config_dict, cpu_sample, ClockSampler, measured_peak)
 
 

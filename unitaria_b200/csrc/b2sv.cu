@@ -1120,6 +1120,8 @@ int b2sv_project_norm2_at(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, in
         k_project_norm2<A><<<grid, kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, index_base,
                                                              sv->d_partial);
         k_reduce_partials<<<1, kThreads, 0, sv->stream>>>(sv->d_partial, grid, sv->d_partial + sv->n_partial);
+        sv->stats.launches++;  // the reduction is a launch too
+        sv->stats.launches_by_class[CLS_PROJECT]++;
         return B2SV_OK;
     });
     if (rc) return rc;

@@ -500,6 +500,35 @@ def make_gpu_shard_factory(dtype: str, device: int):
     return lambda n_local: GpuShard(n_local, dtype, device)
 
 
+def _family_single_gpu(case1, dtype, device, jit):
+    """gates/s of the scaling family's single-GPU member (same amplitudes per GPU), 3 timed steps."""
+    from .cabi import PlanOpts
+    from .engine import StateVector
+    from .lowering import lower_gates
+    from .subspace_prog import SubspaceProgram
+
+    n1 = max(1, case1.n_qubits)
+    low = lower_gates(case1.gates, n1)
+    prog = SubspaceProgram(case1.meta["subspace_out"])
+    opts = PlanOpts.make(jit=jit)
+    with StateVector(n1, dtype=dtype, device=device) as sv:
+        for j in (1, 2, 3):
+            sv.set_basis(j)
+            sv.apply_lowered(low, opts)
+            sv.project_norm2(prog)
+        sv.sync()
+        sv.mark(0)
+        steps = 3
+        for j in range(steps):
+            sv.set_basis(5 + j)
+            sv.apply_lowered(low, opts)
+            sv.project_norm2(prog)
+        sv.mark(1)
+        ms = sv.elapsed_ms(0, 1)
+        live = sv.stats()["gates_live"] // (steps + 3)
+    return {"workload": case1.meta["name"], "qubits": n1, "gates_live": int(live), "ms_per_step": ms / steps, "value": live * steps / (ms * 1e-3), "unit": "gates/s"}
+
+
 def bench_main(args, case, config_dict, cpu_sample, ClockSampler, measured_peak):
     import json
 
@@ -522,6 +551,13 @@ def bench_main(args, case, config_dict, cpu_sample, ClockSampler, measured_peak)
     comm = TorchComm(device=torch.device(f"cuda:{local_rank}"))
     dtype = "complex128" if args.dtype == "c128" else "complex64"
     n = max(1, case.n_qubits)
+    # the scaling family keeps 2^(n - log2 N) amplitudes per GPU; its N = 1 member is measured here on
+    # rank 0 (bench.py's own N = 1 run is BASELINE config 2, a different circuit), so that the line
+    # carries what a weak-scaling efficiency has to be computed against
+    family_n1 = None
+    if rank == 0 and getattr(args, "family_n1", None) is not None:
+        family_n1 = _family_single_gpu(args.family_n1, dtype, local_rank, args.jit)
+    comm.barrier()
     sv = ShardedStateVector(n, comm, make_gpu_shard_factory(dtype, local_rank))
     exchange = "peer-memory pull (CUDA IPC mapped send buffers, one NVLink copy per swap)"
     if args.exchange == "nccl" or not comm.enable_peer_pull(sv.shard.send):
@@ -609,6 +645,7 @@ def bench_main(args, case, config_dict, cpu_sample, ClockSampler, measured_peak)
                 "breakdown_s_per_step_rank0": {k: sv.stats[k] / args.steps for k in ("pack_s", "barrier_s", "transfer_s", "unpack_s") if k in sv.stats},
                 "note": "seconds include pack + transfer + unpack",
             },
+            "weak_scaling_n1": family_n1,
             "kernels_rank0": {c: {"launches": st["launches_by_class"][c], "ms": st["ms_by_class"][c]} for c in st["ms_by_class"] if st["launches_by_class"][c]},
             "cpu_baseline": None,
             "e2e": {
