@@ -179,6 +179,18 @@ class TorchComm:
         torch.cuda.synchronize(src.device)
         torch.cuda.synchronize(recv_view.device)
 
+    def pull_async(self, recv_view, partner: int, first_byte: int):
+        """Enqueue recv_view <- partner's send buffer [first_byte, +len) and return an event that fires when
+        the bytes have landed (torch makes the destination device's current stream wait for a cross-device
+        copy, so an event recorded there afterwards covers it)."""
+        import torch
+
+        n = recv_view.numel()
+        recv_view.copy_(self.peer_send[partner][first_byte : first_byte + n], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(recv_view.device))
+        return ev
+
     def stream_sync(self, tensor) -> None:
         import torch
 
@@ -329,6 +341,18 @@ class ShardedStateVector:
                 for q in missing:
                     victim = self._pick_victim(need, i, exclude=set(nd))
                     self._swap(q, victim)
+                # While the engine is drained anyway, also bring in every other global qubit that will be
+                # a target later, as long as a local qubit with no further use can take its place: one
+                # flush instead of one per qubit keeps long fused runs (permutation sweeps) in one piece.
+                never = 1 << 60
+                for p in range(lay.n_local, lay.n):
+                    q = lay.at[p]
+                    if need.next_after(q, i) >= never:
+                        continue
+                    victim = self._pick_victim(need, i, exclude=set(nd))
+                    if victim is None or need.next_after(victim, i) < never:
+                        break
+                    self._swap(q, victim)
             lg = localise_gate(g, lay, self.rank)
             if lg is not None:
                 pending.append(lg)
@@ -366,11 +390,21 @@ class ShardedStateVector:
             tb = time.perf_counter()
             self.comm.allreduce_sum(0.0)              # light barrier: the partner's send buffer is complete
             tc = time.perf_counter()
-            _s, recv = self.shard.views(0, half)
-            self.comm.pull(recv, partner, 0)
-            td = time.perf_counter()
-            self.shard.unpack(pl, my_bit)
+            # all pieces are queued on the copy engine at once; piece c is unpacked while c+1.. still fly
+            step = max(1, half // max(1, chunks))
+            pending = []
+            for first in range(0, half, step):
+                count = min(step, half - first)
+                _s, recv = self.shard.views(first, count)
+                pending.append((self.comm.pull_async(recv, partner, first * b), first, count))
+            unpack_s = 0.0
+            for ev, first, count in pending:
+                ev.synchronize()
+                tu = time.perf_counter()
+                self.shard.unpack(pl, my_bit, first, count)
+                unpack_s += time.perf_counter() - tu
             te = time.perf_counter()
+            td = te - unpack_s  # transfer time not hidden behind unpacking
             self.comm.allreduce_sum(0.0)              # nobody re-packs while a peer is still reading
             tf = time.perf_counter()
             for key, dt in (("pack_s", tb - ta), ("barrier_s", tc - tb + tf - te), ("transfer_s", td - tc), ("unpack_s", te - td)):

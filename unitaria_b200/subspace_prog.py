@@ -201,6 +201,30 @@ class ShardProgram:
                 entry = emit(op=SUB_ZEROS, pos=p, len=1, next0=entry, next1=0, weight=0, add=0)
             elif rank_value(p):
                 entry = emit(op=SUB_REJECT, pos=0, len=0, next0=0, next1=0, weight=0, add=0)
+        # peephole: jump over the no-ops (FREE with weight 0) so the device walk only executes tests
+        def resolve(pc):
+            while out[pc]["op"] == SUB_FREE and out[pc]["weight"] == 0:
+                pc = out[pc]["next0"]
+            return pc
+
+        for r in out:
+            if r["op"] in (SUB_ZEROS, SUB_FREE):
+                r["next0"] = resolve(r["next0"])
+            elif r["op"] == SUB_BRANCH:
+                r["next0"], r["next1"] = resolve(r["next0"]), resolve(r["next1"])
+        entry = resolve(entry)
+        # merge chains of single-bit ZEROS on adjacent positions into one mask test
+        for r in out:
+            while r["op"] == SUB_ZEROS:
+                nx = out[r["next0"]]
+                if nx["op"] == SUB_ZEROS and nx["pos"] == r["pos"] + r["len"]:
+                    r["len"] += nx["len"]
+                    r["next0"] = nx["next0"]
+                elif nx["op"] == SUB_ZEROS and nx["pos"] + nx["len"] == r["pos"]:
+                    r["pos"], r["len"] = nx["pos"], r["len"] + nx["len"]
+                    r["next0"] = nx["next0"]
+                else:
+                    break
         if len(out) > 65535:
             raise ValueError("subspace program too long")
         self.instrs = np.zeros(len(out), dtype=SUBINSTR_DTYPE)
