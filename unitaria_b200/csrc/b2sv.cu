@@ -80,6 +80,13 @@ struct b2sv {
     double* d_partial = nullptr;   // projection partial sums (+1 slot for the result)
     int n_partial = 0;
     int sm_count = 148;
+    // TMA tensor maps of the (up to two) state buffers: rows of 128 bytes, SWIZZLE_128B, per chunk size
+    struct MapEntry {
+        void* ptr;
+        int rows_per_box;
+        CUtensorMap map;
+    };
+    std::vector<MapEntry> maps;
     // the plan of the last b2sv_apply (verify-style callers apply one circuit to many inputs)
     bool plan_valid = false;
     uint64_t plan_key = 0, plan_key2 = 0;
@@ -434,6 +441,57 @@ int set_tile_smem(size_t bytes) {
     return B2SV_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// Tensor map viewing the current state buffer as rows of 128 bytes with the hardware 128-byte swizzle.
+const CUtensorMap* state_tensor_map(b2sv* sv, int rows_per_box) {
+    for (auto& e : sv->maps)
+        if (e.ptr == sv->amps && e.rows_per_box == rows_per_box) return &e.map;
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return nullptr;
+    b2sv::MapEntry e{};
+    e.ptr = sv->amps;
+    e.rows_per_box = rows_per_box;
+    const cuuint64_t dims[2] = {16, (cuuint64_t)(sv->count * (uint64_t)sv->amp_bytes / 128)};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {16, (cuuint32_t)rows_per_box};
+    const cuuint32_t estr[2] = {1, 1};
+    if (fn(&e.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, sv->amps, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return nullptr;
+    if (sv->maps.size() >= 8) sv->maps.erase(sv->maps.begin());
+    sv->maps.push_back(e);
+    return &sv->maps.back().map;
+}
+
+template <typename A>
+int set_swz_smem(size_t bytes) {
+    static size_t configured = 0;
+    if (bytes > 48 * 1024 && configured < bytes) {
+        CU(cudaFuncSetAttribute(k_tile_swz<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        CU(cudaFuncSetAttribute(k_tile_swz<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured = bytes;
+    }
+    return B2SV_OK;
+}
+
 template <typename A>
 int set_pipe_smem(size_t bytes) {
     static size_t configured = 0;
@@ -468,6 +526,26 @@ int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, co
     const uint64_t n_tiles = 1ull << (sv->n - a.cta_ex.m);
     if (n_ops > kTileMaxOps) return fail(B2SV_EINVAL, "tile sweep with %d ops (max %d)", n_ops, kTileMaxOps);
     const size_t smem = ((size_t)sv->amp_bytes << a.k) + (size_t)kTileMaxOps * sizeof(TileOp);
+    // default path: TMA tensor copies with the hardware 128-byte swizzle (needs chunks of >= one 128-byte
+    // row and a tile of >= one 1 KiB swizzle atom; tiny registers use the linear bulk-copy kernel below)
+    const int row_shift = sv->amp_bytes == 16 ? 3 : 4;
+    if (tile_io == 0 && lc >= row_shift && a.k >= row_shift + 3 && (1 << (lc - row_shift)) <= 256) {
+        if (const CUtensorMap* map = state_tensor_map(sv, 1 << (lc - row_shift))) {
+            TileArgsSwz as;
+            as.map = *map;
+            as.t = a;
+            const size_t swz_smem = smem + 16;  // tile + ops + the mbarrier
+            return dispatch_dtype(sv, [&](auto* tag) -> int {
+                using A = std::remove_pointer_t<decltype(tag)>;
+                int rc = set_swz_smem<A>(swz_smem);
+                if (rc) return rc;
+                LaunchTimer lt(sv, timing, CLS_TILE, (lazy_init ? 1.0 : 2.0) * sv->amp_bytes * (double)(n_tiles << a.k));
+                if (fused_ops) k_tile_swz<A, true><<<(unsigned)n_tiles, kThreads, swz_smem, sv->stream>>>(as);
+                else k_tile_swz<A, false><<<(unsigned)n_tiles, kThreads, swz_smem, sv->stream>>>(as);
+                return B2SV_OK;
+            });
+        }
+    }
     if (tile_io == 3) {  // experimental: persistent three-stage pipeline, one CTA per SM (measured slower)
         const size_t pipe_smem = (((size_t)sv->amp_bytes << a.k) * kPipeStages) + (size_t)kTileMaxOps * sizeof(TileOp);
         const uint64_t grid = n_tiles < (uint64_t)sv->sm_count ? n_tiles : (uint64_t)sv->sm_count;

@@ -8,6 +8,7 @@
 // whole tile chunks), grids that are multiples of the SM count, and as few sweeps as possible.
 #pragma once
 
+#include <cuda.h>  // CUtensorMap (type only: the driver entry point is resolved at run time)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -210,6 +211,23 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
 
 constexpr int kTileMaxOps = 112;  // ops of one sweep are staged in shared memory (10.5 KiB)
 
+// View of a tile in shared memory.  SWZ = true: the tile was written by TMA tensor copies with the
+// hardware 128-byte swizzle (16-byte chunk index XOR row index mod 8), so element l lives at
+// l ^ f(l).  The swizzle is what makes the access patterns of gates on the LOW tile qubits -- fixed low
+// bits, i.e. every lane in the same 16-byte column of its 128-byte row -- spread over all banks
+// (ncu on Pseudoinverse(BPX) sweeps: 69 % of the shared-memory wavefronts were bank conflicts without it).
+template <typename A, bool SWZ>
+struct TileView {
+    A* p;
+    __device__ __forceinline__ A& operator[](uint32_t l) const {
+        if (SWZ) {
+            if (sizeof(A) == 16) l ^= (l >> 3) & 7u;
+            else l ^= ((l >> 4) & 7u) << 1;
+        }
+        return p[l];
+    }
+};
+
 // Enumerate the tile-local indices with the fixed positions cleared, UNROLL at a time, so that a
 // thread has UNROLL independent shared-memory round trips in flight (the tile phase is latency-
 // bound otherwise: 8 warps per CTA, a dependent LDS -> DFMA -> STS chain per element).
@@ -232,8 +250,8 @@ __device__ __forceinline__ void tile_for_each(uint32_t cnt, uint64_t fixpos, int
 
 // FUSED = false compiles the light variant (no table-driven ops): fewer registers for sweeps that
 // only hold plain gates.
-template <typename A, bool FUSED>
-__device__ __forceinline__ void tile_apply_op(A* tile, const TileOp& op, int k, uint64_t base,
+template <typename A, bool FUSED, typename TV>
+__device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, uint64_t base,
                                               const double2* __restrict__ tables) {
     const uint32_t cnt = 1u << (k - op.nfix);
     const uint64_t fixpos = op.fixpos;
@@ -445,8 +463,8 @@ __device__ __forceinline__ void tile_apply_op(A* tile, const TileOp& op, int k, 
         default: F(0, 4) F(1, 5) F(2, 6) F(3, 7) break;     \
     }
 
-template <typename A>
-__device__ __forceinline__ void tile_apply_phase(A* tile, const TileOp& hdr, const TileOp* ops, int k, uint64_t base) {
+template <typename A, typename TV>
+__device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, const TileOp* ops, int k, uint64_t base) {
     const uint32_t r0 = hdr.ph.rpos[0], r1 = hdr.ph.rpos[1], r2 = hdr.ph.rpos[2];
     const uint32_t b0 = 1u << r0, b1 = 1u << r1, b2 = 1u << r2, rmask = b0 | b1 | b2;
     const int count = hdr.ph.count;
@@ -550,7 +568,7 @@ __device__ __forceinline__ uint64_t chunk_offset(uint32_t j, const ExpandArgs& e
 
 template <typename A, bool BULK, bool FUSED>
 __global__ void __launch_bounds__(kThreads, 3) k_tile(A* __restrict__ psi, const TileArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     A* tile = reinterpret_cast<A*>(smem_raw);
     const int k = a.k, lc = a.lc;
     // the sweep's ops live behind the tile: fetched once, coalesced, while the tile is in flight
@@ -606,14 +624,14 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile(A* __restrict__ psi, const
             bool any = false;  // CTA-uniform: is any gate of the phase active on this tile?
             for (int mi = 1; mi <= op.ph.count; ++mi) any |= (base & s_ops[o + mi].ext_ctrl) == s_ops[o + mi].ext_ctrl;
             if (any) {
-                tile_apply_phase<A>(tile, op, s_ops + o + 1, k, base);
+                tile_apply_phase<A>(TileView<A, false>{tile}, op, s_ops + o + 1, k, base);
                 __syncthreads();
             }
             o += op.ph.count;
             continue;
         }
         if ((base & op.ext_ctrl) != op.ext_ctrl) continue;  // CTA-uniform: gate not active on this tile
-        tile_apply_op<A, FUSED>(tile, op, k, base, a.tables);
+        tile_apply_op<A, FUSED>(TileView<A, false>{tile}, op, k, base, a.tables);
         __syncthreads();
     }
 
@@ -635,6 +653,108 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile(A* __restrict__ psi, const
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Swizzled form of the tile sweep (the default whenever a tile chunk is at least one 128-byte row): the
+// chunks are moved by TMA *tensor* copies (cp.async.bulk.tensor.2d, SASS UTMALDG / UTMASTG) through a
+// tensor map that views the state as rows of 128 bytes with the hardware 128-byte swizzle, so the tile
+// lands in shared memory already XOR-swizzled and goes back un-swizzled, with no extra pass.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_g2s_2d(void* dst_smem, const CUtensorMap* map, uint32_t c0, uint32_t c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_s2g_2d(const CUtensorMap* map, uint32_t c0, uint32_t c1, const void* src_smem) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1),
+                 "r"(smem_u32(src_smem))
+                 : "memory");
+}
+
+struct alignas(64) TileArgsSwz {
+    CUtensorMap map;  // {16 doubles (128 B), rows}, box {16, rows per chunk}, SWIZZLE_128B
+    TileArgs t;
+};
+
+template <typename A, bool FUSED>
+__global__ void __launch_bounds__(kThreads, 3) k_tile_swz(const __grid_constant__ TileArgsSwz args) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const TileArgs& a = args.t;
+    A* tile_raw = reinterpret_cast<A*>(smem_raw);
+    const TileView<A, true> tile{tile_raw};
+    const int k = a.k, lc = a.lc;
+    TileOp* s_ops = reinterpret_cast<TileOp*>(smem_raw + ((size_t)sizeof(A) << k));
+    // the mbarrier lives in dynamic shared memory too: static shared memory would push the 1 KiB-aligned
+    // tile down by a whole kilobyte and cost the third resident CTA
+    uint64_t& bar = *reinterpret_cast<uint64_t*>(smem_raw + ((size_t)sizeof(A) << k) + (size_t)kTileMaxOps * sizeof(TileOp));
+    const int tid = threadIdx.x;
+    const uint32_t n_chunks = 1u << (k - lc), chunk_elems = 1u << lc;
+    const uint32_t chunk_bytes = chunk_elems * (uint32_t)sizeof(A);
+    constexpr int kRowShift = sizeof(A) == 16 ? 3 : 4;  // amplitudes per 128-byte row
+    const uint64_t base = expand_bits((uint64_t)blockIdx.x, a.cta_ex) | a.cta_or;
+    const bool load = a.init_mode == 0;
+
+    if (load) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) mbar_expect_tx(&bar, chunk_bytes * n_chunks);
+        __syncthreads();
+        for (uint32_t j = tid; j < n_chunks; j += kThreads) {
+            const uint64_t g = base | chunk_offset(j, a.tile_ex, k, lc);
+            tma_g2s_2d(tile_raw + (size_t)j * chunk_elems, &args.map, 0u, (uint32_t)(g >> kRowShift), &bar);
+        }
+    }
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.ops);
+        uint4* dst = reinterpret_cast<uint4*>(s_ops);
+        const int n16 = a.n_ops * (int)(sizeof(TileOp) / 16);
+        for (int i = tid; i < n16; i += kThreads) dst[i] = __ldg(src + i);
+    }
+    if (!load) {
+        const uint32_t elems = 1u << k;
+        const A zero = from_c128<A>(make_double2(0.0, 0.0));
+        for (uint32_t l = tid; l < elems; l += kThreads) tile_raw[l] = zero;
+        __syncthreads();
+        if (tid == 0 && (a.init_index & ~a.tile_mask) == base) {
+            uint32_t l = 0;
+            for (int i = 0; i < k; ++i) l |= (uint32_t)((a.init_index >> a.tile_ex.pos[i]) & 1ull) << i;
+            tile[l] = from_c128<A>(make_double2(1.0, 0.0));
+        }
+    } else {
+        mbar_wait(&bar, 0);
+    }
+    __syncthreads();
+
+    for (int o = 0; o < a.n_ops; ++o) {
+        const TileOp& op = s_ops[o];
+        if (op.op == kOpPhase) {
+            bool any = false;  // CTA-uniform: is any gate of the phase active on this tile?
+            for (int mi = 1; mi <= op.ph.count; ++mi) any |= (base & s_ops[o + mi].ext_ctrl) == s_ops[o + mi].ext_ctrl;
+            if (any) {
+                tile_apply_phase<A>(tile, op, s_ops + o + 1, k, base);
+                __syncthreads();
+            }
+            o += op.ph.count;
+            continue;
+        }
+        if ((base & op.ext_ctrl) != op.ext_ctrl) continue;  // CTA-uniform: gate not active on this tile
+        tile_apply_op<A, FUSED>(tile, op, k, base, a.tables);
+        __syncthreads();
+    }
+
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    for (uint32_t j = tid; j < n_chunks; j += kThreads) {
+        const uint64_t g = base | chunk_offset(j, a.tile_ex, k, lc);
+        tma_s2g_2d(&args.map, 0u, (uint32_t)(g >> kRowShift), tile_raw + (size_t)j * chunk_elems);
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Persistent, pipelined form of the tile sweep: ONE CTA per SM walks over its tiles with a ring of
 // three shared-memory stages, so that at any time one tile is arriving (bulk-async copies tracked by
 // an mbarrier), one is being worked on by all threads, and one is leaving (bulk-async stores).  The
@@ -647,7 +767,7 @@ constexpr int kPipeStages = 3;
 
 template <typename A, bool FUSED>
 __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(A* __restrict__ psi, const TileArgs a, uint32_t n_tiles) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int k = a.k, lc = a.lc;
     const size_t tile_bytes = (size_t)sizeof(A) << k;
     TileOp* s_ops = reinterpret_cast<TileOp*>(smem_raw + kPipeStages * tile_bytes);
@@ -716,14 +836,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(A* __restrict__ p
                 bool any = false;
                 for (int mi = 1; mi <= op.ph.count; ++mi) any |= (base & s_ops[o + mi].ext_ctrl) == s_ops[o + mi].ext_ctrl;
                 if (any) {
-                    tile_apply_phase<A>(tile, op, s_ops + o + 1, k, base);
+                    tile_apply_phase<A>(TileView<A, false>{tile}, op, s_ops + o + 1, k, base);
                     __syncthreads();
                 }
                 o += op.ph.count;
                 continue;
             }
             if ((base & op.ext_ctrl) != op.ext_ctrl) continue;
-            tile_apply_op<A, FUSED>(tile, op, k, base, a.tables);
+            tile_apply_op<A, FUSED>(TileView<A, false>{tile}, op, k, base, a.tables);
             __syncthreads();
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -782,7 +902,7 @@ __device__ __forceinline__ void low6_apply_2x2(double2& v0, double2& v1, int lan
 
 template <typename A>
 __global__ void __launch_bounds__(kThreads) k_low6(A* __restrict__ psi, const Low6Args a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     TileOp* s_ops = reinterpret_cast<TileOp*>(smem_raw);
     {
         const uint4* src = reinterpret_cast<const uint4*>(a.ops);
