@@ -592,7 +592,8 @@ int launch_low6(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, bo
     a.init_mode = lazy_init ? 1 : 0;
     a.init_index = sv->basis_index;
     const size_t smem = (size_t)kTileMaxOps * sizeof(TileOp);
-    const uint64_t want = (a.n_blocks + (kThreads / 32) - 1) / (kThreads / 32);
+    const uint64_t n_groups = (a.n_blocks + kLow6Blocks - 1) / kLow6Blocks;
+    const uint64_t want = (n_groups + (kThreads / 32) - 1) / (kThreads / 32);
     const uint64_t cap = (uint64_t)sv->sm_count * 8;
     const unsigned grid = (unsigned)(want < cap ? (want ? want : 1) : cap);
     return dispatch_dtype(sv, [&](auto* tag) -> int {

@@ -900,6 +900,38 @@ __device__ __forceinline__ void low6_apply_2x2(double2& v0, double2& v1, int lan
     }
 }
 
+constexpr int kLow6Blocks = 4;  // 64-amplitude blocks a warp holds at once (amortises the table look-ups)
+
+// coefficients of "new = ca * mine + cb * partner" of a multiplexor for the lane's two elements
+__device__ __forceinline__ void low6_mux_coeffs(const TileOp& op, const double2* __restrict__ tables, uint64_t base, uint32_t e0,
+                                                uint32_t e1, int tgt, bool hi, double2& ca0, double2& cb0, double2& ca1,
+                                                double2& cb1) {
+    uint32_t i0 = 0, i1 = 0;
+    for (int j = 0; j < op.mux.nmux; ++j) {
+        if (op.mux.mpos[j] == 0xFF) {
+            const uint32_t bit = (uint32_t)((base >> op.mux.mq[j]) & 1ull) << j;
+            i0 |= bit;
+            i1 |= bit;
+        } else {
+            i0 |= ((e0 >> op.mux.mpos[j]) & 1u) << j;
+            i1 |= ((e1 >> op.mux.mpos[j]) & 1u) << j;
+        }
+    }
+    const double2* T0 = tables + (op.mux.table_off + i0) * 4;
+    const double2* T1 = tables + (op.mux.table_off + i1) * 4;
+    if (tgt == 5) {  // in-thread pair: element 0 is the |0> row, element 1 the |1> row
+        ca0 = __ldg(T0);
+        cb0 = __ldg(T0 + 1);
+        ca1 = __ldg(T1 + 3);
+        cb1 = __ldg(T1 + 2);
+    } else {
+        ca0 = __ldg(T0 + (hi ? 3 : 0));
+        cb0 = __ldg(T0 + (hi ? 2 : 1));
+        ca1 = __ldg(T1 + (hi ? 3 : 0));
+        cb1 = __ldg(T1 + (hi ? 2 : 1));
+    }
+}
+
 template <typename A>
 __global__ void __launch_bounds__(kThreads) k_low6(A* __restrict__ psi, const Low6Args a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -911,88 +943,107 @@ __global__ void __launch_bounds__(kThreads) k_low6(A* __restrict__ psi, const Lo
         for (int i = threadIdx.x; i < n16; i += kThreads) dst[i] = __ldg(src + i);
     }
     __syncthreads();
+    constexpr int NB = kLow6Blocks;
     const int lane = threadIdx.x & 31;
     const uint32_t e0 = lane, e1 = lane | 32;
     const uint64_t warps = (uint64_t)gridDim.x * (kThreads / 32);
-    for (uint64_t b = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); b < a.n_blocks; b += warps) {
-        const uint64_t base = expand_bits(b, a.blk_ex) | a.blk_or;
-        double2 v0, v1;
-        if (a.init_mode) {
-            v0 = make_double2((base | e0) == a.init_index ? 1.0 : 0.0, 0.0);
-            v1 = make_double2((base | e1) == a.init_index ? 1.0 : 0.0, 0.0);
-        } else {
-            v0 = to_c128(psi[base + e0]);
-            v1 = to_c128(psi[base + e1]);
+    const uint64_t n_groups = (a.n_blocks + NB - 1) / NB;
+    for (uint64_t grp = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); grp < n_groups; grp += warps) {
+        uint64_t base[NB];
+        bool live[NB];
+        double2 v0[NB], v1[NB];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const uint64_t b = grp * NB + u;
+            live[u] = b < a.n_blocks;
+            base[u] = expand_bits(live[u] ? b : 0, a.blk_ex) | a.blk_or;
+            if (a.init_mode || !live[u]) {
+                v0[u] = make_double2(live[u] && (base[u] | e0) == a.init_index ? 1.0 : 0.0, 0.0);
+                v1[u] = make_double2(live[u] && (base[u] | e1) == a.init_index ? 1.0 : 0.0, 0.0);
+            } else {
+                v0[u] = to_c128(psi[base[u] + e0]);
+                v1[u] = to_c128(psi[base[u] + e1]);
+            }
         }
         for (int o = 0; o < a.n_ops; ++o) {
             const TileOp& op = s_ops[o];
-            if ((base & op.ext_ctrl) != op.ext_ctrl) continue;  // warp-uniform
             const uint32_t lc = op.lctrl;
             const bool ok0 = (e0 & lc) == lc, ok1 = (e1 & lc) == lc;
-            switch (op.op) {
-                case B2SV_OP_X:  // exact data movement: take the partner's amplitude, no arithmetic
-                    if (op.tpos == 5) {
-                        if (ok0) {
-                            const double2 t = v0;
-                            v0 = v1;
-                            v1 = t;
-                        }
-                    } else {
-                        const double2 p0 = shfl_xor_c128(v0, 1 << op.tpos), p1 = shfl_xor_c128(v1, 1 << op.tpos);
-                        if (ok0) v0 = p0;
-                        if (ok1) v1 = p1;
-                    }
-                    break;
-                case B2SV_OP_MAT1:
-                    low6_apply_2x2(v0, v1, lane, op.tpos, ok0, ok1, make_double2(op.m[0], op.m[1]), make_double2(op.m[2], op.m[3]),
-                                   make_double2(op.m[4], op.m[5]), make_double2(op.m[6], op.m[7]));
-                    break;
-                case B2SV_OP_DIAG1: {
-                    const double2 d0 = make_double2(op.m[0], op.m[1]), d1 = make_double2(op.m[2], op.m[3]);
-                    if (op.tpos == 0xFF) {
-                        const double2 d = (base & op.ext_tbit) ? d1 : d0;
-                        if (ok0) v0 = cmul(d, v0);
-                        if (ok1) v1 = cmul(d, v1);
-                    } else {
-                        if (ok0) v0 = cmul(((e0 >> op.tpos) & 1u) ? d1 : d0, v0);
-                        if (ok1) v1 = cmul(((e1 >> op.tpos) & 1u) ? d1 : d0, v1);
-                    }
-                } break;
-                case kOpMux: {
-                    uint32_t i0 = 0, i1 = 0;
-                    for (int j = 0; j < op.mux.nmux; ++j) {
-                        if (op.mux.mpos[j] == 0xFF) {
-                            const uint32_t bit = (uint32_t)((base >> op.mux.mq[j]) & 1ull) << j;
-                            i0 |= bit;
-                            i1 |= bit;
+            // coefficients of "new = ca * mine + cb * partner" for the lane's two elements, fetched once
+            // per gate for all NB blocks when they do not depend on bits above the block
+            double2 ca0 = make_double2(1, 0), cb0 = make_double2(0, 0), ca1 = ca0, cb1 = cb0;
+            bool per_block = false;
+            const int tgt = op.tpos;
+            const bool hi = tgt < 5 ? ((lane >> tgt) & 1) : false;
+            if (op.op == B2SV_OP_MAT1) {
+                if (tgt == 5) {
+                    ca0 = make_double2(op.m[0], op.m[1]);
+                    cb0 = make_double2(op.m[2], op.m[3]);
+                    ca1 = make_double2(op.m[6], op.m[7]);
+                    cb1 = make_double2(op.m[4], op.m[5]);
+                } else {
+                    ca0 = ca1 = hi ? make_double2(op.m[6], op.m[7]) : make_double2(op.m[0], op.m[1]);
+                    cb0 = cb1 = hi ? make_double2(op.m[4], op.m[5]) : make_double2(op.m[2], op.m[3]);
+                }
+            } else if (op.op == kOpMux) {
+                for (int j = 0; j < op.mux.nmux; ++j) per_block |= op.mux.mpos[j] == 0xFF;
+                if (!per_block) low6_mux_coeffs(op, a.tables, 0ull, e0, e1, tgt, hi, ca0, cb0, ca1, cb1);
+            }
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                if ((base[u] & op.ext_ctrl) != op.ext_ctrl) continue;  // warp-uniform
+                switch (op.op) {
+                    case B2SV_OP_X:  // exact data movement: take the partner's amplitude, no arithmetic
+                        if (tgt == 5) {
+                            if (ok0) {
+                                const double2 t = v0[u];
+                                v0[u] = v1[u];
+                                v1[u] = t;
+                            }
                         } else {
-                            i0 |= ((e0 >> op.mux.mpos[j]) & 1u) << j;
-                            i1 |= ((e1 >> op.mux.mpos[j]) & 1u) << j;
+                            const double2 p0 = shfl_xor_c128(v0[u], 1 << tgt), p1 = shfl_xor_c128(v1[u], 1 << tgt);
+                            if (ok0) v0[u] = p0;
+                            if (ok1) v1[u] = p1;
                         }
-                    }
-                    const double2* T0 = a.tables + (op.mux.table_off + i0) * 4;
-                    if (op.tpos == 5) {  // in-thread pair: both elements share the control bits, so i0 == i1
-                        low6_apply_2x2(v0, v1, lane, 5, ok0, ok1, __ldg(T0), __ldg(T0 + 1), __ldg(T0 + 2), __ldg(T0 + 3));
-                    } else {
-                        // the two elements of a lane may select different matrices (bit 5 can be a control)
-                        const double2* T1 = a.tables + (op.mux.table_off + i1) * 4;
-                        const bool hi = (lane >> op.tpos) & 1;
-                        const double2 p0 = shfl_xor_c128(v0, 1 << op.tpos), p1 = shfl_xor_c128(v1, 1 << op.tpos);
-                        const double2 a0 = __ldg(T0 + (hi ? 3 : 0)), b0 = __ldg(T0 + (hi ? 2 : 1));
-                        const double2 a1 = __ldg(T1 + (hi ? 3 : 0)), b1 = __ldg(T1 + (hi ? 2 : 1));
-                        if (ok0) v0 = cfma(b0, p0, cmul(a0, v0));
-                        if (ok1) v1 = cfma(b1, p1, cmul(a1, v1));
-                    }
-                } break;
-                default: {  // PHASE
-                    const double2 w = make_double2(op.m[0], op.m[1]);
-                    if (ok0) v0 = cmul(w, v0);
-                    if (ok1) v1 = cmul(w, v1);
-                } break;
+                        break;
+                    case B2SV_OP_DIAG1: {
+                        const double2 d0 = make_double2(op.m[0], op.m[1]), d1 = make_double2(op.m[2], op.m[3]);
+                        if (tgt == 0xFF) {
+                            const double2 d = (base[u] & op.ext_tbit) ? d1 : d0;
+                            if (ok0) v0[u] = cmul(d, v0[u]);
+                            if (ok1) v1[u] = cmul(d, v1[u]);
+                        } else {
+                            if (ok0) v0[u] = cmul(((e0 >> tgt) & 1u) ? d1 : d0, v0[u]);
+                            if (ok1) v1[u] = cmul(((e1 >> tgt) & 1u) ? d1 : d0, v1[u]);
+                        }
+                    } break;
+                    case B2SV_OP_PHASE: {
+                        const double2 w = make_double2(op.m[0], op.m[1]);
+                        if (ok0) v0[u] = cmul(w, v0[u]);
+                        if (ok1) v1[u] = cmul(w, v1[u]);
+                    } break;
+                    default: {  // MAT1 or multiplexor: new = ca * mine + cb * partner
+                        if (op.op == kOpMux && per_block) low6_mux_coeffs(op, a.tables, base[u], e0, e1, tgt, hi, ca0, cb0, ca1, cb1);
+                        double2 p0, p1;
+                        if (tgt == 5) {
+                            p0 = v1[u];
+                            p1 = v0[u];
+                        } else {
+                            p0 = shfl_xor_c128(v0[u], 1 << tgt);
+                            p1 = shfl_xor_c128(v1[u], 1 << tgt);
+                        }
+                        if (ok0) v0[u] = cfma(cb0, p0, cmul(ca0, v0[u]));
+                        if (ok1) v1[u] = cfma(cb1, p1, cmul(ca1, v1[u]));
+                    } break;
+                }
             }
         }
-        psi[base + e0] = from_c128<A>(v0);
-        psi[base + e1] = from_c128<A>(v1);
+#pragma unroll
+        for (int u = 0; u < NB; ++u)
+            if (live[u]) {
+                psi[base[u] + e0] = from_c128<A>(v0[u]);
+                psi[base[u] + e1] = from_c128<A>(v1[u]);
+            }
     }
 }
 
