@@ -966,17 +966,58 @@ __global__ void __launch_bounds__(kThreads) k_low6(A* __restrict__ psi, const Lo
             }
         }
         for (int o = 0; o < a.n_ops; ++o) {
+            // everything about the gate is warp-uniform; the per-block / per-element conditions are plain
+            // predicates, so the shuffles below are never inside divergent code
             const TileOp& op = s_ops[o];
             const uint32_t lc = op.lctrl;
-            const bool ok0 = (e0 & lc) == lc, ok1 = (e1 & lc) == lc;
-            // coefficients of "new = ca * mine + cb * partner" for the lane's two elements, fetched once
-            // per gate for all NB blocks when they do not depend on bits above the block
-            double2 ca0 = make_double2(1, 0), cb0 = make_double2(0, 0), ca1 = ca0, cb1 = cb0;
-            bool per_block = false;
+            const uint64_t ext = op.ext_ctrl;
+            const int kind = op.op;
             const int tgt = op.tpos;
+            const bool in_thread = tgt == 5;
+            const int xm = (tgt < 5) ? (1 << tgt) : 0;
             const bool hi = tgt < 5 ? ((lane >> tgt) & 1) : false;
-            if (op.op == B2SV_OP_MAT1) {
-                if (tgt == 5) {
+            const bool ok0 = (e0 & lc) == lc, ok1 = (e1 & lc) == lc;
+            bool a0[NB], a1[NB];
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                const bool act = (base[u] & ext) == ext;
+                a0[u] = act && ok0;
+                a1[u] = act && ok1;
+            }
+            if (kind == B2SV_OP_X) {  // exact data movement: take the partner's amplitude, no arithmetic
+#pragma unroll
+                for (int u = 0; u < NB; ++u) {
+                    const double2 p0 = in_thread ? v1[u] : shfl_xor_c128(v0[u], xm);
+                    const double2 p1 = in_thread ? v0[u] : shfl_xor_c128(v1[u], xm);
+                    if (a0[u]) v0[u] = p0;
+                    if (a1[u]) v1[u] = p1;
+                }
+            } else if (kind == B2SV_OP_DIAG1) {
+                const double2 d0 = make_double2(op.m[0], op.m[1]), d1 = make_double2(op.m[2], op.m[3]);
+                const bool ext_t = tgt == 0xFF;
+                const uint64_t tb = op.ext_tbit;
+                const double2 f0 = ext_t ? d0 : (((e0 >> (tgt & 7)) & 1u) ? d1 : d0);
+                const double2 f1 = ext_t ? d0 : (((e1 >> (tgt & 7)) & 1u) ? d1 : d0);
+#pragma unroll
+                for (int u = 0; u < NB; ++u) {
+                    const bool up = ext_t && (base[u] & tb);
+                    if (a0[u]) v0[u] = cmul(up ? d1 : f0, v0[u]);
+                    if (a1[u]) v1[u] = cmul(up ? d1 : f1, v1[u]);
+                }
+            } else if (kind == B2SV_OP_PHASE) {
+                const double2 w = make_double2(op.m[0], op.m[1]);
+#pragma unroll
+                for (int u = 0; u < NB; ++u) {
+                    if (a0[u]) v0[u] = cmul(w, v0[u]);
+                    if (a1[u]) v1[u] = cmul(w, v1[u]);
+                }
+            } else {  // MAT1 or multiplexor: new = ca * mine + cb * partner
+                double2 ca0, cb0, ca1, cb1;
+                bool per_block = false;
+                if (kind == kOpMux) {
+                    for (int j = 0; j < op.mux.nmux; ++j) per_block |= op.mux.mpos[j] == 0xFF;
+                    if (!per_block) low6_mux_coeffs(op, a.tables, 0ull, e0, e1, tgt, hi, ca0, cb0, ca1, cb1);
+                } else if (in_thread) {
                     ca0 = make_double2(op.m[0], op.m[1]);
                     cb0 = make_double2(op.m[2], op.m[3]);
                     ca1 = make_double2(op.m[6], op.m[7]);
@@ -985,56 +1026,14 @@ __global__ void __launch_bounds__(kThreads) k_low6(A* __restrict__ psi, const Lo
                     ca0 = ca1 = hi ? make_double2(op.m[6], op.m[7]) : make_double2(op.m[0], op.m[1]);
                     cb0 = cb1 = hi ? make_double2(op.m[4], op.m[5]) : make_double2(op.m[2], op.m[3]);
                 }
-            } else if (op.op == kOpMux) {
-                for (int j = 0; j < op.mux.nmux; ++j) per_block |= op.mux.mpos[j] == 0xFF;
-                if (!per_block) low6_mux_coeffs(op, a.tables, 0ull, e0, e1, tgt, hi, ca0, cb0, ca1, cb1);
-            }
 #pragma unroll
-            for (int u = 0; u < NB; ++u) {
-                if ((base[u] & op.ext_ctrl) != op.ext_ctrl) continue;  // warp-uniform
-                switch (op.op) {
-                    case B2SV_OP_X:  // exact data movement: take the partner's amplitude, no arithmetic
-                        if (tgt == 5) {
-                            if (ok0) {
-                                const double2 t = v0[u];
-                                v0[u] = v1[u];
-                                v1[u] = t;
-                            }
-                        } else {
-                            const double2 p0 = shfl_xor_c128(v0[u], 1 << tgt), p1 = shfl_xor_c128(v1[u], 1 << tgt);
-                            if (ok0) v0[u] = p0;
-                            if (ok1) v1[u] = p1;
-                        }
-                        break;
-                    case B2SV_OP_DIAG1: {
-                        const double2 d0 = make_double2(op.m[0], op.m[1]), d1 = make_double2(op.m[2], op.m[3]);
-                        if (tgt == 0xFF) {
-                            const double2 d = (base[u] & op.ext_tbit) ? d1 : d0;
-                            if (ok0) v0[u] = cmul(d, v0[u]);
-                            if (ok1) v1[u] = cmul(d, v1[u]);
-                        } else {
-                            if (ok0) v0[u] = cmul(((e0 >> tgt) & 1u) ? d1 : d0, v0[u]);
-                            if (ok1) v1[u] = cmul(((e1 >> tgt) & 1u) ? d1 : d0, v1[u]);
-                        }
-                    } break;
-                    case B2SV_OP_PHASE: {
-                        const double2 w = make_double2(op.m[0], op.m[1]);
-                        if (ok0) v0[u] = cmul(w, v0[u]);
-                        if (ok1) v1[u] = cmul(w, v1[u]);
-                    } break;
-                    default: {  // MAT1 or multiplexor: new = ca * mine + cb * partner
-                        if (op.op == kOpMux && per_block) low6_mux_coeffs(op, a.tables, base[u], e0, e1, tgt, hi, ca0, cb0, ca1, cb1);
-                        double2 p0, p1;
-                        if (tgt == 5) {
-                            p0 = v1[u];
-                            p1 = v0[u];
-                        } else {
-                            p0 = shfl_xor_c128(v0[u], 1 << tgt);
-                            p1 = shfl_xor_c128(v1[u], 1 << tgt);
-                        }
-                        if (ok0) v0[u] = cfma(cb0, p0, cmul(ca0, v0[u]));
-                        if (ok1) v1[u] = cfma(cb1, p1, cmul(ca1, v1[u]));
-                    } break;
+                for (int u = 0; u < NB; ++u) {
+                    if (per_block) low6_mux_coeffs(op, a.tables, base[u], e0, e1, tgt, hi, ca0, cb0, ca1, cb1);
+                    const double2 p0 = in_thread ? v1[u] : shfl_xor_c128(v0[u], xm);
+                    const double2 p1 = in_thread ? v0[u] : shfl_xor_c128(v1[u], xm);
+                    const double2 n0 = cfma(cb0, p0, cmul(ca0, v0[u])), n1 = cfma(cb1, p1, cmul(ca1, v1[u]));
+                    if (a0[u]) v0[u] = n0;
+                    if (a1[u]) v1[u] = n1;
                 }
             }
         }
