@@ -1026,14 +1026,34 @@ __global__ void __launch_bounds__(kThreads) k_low6(A* __restrict__ psi, const Lo
                     ca0 = ca1 = hi ? make_double2(op.m[6], op.m[7]) : make_double2(op.m[0], op.m[1]);
                     cb0 = cb1 = hi ? make_double2(op.m[4], op.m[5]) : make_double2(op.m[2], op.m[3]);
                 }
+                if (lc == 0 && ext == 0 && !per_block) {
+                    // the common state-preparation case: no predicate at all (a multiplexor carries its
+                    // controls in the table), so the update is unconditional straight-line FP64 code
+                    if (in_thread) {
 #pragma unroll
-                for (int u = 0; u < NB; ++u) {
-                    if (per_block) low6_mux_coeffs(op, a.tables, base[u], e0, e1, tgt, hi, ca0, cb0, ca1, cb1);
-                    const double2 p0 = in_thread ? v1[u] : shfl_xor_c128(v0[u], xm);
-                    const double2 p1 = in_thread ? v0[u] : shfl_xor_c128(v1[u], xm);
-                    const double2 n0 = cfma(cb0, p0, cmul(ca0, v0[u])), n1 = cfma(cb1, p1, cmul(ca1, v1[u]));
-                    if (a0[u]) v0[u] = n0;
-                    if (a1[u]) v1[u] = n1;
+                        for (int u = 0; u < NB; ++u) {
+                            const double2 x = v0[u], y = v1[u];
+                            v0[u] = cfma(cb0, y, cmul(ca0, x));
+                            v1[u] = cfma(cb1, x, cmul(ca1, y));
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < NB; ++u) {
+                            const double2 p0 = shfl_xor_c128(v0[u], xm), p1 = shfl_xor_c128(v1[u], xm);
+                            v0[u] = cfma(cb0, p0, cmul(ca0, v0[u]));
+                            v1[u] = cfma(cb1, p1, cmul(ca1, v1[u]));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < NB; ++u) {
+                        if (per_block) low6_mux_coeffs(op, a.tables, base[u], e0, e1, tgt, hi, ca0, cb0, ca1, cb1);
+                        const double2 p0 = in_thread ? v1[u] : shfl_xor_c128(v0[u], xm);
+                        const double2 p1 = in_thread ? v0[u] : shfl_xor_c128(v1[u], xm);
+                        const double2 n0 = cfma(cb0, p0, cmul(ca0, v0[u])), n1 = cfma(cb1, p1, cmul(ca1, v1[u]));
+                        if (a0[u]) v0[u] = n0;
+                        if (a1[u]) v1[u] = n1;
+                    }
                 }
             }
         }
