@@ -243,3 +243,23 @@ def test_bad_arguments_are_rejected():
             sv.apply_lowered(bad)
         with pytest.raises(cabi.B2svError):
             sv.project_norm2("#####")  # a 5-qubit subspace on a 3-qubit register
+
+
+def test_sampling_mode_matches_exact_norm_statistically():
+    """BackendEstimator's seam (estimator/backend_estimator.py:39-51): post-selected shot counts.  The
+    engine draws the two binomial counts from exact device reductions; with N shots the estimate must
+    sit within a few standard errors of the exact norm."""
+    case = load_golden("constant_vector5")  # ConstantVector(5 entries) on 3 qubits, subspace from_dim(5)
+
+    class C:
+        gates = case.gates
+
+    n, norm, spec = case.n_qubits, case.meta["normalization"], case.meta["subspace_out"]
+    exact = float(np.linalg.norm(case.arrays["expected"]))
+    rng = np.random.default_rng(7)
+    samples = 200_000
+    est = [adapter.estimate_norm_sampled(C, n, spec, norm, samples, rng=rng) for _ in range(8)]
+    p = (exact / norm) ** 2
+    stderr = norm * np.sqrt(p * (1 - p) / samples) / (2 * np.sqrt(p)) if 0 < p < 1 else 1e-9
+    assert abs(np.mean(est) - exact) < 6 * stderr / np.sqrt(len(est)) + 1e-9
+    assert all(abs(e - exact) < 8 * stderr + 1e-9 for e in est)

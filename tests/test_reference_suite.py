@@ -29,6 +29,7 @@ def _b200_backend():
     from tests.fake_engine import FakeStateVector
     adapter.StateVector = FakeStateVector      # test double instead of the CUDA engine
     unitaria_b200.install()
+    unitaria_b200.seed_sampling(1234)
     import tequila
     calls_before = len(tequila.SIM_CALLS)
     yield
@@ -48,7 +49,10 @@ def test_reference_suite_passes_through_our_host_path(tmp_path):
     cmd = [
         sys.executable, "-m", "pytest", "/root/reference/tests", "/root/reference/examples", "-q", "-x",
         "-p", "no:cacheprovider", "-p", "b200_plugin", "--import-mode=importlib", "-c", "/dev/null",
-        "-o", "python_files=test_*.py example_*.py", "--ignore=/root/reference/tests/estimator",
+        "-o", "python_files=test_*.py example_*.py",
+        # estimator/test_simulator.py never touches the simulation seam (binomial model + tequila's gate
+        # compiler for counting, which the stand-in does not provide); test_backend_estimator.py does
+        "--ignore=/root/reference/tests/estimator/test_simulator.py",
         "--rootdir", str(tmp_path),
     ]
     proc = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=str(tmp_path), timeout=1500)

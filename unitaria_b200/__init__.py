@@ -7,8 +7,8 @@ Hot path replaced: ``Circuit.simulate`` -> ``tq.simulate(..., backend="qulacs")`
 Public surface:
 
 * :func:`install` / :func:`uninstall` -- patch unitaria in place (drop-in backend).
-* :func:`simulate_circuit`, :func:`simulate_projected`, :func:`simulate_norm` -- the same calls on any
-  tequila-like circuit object.
+* :func:`simulate_circuit`, :func:`simulate_projected`, :func:`simulate_norm`,
+  :func:`estimate_norm_sampled` (sampling mode) -- the same calls on any tequila-like circuit object.
 * :class:`StateVector` -- one device-resident register; :class:`SubspaceProgram`; :func:`lower_gates`.
 
 There is no CPU fallback: the CUDA library must be built (``python -m unitaria_b200.build``) and a
@@ -18,7 +18,9 @@ CUDA device must be present for any compute call.
 from .adapter import (  # noqa: F401
     clear_caches,
     configure,
+    estimate_norm_sampled,
     install,
+    seed_sampling,
     simulate_circuit,
     simulate_norm,
     simulate_projected,

@@ -123,6 +123,55 @@ def simulate_norm(tq_circuit, n_qubits: int, subspace_out, normalization, input=
     return float(abs(normalization) * np.sqrt(_run(tq_circuit, n_qubits, input).project_norm2(prog)))
 
 
+_SAMPLING_RNG = np.random.default_rng()
+
+
+def seed_sampling(seed) -> None:
+    """Seed the generator behind :func:`estimate_norm_sampled` (sampling mode is random by nature)."""
+    global _SAMPLING_RNG
+    _SAMPLING_RNG = np.random.default_rng(seed)
+
+
+def estimate_norm_sampled(tq_circuit, n_qubits: int, subspace_out, normalization, samples: int, rng=None) -> float:
+    """Sampling mode of the seam: what ``BackendEstimator.estimate_norm`` computes from
+    ``tq.simulate(circuit, samples=N)`` (/root/reference/src/unitaria/estimator/backend_estimator.py:39-51).
+
+    The reference draws N bitstrings, discards those with an ancilla bit set (``k_int > max_result``) and
+    counts the survivors that pass ``subspace_out.test_basis``.  The two counts are binomial:
+    ``successful ~ B(N, p_anc0)`` and ``hits | successful ~ B(successful, p_member / p_anc0)`` with
+    ``p_anc0 = sum_{ancillae = 0} |psi_i|^2`` and ``p_member`` the same sum over the subspace -- two device
+    reductions.  Drawing them directly gives exactly the reference's distribution without materialising
+    N samples (N is ~10^5..10^7 from ``sample_bound``).
+    """
+    rng = rng or _SAMPLING_RNG
+    prog = subspace_out if isinstance(subspace_out, SubspaceProgram) else SubspaceProgram(subspace_out)
+    t = prog.total_qubits
+    if touches_any_qubit(tq_circuit.gates):
+        sv = _run(tq_circuit, n_qubits, 0)
+        p_member = sv.project_norm2(prog)
+        p_anc0 = sv.project_norm2(_all_free_program(t)) if t > 0 else p_member
+    else:  # the circuit leaves |0..0> untouched
+        member0 = len(prog.instrs) > 0 and bool(_state(max(1, t)).enumerate_basis(prog)[:1] == 0) if prog.dimension else False
+        p_member, p_anc0 = (1.0 if member0 else 0.0), 1.0
+    p_anc0 = min(1.0, max(0.0, p_anc0))
+    p_member = min(p_anc0, max(0.0, p_member))
+    successful = int(rng.binomial(int(samples), p_anc0))
+    if successful == 0:
+        return float("nan")  # the reference divides by zero here too
+    hits = int(rng.binomial(successful, p_member / p_anc0 if p_anc0 > 0 else 0.0))
+    return float(np.sqrt(hits / successful) * normalization)
+
+
+_FREE_PROGRAMS: dict = {}
+
+
+def _all_free_program(t: int) -> SubspaceProgram:
+    hit = _FREE_PROGRAMS.get(t)
+    if hit is None:
+        hit = _FREE_PROGRAMS[t] = SubspaceProgram("#" * t)
+    return hit
+
+
 def _host_project(prog: SubspaceProgram, vector: np.ndarray) -> np.ndarray:
     # only reached for circuits that touch no qubit (tiny registers): index list from the device
     sv = _state(max(1, prog.total_qubits))
@@ -182,6 +231,29 @@ def install(dtype="complex128", device: int = 0, opts: PlanOpts | None = None, p
             prog = _subspace_program(self.subspace_out)
             return simulate_norm(circuit._tq_circuit, circuit.n_qubits, prog, self.normalization, input)
 
+        try:  # sampling mode: BackendEstimator without materialised shots
+            import unitaria.estimator.backend_estimator as ube
+            from unitaria.util import sample_bound
+
+            if "BackendEstimator.estimate_norm" not in _ORIGINALS:
+                _ORIGINALS["BackendEstimator.estimate_norm"] = ube.BackendEstimator.estimate_norm
+
+            def backend_estimate_norm(self, node, precision=None, failure_probability=None):
+                if not node.is_vector():
+                    raise ValueError("Can only estimate the norm of vectors")
+                precision = self.default_precision if precision is None else precision
+                failure_probability = self.default_failure_probability if failure_probability is None else failure_probability
+                normalization = node.normalization
+                samples = sample_bound(precision / normalization, failure_probability)
+                circuit = node.circuit()
+                return estimate_norm_sampled(
+                    circuit._tq_circuit, circuit.n_qubits, _subspace_program(node.subspace_out), normalization, samples
+                )
+
+            ube.BackendEstimator.estimate_norm = backend_estimate_norm
+        except ImportError:  # pragma: no cover - a unitaria without the estimator package
+            pass
+
         node_simulate.__doc__ = _ORIGINALS["Node.simulate"].__doc__
         node_simulate_norm.__doc__ = _ORIGINALS["Node.simulate_norm"].__doc__
         Node.simulate = node_simulate
@@ -194,6 +266,10 @@ def uninstall() -> None:
         import unitaria.circuit as ucircuit
 
         ucircuit.Circuit.simulate = _ORIGINALS.pop("Circuit.simulate")
+    if "BackendEstimator.estimate_norm" in _ORIGINALS:
+        import unitaria.estimator.backend_estimator as ube
+
+        ube.BackendEstimator.estimate_norm = _ORIGINALS.pop("BackendEstimator.estimate_norm")
     if "Node.simulate" in _ORIGINALS:
         import unitaria.nodes.node as unode
 
