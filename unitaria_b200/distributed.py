@@ -168,17 +168,6 @@ class TorchComm:
             self.peer_send = {}
         return all_ok
 
-    def pull(self, recv_view, partner: int, first_byte: int) -> None:
-        """recv_view <- partner's send buffer [first_byte, +len(recv_view)) and wait for it.  torch runs a
-        cross-device copy on the SOURCE device's stream (of this process), so both devices are synchronised."""
-        import torch
-
-        n = recv_view.numel()
-        src = self.peer_send[partner][first_byte : first_byte + n]
-        recv_view.copy_(src, non_blocking=True)
-        torch.cuda.synchronize(src.device)
-        torch.cuda.synchronize(recv_view.device)
-
     def pull_async(self, recv_view, partner: int, first_byte: int):
         """Enqueue recv_view <- partner's send buffer [first_byte, +len) and return an event that fires when
         the bytes have landed (torch makes the destination device's current stream wait for a cross-device
@@ -190,11 +179,6 @@ class TorchComm:
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(recv_view.device))
         return ev
-
-    def stream_sync(self, tensor) -> None:
-        import torch
-
-        torch.cuda.current_stream(tensor.device).synchronize()
 
     def allreduce_min(self, value: float) -> float:
         import torch
@@ -230,7 +214,6 @@ class GpuShard:
 
         from .engine import StateVector
 
-        self.torch = torch
         self.device = device
         self.sv = StateVector(n_local, dtype=dtype, device=device)
         half_bytes = (self.sv.size // 2) * self.sv.amp_bytes
