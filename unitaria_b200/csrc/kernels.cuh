@@ -618,7 +618,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile(A* __restrict__ psi, const
     }
     __syncthreads();
 
-    for (int o = 0; o < a.n_ops; ++o) {
+    // a generated (lazy-init) tile that does not hold the basis index is all zeros: every gate maps it to
+    // itself, so only the one tile that owns the index runs the gates -- the others just write zeros
+    const int n_ops_here = (load || (a.init_index & ~a.tile_mask) == base) ? a.n_ops : 0;
+    for (int o = 0; o < n_ops_here; ++o) {
         const TileOp& op = s_ops[o];
         if (op.op == kOpPhase) {
             bool any = false;  // CTA-uniform: is any gate of the phase active on this tile?
@@ -727,7 +730,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile_swz(const __grid_constant_
     }
     __syncthreads();
 
-    for (int o = 0; o < a.n_ops; ++o) {
+    // a generated (lazy-init) tile that does not hold the basis index is all zeros: every gate maps it to
+    // itself, so only the one tile that owns the index runs the gates -- the others just write zeros
+    const int n_ops_here = (load || (a.init_index & ~a.tile_mask) == base) ? a.n_ops : 0;
+    for (int o = 0; o < n_ops_here; ++o) {
         const TileOp& op = s_ops[o];
         if (op.op == kOpPhase) {
             bool any = false;  // CTA-uniform: is any gate of the phase active on this tile?
