@@ -313,6 +313,9 @@ def run_single(args):
         "ms_per_launch": per_launch_ms,
         "launches": launches,
         "traffic": recorded_traffic(cls),
+        "note": "per launch = mean over the launches of the step; the first tile sweep after set_basis generates the "
+        "basis state in shared memory and only WRITES the state (algorithmic bytes 1*B*2^n, counted as such), and "
+        "write-only traffic runs above the read+write copy peak, which is how the mean can sit slightly above 1.0",
     }
     kernels = {}
     for c in ("tile", "low6", "perm", "perm_jit", "gate1q", "project", "init", "scale"):
