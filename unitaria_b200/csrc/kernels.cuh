@@ -352,7 +352,7 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
             // pair's control bits (tile-local ones per element, outside ones CTA-uniform)
             const uint32_t bt = 1u << op.tpos;
             const int nmux = op.mux.nmux;
-            uint32_t idx_ext = 0, lsel = 0;
+            uint32_t idx_ext = 0;
             uint8_t lp[7];
             int nl = 0, ljb[7];
             for (int j = 0; j < nmux; ++j) {
@@ -363,7 +363,6 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
                     ++nl;
                 }
             }
-            (void)lsel;
             const double2* __restrict__ tab = tables + op.mux.table_off * 4;
             tile_for_each<2>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
                 double2 v0[2], v1[2];
