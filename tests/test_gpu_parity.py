@@ -27,6 +27,8 @@ VARIANTS = {
     "no_phases": dict(phases=False),
     "no_low6": dict(low6=False),
     "no_phases_no_mux": dict(phases=False, mux=False),
+    "no_mono": dict(mono=False),
+    "no_mono_tiles_only": dict(mono=False, perm_runs=False),
     "tile_pipelined": dict(tile_io=3),
     "tile_pipelined_tiles_only": dict(tile_io=3, perm_runs=False),
 }
@@ -122,6 +124,49 @@ def test_permutation_circuits_are_bit_exact(n, variant):
         sv.apply(circuit.gates, PlanOpts.make(**VARIANTS[variant]))
         got = sv.download()
     assert np.count_nonzero(got) == 1 and got[np.flatnonzero(got)[0]] == 1
+
+
+def _perm_heavy(n, m, rng, max_controls=4):
+    kinds = ["X"] * 8 + ["CNOT"] * 3 + ["Toffoli"] * 3 + ["SWAP"] * 3 + ["Phase", "GlobalPhase", "Z", "Zp", "Rz"] * 2 + ["Ry", "H"]
+    return random_circuit(n, m, rng, kinds=kinds, max_controls=max_controls)
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("n,seed,tile_qubits", [(7, 0, 5), (9, 1, 6), (12, 2, 8), (14, 3, 0), (15, 4, 12), (16, 5, 13), (17, 6, 0), (20, 7, 0)])
+def test_monomial_phases_random(n, seed, tile_qubits, dtype):
+    """Runs of X / SWAP / phase gates inside tile sweeps (kernels.cuh: tile_apply_mono) against the oracle:
+    the same circuits the CPU suite pushes through the host emulator (tests/test_tile_emul.py)."""
+    rng = np.random.default_rng(seed)
+    circuit = _perm_heavy(n, 600, rng)
+    psi0 = random_state(n, rng)
+    want = c_oracle.simulate_gates(circuit.gates, n, psi0)
+    with StateVector(n, dtype) as sv:
+        for mono in (True, False):
+            sv.upload(psi0)
+            sv.apply(circuit.gates, PlanOpts.make(tile_qubits=tile_qubits, mono=mono, perm_runs=False))
+            got = sv.download()
+            assert np.abs(got - want).max() < tol(dtype, 600), (mono,)
+
+
+@pytest.mark.parametrize("dtype,n", [("complex128", 15), ("complex64", 15), ("complex128", 22)])
+def test_monomial_long_runs_are_bit_exact_and_batched(dtype, n):
+    """Several hundred X-family gates confined to ten qubits ride in ONE tile sweep: more ops than one staged
+    batch, four rounds per phase for complex64 tiles.  Pure permutations must be exact data movement."""
+    rng = np.random.default_rng(7)
+    circuit = random_circuit(n, 900, rng, kinds=["X", "CNOT", "Toffoli", "SWAP"], max_controls=3)
+    keep = [g for g in circuit.gates if all(t < 10 for t in g.target)]
+    psi0 = random_state(n, rng)
+    if dtype == "complex64":
+        psi0 = psi0.astype(np.complex64).astype(np.complex128)
+    want = c_oracle.simulate_gates(keep, n, psi0)
+    with StateVector(n, dtype) as sv:
+        sv.upload(psi0)
+        sv.stats_reset()
+        sv.apply(keep, PlanOpts.make(perm_runs=False))
+        got = sv.download()
+        launches = sv.stats()["launches_by_class"]
+    assert np.array_equal(got, want)
+    assert 1 <= launches["tile"] <= 8, launches
 
 
 @pytest.mark.parametrize("name", ["laplace_n12", "laplace_n16", "laplace_n20", "gaussian_s3_t13", "bpx_L4", "bpx_L5", "cfg5_bits13"])

@@ -1,0 +1,122 @@
+"""Tile-op programs (host side of the tile sweeps), checked on CPU.
+
+``tests/emul/tile_emul.cu`` is a host-only interpreter of the op programs that
+``unitaria_b200/csrc/tileops.hpp`` builds for the CUDA tile kernels: tile-local positions, fixed-position
+enumeration, register phases, monomial phases (round masks, shared controls), batch padding.  The
+planner and op builders are the product's, included unchanged; the result is compared with the CPU
+oracle.  The device code that interprets the same arrays is covered by the ``-m gpu`` parity tests.
+"""
+
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle
+from tests.helpers import load_golden, random_circuit, random_state
+from unitaria_b200 import cabi
+from unitaria_b200.lowering import lower_gates
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "emul", "tile_emul.cu")
+LIB = os.path.join(HERE, "emul", "libtile_emul.so")
+CSRC = os.path.join(os.path.dirname(HERE), "unitaria_b200", "csrc")
+INFO = ["tile", "perm", "gate1q", "low6", "mono_phases", "mono_members", "reg_phases", "reg_members", "max_ops", "nops", "mono_rounds_max"]
+
+
+def _build():
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("kernels.cuh", "planner.hpp", "tileops.hpp")]
+    if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
+        return LIB
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-o", LIB, SRC]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    return LIB
+
+
+@pytest.fixture(scope="module")
+def emul():
+    lib = ctypes.CDLL(_build())
+    lib.emul_apply.restype = ctypes.c_int
+    lib.emul_apply.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+
+    def run(gates, n, psi0, dtype=cabi.B2SV_C128, **kw):
+        live = [g for g in gates if g.name != "I"]
+        low = np.ascontiguousarray(lower_gates(live, n), dtype=cabi.GATE_DTYPE)
+        opts = cabi.PlanOpts.make(**kw)
+        amps = np.ascontiguousarray(psi0, dtype=np.complex128).copy()
+        info = np.zeros(len(INFO), dtype=np.int64)
+        rc = lib.emul_apply(n, dtype, low.ctypes.data, len(low), ctypes.byref(opts), amps.ctypes.data, info.ctypes.data)
+        assert rc == 0, f"emulator rejected the program: rc={rc}"
+        return amps, dict(zip(INFO, (int(x) for x in info)))
+
+    return run
+
+
+def perm_heavy_circuit(n, m, rng, max_controls=4):
+    """Mostly X / SWAP / phase gates with a few rotations: what ripple-carry arithmetic under selector
+    controls looks like (circuits/arithmetic.py), so that long monomial runs form."""
+    kinds = ["X"] * 8 + ["CNOT"] * 3 + ["Toffoli"] * 3 + ["SWAP"] * 3 + ["Phase", "GlobalPhase", "Z", "Zp", "Rz"] * 2 + ["Ry", "H"]
+    return random_circuit(n, m, rng, kinds=kinds, max_controls=max_controls)
+
+
+@pytest.mark.parametrize("n,seed,tile_qubits", [(7, 0, 5), (9, 1, 6), (12, 2, 8), (14, 3, 0), (15, 4, 12), (15, 5, 13)])
+@pytest.mark.parametrize("mono", [True, False])
+def test_random_permutation_heavy(emul, n, seed, tile_qubits, mono):
+    rng = np.random.default_rng(seed)
+    circuit = perm_heavy_circuit(n, 600, rng)
+    psi0 = random_state(n, rng)
+    want = np_oracle.simulate_gates([g for g in circuit.gates if g.name != "I"], n, psi0)
+    got, info = emul(circuit.gates, n, psi0, tile_qubits=tile_qubits, mono=mono, perm_runs=False)
+    assert np.abs(got - want).max() < 1e-12
+    if mono:
+        assert info["mono_phases"] > 0 and info["mono_members"] >= 2 * info["mono_phases"]
+    else:
+        assert info["mono_phases"] == 0
+
+
+@pytest.mark.parametrize("n,seed", [(8, 10), (13, 11), (14, 12)])
+@pytest.mark.parametrize("dtype", [cabi.B2SV_C128, cabi.B2SV_C64])
+def test_random_whole_alphabet(emul, n, seed, dtype):
+    rng = np.random.default_rng(seed)
+    circuit = random_circuit(n, 500, rng)
+    psi0 = random_state(n, rng)
+    want = np_oracle.simulate_gates([g for g in circuit.gates if g.name != "I"], n, psi0)
+    got, _ = emul(circuit.gates, n, psi0, dtype=dtype)
+    assert np.abs(got - want).max() < 1e-12
+
+
+def test_long_runs_are_batched_and_rounds_are_used(emul):
+    """A run of several hundred X-family gates on <= 11 qubits inside one sweep: more ops than one staged
+    batch holds, phases never straddle a batch boundary (the emulator rejects that), 13-qubit tiles need
+    four rounds per monomial phase."""
+    n = 15
+    rng = np.random.default_rng(7)
+    circuit = random_circuit(n, 900, rng, kinds=["X", "CNOT", "Toffoli", "SWAP", "Phase"], max_controls=3)
+    # confine the moved qubits to ten of them so that the run fits one tile sweep
+    keep = [g for g in circuit.gates if all(t < 10 for t in g.target)]
+    psi0 = random_state(n, rng)
+    want = np_oracle.simulate_gates(keep, n, psi0)
+    for dtype, rounds in ((cabi.B2SV_C128, 2), (cabi.B2SV_C64, 4)):
+        got, info = emul(keep, n, psi0, dtype=dtype, perm_runs=False)
+        assert np.abs(got - want).max() < 1e-12
+        assert info["max_ops"] > 112, info
+        assert info["mono_rounds_max"] == rounds, info
+
+
+@pytest.mark.parametrize("name", ["bpx_L3", "bpx_L4", "pinv_bpx_L2", "laplace_n12", "gaussian_s3_t8", "cfg5_bits5", "qsvt_inc2_cheb", "sinv_rhs_bpx_L2"])
+def test_goldens_through_the_tile_programs(emul, name):
+    case = load_golden(name)
+    n = case.n_qubits
+    rng = np.random.default_rng(3)
+    psi0 = random_state(n, rng)
+    live = [g for g in case.gates if g.name != "I"]
+    want = np_oracle.simulate_gates(live, n, psi0)
+    got, info = emul(case.gates, n, psi0)
+    assert np.abs(got - want).max() < 1e-12, info

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libunitaria_b200.so")
 SOURCES = ["b2sv.cu"]
-HEADERS = ["kernels.cuh", "planner.hpp", "perm_jit.hpp", os.path.join("..", "..", "include", "b2sv.h")]
+HEADERS = ["kernels.cuh", "planner.hpp", "tileops.hpp", "perm_jit.hpp", os.path.join("..", "..", "include", "b2sv.h")]
 
 NVCC_FLAGS = [
     "-gencode",

@@ -22,6 +22,7 @@
 #include "../../include/b2sv.h"
 #include "kernels.cuh"
 #include "planner.hpp"
+#include "tileops.hpp"
 #include "perm_jit.hpp"
 
 namespace {
@@ -249,12 +250,6 @@ int materialise(b2sv* sv) {
 
 // ---- launch helpers ---------------------------------------------------------------------------
 
-void fill_expand(ExpandArgs& ex, uint64_t mask) {
-    ex.m = 0;
-    for (int q = 0; q < 64; ++q)
-        if ((mask >> q) & 1) ex.pos[ex.m++] = (uint8_t)q;
-}
-
 int launch_gate1(b2sv* sv, const PGate& g, bool timing) {
     Gate1Args a{};
     uint64_t fixed = g.ctrl;
@@ -286,146 +281,6 @@ int launch_gate1(b2sv* sv, const PGate& g, bool timing) {
         k_gate1<A><<<grid_for(sv, a.count), kThreads, 0, sv->stream>>>((A*)sv->amps, a);
         return B2SV_OK;
     });
-}
-
-// Translate a planned gate into a tile-local op for the tile with (ascending) qubit positions `ex`.
-TileOp make_tile_op(const Plan& plan, const PGate& g, uint64_t tile_mask, const ExpandArgs& ex) {
-    TileOp op{};
-    auto local_pos = [&](int q) -> int {
-        for (int i = 0; i < ex.m; ++i)
-            if (ex.pos[i] == q) return i;
-        return -1;
-    };
-    op.op = g.op;
-    op.tpos = op.tpos2 = 0;
-    op.ext_ctrl = g.ctrl & ~tile_mask;
-    op.ext_tbit = 0;
-    uint32_t lctrl = 0;
-    for (int i = 0; i < ex.m; ++i)
-        if ((g.ctrl >> ex.pos[i]) & 1) lctrl |= 1u << i;
-    op.lctrl = lctrl;
-    uint32_t fixed = lctrl;
-    switch (g.op) {
-        case B2SV_OP_PHASE:
-            break;
-        case B2SV_OP_DIAG1: {
-            const int p = local_pos(g.t0);
-            if (p < 0) {
-                op.tpos = 0xFF;
-                op.ext_tbit = 1ull << g.t0;
-            } else {
-                op.tpos = (uint8_t)p;
-                fixed |= 1u << p;
-            }
-        } break;
-        case B2SV_OP_SWAP:
-            op.tpos = (uint8_t)local_pos(g.t0);
-            op.tpos2 = (uint8_t)local_pos(g.t1);
-            fixed |= (1u << op.tpos) | (1u << op.tpos2);
-            break;
-        case B2SV_OP_BLOCK: {
-            const BlockInfo& bi = plan.blocks[g.blk];
-            for (int i = 0; i < bi.kb; ++i) fixed |= 1u << local_pos(bi.q[i]);
-        } break;
-        default:
-            op.tpos = (uint8_t)local_pos(g.t0);
-            fixed |= 1u << op.tpos;
-            break;
-    }
-    op.nfix = 0;
-    op.fixpos = 0;
-    for (int i = 0; i < ex.m; ++i)
-        if ((fixed >> i) & 1) {
-            op.fixpos |= (uint64_t)i << (4 * op.nfix);
-            op.nfix++;
-        }
-    std::memcpy(op.m, g.m, sizeof(op.m));
-    if (g.op == B2SV_OP_BLOCK) {
-        const BlockInfo& bi = plan.blocks[g.blk];
-        op.blk.mat_off = bi.mat_off;
-        op.blk.kb = (uint8_t)bi.kb;
-        for (int i = 0; i < bi.kb; ++i) op.blk.bpos[i] = (uint8_t)local_pos(bi.q[i]);
-    }
-    if (g.op == B2SV_OP_MUX) {
-        const MuxInfo& mi = plan.mux[g.mux];
-        // g.ctrl (the run's common controls) is already a predicate in lctrl / ext_ctrl
-        op.mux.table_off = mi.table_off;
-        op.mux.nmux = (uint8_t)mi.nbits;
-        int j = 0;
-        for (int q = 0; q < 64 && j < mi.nbits; ++q)
-            if ((mi.ctrl_mask >> q) & 1) {
-                const int lp = local_pos(q);
-                op.mux.mpos[j] = lp < 0 ? 0xFF : (uint8_t)lp;
-                op.mux.mq[j] = (uint8_t)q;
-                ++j;
-            }
-    }
-    return op;
-}
-
-// Group the ops of one tile sweep into register phases (kernels.cuh: tile_apply_phase): maximal runs of
-// consecutive plain gates whose targets fall on at most three tile-local positions.
-void append_with_phases(const std::vector<TileOp>& ops, int k, bool enable, std::vector<TileOp>& out) {
-    auto plain = [](const TileOp& o) {
-        return o.op == B2SV_OP_MAT1 || o.op == B2SV_OP_DIAG1 || o.op == B2SV_OP_X || o.op == B2SV_OP_SWAP || o.op == B2SV_OP_PHASE;
-    };
-    auto targets = [](const TileOp& o) -> uint32_t {
-        uint32_t t = 0;
-        if (o.op == B2SV_OP_PHASE) return 0;
-        if (o.tpos != 0xFF) t |= 1u << o.tpos;
-        if (o.op == B2SV_OP_SWAP) t |= 1u << o.tpos2;
-        return t;
-    };
-    size_t i = 0;
-    while (i < ops.size()) {
-        if (!enable || k < 3 || !plain(ops[i])) {
-            out.push_back(ops[i++]);
-            continue;
-        }
-        uint32_t R = targets(ops[i]);
-        uint32_t K = ops[i].lctrl;  // tile-local controls shared by every gate taken so far
-        size_t j = i + 1;
-        auto pass_cost = [](uint32_t common_outside_r) { return std::ldexp(1.0, -__builtin_popcount(common_outside_r)); };
-        while (j < ops.size() && plain(ops[j]) && j - i < 60000) {
-            const uint32_t R2 = R | targets(ops[j]);
-            if (__builtin_popcount(R2) > 3) break;
-            // like the sweeps themselves: do not let one lightly controlled gate make a heavily
-            // controlled stretch walk over the whole tile
-            const double now = pass_cost(K & ~R2), joined = pass_cost(K & ops[j].lctrl & ~R2), alone = pass_cost(ops[j].lctrl & ~R2);
-            if (joined > now + 0.5 * alone) break;
-            R = R2;
-            K &= ops[j].lctrl;
-            ++j;
-        }
-        if (j - i < 2) {
-            out.push_back(ops[i++]);
-            continue;
-        }
-        // pad R to three positions with the HIGHEST free tile positions that are not shared controls:
-        // a thread's eight amplitudes then sit far apart and neighbouring lanes read neighbouring
-        // addresses (no bank conflicts)
-        for (int p = k - 1; p >= 0 && __builtin_popcount(R) < 3; --p)
-            if (!((R >> p) & 1) && !((K >> p) & 1)) R |= 1u << p;
-        for (int p = k - 1; p >= 0 && __builtin_popcount(R) < 3; --p)
-            if (!((R >> p) & 1)) R |= 1u << p;
-        K &= ~R;
-        TileOp h{};
-        h.op = kOpPhase;
-        h.lctrl = K;
-        h.ph.count = (uint16_t)(j - i);
-        int nr = 0;
-        for (int p = 0; p < k; ++p)
-            if ((R >> p) & 1) h.ph.rpos[nr++] = (uint8_t)p;
-        h.nfix = 0;
-        for (int p = 0; p < k; ++p)
-            if (((R | K) >> p) & 1) {
-                h.fixpos |= (uint64_t)p << (4 * h.nfix);
-                h.nfix++;
-            }
-        out.push_back(h);
-        for (size_t q = i; q < j; ++q) out.push_back(ops[q]);
-        i = j;
-    }
 }
 
 template <typename A>
@@ -524,7 +379,7 @@ int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, co
     a.init_index = sv->basis_index;
     a.tile_mask = seg.tile_mask;
     const uint64_t n_tiles = 1ull << (sv->n - a.cta_ex.m);
-    if (n_ops > kTileMaxOps) return fail(B2SV_EINVAL, "tile sweep with %d ops (max %d)", n_ops, kTileMaxOps);
+    if (n_ops > kTileMaxOps && tile_io == 3) tile_io = 0;  // the experimental pipelined kernel takes one batch only
     const size_t smem = ((size_t)sv->amp_bytes << a.k) + (size_t)kTileMaxOps * sizeof(TileOp);
     // default path: TMA tensor copies with the hardware 128-byte swizzle (needs chunks of >= one 128-byte
     // row and a tile of >= one 1 KiB swizzle atom; tiny registers use the linear bulk-copy kernel below)
@@ -641,7 +496,7 @@ void encode_perm_gate(const PGate& g, int n, std::vector<uint4>& out) {
     for (size_t i = prologue.size(); i-- > 0;) out.push_back(prologue[i]);  // un-compute the temporaries
 }
 
-static_assert(kPlanMaxTileOps + (kPlanMaxTileOps + 1) / 2 <= kTileMaxOps, "planner and kernel disagree on the ops per tile sweep");
+static_assert(kPlanMaxTileOps + (kPlanMaxTileOps + 1) / 2 <= kTileMaxOps, "planner and kernel disagree on the ops per single-batch sweep");
 static_assert(kPermMaxCtrlX == 3 + 2 * kPermTemps && kPermMaxCtrlSwap == 2 + 2 * kPermTemps,
               "planner's control limits must match the scratch rows of k_perm");
 
@@ -1049,7 +904,7 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
             key = (key ^ w[i]) * 1099511628211ull;
             key2 += w[i] * (2 * i + 1);
         }
-        const uint64_t o = (uint64_t)cfg.fuse | ((uint64_t)cfg.perm_runs << 1) | ((uint64_t)cfg.mux << 2) | ((uint64_t)cfg.phases << 3) | ((uint64_t)cfg.low6 << 4) |
+        const uint64_t o = (uint64_t)cfg.fuse | ((uint64_t)cfg.perm_runs << 1) | ((uint64_t)cfg.mux << 2) | ((uint64_t)cfg.phases << 3) | ((uint64_t)cfg.low6 << 4) | ((uint64_t)cfg.mono << 5) |
                            ((uint64_t)cfg.tile_qubits << 8) | ((uint64_t)cfg.lookahead << 16) | ((uint64_t)sv->scratch_failed << 40);
         key = (key ^ o) * 1099511628211ull;
     }
@@ -1090,12 +945,8 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
         for (size_t s = 0; s < np.segs.size(); ++s) {
             const Segment& seg = np.segs[s];
             if (seg.cls != SEG_TILE && seg.cls != SEG_LOW6) continue;
-            ExpandArgs ex;
-            fill_expand(ex, seg.tile_mask);
             sv->plan_seg_first[s] = host_ops.size();
-            std::vector<TileOp> seg_ops;
-            for (int gi : seg.gates) seg_ops.push_back(make_tile_op(np, np.gates[gi], seg.tile_mask, ex));
-            append_with_phases(seg_ops, ex.m, cfg.phases && seg.cls == SEG_TILE, host_ops);
+            build_segment_ops(np, seg, cfg, host_ops);
             sv->plan_seg_nops[s] = (int)(host_ops.size() - sv->plan_seg_first[s]);
         }
         if (!host_ops.empty()) {

@@ -48,7 +48,7 @@ template <>
 __device__ __forceinline__ float2 from_c128<float2>(double2 v) {
     return make_float2((float)v.x, (float)v.y);
 }
-__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+__host__ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 __device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {  // a*b + c
@@ -144,11 +144,24 @@ struct __align__(16) TileOp {
             uint16_t count;
             uint8_t rpos[3];       // the three tile-local positions held in registers (ascending)
         } ph;
+        struct {               // op == kOpMono: header of a monomial phase, `count` member ops follow
+            uint16_t count;        // (same place as ph.count)
+            uint8_t tb, lb;        // tile-local index = thread bits (tb of them) + loop bits (lb of them)
+            uint8_t vbits;         // the first `vbits` loop bits are touched by the run (Q bits), the rest are not
+            uint8_t fac;           // 1: the run has PHASE / DIAG1 members (amplitudes pick up factors)
+            uint8_t tp[8];         // tile-local position of thread bit i (ascending)
+            uint8_t lp[8];         // tile-local position of loop bit i
+        } mono;
     };
 };
 constexpr int kOpMux = 5;
 constexpr int kOpBlock = 6;
 constexpr int kOpPhase = 7;
+constexpr int kOpMono = 8;   // header of a monomial phase (index moves + phase factors only)
+constexpr int kOpNop = 9;    // padding in front of a batch boundary of a long op list
+constexpr int kMonoElems = 8;              // amplitudes a thread carries through one round of a monomial phase
+constexpr int kMonoThreadBits = 8;         // log2(kThreads)
+constexpr int kMonoMaxV = 8, kMonoMaxVFac = 4;  // index walks per thread (pure permutation / with factors)
 static_assert(sizeof(TileOp) == 96, "TileOp layout");
 
 struct TileArgs {
@@ -167,7 +180,7 @@ struct TileArgs {
     uint64_t tile_mask;
 };
 
-__device__ __forceinline__ uint32_t expand_local(uint32_t p, uint64_t fixpos, int nfix) {
+__host__ __device__ __forceinline__ uint32_t expand_local(uint32_t p, uint64_t fixpos, int nfix) {
     for (int i = 0; i < nfix; ++i) {
         const int pos = (int)((fixpos >> (4 * i)) & 15);
         const uint32_t lo = p & ((1u << pos) - 1);
@@ -557,6 +570,172 @@ __device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, con
 }
 #undef B2SV_PAIRS
 
+// Monomial phase: a run of consecutive X / SWAP / PHASE / DIAG1 gates (any controls) maps every basis
+// state of the tile to ONE basis state times a factor, so the whole run is "index arithmetic + one
+// move".  Only the tile bits the run touches (targets and tile-local controls: the Q bits) matter for
+// where an amplitude goes, so the thread <-> amplitude map puts the Q bits into the thread number first:
+// a thread then owns 2^lb amplitudes that share at most V = 2^vbits different Q values, walks just those
+// V INDICES through the gates in registers (an X is `idx ^= bit` under a mask test, a phase gate
+// multiplies the walk's factor), and moves all its amplitudes by the resulting XOR masks -- in rounds of
+// kMonoElems amplitudes per thread with one barrier between the reads and the writes of a round (a
+// round holds every Q value of a set of non-Q values, so it is closed under the run).
+// One shared-memory round trip for the whole run: the ripple-carry arithmetic of circuits/arithmetic.py
+// under LCU / BlockDiagonal selector controls is 50-80 such gates in a row, which used to be one
+// shared-memory pass each.  X and SWAP stay exact data movement.
+template <int V, bool FAC>
+__host__ __device__ __forceinline__ void mono_run_members(const TileOp* ops, int count, uint64_t base, uint32_t (&idx)[V],
+                                                          double2 (&f)[V]) {
+    for (int mi = 0; mi < count; ++mi) {
+        const TileOp& op = ops[mi];
+        if ((base & op.ext_ctrl) != op.ext_ctrl) continue;  // CTA-uniform
+        const uint32_t lc = op.lctrl;
+        const int kind = op.op;
+        if (kind == B2SV_OP_X) {
+            const uint32_t bt = 1u << op.tpos;
+#pragma unroll
+            for (int e = 0; e < V; ++e) idx[e] ^= ((~idx[e] & lc) == 0u) ? bt : 0u;
+        } else if (kind == B2SV_OP_SWAP) {
+            const int pa = op.tpos, pb = op.tpos2;
+            const uint32_t both = (1u << pa) | (1u << pb);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const bool differ = ((idx[e] >> pa) ^ (idx[e] >> pb)) & 1u;
+                idx[e] ^= (differ && (~idx[e] & lc) == 0u) ? both : 0u;
+            }
+        } else if (FAC && kind == B2SV_OP_PHASE) {
+            const double2 w = make_double2(op.m[0], op.m[1]);
+#pragma unroll
+            for (int e = 0; e < V; ++e)
+                if ((~idx[e] & lc) == 0u) f[e] = cmul(w, f[e]);
+        } else if (FAC && kind == B2SV_OP_DIAG1) {
+            const double2 d0 = make_double2(op.m[0], op.m[1]), d1 = make_double2(op.m[2], op.m[3]);
+            if (op.tpos == 0xFF) {  // target outside the tile: one CTA-uniform factor
+                const double2 d = (base & op.ext_tbit) ? d1 : d0;
+#pragma unroll
+                for (int e = 0; e < V; ++e)
+                    if ((~idx[e] & lc) == 0u) f[e] = cmul(d, f[e]);
+            } else {
+                const int pt = op.tpos;
+#pragma unroll
+                for (int e = 0; e < V; ++e)
+                    if ((~idx[e] & lc) == 0u) f[e] = cmul(((idx[e] >> pt) & 1u) ? d1 : d0, f[e]);
+            }
+        }
+    }
+}
+
+// scatter the low bits of x to the tile-local positions pos[0..n)
+__host__ __device__ __forceinline__ uint32_t mono_deposit(uint32_t x, const uint8_t* pos, int n) {
+    uint32_t out = 0;
+    for (int i = 0; i < n; ++i) out |= ((x >> i) & 1u) << pos[i];
+    return out;
+}
+
+template <typename A, int V, bool FAC, typename TV>
+__device__ __forceinline__ void tile_mono_rounds(TV tile, const TileOp& hdr, const TileOp* ops, uint64_t base) {
+    constexpr int E = kMonoElems;
+    const int lb = hdr.mono.lb, vbits = hdr.mono.vbits;
+    const uint32_t tpart = mono_deposit(threadIdx.x, hdr.mono.tp, hdr.mono.tb);
+    const bool active = threadIdx.x < (1u << hdr.mono.tb);
+    // walk this thread's V index values through the run
+    uint32_t qsrc[V], qidx[V];
+    double2 fac[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        qsrc[v] = qidx[v] = tpart | mono_deposit((uint32_t)v, hdr.mono.lp, vbits);
+        fac[v] = make_double2(1.0, 0.0);
+    }
+    mono_run_members<V, FAC>(ops, hdr.mono.count, base, qidx, fac);
+#pragma unroll
+    for (int v = 0; v < V; ++v) qidx[v] ^= qsrc[v];  // XOR mask that takes a source index to its destination
+    const uint32_t per_thread = 1u << lb;
+    for (uint32_t j0 = 0; j0 < per_thread; j0 += E) {
+        uint32_t dst[E];
+        double2 val[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const uint32_t j = j0 + e;
+            const int v = e & (V - 1);  // E is a multiple of V: the walk of element j is j mod V
+            const uint32_t src = qsrc[v] | mono_deposit(j >> vbits, hdr.mono.lp + vbits, lb - vbits);
+            dst[e] = src ^ qidx[v];
+            if (active && j < per_thread) {
+                val[e] = to_c128(tile[src]);
+                if (FAC) val[e] = cmul(fac[v], val[e]);
+            }
+        }
+        __syncthreads();  // every amplitude of the round is in registers before the first one is overwritten
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (active && j0 + e < per_thread) tile[dst[e]] = from_c128<A>(val[e]);
+        // the next round works on a disjoint set of amplitudes: no barrier needed in between
+    }
+}
+
+template <typename A, typename TV>
+__device__ __forceinline__ void tile_apply_mono(TV tile, const TileOp& hdr, const TileOp* ops, uint64_t base) {
+    if (hdr.mono.fac) {
+        switch (hdr.mono.vbits) {
+            case 0: tile_mono_rounds<A, 1, true>(tile, hdr, ops, base); break;
+            case 1: tile_mono_rounds<A, 2, true>(tile, hdr, ops, base); break;
+            default: tile_mono_rounds<A, 4, true>(tile, hdr, ops, base); break;
+        }
+    } else {
+        switch (hdr.mono.vbits) {
+            case 0: tile_mono_rounds<A, 1, false>(tile, hdr, ops, base); break;
+            case 1: tile_mono_rounds<A, 2, false>(tile, hdr, ops, base); break;
+            case 2: tile_mono_rounds<A, 4, false>(tile, hdr, ops, base); break;
+            default: tile_mono_rounds<A, 8, false>(tile, hdr, ops, base); break;
+        }
+    }
+}
+
+// Run the staged ops [0, n) of a sweep on the tile in shared memory.
+template <typename A, bool FUSED, typename TV>
+__device__ __forceinline__ void tile_run_ops(TV tile, const TileOp* s_ops, int n, int k, uint64_t base,
+                                             const double2* __restrict__ tables) {
+    for (int o = 0; o < n; ++o) {
+        const TileOp& op = s_ops[o];
+        if (op.op == kOpPhase || op.op == kOpMono) {
+            bool any = false;  // CTA-uniform: is any gate of the phase active on this tile?
+            for (int mi = 1; mi <= op.ph.count; ++mi) any |= (base & s_ops[o + mi].ext_ctrl) == s_ops[o + mi].ext_ctrl;
+            if (any) {
+                if (op.op == kOpPhase) tile_apply_phase<A>(tile, op, s_ops + o + 1, k, base);
+                else tile_apply_mono<A>(tile, op, s_ops + o + 1, base);
+                __syncthreads();
+            }
+            o += op.ph.count;
+            continue;
+        }
+        if (op.op == kOpNop) continue;
+        if ((base & op.ext_ctrl) != op.ext_ctrl) continue;  // CTA-uniform: gate not active on this tile
+        tile_apply_op<A, FUSED>(tile, op, k, base, tables);
+        __syncthreads();
+    }
+}
+
+// Long op lists come in batches of kTileMaxOps slots (the host never lets a phase straddle a batch
+// boundary): the first batch is staged while the tile is in flight, later ones between batches.
+__device__ __forceinline__ void tile_stage_ops(TileOp* s_ops, const TileOp* g_ops, int n, int tid, int nt) {
+    const uint4* src = reinterpret_cast<const uint4*>(g_ops);
+    uint4* dst = reinterpret_cast<uint4*>(s_ops);
+    const int n16 = n * (int)(sizeof(TileOp) / 16);
+    for (int i = tid; i < n16; i += nt) dst[i] = __ldg(src + i);
+}
+
+template <typename A, bool FUSED, typename TV>
+__device__ __forceinline__ void tile_run_batches(TV tile, TileOp* s_ops, const TileOp* g_ops, int n_ops, int k, uint64_t base,
+                                                 const double2* __restrict__ tables) {
+    for (int b0 = 0; b0 < n_ops; b0 += kTileMaxOps) {
+        const int nb = n_ops - b0 < kTileMaxOps ? n_ops - b0 : kTileMaxOps;
+        if (b0 > 0) {
+            __syncthreads();
+            tile_stage_ops(s_ops, g_ops + b0, nb, (int)threadIdx.x, (int)blockDim.x);
+            __syncthreads();
+        }
+        tile_run_ops<A, FUSED>(tile, s_ops, nb, k, base, tables);
+    }
+}
+
 // global offset (in amplitudes, relative to the tile base) of chunk j of the tile
 __device__ __forceinline__ uint64_t chunk_offset(uint32_t j, const ExpandArgs& ex, int k, int lc) {
     uint64_t off = 0;
@@ -590,12 +769,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile(A* __restrict__ psi, const
         for (uint32_t j = tid; j < n_chunks; j += kThreads)
             bulk_g2s(tile + (size_t)j * chunk_elems, psi + (base | chunk_offset(j, a.tile_ex, k, lc)), chunk_bytes, &bar);
     }
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(a.ops);
-        uint4* dst = reinterpret_cast<uint4*>(s_ops);
-        const int n16 = a.n_ops * (int)(sizeof(TileOp) / 16);
-        for (int i = tid; i < n16; i += kThreads) dst[i] = __ldg(src + i);
-    }
+    tile_stage_ops(s_ops, a.ops, a.n_ops < kTileMaxOps ? a.n_ops : kTileMaxOps, tid, kThreads);
     if (!load) {
         const uint32_t elems = 1u << k;
         const A zero = from_c128<A>(make_double2(0.0, 0.0));
@@ -620,22 +794,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile(A* __restrict__ psi, const
     // a generated (lazy-init) tile that does not hold the basis index is all zeros: every gate maps it to
     // itself, so only the one tile that owns the index runs the gates -- the others just write zeros
     const int n_ops_here = (load || (a.init_index & ~a.tile_mask) == base) ? a.n_ops : 0;
-    for (int o = 0; o < n_ops_here; ++o) {
-        const TileOp& op = s_ops[o];
-        if (op.op == kOpPhase) {
-            bool any = false;  // CTA-uniform: is any gate of the phase active on this tile?
-            for (int mi = 1; mi <= op.ph.count; ++mi) any |= (base & s_ops[o + mi].ext_ctrl) == s_ops[o + mi].ext_ctrl;
-            if (any) {
-                tile_apply_phase<A>(TileView<A, false>{tile}, op, s_ops + o + 1, k, base);
-                __syncthreads();
-            }
-            o += op.ph.count;
-            continue;
-        }
-        if ((base & op.ext_ctrl) != op.ext_ctrl) continue;  // CTA-uniform: gate not active on this tile
-        tile_apply_op<A, FUSED>(TileView<A, false>{tile}, op, k, base, a.tables);
-        __syncthreads();
-    }
+    tile_run_batches<A, FUSED>(TileView<A, false>{tile}, s_ops, a.ops, n_ops_here, k, base, a.tables);
 
     if (BULK) {
         // generic-proxy writes to shared memory must be visible to the async proxy before the copy out
@@ -708,12 +867,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile_swz(const __grid_constant_
             tma_g2s_2d(tile_raw + (size_t)j * chunk_elems, &args.map, 0u, (uint32_t)(g >> kRowShift), &bar);
         }
     }
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(a.ops);
-        uint4* dst = reinterpret_cast<uint4*>(s_ops);
-        const int n16 = a.n_ops * (int)(sizeof(TileOp) / 16);
-        for (int i = tid; i < n16; i += kThreads) dst[i] = __ldg(src + i);
-    }
+    tile_stage_ops(s_ops, a.ops, a.n_ops < kTileMaxOps ? a.n_ops : kTileMaxOps, tid, kThreads);
     if (!load) {
         const uint32_t elems = 1u << k;
         const A zero = from_c128<A>(make_double2(0.0, 0.0));
@@ -732,22 +886,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile_swz(const __grid_constant_
     // a generated (lazy-init) tile that does not hold the basis index is all zeros: every gate maps it to
     // itself, so only the one tile that owns the index runs the gates -- the others just write zeros
     const int n_ops_here = (load || (a.init_index & ~a.tile_mask) == base) ? a.n_ops : 0;
-    for (int o = 0; o < n_ops_here; ++o) {
-        const TileOp& op = s_ops[o];
-        if (op.op == kOpPhase) {
-            bool any = false;  // CTA-uniform: is any gate of the phase active on this tile?
-            for (int mi = 1; mi <= op.ph.count; ++mi) any |= (base & s_ops[o + mi].ext_ctrl) == s_ops[o + mi].ext_ctrl;
-            if (any) {
-                tile_apply_phase<A>(tile, op, s_ops + o + 1, k, base);
-                __syncthreads();
-            }
-            o += op.ph.count;
-            continue;
-        }
-        if ((base & op.ext_ctrl) != op.ext_ctrl) continue;  // CTA-uniform: gate not active on this tile
-        tile_apply_op<A, FUSED>(tile, op, k, base, a.tables);
-        __syncthreads();
-    }
+    tile_run_batches<A, FUSED>(tile, s_ops, a.ops, n_ops_here, k, base, a.tables);
 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -835,22 +974,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(A* __restrict__ p
             }
             __syncthreads();
         }
-        for (int o = 0; o < a.n_ops; ++o) {
-            const TileOp& op = s_ops[o];
-            if (op.op == kOpPhase) {
-                bool any = false;
-                for (int mi = 1; mi <= op.ph.count; ++mi) any |= (base & s_ops[o + mi].ext_ctrl) == s_ops[o + mi].ext_ctrl;
-                if (any) {
-                    tile_apply_phase<A>(TileView<A, false>{tile}, op, s_ops + o + 1, k, base);
-                    __syncthreads();
-                }
-                o += op.ph.count;
-                continue;
-            }
-            if ((base & op.ext_ctrl) != op.ext_ctrl) continue;
-            tile_apply_op<A, FUSED>(TileView<A, false>{tile}, op, k, base, a.tables);
-            __syncthreads();
-        }
+        tile_run_ops<A, FUSED>(TileView<A, false>{tile}, s_ops, a.n_ops, k, base, a.tables);  // single batch (host checks)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (tid < 32) {
@@ -970,7 +1094,16 @@ __global__ void __launch_bounds__(kThreads) k_low6(A* __restrict__ psi, const Lo
                 v1[u] = to_c128(psi[base[u] + e1]);
             }
         }
-        for (int o = 0; o < a.n_ops; ++o) {
+        // a generated (lazy-init) group that does not hold the basis index is all zeros, which every gate
+        // maps to itself: only the one warp that owns the index runs the gates (warp-uniform decision)
+        bool run_ops = true;
+        if (a.init_mode) {
+            run_ops = false;
+#pragma unroll
+            for (int u = 0; u < NB; ++u) run_ops |= live[u] && base[u] == (a.init_index & ~63ull);
+        }
+        const int n_ops_here = run_ops ? a.n_ops : 0;
+        for (int o = 0; o < n_ops_here; ++o) {
             // everything about the gate is warp-uniform; the per-block / per-element conditions are plain
             // predicates, so the shuffles below are never inside divergent code
             const TileOp& op = s_ops[o];

@@ -40,8 +40,10 @@ constexpr int B2SV_OP_MUX = 5;        // internal: fused same-target run, a tabl
 constexpr int kMuxMaxCtrl = 6;        // table of at most 64 matrices (4 KiB)
 constexpr int B2SV_OP_BLOCK = 6;      // internal: fused run on <= 3 qubits, one dense 2^kb x 2^kb matrix
 constexpr int kBlockMaxQubits = 3;
-constexpr int kPlanMaxTileOps = 74;   // gates per tile sweep: with one register-phase header per two gates
-                                      // they still fit the 112 op slots staged in shared memory
+constexpr int kPlanMaxTileOps = 74;   // gates per LOW6 sweep / per tile sweep without monomial phases: with one
+                                      // register-phase header per two gates they still fit the 112 op slots
+                                      // staged in shared memory
+constexpr int kPlanMaxTileGates = 1536;  // gates per tile sweep (the kernels stage long programs in batches)
 
 struct PGate {
     uint8_t op;
@@ -84,7 +86,21 @@ struct PlanConfig {
     bool mux = true;                      // fuse same-target runs into multiplexed 2x2 ops
     bool phases = true;                   // group plain gates of a sweep into register phases
     bool low6 = true;                     // sweeps confined to the low 6 qubits use the warp-shuffle kernel
+    bool mono = true;                     // monomial phases: runs of X / SWAP / phase gates inside a tile sweep cost
+                                          // index arithmetic only, so such runs ride in tile sweeps
+    double mono_gate_cost = 0.008;        // one gate of a monomial phase in units of one full sweep (~40-55 issue
+                                          // cycles per 64 KiB tile against ~5700 cycles of HBM time per tile)
 };
+
+// Tunable for experiments through B2SV_MONO_COST.
+inline double mono_gate_cost_default() {
+    static const double v = [] {
+        const char* e = std::getenv("B2SV_MONO_COST");
+        const double x = e ? std::atof(e) : 0.0;
+        return x > 0.0 ? x : 0.008;
+    }();
+    return v;
+}
 
 // A run of consecutive gates on ONE target whose other qubits are only controls multiplies out to
 // sum_c |c><c| (x) M_c: one 2x2 matrix per value c of the union of the control qubits.  This is what
@@ -124,17 +140,30 @@ inline PlanConfig default_config(int n, int dtype, const b2sv_plan_opts* o) {
     PlanConfig c;
     c.n = n;
     c.amp_bytes = dtype == B2SV_C64 ? 8 : 16;
+    c.mono_gate_cost = mono_gate_cost_default();
     c.tile_qubits = dtype == B2SV_C64 ? 13 : 12;  // 64 KiB of shared memory either way
     c.chunk_bits = dtype == B2SV_C64 ? 8 : 7;     // 2 KiB contiguous per bulk copy
+    // B2SV_AB: A/B switch bits (same meaning as b2sv_plan_opts::reserved) for runs that use default options
+    static const int env_ab = [] {
+        const char* e = std::getenv("B2SV_AB");
+        return e ? std::atoi(e) : 0;
+    }();
+    c.mux = !(env_ab & 1);
+    c.phases = !(env_ab & 2);
+    c.low6 = !(env_ab & 4);
+    c.mono = !(env_ab & 8);
     if (o) {
         c.fuse = o->fuse != 0;
         c.perm_runs = o->perm_runs != 0;
         if (o->tile_qubits > 0) c.tile_qubits = o->tile_qubits;
         if (o->lookahead > 0) c.lookahead = o->lookahead;
-        c.mux = !(o->reserved & 1);     // reserved bit 0: no multiplexor / block fusion (A/B switch)
-        c.phases = !(o->reserved & 2);  // reserved bit 1: no register phases (A/B switch)
-        c.low6 = !(o->reserved & 4);    // reserved bit 2: no warp-shuffle low-qubit sweeps (A/B switch)
+        const int ab = o->reserved | env_ab;
+        c.mux = !(ab & 1);     // reserved bit 0: no multiplexor / block fusion (A/B switch)
+        c.phases = !(ab & 2);  // reserved bit 1: no register phases (A/B switch)
+        c.low6 = !(ab & 4);    // reserved bit 2: no warp-shuffle low-qubit sweeps (A/B switch)
+        c.mono = !(ab & 8);    // reserved bit 3: no monomial phases (A/B switch)
     }
+    if (!c.phases) c.mono = false;
     if (c.tile_qubits > 13 && c.amp_bytes == 16) c.tile_qubits = 13;
     if (c.tile_qubits > 14) c.tile_qubits = 14;
     if (c.tile_qubits < 3) c.tile_qubits = 3;
@@ -536,10 +565,13 @@ inline void plan_tiles(const std::vector<PGate>& G, const std::vector<int>& idx,
         uint64_t T = base;
         uint64_t K = ~0ull;  // controls common to every gate taken so far
         uint64_t blocked_any = 0, blocked_nd = 0;
+        // the look-ahead window counts the gates passed over, not the ones taken: with monomial phases a
+        // sweep can carry hundreds of gates
         int scanned = 0;
-        for (size_t p = head; p < idx.size() && scanned < cfg.lookahead && (int)seg.gates.size() < kPlanMaxTileOps; ++p) {
+        const int max_gates = cfg.mono ? kPlanMaxTileGates : kPlanMaxTileOps;
+        for (size_t p = head; p < idx.size() && scanned < cfg.lookahead && (int)seg.gates.size() < max_gates; ++p) {
             if (done[p]) continue;
-            ++scanned;
+            if (!cfg.mono) ++scanned;
             const PGate& g = G[idx[p]];
             const bool commutes = ((g.tmask & blocked_any) == 0) && ((g.qmask & blocked_nd) == 0);
             const uint64_t T2 = T | g.tmask;
@@ -561,6 +593,7 @@ inline void plan_tiles(const std::vector<PGate>& G, const std::vector<int>& idx,
                 seg.gates.push_back(idx[p]);
                 done[p] = 1;
             } else {
+                if (cfg.mono) ++scanned;
                 blocked_any |= g.qmask;
                 blocked_nd |= g.tmask;
                 if (p == head) break;  // cannot happen (k >= chunk_bits + 2), but never spin
@@ -595,7 +628,7 @@ inline void plan_tiles(const std::vector<PGate>& G, const std::vector<int>& idx,
         } else {
             // state-preparation style sweeps: every (non-diagonal) target sits in the low kLowBits qubits,
             // i.e. inside one 64-amplitude block a warp can hold in registers and exchange by shuffles
-            bool low = cfg.low6 && n >= kLowBits + 1;
+            bool low = cfg.low6 && n >= kLowBits + 1 && (int)seg.gates.size() <= kPlanMaxTileOps;
             for (int gi : seg.gates) {
                 const PGate& g = G[gi];
                 low = low && (g.tmask >> kLowBits) == 0 && g.op != B2SV_OP_SWAP && g.op != B2SV_OP_BLOCK;
@@ -666,10 +699,18 @@ inline Plan make_plan(const b2sv_gate* gates, size_t n_gates, const PlanConfig& 
                 plan_tiles(G, run, cfg, alt);
                 double tile_cost = 0;
                 for (const Segment& s : alt) {
-                    if (s.cls == SEG_TILE || s.cls == SEG_LOW6) tile_cost += sweep_cost(s.common_ctrl);
+                    if (s.cls == SEG_TILE || s.cls == SEG_LOW6)
+                        tile_cost += sweep_cost(s.common_ctrl) * (1.0 + (cfg.mono ? cfg.mono_gate_cost * (double)s.gates.size() : 0.0));
                     else tile_cost += gate_sweep_fraction(G[s.gates[0]]);
                 }
-                const double perm_cost = 1.0 + cfg.perm_gate_cost * (double)len;
+                double perm_cost = 1.0 + cfg.perm_gate_cost * (double)len;
+                if (cfg.mono && alt.size() == 1 && alt[0].cls == SEG_TILE) {
+                    // a compact run (its targets fit one tile) rides with its neighbours as a monomial phase:
+                    // what it adds to their sweep is index arithmetic, while a permutation sweep of its own
+                    // also cuts the neighbours' sweep in two
+                    tile_cost = sweep_cost(alt[0].common_ctrl) * (0.3 + cfg.mono_gate_cost * (double)len);
+                    perm_cost += 0.3;
+                }
                 use_perm = perm_cost < tile_cost;
                 if (cfg.n <= 16) use_perm = alt.size() > 1;  // launch-bound regime: fewest launches
             }

@@ -1,0 +1,270 @@
+// tileops.hpp -- host side of the tile sweeps: turns the planned gates of one sweep into the tile-local
+// op program the kernels of kernels.cuh interpret (no CUDA calls in this file; the tests also build
+// it into a host-only emulator of that program, tests/emul/).
+//
+//   make_tile_op         one planned gate -> one TileOp (targets / controls as tile-local positions)
+//   append_with_phases   groups consecutive ops into register phases (<= 3 target qubits, any plain
+//                        gate) and monomial phases (X / SWAP / PHASE / DIAG1 on up to 11 target qubits)
+//   layout_batches       pads the program so that no phase straddles a kTileMaxOps batch boundary
+#pragma once
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "kernels.cuh"
+#include "planner.hpp"
+
+namespace b2svk {
+
+inline void fill_expand(ExpandArgs& ex, uint64_t mask) {
+    ex.m = 0;
+    for (int q = 0; q < 64; ++q)
+        if ((mask >> q) & 1) ex.pos[ex.m++] = (uint8_t)q;
+}
+
+// Translate a planned gate into a tile-local op for the tile with (ascending) qubit positions `ex`.
+inline TileOp make_tile_op(const Plan& plan, const PGate& g, uint64_t tile_mask, const ExpandArgs& ex) {
+    TileOp op{};
+    auto local_pos = [&](int q) -> int {
+        for (int i = 0; i < ex.m; ++i)
+            if (ex.pos[i] == q) return i;
+        return -1;
+    };
+    op.op = g.op;
+    op.tpos = op.tpos2 = 0;
+    op.ext_ctrl = g.ctrl & ~tile_mask;
+    op.ext_tbit = 0;
+    uint32_t lctrl = 0;
+    for (int i = 0; i < ex.m; ++i)
+        if ((g.ctrl >> ex.pos[i]) & 1) lctrl |= 1u << i;
+    op.lctrl = lctrl;
+    uint32_t fixed = lctrl;
+    switch (g.op) {
+        case B2SV_OP_PHASE:
+            break;
+        case B2SV_OP_DIAG1: {
+            const int p = local_pos(g.t0);
+            if (p < 0) {
+                op.tpos = 0xFF;
+                op.ext_tbit = 1ull << g.t0;
+            } else {
+                op.tpos = (uint8_t)p;
+                fixed |= 1u << p;
+            }
+        } break;
+        case B2SV_OP_SWAP:
+            op.tpos = (uint8_t)local_pos(g.t0);
+            op.tpos2 = (uint8_t)local_pos(g.t1);
+            fixed |= (1u << op.tpos) | (1u << op.tpos2);
+            break;
+        case B2SV_OP_BLOCK: {
+            const BlockInfo& bi = plan.blocks[g.blk];
+            for (int i = 0; i < bi.kb; ++i) fixed |= 1u << local_pos(bi.q[i]);
+        } break;
+        default:
+            op.tpos = (uint8_t)local_pos(g.t0);
+            fixed |= 1u << op.tpos;
+            break;
+    }
+    op.nfix = 0;
+    op.fixpos = 0;
+    for (int i = 0; i < ex.m; ++i)
+        if ((fixed >> i) & 1) {
+            op.fixpos |= (uint64_t)i << (4 * op.nfix);
+            op.nfix++;
+        }
+    std::memcpy(op.m, g.m, sizeof(op.m));
+    if (g.op == B2SV_OP_BLOCK) {
+        const BlockInfo& bi = plan.blocks[g.blk];
+        op.blk.mat_off = bi.mat_off;
+        op.blk.kb = (uint8_t)bi.kb;
+        for (int i = 0; i < bi.kb; ++i) op.blk.bpos[i] = (uint8_t)local_pos(bi.q[i]);
+    }
+    if (g.op == B2SV_OP_MUX) {
+        const MuxInfo& mi = plan.mux[g.mux];
+        // g.ctrl (the run's common controls) is already a predicate in lctrl / ext_ctrl
+        op.mux.table_off = mi.table_off;
+        op.mux.nmux = (uint8_t)mi.nbits;
+        int j = 0;
+        for (int q = 0; q < 64 && j < mi.nbits; ++q)
+            if ((mi.ctrl_mask >> q) & 1) {
+                const int lp = local_pos(q);
+                op.mux.mpos[j] = lp < 0 ? 0xFF : (uint8_t)lp;
+                op.mux.mq[j] = (uint8_t)q;
+                ++j;
+            }
+    }
+    return op;
+}
+
+constexpr int kPhaseMaxMembers = kTileMaxOps - 1; // header + members fit one staged batch
+
+// Group the ops of one tile sweep into phases (kernels.cuh: tile_apply_phase / tile_apply_mono).
+//   register phase: maximal run of consecutive plain gates whose targets fall on at most three tile-local
+//                   positions -- applied in registers, one shared-memory round trip for the run;
+//   monomial phase: maximal run of consecutive X / SWAP / PHASE / DIAG1 gates touching (as target or tile-local
+//                   control) at most tb+3 tile positions (tb+2 with phase factors) -- every thread walks the
+//                   few index values its amplitudes can have on those positions through the run.
+// At every position the kind that swallows more gates wins.
+inline void append_with_phases(const std::vector<TileOp>& ops, int k, bool enable, bool mono, std::vector<TileOp>& out) {
+    auto plain = [](const TileOp& o) {
+        return o.op == B2SV_OP_MAT1 || o.op == B2SV_OP_DIAG1 || o.op == B2SV_OP_X || o.op == B2SV_OP_SWAP || o.op == B2SV_OP_PHASE;
+    };
+    auto monomial = [](const TileOp& o) {
+        return o.op == B2SV_OP_DIAG1 || o.op == B2SV_OP_X || o.op == B2SV_OP_SWAP || o.op == B2SV_OP_PHASE;
+    };
+    auto targets = [](const TileOp& o) -> uint32_t {
+        uint32_t t = 0;
+        if (o.op == B2SV_OP_PHASE) return 0;
+        if (o.tpos != 0xFF) t |= 1u << o.tpos;
+        if (o.op == B2SV_OP_SWAP) t |= 1u << o.tpos2;
+        return t;
+    };
+    // what the op costs as a stand-alone pass, in units of one read+write pass over the whole tile
+    auto alone_cost = [](const TileOp& o) {
+        const int c = __builtin_popcount(o.lctrl) + (o.op == B2SV_OP_SWAP ? 1 : 0);
+        return std::ldexp(1.0, -c) + 0.08;  // + barrier and latency of a pass of its own
+    };
+    auto pass_cost = [](uint32_t common) { return std::ldexp(1.0, -__builtin_popcount(common)); };
+    size_t i = 0;
+    while (i < ops.size()) {
+        if (!enable || k < 3 || !plain(ops[i])) {
+            out.push_back(ops[i++]);
+            continue;
+        }
+        // ---- register-phase candidate [i, jr)
+        uint32_t R = targets(ops[i]);
+        uint32_t K = ops[i].lctrl;  // tile-local controls shared by every gate taken so far
+        size_t jr = i + 1;
+        while (jr < ops.size() && plain(ops[jr]) && (int)(jr - i) < kPhaseMaxMembers) {
+            const uint32_t R2 = R | targets(ops[jr]);
+            if (__builtin_popcount(R2) > 3) break;
+            // like the sweeps themselves: do not let one lightly controlled gate make a heavily
+            // controlled stretch walk over the whole tile
+            const double now = pass_cost(K & ~R2), joined = pass_cost(K & ops[jr].lctrl & ~R2), alone = pass_cost(ops[jr].lctrl & ~R2);
+            if (joined > now + 0.5 * alone) break;
+            R = R2;
+            K &= ops[jr].lctrl;
+            ++jr;
+        }
+        // ---- monomial-phase candidate [i, jm)
+        size_t jm = i;
+        uint32_t Q = 0;      // tile positions the run reads or moves
+        bool fac = false;
+        bool mono_worth = false;
+        const int tb = k < kMonoThreadBits ? k : kMonoThreadBits;
+        auto touched = [&](const TileOp& o) { return o.lctrl | targets(o); };
+        auto q_fits = [&](uint32_t q, bool f) {
+            const int extra = __builtin_popcount(q) - tb;  // Q bits that must become loop bits: V = 2^extra walks per thread
+            return extra <= (f ? 2 : 3) && (extra <= 0 || extra <= k - tb);
+        };
+        if (mono && monomial(ops[i])) {
+            Q = touched(ops[i]);
+            fac = !(ops[i].op == B2SV_OP_X || ops[i].op == B2SV_OP_SWAP);
+            double separate = alone_cost(ops[i]);
+            jm = i + 1;
+            while (q_fits(Q, fac) && jm < ops.size() && monomial(ops[jm]) && (int)(jm - i) < kPhaseMaxMembers) {
+                const uint32_t Q2 = Q | touched(ops[jm]);
+                const bool fac2 = fac || !(ops[jm].op == B2SV_OP_X || ops[jm].op == B2SV_OP_SWAP);
+                if (!q_fits(Q2, fac2)) break;
+                Q = Q2;
+                fac = fac2;
+                separate += alone_cost(ops[jm]);
+                ++jm;
+            }
+            // one round trip of the whole tile + the index walks (~0.04 pass per gate)
+            const double mono_cost = 1.0 + 0.04 * (double)(jm - i) + 0.08;
+            mono_worth = q_fits(Q, fac) && jm - i >= 2 && separate > mono_cost;
+        }
+        if (mono_worth && jm >= jr) {
+            TileOp h{};
+            h.op = kOpMono;
+            h.mono.count = (uint16_t)(jm - i);
+            h.mono.fac = fac ? 1 : 0;
+            h.mono.tb = (uint8_t)tb;
+            h.mono.lb = (uint8_t)(k - tb);
+            // thread bits: Q positions first (ascending), filled up with the lowest other positions; the lowest
+            // positions end up in the lane number, so a warp reads whole 128-byte rows whenever it can
+            uint32_t tmask = 0;
+            for (int p = 0; p < k && __builtin_popcount(tmask) < tb; ++p)
+                if ((Q >> p) & 1) tmask |= 1u << p;
+            for (int p = 0; p < k && __builtin_popcount(tmask) < tb; ++p)
+                if (!((tmask >> p) & 1)) tmask |= 1u << p;
+            int nt = 0, nl = 0;
+            for (int p = 0; p < k; ++p)
+                if ((tmask >> p) & 1) h.mono.tp[nt++] = (uint8_t)p;
+            for (int p = 0; p < k; ++p)  // loop bits: the Q positions that did not fit first
+                if (!((tmask >> p) & 1) && ((Q >> p) & 1)) h.mono.lp[nl++] = (uint8_t)p;
+            h.mono.vbits = (uint8_t)nl;
+            for (int p = 0; p < k; ++p)
+                if (!((tmask >> p) & 1) && !((Q >> p) & 1)) h.mono.lp[nl++] = (uint8_t)p;
+            out.push_back(h);
+            for (size_t q = i; q < jm; ++q) out.push_back(ops[q]);
+            i = jm;
+            continue;
+        }
+        if (jr - i < 2) {
+            out.push_back(ops[i++]);
+            continue;
+        }
+        // pad R to three positions with the HIGHEST free tile positions that are not shared controls:
+        // a thread's eight amplitudes then sit far apart and neighbouring lanes read neighbouring
+        // addresses (no bank conflicts)
+        for (int p = k - 1; p >= 0 && __builtin_popcount(R) < 3; --p)
+            if (!((R >> p) & 1) && !((K >> p) & 1)) R |= 1u << p;
+        for (int p = k - 1; p >= 0 && __builtin_popcount(R) < 3; --p)
+            if (!((R >> p) & 1)) R |= 1u << p;
+        K &= ~R;
+        TileOp h{};
+        h.op = kOpPhase;
+        h.lctrl = K;
+        h.ph.count = (uint16_t)(jr - i);
+        int nr = 0;
+        for (int p = 0; p < k; ++p)
+            if ((R >> p) & 1) h.ph.rpos[nr++] = (uint8_t)p;
+        h.nfix = 0;
+        for (int p = 0; p < k; ++p)
+            if (((R | K) >> p) & 1) {
+                h.fixpos |= (uint64_t)p << (4 * h.nfix);
+                h.nfix++;
+            }
+        out.push_back(h);
+        for (size_t q = i; q < jr; ++q) out.push_back(ops[q]);
+        i = jr;
+    }
+}
+
+// The kernels stage the program kTileMaxOps slots at a time; a phase (header + members) must sit inside
+// one batch, so pad with no-ops in front of a phase that would straddle a boundary.
+inline void layout_batches(const std::vector<TileOp>& in, std::vector<TileOp>& out) {
+    const size_t first = out.size();
+    size_t i = 0;
+    while (i < in.size()) {
+        const bool hdr = in[i].op == kOpPhase || in[i].op == kOpMono;
+        const size_t unit = hdr ? (size_t)in[i].ph.count + 1 : 1;
+        const size_t used = (out.size() - first) % kTileMaxOps;
+        if (used + unit > (size_t)kTileMaxOps) {
+            TileOp nop{};
+            nop.op = kOpNop;
+            for (size_t p = used; p < (size_t)kTileMaxOps; ++p) out.push_back(nop);
+        }
+        for (size_t q = 0; q < unit; ++q) out.push_back(in[i + q]);
+        i += unit;
+    }
+}
+
+// The complete op program of one SEG_TILE / SEG_LOW6 segment, appended to `out`.
+inline void build_segment_ops(const Plan& plan, const Segment& seg, const PlanConfig& cfg, std::vector<TileOp>& out) {
+    ExpandArgs ex;
+    fill_expand(ex, seg.tile_mask);
+    std::vector<TileOp> seg_ops, grouped;
+    seg_ops.reserve(seg.gates.size());
+    for (int gi : seg.gates) seg_ops.push_back(make_tile_op(plan, plan.gates[gi], seg.tile_mask, ex));
+    const bool tile = seg.cls == SEG_TILE;
+    append_with_phases(seg_ops, ex.m, cfg.phases && tile, cfg.mono && tile, grouped);
+    if (tile) layout_batches(grouped, out);
+    else out.insert(out.end(), grouped.begin(), grouped.end());
+}
+
+}  // namespace b2svk
