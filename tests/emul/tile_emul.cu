@@ -189,15 +189,13 @@ void run_reg_phase(std::vector<cplx>& tile, const TileOp& hdr, const TileOp* ops
 template <int V>
 int run_mono_rounds(std::vector<cplx>& tile, const TileOp& hdr, const TileOp* ops, int k, uint64_t base, Counters& c) {
     const int E = kMonoElems;
-    const int tb = hdr.mono.tb, lb = hdr.mono.lb, vbits = hdr.mono.vbits;
+    const uint32_t tmask = hdr.mono.tmask, qlmask = hdr.mono.qlmask, nmask = hdr.mono.nmask;
+    const int tb = __builtin_popcount(tmask), lb = hdr.mono.lb, vbits = hdr.mono.vbits;
     if (tb + lb != k || (1 << vbits) != V || vbits > lb || tb > kMonoThreadBits) return -1;
     if (hdr.mono.fac ? V > kMonoMaxVFac : V > kMonoMaxV) return -4;
-    {  // the thread and loop positions must be a permutation of the tile positions
-        uint32_t seen = 0;
-        for (int i = 0; i < tb; ++i) seen |= 1u << hdr.mono.tp[i];
-        for (int i = 0; i < lb; ++i) seen |= 1u << hdr.mono.lp[i];
-        if (seen != (1u << k) - 1u) return -5;
-    }
+    // thread, walk and untouched loop positions partition the tile positions
+    if ((tmask | qlmask | nmask) != (1u << k) - 1u || (tmask & qlmask) || (tmask & nmask) || (qlmask & nmask)) return -5;
+    if (__builtin_popcount(qlmask) != vbits) return -5;
     const uint32_t n_threads = 1u << tb, per_thread = 1u << lb;
     const uint32_t rounds = per_thread > (uint32_t)E ? per_thread / E : 1;
     if ((int64_t)rounds > c.mono_rounds_max) c.mono_rounds_max = rounds;
@@ -206,10 +204,12 @@ int run_mono_rounds(std::vector<cplx>& tile, const TileOp& hdr, const TileOp* op
     for (uint32_t t = 0; t < n_threads; ++t) {
         uint32_t idx[V];
         double2 f[V];
-        const uint32_t tpart = mono_deposit(t, hdr.mono.tp, tb);
+        const uint32_t tpart = mono_deposit(t, tmask);
+        uint32_t q = 0;
         for (int v = 0; v < V; ++v) {
-            idx[v] = qsrc[(size_t)t * V + v] = tpart | mono_deposit((uint32_t)v, hdr.mono.lp, vbits);
+            idx[v] = qsrc[(size_t)t * V + v] = tpart | q;
             f[v] = make_double2(1.0, 0.0);
+            q = mono_next_subset(q, qlmask);
         }
         if (hdr.mono.fac) mono_run_members<V, true>(ops, hdr.mono.count, base, idx, f);
         else mono_run_members<V, false>(ops, hdr.mono.count, base, idx, f);
@@ -221,19 +221,22 @@ int run_mono_rounds(std::vector<cplx>& tile, const TileOp& hdr, const TileOp* op
     std::vector<char> written(tile.size(), 0);
     std::vector<uint32_t> dst;
     std::vector<cplx> val;
+    std::vector<uint32_t> ncur(n_threads, 0);
     for (uint32_t j0 = 0; j0 < per_thread; j0 += E) {
         dst.clear();
         val.clear();
         std::vector<char> in_round(tile.size(), 0);
         for (uint32_t t = 0; t < n_threads; ++t)
-            for (int e = 0; e < E && j0 + e < per_thread; ++e) {
-                const uint32_t j = j0 + e;
+            for (int e = 0; e < E; ++e) {
                 const int v = e & (V - 1);
-                const uint32_t src = qsrc[(size_t)t * V + v] | mono_deposit(j >> vbits, hdr.mono.lp + vbits, lb - vbits);
-                if (src >= tile.size() || in_round[src]) return -6;  // every amplitude is read exactly once
-                in_round[src] = 1;
-                dst.push_back(src ^ qx[(size_t)t * V + v]);
-                val.push_back(hdr.mono.fac ? fac[(size_t)t * V + v] * tile[src] : tile[src]);
+                const uint32_t src = qsrc[(size_t)t * V + v] | ncur[t];
+                if (j0 + e < per_thread) {
+                    if (src >= tile.size() || in_round[src]) return -6;  // every amplitude is read exactly once
+                    in_round[src] = 1;
+                    dst.push_back(src ^ qx[(size_t)t * V + v]);
+                    val.push_back(hdr.mono.fac ? fac[(size_t)t * V + v] * tile[src] : tile[src]);
+                }
+                if (v == V - 1) ncur[t] = mono_next_subset(ncur[t], nmask);
             }
         for (size_t q = 0; q < dst.size(); ++q) {
             if (dst[q] >= tile.size() || written[dst[q]]) return -2;  // a bijection

@@ -138,12 +138,20 @@ cudaEvent_t get_event(b2sv* sv) {
 // Resolve recorded event pairs into the stats (synchronises the stream).
 int drain_events(b2sv* sv) {
     CU(cudaStreamSynchronize(sv->stream));
+    // B2SV_DUMP_TIMES=<file>: append "class ms" of every timed launch, in launch order (profiling aid)
+    static const char* dump_path = std::getenv("B2SV_DUMP_TIMES");
+    FILE* dump = (dump_path && !sv->timed.empty()) ? std::fopen(dump_path, "a") : nullptr;
     for (auto& t : sv->timed) {
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, t.a, t.b));
+        if (dump) std::fprintf(dump, "%d %.6f\n", t.cls, ms);
         sv->stats.ms_by_class[t.cls] += ms;
         sv->event_pool.push_back(t.a);
         sv->event_pool.push_back(t.b);
+    }
+    if (dump) {
+        std::fprintf(dump, "-1 0\n");
+        std::fclose(dump);
     }
     sv->timed.clear();
     for (auto& p : sv->apply_events) {

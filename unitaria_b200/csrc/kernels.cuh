@@ -146,11 +146,13 @@ struct __align__(16) TileOp {
         } ph;
         struct {               // op == kOpMono: header of a monomial phase, `count` member ops follow
             uint16_t count;        // (same place as ph.count)
-            uint8_t tb, lb;        // tile-local index = thread bits (tb of them) + loop bits (lb of them)
-            uint8_t vbits;         // the first `vbits` loop bits are touched by the run (Q bits), the rest are not
+            uint8_t lb;            // a thread owns 2^lb amplitudes (tile-local index = thread bits + loop bits)
+            uint8_t vbits;         // 2^vbits index walks per thread = popcount(qlmask)
             uint8_t fac;           // 1: the run has PHASE / DIAG1 members (amplitudes pick up factors)
-            uint8_t tp[8];         // tile-local position of thread bit i (ascending)
-            uint8_t lp[8];         // tile-local position of loop bit i
+            uint8_t pad[3];
+            uint32_t tmask;        // tile-local positions that take the thread number (ascending)
+            uint32_t qlmask;       // loop positions the run touches (Q bits that did not fit the thread number)
+            uint32_t nmask;        // loop positions the run does not touch
         } mono;
     };
 };
@@ -585,17 +587,25 @@ __device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, con
 template <int V, bool FAC>
 __host__ __device__ __forceinline__ void mono_run_members(const TileOp* ops, int count, uint64_t base, uint32_t (&idx)[V],
                                                           double2 (&f)[V]) {
+    // the first 16 bytes of a TileOp hold {op, tpos, tpos2, nfix, lctrl, ...}; the next gate's words are
+    // fetched while the current one is applied (the loop is a chain of dependent shared-memory loads otherwise)
+    uint4 hn = *reinterpret_cast<const uint4*>(&ops[0]);
+    uint64_t extn = ops[0].ext_ctrl;
     for (int mi = 0; mi < count; ++mi) {
-        const TileOp& op = ops[mi];
-        if ((base & op.ext_ctrl) != op.ext_ctrl) continue;  // CTA-uniform
-        const uint32_t lc = op.lctrl;
-        const int kind = op.op;
+        const uint4 h = hn;
+        const uint64_t ext = extn;
+        if (mi + 1 < count) {
+            hn = *reinterpret_cast<const uint4*>(&ops[mi + 1]);
+            extn = ops[mi + 1].ext_ctrl;
+        }
+        if ((base & ext) != ext) continue;  // CTA-uniform
+        const uint32_t lc = h.y;
+        const int kind = (int)(h.x & 0xFFu), pa = (int)((h.x >> 8) & 0xFFu), pb = (int)((h.x >> 16) & 0xFFu);
         if (kind == B2SV_OP_X) {
-            const uint32_t bt = 1u << op.tpos;
+            const uint32_t bt = 1u << pa;
 #pragma unroll
             for (int e = 0; e < V; ++e) idx[e] ^= ((~idx[e] & lc) == 0u) ? bt : 0u;
         } else if (kind == B2SV_OP_SWAP) {
-            const int pa = op.tpos, pb = op.tpos2;
             const uint32_t both = (1u << pa) | (1u << pb);
 #pragma unroll
             for (int e = 0; e < V; ++e) {
@@ -603,65 +613,82 @@ __host__ __device__ __forceinline__ void mono_run_members(const TileOp* ops, int
                 idx[e] ^= (differ && (~idx[e] & lc) == 0u) ? both : 0u;
             }
         } else if (FAC && kind == B2SV_OP_PHASE) {
+            const TileOp& op = ops[mi];
             const double2 w = make_double2(op.m[0], op.m[1]);
 #pragma unroll
             for (int e = 0; e < V; ++e)
                 if ((~idx[e] & lc) == 0u) f[e] = cmul(w, f[e]);
         } else if (FAC && kind == B2SV_OP_DIAG1) {
+            const TileOp& op = ops[mi];
             const double2 d0 = make_double2(op.m[0], op.m[1]), d1 = make_double2(op.m[2], op.m[3]);
-            if (op.tpos == 0xFF) {  // target outside the tile: one CTA-uniform factor
+            if (pa == 0xFF) {  // target outside the tile: one CTA-uniform factor
                 const double2 d = (base & op.ext_tbit) ? d1 : d0;
 #pragma unroll
                 for (int e = 0; e < V; ++e)
                     if ((~idx[e] & lc) == 0u) f[e] = cmul(d, f[e]);
             } else {
-                const int pt = op.tpos;
 #pragma unroll
                 for (int e = 0; e < V; ++e)
-                    if ((~idx[e] & lc) == 0u) f[e] = cmul(((idx[e] >> pt) & 1u) ? d1 : d0, f[e]);
+                    if ((~idx[e] & lc) == 0u) f[e] = cmul(((idx[e] >> pa) & 1u) ? d1 : d0, f[e]);
             }
         }
     }
 }
 
-// scatter the low bits of x to the tile-local positions pos[0..n)
-__host__ __device__ __forceinline__ uint32_t mono_deposit(uint32_t x, const uint8_t* pos, int n) {
+// scatter the low bits of x to the set positions of mask (ascending)
+__host__ __device__ __forceinline__ uint32_t mono_deposit(uint32_t x, uint32_t mask) {
     uint32_t out = 0;
-    for (int i = 0; i < n; ++i) out |= ((x >> i) & 1u) << pos[i];
+#pragma unroll 1
+    while (mask) {
+        const uint32_t low = mask & (0u - mask);
+        if (x & 1u) out |= low;
+        x >>= 1;
+        mask ^= low;
+    }
     return out;
 }
+// successor of subset `cur` of `mask` in counting order (wraps to 0 after the full mask)
+__host__ __device__ __forceinline__ uint32_t mono_next_subset(uint32_t cur, uint32_t mask) { return ((cur | ~mask) + 1u) & mask; }
 
 template <typename A, int V, bool FAC, typename TV>
 __device__ __forceinline__ void tile_mono_rounds(TV tile, const TileOp& hdr, const TileOp* ops, uint64_t base) {
     constexpr int E = kMonoElems;
-    const int lb = hdr.mono.lb, vbits = hdr.mono.vbits;
-    const uint32_t tpart = mono_deposit(threadIdx.x, hdr.mono.tp, hdr.mono.tb);
-    const bool active = threadIdx.x < (1u << hdr.mono.tb);
+    const uint32_t tmask = hdr.mono.tmask, qlmask = hdr.mono.qlmask, nmask = hdr.mono.nmask;
+    const uint32_t per_thread = 1u << hdr.mono.lb;
+    const int count = hdr.mono.count;
+    const uint32_t tpart = mono_deposit(threadIdx.x, tmask);
+    const bool active = threadIdx.x < (1u << __popc(tmask));
     // walk this thread's V index values through the run
     uint32_t qsrc[V], qidx[V];
     double2 fac[V];
+    {
+        uint32_t q = 0;
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-        qsrc[v] = qidx[v] = tpart | mono_deposit((uint32_t)v, hdr.mono.lp, vbits);
-        fac[v] = make_double2(1.0, 0.0);
+        for (int v = 0; v < V; ++v) {
+            qsrc[v] = qidx[v] = tpart | q;
+            fac[v] = make_double2(1.0, 0.0);
+            q = mono_next_subset(q, qlmask);
+        }
     }
-    mono_run_members<V, FAC>(ops, hdr.mono.count, base, qidx, fac);
+    mono_run_members<V, FAC>(ops, count, base, qidx, fac);
 #pragma unroll
     for (int v = 0; v < V; ++v) qidx[v] ^= qsrc[v];  // XOR mask that takes a source index to its destination
-    const uint32_t per_thread = 1u << lb;
+    uint32_t ncur = 0;  // the untouched loop bits of the current amplitudes
+#pragma unroll 1
     for (uint32_t j0 = 0; j0 < per_thread; j0 += E) {
         uint32_t dst[E];
         double2 val[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            const uint32_t j = j0 + e;
-            const int v = e & (V - 1);  // E is a multiple of V: the walk of element j is j mod V
-            const uint32_t src = qsrc[v] | mono_deposit(j >> vbits, hdr.mono.lp + vbits, lb - vbits);
+            constexpr int VM = V - 1;
+            const int v = e & VM;  // E is a multiple of V: consecutive amplitudes cycle through the walks
+            const uint32_t src = qsrc[v] | ncur;
             dst[e] = src ^ qidx[v];
-            if (active && j < per_thread) {
+            if (active && j0 + e < per_thread) {
                 val[e] = to_c128(tile[src]);
                 if (FAC) val[e] = cmul(fac[v], val[e]);
             }
+            if (v == VM) ncur = mono_next_subset(ncur, nmask);
         }
         __syncthreads();  // every amplitude of the round is in registers before the first one is overwritten
 #pragma unroll
@@ -671,8 +698,10 @@ __device__ __forceinline__ void tile_mono_rounds(TV tile, const TileOp& hdr, con
     }
 }
 
+// Out of line on purpose: the seven walk variants are large, and inlined into the sweep kernels they
+// slowed down sweeps that never run them (more than 200 KiB of extra code per kernel).
 template <typename A, typename TV>
-__device__ __forceinline__ void tile_apply_mono(TV tile, const TileOp& hdr, const TileOp* ops, uint64_t base) {
+__device__ __noinline__ void tile_apply_mono(TV tile, const TileOp& hdr, const TileOp* ops, uint64_t base) {
     if (hdr.mono.fac) {
         switch (hdr.mono.vbits) {
             case 0: tile_mono_rounds<A, 1, true>(tile, hdr, ops, base); break;

@@ -182,7 +182,6 @@ inline void append_with_phases(const std::vector<TileOp>& ops, int k, bool enabl
             h.op = kOpMono;
             h.mono.count = (uint16_t)(jm - i);
             h.mono.fac = fac ? 1 : 0;
-            h.mono.tb = (uint8_t)tb;
             h.mono.lb = (uint8_t)(k - tb);
             // thread bits: Q positions first (ascending), filled up with the lowest other positions; the lowest
             // positions end up in the lane number, so a warp reads whole 128-byte rows whenever it can
@@ -191,14 +190,11 @@ inline void append_with_phases(const std::vector<TileOp>& ops, int k, bool enabl
                 if ((Q >> p) & 1) tmask |= 1u << p;
             for (int p = 0; p < k && __builtin_popcount(tmask) < tb; ++p)
                 if (!((tmask >> p) & 1)) tmask |= 1u << p;
-            int nt = 0, nl = 0;
-            for (int p = 0; p < k; ++p)
-                if ((tmask >> p) & 1) h.mono.tp[nt++] = (uint8_t)p;
-            for (int p = 0; p < k; ++p)  // loop bits: the Q positions that did not fit first
-                if (!((tmask >> p) & 1) && ((Q >> p) & 1)) h.mono.lp[nl++] = (uint8_t)p;
-            h.mono.vbits = (uint8_t)nl;
-            for (int p = 0; p < k; ++p)
-                if (!((tmask >> p) & 1) && !((Q >> p) & 1)) h.mono.lp[nl++] = (uint8_t)p;
+            const uint32_t all = (1u << k) - 1u;
+            h.mono.tmask = tmask;
+            h.mono.qlmask = Q & ~tmask & all;       // the Q positions that did not fit: 2^vbits walks per thread
+            h.mono.nmask = ~Q & ~tmask & all;
+            h.mono.vbits = (uint8_t)__builtin_popcount(h.mono.qlmask);
             out.push_back(h);
             for (size_t q = i; q < jm; ++q) out.push_back(ops[q]);
             i = jm;
