@@ -60,7 +60,7 @@ void apply_plain(std::vector<cplx>& psi, int n, const PGate& g) {
 
 struct Counters {
     int64_t tile = 0, perm = 0, gate1q = 0, low6 = 0, mono_phases = 0, mono_members = 0, reg_phases = 0, reg_members = 0, max_ops = 0,
-            nops = 0, mono_rounds_max = 0;
+            nops = 0, mono_rounds_max = 0, mono_tab = 0, mono_tab_phases_run = 0;
 };
 
 // one op (not a header) on a tile held as tile[l], l = tile-local index
@@ -187,7 +187,7 @@ void run_reg_phase(std::vector<cplx>& tile, const TileOp& hdr, const TileOp* ops
 // mirrors tile_apply_mono / tile_mono_rounds: per-thread index walks, rounds of kMonoElems amplitudes per
 // thread, all reads of a round before its writes
 template <int V>
-int run_mono_rounds(std::vector<cplx>& tile, const TileOp& hdr, const TileOp* ops, int k, uint64_t base, Counters& c) {
+int run_mono_rounds(std::vector<cplx>& tile, const TileOp& hdr, const TileOp* ops, int k, uint64_t base, const Plan& plan, Counters& c) {
     const int E = kMonoElems;
     const uint32_t tmask = hdr.mono.tmask, qlmask = hdr.mono.qlmask, nmask = hdr.mono.nmask;
     const int tb = __builtin_popcount(tmask), lb = hdr.mono.lb, vbits = hdr.mono.vbits;
@@ -210,6 +210,25 @@ int run_mono_rounds(std::vector<cplx>& tile, const TileOp& hdr, const TileOp* op
             idx[v] = qsrc[(size_t)t * V + v] = tpart | q;
             f[v] = make_double2(1.0, 0.0);
             q = mono_next_subset(q, qlmask);
+        }
+        if (hdr.mono.tab) {
+            // table-driven: the host did the walks (tileops.hpp: mono_build_table); index exactly as the device does
+            if (hdr.mono.count != 0 || hdr.mono.ebits > kMonoMaxEbits) return -9;
+            uint32_t slice = 0;
+            for (int i = 0; i < hdr.mono.ebits; ++i) slice |= (uint32_t)((base >> hdr.mono.epos[i]) & 1ull) << i;
+            const size_t first = (((size_t)slice << tb) + t) * V;
+            const double2* tables = reinterpret_cast<const double2*>(plan.mux_tables.data());
+            const uint16_t* xm = reinterpret_cast<const uint16_t*>(tables + hdr.mono.mask_off) + first;
+            if ((hdr.mono.mask_off * 2 + ((first + V) * 2 + 7) / 8) > plan.mux_tables.size()) return -11;
+            for (int v = 0; v < V; ++v) {
+                qx[(size_t)t * V + v] = xm[v];
+                fac[(size_t)t * V + v] = cplx(1.0, 0.0);
+                if (hdr.mono.fac) {
+                    const double2 fv = (tables + hdr.mono.fac_off + first)[v];
+                    fac[(size_t)t * V + v] = cplx(fv.x, fv.y);
+                }
+            }
+            continue;
         }
         if (hdr.mono.fac) mono_run_members<V, true>(ops, hdr.mono.count, base, idx, f);
         else mono_run_members<V, false>(ops, hdr.mono.count, base, idx, f);
@@ -250,12 +269,12 @@ int run_mono_rounds(std::vector<cplx>& tile, const TileOp& hdr, const TileOp* op
     return 0;
 }
 
-int run_mono_phase(std::vector<cplx>& tile, const TileOp& hdr, const TileOp* ops, int k, uint64_t base, Counters& c) {
+int run_mono_phase(std::vector<cplx>& tile, const TileOp& hdr, const TileOp* ops, int k, uint64_t base, const Plan& plan, Counters& c) {
     switch (hdr.mono.vbits) {
-        case 0: return run_mono_rounds<1>(tile, hdr, ops, k, base, c);
-        case 1: return run_mono_rounds<2>(tile, hdr, ops, k, base, c);
-        case 2: return run_mono_rounds<4>(tile, hdr, ops, k, base, c);
-        case 3: return run_mono_rounds<8>(tile, hdr, ops, k, base, c);
+        case 0: return run_mono_rounds<1>(tile, hdr, ops, k, base, plan, c);
+        case 1: return run_mono_rounds<2>(tile, hdr, ops, k, base, plan, c);
+        case 2: return run_mono_rounds<4>(tile, hdr, ops, k, base, plan, c);
+        case 3: return run_mono_rounds<8>(tile, hdr, ops, k, base, plan, c);
         default: return -8;
     }
 }
@@ -267,12 +286,19 @@ int run_program(std::vector<cplx>& tile, const TileOp* ops, int n_ops, int k, ui
         for (int o = 0; o < nb; ++o) {
             const TileOp& op = s_ops[o];
             if (op.op == kOpPhase || op.op == kOpMono) {
-                if (o + op.ph.count >= nb) return -10;  // a phase straddles a batch boundary
+                if (o + op.ph.count >= nb + (op.ph.count == 0 ? 1 : 0)) return -10;  // a phase straddles a batch boundary
                 bool any = false;
-                for (int mi = 1; mi <= op.ph.count; ++mi) any |= (base & s_ops[o + mi].ext_ctrl) == s_ops[o + mi].ext_ctrl;
+                if (op.op == kOpMono && op.mono.tab) {
+                    uint32_t slice = 0;
+                    for (int i = 0; i < op.mono.ebits; ++i) slice |= (uint32_t)((base >> op.mono.epos[i]) & 1ull) << i;
+                    any = !((op.mono.identity >> slice) & 1u);
+                    c.mono_tab_phases_run++;
+                } else {
+                    for (int mi = 1; mi <= op.ph.count; ++mi) any |= (base & s_ops[o + mi].ext_ctrl) == s_ops[o + mi].ext_ctrl;
+                }
                 if (any) {
                     if (op.op == kOpPhase) run_reg_phase(tile, op, s_ops + o + 1, k, base);
-                    else if (int rc = run_mono_phase(tile, op, s_ops + o + 1, k, base, c)) return rc;
+                    else if (int rc = run_mono_phase(tile, op, s_ops + o + 1, k, base, plan, c)) return rc;
                 }
                 o += op.ph.count;
                 continue;
@@ -287,7 +313,7 @@ int run_program(std::vector<cplx>& tile, const TileOp* ops, int n_ops, int k, ui
 }  // namespace
 
 extern "C" int emul_apply(int n, int dtype, const b2sv_gate* gates, size_t n_gates, const b2sv_plan_opts* opts, double* amps,
-                          int64_t* info /* 11 counters */) {
+                          int64_t* info /* 12 counters */) {
     PlanConfig cfg = default_config(n, dtype, opts);
     if (n < 13) cfg.perm_runs = false;  // as b2sv_apply
     Plan plan = make_plan(gates, n_gates, cfg, true);
@@ -314,6 +340,7 @@ extern "C" int emul_apply(int n, int dtype, const b2sv_gate* gates, size_t n_gat
         for (size_t o = 0; o < ops.size(); ++o) {
             if (ops[o].op == kOpMono) {
                 c.mono_phases++;
+                c.mono_tab += ops[o].mono.tab;
                 c.mono_members += ops[o].ph.count;
             } else if (ops[o].op == kOpPhase) {
                 c.reg_phases++;
@@ -348,7 +375,7 @@ extern "C" int emul_apply(int n, int dtype, const b2sv_gate* gates, size_t n_gat
         amps[2 * i + 1] = v.imag();
     }
     if (info) {
-        const int64_t out[11] = {c.tile, c.perm, c.gate1q, c.low6, c.mono_phases, c.mono_members, c.reg_phases, c.reg_members, c.max_ops, c.nops, c.mono_rounds_max};
+        const int64_t out[12] = {c.tile, c.perm, c.gate1q, c.low6, c.mono_phases, c.mono_members, c.reg_phases, c.reg_members, c.max_ops, c.nops, c.mono_rounds_max, c.mono_tab};
         std::memcpy(info, out, sizeof(out));
     }
     return 0;

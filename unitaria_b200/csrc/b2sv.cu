@@ -912,7 +912,7 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
             key = (key ^ w[i]) * 1099511628211ull;
             key2 += w[i] * (2 * i + 1);
         }
-        const uint64_t o = (uint64_t)cfg.fuse | ((uint64_t)cfg.perm_runs << 1) | ((uint64_t)cfg.mux << 2) | ((uint64_t)cfg.phases << 3) | ((uint64_t)cfg.low6 << 4) | ((uint64_t)cfg.mono << 5) |
+        const uint64_t o = (uint64_t)cfg.fuse | ((uint64_t)cfg.perm_runs << 1) | ((uint64_t)cfg.mux << 2) | ((uint64_t)cfg.phases << 3) | ((uint64_t)cfg.low6 << 4) | ((uint64_t)cfg.mono << 5) | ((uint64_t)cfg.mono_tables << 6) |
                            ((uint64_t)cfg.tile_qubits << 8) | ((uint64_t)cfg.lookahead << 16) | ((uint64_t)sv->scratch_failed << 40);
         key = (key ^ o) * 1099511628211ull;
     }
@@ -945,7 +945,7 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
             if ((int)best >= cfg.perm_min) scratch_ok = ensure_scratch(sv) == B2SV_OK;
         }
         sv->plan = make_plan(gates, n_gates, cfg, scratch_ok);
-        const Plan& np = sv->plan;
+        Plan& np = sv->plan;
         // tile ops of all tile segments, one upload
         std::vector<TileOp> host_ops;
         sv->plan_seg_first.assign(np.segs.size(), 0);

@@ -144,15 +144,21 @@ struct __align__(16) TileOp {
             uint16_t count;
             uint8_t rpos[3];       // the three tile-local positions held in registers (ascending)
         } ph;
-        struct {               // op == kOpMono: header of a monomial phase, `count` member ops follow
-            uint16_t count;        // (same place as ph.count)
+        struct {               // op == kOpMono: header of a monomial phase
+            uint16_t count;        // member ops that follow (same place as ph.count); 0 when the phase is table-driven
             uint8_t lb;            // a thread owns 2^lb amplitudes (tile-local index = thread bits + loop bits)
             uint8_t vbits;         // 2^vbits index walks per thread = popcount(qlmask)
             uint8_t fac;           // 1: the run has PHASE / DIAG1 members (amplitudes pick up factors)
-            uint8_t pad[3];
+            uint8_t tab;           // 1: the walks were done on the host, their results are in TileArgs::tables
+            uint8_t ebits;         // table-driven: qubits outside the tile that members test (beyond the sweep's
+            uint8_t pad;           //   common controls): one table slice per value of those bits
             uint32_t tmask;        // tile-local positions that take the thread number (ascending)
             uint32_t qlmask;       // loop positions the run touches (Q bits that did not fit the thread number)
             uint32_t nmask;        // loop positions the run does not touch
+            uint8_t epos[4];       // global qubit numbers of the `ebits` outside bits
+            uint32_t identity;     // bit p set: slice p moves nothing and multiplies nothing -- skip the phase
+            uint64_t mask_off;     // first uint16 XOR mask, counted in double2 units from the start of the tables
+            uint64_t fac_off;      // first double2 factor (fac == 1), same units
         } mono;
     };
 };
@@ -164,6 +170,7 @@ constexpr int kOpNop = 9;    // padding in front of a batch boundary of a long o
 constexpr int kMonoElems = 8;              // amplitudes a thread carries through one round of a monomial phase
 constexpr int kMonoThreadBits = 8;         // log2(kThreads)
 constexpr int kMonoMaxV = 8, kMonoMaxVFac = 4;  // index walks per thread (pure permutation / with factors)
+constexpr int kMonoMaxEbits = 4;           // table-driven phases: at most 16 slices
 static_assert(sizeof(TileOp) == 96, "TileOp layout");
 
 struct TileArgs {
@@ -651,15 +658,15 @@ __host__ __device__ __forceinline__ uint32_t mono_deposit(uint32_t x, uint32_t m
 __host__ __device__ __forceinline__ uint32_t mono_next_subset(uint32_t cur, uint32_t mask) { return ((cur | ~mask) + 1u) & mask; }
 
 template <typename A, int V, bool FAC, typename TV>
-__device__ __forceinline__ void tile_mono_rounds(TV tile, const TileOp& hdr, const TileOp* ops, uint64_t base) {
+__device__ __forceinline__ void tile_mono_rounds(TV tile, const TileOp& hdr, const TileOp* ops, uint64_t base,
+                                                 const double2* __restrict__ tables) {
     constexpr int E = kMonoElems;
     const uint32_t tmask = hdr.mono.tmask, qlmask = hdr.mono.qlmask, nmask = hdr.mono.nmask;
     const uint32_t per_thread = 1u << hdr.mono.lb;
-    const int count = hdr.mono.count;
+    const int tbits = __popc(tmask);
     const uint32_t tpart = mono_deposit(threadIdx.x, tmask);
-    const bool active = threadIdx.x < (1u << __popc(tmask));
-    // walk this thread's V index values through the run
-    uint32_t qsrc[V], qidx[V];
+    const bool active = threadIdx.x < (1u << tbits);
+    uint32_t qsrc[V], qidx[V];  // source index of each walk; afterwards the XOR mask to its destination
     double2 fac[V];
     {
         uint32_t q = 0;
@@ -670,9 +677,26 @@ __device__ __forceinline__ void tile_mono_rounds(TV tile, const TileOp& hdr, con
             q = mono_next_subset(q, qlmask);
         }
     }
-    mono_run_members<V, FAC>(ops, count, base, qidx, fac);
+    if (hdr.mono.tab) {
+        // the host walked every (thread, walk) index through the run, once per value of the outside bits the
+        // members test: fetch this thread's results
+        uint32_t slice = 0;
+        for (int i = 0; i < hdr.mono.ebits; ++i) slice |= (uint32_t)((base >> hdr.mono.epos[i]) & 1ull) << i;
+        const size_t first = (((size_t)slice << tbits) + (active ? threadIdx.x : 0u)) * V;
+        const uint16_t* __restrict__ xm = reinterpret_cast<const uint16_t*>(tables + hdr.mono.mask_off) + first;
 #pragma unroll
-    for (int v = 0; v < V; ++v) qidx[v] ^= qsrc[v];  // XOR mask that takes a source index to its destination
+        for (int v = 0; v < V; ++v) qidx[v] = __ldg(xm + v);
+        if (FAC) {
+            const double2* __restrict__ fm = tables + hdr.mono.fac_off + first;
+#pragma unroll
+            for (int v = 0; v < V; ++v) fac[v] = __ldg(fm + v);
+        }
+    } else {
+        // walk this thread's V index values through the run
+        mono_run_members<V, FAC>(ops, hdr.mono.count, base, qidx, fac);
+#pragma unroll
+        for (int v = 0; v < V; ++v) qidx[v] ^= qsrc[v];
+    }
     uint32_t ncur = 0;  // the untouched loop bits of the current amplitudes
 #pragma unroll 1
     for (uint32_t j0 = 0; j0 < per_thread; j0 += E) {
@@ -701,19 +725,20 @@ __device__ __forceinline__ void tile_mono_rounds(TV tile, const TileOp& hdr, con
 // Out of line on purpose: the seven walk variants are large, and inlined into the sweep kernels they
 // slowed down sweeps that never run them (more than 200 KiB of extra code per kernel).
 template <typename A, typename TV>
-__device__ __noinline__ void tile_apply_mono(TV tile, const TileOp& hdr, const TileOp* ops, uint64_t base) {
+__device__ __noinline__ void tile_apply_mono(TV tile, const TileOp& hdr, const TileOp* ops, uint64_t base,
+                                             const double2* __restrict__ tables) {
     if (hdr.mono.fac) {
         switch (hdr.mono.vbits) {
-            case 0: tile_mono_rounds<A, 1, true>(tile, hdr, ops, base); break;
-            case 1: tile_mono_rounds<A, 2, true>(tile, hdr, ops, base); break;
-            default: tile_mono_rounds<A, 4, true>(tile, hdr, ops, base); break;
+            case 0: tile_mono_rounds<A, 1, true>(tile, hdr, ops, base, tables); break;
+            case 1: tile_mono_rounds<A, 2, true>(tile, hdr, ops, base, tables); break;
+            default: tile_mono_rounds<A, 4, true>(tile, hdr, ops, base, tables); break;
         }
     } else {
         switch (hdr.mono.vbits) {
-            case 0: tile_mono_rounds<A, 1, false>(tile, hdr, ops, base); break;
-            case 1: tile_mono_rounds<A, 2, false>(tile, hdr, ops, base); break;
-            case 2: tile_mono_rounds<A, 4, false>(tile, hdr, ops, base); break;
-            default: tile_mono_rounds<A, 8, false>(tile, hdr, ops, base); break;
+            case 0: tile_mono_rounds<A, 1, false>(tile, hdr, ops, base, tables); break;
+            case 1: tile_mono_rounds<A, 2, false>(tile, hdr, ops, base, tables); break;
+            case 2: tile_mono_rounds<A, 4, false>(tile, hdr, ops, base, tables); break;
+            default: tile_mono_rounds<A, 8, false>(tile, hdr, ops, base, tables); break;
         }
     }
 }
@@ -726,10 +751,16 @@ __device__ __forceinline__ void tile_run_ops(TV tile, const TileOp* s_ops, int n
         const TileOp& op = s_ops[o];
         if (op.op == kOpPhase || op.op == kOpMono) {
             bool any = false;  // CTA-uniform: is any gate of the phase active on this tile?
-            for (int mi = 1; mi <= op.ph.count; ++mi) any |= (base & s_ops[o + mi].ext_ctrl) == s_ops[o + mi].ext_ctrl;
+            if (op.op == kOpMono && op.mono.tab) {
+                uint32_t slice = 0;
+                for (int i = 0; i < op.mono.ebits; ++i) slice |= (uint32_t)((base >> op.mono.epos[i]) & 1ull) << i;
+                any = !((op.mono.identity >> slice) & 1u);
+            } else {
+                for (int mi = 1; mi <= op.ph.count; ++mi) any |= (base & s_ops[o + mi].ext_ctrl) == s_ops[o + mi].ext_ctrl;
+            }
             if (any) {
                 if (op.op == kOpPhase) tile_apply_phase<A>(tile, op, s_ops + o + 1, k, base);
-                else tile_apply_mono<A>(tile, op, s_ops + o + 1, base);
+                else tile_apply_mono<A>(tile, op, s_ops + o + 1, base, tables);
                 __syncthreads();
             }
             o += op.ph.count;

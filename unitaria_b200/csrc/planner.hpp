@@ -88,8 +88,9 @@ struct PlanConfig {
     bool low6 = true;                     // sweeps confined to the low 6 qubits use the warp-shuffle kernel
     bool mono = true;                     // monomial phases: runs of X / SWAP / phase gates inside a tile sweep cost
                                           // index arithmetic only, so such runs ride in tile sweeps
-    double mono_gate_cost = 0.008;        // one gate of a monomial phase in units of one full sweep (~40-55 issue
-                                          // cycles per 64 KiB tile against ~5700 cycles of HBM time per tile)
+    bool mono_tables = true;              // monomial phases: do the index walks on the host (per-gate device cost: none)
+    double mono_gate_cost = 0.015;        // one gate of a device-walked monomial phase in units of one full sweep
+                                          // (measured 0.010-0.023, scripts/microbench_mono.py)
 };
 
 // Tunable for experiments through B2SV_MONO_COST.
@@ -97,7 +98,7 @@ inline double mono_gate_cost_default() {
     static const double v = [] {
         const char* e = std::getenv("B2SV_MONO_COST");
         const double x = e ? std::atof(e) : 0.0;
-        return x > 0.0 ? x : 0.008;
+        return x > 0.0 ? x : 0.015;  // measured: scripts/microbench_mono.py
     }();
     return v;
 }
@@ -140,9 +141,16 @@ inline PlanConfig default_config(int n, int dtype, const b2sv_plan_opts* o) {
     PlanConfig c;
     c.n = n;
     c.amp_bytes = dtype == B2SV_C64 ? 8 : 16;
-    c.mono_gate_cost = mono_gate_cost_default();
+    c.mono_gate_cost = mono_gate_cost_default();  // (device walks; halved below when the host does the walks)
     c.tile_qubits = dtype == B2SV_C64 ? 13 : 12;  // 64 KiB of shared memory either way
     c.chunk_bits = dtype == B2SV_C64 ? 8 : 7;     // 2 KiB contiguous per bulk copy
+    {   // B2SV_CHUNK_BITS: experiment knob (fewer forced low qubits leave more tile qubits for targets)
+        static const int env_chunk = [] {
+            const char* e = std::getenv("B2SV_CHUNK_BITS");
+            return e ? std::atoi(e) : 0;
+        }();
+        if (env_chunk > 0) c.chunk_bits = env_chunk;
+    }
     // B2SV_AB: A/B switch bits (same meaning as b2sv_plan_opts::reserved) for runs that use default options
     static const int env_ab = [] {
         const char* e = std::getenv("B2SV_AB");
@@ -152,6 +160,7 @@ inline PlanConfig default_config(int n, int dtype, const b2sv_plan_opts* o) {
     c.phases = !(env_ab & 2);
     c.low6 = !(env_ab & 4);
     c.mono = !(env_ab & 8);
+    c.mono_tables = !(env_ab & 16);
     if (o) {
         c.fuse = o->fuse != 0;
         c.perm_runs = o->perm_runs != 0;
@@ -162,8 +171,10 @@ inline PlanConfig default_config(int n, int dtype, const b2sv_plan_opts* o) {
         c.phases = !(ab & 2);  // reserved bit 1: no register phases (A/B switch)
         c.low6 = !(ab & 4);    // reserved bit 2: no warp-shuffle low-qubit sweeps (A/B switch)
         c.mono = !(ab & 8);    // reserved bit 3: no monomial phases (A/B switch)
+        c.mono_tables = !(ab & 16);  // reserved bit 4: monomial phases walk on the device (A/B switch)
     }
     if (!c.phases) c.mono = false;
+    if (c.mono_tables && !std::getenv("B2SV_MONO_COST")) c.mono_gate_cost = 0.001;  // table-driven: gates are free on the device
     if (c.tile_qubits > 13 && c.amp_bytes == 16) c.tile_qubits = 13;
     if (c.tile_qubits > 14) c.tile_qubits = 14;
     if (c.tile_qubits < 3) c.tile_qubits = 3;
@@ -704,11 +715,14 @@ inline Plan make_plan(const b2sv_gate* gates, size_t n_gates, const PlanConfig& 
                     else tile_cost += gate_sweep_fraction(G[s.gates[0]]);
                 }
                 double perm_cost = 1.0 + cfg.perm_gate_cost * (double)len;
-                if (cfg.mono && alt.size() == 1 && alt[0].cls == SEG_TILE) {
+                uint64_t run_targets = 0;
+                for (size_t q = j; q < e; ++q) run_targets |= G[q].tmask;
+                if (cfg.mono && popcount64(low_mask(std::min(cfg.chunk_bits, cfg.n)) | run_targets) <= cfg.tile_qubits) {
                     // a compact run (its targets fit one tile) rides with its neighbours as a monomial phase:
-                    // what it adds to their sweep is index arithmetic, while a permutation sweep of its own
-                    // also cuts the neighbours' sweep in two
-                    tile_cost = sweep_cost(alt[0].common_ctrl) * (0.3 + cfg.mono_gate_cost * (double)len);
+                    // what it adds to their sweep is one shared-memory round trip (plus index arithmetic when
+                    // the walks run on the device), while a permutation sweep of its own also cuts the
+                    // neighbours' sweep in two
+                    tile_cost = 0.3 + cfg.mono_gate_cost * (double)len;
                     perm_cost += 0.3;
                 }
                 use_perm = perm_cost < tile_cost;

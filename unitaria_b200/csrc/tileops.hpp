@@ -8,6 +8,7 @@
 //   layout_batches       pads the program so that no phase straddles a kTileMaxOps batch boundary
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -99,6 +100,94 @@ inline TileOp make_tile_op(const Plan& plan, const PGate& g, uint64_t tile_mask,
 }
 
 constexpr int kPhaseMaxMembers = kTileMaxOps - 1; // header + members fit one staged batch
+constexpr size_t kMonoMaxTableBytes = 256 * 1024; // per table-driven phase
+
+// Host side of a table-driven monomial phase: walk every (thread, walk) index of the phase through the
+// members, once per value of the `ebits` outside qubits the members test (beyond the sweep's common
+// controls, which hold in every launched tile).  The walks run bit-sliced, 64 at a time: word b holds
+// bit b of 64 indices, an X is `word[t] ^= AND of the control words`.  Results: per walk the XOR mask
+// from source to destination index, and (fac) the product of the phase factors it collected.
+inline void mono_build_table(const TileOp* members, size_t count, int k, uint32_t tmask, uint32_t qlmask, int V, bool fac,
+                             uint64_t common, const uint8_t* epos, int ebits, std::vector<uint16_t>& masks,
+                             std::vector<double>& factors, uint32_t& identity) {
+    const uint32_t nthreads = 1u << __builtin_popcount(tmask);
+    const size_t W = (size_t)nthreads * V;
+    std::vector<uint32_t> idx0(W);
+    for (uint32_t t = 0; t < nthreads; ++t) {
+        const uint32_t tpart = mono_deposit(t, tmask);
+        uint32_t q = 0;
+        for (int v = 0; v < V; ++v) {
+            idx0[(size_t)t * V + v] = tpart | q;
+            q = mono_next_subset(q, qlmask);
+        }
+    }
+    masks.assign(W << ebits, 0);
+    if (fac) factors.assign((W << ebits) * 2, 0.0);
+    identity = 0;
+    for (uint32_t slice = 0; slice < (1u << ebits); ++slice) {
+        uint64_t have = common;  // outside bits known to be 1 in this slice
+        for (int i = 0; i < ebits; ++i)
+            if ((slice >> i) & 1) have |= 1ull << epos[i];
+        bool ident = true;
+        for (size_t w0 = 0; w0 < W; w0 += 64) {
+            const int nw = (int)std::min<size_t>(64, W - w0);
+            uint64_t word[16] = {0};
+            for (int i = 0; i < nw; ++i)
+                for (int b = 0; b < k; ++b) word[b] |= (uint64_t)((idx0[w0 + i] >> b) & 1u) << i;
+            double2 f[64];
+            for (int i = 0; i < 64; ++i) f[i] = make_double2(1.0, 0.0);
+            const uint64_t live = nw == 64 ? ~0ull : ((1ull << nw) - 1);
+            for (size_t mi = 0; mi < count; ++mi) {
+                const TileOp& op = members[mi];
+                if ((op.ext_ctrl & ~have) != 0) continue;  // an outside control is 0 in this slice
+                uint64_t cond = live;
+                for (uint32_t lc = op.lctrl; lc; lc &= lc - 1) cond &= word[__builtin_ctz(lc)];
+                if (!cond) continue;
+                if (op.op == B2SV_OP_X) {
+                    word[op.tpos] ^= cond;
+                } else if (op.op == B2SV_OP_SWAP) {
+                    const uint64_t d = (word[op.tpos] ^ word[op.tpos2]) & cond;
+                    word[op.tpos] ^= d;
+                    word[op.tpos2] ^= d;
+                } else if (op.op == B2SV_OP_PHASE) {
+                    const double2 wv = make_double2(op.m[0], op.m[1]);
+                    for (uint64_t c = cond; c; c &= c - 1) {
+                        const int i = __builtin_ctzll(c);
+                        f[i] = cmul(wv, f[i]);
+                    }
+                } else {  // DIAG1
+                    const double2 d0 = make_double2(op.m[0], op.m[1]), d1 = make_double2(op.m[2], op.m[3]);
+                    if (op.tpos == 0xFF) {
+                        const double2 d = (have & op.ext_tbit) ? d1 : d0;
+                        for (uint64_t c = cond; c; c &= c - 1) {
+                            const int i = __builtin_ctzll(c);
+                            f[i] = cmul(d, f[i]);
+                        }
+                    } else {
+                        for (uint64_t c = cond; c; c &= c - 1) {
+                            const int i = __builtin_ctzll(c);
+                            f[i] = cmul(((word[op.tpos] >> i) & 1ull) ? d1 : d0, f[i]);
+                        }
+                    }
+                }
+            }
+            for (int i = 0; i < nw; ++i) {
+                uint32_t fin = 0;
+                for (int b = 0; b < k; ++b) fin |= (uint32_t)((word[b] >> i) & 1ull) << b;
+                const uint16_t xm = (uint16_t)(fin ^ idx0[w0 + i]);
+                const size_t at = ((size_t)slice * W) + w0 + i;
+                masks[at] = xm;
+                if (xm) ident = false;
+                if (fac) {
+                    factors[2 * at] = f[i].x;
+                    factors[2 * at + 1] = f[i].y;
+                    if (!(f[i].x == 1.0 && f[i].y == 0.0)) ident = false;
+                }
+            }
+        }
+        if (ident) identity |= 1u << slice;
+    }
+}
 
 // Group the ops of one tile sweep into phases (kernels.cuh: tile_apply_phase / tile_apply_mono).
 //   register phase: maximal run of consecutive plain gates whose targets fall on at most three tile-local
@@ -107,7 +196,10 @@ constexpr int kPhaseMaxMembers = kTileMaxOps - 1; // header + members fit one st
 //                   control) at most tb+3 tile positions (tb+2 with phase factors) -- every thread walks the
 //                   few index values its amplitudes can have on those positions through the run.
 // At every position the kind that swallows more gates wins.
-inline void append_with_phases(const std::vector<TileOp>& ops, int k, bool enable, bool mono, std::vector<TileOp>& out) {
+// `common`: the sweep's common outside controls (set in every launched tile); `tables`: where table-driven
+// phases put their walk results (Plan::mux_tables; nullptr = always walk on the device).
+inline void append_with_phases(const std::vector<TileOp>& ops, int k, bool enable, bool mono, uint64_t common,
+                               std::vector<double>* tables, std::vector<TileOp>& out) {
     auto plain = [](const TileOp& o) {
         return o.op == B2SV_OP_MAT1 || o.op == B2SV_OP_DIAG1 || o.op == B2SV_OP_X || o.op == B2SV_OP_SWAP || o.op == B2SV_OP_PHASE;
     };
@@ -151,36 +243,49 @@ inline void append_with_phases(const std::vector<TileOp>& ops, int k, bool enabl
         // ---- monomial-phase candidate [i, jm)
         size_t jm = i;
         uint32_t Q = 0;      // tile positions the run reads or moves
-        bool fac = false;
+        uint64_t EX = 0;     // outside qubits the run tests beyond the sweep's common controls
+        bool fac = false, tab = false;
         bool mono_worth = false;
         const int tb = k < kMonoThreadBits ? k : kMonoThreadBits;
         auto touched = [&](const TileOp& o) { return o.lctrl | targets(o); };
+        auto outside = [&](const TileOp& o) { return (o.ext_ctrl & ~common) | o.ext_tbit; };
         auto q_fits = [&](uint32_t q, bool f) {
             const int extra = __builtin_popcount(q) - tb;  // Q bits that must become loop bits: V = 2^extra walks per thread
             return extra <= (f ? 2 : 3) && (extra <= 0 || extra <= k - tb);
         };
+        auto tab_fits = [&](uint32_t q, bool f, uint64_t ex) {  // can the walks be done on the host?
+            if (!tables || k < kMonoThreadBits || k > 16 || popcount64(ex) > kMonoMaxEbits) return false;
+            const int extra = std::max(0, __builtin_popcount(q) - tb);
+            const size_t walks = ((size_t)1 << (tb + extra)) << popcount64(ex);
+            return walks * (f ? 18 : 2) <= kMonoMaxTableBytes;
+        };
         if (mono && monomial(ops[i])) {
             Q = touched(ops[i]);
+            EX = outside(ops[i]);
             fac = !(ops[i].op == B2SV_OP_X || ops[i].op == B2SV_OP_SWAP);
+            tab = tab_fits(Q, fac, EX);
             double separate = alone_cost(ops[i]);
             jm = i + 1;
-            while (q_fits(Q, fac) && jm < ops.size() && monomial(ops[jm]) && (int)(jm - i) < kPhaseMaxMembers) {
+            // a table-driven phase has no members on the device, so it may be as long as the run
+            while (q_fits(Q, fac) && jm < ops.size() && monomial(ops[jm]) && (tab ? jm - i < 60000 : (int)(jm - i) < kPhaseMaxMembers)) {
                 const uint32_t Q2 = Q | touched(ops[jm]);
+                const uint64_t EX2 = EX | outside(ops[jm]);
                 const bool fac2 = fac || !(ops[jm].op == B2SV_OP_X || ops[jm].op == B2SV_OP_SWAP);
                 if (!q_fits(Q2, fac2)) break;
+                if (tab && !tab_fits(Q2, fac2, EX2)) break;  // close the table-driven phase here, start another one
                 Q = Q2;
+                EX = EX2;
                 fac = fac2;
                 separate += alone_cost(ops[jm]);
                 ++jm;
             }
-            // one round trip of the whole tile + the index walks (~0.04 pass per gate)
-            const double mono_cost = 1.0 + 0.04 * (double)(jm - i) + 0.08;
+            // one round trip of the whole tile, plus (device walks only) ~0.1 pass of index arithmetic per gate
+            const double mono_cost = 1.0 + (tab ? 0.0 : 0.1 * (double)(jm - i)) + 0.08;
             mono_worth = q_fits(Q, fac) && jm - i >= 2 && separate > mono_cost;
         }
         if (mono_worth && jm >= jr) {
             TileOp h{};
             h.op = kOpMono;
-            h.mono.count = (uint16_t)(jm - i);
             h.mono.fac = fac ? 1 : 0;
             h.mono.lb = (uint8_t)(k - tb);
             // thread bits: Q positions first (ascending), filled up with the lowest other positions; the lowest
@@ -195,8 +300,32 @@ inline void append_with_phases(const std::vector<TileOp>& ops, int k, bool enabl
             h.mono.qlmask = Q & ~tmask & all;       // the Q positions that did not fit: 2^vbits walks per thread
             h.mono.nmask = ~Q & ~tmask & all;
             h.mono.vbits = (uint8_t)__builtin_popcount(h.mono.qlmask);
-            out.push_back(h);
-            for (size_t q = i; q < jm; ++q) out.push_back(ops[q]);
+            if (tab) {
+                h.mono.tab = 1;
+                h.mono.count = 0;
+                int ne = 0;
+                for (int q = 0; q < 64; ++q)
+                    if ((EX >> q) & 1) h.mono.epos[ne++] = (uint8_t)q;
+                h.mono.ebits = (uint8_t)ne;
+                std::vector<uint16_t> masks;
+                std::vector<double> factors;
+                mono_build_table(&ops[i], jm - i, k, tmask, h.mono.qlmask, 1 << h.mono.vbits, fac, common, h.mono.epos, ne, masks,
+                                 factors, h.mono.identity);
+                while (tables->size() % 2) tables->push_back(0.0);  // offsets count 16-byte units
+                h.mono.mask_off = tables->size() / 2;
+                const size_t mask_doubles = (masks.size() * sizeof(uint16_t) + 15) / 16 * 2;
+                tables->resize(tables->size() + mask_doubles, 0.0);
+                std::memcpy(reinterpret_cast<char*>(tables->data()) + h.mono.mask_off * 16, masks.data(), masks.size() * sizeof(uint16_t));
+                if (fac) {
+                    h.mono.fac_off = tables->size() / 2;
+                    tables->insert(tables->end(), factors.begin(), factors.end());
+                }
+                out.push_back(h);
+            } else {
+                h.mono.count = (uint16_t)(jm - i);
+                out.push_back(h);
+                for (size_t q = i; q < jm; ++q) out.push_back(ops[q]);
+            }
             i = jm;
             continue;
         }
@@ -251,14 +380,16 @@ inline void layout_batches(const std::vector<TileOp>& in, std::vector<TileOp>& o
 }
 
 // The complete op program of one SEG_TILE / SEG_LOW6 segment, appended to `out`.
-inline void build_segment_ops(const Plan& plan, const Segment& seg, const PlanConfig& cfg, std::vector<TileOp>& out) {
+// Table-driven monomial phases append their walk results to plan.mux_tables.
+inline void build_segment_ops(Plan& plan, const Segment& seg, const PlanConfig& cfg, std::vector<TileOp>& out) {
     ExpandArgs ex;
     fill_expand(ex, seg.tile_mask);
     std::vector<TileOp> seg_ops, grouped;
     seg_ops.reserve(seg.gates.size());
     for (int gi : seg.gates) seg_ops.push_back(make_tile_op(plan, plan.gates[gi], seg.tile_mask, ex));
     const bool tile = seg.cls == SEG_TILE;
-    append_with_phases(seg_ops, ex.m, cfg.phases && tile, cfg.mono && tile, grouped);
+    append_with_phases(seg_ops, ex.m, cfg.phases && tile, cfg.mono && tile, seg.common_ctrl, cfg.mono_tables ? &plan.mux_tables : nullptr,
+                       grouped);
     if (tile) layout_batches(grouped, out);
     else out.insert(out.end(), grouped.begin(), grouped.end());
 }
