@@ -78,8 +78,7 @@ typedef struct b2sv_plan_opts {
     int32_t jit;          /* permutation runs: 0 = specialise with NVRTC in the background after first use
                              (default), 1 = never (generic kernel only), 2 = compile synchronously       */
     int32_t reserved;     /* A/B switches: bit 0 = no multiplexor / block fusion, bit 1 = no register phases,
-                             bit 2 = no warp-shuffle low-qubit sweeps, bit 3 = no monomial phases,
-                             bit 4 = monomial phases walk the indices on the device instead of the host */
+                             bit 2 = no warp-shuffle low-qubit sweeps, bit 3 = no monomial phases */
 } b2sv_plan_opts;
 
 /* Subspace program (restates Subspace.test_basis / enumerate_basis,

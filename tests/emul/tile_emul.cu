@@ -3,10 +3,10 @@
 // Host-only interpreter of the tile-op programs that unitaria_b200/csrc/tileops.hpp builds for the
 // CUDA kernels of kernels.cuh.  The GPU is scarce while developing; this lets the CPU test-suite check
 // everything the host prepares for a tile sweep -- tile-local positions, fixed-position enumeration,
-// register-phase and monomial-phase headers, round masks, batch padding -- by running the very same
-// TileOp arrays over a small state and comparing with the CPU oracle.  It includes the product's
-// planner and op builders unchanged; only the interpretation below is written a second time (the member
-// loop of a monomial phase, mono_run_members, is shared with the device code).
+// register-phase and monomial-phase headers with their host-built walk tables, batch padding -- by
+// running the very same TileOp arrays and tables over a small state and comparing with the CPU oracle.
+// It includes the product's planner and op builders unchanged; only the interpretation below is written
+// a second time.
 //
 // Built by tests/test_tile_emul.py with nvcc (host code only; no kernel is launched).
 #include <complex>
@@ -60,7 +60,7 @@ void apply_plain(std::vector<cplx>& psi, int n, const PGate& g) {
 
 struct Counters {
     int64_t tile = 0, perm = 0, gate1q = 0, low6 = 0, mono_phases = 0, mono_members = 0, reg_phases = 0, reg_members = 0, max_ops = 0,
-            nops = 0, mono_rounds_max = 0, mono_tab = 0, mono_tab_phases_run = 0;
+            nops = 0, mono_rounds_max = 0, mono_gates = 0;
 };
 
 // one op (not a header) on a tile held as tile[l], l = tile-local index
@@ -184,57 +184,39 @@ void run_reg_phase(std::vector<cplx>& tile, const TileOp& hdr, const TileOp* ops
     }
 }
 
-// mirrors tile_apply_mono / tile_mono_rounds: per-thread index walks, rounds of kMonoElems amplitudes per
+// mirrors tile_apply_mono: table look-up of the per-thread walk results, rounds of kMonoElems amplitudes per
 // thread, all reads of a round before its writes
-template <int V>
-int run_mono_rounds(std::vector<cplx>& tile, const TileOp& hdr, const TileOp* ops, int k, uint64_t base, const Plan& plan, Counters& c) {
+int run_mono_phase(std::vector<cplx>& tile, const TileOp& hdr, int k, uint64_t base, uint32_t slice, const Plan& plan, Counters& c) {
     const int E = kMonoElems;
+    const int V = hdr.mono.fac ? kMonoVFac : kMonoV;
     const uint32_t tmask = hdr.mono.tmask, qlmask = hdr.mono.qlmask, nmask = hdr.mono.nmask;
     const int tb = __builtin_popcount(tmask), lb = hdr.mono.lb, vbits = hdr.mono.vbits;
-    if (tb + lb != k || (1 << vbits) != V || vbits > lb || tb > kMonoThreadBits) return -1;
-    if (hdr.mono.fac ? V > kMonoMaxVFac : V > kMonoMaxV) return -4;
+    if (tb + lb != k || (1 << vbits) != V || lb < 3 || tb != kMonoThreadBits || hdr.mono.count != 0) return -1;
+    if (hdr.mono.ebits > kMonoMaxEbits || slice >= (1u << hdr.mono.ebits)) return -9;
     // thread, walk and untouched loop positions partition the tile positions
     if ((tmask | qlmask | nmask) != (1u << k) - 1u || (tmask & qlmask) || (tmask & nmask) || (qlmask & nmask)) return -5;
     if (__builtin_popcount(qlmask) != vbits) return -5;
     const uint32_t n_threads = 1u << tb, per_thread = 1u << lb;
-    const uint32_t rounds = per_thread > (uint32_t)E ? per_thread / E : 1;
+    const uint32_t rounds = per_thread / E;
     if ((int64_t)rounds > c.mono_rounds_max) c.mono_rounds_max = rounds;
+    const double2* tables = reinterpret_cast<const double2*>(plan.mux_tables.data());
     std::vector<uint32_t> qsrc((size_t)n_threads * V), qx((size_t)n_threads * V);
-    std::vector<cplx> fac((size_t)n_threads * V);
+    std::vector<cplx> fac((size_t)n_threads * V, cplx(1.0, 0.0));
     for (uint32_t t = 0; t < n_threads; ++t) {
-        uint32_t idx[V];
-        double2 f[V];
         const uint32_t tpart = mono_deposit(t, tmask);
+        const size_t first = (((size_t)slice << tb) + t) * V;
+        if ((hdr.mono.mask_off * 16 + (first + V) * 2) > plan.mux_tables.size() * 8) return -11;
+        const uint16_t* xm = reinterpret_cast<const uint16_t*>(tables + hdr.mono.mask_off) + first;
         uint32_t q = 0;
         for (int v = 0; v < V; ++v) {
-            idx[v] = qsrc[(size_t)t * V + v] = tpart | q;
-            f[v] = make_double2(1.0, 0.0);
+            qsrc[(size_t)t * V + v] = tpart | q;
             q = mono_next_subset(q, qlmask);
-        }
-        if (hdr.mono.tab) {
-            // table-driven: the host did the walks (tileops.hpp: mono_build_table); index exactly as the device does
-            if (hdr.mono.count != 0 || hdr.mono.ebits > kMonoMaxEbits) return -9;
-            uint32_t slice = 0;
-            for (int i = 0; i < hdr.mono.ebits; ++i) slice |= (uint32_t)((base >> hdr.mono.epos[i]) & 1ull) << i;
-            const size_t first = (((size_t)slice << tb) + t) * V;
-            const double2* tables = reinterpret_cast<const double2*>(plan.mux_tables.data());
-            const uint16_t* xm = reinterpret_cast<const uint16_t*>(tables + hdr.mono.mask_off) + first;
-            if ((hdr.mono.mask_off * 2 + ((first + V) * 2 + 7) / 8) > plan.mux_tables.size()) return -11;
-            for (int v = 0; v < V; ++v) {
-                qx[(size_t)t * V + v] = xm[v];
-                fac[(size_t)t * V + v] = cplx(1.0, 0.0);
-                if (hdr.mono.fac) {
-                    const double2 fv = (tables + hdr.mono.fac_off + first)[v];
-                    fac[(size_t)t * V + v] = cplx(fv.x, fv.y);
-                }
+            qx[(size_t)t * V + v] = xm[v];
+            if (hdr.mono.fac) {
+                if ((hdr.mono.fac_off + first + V) * 2 > plan.mux_tables.size()) return -12;
+                const double2 fv = (tables + hdr.mono.fac_off + first)[v];
+                fac[(size_t)t * V + v] = cplx(fv.x, fv.y);
             }
-            continue;
-        }
-        if (hdr.mono.fac) mono_run_members<V, true>(ops, hdr.mono.count, base, idx, f);
-        else mono_run_members<V, false>(ops, hdr.mono.count, base, idx, f);
-        for (int v = 0; v < V; ++v) {
-            qx[(size_t)t * V + v] = idx[v] ^ qsrc[(size_t)t * V + v];
-            fac[(size_t)t * V + v] = cplx(f[v].x, f[v].y);
         }
     }
     std::vector<char> written(tile.size(), 0);
@@ -249,12 +231,10 @@ int run_mono_rounds(std::vector<cplx>& tile, const TileOp& hdr, const TileOp* op
             for (int e = 0; e < E; ++e) {
                 const int v = e & (V - 1);
                 const uint32_t src = qsrc[(size_t)t * V + v] | ncur[t];
-                if (j0 + e < per_thread) {
-                    if (src >= tile.size() || in_round[src]) return -6;  // every amplitude is read exactly once
-                    in_round[src] = 1;
-                    dst.push_back(src ^ qx[(size_t)t * V + v]);
-                    val.push_back(hdr.mono.fac ? fac[(size_t)t * V + v] * tile[src] : tile[src]);
-                }
+                if (src >= tile.size() || in_round[src]) return -6;  // every amplitude is read exactly once
+                in_round[src] = 1;
+                dst.push_back(src ^ qx[(size_t)t * V + v]);
+                val.push_back(hdr.mono.fac ? fac[(size_t)t * V + v] * tile[src] : tile[src]);
                 if (v == V - 1) ncur[t] = mono_next_subset(ncur[t], nmask);
             }
         for (size_t q = 0; q < dst.size(); ++q) {
@@ -269,37 +249,24 @@ int run_mono_rounds(std::vector<cplx>& tile, const TileOp& hdr, const TileOp* op
     return 0;
 }
 
-int run_mono_phase(std::vector<cplx>& tile, const TileOp& hdr, const TileOp* ops, int k, uint64_t base, const Plan& plan, Counters& c) {
-    switch (hdr.mono.vbits) {
-        case 0: return run_mono_rounds<1>(tile, hdr, ops, k, base, plan, c);
-        case 1: return run_mono_rounds<2>(tile, hdr, ops, k, base, plan, c);
-        case 2: return run_mono_rounds<4>(tile, hdr, ops, k, base, plan, c);
-        case 3: return run_mono_rounds<8>(tile, hdr, ops, k, base, plan, c);
-        default: return -8;
-    }
-}
-
 int run_program(std::vector<cplx>& tile, const TileOp* ops, int n_ops, int k, uint64_t base, const Plan& plan, Counters& c) {
     for (int b0 = 0; b0 < n_ops; b0 += kTileMaxOps) {
         const int nb = n_ops - b0 < kTileMaxOps ? n_ops - b0 : kTileMaxOps;
         const TileOp* s_ops = ops + b0;
         for (int o = 0; o < nb; ++o) {
             const TileOp& op = s_ops[o];
-            if (op.op == kOpPhase || op.op == kOpMono) {
-                if (o + op.ph.count >= nb + (op.ph.count == 0 ? 1 : 0)) return -10;  // a phase straddles a batch boundary
+            if (op.op == kOpMono) {
+                uint32_t slice = 0;
+                for (int i = 0; i < op.mono.ebits; ++i) slice |= (uint32_t)((base >> op.mono.epos[i]) & 1ull) << i;
+                if (!((op.mono.identity >> slice) & 1u))
+                    if (int rc = run_mono_phase(tile, op, k, base, slice, plan, c)) return rc;
+                continue;
+            }
+            if (op.op == kOpPhase) {
+                if (o + op.ph.count >= nb) return -10;  // a phase straddles a batch boundary
                 bool any = false;
-                if (op.op == kOpMono && op.mono.tab) {
-                    uint32_t slice = 0;
-                    for (int i = 0; i < op.mono.ebits; ++i) slice |= (uint32_t)((base >> op.mono.epos[i]) & 1ull) << i;
-                    any = !((op.mono.identity >> slice) & 1u);
-                    c.mono_tab_phases_run++;
-                } else {
-                    for (int mi = 1; mi <= op.ph.count; ++mi) any |= (base & s_ops[o + mi].ext_ctrl) == s_ops[o + mi].ext_ctrl;
-                }
-                if (any) {
-                    if (op.op == kOpPhase) run_reg_phase(tile, op, s_ops + o + 1, k, base);
-                    else if (int rc = run_mono_phase(tile, op, s_ops + o + 1, k, base, plan, c)) return rc;
-                }
+                for (int mi = 1; mi <= op.ph.count; ++mi) any |= (base & s_ops[o + mi].ext_ctrl) == s_ops[o + mi].ext_ctrl;
+                if (any) run_reg_phase(tile, op, s_ops + o + 1, k, base);
                 o += op.ph.count;
                 continue;
             }
@@ -340,7 +307,6 @@ extern "C" int emul_apply(int n, int dtype, const b2sv_gate* gates, size_t n_gat
         for (size_t o = 0; o < ops.size(); ++o) {
             if (ops[o].op == kOpMono) {
                 c.mono_phases++;
-                c.mono_tab += ops[o].mono.tab;
                 c.mono_members += ops[o].ph.count;
             } else if (ops[o].op == kOpPhase) {
                 c.reg_phases++;
@@ -375,7 +341,7 @@ extern "C" int emul_apply(int n, int dtype, const b2sv_gate* gates, size_t n_gat
         amps[2 * i + 1] = v.imag();
     }
     if (info) {
-        const int64_t out[12] = {c.tile, c.perm, c.gate1q, c.low6, c.mono_phases, c.mono_members, c.reg_phases, c.reg_members, c.max_ops, c.nops, c.mono_rounds_max, c.mono_tab};
+        const int64_t out[12] = {c.tile, c.perm, c.gate1q, c.low6, c.mono_phases, c.mono_members, c.reg_phases, c.reg_members, c.max_ops, c.nops, c.mono_rounds_max, c.mono_gates};
         std::memcpy(info, out, sizeof(out));
     }
     return 0;

@@ -24,7 +24,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "emul", "tile_emul.cu")
 LIB = os.path.join(HERE, "emul", "libtile_emul.so")
 CSRC = os.path.join(os.path.dirname(HERE), "unitaria_b200", "csrc")
-INFO = ["tile", "perm", "gate1q", "low6", "mono_phases", "mono_members", "reg_phases", "reg_members", "max_ops", "nops", "mono_rounds_max", "mono_tab"]
+INFO = ["tile", "perm", "gate1q", "low6", "mono_phases", "mono_members", "reg_phases", "reg_members", "max_ops", "nops", "mono_rounds_max", "mono_gates"]
 
 
 def _build():
@@ -66,21 +66,19 @@ def perm_heavy_circuit(n, m, rng, max_controls=4):
     return random_circuit(n, m, rng, kinds=kinds, max_controls=max_controls)
 
 
-@pytest.mark.parametrize("n,seed,tile_qubits", [(7, 0, 5), (9, 1, 6), (12, 2, 8), (14, 3, 0), (15, 4, 12), (15, 5, 13)])
-@pytest.mark.parametrize("mono", ["tables", "walks", "off"])
+@pytest.mark.parametrize("n,seed,tile_qubits", [(7, 0, 5), (9, 1, 6), (12, 2, 8), (13, 6, 11), (14, 3, 0), (15, 4, 12), (15, 5, 13)])
+@pytest.mark.parametrize("mono", [True, False])
 def test_random_permutation_heavy(emul, n, seed, tile_qubits, mono):
     rng = np.random.default_rng(seed)
     circuit = perm_heavy_circuit(n, 600, rng)
     psi0 = random_state(n, rng)
     want = np_oracle.simulate_gates([g for g in circuit.gates if g.name != "I"], n, psi0)
-    got, info = emul(circuit.gates, n, psi0, tile_qubits=tile_qubits, mono=mono != "off", mono_tables=mono == "tables", perm_runs=False)
+    got, info = emul(circuit.gates, n, psi0, tile_qubits=tile_qubits, mono=mono, perm_runs=False)
     assert np.abs(got - want).max() < 1e-12
     k = tile_qubits or 12
-    if mono == "tables" and k >= 8:
-        assert info["mono_tab"] > 0, info
-    elif mono == "walks":
-        assert info["mono_phases"] > 0 and info["mono_tab"] == 0 and info["mono_members"] >= 2 * info["mono_phases"]
-    elif mono == "off":
+    if mono and k >= 11:  # a thread needs at least eight amplitudes of its own
+        assert info["mono_phases"] > 0, info
+    else:
         assert info["mono_phases"] == 0
 
 
@@ -107,14 +105,16 @@ def test_long_runs_are_batched_and_rounds_are_used(emul):
     psi0 = random_state(n, rng)
     want = np_oracle.simulate_gates(keep, n, psi0)
     for dtype, rounds in ((cabi.B2SV_C128, 2), (cabi.B2SV_C64, 4)):
-        got, info = emul(keep, n, psi0, dtype=dtype, perm_runs=False, mono_tables=False)
-        assert np.abs(got - want).max() < 1e-12
-        assert info["max_ops"] > 112, info
-        assert info["mono_rounds_max"] == rounds, info
-        # table-driven: the same run is a handful of headers and no members
+        # a handful of headers: the walks were done on the host
         got, info = emul(keep, n, psi0, dtype=dtype, perm_runs=False)
         assert np.abs(got - want).max() < 1e-12
-        assert info["mono_tab"] > 0 and info["max_ops"] < 112 and info["mono_members"] == 0, info
+        assert info["mono_phases"] > 0 and info["max_ops"] < 112 and info["mono_rounds_max"] == rounds, info
+    # dense gates on ten qubits cannot be grouped like that: one sweep, more ops than one staged batch holds
+    dense = [g for g in random_circuit(n, 700, rng, kinds=["Ry", "H", "Rz", "CNOT"], max_controls=1).gates if all(t < 10 for t in g.target)]
+    want = np_oracle.simulate_gates(dense, n, psi0)
+    got, info = emul(dense, n, psi0, perm_runs=False, mux=False)
+    assert np.abs(got - want).max() < 1e-12
+    assert info["max_ops"] > 112, info
 
 
 @pytest.mark.parametrize("name", ["bpx_L3", "bpx_L4", "pinv_bpx_L2", "laplace_n12", "gaussian_s3_t8", "cfg5_bits5", "qsvt_inc2_cheb", "sinv_rhs_bpx_L2"])

@@ -377,7 +377,8 @@ int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, co
     a.k = a.tile_ex.m;
     int lc = 0;
     while (lc < a.k && a.tile_ex.pos[lc] == lc) ++lc;  // contiguous low run of the tile
-    if (lc > cfg.chunk_bits + 3) lc = cfg.chunk_bits + 3;  // keep enough chunks in flight
+    const int lc_cap = sv->amp_bytes == 16 ? 10 : 11;  // at most 16 KiB per copy: keep enough chunks in flight
+    if (lc > lc_cap) lc = lc_cap;
     if (((size_t)sv->amp_bytes << lc) < 16) return fail(B2SV_EINVAL, "tile chunk smaller than 16 bytes");
     a.lc = lc;
     a.n_ops = n_ops;
@@ -912,7 +913,7 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
             key = (key ^ w[i]) * 1099511628211ull;
             key2 += w[i] * (2 * i + 1);
         }
-        const uint64_t o = (uint64_t)cfg.fuse | ((uint64_t)cfg.perm_runs << 1) | ((uint64_t)cfg.mux << 2) | ((uint64_t)cfg.phases << 3) | ((uint64_t)cfg.low6 << 4) | ((uint64_t)cfg.mono << 5) | ((uint64_t)cfg.mono_tables << 6) |
+        const uint64_t o = (uint64_t)cfg.fuse | ((uint64_t)cfg.perm_runs << 1) | ((uint64_t)cfg.mux << 2) | ((uint64_t)cfg.phases << 3) | ((uint64_t)cfg.low6 << 4) | ((uint64_t)cfg.mono << 5) |
                            ((uint64_t)cfg.tile_qubits << 8) | ((uint64_t)cfg.lookahead << 16) | ((uint64_t)sv->scratch_failed << 40);
         key = (key ^ o) * 1099511628211ull;
     }

@@ -144,17 +144,16 @@ struct __align__(16) TileOp {
             uint16_t count;
             uint8_t rpos[3];       // the three tile-local positions held in registers (ascending)
         } ph;
-        struct {               // op == kOpMono: header of a monomial phase
-            uint16_t count;        // member ops that follow (same place as ph.count); 0 when the phase is table-driven
+        struct {               // op == kOpMono: a monomial phase (no member ops follow: count == 0)
+            uint16_t count;        // 0 (same place as ph.count)
             uint8_t lb;            // a thread owns 2^lb amplitudes (tile-local index = thread bits + loop bits)
-            uint8_t vbits;         // 2^vbits index walks per thread = popcount(qlmask)
+            uint8_t vbits;         // 2^vbits index walks per thread: 3 (pure permutation) or 2 (with factors)
             uint8_t fac;           // 1: the run has PHASE / DIAG1 members (amplitudes pick up factors)
-            uint8_t tab;           // 1: the walks were done on the host, their results are in TileArgs::tables
-            uint8_t ebits;         // table-driven: qubits outside the tile that members test (beyond the sweep's
-            uint8_t pad;           //   common controls): one table slice per value of those bits
+            uint8_t ebits;         // qubits outside the tile that members test (beyond the sweep's common
+            uint8_t pad[2];        //   controls): one table slice per value of those bits
             uint32_t tmask;        // tile-local positions that take the thread number (ascending)
-            uint32_t qlmask;       // loop positions the run touches (Q bits that did not fit the thread number)
-            uint32_t nmask;        // loop positions the run does not touch
+            uint32_t qlmask;       // loop positions that number a thread's walks (all touched loop positions are here)
+            uint32_t nmask;        // the other loop positions (not touched by the run)
             uint8_t epos[4];       // global qubit numbers of the `ebits` outside bits
             uint32_t identity;     // bit p set: slice p moves nothing and multiplies nothing -- skip the phase
             uint64_t mask_off;     // first uint16 XOR mask, counted in double2 units from the start of the tables
@@ -169,7 +168,7 @@ constexpr int kOpMono = 8;   // header of a monomial phase (index moves + phase 
 constexpr int kOpNop = 9;    // padding in front of a batch boundary of a long op list
 constexpr int kMonoElems = 8;              // amplitudes a thread carries through one round of a monomial phase
 constexpr int kMonoThreadBits = 8;         // log2(kThreads)
-constexpr int kMonoMaxV = 8, kMonoMaxVFac = 4;  // index walks per thread (pure permutation / with factors)
+constexpr int kMonoV = 8, kMonoVFac = 4;   // index walks per thread (pure permutation / with factors)
 constexpr int kMonoMaxEbits = 4;           // table-driven phases: at most 16 slices
 static_assert(sizeof(TileOp) == 96, "TileOp layout");
 
@@ -581,67 +580,18 @@ __device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, con
 
 // Monomial phase: a run of consecutive X / SWAP / PHASE / DIAG1 gates (any controls) maps every basis
 // state of the tile to ONE basis state times a factor, so the whole run is "index arithmetic + one
-// move".  Only the tile bits the run touches (targets and tile-local controls: the Q bits) matter for
-// where an amplitude goes, so the thread <-> amplitude map puts the Q bits into the thread number first:
-// a thread then owns 2^lb amplitudes that share at most V = 2^vbits different Q values, walks just those
-// V INDICES through the gates in registers (an X is `idx ^= bit` under a mask test, a phase gate
-// multiplies the walk's factor), and moves all its amplitudes by the resulting XOR masks -- in rounds of
-// kMonoElems amplitudes per thread with one barrier between the reads and the writes of a round (a
-// round holds every Q value of a set of non-Q values, so it is closed under the run).
-// One shared-memory round trip for the whole run: the ripple-carry arithmetic of circuits/arithmetic.py
-// under LCU / BlockDiagonal selector controls is 50-80 such gates in a row, which used to be one
-// shared-memory pass each.  X and SWAP stay exact data movement.
-template <int V, bool FAC>
-__host__ __device__ __forceinline__ void mono_run_members(const TileOp* ops, int count, uint64_t base, uint32_t (&idx)[V],
-                                                          double2 (&f)[V]) {
-    // the first 16 bytes of a TileOp hold {op, tpos, tpos2, nfix, lctrl, ...}; the next gate's words are
-    // fetched while the current one is applied (the loop is a chain of dependent shared-memory loads otherwise)
-    uint4 hn = *reinterpret_cast<const uint4*>(&ops[0]);
-    uint64_t extn = ops[0].ext_ctrl;
-    for (int mi = 0; mi < count; ++mi) {
-        const uint4 h = hn;
-        const uint64_t ext = extn;
-        if (mi + 1 < count) {
-            hn = *reinterpret_cast<const uint4*>(&ops[mi + 1]);
-            extn = ops[mi + 1].ext_ctrl;
-        }
-        if ((base & ext) != ext) continue;  // CTA-uniform
-        const uint32_t lc = h.y;
-        const int kind = (int)(h.x & 0xFFu), pa = (int)((h.x >> 8) & 0xFFu), pb = (int)((h.x >> 16) & 0xFFu);
-        if (kind == B2SV_OP_X) {
-            const uint32_t bt = 1u << pa;
-#pragma unroll
-            for (int e = 0; e < V; ++e) idx[e] ^= ((~idx[e] & lc) == 0u) ? bt : 0u;
-        } else if (kind == B2SV_OP_SWAP) {
-            const uint32_t both = (1u << pa) | (1u << pb);
-#pragma unroll
-            for (int e = 0; e < V; ++e) {
-                const bool differ = ((idx[e] >> pa) ^ (idx[e] >> pb)) & 1u;
-                idx[e] ^= (differ && (~idx[e] & lc) == 0u) ? both : 0u;
-            }
-        } else if (FAC && kind == B2SV_OP_PHASE) {
-            const TileOp& op = ops[mi];
-            const double2 w = make_double2(op.m[0], op.m[1]);
-#pragma unroll
-            for (int e = 0; e < V; ++e)
-                if ((~idx[e] & lc) == 0u) f[e] = cmul(w, f[e]);
-        } else if (FAC && kind == B2SV_OP_DIAG1) {
-            const TileOp& op = ops[mi];
-            const double2 d0 = make_double2(op.m[0], op.m[1]), d1 = make_double2(op.m[2], op.m[3]);
-            if (pa == 0xFF) {  // target outside the tile: one CTA-uniform factor
-                const double2 d = (base & op.ext_tbit) ? d1 : d0;
-#pragma unroll
-                for (int e = 0; e < V; ++e)
-                    if ((~idx[e] & lc) == 0u) f[e] = cmul(d, f[e]);
-            } else {
-#pragma unroll
-                for (int e = 0; e < V; ++e)
-                    if ((~idx[e] & lc) == 0u) f[e] = cmul(((idx[e] >> pa) & 1u) ? d1 : d0, f[e]);
-            }
-        }
-    }
-}
-
+// move" -- and the index arithmetic does not depend on the amplitudes, so the HOST does it once per plan
+// (tileops.hpp: mono_build_table, bit-sliced) and the device only moves data.  Only the tile bits the run
+// touches (targets and tile-local controls: the Q bits) decide where an amplitude goes, so the thread <->
+// amplitude map puts the Q bits into the thread number first: a thread then owns 2^lb amplitudes that
+// share at most V different Q values ("walks"), fetches the V results -- the XOR mask from source to
+// destination index and, if the run has phase gates, the accumulated factor -- and moves its amplitudes
+// in rounds of kMonoElems with one barrier between the reads and the writes of a round (a round holds
+// every Q value of a set of non-Q values, so it is closed under the run).
+// One shared-memory round trip for a run of ANY length: the ripple-carry arithmetic of
+// circuits/arithmetic.py under LCU / BlockDiagonal selector controls is 50-150 such gates in a row, which
+// used to be one shared-memory pass each.  X and SWAP stay exact data movement.
+//
 // scatter the low bits of x to the set positions of mask (ascending)
 __host__ __device__ __forceinline__ uint32_t mono_deposit(uint32_t x, uint32_t mask) {
     uint32_t out = 0;
@@ -658,88 +608,70 @@ __host__ __device__ __forceinline__ uint32_t mono_deposit(uint32_t x, uint32_t m
 __host__ __device__ __forceinline__ uint32_t mono_next_subset(uint32_t cur, uint32_t mask) { return ((cur | ~mask) + 1u) & mask; }
 
 template <typename A, int V, bool FAC, typename TV>
-__device__ __forceinline__ void tile_mono_rounds(TV tile, const TileOp& hdr, const TileOp* ops, uint64_t base,
-                                                 const double2* __restrict__ tables) {
+__device__ __forceinline__ void tile_apply_mono(TV tile, const TileOp& hdr, uint64_t base, uint32_t slice,
+                                                const double2* __restrict__ tables) {
     constexpr int E = kMonoElems;
+    static_assert(V == 8 || V == 4, "walks per thread");
     const uint32_t tmask = hdr.mono.tmask, qlmask = hdr.mono.qlmask, nmask = hdr.mono.nmask;
     const uint32_t per_thread = 1u << hdr.mono.lb;
     const int tbits = __popc(tmask);
-    const uint32_t tpart = mono_deposit(threadIdx.x, tmask);
-    const bool active = threadIdx.x < (1u << tbits);
-    uint32_t qsrc[V], qidx[V];  // source index of each walk; afterwards the XOR mask to its destination
-    double2 fac[V];
-    {
-        uint32_t q = 0;
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            qsrc[v] = qidx[v] = tpart | q;
-            fac[v] = make_double2(1.0, 0.0);
-            q = mono_next_subset(q, qlmask);
-        }
-    }
-    if (hdr.mono.tab) {
-        // the host walked every (thread, walk) index through the run, once per value of the outside bits the
-        // members test: fetch this thread's results
-        uint32_t slice = 0;
-        for (int i = 0; i < hdr.mono.ebits; ++i) slice |= (uint32_t)((base >> hdr.mono.epos[i]) & 1ull) << i;
-        const size_t first = (((size_t)slice << tbits) + (active ? threadIdx.x : 0u)) * V;
-        const uint16_t* __restrict__ xm = reinterpret_cast<const uint16_t*>(tables + hdr.mono.mask_off) + first;
-#pragma unroll
-        for (int v = 0; v < V; ++v) qidx[v] = __ldg(xm + v);
-        if (FAC) {
-            const double2* __restrict__ fm = tables + hdr.mono.fac_off + first;
-#pragma unroll
-            for (int v = 0; v < V; ++v) fac[v] = __ldg(fm + v);
-        }
+    // (a CTA with more than 2^tbits threads -- the pipelined kernel -- has the upper half mirror the lower half:
+    // same reads, same writes of the same values)
+    const uint32_t t = threadIdx.x & ((1u << tbits) - 1u);
+    const uint32_t tpart = mono_deposit(t, tmask);
+    // this thread's walk results: entry (slice, thread, walk)
+    const size_t first = (((size_t)slice << tbits) + t) * V;
+    uint32_t xw[V / 2];  // V uint16 XOR masks, two per word
+    if (V == 8) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(tables + hdr.mono.mask_off) + first));
+        xw[0] = w.x;
+        xw[1] = w.y;
+        xw[V / 2 - 2] = w.z;
+        xw[V / 2 - 1] = w.w;
     } else {
-        // walk this thread's V index values through the run
-        mono_run_members<V, FAC>(ops, hdr.mono.count, base, qidx, fac);
-#pragma unroll
-        for (int v = 0; v < V; ++v) qidx[v] ^= qsrc[v];
+        const uint2 w = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(tables + hdr.mono.mask_off) + first));
+        xw[0] = w.x;
+        xw[1] = w.y;
     }
-    uint32_t ncur = 0;  // the untouched loop bits of the current amplitudes
+    double2 fac[FAC ? V : 1];
+    if (FAC) {
+        const double2* __restrict__ fm = tables + hdr.mono.fac_off + first;
+#pragma unroll
+        for (int v = 0; v < V; ++v) fac[v] = __ldg(fm + v);
+    }
+    // amplitude e of a round belongs to walk e mod V (E is a multiple of V); `q` runs through the walk bits,
+    // `ncur` through the untouched loop bits.  The destinations are recomputed after the barrier rather
+    // than kept in registers.
+    uint32_t ncur = 0;
 #pragma unroll 1
     for (uint32_t j0 = 0; j0 < per_thread; j0 += E) {
-        uint32_t dst[E];
         double2 val[E];
+        {
+            uint32_t q = 0, nn = ncur;
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            constexpr int VM = V - 1;
-            const int v = e & VM;  // E is a multiple of V: consecutive amplitudes cycle through the walks
-            const uint32_t src = qsrc[v] | ncur;
-            dst[e] = src ^ qidx[v];
-            if (active && j0 + e < per_thread) {
-                val[e] = to_c128(tile[src]);
+            for (int e = 0; e < E; ++e) {
+                constexpr int VM = V - 1;
+                const int v = e & VM;
+                val[e] = to_c128(tile[tpart | q | nn]);
                 if (FAC) val[e] = cmul(fac[v], val[e]);
+                q = mono_next_subset(q, qlmask);
+                if (v == VM) nn = mono_next_subset(nn, nmask);
             }
-            if (v == VM) ncur = mono_next_subset(ncur, nmask);
         }
         __syncthreads();  // every amplitude of the round is in registers before the first one is overwritten
+        {
+            uint32_t q = 0;
 #pragma unroll
-        for (int e = 0; e < E; ++e)
-            if (active && j0 + e < per_thread) tile[dst[e]] = from_c128<A>(val[e]);
+            for (int e = 0; e < E; ++e) {
+                constexpr int VM = V - 1;
+                const int v = e & VM;
+                const uint32_t xm = (v & 1) ? (xw[v >> 1] >> 16) : (xw[v >> 1] & 0xFFFFu);
+                tile[(tpart | q | ncur) ^ xm] = from_c128<A>(val[e]);
+                q = mono_next_subset(q, qlmask);
+                if (v == VM) ncur = mono_next_subset(ncur, nmask);
+            }
+        }
         // the next round works on a disjoint set of amplitudes: no barrier needed in between
-    }
-}
-
-// Out of line on purpose: the seven walk variants are large, and inlined into the sweep kernels they
-// slowed down sweeps that never run them (more than 200 KiB of extra code per kernel).
-template <typename A, typename TV>
-__device__ __noinline__ void tile_apply_mono(TV tile, const TileOp& hdr, const TileOp* ops, uint64_t base,
-                                             const double2* __restrict__ tables) {
-    if (hdr.mono.fac) {
-        switch (hdr.mono.vbits) {
-            case 0: tile_mono_rounds<A, 1, true>(tile, hdr, ops, base, tables); break;
-            case 1: tile_mono_rounds<A, 2, true>(tile, hdr, ops, base, tables); break;
-            default: tile_mono_rounds<A, 4, true>(tile, hdr, ops, base, tables); break;
-        }
-    } else {
-        switch (hdr.mono.vbits) {
-            case 0: tile_mono_rounds<A, 1, false>(tile, hdr, ops, base, tables); break;
-            case 1: tile_mono_rounds<A, 2, false>(tile, hdr, ops, base, tables); break;
-            case 2: tile_mono_rounds<A, 4, false>(tile, hdr, ops, base, tables); break;
-            default: tile_mono_rounds<A, 8, false>(tile, hdr, ops, base, tables); break;
-        }
     }
 }
 
@@ -749,18 +681,21 @@ __device__ __forceinline__ void tile_run_ops(TV tile, const TileOp* s_ops, int n
                                              const double2* __restrict__ tables) {
     for (int o = 0; o < n; ++o) {
         const TileOp& op = s_ops[o];
-        if (op.op == kOpPhase || op.op == kOpMono) {
-            bool any = false;  // CTA-uniform: is any gate of the phase active on this tile?
-            if (op.op == kOpMono && op.mono.tab) {
-                uint32_t slice = 0;
-                for (int i = 0; i < op.mono.ebits; ++i) slice |= (uint32_t)((base >> op.mono.epos[i]) & 1ull) << i;
-                any = !((op.mono.identity >> slice) & 1u);
-            } else {
-                for (int mi = 1; mi <= op.ph.count; ++mi) any |= (base & s_ops[o + mi].ext_ctrl) == s_ops[o + mi].ext_ctrl;
+        if (op.op == kOpMono) {
+            uint32_t slice = 0;  // CTA-uniform: which of the outside bits the run tests are set for this tile
+            for (int i = 0; i < op.mono.ebits; ++i) slice |= (uint32_t)((base >> op.mono.epos[i]) & 1ull) << i;
+            if (!((op.mono.identity >> slice) & 1u)) {
+                if (op.mono.fac) tile_apply_mono<A, kMonoVFac, true>(tile, op, base, slice, tables);
+                else tile_apply_mono<A, kMonoV, false>(tile, op, base, slice, tables);
+                __syncthreads();
             }
+            continue;
+        }
+        if (op.op == kOpPhase) {
+            bool any = false;  // CTA-uniform: is any gate of the phase active on this tile?
+            for (int mi = 1; mi <= op.ph.count; ++mi) any |= (base & s_ops[o + mi].ext_ctrl) == s_ops[o + mi].ext_ctrl;
             if (any) {
-                if (op.op == kOpPhase) tile_apply_phase<A>(tile, op, s_ops + o + 1, k, base);
-                else tile_apply_mono<A>(tile, op, s_ops + o + 1, base, tables);
+                tile_apply_phase<A>(tile, op, s_ops + o + 1, k, base);
                 __syncthreads();
             }
             o += op.ph.count;

@@ -88,9 +88,8 @@ struct PlanConfig {
     bool low6 = true;                     // sweeps confined to the low 6 qubits use the warp-shuffle kernel
     bool mono = true;                     // monomial phases: runs of X / SWAP / phase gates inside a tile sweep cost
                                           // index arithmetic only, so such runs ride in tile sweeps
-    bool mono_tables = true;              // monomial phases: do the index walks on the host (per-gate device cost: none)
-    double mono_gate_cost = 0.015;        // one gate of a device-walked monomial phase in units of one full sweep
-                                          // (measured 0.010-0.023, scripts/microbench_mono.py)
+    double mono_gate_cost = 0.001;        // one gate of a monomial phase in units of one full sweep: the index walks
+                                          // run on the host, the device pays per phase, not per gate
 };
 
 // Tunable for experiments through B2SV_MONO_COST.
@@ -98,7 +97,7 @@ inline double mono_gate_cost_default() {
     static const double v = [] {
         const char* e = std::getenv("B2SV_MONO_COST");
         const double x = e ? std::atof(e) : 0.0;
-        return x > 0.0 ? x : 0.015;  // measured: scripts/microbench_mono.py
+        return x > 0.0 ? x : 0.001;
     }();
     return v;
 }
@@ -141,9 +140,13 @@ inline PlanConfig default_config(int n, int dtype, const b2sv_plan_opts* o) {
     PlanConfig c;
     c.n = n;
     c.amp_bytes = dtype == B2SV_C64 ? 8 : 16;
-    c.mono_gate_cost = mono_gate_cost_default();  // (device walks; halved below when the host does the walks)
+    c.mono_gate_cost = mono_gate_cost_default();
     c.tile_qubits = dtype == B2SV_C64 ? 13 : 12;  // 64 KiB of shared memory either way
-    c.chunk_bits = dtype == B2SV_C64 ? 8 : 7;     // 2 KiB contiguous per bulk copy
+    // low qubits every tile contains, i.e. the contiguous run one TMA box moves: 256 bytes.  Measured on
+    // B200: sweeps stream at the same rate with 256 B .. 2 KiB runs (cfg 2: 7.08 vs 7.14 ms), while every
+    // forced low qubit takes a tile position away from the gates' targets (BPX L=8: 289 sweeps / 111 ms
+    // with 2 KiB runs, 141 sweeps / 92 ms with 256 B runs)
+    c.chunk_bits = dtype == B2SV_C64 ? 5 : 4;
     {   // B2SV_CHUNK_BITS: experiment knob (fewer forced low qubits leave more tile qubits for targets)
         static const int env_chunk = [] {
             const char* e = std::getenv("B2SV_CHUNK_BITS");
@@ -160,7 +163,6 @@ inline PlanConfig default_config(int n, int dtype, const b2sv_plan_opts* o) {
     c.phases = !(env_ab & 2);
     c.low6 = !(env_ab & 4);
     c.mono = !(env_ab & 8);
-    c.mono_tables = !(env_ab & 16);
     if (o) {
         c.fuse = o->fuse != 0;
         c.perm_runs = o->perm_runs != 0;
@@ -171,10 +173,8 @@ inline PlanConfig default_config(int n, int dtype, const b2sv_plan_opts* o) {
         c.phases = !(ab & 2);  // reserved bit 1: no register phases (A/B switch)
         c.low6 = !(ab & 4);    // reserved bit 2: no warp-shuffle low-qubit sweeps (A/B switch)
         c.mono = !(ab & 8);    // reserved bit 3: no monomial phases (A/B switch)
-        c.mono_tables = !(ab & 16);  // reserved bit 4: monomial phases walk on the device (A/B switch)
     }
     if (!c.phases) c.mono = false;
-    if (c.mono_tables && !std::getenv("B2SV_MONO_COST")) c.mono_gate_cost = 0.001;  // table-driven: gates are free on the device
     if (c.tile_qubits > 13 && c.amp_bytes == 16) c.tile_qubits = 13;
     if (c.tile_qubits > 14) c.tile_qubits = 14;
     if (c.tile_qubits < 3) c.tile_qubits = 3;

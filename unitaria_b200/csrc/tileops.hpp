@@ -102,7 +102,7 @@ inline TileOp make_tile_op(const Plan& plan, const PGate& g, uint64_t tile_mask,
 constexpr int kPhaseMaxMembers = kTileMaxOps - 1; // header + members fit one staged batch
 constexpr size_t kMonoMaxTableBytes = 256 * 1024; // per table-driven phase
 
-// Host side of a table-driven monomial phase: walk every (thread, walk) index of the phase through the
+// Host side of a monomial phase: walk every (thread, walk) index of the phase through the
 // members, once per value of the `ebits` outside qubits the members test (beyond the sweep's common
 // controls, which hold in every launched tile).  The walks run bit-sliced, 64 at a time: word b holds
 // bit b of 64 indices, an X is `word[t] ^= AND of the control words`.  Results: per walk the XOR mask
@@ -193,11 +193,11 @@ inline void mono_build_table(const TileOp* members, size_t count, int k, uint32_
 //   register phase: maximal run of consecutive plain gates whose targets fall on at most three tile-local
 //                   positions -- applied in registers, one shared-memory round trip for the run;
 //   monomial phase: maximal run of consecutive X / SWAP / PHASE / DIAG1 gates touching (as target or tile-local
-//                   control) at most tb+3 tile positions (tb+2 with phase factors) -- every thread walks the
-//                   few index values its amplitudes can have on those positions through the run.
+//                   control) at most 11 tile positions (10 with phase factors) -- the index walks are done here,
+//                   on the host (mono_build_table); the device fetches their results and moves the amplitudes.
 // At every position the kind that swallows more gates wins.
-// `common`: the sweep's common outside controls (set in every launched tile); `tables`: where table-driven
-// phases put their walk results (Plan::mux_tables; nullptr = always walk on the device).
+// `common`: the sweep's common outside controls (set in every launched tile); `tables`: where monomial
+// phases put their walk results (Plan::mux_tables).
 inline void append_with_phases(const std::vector<TileOp>& ops, int k, bool enable, bool mono, uint64_t common,
                                std::vector<double>* tables, std::vector<TileOp>& out) {
     auto plain = [](const TileOp& o) {
@@ -244,50 +244,49 @@ inline void append_with_phases(const std::vector<TileOp>& ops, int k, bool enabl
         size_t jm = i;
         uint32_t Q = 0;      // tile positions the run reads or moves
         uint64_t EX = 0;     // outside qubits the run tests beyond the sweep's common controls
-        bool fac = false, tab = false;
+        bool fac = false;
         bool mono_worth = false;
-        const int tb = k < kMonoThreadBits ? k : kMonoThreadBits;
+        const int tb = kMonoThreadBits, lb = k - tb;
         auto touched = [&](const TileOp& o) { return o.lctrl | targets(o); };
         auto outside = [&](const TileOp& o) { return (o.ext_ctrl & ~common) | o.ext_tbit; };
-        auto q_fits = [&](uint32_t q, bool f) {
-            const int extra = __builtin_popcount(q) - tb;  // Q bits that must become loop bits: V = 2^extra walks per thread
-            return extra <= (f ? 2 : 3) && (extra <= 0 || extra <= k - tb);
-        };
-        auto tab_fits = [&](uint32_t q, bool f, uint64_t ex) {  // can the walks be done on the host?
-            if (!tables || k < kMonoThreadBits || k > 16 || popcount64(ex) > kMonoMaxEbits) return false;
-            const int extra = std::max(0, __builtin_popcount(q) - tb);
-            const size_t walks = ((size_t)1 << (tb + extra)) << popcount64(ex);
+        // the walks of a thread: 8 for a pure permutation, 4 when amplitudes pick up factors; at most 16 table
+        // slices, and a bounded table
+        auto fits = [&](uint32_t q, bool f, uint64_t ex) {
+            const int vbits = f ? 2 : 3;
+            if (__builtin_popcount(q) > tb + vbits || popcount64(ex) > kMonoMaxEbits) return false;
+            const size_t walks = ((size_t)1 << (tb + vbits)) << popcount64(ex);
             return walks * (f ? 18 : 2) <= kMonoMaxTableBytes;
         };
-        if (mono && monomial(ops[i])) {
+        if (mono && tables && lb >= 3 && k <= 16 && monomial(ops[i])) {
             Q = touched(ops[i]);
             EX = outside(ops[i]);
             fac = !(ops[i].op == B2SV_OP_X || ops[i].op == B2SV_OP_SWAP);
-            tab = tab_fits(Q, fac, EX);
             double separate = alone_cost(ops[i]);
             jm = i + 1;
-            // a table-driven phase has no members on the device, so it may be as long as the run
-            while (q_fits(Q, fac) && jm < ops.size() && monomial(ops[jm]) && (tab ? jm - i < 60000 : (int)(jm - i) < kPhaseMaxMembers)) {
+            // the phase has no members on the device, so it may be as long as the run
+            while (fits(Q, fac, EX) && jm < ops.size() && monomial(ops[jm])) {
                 const uint32_t Q2 = Q | touched(ops[jm]);
                 const uint64_t EX2 = EX | outside(ops[jm]);
                 const bool fac2 = fac || !(ops[jm].op == B2SV_OP_X || ops[jm].op == B2SV_OP_SWAP);
-                if (!q_fits(Q2, fac2)) break;
-                if (tab && !tab_fits(Q2, fac2, EX2)) break;  // close the table-driven phase here, start another one
+                if (!fits(Q2, fac2, EX2)) break;  // close the phase here, the next one starts with this gate
                 Q = Q2;
                 EX = EX2;
                 fac = fac2;
                 separate += alone_cost(ops[jm]);
                 ++jm;
             }
-            // one round trip of the whole tile, plus (device walks only) ~0.1 pass of index arithmetic per gate
-            const double mono_cost = 1.0 + (tab ? 0.0 : 0.1 * (double)(jm - i)) + 0.08;
-            mono_worth = q_fits(Q, fac) && jm - i >= 2 && separate > mono_cost;
+            // measured (scripts/microbench_mono.py): a phase costs ~0.45 sweep whatever its length = ~2.5 passes
+            mono_worth = fits(Q, fac, EX) && jm - i >= 2 && separate > 2.5;
         }
-        if (mono_worth && jm >= jr) {
+        // a register phase is the cheaper round trip (no bank conflicts, ~1 pass) but pays per gate; a monomial
+        // phase costs the same whatever its length
+        if (mono_worth && (jm >= jr || jm - i >= 16)) {
             TileOp h{};
             h.op = kOpMono;
+            h.mono.count = 0;
             h.mono.fac = fac ? 1 : 0;
-            h.mono.lb = (uint8_t)(k - tb);
+            h.mono.lb = (uint8_t)lb;
+            h.mono.vbits = (uint8_t)(fac ? 2 : 3);
             // thread bits: Q positions first (ascending), filled up with the lowest other positions; the lowest
             // positions end up in the lane number, so a warp reads whole 128-byte rows whenever it can
             uint32_t tmask = 0;
@@ -296,36 +295,31 @@ inline void append_with_phases(const std::vector<TileOp>& ops, int k, bool enabl
             for (int p = 0; p < k && __builtin_popcount(tmask) < tb; ++p)
                 if (!((tmask >> p) & 1)) tmask |= 1u << p;
             const uint32_t all = (1u << k) - 1u;
+            // walk bits: the Q positions that did not fit the thread number, filled up with the highest others
+            uint32_t qlmask = Q & ~tmask & all;
+            for (int p = k - 1; p >= 0 && __builtin_popcount(qlmask) < h.mono.vbits; --p)
+                if (!((tmask >> p) & 1) && !((qlmask >> p) & 1)) qlmask |= 1u << p;
             h.mono.tmask = tmask;
-            h.mono.qlmask = Q & ~tmask & all;       // the Q positions that did not fit: 2^vbits walks per thread
-            h.mono.nmask = ~Q & ~tmask & all;
-            h.mono.vbits = (uint8_t)__builtin_popcount(h.mono.qlmask);
-            if (tab) {
-                h.mono.tab = 1;
-                h.mono.count = 0;
-                int ne = 0;
-                for (int q = 0; q < 64; ++q)
-                    if ((EX >> q) & 1) h.mono.epos[ne++] = (uint8_t)q;
-                h.mono.ebits = (uint8_t)ne;
-                std::vector<uint16_t> masks;
-                std::vector<double> factors;
-                mono_build_table(&ops[i], jm - i, k, tmask, h.mono.qlmask, 1 << h.mono.vbits, fac, common, h.mono.epos, ne, masks,
-                                 factors, h.mono.identity);
-                while (tables->size() % 2) tables->push_back(0.0);  // offsets count 16-byte units
-                h.mono.mask_off = tables->size() / 2;
-                const size_t mask_doubles = (masks.size() * sizeof(uint16_t) + 15) / 16 * 2;
-                tables->resize(tables->size() + mask_doubles, 0.0);
-                std::memcpy(reinterpret_cast<char*>(tables->data()) + h.mono.mask_off * 16, masks.data(), masks.size() * sizeof(uint16_t));
-                if (fac) {
-                    h.mono.fac_off = tables->size() / 2;
-                    tables->insert(tables->end(), factors.begin(), factors.end());
-                }
-                out.push_back(h);
-            } else {
-                h.mono.count = (uint16_t)(jm - i);
-                out.push_back(h);
-                for (size_t q = i; q < jm; ++q) out.push_back(ops[q]);
+            h.mono.qlmask = qlmask;
+            h.mono.nmask = ~qlmask & ~tmask & all;
+            int ne = 0;
+            for (int q = 0; q < 64; ++q)
+                if ((EX >> q) & 1) h.mono.epos[ne++] = (uint8_t)q;
+            h.mono.ebits = (uint8_t)ne;
+            std::vector<uint16_t> masks;
+            std::vector<double> factors;
+            mono_build_table(&ops[i], jm - i, k, tmask, qlmask, 1 << h.mono.vbits, fac, common, h.mono.epos, ne, masks, factors,
+                             h.mono.identity);
+            while (tables->size() % 2) tables->push_back(0.0);  // offsets count 16-byte units
+            h.mono.mask_off = tables->size() / 2;
+            const size_t mask_doubles = (masks.size() * sizeof(uint16_t) + 15) / 16 * 2;
+            tables->resize(tables->size() + mask_doubles, 0.0);
+            std::memcpy(reinterpret_cast<char*>(tables->data()) + h.mono.mask_off * 16, masks.data(), masks.size() * sizeof(uint16_t));
+            if (fac) {
+                h.mono.fac_off = tables->size() / 2;
+                tables->insert(tables->end(), factors.begin(), factors.end());
             }
+            out.push_back(h);
             i = jm;
             continue;
         }
@@ -388,8 +382,7 @@ inline void build_segment_ops(Plan& plan, const Segment& seg, const PlanConfig& 
     seg_ops.reserve(seg.gates.size());
     for (int gi : seg.gates) seg_ops.push_back(make_tile_op(plan, plan.gates[gi], seg.tile_mask, ex));
     const bool tile = seg.cls == SEG_TILE;
-    append_with_phases(seg_ops, ex.m, cfg.phases && tile, cfg.mono && tile, seg.common_ctrl, cfg.mono_tables ? &plan.mux_tables : nullptr,
-                       grouped);
+    append_with_phases(seg_ops, ex.m, cfg.phases && tile, cfg.mono && tile, seg.common_ctrl, &plan.mux_tables, grouped);
     if (tile) layout_batches(grouped, out);
     else out.insert(out.end(), grouped.begin(), grouped.end());
 }
