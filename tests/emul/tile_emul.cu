@@ -346,3 +346,47 @@ extern "C" int emul_apply(int n, int dtype, const b2sv_gate* gates, size_t n_gat
     }
     return 0;
 }
+
+// Introspection for profiling scripts: the op program of tile segment `seg_index` as (kind, detail) pairs --
+// detail = members of a register phase, block qubits, multiplexor index bits, local controls of a plain op.
+extern "C" int emul_describe_segment(int n, int dtype, const b2sv_gate* gates, size_t n_gates, const b2sv_plan_opts* opts, int seg_index,
+                                     int32_t* out, int cap) {
+    PlanConfig cfg = default_config(n, dtype, opts);
+    if (n < 13) cfg.perm_runs = false;
+    Plan plan = make_plan(gates, n_gates, cfg, true);
+    if (seg_index < 0 || seg_index >= (int)plan.segs.size()) return -1;
+    const Segment& seg = plan.segs[seg_index];
+    if (seg.cls != SEG_TILE && seg.cls != SEG_LOW6) return 0;
+    std::vector<TileOp> ops;
+    build_segment_ops(plan, seg, cfg, ops);
+    int m = 0;
+    for (size_t o = 0; o < ops.size() && 2 * m + 1 < cap; ++o) {
+        const TileOp& op = ops[o];
+        int detail = 0;
+        if (op.op == kOpPhase) detail = op.ph.count;
+        else if (op.op == kOpMono) detail = op.mono.fac * 100 + op.mono.ebits;
+        else if (op.op == kOpBlock) detail = op.blk.kb;
+        else if (op.op == kOpMux) detail = op.mux.nmux;
+        else detail = __builtin_popcount(op.lctrl);
+        out[2 * m] = op.op;
+        out[2 * m + 1] = detail;
+        ++m;
+        if (op.op == kOpPhase) o += op.ph.count;
+    }
+    return m;
+}
+
+// Plan + build every segment's op program (what b2sv_apply does on the host before the first launch);
+// returns {segments, ops, table doubles} -- used to time the host side.
+extern "C" int emul_build_all(int n, int dtype, const b2sv_gate* gates, size_t n_gates, const b2sv_plan_opts* opts, int64_t* out3) {
+    PlanConfig cfg = default_config(n, dtype, opts);
+    if (n < 13) cfg.perm_runs = false;
+    Plan plan = make_plan(gates, n_gates, cfg, true);
+    std::vector<TileOp> ops;
+    for (const Segment& seg : plan.segs)
+        if (seg.cls == SEG_TILE || seg.cls == SEG_LOW6) build_segment_ops(plan, seg, cfg, ops);
+    out3[0] = (int64_t)plan.segs.size();
+    out3[1] = (int64_t)ops.size();
+    out3[2] = (int64_t)plan.mux_tables.size();
+    return 0;
+}
