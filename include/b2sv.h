@@ -145,6 +145,12 @@ int b2sv_project_norm2_at(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, in
  * (= Subspace.enumerate_basis order, subspace.py:325-329); `dim` must equal the subspace dimension. */
 int b2sv_project_gather(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
                         double scale_re, double scale_im, void* host_out_c128, uint64_t dim);
+/* The inverse hand-off: psi := sum_r host_in[r] |basis_r>, i.e. the members of the subspace (ascending
+ * index order) take the `dim` amplitudes and every other amplitude is 0.  Replaces the 2^n-element host
+ * array BlockEncoding.compute fills and uploads (nodes/block_encoding.py:45-52: full_input[basis] = input):
+ * only `dim` amplitudes cross PCIe.  `dim` must equal the subspace dimension. */
+int b2sv_embed(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
+               const void* host_in_c128, uint64_t dim);
 /* Same predicate on the host-visible side of enumerate_basis: writes the member indices (int64). */
 int b2sv_enumerate_basis(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
                          int64_t* host_out, uint64_t dim);

@@ -121,6 +121,11 @@ class FakeStateVector:
         prog = subspace if isinstance(subspace, SubspaceProgram) else SubspaceProgram(subspace)
         return self._members(prog)
 
+    def embed(self, subspace, vector):
+        prog = subspace if isinstance(subspace, SubspaceProgram) else SubspaceProgram(subspace)
+        self.psi[:] = 0
+        self.psi[self._members(prog)] = np.asarray(vector, dtype=np.complex128).reshape(-1)
+
     def project(self, subspace, scale=1.0):
         prog = subspace if isinstance(subspace, SubspaceProgram) else SubspaceProgram(subspace)
         return complex(scale) * self.psi[self._members(prog)]

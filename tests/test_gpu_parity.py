@@ -217,6 +217,64 @@ def test_device_enumerate_basis_and_projection_order(name, which):
         assert abs(sv.project_norm2(prog) - float(np.sum(np.abs(psi[want]) ** 2))) < 1e-13
 
 
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("name", ["laplace_readme_n8", "bpx_L3", "pinv_bpx_L2", "cfg5_bits13", "laplace_n16"])
+def test_embed_is_the_inverse_of_project(name, dtype):
+    """b2sv_embed: the members take the vector in enumerate_basis order, everything else is zero
+    (BlockEncoding.compute's ``full_input[basis] = input``, nodes/block_encoding.py:49-52)."""
+    case = load_golden(name)
+    spec = case.meta["subspace_in"]
+    prog = SubspaceProgram(spec)
+    if prog.total_qubits > 22:
+        pytest.skip("oracle enumeration too large")
+    basis = np_oracle.enumerate_basis(spec)
+    n = case.n_qubits
+    rng = np.random.default_rng(12)
+    vec = rng.normal(size=len(basis)) + 1j * rng.normal(size=len(basis))
+    if dtype == "complex64":
+        vec = vec.astype(np.complex64).astype(np.complex128)
+    want = np.zeros(2**n, dtype=np.complex128)
+    want[basis] = vec
+    with StateVector(n, dtype) as sv:
+        sv.set_basis(3)  # a pending basis state must not survive the embedding
+        sv.embed(prog, vec)
+        assert np.array_equal(sv.download(), want)
+        assert np.array_equal(sv.project(prog), vec)
+        with pytest.raises(ValueError):
+            sv.embed(prog, vec[:-1])
+
+
+@pytest.mark.parametrize("name", ["laplace_n8", "bpx_L3", "gaussian_s3_t8", "laplace_readme_n8"])
+def test_block_encoding_compute_device_resident(name):
+    """adapter.block_encoding_compute == the reference's BlockEncoding.compute formula evaluated with the
+    oracle: embed, simulate, normalization * project, project again (block_encoding.py:45-66)."""
+    case = load_golden(name)
+    if case.meta["is_vector"]:
+        pytest.skip("needs a matrix-valued case")
+    n, norm = case.n_qubits, case.meta["normalization"]
+    s_in, s_out = case.meta["subspace_in"], case.meta["subspace_out"]
+    b_in, b_out = np_oracle.enumerate_basis(s_in), np_oracle.enumerate_basis(s_out)
+    if len(b_out) and b_out.max() >= len(b_out):
+        pytest.skip("the reference's second projection is out of range for this subspace")
+    rng = np.random.default_rng(13)
+    batch = rng.normal(size=(3, len(b_in))) + 1j * rng.normal(size=(3, len(b_in)))
+
+    class Circuit:
+        gates = case.gates
+
+    def ref(vec):
+        full = np.zeros(2**n, dtype=np.complex128)
+        full[b_in] = vec
+        out = norm * np_oracle.simulate_gates(case.gates, n, full)[b_out]
+        return out[b_out]
+
+    got = adapter.block_encoding_compute(Circuit, n, s_in, s_out, norm, batch[0])
+    assert np.abs(got - ref(batch[0])).max() < tol("complex128", len(case.gates))
+    got = adapter.block_encoding_compute(Circuit, n, s_in, s_out, norm, batch)
+    want = np.stack([ref(v) for v in batch])
+    assert got.shape == want.shape and np.abs(got - want).max() < tol("complex128", len(case.gates))
+
+
 def test_adapter_simulate_circuit_contract():
     """Circuit.simulate's contract (circuit.py:42-70) incl. quirks Q1-Q3, Q7 of SURVEY.md App. D."""
     import tequila as tq

@@ -8,7 +8,8 @@ Public surface:
 
 * :func:`install` / :func:`uninstall` -- patch unitaria in place (drop-in backend).
 * :func:`simulate_circuit`, :func:`simulate_projected`, :func:`simulate_norm`,
-  :func:`estimate_norm_sampled` (sampling mode) -- the same calls on any tequila-like circuit object.
+  :func:`estimate_norm_sampled` (sampling mode), :func:`block_encoding_compute` (device-resident
+  ``BlockEncoding.compute``) -- the same calls on any tequila-like circuit object.
 * :class:`StateVector` -- one device-resident register; :class:`SubspaceProgram`; :func:`lower_gates`.
 
 There is no CPU fallback: the CUDA library must be built (``python -m unitaria_b200.build``) and a
@@ -16,6 +17,7 @@ CUDA device must be present for any compute call.
 """
 
 from .adapter import (  # noqa: F401
+    block_encoding_compute,
     clear_caches,
     configure,
     estimate_norm_sampled,

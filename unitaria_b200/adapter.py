@@ -41,6 +41,7 @@ def configure(dtype=None, device=None, opts: PlanOpts | None = None) -> None:
 
 
 def clear_caches() -> None:
+    _BASIS.clear()
     _LOWERED.clear()
     for sv in _STATES.values():
         sv.close()
@@ -121,6 +122,52 @@ def simulate_norm(tq_circuit, n_qubits: int, subspace_out, normalization, input=
     if not touches_any_qubit(tq_circuit.gates):
         return float(np.linalg.norm(simulate_projected(tq_circuit, n_qubits, prog, normalization, input)))
     return float(abs(normalization) * np.sqrt(_run(tq_circuit, n_qubits, input).project_norm2(prog)))
+
+
+_BASIS: dict = {}
+
+
+def _basis_indices(prog: SubspaceProgram) -> np.ndarray:
+    """``Subspace.enumerate_basis()`` of a compiled subspace, enumerated on the device once and kept."""
+    key = (prog.instrs.tobytes(), prog.entry)
+    hit = _BASIS.get(key)
+    if hit is None:
+        hit = _state(max(1, prog.total_qubits)).enumerate_basis(prog)
+        if len(_BASIS) > 64:
+            _BASIS.clear()
+        _BASIS[key] = hit
+    return hit
+
+
+def block_encoding_compute(tq_circuit, n_qubits: int, subspace_in, subspace_out, normalization, input: np.ndarray) -> np.ndarray:
+    """``BlockEncoding.compute`` (nodes/block_encoding.py:45-66) with the state kept on the device: the
+    reference fills a 2^n host array (``full_input[basis_in] = input``), simulates it and projects twice;
+    here the ``dimension_in`` amplitudes are embedded on the device (b2sv_embed), the circuit runs, and
+    only ``dimension_out`` amplitudes come back.  Vector and batch forms, same results and quirks."""
+    prog_in = subspace_in if isinstance(subspace_in, SubspaceProgram) else SubspaceProgram(subspace_in)
+    prog_out = subspace_out if isinstance(subspace_out, SubspaceProgram) else SubspaceProgram(subspace_out)
+    n = max(1, int(n_qubits))
+    input = np.asarray(input)
+
+    def one(vec):
+        if not touches_any_qubit(tq_circuit.gates) or prog_in.total_qubits > n:
+            full_input = np.zeros(2**n_qubits, dtype=np.complex128)
+            full_input[_basis_indices(prog_in)] = vec
+            out = simulate_projected(tq_circuit, n_qubits, prog_out, normalization, full_input)
+        else:
+            sv = _state(n)
+            sv.embed(prog_in, vec)
+            sv.apply_lowered(_lowered(tq_circuit, n_qubits), _DEFAULTS["opts"])
+            out = sv.project(prog_out, scale=normalization)
+        # the reference projects the already projected vector once more (block_encoding.py:54)
+        return out[_basis_indices(prog_out)]
+
+    if input.ndim == 1:
+        return one(input)
+    results = np.zeros((input.shape[0], prog_out.dimension), dtype=np.complex128)
+    for idx in np.ndindex(input.shape[:-1]):
+        results[idx] = one(input[idx])
+    return results
 
 
 _SAMPLING_RNG = np.random.default_rng()
@@ -254,6 +301,24 @@ def install(dtype="complex128", device: int = 0, opts: PlanOpts | None = None, p
         except ImportError:  # pragma: no cover - a unitaria without the estimator package
             pass
 
+        try:  # device-resident BlockEncoding.compute
+            import unitaria.nodes.block_encoding as ube_node
+
+            if "BlockEncoding.compute" not in _ORIGINALS:
+                _ORIGINALS["BlockEncoding.compute"] = ube_node.BlockEncoding.compute
+
+            def block_encoding_compute_patched(self, input):
+                circuit = self.circuit()
+                return block_encoding_compute(
+                    circuit._tq_circuit, circuit.n_qubits, _subspace_program(self._subspace_in_obj),
+                    _subspace_program(self._subspace_out_obj), self.normalization, input,
+                )
+
+            block_encoding_compute_patched.__doc__ = _ORIGINALS["BlockEncoding.compute"].__doc__
+            ube_node.BlockEncoding.compute = block_encoding_compute_patched
+        except ImportError:  # pragma: no cover
+            pass
+
         node_simulate.__doc__ = _ORIGINALS["Node.simulate"].__doc__
         node_simulate_norm.__doc__ = _ORIGINALS["Node.simulate_norm"].__doc__
         Node.simulate = node_simulate
@@ -270,6 +335,10 @@ def uninstall() -> None:
         import unitaria.estimator.backend_estimator as ube
 
         ube.BackendEstimator.estimate_norm = _ORIGINALS.pop("BackendEstimator.estimate_norm")
+    if "BlockEncoding.compute" in _ORIGINALS:
+        import unitaria.nodes.block_encoding as ube_node
+
+        ube_node.BlockEncoding.compute = _ORIGINALS.pop("BlockEncoding.compute")
     if "Node.simulate" in _ORIGINALS:
         import unitaria.nodes.node as unode
 

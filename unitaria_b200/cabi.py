@@ -121,6 +121,7 @@ SYMBOLS = {
         ctypes.c_int,
         [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, _P, ctypes.c_uint64],
     ),
+    "b2sv_embed": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, ctypes.c_uint64]),
     "b2sv_enumerate_basis": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, ctypes.c_uint64]),
     "b2sv_device_ptr": (ctypes.c_int, [_P, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_uint64)]),
     "b2sv_sync": (ctypes.c_int, [_P]),

@@ -1106,6 +1106,33 @@ int b2sv_project_gather(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int 
     return B2SV_OK;
 }
 
+int b2sv_embed(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits, const void* host_in,
+               uint64_t dim) {
+    if (int rc = check(sv)) return rc;
+    if (!host_in && dim > 0) return fail(B2SV_EINVAL, "host_in is null");
+    CU(cudaSetDevice(sv->device));
+    int count_bits = 0;
+    if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits)) return rc;
+    const uint64_t cnt = 1ull << count_bits;
+    if (int rc = ensure_gather(sv, (dim ? dim : 1) * 16)) return rc;
+    double2* d_in = (double2*)sv->d_gather;
+    if (dim) CU(cudaMemcpyAsync(d_in, host_in, dim * 16, cudaMemcpyHostToDevice, sv->stream));
+    // the register is overwritten: nothing pending survives
+    sv->pending_basis = false;
+    sv->sre = 1.0;
+    sv->sim = 0.0;
+    dispatch_dtype(sv, [&](auto* tag) -> int {
+        using A = std::remove_pointer_t<decltype(tag)>;
+        LaunchTimer lt(sv, sv->timing_on, CLS_INIT, (double)sv->amp_bytes * (double)sv->count + 16.0 * (double)dim);
+        k_embed<A><<<grid_for(sv, sv->count), kThreads, 0, sv->stream>>>((A*)sv->amps, sv->d_sub, sv->count, cnt, entry, n_instr + 1, d_in, dim);
+        return B2SV_OK;
+    });
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sv->stream);  // host_in is borrowed for the call only
+    if (e != cudaSuccess) return fail(B2SV_ECUDA, "embed failed: %s", cudaGetErrorString(e));
+    return B2SV_OK;
+}
+
 int b2sv_enumerate_basis(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
                          int64_t* host_out, uint64_t dim) {
     if (int rc = check(sv)) return rc;

@@ -1378,6 +1378,22 @@ __global__ void __launch_bounds__(kThreads) k_project_gather(const A* __restrict
     }
 }
 
+// The inverse of the gather: psi_i = in[rank(i)] for the members of the subspace, 0 everywhere else
+// (the embedding BlockEncoding.compute builds on the host, nodes/block_encoding.py:49-52); `count` is
+// the index range that can hold members, `total` the whole register.
+template <typename A>
+__global__ void __launch_bounds__(kThreads) k_embed(A* __restrict__ psi, const b2sv_subinstr* __restrict__ sub, uint64_t total,
+                                                    uint64_t count, int entry, int max_steps, const double2* __restrict__ in,
+                                                    uint64_t dim) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        uint64_t r;
+        double2 v = make_double2(0.0, 0.0);
+        if (i < count && sub_member_rank(sub, entry, max_steps, i, r) && r < dim) v = __ldg(in + r);
+        psi[i] = from_c128<A>(v);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) k_enumerate_basis(const b2sv_subinstr* __restrict__ sub, uint64_t count, int entry, int max_steps,
                                                               long long* __restrict__ out,
                                                               uint64_t dim) {

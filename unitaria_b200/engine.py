@@ -218,6 +218,16 @@ class StateVector:
         )
         return out
 
+    def embed(self, subspace, vector: np.ndarray) -> None:
+        """psi := sum_r vector[r] |basis_r>: the inverse of :meth:`project` and the device form of the
+        embedding in ``BlockEncoding.compute`` (nodes/block_encoding.py:49-52) -- only ``dimension``
+        amplitudes are uploaded, the rest of the register is zero-filled on the device."""
+        p = self._program(subspace)
+        v = np.ascontiguousarray(vector, dtype=np.complex128).reshape(-1)
+        if v.size != p.dimension:
+            raise ValueError(f"vector has {v.size} entries, the subspace has dimension {p.dimension}")
+        cabi.check(self._lib.b2sv_embed(self._h, p.instrs.ctypes.data, len(p.instrs), p.entry, p.total_qubits, v.ctypes.data, p.dimension))
+
     def enumerate_basis(self, subspace) -> np.ndarray:
         """``Subspace.enumerate_basis`` (subspace.py:325-329) with int64 indices."""
         p = self._program(subspace)
