@@ -1329,17 +1329,25 @@ __device__ __forceinline__ bool sub_member_rank(const b2sv_subinstr* __restrict_
     return false;
 }
 
-template <typename A>
+// G > 1: the program starts with a FREE instruction on the low bits [0, len >= log2 G), so the G amplitudes of
+// an aligned group are members together (and their ranks are consecutive multiples of that instruction's
+// weight): the decision program is walked once per group instead of once per amplitude -- for the
+// "0..0#..#" subspaces of block encodings the walk, not the memory, was the bound (ncu: 17 % DRAM, 68 % SM).
+template <typename A, int G>
 __global__ void __launch_bounds__(kThreads) k_project_norm2(const A* __restrict__ psi, const b2sv_subinstr* __restrict__ sub,
                                                             uint64_t count, int entry, int max_steps, uint64_t index_base,
                                                             double* __restrict__ partial) {
     double acc = 0.0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g * G < count; g += stride) {
+        const uint64_t i = g * G;
         uint64_t r;
         if (sub_member_rank(sub, entry, max_steps, index_base | i, r)) {
-            const double2 v = to_c128(psi[i]);
-            acc = fma(v.x, v.x, fma(v.y, v.y, acc));
+            double2 v[G];
+#pragma unroll
+            for (int j = 0; j < G; ++j) v[j] = to_c128(psi[i + j]);
+#pragma unroll
+            for (int j = 0; j < G; ++j) acc = fma(v[j].x, v[j].x, fma(v[j].y, v[j].y, acc));
         }
     }
     __shared__ double red[kThreads / 32];
@@ -1367,14 +1375,22 @@ __global__ void __launch_bounds__(kThreads) k_reduce_partials(const double* __re
     if (threadIdx.x == 0) *out = red[0];
 }
 
-template <typename A>
+template <typename A, int G>
 __global__ void __launch_bounds__(kThreads) k_project_gather(const A* __restrict__ psi, const b2sv_subinstr* __restrict__ sub,
                                                              uint64_t count, int entry, int max_steps,
-                                                             double2 scale, double2* __restrict__ out, uint64_t dim) {
+                                                             double2 scale, double2* __restrict__ out, uint64_t dim, uint64_t weight) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g * G < count; g += stride) {
+        const uint64_t i = g * G;
         uint64_t r;
-        if (sub_member_rank(sub, entry, max_steps, i, r) && r < dim) out[r] = cmul(scale, to_c128(psi[i]));
+        if (sub_member_rank(sub, entry, max_steps, i, r)) {
+            double2 v[G];
+#pragma unroll
+            for (int j = 0; j < G; ++j) v[j] = to_c128(psi[i + j]);
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+                if (r + j * weight < dim) out[r + j * weight] = cmul(scale, v[j]);
+        }
     }
 }
 
