@@ -169,6 +169,43 @@ def test_monomial_long_runs_are_bit_exact_and_batched(dtype, n):
     assert 1 <= launches["tile"] <= 16, launches
 
 
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("jit", ["sync", "off"])
+@pytest.mark.parametrize("name", ["laplace_n12", "laplace_n16", "laplace_n20", "gaussian_s3_t13", "cfg5_bits13"])
+def test_basis_inputs_through_the_live_window(name, jit, dtype):
+    """set_basis + [one tile sweep] + [permutation sweep]: only the tile that owns the index is written and the
+    permutation sweep takes zeros for the rest (b2sv::window).  Full-state parity for basis indices in
+    different tiles, then readers that need the whole register right after the first sweep."""
+    case = load_golden(name)
+    n = case.n_qubits
+    live = [g for g in case.gates if g.name != "I"]  # lowering drops the I pads: keep plan indices aligned
+    low = lower_gates(live, n)
+    opts = PlanOpts.make(jit=jit)
+    with StateVector(n, dtype) as sv:
+        segs, _ = cabi.plan_describe(n, cabi.B2SV_C128 if dtype == "complex128" else cabi.B2SV_C64, low, opts)
+        classes = [c for c, _m, _i in segs]
+        assert classes[0] in (cabi.SEG_TILE, cabi.SEG_LOW6) and cabi.SEG_PERM in classes[1:2], classes  # the shape this test is about
+        for index in (0, 1, 5, (1 << n) - 1, 1 << (n - 1), (1 << (n - 2)) + 77):
+            psi0 = np.zeros(2**n, dtype=np.complex128)
+            psi0[index] = 1
+            want = c_oracle.simulate_gates(case.gates, n, psi0)
+            # dirty the buffers first: the window must not read stale amplitudes
+            sv.upload(random_state(n, np.random.default_rng(index)))
+            sv.apply_lowered(low, opts)
+            sv.set_basis(index)
+            sv.apply_lowered(low, opts)
+            got = sv.download()
+            assert np.abs(got - want).max() < tol(dtype, len(case.gates)), index
+        # a prefix that ends right after the first sweep: the next reader materialises the implied zeros
+        first = [live[i] for i in segs[0][2]]
+        sv.upload(random_state(n, np.random.default_rng(1)))
+        sv.set_basis(3)
+        sv.apply(first, opts)
+        psi0 = np.zeros(2**n, dtype=np.complex128)
+        psi0[3] = 1
+        assert np.abs(sv.download() - c_oracle.simulate_gates(first, n, psi0)).max() < tol(dtype, len(first))
+
+
 @pytest.mark.parametrize("name", ["laplace_n12", "laplace_n16", "laplace_n20", "gaussian_s3_t13", "bpx_L4", "bpx_L5", "cfg5_bits13"])
 def test_mid_size_configs_against_c_oracle(name):
     """The BASELINE.json circuit families at sizes the CPU oracle finishes in seconds: full state."""

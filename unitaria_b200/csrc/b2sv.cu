@@ -68,6 +68,11 @@ struct b2sv {
     bool scratch_failed = false;
     bool pending_basis = false;    // |basis_index> has been requested but not written yet (lazy init)
     uint64_t basis_index = 0;
+    // live window: the state is zero outside {i : (i & win_mask) == win_value} and only that part of the
+    // buffer has been written (a basis state after one sweep that ran on the single tile owning the index,
+    // when a permutation sweep follows: that sweep then reads one tile instead of a whole register of zeros)
+    bool window = false;
+    uint64_t win_mask = 0, win_value = 0;
     bool timing_on = false;        // last b2sv_apply asked for per-launch timing: time init/project too
     double sre = 1.0, sim = 0.0;   // pending global scalar (folded uncontrolled global phases)
     void* d_ops = nullptr;         // device copy of the tile ops of the current apply
@@ -243,6 +248,18 @@ int flush_scalar(b2sv* sv, bool timing) {
 
 // Write the lazily requested basis state out (every reader of the amplitudes calls this first).
 int materialise(b2sv* sv) {
+    if (sv->window) {  // write the implied zeros
+        sv->window = false;
+        const uint64_t mask = sv->win_mask, value = sv->win_value;
+        int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
+            using A = std::remove_pointer_t<decltype(tag)>;
+            LaunchTimer lt(sv, sv->timing_on, CLS_INIT, (double)sv->amp_bytes * (double)sv->count);
+            k_window_fill<A><<<grid_for(sv, sv->count), kThreads, 0, sv->stream>>>((A*)sv->amps, sv->count, mask, value);
+            return B2SV_OK;
+        });
+        CU(cudaGetLastError());
+        if (rc) return rc;
+    }
     if (!sv->pending_basis) return B2SV_OK;
     sv->pending_basis = false;
     const uint64_t index = sv->basis_index;
@@ -366,14 +383,22 @@ int set_pipe_smem(size_t bytes) {
     return B2SV_OK;
 }
 
+// owner_only (with lazy_init): launch just the one tile that holds the pending basis index; the caller then
+// records the rest of the register as "implied zeros" (b2sv::window).
 int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, const PlanConfig& cfg, int tile_io,
-                bool fused_ops, bool timing, bool lazy_init) {
+                bool fused_ops, bool timing, bool lazy_init, bool owner_only = false) {
     const bool bulk = tile_io != 1;
     TileArgs a{};
     fill_expand(a.tile_ex, seg.tile_mask);
     if (popcount64(seg.tile_mask | seg.common_ctrl) > kMaxFixed) return fail(B2SV_EINVAL, "tile + common controls exceed %d qubits", kMaxFixed);
-    fill_expand(a.cta_ex, seg.tile_mask | seg.common_ctrl);
-    a.cta_or = seg.common_ctrl;
+    if (owner_only) {
+        if (sv->n > kMaxFixed) return fail(B2SV_EINVAL, "register wider than %d qubits", kMaxFixed);
+        fill_expand(a.cta_ex, low_mask(sv->n));           // every bit fixed: one tile
+        a.cta_or = sv->basis_index & ~seg.tile_mask;      // ... the one that owns the basis index
+    } else {
+        fill_expand(a.cta_ex, seg.tile_mask | seg.common_ctrl);
+        a.cta_or = seg.common_ctrl;
+    }
     a.k = a.tile_ex.m;
     int lc = 0;
     while (lc < a.k && a.tile_ex.pos[lc] == lc) ++lc;  // contiguous low run of the tile
@@ -442,13 +467,19 @@ int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, co
     });
 }
 
-int launch_low6(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, bool timing, bool lazy_init) {
+int launch_low6(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, bool timing, bool lazy_init, bool owner_only = false) {
     if (n_ops > kTileMaxOps) return fail(B2SV_EINVAL, "low-qubit sweep with %d ops (max %d)", n_ops, kTileMaxOps);
     Low6Args a{};
     const uint64_t fixed = seg.tile_mask | seg.common_ctrl;
     if (popcount64(fixed) > kMaxFixed) return fail(B2SV_EINVAL, "block + common controls exceed %d qubits", kMaxFixed);
-    fill_expand(a.blk_ex, fixed);
-    a.blk_or = seg.common_ctrl;
+    if (owner_only) {  // just the 64-amplitude block that holds the pending basis index
+        if (sv->n > kMaxFixed) return fail(B2SV_EINVAL, "register wider than %d qubits", kMaxFixed);
+        fill_expand(a.blk_ex, low_mask(sv->n));
+        a.blk_or = sv->basis_index & ~seg.tile_mask;
+    } else {
+        fill_expand(a.blk_ex, fixed);
+        a.blk_or = seg.common_ctrl;
+    }
     a.n_blocks = 1ull << (sv->n - a.blk_ex.m);
     a.n_ops = n_ops;
     a.ops = d_ops;
@@ -595,12 +626,14 @@ int launch_perm(b2sv* sv, const Plan& plan, const Segment& seg, bool timing, int
         if (cudaKernel_t k = jit_lookup(sv, gates, jit_mode)) {
             const void* in = sv->amps;
             void* out = sv->scratch;
-            void* args[] = {(void*)&in, (void*)&out};
+            unsigned long long wmask = sv->window ? sv->win_mask : 0ull, wval = sv->window ? sv->win_value : 0ull;
+            void* args[] = {(void*)&in, (void*)&out, (void*)&wmask, (void*)&wval};
             const uint64_t blocks = sv->count / (uint64_t)(kPermThreads * 32);
             {
-                LaunchTimer lt(sv, timing, CLS_PERM_JIT, 2.0 * sv->amp_bytes * (double)sv->count);
+                LaunchTimer lt(sv, timing, CLS_PERM_JIT, (sv->window ? 1.0 : 2.0) * sv->amp_bytes * (double)sv->count);
                 CU(cudaLaunchKernel((const void*)k, dim3((unsigned)blocks), dim3(kPermThreads), args, 0, sv->stream));
             }
+            sv->window = false;  // the sweep wrote every amplitude
             std::swap(sv->amps, sv->scratch);
             return B2SV_OK;
         }
@@ -639,13 +672,15 @@ int launch_perm(b2sv* sv, const Plan& plan, const Segment& seg, bool timing, int
                 CU(cudaFuncSetAttribute(k_perm<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
                 configured = true;
             }
-            LaunchTimer lt(sv, timing, CLS_PERM, 2.0 * sv->amp_bytes * (double)sv->count);
+            LaunchTimer lt(sv, timing, CLS_PERM, (sv->window ? 1.0 : 2.0) * sv->amp_bytes * (double)sv->count);
             k_perm<A><<<(unsigned)blocks, kPermThreads, smem, sv->stream>>>((const A*)sv->amps, (A*)sv->scratch, sv->n,
-                                                                           (int)prog.size());
+                                                                           (int)prog.size(), sv->window ? sv->win_mask : 0ull,
+                                                                           sv->window ? sv->win_value : 0ull);
             return B2SV_OK;
         });
         if (rc) return rc;
         CU(cudaGetLastError());
+        sv->window = false;  // the sweep wrote every amplitude
         std::swap(sv->amps, sv->scratch);
         pos = e;
     }
@@ -825,6 +860,7 @@ int b2sv_set_basis(b2sv_t* sv, uint64_t index) {
     // lazy: the first full tile sweep of the next b2sv_apply generates the state in shared memory;
     // any other reader materialises it first
     sv->pending_basis = true;
+    sv->window = false;
     sv->basis_index = index;
     return B2SV_OK;
 }
@@ -835,6 +871,7 @@ int b2sv_set_zero(b2sv_t* sv) {
     sv->sre = 1.0;
     sv->sim = 0.0;
     sv->pending_basis = false;
+    sv->window = false;
     sv->stats.launches_by_class[CLS_INIT]++;
     CU(cudaMemsetAsync(sv->amps, 0, sv->count * sv->amp_bytes, sv->stream));
     return B2SV_OK;
@@ -850,6 +887,7 @@ int b2sv_upload(b2sv_t* sv, const void* host) {
     sv->sre = 1.0;
     sv->sim = 0.0;
     sv->pending_basis = false;
+    sv->window = false;
     if (sv->dtype == B2SV_C128) {
         CU(cudaMemcpyAsync(sv->amps, host, sv->count * 16, cudaMemcpyHostToDevice, sv->stream));
         CU(cudaStreamSynchronize(sv->stream));
@@ -1013,7 +1051,11 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
         int rc = B2SV_OK;
         // a pending basis state is generated by the first sweep if that sweep visits every tile
         const bool lazy_init = sv->pending_basis && (seg.cls == SEG_TILE || seg.cls == SEG_LOW6) && seg.common_ctrl == 0;
-        if (sv->pending_basis && !lazy_init) {
+        // ... and if a permutation sweep comes next, only the tile that owns the index is written at all: the
+        // permutation sweep reads that tile and takes zeros for everything else
+        const bool owner_only = lazy_init && s + 1 < plan.segs.size() && plan.segs[s + 1].cls == SEG_PERM && sv->n <= kMaxFixed &&
+                                !std::getenv("B2SV_NO_WINDOW");
+        if ((sv->pending_basis && !lazy_init) || (sv->window && seg.cls != SEG_PERM)) {
             rc = materialise(sv);
             if (rc) return rc;
         }
@@ -1025,16 +1067,22 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
         } else if (seg.cls == SEG_TILE) {
             bool fused_ops = false;
             for (int gi : seg.gates) fused_ops |= plan.gates[gi].op == B2SV_OP_MUX || plan.gates[gi].op == B2SV_OP_BLOCK;
-            rc = launch_tile(sv, seg, (const TileOp*)sv->d_ops + seg_first[s], sv->plan_seg_nops[s], cfg, tile_io, fused_ops, timing, lazy_init);
+            rc = launch_tile(sv, seg, (const TileOp*)sv->d_ops + seg_first[s], sv->plan_seg_nops[s], cfg, tile_io, fused_ops, timing, lazy_init,
+                             owner_only);
             if (lazy_init) sv->pending_basis = false;
         } else if (seg.cls == SEG_LOW6) {
-            rc = launch_low6(sv, seg, (const TileOp*)sv->d_ops + seg_first[s], sv->plan_seg_nops[s], timing, lazy_init);
+            rc = launch_low6(sv, seg, (const TileOp*)sv->d_ops + seg_first[s], sv->plan_seg_nops[s], timing, lazy_init, owner_only);
             if (lazy_init) sv->pending_basis = false;
         } else {
             rc = launch_perm(sv, plan, seg, timing, jit_mode);
         }
         if (rc) return rc;
         CU(cudaGetLastError());
+        if (owner_only) {
+            sv->window = true;
+            sv->win_mask = low_mask(sv->n) & ~seg.tile_mask;
+            sv->win_value = sv->basis_index & ~seg.tile_mask;
+        }
     }
     CU(cudaEventRecord(ev_b, sv->stream));
     sv->apply_events.push_back({ev_a, ev_b});
@@ -1137,6 +1185,7 @@ int b2sv_embed(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, in
     if (dim) CU(cudaMemcpyAsync(d_in, host_in, dim * 16, cudaMemcpyHostToDevice, sv->stream));
     // the register is overwritten: nothing pending survives
     sv->pending_basis = false;
+    sv->window = false;
     sv->sre = 1.0;
     sv->sim = 0.0;
     dispatch_dtype(sv, [&](auto* tag) -> int {

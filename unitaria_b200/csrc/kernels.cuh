@@ -1238,7 +1238,8 @@ __device__ __forceinline__ void transpose32(uint32_t (&a)[32]) {
 }
 
 template <typename A>
-__global__ void __launch_bounds__(kPermThreads) k_perm(const A* __restrict__ in, A* __restrict__ out, int n, int n_ops) {
+__global__ void __launch_bounds__(kPermThreads) k_perm(const A* __restrict__ in, A* __restrict__ out, int n, int n_ops,
+                                                       uint64_t win_mask, uint64_t win_value) {
     extern __shared__ __align__(16) uint32_t W[];  // (n + 1 + kPermTemps) rows of kPermThreads words
     const int tid = threadIdx.x, lane = tid & 31;
     const uint64_t warp_global = (uint64_t)blockIdx.x * (kPermThreads / 32) + (tid >> 5);
@@ -1280,9 +1281,12 @@ __global__ void __launch_bounds__(kPermThreads) k_perm(const A* __restrict__ in,
 #pragma unroll
             for (int u = 0; u < 8; ++u) src[u] |= (uint64_t)((w >> u) & 1u) << q;
         }
+        // live window (win_mask != 0): the input is known to be zero outside {i : (i & win_mask) == win_value}
+        // (a basis state that has only been through one tile so far) and is not even materialised there
         A v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = in[src[u]];
+        for (int u = 0; u < 8; ++u)
+            v[u] = ((src[u] & win_mask) == win_value) ? in[src[u]] : from_c128<A>(make_double2(0.0, 0.0));
 #pragma unroll
         for (int u = 0; u < 8; ++u) out[warp_base + (uint64_t)(b0 + u) * 32 + lane] = v[u];
     }
@@ -1429,6 +1433,16 @@ __global__ void __launch_bounds__(kThreads) k_set_basis(A* __restrict__ psi, uin
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
         psi[i] = from_c128<A>(make_double2(i == index ? 1.0 : 0.0, 0.0));
+}
+
+// Zero everything outside the live window {i : (i & mask) == value} (see b2sv.cu: a basis state that was only
+// ever touched inside one tile is kept as "that tile + implied zeros" until somebody needs the whole state).
+template <typename A>
+__global__ void __launch_bounds__(kThreads) k_window_fill(A* __restrict__ psi, uint64_t count, uint64_t mask, uint64_t value) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const A zero = from_c128<A>(make_double2(0.0, 0.0));
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        if ((i & mask) != value) psi[i] = zero;
 }
 
 template <typename A>

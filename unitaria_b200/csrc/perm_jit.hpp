@@ -28,7 +28,7 @@ inline std::string perm_jit_source(const std::vector<PGate>& exec_order, int n, 
     s.reserve(exec_order.size() * 40 + 8192);
     char buf[256];
     s += dtype == B2SV_C64 ? "typedef float2 amp_t;\n" : "typedef double2 amp_t;\n";
-    s += "extern \"C\" __global__ void __launch_bounds__(256) b2sv_perm_jit(const amp_t* __restrict__ in, amp_t* __restrict__ out) {\n";
+    s += "extern \"C\" __global__ void __launch_bounds__(256) b2sv_perm_jit(const amp_t* __restrict__ in, amp_t* __restrict__ out, unsigned long long win_mask, unsigned long long win_value) {\n";
     s += "  const unsigned tid = threadIdx.x, lane = tid & 31u;\n";
     s += "  const unsigned long long wg = (unsigned long long)blockIdx.x * 8ull + (tid >> 5);\n";
     s += "  const unsigned long long warp_base = wg << 10;\n";
@@ -86,9 +86,11 @@ inline std::string perm_jit_source(const std::vector<PGate>& exec_order, int n, 
                  "    #pragma unroll\n    for (int u = 0; u < 8; ++u) src[u] |= (unsigned long long)((w%d >> (b0 + u)) & 1u) << %d;\n", q, q);
         s += buf;
     }
+    // live window: see k_perm (win_mask == 0: every source is read)
     s += "    amp_t v[8];\n"
+         "    amp_t zero; zero.x = 0; zero.y = 0;\n"
          "    #pragma unroll\n"
-         "    for (int u = 0; u < 8; ++u) v[u] = in[src[u]];\n"
+         "    for (int u = 0; u < 8; ++u) v[u] = ((src[u] & win_mask) == win_value) ? in[src[u]] : zero;\n"
          "    #pragma unroll\n"
          "    for (int u = 0; u < 8; ++u) out[warp_base + (unsigned long long)(b0 + u) * 32ull + lane] = v[u];\n"
          "  }\n"
