@@ -263,8 +263,11 @@ def run_single(args):
     if prog_in.total_qubits <= 24:
         basis_in = sv.enumerate_basis(prog_in)
         inputs = [int(basis_in[i]) for i in rng.integers(0, len(basis_in), size=n_inputs)]
-    else:  # subspace_in of the big configs is "0..0#..#": any index below its dimension is a member
-        inputs = [int(i) for i in rng.integers(0, min(prog_in.dimension, 2**prog_in.total_qubits), size=n_inputs)]
+    else:  # big input subspaces: members by rank (the inverse of the device's rank computation), no enumeration
+        from unitaria_b200.subspace_prog import spec_member, to_spec
+
+        spec_in = to_spec(case.meta["subspace_in"])
+        inputs = [spec_member(spec_in, int(r)) for r in rng.integers(0, prog_in.dimension, size=n_inputs)]
 
     def step(j):
         sv.set_basis(j)

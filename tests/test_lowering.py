@@ -131,6 +131,18 @@ def test_subspace_program_reproduces_enumerate_basis_order(name, which):
     assert [got[r] for r in range(len(want))] == list(want)
 
 
+@pytest.mark.parametrize("name", ["laplace_n3", "laplace_readme_n8", "bpx_L3", "bpx_L2", "pinv_bpx_L2", "gaussian_s3_t4", "cfg5_bits5"])
+@pytest.mark.parametrize("which", ["subspace_in", "subspace_out"])
+def test_spec_member_is_enumerate_basis_by_rank(name, which):
+    from unitaria_b200.subspace_prog import spec_member
+
+    spec = to_spec(load_golden(name).meta[which])
+    want = np_oracle.enumerate_basis(spec)
+    assert [spec_member(spec, r) for r in range(len(want))] == list(want)
+    with pytest.raises(IndexError):
+        spec_member(spec, len(want))
+
+
 def test_subspace_string_form():
     # subspace.py:114-125: leftmost character is the most significant qubit
     assert to_spec("0#") == [[[], []], 0]

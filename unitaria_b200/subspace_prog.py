@@ -60,6 +60,28 @@ def spec_dimension(spec) -> int:
     return d
 
 
+def spec_member(spec, rank: int) -> int:
+    """The ``rank``-th member of the subspace in ``enumerate_basis`` order (ascending index,
+    subspace.py:325-329), without enumerating: the rank is a mixed-radix number over the factors, factor 0
+    least significant; the inverse of the rank the device programs compute."""
+    index, pos = 0, 0
+    for f in spec:
+        if f == 0:
+            pos += 1
+            continue
+        d0, d1 = spec_dimension(f[0]), spec_dimension(f[1])
+        rank, r = divmod(rank, d0 + d1)
+        width = spec_total_qubits(f[0])
+        if r < d0:
+            index |= spec_member(f[0], r) << pos
+        else:
+            index |= (spec_member(f[1], r - d0) | (1 << width)) << pos
+        pos += width + 1
+    if rank:
+        raise IndexError("rank outside the subspace dimension")
+    return index
+
+
 class SubspaceProgram:
     """Compiled subspace: ``instrs`` (SUBINSTR_DTYPE), ``entry``, ``total_qubits``, ``dimension``.
 
