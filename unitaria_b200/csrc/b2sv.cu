@@ -697,6 +697,7 @@ int check(const b2sv* sv) {
 // A program that starts with FREE on the bits [0, len): aligned groups of up to 2^len amplitudes are members
 // together, so the projection kernels walk the program once per group.
 constexpr int kProjectGroupBits = 3;
+static_assert((1 << kProjectGroupBits) == kProjectGroup, "group size");
 int low_free_bits(const b2sv_subinstr* prog, int entry) {
     const b2sv_subinstr& in = prog[entry];
     return (in.op == B2SV_SUB_FREE && in.pos == 0) ? in.len : 0;
@@ -1108,17 +1109,17 @@ int b2sv_project_norm2_at(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, in
     }
     if (count_bits > sv->n) count_bits = sv->n;
     const uint64_t cnt = 1ull << count_bits;
-    const bool grouped = low_free_bits(prog, entry) >= kProjectGroupBits && cnt >= (1ull << kProjectGroupBits);
+    const bool grouped = low_free_bits(prog, entry) >= kProjectGroupBits && cnt >= (uint64_t)kProjectWarpSpan;
     const int grid = grid_for(sv, grouped ? cnt >> kProjectGroupBits : cnt);
     int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
         using A = std::remove_pointer_t<decltype(tag)>;
         LaunchTimer lt(sv, sv->timing_on, CLS_PROJECT, (double)sv->amp_bytes * (double)cnt);
         if (grouped)
-            k_project_norm2<A, 1 << kProjectGroupBits><<<grid, kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1,
-                                                                                         index_base, sv->d_partial);
+            k_project_norm2<A, true><<<grid, kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, index_base,
+                                                                       sv->d_partial);
         else
-            k_project_norm2<A, 1><<<grid, kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, index_base,
-                                                                    sv->d_partial);
+            k_project_norm2<A, false><<<grid, kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, index_base,
+                                                                        sv->d_partial);
         k_reduce_partials<<<1, kThreads, 0, sv->stream>>>(sv->d_partial, grid, sv->d_partial + sv->n_partial);
         sv->stats.launches++;  // the reduction is a launch too
         sv->stats.launches_by_class[CLS_PROJECT]++;
@@ -1157,12 +1158,12 @@ int b2sv_project_gather(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int 
     dispatch_dtype(sv, [&](auto* tag) -> int {
         using A = std::remove_pointer_t<decltype(tag)>;
         LaunchTimer lt(sv, sv->timing_on, CLS_PROJECT, (double)sv->amp_bytes * (double)cnt + 16.0 * (double)dim);
-        if (low_free_bits(prog, entry) >= kProjectGroupBits && cnt >= (1ull << kProjectGroupBits))
-            k_project_gather<A, 1 << kProjectGroupBits><<<grid_for(sv, cnt >> kProjectGroupBits), kThreads, 0, sv->stream>>>(
+        if (low_free_bits(prog, entry) >= kProjectGroupBits && cnt >= (uint64_t)kProjectWarpSpan)
+            k_project_gather<A, true><<<grid_for(sv, cnt >> kProjectGroupBits), kThreads, 0, sv->stream>>>(
                 (const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, s, d_out, dim, prog[entry].weight);
         else
-            k_project_gather<A, 1><<<grid_for(sv, cnt), kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, s,
-                                                                                 d_out, dim, 0);
+            k_project_gather<A, false><<<grid_for(sv, cnt), kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1,
+                                                                                     s, d_out, dim, 0);
         return B2SV_OK;
     });
     cudaError_t e = cudaGetLastError();

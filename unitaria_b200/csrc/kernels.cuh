@@ -1333,25 +1333,46 @@ __device__ __forceinline__ bool sub_member_rank(const b2sv_subinstr* __restrict_
     return false;
 }
 
-// G > 1: the program starts with a FREE instruction on the low bits [0, len >= log2 G), so the G amplitudes of
+// GROUPED: the program starts with a FREE instruction on the low bits [0, len >= 3), so the 8 amplitudes of
 // an aligned group are members together (and their ranks are consecutive multiples of that instruction's
 // weight): the decision program is walked once per group instead of once per amplitude -- for the
 // "0..0#..#" subspaces of block encodings the walk, not the memory, was the bound (ncu: 17 % DRAM, 68 % SM).
-template <typename A, int G>
+// A warp takes 256 consecutive amplitudes: lane l walks group l, the verdicts are exchanged by ballot /
+// shuffle, and the loads stay fully coalesced (lane l reads amplitude j*32 + l in step j).
+constexpr int kProjectGroup = 8;        // amplitudes per group
+constexpr int kProjectWarpSpan = 256;   // amplitudes a warp handles per iteration (32 groups)
+
+template <typename A, bool GROUPED>
 __global__ void __launch_bounds__(kThreads) k_project_norm2(const A* __restrict__ psi, const b2sv_subinstr* __restrict__ sub,
                                                             uint64_t count, int entry, int max_steps, uint64_t index_base,
                                                             double* __restrict__ partial) {
     double acc = 0.0;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g * G < count; g += stride) {
-        const uint64_t i = g * G;
-        uint64_t r;
-        if (sub_member_rank(sub, entry, max_steps, index_base | i, r)) {
-            double2 v[G];
+    if (GROUPED) {
+        const int lane = threadIdx.x & 31;
+        const uint64_t warps = (uint64_t)gridDim.x * (kThreads / 32);
+        for (uint64_t w = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); w * kProjectWarpSpan < count; w += warps) {
+            const uint64_t base = w * kProjectWarpSpan;  // count is a multiple of kProjectWarpSpan
+            uint64_t r;
+            const bool mine = sub_member_rank(sub, entry, max_steps, index_base | (base + (uint64_t)lane * kProjectGroup), r);
+            const uint32_t members = __ballot_sync(0xffffffffu, mine);
+            if (members == 0u) continue;  // warp-uniform
+            double2 v[8];
 #pragma unroll
-            for (int j = 0; j < G; ++j) v[j] = to_c128(psi[i + j]);
+            for (int j = 0; j < 8; ++j) {
+                const int group = j * 4 + (lane >> 3);
+                v[j] = ((members >> group) & 1u) ? to_c128(psi[base + (uint64_t)(j * 32 + lane)]) : make_double2(0.0, 0.0);
+            }
 #pragma unroll
-            for (int j = 0; j < G; ++j) acc = fma(v[j].x, v[j].x, fma(v[j].y, v[j].y, acc));
+            for (int j = 0; j < 8; ++j) acc = fma(v[j].x, v[j].x, fma(v[j].y, v[j].y, acc));
+        }
+    } else {
+        const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+            uint64_t r;
+            if (sub_member_rank(sub, entry, max_steps, index_base | i, r)) {
+                const double2 v = to_c128(psi[i]);
+                acc = fma(v.x, v.x, fma(v.y, v.y, acc));
+            }
         }
     }
     __shared__ double red[kThreads / 32];
@@ -1379,21 +1400,35 @@ __global__ void __launch_bounds__(kThreads) k_reduce_partials(const double* __re
     if (threadIdx.x == 0) *out = red[0];
 }
 
-template <typename A, int G>
+template <typename A, bool GROUPED>
 __global__ void __launch_bounds__(kThreads) k_project_gather(const A* __restrict__ psi, const b2sv_subinstr* __restrict__ sub,
                                                              uint64_t count, int entry, int max_steps,
                                                              double2 scale, double2* __restrict__ out, uint64_t dim, uint64_t weight) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g * G < count; g += stride) {
-        const uint64_t i = g * G;
-        uint64_t r;
-        if (sub_member_rank(sub, entry, max_steps, i, r)) {
-            double2 v[G];
+    if (GROUPED) {
+        const int lane = threadIdx.x & 31;
+        const uint64_t warps = (uint64_t)gridDim.x * (kThreads / 32);
+        for (uint64_t w = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); w * kProjectWarpSpan < count; w += warps) {
+            const uint64_t base = w * kProjectWarpSpan;
+            uint64_t r = 0;
+            const bool mine = sub_member_rank(sub, entry, max_steps, base + (uint64_t)lane * kProjectGroup, r);
+            const uint32_t members = __ballot_sync(0xffffffffu, mine);
+            if (members == 0u) continue;  // warp-uniform
 #pragma unroll
-            for (int j = 0; j < G; ++j) v[j] = to_c128(psi[i + j]);
-#pragma unroll
-            for (int j = 0; j < G; ++j)
-                if (r + j * weight < dim) out[r + j * weight] = cmul(scale, v[j]);
+            for (int j = 0; j < 8; ++j) {
+                const int group = j * 4 + (lane >> 3);
+                // rank of the group's first amplitude, from the lane that walked it
+                const unsigned long long rg = __shfl_sync(0xffffffffu, (unsigned long long)r, group);
+                if ((members >> group) & 1u) {
+                    const uint64_t rr = rg + (uint64_t)(lane & 7) * weight;
+                    if (rr < dim) out[rr] = cmul(scale, to_c128(psi[base + (uint64_t)(j * 32 + lane)]));
+                }
+            }
+        }
+    } else {
+        const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+            uint64_t r;
+            if (sub_member_rank(sub, entry, max_steps, i, r) && r < dim) out[r] = cmul(scale, to_c128(psi[i]));
         }
     }
 }
