@@ -316,9 +316,10 @@ def run_single(args):
         "ms_per_launch": per_launch_ms,
         "launches": launches,
         "traffic": recorded_traffic(cls),
-        "note": "per launch = mean over the launches of the step; the first tile sweep after set_basis generates the "
-        "basis state in shared memory and only WRITES the state (algorithmic bytes 1*B*2^n, counted as such), and "
-        "write-only traffic runs above the read+write copy peak, which is how the mean can sit slightly above 1.0",
+        "note": "per launch = total algorithmic bytes / total device time over the launches of the step.  After set_basis the "
+        "first sweep runs only on the tile that owns the basis index when a permutation sweep follows (live window: 64 KiB, "
+        "and that permutation sweep is write-only: 1*B*2^n), or generates the basis state in shared memory and only WRITES "
+        "the state otherwise (1*B*2^n, counted as such); write-only traffic runs above the read+write copy peak",
     }
     kernels = {}
     for c in ("tile", "low6", "perm", "perm_jit", "gate1q", "project", "init", "scale"):
