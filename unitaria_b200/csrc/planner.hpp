@@ -92,16 +92,6 @@ struct PlanConfig {
                                           // run on the host, the device pays per phase, not per gate
 };
 
-// Tunable for experiments through B2SV_MONO_COST.
-inline double mono_gate_cost_default() {
-    static const double v = [] {
-        const char* e = std::getenv("B2SV_MONO_COST");
-        const double x = e ? std::atof(e) : 0.0;
-        return x > 0.0 ? x : 0.001;
-    }();
-    return v;
-}
-
 // A run of consecutive gates on ONE target whose other qubits are only controls multiplies out to
 // sum_c |c><c| (x) M_c: one 2x2 matrix per value c of the union of the control qubits.  This is what
 // Moettoenen state preparation emits (circuits/multiplexed_rot.py:8-77: Ry/Rz interleaved with CNOTs
@@ -140,7 +130,6 @@ inline PlanConfig default_config(int n, int dtype, const b2sv_plan_opts* o) {
     PlanConfig c;
     c.n = n;
     c.amp_bytes = dtype == B2SV_C64 ? 8 : 16;
-    c.mono_gate_cost = mono_gate_cost_default();
     c.tile_qubits = dtype == B2SV_C64 ? 13 : 12;  // 64 KiB of shared memory either way
     // low qubits every tile contains, i.e. the contiguous run one TMA box moves: 256 bytes.  Measured on
     // B200: sweeps stream at the same rate with 256 B .. 2 KiB runs (cfg 2: 7.08 vs 7.14 ms), while every
