@@ -4,7 +4,8 @@
 //
 //   make_tile_op         one planned gate -> one TileOp (targets / controls as tile-local positions)
 //   append_with_phases   groups consecutive ops into register phases (<= 3 target qubits, any plain
-//                        gate) and monomial phases (X / SWAP / PHASE / DIAG1 on up to 11 target qubits)
+//                        gate) and monomial phases (X / SWAP / PHASE / DIAG1 touching up to 11 tile qubits;
+//                        their index walks are done here, on the host: mono_build_table)
 //   layout_batches       pads the program so that no phase straddles a kTileMaxOps batch boundary
 #pragma once
 
@@ -100,7 +101,7 @@ inline TileOp make_tile_op(const Plan& plan, const PGate& g, uint64_t tile_mask,
 }
 
 constexpr int kPhaseMaxMembers = kTileMaxOps - 1; // header + members fit one staged batch
-constexpr size_t kMonoMaxTableBytes = 256 * 1024; // per table-driven phase
+constexpr size_t kMonoMaxTableBytes = 256 * 1024; // walk results of one monomial phase
 
 // Host side of a monomial phase: walk every (thread, walk) index of the phase through the
 // members, once per value of the `ebits` outside qubits the members test (beyond the sweep's common
@@ -195,7 +196,8 @@ inline void mono_build_table(const TileOp* members, size_t count, int k, uint32_
 //   monomial phase: maximal run of consecutive X / SWAP / PHASE / DIAG1 gates touching (as target or tile-local
 //                   control) at most 11 tile positions (10 with phase factors) -- the index walks are done here,
 //                   on the host (mono_build_table); the device fetches their results and moves the amplitudes.
-// At every position the kind that swallows more gates wins.
+// At every position the kind that swallows more gates wins; a monomial phase of 16 or more gates always does
+// (its cost does not grow with the run, a register phase pays per gate).
 // `common`: the sweep's common outside controls (set in every launched tile); `tables`: where monomial
 // phases put their walk results (Plan::mux_tables).
 inline void append_with_phases(const std::vector<TileOp>& ops, int k, bool enable, bool mono, uint64_t common,
