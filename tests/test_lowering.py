@@ -143,6 +143,15 @@ def test_spec_member_is_enumerate_basis_by_rank(name, which):
         spec_member(spec, len(want))
 
 
+def test_index_window_subspaces_are_recognised():
+    for text, want in [("00###", True), ("###", True), ("000", True), ("0#0", False), ("#0", False), ("##0", False)]:
+        prog = SubspaceProgram(text)
+        assert prog.is_index_window is want, text
+        if want:
+            assert list(np_oracle.enumerate_basis(to_spec(text))) == list(range(prog.dimension))
+    assert SubspaceProgram(load_golden("laplace_readme_n8").meta["subspace_out"]).is_index_window is False
+
+
 def test_subspace_string_form():
     # subspace.py:114-125: leftmost character is the most significant qubit
     assert to_spec("0#") == [[[], []], 0]

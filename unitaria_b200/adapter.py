@@ -129,6 +129,8 @@ _BASIS: dict = {}
 
 def _basis_indices(prog: SubspaceProgram) -> np.ndarray:
     """``Subspace.enumerate_basis()`` of a compiled subspace, enumerated on the device once and kept."""
+    if prog.is_index_window:  # "0..0#..#": no register, no enumeration
+        return np.arange(prog.dimension, dtype=np.int64)
     key = (prog.instrs.tobytes(), prog.entry)
     hit = _BASIS.get(key)
     if hit is None:
@@ -159,8 +161,9 @@ def block_encoding_compute(tq_circuit, n_qubits: int, subspace_in, subspace_out,
             sv.embed(prog_in, vec)
             sv.apply_lowered(_lowered(tq_circuit, n_qubits), _DEFAULTS["opts"])
             out = sv.project(prog_out, scale=normalization)
-        # the reference projects the already projected vector once more (block_encoding.py:54)
-        return out[_basis_indices(prog_out)]
+        # the reference projects the already projected vector once more (block_encoding.py:54): the identity
+        # for "0..0#..#" subspaces, a fancy index (or the reference's IndexError) otherwise
+        return out if prog_out.is_index_window else out[_basis_indices(prog_out)]
 
     if input.ndim == 1:
         return one(input)

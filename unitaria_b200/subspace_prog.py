@@ -96,6 +96,11 @@ class SubspaceProgram:
         self.dimension = spec_dimension(self.spec)
         if self.total_qubits > 64:
             raise ValueError("subspaces wider than 64 qubits are not supported")
+        # "0..0#..#" (free qubits below, zero qubits above): the members are exactly 0 .. dimension-1, so
+        # enumerate_basis() is arange(dimension) and projecting a length-dimension vector again is the identity
+        free = [f != 0 and f == [[], []] for f in self.spec]
+        n_free = sum(free)
+        self.is_index_window = all(free[:n_free]) and all(f == 0 for f in self.spec[n_free:])
         self._ins: list = [dict(op=SUB_END, pos=0, len=0, next0=0, next1=0, weight=0, add=0)]
         self.entry = self._emit_list(self.spec, 0, 1, 0)
         if len(self._ins) > 65535:
