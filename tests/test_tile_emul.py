@@ -127,3 +127,32 @@ def test_goldens_through_the_tile_programs(emul, name):
     want = np_oracle.simulate_gates(live, n, psi0)
     got, info = emul(case.gates, n, psi0)
     assert np.abs(got - want).max() < 1e-12, info
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_fuzz_random_shapes(emul, block):
+    """Random sizes, tile widths, control counts, look-ahead windows and gate mixes (with and without targets
+    confined to a few qubits, which is what makes long compact runs): the builder must never produce a
+    program the interpreter rejects, and the result must match the oracle."""
+    mixes = [
+        ["X"] * 8 + ["CNOT"] * 3 + ["Toffoli"] * 3 + ["SWAP"] * 3 + ["Phase", "GlobalPhase", "Z", "Zp", "Rz"] * 2 + ["Ry", "H"],
+        ["X", "CNOT", "Toffoli", "SWAP", "Phase", "Rz", "GlobalPhase", "Z"],
+        ["X", "SWAP", "Rz", "Phase"] * 3 + ["Ry"],
+        None,
+    ]
+    for seed in range(10 * block, 10 * block + 10):
+        rng = np.random.default_rng(1000 + seed)
+        n = int(rng.integers(11, 16))
+        tile_qubits = int(rng.choice([0, 11, 12, 13])) if n >= 13 else 0
+        dtype = cabi.B2SV_C64 if rng.integers(0, 2) else cabi.B2SV_C128
+        circuit = random_circuit(n, int(rng.integers(50, 500)), rng, kinds=mixes[int(rng.integers(0, 4))], max_controls=int(rng.integers(1, 7)))
+        gates = [g for g in circuit.gates if g.name != "I"]
+        if rng.integers(0, 2):
+            limit = int(rng.integers(6, n))
+            gates = [g for g in gates if all(t < limit for t in g.target)]
+        if not gates:
+            continue
+        psi0 = random_state(n, rng)
+        want = np_oracle.simulate_gates(gates, n, psi0)
+        got, _ = emul(gates, n, psi0, dtype=dtype, tile_qubits=tile_qubits, perm_runs=bool(rng.integers(0, 2)), lookahead=int(rng.choice([0, 4, 32])))
+        assert np.abs(got - want).max() < 1e-11, seed
