@@ -27,6 +27,8 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <string>
 #include <vector>
 
 #include "../../include/b2sv.h"
@@ -113,7 +115,15 @@ struct BlockInfo {
     std::vector<int> sources;
 };
 
+// walk results of a monomial phase already in Plan::mux_tables (block-encoding circuits repeat the same
+// arithmetic dozens of times: QSVT steps, LCU terms), keyed by everything the results depend on
+struct MonoTableRef {
+    uint64_t mask_off = 0, fac_off = 0;
+    uint32_t identity = 0;
+};
+
 struct Plan {
+    std::map<std::string, MonoTableRef> mono_tables;
     std::vector<BlockInfo> blocks;
     std::vector<MuxInfo> mux;
     std::vector<double> mux_tables;

@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
+#include <string>
 #include <vector>
 
 #include "kernels.cuh"
@@ -201,7 +203,8 @@ inline void mono_build_table(const TileOp* members, size_t count, int k, uint32_
 // `common`: the sweep's common outside controls (set in every launched tile); `tables`: where monomial
 // phases put their walk results (Plan::mux_tables).
 inline void append_with_phases(const std::vector<TileOp>& ops, int k, bool enable, bool mono, uint64_t common,
-                               std::vector<double>* tables, std::vector<TileOp>& out) {
+                               std::vector<double>* tables, std::vector<TileOp>& out,
+                               std::map<std::string, MonoTableRef>* table_cache = nullptr) {
     auto plain = [](const TileOp& o) {
         return o.op == B2SV_OP_MAT1 || o.op == B2SV_OP_DIAG1 || o.op == B2SV_OP_X || o.op == B2SV_OP_SWAP || o.op == B2SV_OP_PHASE;
     };
@@ -308,18 +311,48 @@ inline void append_with_phases(const std::vector<TileOp>& ops, int k, bool enabl
             for (int q = 0; q < 64; ++q)
                 if ((EX >> q) & 1) h.mono.epos[ne++] = (uint8_t)q;
             h.mono.ebits = (uint8_t)ne;
-            std::vector<uint16_t> masks;
-            std::vector<double> factors;
-            mono_build_table(&ops[i], jm - i, k, tmask, qlmask, 1 << h.mono.vbits, fac, common, h.mono.epos, ne, masks, factors,
-                             h.mono.identity);
-            while (tables->size() % 2) tables->push_back(0.0);  // offsets count 16-byte units
-            h.mono.mask_off = tables->size() / 2;
-            const size_t mask_doubles = (masks.size() * sizeof(uint16_t) + 15) / 16 * 2;
-            tables->resize(tables->size() + mask_doubles, 0.0);
-            std::memcpy(reinterpret_cast<char*>(tables->data()) + h.mono.mask_off * 16, masks.data(), masks.size() * sizeof(uint16_t));
-            if (fac) {
-                h.mono.fac_off = tables->size() / 2;
-                tables->insert(tables->end(), factors.begin(), factors.end());
+            // the same run under the same tile layout has been walked before (QSVT steps, LCU terms repeat their
+            // arithmetic verbatim): share its tables
+            std::string key;
+            if (table_cache) {
+                key.reserve((jm - i) * 56 + 32);
+                auto put = [&](const void* p, size_t nbytes) { key.append(reinterpret_cast<const char*>(p), nbytes); };
+                put(&k, sizeof(k));
+                put(&tmask, sizeof(tmask));
+                put(&qlmask, sizeof(qlmask));
+                put(&common, sizeof(common));
+                for (size_t q = i; q < jm; ++q) {
+                    const TileOp& o = ops[q];
+                    put(&o.op, 1);
+                    put(&o.tpos, 1);
+                    put(&o.tpos2, 1);
+                    put(&o.lctrl, sizeof(o.lctrl));
+                    put(&o.ext_ctrl, sizeof(o.ext_ctrl));
+                    put(&o.ext_tbit, sizeof(o.ext_tbit));
+                    if (o.op == B2SV_OP_PHASE || o.op == B2SV_OP_DIAG1) put(o.m, 4 * sizeof(double));
+                }
+            }
+            const auto hit = table_cache ? table_cache->find(key) : decltype(table_cache->end())();
+            if (table_cache && hit != table_cache->end()) {
+                h.mono.mask_off = hit->second.mask_off;
+                h.mono.fac_off = hit->second.fac_off;
+                h.mono.identity = hit->second.identity;
+            } else {
+                std::vector<uint16_t> masks;
+                std::vector<double> factors;
+                mono_build_table(&ops[i], jm - i, k, tmask, qlmask, 1 << h.mono.vbits, fac, common, h.mono.epos, ne, masks, factors,
+                                 h.mono.identity);
+                while (tables->size() % 2) tables->push_back(0.0);  // offsets count 16-byte units
+                h.mono.mask_off = tables->size() / 2;
+                const size_t mask_doubles = (masks.size() * sizeof(uint16_t) + 15) / 16 * 2;
+                tables->resize(tables->size() + mask_doubles, 0.0);
+                std::memcpy(reinterpret_cast<char*>(tables->data()) + h.mono.mask_off * 16, masks.data(),
+                            masks.size() * sizeof(uint16_t));
+                if (fac) {
+                    h.mono.fac_off = tables->size() / 2;
+                    tables->insert(tables->end(), factors.begin(), factors.end());
+                }
+                if (table_cache) (*table_cache)[key] = MonoTableRef{h.mono.mask_off, h.mono.fac_off, h.mono.identity};
             }
             out.push_back(h);
             i = jm;
@@ -384,7 +417,7 @@ inline void build_segment_ops(Plan& plan, const Segment& seg, const PlanConfig& 
     seg_ops.reserve(seg.gates.size());
     for (int gi : seg.gates) seg_ops.push_back(make_tile_op(plan, plan.gates[gi], seg.tile_mask, ex));
     const bool tile = seg.cls == SEG_TILE;
-    append_with_phases(seg_ops, ex.m, cfg.phases && tile, cfg.mono && tile, seg.common_ctrl, &plan.mux_tables, grouped);
+    append_with_phases(seg_ops, ex.m, cfg.phases && tile, cfg.mono && tile, seg.common_ctrl, &plan.mux_tables, grouped, &plan.mono_tables);
     if (tile) layout_batches(grouped, out);
     else out.insert(out.end(), grouped.begin(), grouped.end());
 }
