@@ -123,35 +123,61 @@ class ClockSampler:
 
 
 class CpuState:
-    """The CPU port's full-width complex128 register, allocated once (8 GiB for 29 qubits)."""
+    """The CPU port's complex128 register, allocated once.  The sample runs on the FULL register when it has at
+    most ``max_qubits`` qubits (29 qubits = 8 GiB for config 2) and on a ``max_qubits``-qubit register otherwise:
+    one in-place sweep per gate costs time proportional to the amplitudes it visits, so the full-size rate is the
+    sampled rate times 2^(sample qubits - full qubits) -- stated in the line's ``sample`` text."""
 
-    def __init__(self, case):
+    def __init__(self, case, max_qubits=30):
         from oracle import c_oracle
 
-        self.n = max(1, case.n_qubits)
-        while True:
-            try:
-                self.psi = np.empty(2**self.n, dtype=np.complex128)
-                break
-            except MemoryError:
-                self.n -= 1  # host RAM too small for the full register: shrink and say so
+        self.n_full = max(1, case.n_qubits)
+        self.n = min(self.n_full, max_qubits)
+        try:
+            import psutil
+
+            avail = psutil.virtual_memory().available
+            while self.n > 20 and (16 << self.n) > 0.6 * avail:
+                self.n -= 1
+        except Exception:
+            pass
+        self.psi = np.zeros(2**self.n, dtype=np.complex128)  # zeros: touches every page now, not inside the timing
         c_oracle.lib().orc_set_basis(self.psi.ctypes.data, self.n, 0)
         live = [g for g in case.gates if g.name.upper() != "I"]
         self.live = len(live)
-        self.keep = [g for g in live if all(q < self.n for q in tuple(g.target) + tuple(g.control))]
+        # gates that do not fit the sampled register are re-homed on it (same control count, same sweep size)
+        shift = self.n_full - self.n
+        self.keep = live if shift == 0 else [_fold_gate(g, self.n) for g in live]
+        self.scale = 2.0 ** (self.n - self.n_full)
 
 
-def cpu_sample(case, budget_s=20.0, stride=4, state=None):
+def _fold_gate(g, n):
+    """The same gate on qubits folded into an n-qubit register (distinct qubits stay distinct): per-gate CPU cost
+    depends on the number of controls and the register size, not on which qubits they are."""
+    from unitaria_b200.fixtures import GateRecord
+
+    qs = [int(q) for q in tuple(g.target or ()) + tuple(g.control or ())]
+    used, out = set(), {}
+    for q in qs:
+        f = q % n
+        while f in used:
+            f = (f + 1) % n
+        used.add(f)
+        out[q] = f
+    return GateRecord(g.name, tuple(out[int(t)] for t in (g.target or ())), tuple(out[int(c)] for c in (g.control or ())), g.parameter, getattr(g, "power", 1.0))
+
+
+def cpu_sample(case, budget_s=20.0, stride=4, state=None, max_qubits=30):
     """Time the CPU port on a bounded sample of the workload: every `stride`-th live gate of the
-    circuit applied to the FULL-width complex128 state (per-gate cost does not depend on the
-    amplitudes' values).  Returns gates/s over the sample."""
+    circuit applied to a complex128 state (per-gate cost does not depend on the
+    amplitudes' values).  Returns gates/s over the sample, scaled to the full register size."""
     from oracle import c_oracle
 
-    st = state or CpuState(case)
+    st = state or CpuState(case, max_qubits)
     n, psi = st.n, st.psi
     sample = st.keep[::stride]
     enc = c_oracle.encode_gates(sample)
-    c_oracle.apply_encoded(psi, n, enc[:2])  # touch pages / warm up
+    c_oracle.apply_encoded(psi, n, enc[:2])  # warm up
     done, t0 = 0, time.perf_counter()
     chunk = 8
     while done < len(enc):
@@ -160,13 +186,14 @@ def cpu_sample(case, budget_s=20.0, stride=4, state=None):
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
+    scaled = "" if st.n == st.n_full else f"; sampled on {n} qubits and scaled by 2^({n}-{st.n_full}) to the full {st.n_full}-qubit register (one sweep per gate: time ~ amplitudes visited)"
     return {
-        "value": done / dt,
+        "value": done / dt * st.scale,
         "unit": "gates/s",
         "cores": c_oracle.max_threads(),
         "kind": "port",
-        "sample": f"{done} gates (every {stride}th live gate of {st.live}) on the full {n}-qubit complex128 state, "
-        f"{dt:.1f} s; reference-algorithm CPU restatement (one OpenMP sweep per gate, no fusion), not qulacs",
+        "sample": f"{done} gates (every {stride}th live gate of {st.live}) on a {n}-qubit complex128 state, "
+        f"{dt:.1f} s; reference-algorithm CPU restatement (one OpenMP sweep per gate, no fusion), not qulacs" + scaled,
         "seconds": dt,
         "qubits": n,
     }
@@ -177,9 +204,10 @@ def run_reference_arm(args):
     if rank != 0:
         return
     case = load_workload(args.workload or workload_for(args.gpus))
-    per_step_budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
-    state = CpuState(case)
-    for _ in range(args.warmup):
+    # the whole arm stays under ~2 minutes whatever N is: at N > 1 (32-34 qubit registers) the sample runs on 30 qubits
+    per_step_budget = max(1.5, min(20.0, 100.0 / max(1, args.steps + args.warmup)))
+    state = CpuState(case, max_qubits=30)
+    for _ in range(min(args.warmup, 2)):
         cpu_sample(case, budget_s=per_step_budget / 2, state=state)
     vals, last = [], None
     t0 = time.perf_counter()
@@ -240,73 +268,114 @@ def live_gate_count(case) -> int:
     return sum(len(idx) for _c, _m, idx in segs)
 
 
-def run_single(args):
-    from unitaria_b200 import PlanOpts, StateVector, SubspaceProgram, adapter, cabi, lower_gates
+KERNEL_NAMES = {
+    "tile": "k_tile_swz (fused tile sweep, TMA tensor copies)",
+    "perm": "k_perm (permutation-run sweep, generic)",
+    "perm_jit": "b2sv_perm_jit (permutation-run sweep, NVRTC-specialised)",
+    "gate1q": "k_gate1",
+    "low6": "k_low6 (low-qubit warp-shuffle sweep)",
+    "dist_perm": "b2sv_perm_dist (distributed permutation sweep: gather over peer-mapped shards)",
+}
 
-    if cabi.device_count() == 0:
-        raise SystemExit("bench.py needs a CUDA device: unitaria_b200 has no CPU fallback")
-    case = load_workload(args.workload or workload_for(1))
-    dtype = args.dtype
-    n = max(1, case.n_qubits, args.qubits or 0)  # --qubits pads the register with idle high qubits (A (x) Identity)
+
+def pick_inputs(case, sv, rng, count):
+    """Basis inputs of the encoded matrix: members of subspace_in, picked by rank."""
+    from unitaria_b200 import SubspaceProgram
+    from unitaria_b200.subspace_prog import spec_member, to_spec
+
+    prog_in = SubspaceProgram(case.meta["subspace_in"])
+    spec_in = to_spec(case.meta["subspace_in"])
+    return [spec_member(spec_in, int(r)) for r in rng.integers(0, prog_in.dimension, size=count)], prog_in
+
+
+def measure(case, dtype, n, steps, warmup, opts, dense=False, seed=0):
+    """`steps` timed steps of one workload on one GPU: load the input (a basis state |j>, or -- dense -- a seeded
+    dense vector on the input subspace's qubits, generated on the device and NOT timed), apply the whole circuit,
+    reduce the post-selected norm.  Device time by CUDA events on the engine's stream."""
+    from unitaria_b200 import StateVector, SubspaceProgram, lower_gates
+
     norm = case.meta["normalization"]
     prog = SubspaceProgram(case.meta["subspace_out"])
-    prog_in = SubspaceProgram(case.meta["subspace_in"])
     lowered = lower_gates(case.gates, n)
-    amp_bytes = 16 if dtype == "c128" else 8
-    rng = np.random.default_rng(0)
-    # permutation runs: compile the NVRTC-specialised kernel in the first warm-up step instead of in
-    # the background, so that every timed step runs the same kernels
-    opts = PlanOpts.make(timing=True, jit=args.jit, mux=not args.no_mux, phases=not args.no_phases, tile_qubits=args.tile_qubits, lookahead=args.lookahead, tile_io=args.tile_io)
-
+    rng = np.random.default_rng(seed)
+    peak, _src = measured_peak()
     sv = StateVector(n, "complex128" if dtype == "c128" else "complex64")
-    n_inputs = args.steps + args.warmup
-    if prog_in.total_qubits <= 24:
-        basis_in = sv.enumerate_basis(prog_in)
-        inputs = [int(basis_in[i]) for i in rng.integers(0, len(basis_in), size=n_inputs)]
-    else:  # big input subspaces: members by rank (the inverse of the device's rank computation), no enumeration
-        from unitaria_b200.subspace_prog import spec_member, to_spec
+    try:
+        inputs, prog_in = pick_inputs(case, sv, rng, steps + warmup)
+        support = prog_in.total_qubits
 
-        spec_in = to_spec(case.meta["subspace_in"])
-        inputs = [spec_member(spec_in, int(r)) for r in rng.integers(0, prog_in.dimension, size=n_inputs)]
+        def step(k, j, timed):
+            if dense:
+                sv.fill_random(seed=1000 + k, support_bits=support)
+            else:
+                sv.set_basis(j)
+            if timed:
+                sv.mark(2)
+            sv.apply_lowered(lowered, opts)
+            r = abs(norm) * np.sqrt(sv.project_norm2(prog))
+            if timed:
+                sv.mark(3)
+            return r
 
-    def step(j):
-        sv.set_basis(j)
-        sv.apply_lowered(lowered, opts)
-        return abs(norm) * np.sqrt(sv.project_norm2(prog))
+        for k, j in enumerate(inputs[:warmup]):
+            step(k, j, False)
+        sv.sync()
+        sv.stats_reset()
+        t_begin = time.perf_counter()
+        ms, norms = 0.0, []
+        if dense:  # the fill is not part of the step: time each step between its own marks
+            for k, j in enumerate(inputs[warmup:]):
+                norms.append(step(k, j, True))
+                ms += sv.elapsed_ms(2, 3)
+        else:
+            sv.mark(0)
+            norms = [step(k, j, False) for k, j in enumerate(inputs[warmup:])]
+            sv.mark(1)
+            sv.sync()
+            ms = sv.elapsed_ms(0, 1)
+        window = (t_begin, time.perf_counter())
+        st = sv.stats()
+    finally:
+        sv.close()
+    gates_live = st["gates_live"] // max(1, steps)
+    kernels = {}
+    for c in ("tile", "low6", "perm", "perm_jit", "gate1q", "project", "init", "scale"):
+        L = st["launches_by_class"][c]
+        if L and not (dense and c == "init"):
+            t = st["ms_by_class"][c]
+            bts = st["alg_bytes_by_class"][c]
+            kernels[c] = {
+                "launches_per_step": L / steps,
+                "ms_per_step": t / steps,
+                "alg_GBps": (bts / (t * 1e-3) / 1e9) if t > 0 else None,
+                "frac_of_peak": (bts / (t * 1e-3) / 1e9 / peak) if t > 0 else None,
+            }
+    return {
+        "ms": ms,
+        "ms_per_step": ms / steps,
+        "gates_live": int(gates_live),
+        "value": gates_live * steps / (ms * 1e-3),
+        "kernels": kernels,
+        "stats": st,
+        "norms": norms,
+        "window": window,
+        "lowered": lowered,
+        "inputs": inputs,
+        "prog": prog,
+    }
 
-    clocks = ClockSampler()
-    clocks.start()
-    for j in inputs[: args.warmup]:
-        step(j)
-    sv.stats_reset()
-    sv.sync()
-    t_begin = time.perf_counter()
-    sv.mark(0)
-    norms = [step(j) for j in inputs[args.warmup :]]
-    sv.mark(1)
-    sv.sync()
-    clocks.window = (t_begin, time.perf_counter())
-    ms = sv.elapsed_ms(0, 1)
-    st = sv.stats()
-    gates_live = st["gates_live"] // max(1, args.steps)
-    value = gates_live * args.steps / (ms * 1e-3)
 
-    # dominant kernel class by device time
+def roofline_of(m, steps, dense_note=""):
+    st = m["stats"]
     cls = max(("tile", "perm", "perm_jit", "gate1q", "low6"), key=lambda c: st["ms_by_class"][c])
     launches = st["launches_by_class"][cls]
     peak, peak_src = measured_peak()
     per_launch_bytes = st["alg_bytes_by_class"][cls] / max(1, launches)
     per_launch_ms = st["ms_by_class"][cls] / max(1, launches)
     achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
-    roofline = {
+    return {
         "bound": "hbm",
-        "kernel": {
-            "tile": "k_tile (fused tile sweep)",
-            "perm": "k_perm (permutation-run sweep, generic)",
-            "perm_jit": "b2sv_perm_jit (permutation-run sweep, NVRTC-specialised)",
-            "gate1q": "k_gate1",
-            "low6": "k_low6 (low-qubit warp-shuffle sweep)",
-        }[cls],
+        "kernel": KERNEL_NAMES[cls],
         "achieved": achieved,
         "peak": peak,
         "unit": "GB/s",
@@ -316,25 +385,78 @@ def run_single(args):
         "ms_per_launch": per_launch_ms,
         "launches": launches,
         "traffic": recorded_traffic(cls),
-        "note": "per launch = total algorithmic bytes / total device time over the launches of the step.  After set_basis the "
-        "first sweep runs only on the tile that owns the basis index when a permutation sweep follows (live window: 64 KiB, "
-        "and that permutation sweep is write-only: 1*B*2^n), or generates the basis state in shared memory and only WRITES "
-        "the state otherwise (1*B*2^n, counted as such); write-only traffic runs above the read+write copy peak",
+        "note": "per launch = total algorithmic bytes / total device time over the launches of the class in the timed steps"
+        + dense_note,
     }
-    kernels = {}
-    for c in ("tile", "low6", "perm", "perm_jit", "gate1q", "project", "init", "scale"):
-        L = st["launches_by_class"][c]
-        if L:
-            t = st["ms_by_class"][c]
-            b = st["alg_bytes_by_class"][c]
-            kernels[c] = {
-                "launches_per_step": L / args.steps,
-                "ms_per_step": t / args.steps,
-                "alg_GBps": (b / (t * 1e-3) / 1e9) if t > 0 else None,
-                "frac_of_peak": (b / (t * 1e-3) / 1e9 / peak) if t > 0 else None,
-            }
+
+
+def summarise(m, steps):
+    r = roofline_of(m, steps)
+    return {
+        "ms_per_step": m["ms_per_step"],
+        "gates_per_sec": m["value"],
+        "gates_live_per_step": m["gates_live"],
+        "steps": steps,
+        "dominant_kernel": r["kernel"],
+        "frac": r["frac"],
+        "kernels": m["kernels"],
+        "norm_first": float(m["norms"][0]),
+    }
+
+
+# BASELINE.json configs 3 and 4 next to the headline (config 2): (fixture, dtype, register qubits, steps, warm-up)
+EXTRA_CONFIGS = {
+    "cfg3_gaussian_28q_c64": ("cfg3_gaussian_s3_t21", "c64", 28, 20, 3),
+    "cfg4_bpx_L8_30q": ("cfg4_bpx_L8", "c128", 30, 5, 3),
+    "cfg4_pinv_bpx_L4_30q": ("cfg4_pinv_bpx_L4", "c128", 30, 1, 1),
+}
+
+
+def run_single(args):
+    from unitaria_b200 import PlanOpts, adapter, cabi
+
+    if cabi.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: unitaria_b200 has no CPU fallback")
+    case = load_workload(args.workload or workload_for(1))
+    dtype = args.dtype
+    n = max(1, case.n_qubits, args.qubits or 0)  # --qubits pads the register with idle high qubits (A (x) Identity)
+    norm = case.meta["normalization"]
+    # permutation runs: compile the NVRTC-specialised kernel in the first warm-up step instead of in
+    # the background, so that every timed step runs the same kernels
+    opts = PlanOpts.make(timing=True, jit=args.jit, mux=not args.no_mux, phases=not args.no_phases, tile_qubits=args.tile_qubits, lookahead=args.lookahead, tile_io=args.tile_io)
+
+    clocks = ClockSampler()
+    clocks.start()
+    m = measure(case, dtype, n, args.steps, args.warmup, opts)
+    clocks.window = m["window"]
     clk = clocks.stop()
-    sv.close()
+    st = m["stats"]
+    gates_live = m["gates_live"]
+    roofline = roofline_of(
+        m,
+        args.steps,
+        ".  After set_basis the first sweep runs only on the tile that owns the basis index when a permutation sweep follows "
+        "(live window: 64 KiB, and that permutation sweep is write-only: 1*B*2^n), or generates the basis state in shared memory and "
+        "only WRITES the state otherwise (1*B*2^n, counted as such); write-only traffic runs above the read+write copy peak.  "
+        "`inputs.dense` times the same circuit on a dense input, where every sweep reads and writes the whole register",
+    )
+    # the same workload on a seeded dense vector embedded in the input subspace's qubits: no lazy
+    # initialisation, no live window -- every sweep is a full read+write
+    inputs = {"basis": {"ms_per_step": m["ms_per_step"], "gates_per_sec": m["value"], "kernels": m["kernels"]}}
+    if not args.no_dense:
+        dsteps = max(1, min(args.steps, 10))
+        d = measure(case, dtype, n, dsteps, min(args.warmup, 3), opts, dense=True)
+        inputs["dense"] = summarise(d, dsteps)
+        inputs["dense"]["input"] = "b2sv_fill_random: seeded dense vector on the input subspace's qubits, generated on the device outside the timed region"
+    configs = {}
+    if not args.workload and not args.no_extra_configs:
+        for key, (fixture, cdtype, cn, csteps, cwarm) in EXTRA_CONFIGS.items():
+            try:
+                ccase = load_workload(fixture)
+                cm = measure(ccase, cdtype, max(cn, ccase.n_qubits), csteps, cwarm, PlanOpts.make(timing=True, jit="sync"))
+                configs[key] = summarise(cm, csteps) | {"qubits": max(cn, ccase.n_qubits), "dtype": cdtype, "tequila_gates": ccase.meta["n_gates"]}
+            except Exception as exc:  # noqa: BLE001 - an extra config must not take the headline down with it
+                configs[key] = {"error": repr(exc)}
 
     # ---- end to end through the public API with host buffers (Node.simulate(j) fast path) ----
     class Circuit:
@@ -343,11 +465,12 @@ def run_single(args):
     adapter.configure(dtype="complex128" if dtype == "c128" else "complex64", opts=PlanOpts.make(jit=args.jit))
     e2e_steps = max(1, min(args.steps, 20))
     e2e = None
+    lowered, prog, in_list = m["lowered"], m["prog"], m["inputs"]
     if not args.no_e2e:
-        for j in inputs[: min(3, len(inputs))]:  # warm: lowering cache, resident register, pinned result buffers
+        for j in in_list[: min(3, len(in_list))]:  # warm: lowering cache, resident register, pinned result buffers
             out = adapter.simulate_projected(Circuit, n, prog, norm, j)
         t0 = time.perf_counter()
-        for j in inputs[args.warmup : args.warmup + e2e_steps]:
+        for j in in_list[args.warmup : args.warmup + e2e_steps]:
             out = adapter.simulate_projected(Circuit, n, prog, norm, j)
         e2e_s = time.perf_counter() - t0
         e2e = {
@@ -360,17 +483,31 @@ def run_single(args):
             "call": "unitaria_b200.simulate_projected(circuit, n_qubits, subspace_out, normalization, j) -> host complex128[dim_out] "
             "(= Node.simulate(j)); H2D = lowered gate program, D2H = projected vector",
         }
+        # matrix case of Node.simulate (node.py:381-388): columns pipelined, the D2H of column j overlaps column j+1
+        if hasattr(adapter, "simulate_columns"):
+            cols = in_list[args.warmup : args.warmup + e2e_steps]
+            adapter.simulate_columns(Circuit, n, prog, norm, cols[:2])
+            t0 = time.perf_counter()
+            adapter.simulate_columns(Circuit, n, prog, norm, cols, keep=False)
+            pipe_s = time.perf_counter() - t0
+            e2e["pipelined_columns"] = {
+                "value": gates_live * len(cols) / pipe_s,
+                "unit": "gates/s",
+                "ms_per_column": 1e3 * pipe_s / len(cols),
+                "columns": len(cols),
+                "call": "unitaria_b200.simulate_columns(...): same host result per column, double-buffered D2H on a second stream",
+            }
     adapter.clear_caches()
 
     cpu = None if args.no_cpu_baseline else cpu_sample(case, budget_s=args.cpu_seconds)
     line = {
         "metric": "gates_per_sec",
-        "value": value,
+        "value": m["value"],
         "unit": "gates/s",
         "n_gpus": 1,
         "steps": args.steps,
         "warmup": args.warmup,
-        "ms_per_step": ms / args.steps,
+        "ms_per_step": m["ms_per_step"],
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
@@ -379,12 +516,14 @@ def run_single(args):
         "config": config_dict(case, 1, dtype),
         "gates_live_per_step": gates_live,
         "roofline": roofline,
-        "kernels": kernels,
+        "kernels": m["kernels"],
+        "inputs": inputs,
+        "configs": configs,
         "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": e2e,
         "gpu_launches": int(st["launches"]),
         "clocks": clk,
-        "check": {"norm_first": float(norms[0]), "norm_last": float(norms[-1])},
+        "check": {"norm_first": float(m["norms"][0]), "norm_last": float(m["norms"][-1])},
     }
     print(json.dumps(line), flush=True)
 
@@ -399,11 +538,13 @@ def main():
     ap.add_argument("--dtype", default="c128", choices=["c128", "c64"])
     ap.add_argument("--qubits", type=int, default=None, help="pad the register to this many qubits (idle high qubits)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-input timing of the headline workload")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip BASELINE configs 3 and 4 (cfg3 c64, BPX and Pseudoinverse(BPX) at 30 qubits)")
     ap.add_argument("--no-mux", action="store_true", help="A/B switch: disable same-target multiplexor fusion")
     ap.add_argument("--no-phases", action="store_true", help="A/B switch: disable register phases in tile sweeps")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU swap transport")
+    ap.add_argument("--exchange", default="gather", choices=["gather", "nccl"], help="multi-GPU exchange: fused gather over peer-mapped shards (default) or pack / NCCL send-recv / unpack")
     ap.add_argument("--tile-qubits", type=int, default=0)
-    ap.add_argument("--tile-io", type=int, default=0, help="0 one tile per CTA with bulk-async copies (default), 1 plain ld/st, 3 experimental persistent pipeline")
+    ap.add_argument("--tile-io", type=int, default=0, help="0 one tile per CTA with TMA tensor copies (default), 1 plain ld/st, 2 linear bulk copies")
     ap.add_argument("--lookahead", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--jit", default="sync", choices=["sync", "auto", "off"], help="permutation-run kernel specialisation")

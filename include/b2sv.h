@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B2SV_ABI_VERSION 1
+#define B2SV_ABI_VERSION 2
 
 typedef struct b2sv b2sv_t;
 
@@ -72,9 +72,8 @@ typedef struct b2sv_plan_opts {
     int32_t perm_runs;    /* 1: runs of X/SWAP gates become one index-map sweep (default); 0: off    */
     int32_t timing;       /* 1: bracket every launch with CUDA events and accumulate per-class times */
     int32_t lookahead;    /* commutation-aware lookahead window in gates; 0 = default                 */
-    int32_t tile_io;      /* tile sweeps: 0 = one tile per CTA, bulk-async (TMA engine) copies, 3 CTAs/SM (default);
-                             1 = same with plain ld/st (debug aid); 3 = experimental persistent 3-stage
-                             pipeline, one CTA per SM (slower in round 1: only one load in flight per SM) */
+    int32_t tile_io;      /* tile sweeps: 0 = one tile per CTA, TMA tensor copies with the 128-byte swizzle, 3 CTAs/SM
+                             (default); 1 = plain ld/st (debug aid); 2 = linear bulk-async copies, no swizzle */
     int32_t jit;          /* permutation runs: 0 = specialise with NVRTC in the background after first use
                              (default), 1 = never (generic kernel only), 2 = compile synchronously       */
     int32_t reserved;     /* A/B switches: bit 0 = no multiplexor / block fusion, bit 1 = no register phases,
@@ -109,7 +108,8 @@ typedef struct b2sv_stats_t {
     uint64_t gates_live;      /* ... of which not exact no-ops                                        */
     uint64_t launches;        /* kernel launches made by b2sv_apply                                   */
     uint64_t launches_by_class[12]; /* 0 gate1q, 1 tile sweep, 2 perm run, 3 scale, 4 project, 5 init/convert, 6 swap pack,
-                                      7 perm run (NVRTC-specialised), 8 low-qubit warp-shuffle sweep */
+                                      7 perm run (NVRTC-specialised), 8 low-qubit warp-shuffle sweep,
+                                      9 distributed permutation sweep (gather over peer-mapped shards) */
     double alg_bytes_by_class[12];  /* algorithmic bytes (2*B*M per sweep)                */
     double ms_by_class[12];        /* CUDA-event time per class (only with opts.timing)                */
     double apply_ms;               /* CUDA-event time of whole b2sv_apply calls (always measured)      */
@@ -124,8 +124,14 @@ int b2sv_destroy(b2sv_t* sv);
 
 /* ---- state I/O (circuit.py:62-65: from_basis_state / from_array; :70: to_array) ---------------- */
 int b2sv_set_basis(b2sv_t* sv, uint64_t index);
-int b2sv_set_zero(b2sv_t* sv); /* all amplitudes 0: a shard that does not own the basis state */
+int b2sv_set_zero(b2sv_t* sv); /* all amplitudes 0: a shard that does not own the basis state (lazy: nothing is
+                                  written until a reader needs the zeros; gates on a zero state are skipped) */
 int b2sv_upload(b2sv_t* sv, const void* host_amps_c128);
+/* Seeded dense test vector generated on the device (benchmarks / full-size property tests; no counterpart in the
+ * reference, which uploads numpy arrays): psi_i = scale * (u(2k), u(2k+1)), k = index_base + i, for k < 2^support_bits
+ * and 0 above, u = splitmix64(seed + .) mapped to [-1,1), scale = sqrt(1.5 / 2^support_bits).  index_base lets the
+ * shards of a distributed register hold one global vector. */
+int b2sv_fill_random(b2sv_t* sv, uint64_t seed, int support_bits, uint64_t index_base);
 int b2sv_download(b2sv_t* sv, void* host_out_c128);
 
 /* ---- the simulate call itself (circuit.py:69, tq.simulate -> qulacs update_quantum_state) ------ */
@@ -175,6 +181,38 @@ int b2sv_swap_unpack(b2sv_t* sv, int q, int keep_bit, const void* staging_dev);
  * caller can pipeline pack / exchange / unpack in chunks. */
 int b2sv_swap_pack_range(b2sv_t* sv, int q, int keep_bit, void* staging_dev, uint64_t first, uint64_t count);
 int b2sv_swap_unpack_range(b2sv_t* sv, int q, int keep_bit, const void* staging_dev, uint64_t first, uint64_t count);
+
+/* ---- distributed execution: one process per GPU, the register sharded by its top index bits ------------
+ * (unitaria_b200/distributed.py drives these; the reference is single-process)
+ * Every rank exports its two state buffers and two interprocess events as an opaque blob
+ * (b2sv_ipc_export), the host side all-gathers the blobs, and b2sv_ipc_attach maps every peer's buffers into
+ * this process (CUDA IPC; handles of the same process are attached by pointer).  After that a *distributed
+ * permutation sweep* -- a run of X / multi-controlled X / (controlled) SWAP gates over the WHOLE register, targets
+ * and controls on local or global index positions alike -- is ONE kernel per rank that gathers
+ * out[j] = in[f^-1(rank:j)] straight out of the peers' HBM over NVLink: the all-to-all and the index map are
+ * fused, nothing is packed or staged.  A global<->local swap of k qubits is the same sweep with SWAP gates.
+ * Protocol per sweep (device-side ordering by interprocess events, the host never waits for the GPU):
+ *   1. b2sv_dist_ready        records "my shard is final" and returns this rank's state words
+ *   2. host all-gather of the state words (also guarantees every rank has recorded its event)
+ *   3. b2sv_dist_perm         waits for the peers' events on the stream, launches the gather, records "done"
+ *   4. host barrier           (every rank has recorded "done")
+ *   5. b2sv_dist_done         the stream waits for the peers' "done" before anything overwrites what they read */
+#define B2SV_IPC_BYTES 320
+#define B2SV_DIST_STATE_WORDS 8
+int b2sv_ipc_export(b2sv_t* sv, void* blob_out /* B2SV_IPC_BYTES */);
+int b2sv_ipc_attach(b2sv_t* sv, int rank, int world, const void* blobs /* world * B2SV_IPC_BYTES */);
+int b2sv_ipc_detach(b2sv_t* sv);
+int b2sv_dist_ready(b2sv_t* sv, uint64_t* state_out /* B2SV_DIST_STATE_WORDS */);
+/* gates: X / SWAP only, qubit numbers are index POSITIONS of the n_total-bit register (positions >= the
+ * handle's n_qubits are rank bits).  flip_in / flip_out: per global position, whether the physical rank bit
+ * is the complement of the logical bit before / after the sweep (an uncontrolled X on a global qubit is a
+ * relabel).  states: every rank's words from step 1, in rank order. */
+int b2sv_dist_perm(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, int n_total, uint32_t flip_in, uint32_t flip_out,
+                   const uint64_t* states /* world * B2SV_DIST_STATE_WORDS */, const b2sv_plan_opts* opts);
+int b2sv_dist_done(b2sv_t* sv);
+/* Host-only: the CUDA source of the specialised gather kernel for `gates` (introspection / evidence). */
+int b2sv_dist_source(int n_local, int n_global, int dtype, const b2sv_gate* gates, size_t n_gates, char* out, size_t cap,
+                     size_t* need);
 
 /* ---- planner introspection (no GPU needed): how would `gates` be executed? ---------------------- */
 /* Writes up to `cap` int64 words describing the plan: for each segment

@@ -16,7 +16,11 @@ the reference's own constructors (the ones its tests and examples use), and reco
 No simulator output is stored as "expected": every expected array comes from the reference's
 arithmetic definition of the node, so the fixtures pin simulate-vs-compute parity exactly the way
 ``ut.verify`` does.  ``--big`` also writes the gate lists of the BASELINE.json configs at full size
-(gate lists only; expected outputs at those sizes are checked through properties in the tests).
+(gate lists only).  ``--columns`` freezes, for the mid-size and full-size configs, a handful of COLUMNS of the
+encoded matrix -- ``node.compute(e_j)``, the left-hand side of verifier.py:119-126 -- as sparse vectors in
+``<name>.cols.npz``, so that the GPU suite can check ``normalization * project(simulate(b_j))`` against the
+reference's own numbers at sizes where ``toarray()`` cannot be stored (and ``Adjoint(node)`` / the controlled
+variant of verifier.py:137,146-153 for the <= 16-qubit cases: ``<name>__adjoint.npz`` / ``<name>__controlled.npz``).
 """
 
 from __future__ import annotations
@@ -117,9 +121,47 @@ def record(name, node, expected=True, max_expected_entries=1 << 22, extra_meta=N
     )
 
 
+def record_columns(name, node, n_random=3, seed=0):
+    """Columns of the encoded matrix through the reference's numpy path, stored sparse."""
+    from unitaria_b200.subspace_prog import spec_member
+
+    t0 = time.time()
+    dim_in, dim_out = int(node.dimension_in), int(node.dimension_out)
+    spec_in = spec_from_subspace(node.subspace_in)
+    rng = np.random.default_rng(seed)
+    ranks = sorted(set([0, min(1, dim_in - 1), dim_in // 3, dim_in - 1] + [int(r) for r in rng.integers(0, dim_in, size=n_random)]))
+    if node.is_vector():
+        ranks = [0]
+    idx_all, val_all, ptr = [], [], [0]
+    for r in ranks:
+        if node.is_vector():
+            col = np.asarray(node.compute(), dtype=np.complex128).reshape(-1)
+        else:
+            e = np.zeros(dim_in, dtype=np.complex128)
+            e[r] = 1
+            col = np.asarray(node.compute(e), dtype=np.complex128).reshape(-1)
+        assert col.shape == (dim_out,), (col.shape, dim_out)
+        nz = np.flatnonzero(col != 0)
+        idx_all.append(nz.astype(np.int64))
+        val_all.append(col[nz])
+        ptr.append(ptr[-1] + len(nz))
+    basis = np.array([spec_member(spec_in, r) for r in ranks], dtype=np.int64)
+    np.savez_compressed(
+        os.path.join(HERE, name + ".cols.npz"),
+        col_rank=np.array(ranks, dtype=np.int64),
+        col_basis=basis,
+        col_ptr=np.array(ptr, dtype=np.int64),
+        col_index=np.concatenate(idx_all) if idx_all else np.zeros(0, np.int64),
+        col_value=np.concatenate(val_all) if val_all else np.zeros(0, np.complex128),
+        dim_out=np.int64(dim_out),
+    )
+    print(f"{name:34s} columns={len(ranks)} nnz={ptr[-1]} dim_out={dim_out}  ({time.time() - t0:.1f}s)")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--big", action="store_true", help="also write the full-size BASELINE.json configs")
+    ap.add_argument("--columns", action="store_true", help="freeze columns (node.compute(e_j)) of the mid / full-size configs and the verify legs")
     ap.add_argument("--only", default=None)
     args = ap.parse_args()
     bpx = _load_example("example_bpx")
@@ -184,6 +226,27 @@ def main():
         "cfg5_bits26": lambda: cfg5(26),
         "cfg5_bits24": lambda: cfg5(24),
     }
+    if args.columns:
+        # verifier.py:134-155: besides node itself, ut.verify simulates Adjoint(node) and the controlled variant
+        legs = ["laplace_n3", "laplace_n4", "laplace_readme_n4", "gaussian_s3_t4", "bpx_L2", "bpx_L3", "cfg5_bits5", "qsvt_inc2_cheb",
+                "constant_vector5", "fourier4", "scale_complex", "const_int_add_4_m3", "pinv_bpx_L2"]
+        for name in legs:
+            if args.only and args.only != name:
+                continue
+            node = small[name]()
+            record(name + "__adjoint", ut.Adjoint(node))
+            try:  # verifier.py:146-153 (the reference only does this for nodes with their own controlled circuit)
+                controlled = (node.normalization * ut.Identity(ut.Subspace("#" * node.subspace_out.total_qubits))) | node
+                record(name + "__controlled", controlled)
+            except Exception as exc:  # noqa: BLE001 - shapes that the reference's "|" rejects
+                print(f"{name + '__controlled':34s} skipped: {type(exc).__name__}: {exc}")
+        for name, make in list(mid.items()) + [("cfg5_bits13", small["cfg5_bits13"])] + list(big.items()):
+            if args.only and args.only != name:
+                continue
+            if name.startswith("cfg5_bits2"):
+                continue  # 2^30+ output entries per column: config 5 is pinned at bits=13
+            record_columns(name, make())
+        return
     for name, make in small.items():
         if args.only and args.only != name:
             continue

@@ -7,7 +7,8 @@ import os
 
 import numpy as np
 
-from unitaria_b200.fixtures import load_circuit
+from unitaria_b200.fixtures import column_error, load_circuit  # noqa: F401
+from unitaria_b200.fixtures import load_columns as _load_columns
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -15,6 +16,8 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def golden_names(with_expected=None, max_qubits=None, min_qubits=None):
     names = []
     for path in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
+        if path.endswith(".cols.npz"):  # frozen columns of a case, not a case (load_columns)
+            continue
         c = load_circuit(path)
         if with_expected is not None and (("expected" in c.arrays) != with_expected):
             continue
@@ -28,6 +31,11 @@ def golden_names(with_expected=None, max_qubits=None, min_qubits=None):
 
 def load_golden(name):
     return load_circuit(os.path.join(GOLDEN_DIR, name + ".npz"))
+
+
+def load_columns(name):
+    """Frozen columns of the encoded matrix (reference ``node.compute(e_j)``, tests/golden/make_golden.py --columns)."""
+    return _load_columns(os.path.join(GOLDEN_DIR, name + ".cols.npz"))
 
 
 def golden_inputs(case, limit=None, rng=None):

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_struct_layouts():
     lib = cabi.load()
-    assert lib.b2sv_abi_version() == 1
+    assert lib.b2sv_abi_version() == 2
     assert cabi.GATE_DTYPE.itemsize == 80 and cabi.SUBINSTR_DTYPE.itemsize == 32
     assert ctypes.sizeof(cabi.PlanOpts) == 32
     assert ctypes.sizeof(cabi.Stats) == 8 * 3 + 8 * 12 * 3 + 8

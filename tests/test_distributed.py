@@ -24,6 +24,8 @@ from unitaria_b200.subspace_prog import SubspaceProgram, to_spec
 
 
 class NumpyShard:
+    supports_gather = False  # round-1 schedule: pack / exchange / unpack swaps
+
     def __init__(self, n_local):
         self.n = n_local
         self.psi = np.zeros(2**n_local, dtype=np.complex128)
@@ -99,13 +101,49 @@ class NumpyShard:
         pass
 
 
+class NumpyGatherShard(NumpyShard):
+    """Test double of the fused gather exchange (b2sv_dist_perm): every rank sees all shards (all-gather over
+    gloo stands in for the peer-mapped HBM) and evaluates out[j] = in[f^-1(j)] with the flip-flag semantics of
+    include/b2sv.h -- which is what pins the host logic: run collection, relabels, k-qubit swaps."""
+
+    supports_gather = True
+
+    def __init__(self, n_local):
+        super().__init__(n_local)
+        self.sweeps = 0
+
+    def prepare_dist(self, gates_pos, n_total):
+        return list(gates_pos)
+
+    def dist_perm(self, gates_pos, n_total, flip_in, flip_out, comm, opts=None):
+        nl = self.n
+        full = np.concatenate(comm.all_gather_array(self.psi))   # index = physical rank : local index
+        j_logical = np.arange(2**n_total, dtype=np.int64) ^ (int(flip_out) << nl)
+        src = j_logical.copy()
+        for g in reversed(gates_pos):  # X and SWAP are self-inverse: f^-1 applies them in reverse order
+            assert g.name.upper() in ("X", "SWAP"), g
+            cm = 0
+            for c in g.control:
+                cm |= 1 << int(c)
+            on = (src & cm) == cm
+            if g.name.upper() == "X":
+                src = np.where(on, src ^ (1 << int(g.target[0])), src)
+            else:
+                a, b = (int(t) for t in g.target)
+                differ = ((src >> a) ^ (src >> b)) & 1 == 1
+                src = np.where(on & differ, src ^ ((1 << a) | (1 << b)), src)
+        out = full[src ^ (int(flip_in) << nl)]
+        self.psi = out[comm.rank << nl : (comm.rank + 1) << nl].copy()
+        self.sweeps += 1
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, case_name, seed, out_dir):
+def _worker(rank, world, port, case_name, seed, out_dir, gather=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -120,7 +158,8 @@ def _worker(rank, world, port, case_name, seed, out_dir):
             case = load_golden(case_name)
             n, gates, spec = case.n_qubits, case.gates, case.meta["subspace_out"]
             basis = 3
-        sv = ShardedStateVector(n, TorchComm(), NumpyShard)
+        sv = ShardedStateVector(n, TorchComm(), NumpyGatherShard if gather else NumpyShard)
+        assert sv.gather == gather
         sv.set_basis(basis)
         sv.apply(gates)
         norm2 = sv.project_norm2(SubspaceProgram(spec))
@@ -128,35 +167,37 @@ def _worker(rank, world, port, case_name, seed, out_dir):
         local = sv.local_amplitudes()
         np.save(os.path.join(out_dir, f"shard{rank}.npy"), local)
         if rank == 0:
-            np.save(os.path.join(out_dir, "meta.npy"), np.array([norm2, swaps_before_restore, sv.stats["swaps"]]))
+            np.save(os.path.join(out_dir, "meta.npy"), np.array([norm2, swaps_before_restore, sv.stats["swaps"], sv.stats["dist_sweeps"]]))
     finally:
         dist.destroy_process_group()
 
 
-def run_case(tmp_path, world, case_name, seed=0):
+def run_case(tmp_path, world, case_name, seed=0, gather=False):
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, case_name, seed, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, case_name, seed, str(tmp_path), gather), nprocs=world, join=True)
     full = np.concatenate([np.load(tmp_path / f"shard{r}.npy") for r in range(world)])
     meta = np.load(tmp_path / "meta.npy")
     return full, meta
 
 
+@pytest.mark.parametrize("gather", [False, True])
 @pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("case_name", ["laplace_n4", "cfg5_bits5", "bpx_L2"])
-def test_sharded_matches_single_register_goldens(tmp_path, world, case_name):
+def test_sharded_matches_single_register_goldens(tmp_path, world, case_name, gather):
     case = load_golden(case_name)
-    full, meta = run_case(tmp_path, world, case_name)
+    full, meta = run_case(tmp_path, world, case_name, gather=gather)
     want = np_oracle.simulate_gates(case.gates, case.n_qubits, 3)
     assert np.abs(full - want).max() < 1e-12
     basis = np_oracle.enumerate_basis(case.meta["subspace_out"])
     assert abs(meta[0] - np.sum(np.abs(want[basis]) ** 2)) < 1e-12
 
 
-@pytest.mark.parametrize("world,n,seed", [(2, 6, 1), (4, 7, 2), (2, 9, 3)])
-def test_sharded_matches_single_register_random(tmp_path, world, n, seed):
+@pytest.mark.parametrize("gather", [False, True])
+@pytest.mark.parametrize("world,n,seed", [(2, 6, 1), (4, 7, 2), (2, 9, 3), (8, 8, 4)])
+def test_sharded_matches_single_register_random(tmp_path, world, n, seed, gather):
     """Every gate kind, controls on global qubits, rank relabels (uncontrolled X on a global qubit),
-    diagonal gates on global targets, global<->local swaps."""
-    full, meta = run_case(tmp_path, world, f"random_{n}", seed)
+    diagonal gates on global targets, global<->local swaps / distributed permutation sweeps."""
+    full, meta = run_case(tmp_path, world, f"random_{n}", seed, gather=gather)
     rng = np.random.default_rng(seed)
     gates = random_circuit(n, 160, rng, max_controls=3).gates
     basis = int(rng.integers(0, 2 ** (n - 1)))
@@ -165,6 +206,18 @@ def test_sharded_matches_single_register_random(tmp_path, world, n, seed):
     member = np_oracle.enumerate_basis(to_spec("0" + "#" * (n - 1)))
     assert abs(meta[0] - np.sum(np.abs(want[member]) ** 2)) < 1e-12
     assert meta[1] > 0  # the circuit did need global<->local swaps
+    if gather:
+        assert meta[3] > 0  # ... and they ran as distributed sweeps
+
+
+def test_cfg5_needs_no_swap_with_the_gather_exchange(tmp_path):
+    """BASELINE config 5's shape (Increment across the rank boundary & low-qubit state preparation): the
+    Increment's X-family gates on global targets ride in distributed sweeps, no qubit is ever swapped."""
+    case = load_golden("cfg5_bits5")
+    full, meta = run_case(tmp_path, 4, "cfg5_bits5", gather=True)
+    want = np_oracle.simulate_gates(case.gates, case.n_qubits, 3)
+    assert np.abs(full - want).max() < 1e-12
+    assert meta[1] == 0 and 1 <= meta[3] <= 3, meta
 
 
 def test_localise_gate_rules():

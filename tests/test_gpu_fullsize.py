@@ -4,7 +4,7 @@
 import numpy as np
 import pytest
 
-from tests.helpers import dagger_gates, load_golden
+from tests.helpers import column_error, dagger_gates, load_columns, load_golden
 from unitaria_b200 import PlanOpts, StateVector, SubspaceProgram, cabi, lower_gates
 
 pytestmark = pytest.mark.gpu
@@ -102,3 +102,45 @@ def test_cfg4_bpx_L8_norm_and_dagger_roundtrip():
         sv.apply_lowered(inv_low)
         out = sv.project(SubspaceProgram("0" * (n - 4) + "####"))
         assert abs(out[0] - 1.0) < 1e-11 and np.abs(out[1:]).max() < 1e-11
+
+
+@pytest.mark.parametrize(
+    "name,dtype,qubits,tol",
+    [
+        ("cfg2_laplace_n26", "complex128", 0, 1e-12),
+        ("cfg2_laplace_readme_n26", "complex128", 0, 1e-12),   # 31 qubits, 26-deep nested subspace (README.md:52-55)
+        ("cfg3_gaussian_s3_t21", "complex64", 0, 1e-5),
+        ("cfg3_gaussian_s3_t21", "complex128", 0, 1e-12),
+        ("cfg4_bpx_L8", "complex128", 0, 1e-12),
+        ("cfg4_bpx_L8", "complex128", 30, 1e-12),               # (x) Identity("#"): the 30-qubit register of BASELINE config 4
+        ("cfg4_bpx_L8", "complex64", 0, 1e-5),
+        ("cfg4_pinv_bpx_L4", "complex128", 0, 1e-12),           # the 93 675-gate amplified encoding
+        ("cfg4_pinv_bpx_L4", "complex128", 30, 1e-12),
+        ("cfg4_pinv_bpx_L4", "complex64", 0, 1e-5),
+    ],
+)
+def test_full_size_columns_match_reference_compute(name, dtype, qubits, tol):
+    """normalization * project(simulate(b_j)) == node.compute(e_j) (verifier.py:115-126) at BASELINE sizes: the expected
+    columns are the reference's own numpy results, frozen by tests/golden/make_golden.py --columns.  Tolerance is the
+    north-star's (1e-12 complex128, 1e-5 complex64), relative to the largest entry of the column, NOT scaled by depth."""
+    case = load_golden(name)
+    cols, dim_out = load_columns(name)
+    assert cols, "run tests/golden/make_golden.py --columns"
+    n = max(case.n_qubits, qubits)
+    norm = case.meta["normalization"]
+    prog = SubspaceProgram(case.meta["subspace_out"])
+    assert prog.dimension == dim_out
+    low = lower_gates(case.gates, n)
+    worst = 0.0
+    with StateVector(n, dtype) as sv:
+        for basis, idx, val in cols[:4] if len(case.gates) > 50000 else cols:
+            sv.set_basis(basis)
+            sv.apply_lowered(low)
+            got = sv.project(prog, scale=norm)
+            scale = max(1.0, float(np.abs(val).max()) if len(val) else 1.0)
+            err = column_error(got, idx, val) / scale
+            worst = max(worst, err)
+            assert err <= tol, (name, dtype, basis, err)
+            want_norm = float(np.sqrt(np.sum(np.abs(val) ** 2)))
+            assert abs(abs(norm) * np.sqrt(sv.project_norm2(prog)) - want_norm) <= 10 * tol * max(1.0, want_norm)
+    print(f"{name} {dtype} n={n}: max relative column error {worst:.3e} over {len(cols)} columns ({len(case.gates)} gates)")

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import c_oracle, np_oracle
-from tests.helpers import expected_column, golden_inputs, golden_names, load_golden, random_circuit, random_state
+from tests.helpers import column_error, expected_column, golden_inputs, golden_names, load_columns, load_golden, random_circuit, random_state
 from unitaria_b200 import PlanOpts, StateVector, SubspaceProgram, cabi, lower_gates
 from unitaria_b200 import adapter
 
@@ -29,8 +29,6 @@ VARIANTS = {
     "no_phases_no_mux": dict(phases=False, mux=False),
     "no_mono": dict(mono=False),
     "no_mono_tiles_only": dict(mono=False, perm_runs=False),
-    "tile_pipelined": dict(tile_io=3),
-    "tile_pipelined_tiles_only": dict(tile_io=3, perm_runs=False),
 }
 
 
@@ -232,6 +230,26 @@ def test_mid_size_configs_against_c_oracle(name):
         assert np.abs(got - want).max() <= 1e-5, name
 
 
+@pytest.mark.parametrize("dtype,tol", [("complex128", 1e-12), ("complex64", 1e-5)])
+@pytest.mark.parametrize("name", ["laplace_n12", "laplace_n16", "laplace_n20", "gaussian_s3_t13", "bpx_L4", "bpx_L5", "cfg5_bits13"])
+def test_mid_size_columns_match_reference_compute(name, dtype, tol):
+    """The mid-size circuit families against the reference's own node.compute(e_j) columns (verifier.py:115-126)."""
+    case = load_golden(name)
+    cols, dim_out = load_columns(name)
+    assert cols, "run tests/golden/make_golden.py --columns"
+    n, norm = case.n_qubits, case.meta["normalization"]
+    prog = SubspaceProgram(case.meta["subspace_out"])
+    assert prog.dimension == dim_out
+    low = lower_gates(case.gates, n)
+    with StateVector(n, dtype) as sv:
+        for basis, idx, val in cols:
+            sv.set_basis(basis)
+            sv.apply_lowered(low)
+            got = sv.project(prog, scale=norm)
+            scale = max(1.0, float(np.abs(val).max()) if len(val) else 1.0)
+            assert column_error(got, idx, val) <= tol * scale, (name, dtype, basis)
+
+
 @pytest.mark.parametrize("name", ["laplace_readme_n8", "bpx_L3", "pinv_bpx_L2", "cfg5_bits13", "laplace_n16"])
 @pytest.mark.parametrize("which", ["subspace_in", "subspace_out"])
 def test_device_enumerate_basis_and_projection_order(name, which):
@@ -403,3 +421,56 @@ def test_sampling_mode_matches_exact_norm_statistically():
     stderr = norm * np.sqrt(p * (1 - p) / samples) / (2 * np.sqrt(p)) if 0 < p < 1 else 1e-9
     assert abs(np.mean(est) - exact) < 6 * stderr / np.sqrt(len(est)) + 1e-9
     assert all(abs(e - exact) < 8 * stderr + 1e-9 for e in est)
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_fill_random_matches_its_host_restatement(dtype):
+    """b2sv_fill_random (device-side seeded dense vector for benchmarks / full-size property tests) == the numpy
+    restatement of the same counter hash, including the support window and a shard's index base."""
+    from unitaria_b200.engine import random_state_hash
+
+    n = 12
+    with StateVector(n, dtype) as sv:
+        for seed, bits, base in [(0, None, 0), (7, 9, 0), (3, 14, 3 << n)]:
+            sv.set_basis(5)  # pending state must not survive
+            sv.fill_random(seed=seed, support_bits=bits, index_base=base)
+            got = sv.download()
+            want = random_state_hash(n, seed, bits if bits is not None else n, base)
+            tol = 0 if dtype == "complex128" else 1e-7
+            assert np.abs(got - want).max() <= tol, (seed, bits, base)
+            if bits is None:
+                assert abs(np.linalg.norm(got) - 1.0) < 0.05
+
+
+def test_known_zero_state_is_lazy_and_correct():
+    """b2sv_set_zero writes nothing: gates are skipped, the norm is 0 without a launch, readers get zeros."""
+    import tequila as tq
+
+    n = 14
+    c = tq.gates.H(0) + tq.gates.CNOT(0, 5) + tq.gates.Ry(0.3, 9)
+    with StateVector(n) as sv:
+        sv.upload(random_state(n, np.random.default_rng(0)))  # dirty buffer
+        sv.set_zero()
+        sv.stats_reset()
+        sv.apply(c.gates)
+        assert sv.project_norm2("#" * n) == 0.0
+        assert sv.stats()["launches"] == 0
+        assert not np.any(sv.download())
+        sv.set_basis(3)
+        sv.apply(c.gates)
+        assert abs(sv.project_norm2("#" * n) - 1.0) < 1e-14
+
+
+def test_two_devices_in_one_process():
+    """cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device -- a second StateVector on another
+    device of the same process must run the 64 KiB tile sweeps too."""
+    if cabi.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    case = load_golden("laplace_n12")
+    psi0 = random_state(case.n_qubits, np.random.default_rng(2))
+    want = c_oracle.simulate_gates(case.gates, case.n_qubits, psi0)
+    for device in (0, 1, 0):
+        with StateVector(case.n_qubits, device=device) as sv:
+            sv.upload(psi0)
+            sv.apply(case.gates)
+            assert np.abs(sv.download() - want).max() < 1e-12, device

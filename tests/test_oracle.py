@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import c_oracle, np_oracle
-from tests.helpers import expected_column, golden_inputs, golden_names, load_golden, random_circuit, random_state
+from tests.helpers import column_error, expected_column, golden_inputs, golden_names, load_columns, load_golden, random_circuit, random_state
 
 SMALL = golden_names(with_expected=True, max_qubits=16)
 
@@ -37,6 +37,23 @@ def test_c_oracle_matches_reference_goldens(name):
         want = expected_column(case, col)
         scale = max(1.0, float(np.abs(want).max()))
         assert np.abs(got - want).max() <= 1e-12 * scale * max(1, len(case.gates) / 100), (name, col)
+
+
+@pytest.mark.parametrize("name", ["laplace_n12", "laplace_n16", "laplace_n20", "gaussian_s3_t13", "bpx_L4", "bpx_L5", "cfg5_bits13"])
+def test_c_oracle_matches_reference_columns_at_mid_size(name):
+    """The oracle the GPU suite leans on at 15-23 qubits, pinned to the reference's node.compute(e_j) columns
+    (tests/golden/make_golden.py --columns) -- also pins the rank -> basis-index map used to pick the inputs."""
+    case = load_golden(name)
+    cols, dim_out = load_columns(name)
+    n, norm = case.n_qubits, case.meta["normalization"]
+    basis_out = np_oracle.enumerate_basis(case.meta["subspace_out"])
+    basis_in = np_oracle.enumerate_basis(case.meta["subspace_in"]) if case.meta["subspace_in"] is not None and n <= 20 else None
+    assert len(basis_out) == dim_out
+    for basis, idx, val in cols[:4]:
+        if basis_in is not None:
+            assert basis in basis_in
+        got = norm * c_oracle.simulate_gates(case.gates, n, basis)[basis_out]
+        assert column_error(got, idx, val) <= 1e-12 * max(1.0, float(np.abs(val).max())) * max(1, len(case.gates) / 1000), (name, basis)
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 11])

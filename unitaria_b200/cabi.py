@@ -19,7 +19,9 @@ LIB_PATH = os.path.join(_HERE, "libunitaria_b200.so")
 B2SV_C128, B2SV_C64 = 0, 1
 OP_MAT1, OP_DIAG1, OP_X, OP_SWAP, OP_PHASE = 0, 1, 2, 3, 4
 SEG_GATE1Q, SEG_TILE, SEG_PERM, SEG_LOW6 = 0, 1, 2, 3
-CLASS_NAMES = ("gate1q", "tile", "perm", "scale", "project", "init", "swap", "perm_jit", "low6")
+CLASS_NAMES = ("gate1q", "tile", "perm", "scale", "project", "init", "swap", "perm_jit", "low6", "dist_perm")
+IPC_BYTES = 320
+DIST_STATE_WORDS = 8
 
 # struct b2sv_gate (80 bytes)
 GATE_DTYPE = np.dtype(
@@ -85,9 +87,9 @@ class Stats(ctypes.Structure):
             "gates_in": int(self.gates_in),
             "gates_live": int(self.gates_live),
             "launches": int(self.launches),
-            "launches_by_class": {CLASS_NAMES[i]: int(self.launches_by_class[i]) for i in range(9)},
-            "alg_bytes_by_class": {CLASS_NAMES[i]: float(self.alg_bytes_by_class[i]) for i in range(9)},
-            "ms_by_class": {CLASS_NAMES[i]: float(self.ms_by_class[i]) for i in range(9)},
+            "launches_by_class": {CLASS_NAMES[i]: int(self.launches_by_class[i]) for i in range(len(CLASS_NAMES))},
+            "alg_bytes_by_class": {CLASS_NAMES[i]: float(self.alg_bytes_by_class[i]) for i in range(len(CLASS_NAMES))},
+            "ms_by_class": {CLASS_NAMES[i]: float(self.ms_by_class[i]) for i in range(len(CLASS_NAMES))},
             "apply_ms": float(self.apply_ms),
         }
 
@@ -110,6 +112,7 @@ SYMBOLS = {
     "b2sv_set_basis": (ctypes.c_int, [_P, ctypes.c_uint64]),
     "b2sv_set_zero": (ctypes.c_int, [_P]),
     "b2sv_upload": (ctypes.c_int, [_P, _P]),
+    "b2sv_fill_random": (ctypes.c_int, [_P, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint64]),
     "b2sv_download": (ctypes.c_int, [_P, _P]),
     "b2sv_apply": (ctypes.c_int, [_P, _P, ctypes.c_size_t, ctypes.POINTER(PlanOpts)]),
     "b2sv_project_norm2": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
@@ -133,6 +136,13 @@ SYMBOLS = {
     "b2sv_swap_unpack": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P]),
     "b2sv_swap_pack_range": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P, ctypes.c_uint64, ctypes.c_uint64]),
     "b2sv_swap_unpack_range": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P, ctypes.c_uint64, ctypes.c_uint64]),
+    "b2sv_ipc_export": (ctypes.c_int, [_P, _P]),
+    "b2sv_ipc_attach": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P]),
+    "b2sv_ipc_detach": (ctypes.c_int, [_P]),
+    "b2sv_dist_ready": (ctypes.c_int, [_P, _P]),
+    "b2sv_dist_perm": (ctypes.c_int, [_P, _P, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _P, ctypes.POINTER(PlanOpts)]),
+    "b2sv_dist_done": (ctypes.c_int, [_P]),
+    "b2sv_dist_source": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, ctypes.c_size_t, _P, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
     "b2sv_plan_describe": (
         ctypes.c_int,
         [ctypes.c_int, ctypes.c_int, _P, ctypes.c_size_t, ctypes.POINTER(PlanOpts), _P, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)],

@@ -6,6 +6,9 @@
 // norm of Node.simulate / simulate_norm (/root/reference/src/unitaria/nodes/node.py:363-403).
 #include <cuda_runtime.h>
 
+#include <unistd.h>
+
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -47,7 +50,7 @@ int fail(int code, const char* fmt, ...) {
                         cudaGetErrorString(e_), __FILE__, __LINE__);                               \
     } while (0)
 
-enum { CLS_GATE1 = 0, CLS_TILE = 1, CLS_PERM = 2, CLS_SCALE = 3, CLS_PROJECT = 4, CLS_INIT = 5, CLS_SWAP = 6, CLS_PERM_JIT = 7, CLS_LOW6 = 8, CLS_N = 12 };
+enum { CLS_GATE1 = 0, CLS_TILE = 1, CLS_PERM = 2, CLS_SCALE = 3, CLS_PROJECT = 4, CLS_INIT = 5, CLS_SWAP = 6, CLS_PERM_JIT = 7, CLS_LOW6 = 8, CLS_DIST = 9, CLS_N = 12 };
 
 struct TimedLaunch {
     cudaEvent_t a, b;
@@ -73,6 +76,24 @@ struct b2sv {
     // when a permutation sweep follows: that sweep then reads one tile instead of a whole register of zeros)
     bool window = false;
     uint64_t win_mask = 0, win_value = 0;
+    // known-zero state: every amplitude is 0 and the buffer has not been written (a shard that does not own the
+    // basis state, b2sv_set_zero): every gate maps it to itself, so nothing runs until a distributed sweep brings
+    // amplitudes in or a reader needs the zeros
+    bool zero = false;
+    // distributed execution (b2sv_ipc_* / b2sv_dist_*): the two state buffers and the hand-shake events of every
+    // rank, mapped into this process
+    int dist_rank = -1, dist_world = 0;
+    void* own_buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+    struct Peer {
+        void* buf[2] = {nullptr, nullptr};
+        cudaEvent_t ready = nullptr, done = nullptr;
+        bool ipc = false;  // opened through CUDA IPC (another process): close on detach
+    };
+    std::vector<Peer> peers;
+    void* d_dist_gates = nullptr;
+    size_t d_dist_gates_cap = 0;
+    std::vector<unsigned char> plan_gate_copy;  // the gate list the cached plan was made from (compared on a hash hit)
     bool timing_on = false;        // last b2sv_apply asked for per-launch timing: time init/project too
     double sre = 1.0, sim = 0.0;   // pending global scalar (folded uncontrolled global phases)
     void* d_ops = nullptr;         // device copy of the tile ops of the current apply
@@ -100,6 +121,7 @@ struct b2sv {
     b2svk::Plan plan;
     std::vector<size_t> plan_seg_first;
     std::vector<int> plan_seg_nops;
+    std::vector<std::vector<b2svk::SlotFill>> plan_seg_slots;
     b2sv_stats_t stats{};
     std::vector<TimedLaunch> timed;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> apply_events;
@@ -248,6 +270,12 @@ int flush_scalar(b2sv* sv, bool timing) {
 
 // Write the lazily requested basis state out (every reader of the amplitudes calls this first).
 int materialise(b2sv* sv) {
+    if (sv->zero) {
+        sv->zero = false;
+        sv->stats.launches_by_class[CLS_INIT]++;
+        CU(cudaMemsetAsync(sv->amps, 0, sv->count * sv->amp_bytes, sv->stream));
+        return B2SV_OK;
+    }
     if (sv->window) {  // write the implied zeros
         sv->window = false;
         const uint64_t mask = sv->win_mask, value = sv->win_value;
@@ -309,8 +337,9 @@ int launch_gate1(b2sv* sv, const PGate& g, bool timing) {
 }
 
 template <typename A>
-int set_tile_smem(size_t bytes) {
-    static size_t configured = 0;
+int set_tile_smem(int device, size_t bytes) {
+    static size_t configured_dev[64] = {};  // the attribute is per device
+    size_t& configured = configured_dev[device & 63];
     if (bytes > 48 * 1024 && configured < bytes) {
         CU(cudaFuncSetAttribute(k_tile<A, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         CU(cudaFuncSetAttribute(k_tile<A, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -362,8 +391,9 @@ const CUtensorMap* state_tensor_map(b2sv* sv, int rows_per_box) {
 }
 
 template <typename A>
-int set_swz_smem(size_t bytes) {
-    static size_t configured = 0;
+int set_swz_smem(int device, size_t bytes) {
+    static size_t configured_dev[64] = {};  // the attribute is per device
+    size_t& configured = configured_dev[device & 63];
     if (bytes > 48 * 1024 && configured < bytes) {
         CU(cudaFuncSetAttribute(k_tile_swz<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         CU(cudaFuncSetAttribute(k_tile_swz<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -372,21 +402,11 @@ int set_swz_smem(size_t bytes) {
     return B2SV_OK;
 }
 
-template <typename A>
-int set_pipe_smem(size_t bytes) {
-    static size_t configured = 0;
-    if (bytes > 48 * 1024 && configured < bytes) {
-        CU(cudaFuncSetAttribute(k_tile_pipe<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        CU(cudaFuncSetAttribute(k_tile_pipe<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        configured = bytes;
-    }
-    return B2SV_OK;
-}
-
 // owner_only (with lazy_init): launch just the one tile that holds the pending basis index; the caller then
 // records the rest of the register as "implied zeros" (b2sv::window).
 int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, const PlanConfig& cfg, int tile_io,
-                bool fused_ops, bool timing, bool lazy_init, bool owner_only = false) {
+                bool fused_ops, bool timing, bool lazy_init, bool owner_only, const std::vector<SlotFill>& slots,
+                const std::vector<double>& tables) {
     const bool bulk = tile_io != 1;
     TileArgs a{};
     fill_expand(a.tile_ex, seg.tile_mask);
@@ -413,7 +433,6 @@ int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, co
     a.init_index = sv->basis_index;
     a.tile_mask = seg.tile_mask;
     const uint64_t n_tiles = 1ull << (sv->n - a.cta_ex.m);
-    if (n_ops > kTileMaxOps && tile_io == 3) tile_io = 0;  // the experimental pipelined kernel takes one batch only
     const size_t smem = ((size_t)sv->amp_bytes << a.k) + (size_t)kTileMaxOps * sizeof(TileOp);
     // default path: TMA tensor copies with the hardware 128-byte swizzle (needs chunks of >= one 128-byte
     // row and a tile of >= one 1 KiB swizzle atom; tiny registers use the linear bulk-copy kernel below)
@@ -423,10 +442,12 @@ int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, co
             TileArgsSwz as;
             as.map = *map;
             as.t = a;
+            for (const SlotFill& f : slots)  // the sweep's dense-block matrices ride in the kernel parameters
+                std::memcpy(&as.blk.m[(size_t)f.granule * kBlkGranuleElems], &tables[2 * f.mat_off], sizeof(double2) << (2 * f.kb));
             const size_t swz_smem = smem + 16;  // tile + ops + the mbarrier
             return dispatch_dtype(sv, [&](auto* tag) -> int {
                 using A = std::remove_pointer_t<decltype(tag)>;
-                int rc = set_swz_smem<A>(swz_smem);
+                int rc = set_swz_smem<A>(sv->device, swz_smem);
                 if (rc) return rc;
                 LaunchTimer lt(sv, timing, CLS_TILE, (lazy_init ? 1.0 : 2.0) * sv->amp_bytes * (double)(n_tiles << a.k));
                 if (fused_ops) k_tile_swz<A, true><<<(unsigned)n_tiles, kThreads, swz_smem, sv->stream>>>(as);
@@ -435,24 +456,9 @@ int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, co
             });
         }
     }
-    if (tile_io == 3) {  // experimental: persistent three-stage pipeline, one CTA per SM (measured slower)
-        const size_t pipe_smem = (((size_t)sv->amp_bytes << a.k) * kPipeStages) + (size_t)kTileMaxOps * sizeof(TileOp);
-        const uint64_t grid = n_tiles < (uint64_t)sv->sm_count ? n_tiles : (uint64_t)sv->sm_count;
-        return dispatch_dtype(sv, [&](auto* tag) -> int {
-            using A = std::remove_pointer_t<decltype(tag)>;
-            int rc = set_pipe_smem<A>(pipe_smem);
-            if (rc) return rc;
-            LaunchTimer lt(sv, timing, CLS_TILE, (lazy_init ? 1.0 : 2.0) * sv->amp_bytes * (double)(n_tiles << a.k));
-            if (fused_ops)
-                k_tile_pipe<A, true><<<(unsigned)grid, kPipeThreads, pipe_smem, sv->stream>>>((A*)sv->amps, a, (uint32_t)n_tiles);
-            else
-                k_tile_pipe<A, false><<<(unsigned)grid, kPipeThreads, pipe_smem, sv->stream>>>((A*)sv->amps, a, (uint32_t)n_tiles);
-            return B2SV_OK;
-        });
-    }
     return dispatch_dtype(sv, [&](auto* tag) -> int {
         using A = std::remove_pointer_t<decltype(tag)>;
-        int rc = set_tile_smem<A>(smem);
+        int rc = set_tile_smem<A>(sv->device, smem);
         if (rc) return rc;
         LaunchTimer lt(sv, timing, CLS_TILE, (lazy_init ? 1.0 : 2.0) * sv->amp_bytes * (double)(n_tiles << a.k));
         if (bulk && fused_ops)
@@ -553,11 +559,12 @@ struct JitEntry {
 std::mutex g_jit_mutex;
 std::map<std::string, std::shared_ptr<JitEntry>> g_jit;
 
-std::string perm_key(const std::vector<PGate>& gates, int n, int dtype) {
+std::string perm_key(const std::vector<PGate>& gates, int n, int dtype, int n_global = -1) {
     std::string k;
     k.reserve(gates.size() * 11 + 8);
     k.push_back((char)n);
     k.push_back((char)dtype);
+    k.push_back((char)n_global);  // -1: single-register kernel, >= 0: distributed gather over 2^n_global shards
     for (const PGate& g : gates) {
         k.push_back((char)g.op);
         k.push_back((char)g.t0);
@@ -567,31 +574,61 @@ std::string perm_key(const std::vector<PGate>& gates, int n, int dtype) {
     return k;
 }
 
-void jit_compile_into(const std::shared_ptr<JitEntry>& e, std::vector<PGate> gates, int n, int dtype) {
+void jit_compile_into(const std::shared_ptr<JitEntry>& e, std::vector<PGate> gates, int n, int dtype, int n_global) {
     std::vector<char> cubin;
     std::string log;
-    const bool ok = nvrtc_compile(perm_jit_source(gates, n, dtype), cubin, log);
+    const bool ok = nvrtc_compile(n_global < 0 ? perm_jit_source(gates, n, dtype) : perm_dist_source(gates, n, n_global, dtype), cubin, log);
     std::lock_guard<std::mutex> lk(e->mu);
     e->cubin = std::move(cubin);
     e->log = std::move(log);
     e->state = ok ? 1 : -1;
 }
 
+// Background compiles run on joinable threads that are joined when the library is unloaded / the process
+// exits, so that no thread is still inside NVRTC (or touching g_jit) while the statics are torn down.
+struct JitWorkers {
+    std::mutex mu;
+    std::vector<std::thread> threads;
+    void spawn(const std::shared_ptr<JitEntry>& e, const std::vector<PGate>& gates, int n, int dtype) {
+        std::lock_guard<std::mutex> lk(mu);
+        threads.emplace_back(jit_compile_into, e, gates, n, dtype, -1);
+    }
+    ~JitWorkers() {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto& t : threads)
+            if (t.joinable()) t.join();
+    }
+};
+JitWorkers g_jit_workers;
+
 // Returns the specialised kernel for this run if it is ready (loading it on first use), else null.
-cudaKernel_t jit_lookup(b2sv* sv, const std::vector<PGate>& gates, int jit_mode) {
+// n_global < 0: the single-register sweep (b2sv_perm_jit); >= 0: the distributed gather (b2sv_perm_dist).
+cudaKernel_t jit_lookup(b2sv* sv, const std::vector<PGate>& gates, int jit_mode, int n_global = -1) {
     if (jit_mode == 1 || !nvrtc_api().ok) return nullptr;
     std::shared_ptr<JitEntry> e;
     {
         std::lock_guard<std::mutex> lk(g_jit_mutex);
-        std::string key = perm_key(gates, sv->n, sv->dtype);
+        std::string key = perm_key(gates, sv->n, sv->dtype, n_global);
         auto it = g_jit.find(key);
         if (it == g_jit.end()) {
+            if (g_jit.size() >= 512) {  // bound the cache: drop entries nobody holds a loaded kernel of any more
+                for (auto jt = g_jit.begin(); jt != g_jit.end();) {
+                    std::unique_lock<std::mutex> el(jt->second->mu, std::try_to_lock);
+                    if (el.owns_lock() && jt->second->state != 0) {
+                        for (auto& ld : jt->second->loaded) cudaLibraryUnload(ld.second.first);
+                        el.unlock();
+                        jt = g_jit.erase(jt);
+                    } else {
+                        ++jt;
+                    }
+                }
+            }
             e = std::make_shared<JitEntry>();
             g_jit.emplace(std::move(key), e);
             if (jit_mode == 2) {
-                jit_compile_into(e, gates, sv->n, sv->dtype);
+                jit_compile_into(e, gates, sv->n, sv->dtype, n_global);
             } else {
-                std::thread(jit_compile_into, e, gates, sv->n, sv->dtype).detach();
+                g_jit_workers.spawn(e, gates, sv->n, sv->dtype);
                 return nullptr;  // first sighting: the generic kernel runs while NVRTC works
             }
         } else {
@@ -606,7 +643,7 @@ cudaKernel_t jit_lookup(b2sv* sv, const std::vector<PGate>& gates, int jit_mode)
         cudaLibrary_t lib = nullptr;
         cudaKernel_t k = nullptr;
         if (cudaLibraryLoadData(&lib, e->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
-            cudaLibraryGetKernel(&k, lib, "b2sv_perm_jit") != cudaSuccess) {
+            cudaLibraryGetKernel(&k, lib, n_global < 0 ? "b2sv_perm_jit" : "b2sv_perm_dist") != cudaSuccess) {
             cudaGetLastError();
             e->state = -1;
             e->log = "loading the specialised kernel failed";
@@ -667,7 +704,8 @@ int launch_perm(b2sv* sv, const Plan& plan, const Segment& seg, bool timing, int
         const uint64_t blocks = sv->count / (uint64_t)(kPermThreads * 32);
         int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
             using A = std::remove_pointer_t<decltype(tag)>;
-            static bool configured = false;
+            static bool configured_dev[64] = {};  // the attribute is per device
+            bool& configured = configured_dev[sv->device & 63];
             if (!configured && smem > 48 * 1024) {
                 CU(cudaFuncSetAttribute(k_perm<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
                 configured = true;
@@ -703,8 +741,39 @@ int low_free_bits(const b2sv_subinstr* prog, int entry) {
     return (in.op == B2SV_SUB_FREE && in.pos == 0) ? in.len : 0;
 }
 
+// Number of members of the subspace a (validated) program accepts: what a projection has to read.
+double subprog_members(const b2sv_subinstr* prog, int n_instr, int entry) {
+    std::vector<double> memo(n_instr, -1.0);
+    std::vector<int> stack{entry};
+    while (!stack.empty()) {
+        const int pc = stack.back();
+        const b2sv_subinstr& in = prog[pc];
+        if (memo[pc] >= 0) {
+            stack.pop_back();
+            continue;
+        }
+        if (in.op == B2SV_SUB_END || in.op == B2SV_SUB_REJECT) {
+            memo[pc] = in.op == B2SV_SUB_END ? 1.0 : 0.0;
+            stack.pop_back();
+            continue;
+        }
+        const bool branch = in.op == B2SV_SUB_BRANCH;
+        if (memo[in.next0] < 0 || (branch && memo[in.next1] < 0)) {
+            if ((int)stack.size() > 4 * n_instr + 8) return std::ldexp(1.0, 62);  // malformed (cyclic) program
+            if (memo[in.next0] < 0) stack.push_back(in.next0);
+            if (branch && memo[in.next1] < 0) stack.push_back(in.next1);
+            continue;
+        }
+        if (branch) memo[pc] = memo[in.next0] + memo[in.next1];
+        else if (in.op == B2SV_SUB_FREE) memo[pc] = std::ldexp(memo[in.next0], in.len);
+        else memo[pc] = memo[in.next0];
+        stack.pop_back();
+    }
+    return memo[entry];
+}
+
 int upload_subprog(b2sv* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits, int* count_bits,
-                   int max_target_qubits = -1) {
+                   int max_target_qubits = -1, bool* full_cover = nullptr) {
     if (max_target_qubits < 0) max_target_qubits = sv->n;
     if (!prog || n_instr <= 0) return fail(B2SV_EINVAL, "empty subspace program");
     if (n_instr > kMaxSubInstr) return fail(B2SV_EINVAL, "subspace program has %d instructions (max %d)", n_instr, kMaxSubInstr);
@@ -727,14 +796,16 @@ int upload_subprog(b2sv* sv, const b2sv_subinstr* prog, int n_instr, int entry, 
     // form, max_target_qubits == 64) have had their rank bits resolved on the host
     if (max_target_qubits != 64 && (covered & all) != all)
         return fail(B2SV_EINVAL, "subspace program does not constrain all %d target qubits", target_qubits);
+    if (full_cover) *full_cover = (covered & all) == all;
     // shrink the scan range by the ZEROS runs at the top of the index that every path goes through:
     // conservative version -- follow the entry chain while it is made of ZEROS instructions.
     int bits = target_qubits;
     {
+        // every index goes through the straight-line head of the program (ZEROS / FREE have one successor)
         uint64_t zero_mask = 0;
         int pc = entry;
-        for (int guard = 0; guard < n_instr && prog[pc].op == B2SV_SUB_ZEROS; ++guard) {
-            zero_mask |= (prog[pc].len >= 64 ? ~0ull : ((1ull << prog[pc].len) - 1)) << prog[pc].pos;
+        for (int guard = 0; guard < n_instr && (prog[pc].op == B2SV_SUB_ZEROS || prog[pc].op == B2SV_SUB_FREE); ++guard) {
+            if (prog[pc].op == B2SV_SUB_ZEROS) zero_mask |= (prog[pc].len >= 64 ? ~0ull : ((1ull << prog[pc].len) - 1)) << prog[pc].pos;
             pc = prog[pc].next0;
         }
         while (bits > 0 && ((zero_mask >> (bits - 1)) & 1)) --bits;
@@ -840,6 +911,10 @@ int b2sv_destroy(b2sv_t* sv) {
     for (auto e : sv->event_pool) cudaEventDestroy(e);
     for (auto e : sv->marks)
         if (e) cudaEventDestroy(e);
+    b2sv_ipc_detach(sv);
+    if (sv->ev_ready) cudaEventDestroy(sv->ev_ready);
+    if (sv->ev_done) cudaEventDestroy(sv->ev_done);
+    cudaFree(sv->d_dist_gates);
     cudaFree(sv->amps);
     cudaFree(sv->scratch);
     cudaFree(sv->d_ops);
@@ -862,6 +937,7 @@ int b2sv_set_basis(b2sv_t* sv, uint64_t index) {
     // any other reader materialises it first
     sv->pending_basis = true;
     sv->window = false;
+    sv->zero = false;
     sv->basis_index = index;
     return B2SV_OK;
 }
@@ -873,8 +949,29 @@ int b2sv_set_zero(b2sv_t* sv) {
     sv->sim = 0.0;
     sv->pending_basis = false;
     sv->window = false;
-    sv->stats.launches_by_class[CLS_INIT]++;
-    CU(cudaMemsetAsync(sv->amps, 0, sv->count * sv->amp_bytes, sv->stream));
+    sv->zero = true;  // lazy: nothing is written until somebody needs the zeros (materialise)
+    return B2SV_OK;
+}
+
+int b2sv_fill_random(b2sv_t* sv, uint64_t seed, int support_bits, uint64_t index_base) {
+    if (int rc = check(sv)) return rc;
+    if (support_bits < 0 || support_bits > 63) return fail(B2SV_EINVAL, "support_bits %d outside [0,63]", support_bits);
+    CU(cudaSetDevice(sv->device));
+    sv->sre = 1.0;
+    sv->sim = 0.0;
+    sv->pending_basis = false;
+    sv->window = false;
+    sv->zero = false;
+    const uint64_t support = 1ull << support_bits;
+    const double scale = std::sqrt(1.5 / (double)support);  // E|psi_i|^2 = 2/3 scale^2: unit norm in expectation
+    int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
+        using A = std::remove_pointer_t<decltype(tag)>;
+        LaunchTimer lt(sv, sv->timing_on, CLS_INIT, (double)sv->amp_bytes * (double)sv->count);
+        k_fill_random<A><<<grid_for(sv, sv->count), kThreads, 0, sv->stream>>>((A*)sv->amps, sv->count, support, seed, index_base, scale);
+        return B2SV_OK;
+    });
+    if (rc) return rc;
+    CU(cudaGetLastError());
     return B2SV_OK;
 }
 
@@ -889,6 +986,7 @@ int b2sv_upload(b2sv_t* sv, const void* host) {
     sv->sim = 0.0;
     sv->pending_basis = false;
     sv->window = false;
+    sv->zero = false;
     if (sv->dtype == B2SV_C128) {
         CU(cudaMemcpyAsync(sv->amps, host, sv->count * 16, cudaMemcpyHostToDevice, sv->stream));
         CU(cudaStreamSynchronize(sv->stream));
@@ -945,6 +1043,10 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
     if (int rc = check(sv)) return rc;
     if (n_gates > 0 && !gates) return fail(B2SV_EINVAL, "gates is null");
     CU(cudaSetDevice(sv->device));
+    if (sv->zero) {  // unitary gates map the zero vector to itself
+        sv->stats.gates_in += n_gates;
+        return B2SV_OK;
+    }
     PlanConfig cfg = default_config(sv->n, sv->dtype, opts);
     const bool timing = opts && opts->timing;
     sv->timing_on = timing;
@@ -964,7 +1066,10 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
                            ((uint64_t)cfg.tile_qubits << 8) | ((uint64_t)cfg.lookahead << 16) | ((uint64_t)sv->scratch_failed << 40);
         key = (key ^ o) * 1099511628211ull;
     }
-    const bool reuse = sv->plan_valid && sv->plan_key == key && sv->plan_key2 == key2 && sv->plan_ngates == n_gates;
+    // a hash hit alone could replay another circuit's plan: compare the gate bytes too (cheap next to one sweep)
+    const bool reuse = sv->plan_valid && sv->plan_key == key && sv->plan_key2 == key2 && sv->plan_ngates == n_gates &&
+                       sv->plan_gate_copy.size() == n_gates * sizeof(b2sv_gate) &&
+                       (n_gates == 0 || std::memcmp(sv->plan_gate_copy.data(), gates, n_gates * sizeof(b2sv_gate)) == 0);
     if (!reuse) {
         for (size_t j = 0; j < n_gates; ++j) {
             const b2sv_gate& g = gates[j];
@@ -998,11 +1103,12 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
         std::vector<TileOp> host_ops;
         sv->plan_seg_first.assign(np.segs.size(), 0);
         sv->plan_seg_nops.assign(np.segs.size(), 0);
+        sv->plan_seg_slots.assign(np.segs.size(), {});
         for (size_t s = 0; s < np.segs.size(); ++s) {
             const Segment& seg = np.segs[s];
             if (seg.cls != SEG_TILE && seg.cls != SEG_LOW6) continue;
             sv->plan_seg_first[s] = host_ops.size();
-            build_segment_ops(np, seg, cfg, host_ops);
+            build_segment_ops(np, seg, cfg, host_ops, &sv->plan_seg_slots[s]);
             sv->plan_seg_nops[s] = (int)(host_ops.size() - sv->plan_seg_first[s]);
         }
         if (!host_ops.empty()) {
@@ -1033,6 +1139,7 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
         sv->plan_key = key;
         sv->plan_key2 = key2;
         sv->plan_ngates = n_gates;
+        sv->plan_gate_copy.assign(reinterpret_cast<const unsigned char*>(gates), reinterpret_cast<const unsigned char*>(gates) + n_gates * sizeof(b2sv_gate));
         sv->plan_valid = true;
     }
     const Plan& plan = sv->plan;
@@ -1069,7 +1176,7 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
             bool fused_ops = false;
             for (int gi : seg.gates) fused_ops |= plan.gates[gi].op == B2SV_OP_MUX || plan.gates[gi].op == B2SV_OP_BLOCK;
             rc = launch_tile(sv, seg, (const TileOp*)sv->d_ops + seg_first[s], sv->plan_seg_nops[s], cfg, tile_io, fused_ops, timing, lazy_init,
-                             owner_only);
+                             owner_only, sv->plan_seg_slots[s], plan.mux_tables);
             if (lazy_init) sv->pending_basis = false;
         } else if (seg.cls == SEG_LOW6) {
             rc = launch_low6(sv, seg, (const TileOp*)sv->d_ops + seg_first[s], sv->plan_seg_nops[s], timing, lazy_init, owner_only);
@@ -1100,9 +1207,14 @@ int b2sv_project_norm2_at(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, in
     if (!out) return fail(B2SV_EINVAL, "out is null");
     CU(cudaSetDevice(sv->device));
     if (index_base & (sv->count - 1)) return fail(B2SV_EINVAL, "index_base must have its low %d bits clear", sv->n);
+    if (sv->zero) {
+        *out = 0.0;
+        return B2SV_OK;
+    }
     if (int rc = materialise(sv)) return rc;
     int count_bits = 0;
-    if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits, 64)) return rc;
+    bool full_cover = false;
+    if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits, 64, &full_cover)) return rc;
     if (target_qubits < 64 && (index_base >> target_qubits) != 0) {  // this shard holds ancilla != 0 only
         *out = 0.0;
         return B2SV_OK;
@@ -1113,7 +1225,10 @@ int b2sv_project_norm2_at(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, in
     const int grid = grid_for(sv, grouped ? cnt >> kProjectGroupBits : cnt);
     int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
         using A = std::remove_pointer_t<decltype(tag)>;
-        LaunchTimer lt(sv, sv->timing_on, CLS_PROJECT, (double)sv->amp_bytes * (double)cnt);
+        // algorithmic bytes: the member amplitudes (what has to be read), never more than the scanned range
+        // (per-rank specialised programs do not mention their free bits: book the scanned range for those)
+        const double members = (sv->timing_on && full_cover) ? std::min((double)cnt, subprog_members(prog, n_instr, entry)) : (double)cnt;
+        LaunchTimer lt(sv, sv->timing_on, CLS_PROJECT, (double)sv->amp_bytes * members);
         if (grouped)
             k_project_norm2<A, true><<<grid, kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, index_base,
                                                                        sv->d_partial);
@@ -1157,7 +1272,7 @@ int b2sv_project_gather(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int 
     const double2 s = make_double2(scale_re * sv->sre - scale_im * sv->sim, scale_re * sv->sim + scale_im * sv->sre);
     dispatch_dtype(sv, [&](auto* tag) -> int {
         using A = std::remove_pointer_t<decltype(tag)>;
-        LaunchTimer lt(sv, sv->timing_on, CLS_PROJECT, (double)sv->amp_bytes * (double)cnt + 16.0 * (double)dim);
+        LaunchTimer lt(sv, sv->timing_on, CLS_PROJECT, (double)sv->amp_bytes * std::min((double)cnt, (double)dim) + 16.0 * (double)dim);
         if (low_free_bits(prog, entry) >= kProjectGroupBits && cnt >= (uint64_t)kProjectWarpSpan)
             k_project_gather<A, true><<<grid_for(sv, cnt >> kProjectGroupBits), kThreads, 0, sv->stream>>>(
                 (const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, s, d_out, dim, prog[entry].weight);
@@ -1187,6 +1302,7 @@ int b2sv_embed(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, in
     // the register is overwritten: nothing pending survives
     sv->pending_basis = false;
     sv->window = false;
+    sv->zero = false;
     sv->sre = 1.0;
     sv->sim = 0.0;
     dispatch_dtype(sv, [&](auto* tag) -> int {
@@ -1333,6 +1449,296 @@ int b2sv_swap_pack_range(b2sv_t* sv, int q, int keep_bit, void* staging_dev, uin
 }
 int b2sv_swap_unpack_range(b2sv_t* sv, int q, int keep_bit, const void* staging_dev, uint64_t first, uint64_t count) {
     return swap_pack_impl(sv, q, keep_bit, const_cast<void*>(staging_dev), false, first, count);
+}
+
+
+// ---- distributed execution: peer-mapped shards + one fused gather kernel per exchange ----------------
+
+namespace {
+struct IpcBlob {  // B2SV_IPC_BYTES bytes, plain data
+    cudaIpcMemHandle_t mem[2];
+    cudaIpcEventHandle_t ev[2];
+    int64_t pid;
+    void* raw_buf[2];
+    cudaEvent_t raw_ev[2];
+    int32_t device, n, dtype, pad;
+};
+static_assert(sizeof(IpcBlob) <= B2SV_IPC_BYTES, "IPC blob layout");
+}  // namespace
+
+int b2sv_ipc_export(b2sv_t* sv, void* blob_out) {
+    if (int rc = check(sv)) return rc;
+    if (!blob_out) return fail(B2SV_EINVAL, "blob_out is null");
+    CU(cudaSetDevice(sv->device));
+    if (ensure_scratch(sv) != B2SV_OK) return fail(B2SV_ENOMEM, "no memory for the second state buffer (distributed sweeps are out of place)");
+    if (!sv->own_buf[0]) {
+        sv->own_buf[0] = sv->amps;
+        sv->own_buf[1] = sv->scratch;
+    }
+    if (!sv->ev_ready) {
+        CU(cudaEventCreateWithFlags(&sv->ev_ready, cudaEventDisableTiming | cudaEventInterprocess));
+        CU(cudaEventCreateWithFlags(&sv->ev_done, cudaEventDisableTiming | cudaEventInterprocess));
+    }
+    IpcBlob b;
+    std::memset(&b, 0, sizeof(b));
+    CU(cudaIpcGetMemHandle(&b.mem[0], sv->own_buf[0]));
+    CU(cudaIpcGetMemHandle(&b.mem[1], sv->own_buf[1]));
+    CU(cudaIpcGetEventHandle(&b.ev[0], sv->ev_ready));
+    CU(cudaIpcGetEventHandle(&b.ev[1], sv->ev_done));
+    b.pid = (int64_t)getpid();
+    b.raw_buf[0] = sv->own_buf[0];
+    b.raw_buf[1] = sv->own_buf[1];
+    b.raw_ev[0] = sv->ev_ready;
+    b.raw_ev[1] = sv->ev_done;
+    b.device = sv->device;
+    b.n = sv->n;
+    b.dtype = sv->dtype;
+    std::memset(blob_out, 0, B2SV_IPC_BYTES);
+    std::memcpy(blob_out, &b, sizeof(b));
+    return B2SV_OK;
+}
+
+int b2sv_ipc_detach(b2sv_t* sv) {
+    if (int rc = check(sv)) return rc;
+    if (sv->peers.empty()) return B2SV_OK;
+    cudaSetDevice(sv->device);
+    cudaStreamSynchronize(sv->stream);
+    for (auto& p : sv->peers) {
+        if (!p.ipc) continue;
+        for (int i = 0; i < 2; ++i)
+            if (p.buf[i]) cudaIpcCloseMemHandle(p.buf[i]);
+        if (p.ready) cudaEventDestroy(p.ready);
+        if (p.done) cudaEventDestroy(p.done);
+    }
+    cudaGetLastError();
+    sv->peers.clear();
+    sv->dist_rank = -1;
+    sv->dist_world = 0;
+    return B2SV_OK;
+}
+
+int b2sv_ipc_attach(b2sv_t* sv, int rank, int world, const void* blobs) {
+    if (int rc = check(sv)) return rc;
+    if (!blobs) return fail(B2SV_EINVAL, "blobs is null");
+    if (world < 2 || world > kDistMaxRanks || (world & (world - 1))) return fail(B2SV_EINVAL, "world size %d must be a power of two in [2,%d]", world, kDistMaxRanks);
+    if (rank < 0 || rank >= world) return fail(B2SV_EINVAL, "rank %d outside [0,%d)", rank, world);
+    if (!sv->own_buf[0] || !sv->ev_ready) return fail(B2SV_ESTATE, "b2sv_ipc_export must be called first");
+    CU(cudaSetDevice(sv->device));
+    b2sv_ipc_detach(sv);
+    sv->peers.assign(world, b2sv::Peer());
+    const int64_t me = (int64_t)getpid();
+    for (int r = 0; r < world; ++r) {
+        IpcBlob b;
+        std::memcpy(&b, (const char*)blobs + (size_t)r * B2SV_IPC_BYTES, sizeof(b));
+        if (b.n != sv->n || b.dtype != sv->dtype) {
+            b2sv_ipc_detach(sv);
+            return fail(B2SV_EINVAL, "rank %d holds a %d-qubit dtype-%d shard, this rank a %d-qubit dtype-%d one", r, b.n, b.dtype, sv->n, sv->dtype);
+        }
+        b2sv::Peer& p = sv->peers[r];
+        if (r == rank) {
+            p.buf[0] = sv->own_buf[0];
+            p.buf[1] = sv->own_buf[1];
+            continue;
+        }
+        if (b.pid == me) {  // another handle of this process (threads driving several GPUs): plain pointers
+            if (b.device != sv->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    b2sv_ipc_detach(sv);
+                    return fail(B2SV_ECUDA, "no peer access from device %d to device %d: %s", sv->device, b.device, cudaGetErrorString(e));
+                }
+                cudaGetLastError();
+            }
+            p.buf[0] = b.raw_buf[0];
+            p.buf[1] = b.raw_buf[1];
+            p.ready = b.raw_ev[0];
+            p.done = b.raw_ev[1];
+            continue;
+        }
+        p.ipc = true;
+        cudaError_t e = cudaIpcOpenMemHandle(&p.buf[0], b.mem[0], cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&p.buf[1], b.mem[1], cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) e = cudaIpcOpenEventHandle(&p.ready, b.ev[0]);
+        if (e == cudaSuccess) e = cudaIpcOpenEventHandle(&p.done, b.ev[1]);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            b2sv_ipc_detach(sv);
+            return fail(B2SV_ECUDA, "mapping the shard of rank %d failed: %s", r, cudaGetErrorString(e));
+        }
+    }
+    sv->dist_rank = rank;
+    sv->dist_world = world;
+    return B2SV_OK;
+}
+
+int b2sv_dist_ready(b2sv_t* sv, uint64_t* state_out) {
+    if (int rc = check(sv)) return rc;
+    if (!state_out) return fail(B2SV_EINVAL, "state_out is null");
+    if (sv->dist_world == 0) return fail(B2SV_ESTATE, "not attached (b2sv_ipc_attach)");
+    CU(cudaSetDevice(sv->device));
+    if (sv->pending_basis) {
+        // a basis state nobody has touched yet: one amplitude, everything else implied zeros
+        sv->pending_basis = false;
+        const uint64_t index = sv->basis_index;
+        dispatch_dtype(sv, [&](auto* tag) -> int {
+            using A = std::remove_pointer_t<decltype(tag)>;
+            sv->stats.launches_by_class[CLS_INIT]++;
+            k_set_one<A><<<1, 1, 0, sv->stream>>>((A*)sv->amps, index);
+            return B2SV_OK;
+        });
+        CU(cudaGetLastError());
+        sv->window = true;
+        sv->win_mask = low_mask(sv->n);
+        sv->win_value = index;
+    }
+    std::memset(state_out, 0, 8 * B2SV_DIST_STATE_WORDS);
+    state_out[0] = (sv->amps == sv->own_buf[1] ? 1ull : 0ull) | (sv->window ? 0x100ull : 0ull) | (sv->zero ? 0x200ull : 0ull);
+    if (sv->zero) {
+        state_out[1] = 1;  // (i & 1) == 2 never holds: an empty window
+        state_out[2] = 2;
+    } else if (sv->window) {
+        state_out[1] = sv->win_mask;
+        state_out[2] = sv->win_value;
+    }
+    std::memcpy(&state_out[3], &sv->sre, 8);
+    std::memcpy(&state_out[4], &sv->sim, 8);
+    CU(cudaEventRecord(sv->ev_ready, sv->stream));
+    return B2SV_OK;
+}
+
+int b2sv_dist_perm(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, int n_total, uint32_t flip_in, uint32_t flip_out,
+                   const uint64_t* states, const b2sv_plan_opts* opts) {
+    if (int rc = check(sv)) return rc;
+    if (sv->dist_world == 0) return fail(B2SV_ESTATE, "not attached (b2sv_ipc_attach)");
+    if (n_gates > 0 && !gates) return fail(B2SV_EINVAL, "gates is null");
+    if (!states) return fail(B2SV_EINVAL, "states is null");
+    const int g = n_total - sv->n;
+    if (g < 1 || (1 << g) != sv->dist_world) return fail(B2SV_EINVAL, "n_total %d does not match %d local qubits on %d ranks", n_total, sv->n, sv->dist_world);
+    if (((flip_in | flip_out) >> g) != 0) return fail(B2SV_EINVAL, "flip masks wider than the %d global bits", g);
+    CU(cudaSetDevice(sv->device));
+    const bool timing = opts && opts->timing;
+    const int jit_mode = opts ? opts->jit : 0;
+    std::vector<PGate> pg;
+    pg.reserve(n_gates);
+    {
+        double sre = 1, sim = 0;
+        const uint64_t all = low_mask(n_total);
+        for (size_t j = 0; j < n_gates; ++j) {
+            const b2sv_gate& gt = gates[j];
+            if (gt.op > B2SV_OP_PHASE) return fail(B2SV_EINVAL, "gate %zu: unknown op %d", j, (int)gt.op);
+            PGate p;
+            if (!normalise_gate(gt, (int)j, p, sre, sim)) continue;
+            if (!p.is_perm()) return fail(B2SV_EINVAL, "gate %zu is not an X / SWAP gate: a distributed sweep only moves amplitudes", j);
+            if ((p.qmask & ~all) != 0) return fail(B2SV_EINVAL, "gate %zu: qubit outside the %d-qubit register", j, n_total);
+            if ((p.ctrl & p.tmask) != 0 || (p.op == B2SV_OP_SWAP && p.t0 == p.t1)) return fail(B2SV_EINVAL, "gate %zu: bad targets", j);
+            if (!pg.empty() && same_perm_gate(pg.back(), p)) {
+                pg.pop_back();
+                continue;
+            }
+            pg.push_back(p);
+        }
+        if (!(sre == 1.0 && sim == 0.0)) return fail(B2SV_EINVAL, "a distributed sweep cannot carry a global phase");
+    }
+    DistPermArgs a;
+    std::memset(&a, 0, sizeof(a));
+    bool any_scale = false;
+    for (int r = 0; r < sv->dist_world; ++r) {
+        const uint64_t* st = states + (size_t)r * B2SV_DIST_STATE_WORDS;
+        a.src[r] = sv->peers[r].buf[st[0] & 1ull];
+        a.wmask[r] = st[1];
+        a.wval[r] = st[2];
+        std::memcpy(&a.sre[r], &st[3], 8);
+        std::memcpy(&a.sim[r], &st[4], 8);
+        any_scale |= !(a.sre[r] == 1.0 && a.sim[r] == 0.0);
+    }
+    if (a.src[sv->dist_rank] != sv->amps) return fail(B2SV_ESTATE, "stale state words: call b2sv_dist_ready right before b2sv_dist_perm");
+    a.out = sv->amps == sv->own_buf[0] ? sv->own_buf[1] : sv->own_buf[0];
+    a.rank_logical = (unsigned)sv->dist_rank ^ flip_out;
+    a.flip_in = flip_in;
+    a.has_scale = any_scale ? 1 : 0;
+    // every peer's shard must be final before it is read: wait (on the device) for the events the peers recorded
+    // in b2sv_dist_ready -- the caller's host-side exchange of the state words guarantees they have been recorded
+    for (int r = 0; r < sv->dist_world; ++r)
+        if (r != sv->dist_rank) CU(cudaStreamWaitEvent(sv->stream, sv->peers[r].ready, 0));
+    cudaKernel_t k = nullptr;
+    if (sv->n >= 13 && jit_mode != 1) k = jit_lookup(sv, pg, 2, g);
+    if (k) {
+        void* args[] = {(void*)&a};
+        const uint64_t blocks = sv->count / (uint64_t)(kPermThreads * 32);
+        LaunchTimer lt(sv, timing, CLS_DIST, 2.0 * sv->amp_bytes * (double)sv->count);
+        CU(cudaLaunchKernel((const void*)k, dim3((unsigned)blocks), dim3(kPermThreads), args, 0, sv->stream));
+    } else {
+        // interpreter: shards too small for the bit-sliced layout, or no NVRTC
+        std::vector<DistGate> dg(pg.size());
+        for (size_t j = 0; j < pg.size(); ++j) {
+            std::memset(&dg[j], 0, sizeof(DistGate));
+            dg[j].ctrl = pg[j].ctrl;
+            dg[j].op = pg[j].op;
+            dg[j].t0 = pg[j].t0;
+            dg[j].t1 = pg[j].t1;
+        }
+        const size_t bytes = (dg.size() + 1) * sizeof(DistGate);
+        if (bytes > sv->d_dist_gates_cap) {
+            CU(cudaStreamSynchronize(sv->stream));
+            cudaFree(sv->d_dist_gates);
+            sv->d_dist_gates = nullptr;
+            sv->d_dist_gates_cap = 0;
+            CU(cudaMalloc(&sv->d_dist_gates, bytes * 2));
+            sv->d_dist_gates_cap = bytes * 2;
+        }
+        if (!dg.empty()) CU(cudaMemcpyAsync(sv->d_dist_gates, dg.data(), dg.size() * sizeof(DistGate), cudaMemcpyHostToDevice, sv->stream));
+        int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
+            using A = std::remove_pointer_t<decltype(tag)>;
+            LaunchTimer lt(sv, timing, CLS_DIST, 2.0 * sv->amp_bytes * (double)sv->count);
+            k_dist_perm_generic<A><<<grid_for(sv, sv->count), kThreads, 0, sv->stream>>>(a, (const DistGate*)sv->d_dist_gates, (int)dg.size(), sv->n,
+                                                                                      sv->count);
+            return B2SV_OK;
+        });
+        if (rc) return rc;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(sv->stream));  // dg is pageable host memory
+    }
+    sv->amps = a.out;
+    sv->scratch = sv->amps == sv->own_buf[0] ? sv->own_buf[1] : sv->own_buf[0];
+    sv->window = false;
+    sv->zero = false;
+    sv->pending_basis = false;
+    sv->sre = 1.0;  // every incoming amplitude carried its source shard's scalar
+    sv->sim = 0.0;
+    CU(cudaEventRecord(sv->ev_done, sv->stream));
+    return B2SV_OK;
+}
+
+int b2sv_dist_done(b2sv_t* sv) {
+    if (int rc = check(sv)) return rc;
+    if (sv->dist_world == 0) return fail(B2SV_ESTATE, "not attached (b2sv_ipc_attach)");
+    CU(cudaSetDevice(sv->device));
+    // nobody may overwrite a buffer a peer is still gathering from: this rank's stream continues only when every
+    // peer's sweep is complete (the caller's host barrier guarantees the events have been recorded)
+    for (int r = 0; r < sv->dist_world; ++r)
+        if (r != sv->dist_rank) CU(cudaStreamWaitEvent(sv->stream, sv->peers[r].done, 0));
+    return B2SV_OK;
+}
+
+int b2sv_dist_source(int n_local, int n_global, int dtype, const b2sv_gate* gates, size_t n_gates, char* out, size_t cap, size_t* need) {
+    if (n_local < 10 || n_global < 1 || n_local + n_global > 40) return fail(B2SV_EINVAL, "bad register shape %d + %d", n_local, n_global);
+    if (n_gates > 0 && !gates) return fail(B2SV_EINVAL, "gates is null");
+    std::vector<PGate> pg;
+    double sre = 1, sim = 0;
+    for (size_t j = 0; j < n_gates; ++j) {
+        PGate g;
+        if (!normalise_gate(gates[j], (int)j, g, sre, sim)) continue;
+        if (!g.is_perm()) return fail(B2SV_EINVAL, "gate %zu is not a permutation gate", j);
+        pg.push_back(g);
+    }
+    const std::string src = perm_dist_source(pg, n_local, n_global, dtype);
+    if (need) *need = src.size() + 1;
+    if (out && cap > 0) {
+        const size_t m = src.size() < cap - 1 ? src.size() : cap - 1;
+        std::memcpy(out, src.data(), m);
+        out[m] = 0;
+    }
+    return B2SV_OK;
 }
 
 int b2sv_plan_describe(int n_qubits, int dtype, const b2sv_gate* gates, size_t n_gates, const b2sv_plan_opts* opts,

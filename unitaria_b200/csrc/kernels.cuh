@@ -139,6 +139,8 @@ struct __align__(16) TileOp {
             uint64_t mat_off;      // first double2 of the row-major matrix in TileArgs::tables
             uint8_t kb;
             uint8_t bpos[3];       // tile-local positions of the block qubits (matrix index bit i)
+            uint8_t slot;          // first 256-byte granule of the matrix in the launch's BlkSlots, or 0xFF
+            uint8_t real;          // 1: every entry of the matrix is real (half the FP64 work)
         } blk;
         struct {               // op == kOpPhase: header of a register phase, `count` member ops follow
             uint16_t count;
@@ -269,11 +271,124 @@ __device__ __forceinline__ void tile_for_each(uint32_t cnt, uint64_t fixpos, int
     }
 }
 
+// Dense-block matrices of a sweep travel as KERNEL PARAMETERS (constant bank 0): with the slot number a compile-time
+// constant, every matrix entry is an immediate constant-bank operand of the DFMA that uses it -- no load instruction
+// at all.  (Round 1 read the matrix with __ldg inside the FMA loop: ncu on the heaviest BPX sweep showed 58 % of the
+// stall samples of those DFMAs waiting on that load (long scoreboard), the L1 data pipe at 93 % with a quarter of its
+// wavefronts being matrix loads, and the FP64 pipe 25 % busy.)  A granule is 16 double2 = one 4x4 matrix; an 8x8
+// matrix takes four consecutive granules.
+constexpr int kBlkGranules = 16;
+constexpr int kBlkGranuleElems = 16;
+struct BlkSlots {
+    double2 m[kBlkGranules * kBlkGranuleElems];  // 4 KiB
+};
+
+template <bool REAL>
+__device__ __forceinline__ double2 bmul(double2 m, double2 v) {
+    if (REAL) return make_double2(m.x * v.x, m.x * v.y);
+    return cmul(m, v);
+}
+template <bool REAL>
+__device__ __forceinline__ double2 bfma(double2 m, double2 v, double2 c) {
+    if (REAL) return make_double2(fma(m.x, v.x, c.x), fma(m.x, v.y, c.y));
+    return cfma(m, v, c);
+}
+
+// One dense block pass; U(i) yields entry i of the row-major matrix.
+template <typename A, int KB, bool REAL, typename TV, typename MAT>
+__device__ __forceinline__ void tile_block_pass(TV tile, const TileOp& op, int k, MAT U) {
+    const uint32_t cnt = 1u << (k - op.nfix);
+    if (KB == 3) {
+        const uint32_t b0 = 1u << op.blk.bpos[0], b1 = 1u << op.blk.bpos[1], b2 = 1u << op.blk.bpos[2];
+        tile_for_each<1>(cnt, op.fixpos, op.nfix, op.lctrl, [&](const uint32_t* l, int) {
+            uint32_t off[8];
+            double2 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                off[j] = l[0] | ((j & 1) ? b0 : 0u) | ((j & 2) ? b1 : 0u) | ((j & 4) ? b2 : 0u);
+                v[j] = to_c128(tile[off[j]]);
+            }
+            // four rows at a time: four independent accumulation chains hide the DFMA latency
+#pragma unroll
+            for (int r0 = 0; r0 < 8; r0 += 4) {
+                double2 acc[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[r] = bmul<REAL>(U((r0 + r) * 8), v[0]);
+#pragma unroll
+                for (int c = 1; c < 8; ++c)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) acc[r] = bfma<REAL>(U((r0 + r) * 8 + c), v[c], acc[r]);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) tile[off[r0 + r]] = from_c128<A>(acc[r]);
+            }
+        });
+    } else {  // KB == 2
+        const uint32_t b0 = 1u << op.blk.bpos[0], b1 = 1u << op.blk.bpos[1];
+        tile_for_each<1>(cnt, op.fixpos, op.nfix, op.lctrl, [&](const uint32_t* l, int) {
+            uint32_t off[4];
+            double2 v[4], acc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                off[j] = l[0] | ((j & 1) ? b0 : 0u) | ((j & 2) ? b1 : 0u);
+                v[j] = to_c128(tile[off[j]]);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] = bmul<REAL>(U(r * 4), v[0]);
+#pragma unroll
+            for (int c = 1; c < 4; ++c)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[r] = bfma<REAL>(U(r * 4 + c), v[c], acc[r]);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) tile[off[r]] = from_c128<A>(acc[r]);
+        });
+    }
+}
+
+template <typename A, int KB, int G, typename TV>
+__device__ __forceinline__ void tile_block_slot(TV tile, const TileOp& op, int k, const BlkSlots* bs) {
+    auto U = [bs](int i) { return bs->m[G * kBlkGranuleElems + i]; };  // G and i are compile-time: an immediate operand
+    if (op.blk.real) tile_block_pass<A, KB, true>(tile, op, k, U);
+    else tile_block_pass<A, KB, false>(tile, op, k, U);
+}
+
+template <typename A, typename TV>
+__device__ __forceinline__ void tile_apply_block(TV tile, const TileOp& op, int k, const double2* __restrict__ tables, const BlkSlots* bs) {
+    if (bs != nullptr && op.blk.slot != 0xFF) {
+        if (op.blk.kb == 3) {
+            switch (op.blk.slot) {
+                case 0: tile_block_slot<A, 3, 0>(tile, op, k, bs); break;
+                case 4: tile_block_slot<A, 3, 4>(tile, op, k, bs); break;
+                case 8: tile_block_slot<A, 3, 8>(tile, op, k, bs); break;
+                default: tile_block_slot<A, 3, 12>(tile, op, k, bs); break;
+            }
+        } else {
+            switch (op.blk.slot) {
+#define B2SV_CASE(G) case G: tile_block_slot<A, 2, G>(tile, op, k, bs); break;
+                B2SV_CASE(0) B2SV_CASE(1) B2SV_CASE(2) B2SV_CASE(3) B2SV_CASE(4) B2SV_CASE(5) B2SV_CASE(6) B2SV_CASE(7)
+                B2SV_CASE(8) B2SV_CASE(9) B2SV_CASE(10) B2SV_CASE(11) B2SV_CASE(12) B2SV_CASE(13) B2SV_CASE(14)
+#undef B2SV_CASE
+                default: tile_block_slot<A, 2, 15>(tile, op, k, bs); break;
+            }
+        }
+        return;
+    }
+    // no slot left in this launch (or a kernel without the parameter block): the matrix comes through the read-only path
+    const double2* __restrict__ Ug = tables + op.blk.mat_off;
+    auto U = [Ug](int i) { return __ldg(Ug + i); };
+    if (op.blk.kb == 3) {
+        if (op.blk.real) tile_block_pass<A, 3, true>(tile, op, k, U);
+        else tile_block_pass<A, 3, false>(tile, op, k, U);
+    } else {
+        if (op.blk.real) tile_block_pass<A, 2, true>(tile, op, k, U);
+        else tile_block_pass<A, 2, false>(tile, op, k, U);
+    }
+}
+
 // FUSED = false compiles the light variant (no table-driven ops): fewer registers for sweeps that
 // only hold plain gates.
 template <typename A, bool FUSED, typename TV>
 __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, uint64_t base,
-                                              const double2* __restrict__ tables) {
+                                              const double2* __restrict__ tables, const BlkSlots* bs) {
     const uint32_t cnt = 1u << (k - op.nfix);
     const uint64_t fixpos = op.fixpos;
     const int nfix = op.nfix;
@@ -407,53 +522,8 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
             });
         } break;
         case kOpBlock: if constexpr (FUSED) {
-            // every group of 2^kb amplitudes (block bits free, predicate bits set) is multiplied by one
-            // dense matrix; the matrix is read through the read-only path at warp-uniform addresses
-            const double2* __restrict__ U = tables + op.blk.mat_off;
-            if (op.blk.kb == 3) {
-                const uint32_t b0 = 1u << op.blk.bpos[0], b1 = 1u << op.blk.bpos[1], b2 = 1u << op.blk.bpos[2];
-                tile_for_each<1>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int) {
-                    uint32_t off[8];
-                    double2 v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        off[j] = l[0] | ((j & 1) ? b0 : 0u) | ((j & 2) ? b1 : 0u) | ((j & 4) ? b2 : 0u);
-                        v[j] = to_c128(tile[off[j]]);
-                    }
-                    // four rows at a time: four independent accumulation chains hide the DFMA latency
-#pragma unroll
-                    for (int r0 = 0; r0 < 8; r0 += 4) {
-                        double2 acc[4];
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) acc[r] = cmul(__ldg(U + (r0 + r) * 8), v[0]);
-#pragma unroll
-                        for (int c = 1; c < 8; ++c)
-#pragma unroll
-                            for (int r = 0; r < 4; ++r) acc[r] = cfma(__ldg(U + (r0 + r) * 8 + c), v[c], acc[r]);
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) tile[off[r0 + r]] = from_c128<A>(acc[r]);
-                    }
-                });
-            } else {  // kb == 2
-                const uint32_t b0 = 1u << op.blk.bpos[0], b1 = 1u << op.blk.bpos[1];
-                tile_for_each<1>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int) {
-                    uint32_t off[4];
-                    double2 v[4], acc[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        off[j] = l[0] | ((j & 1) ? b0 : 0u) | ((j & 2) ? b1 : 0u);
-                        v[j] = to_c128(tile[off[j]]);
-                    }
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) acc[r] = cmul(__ldg(U + r * 4), v[0]);
-#pragma unroll
-                    for (int c = 1; c < 4; ++c)
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) acc[r] = cfma(__ldg(U + r * 4 + c), v[c], acc[r]);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) tile[off[r]] = from_c128<A>(acc[r]);
-                });
-            }
+            // every group of 2^kb amplitudes (block bits free, predicate bits set) is multiplied by one dense matrix
+            tile_apply_block<A>(tile, op, k, tables, bs);
         } break;
         default: {  // PHASE
             const double2 w = make_double2(op.m[0], op.m[1]);
@@ -678,7 +748,7 @@ __device__ __forceinline__ void tile_apply_mono(TV tile, const TileOp& hdr, uint
 // Run the staged ops [0, n) of a sweep on the tile in shared memory.
 template <typename A, bool FUSED, typename TV>
 __device__ __forceinline__ void tile_run_ops(TV tile, const TileOp* s_ops, int n, int k, uint64_t base,
-                                             const double2* __restrict__ tables) {
+                                             const double2* __restrict__ tables, const BlkSlots* bs) {
     for (int o = 0; o < n; ++o) {
         const TileOp& op = s_ops[o];
         if (op.op == kOpMono) {
@@ -703,7 +773,7 @@ __device__ __forceinline__ void tile_run_ops(TV tile, const TileOp* s_ops, int n
         }
         if (op.op == kOpNop) continue;
         if ((base & op.ext_ctrl) != op.ext_ctrl) continue;  // CTA-uniform: gate not active on this tile
-        tile_apply_op<A, FUSED>(tile, op, k, base, tables);
+        tile_apply_op<A, FUSED>(tile, op, k, base, tables, bs);
         __syncthreads();
     }
 }
@@ -719,7 +789,7 @@ __device__ __forceinline__ void tile_stage_ops(TileOp* s_ops, const TileOp* g_op
 
 template <typename A, bool FUSED, typename TV>
 __device__ __forceinline__ void tile_run_batches(TV tile, TileOp* s_ops, const TileOp* g_ops, int n_ops, int k, uint64_t base,
-                                                 const double2* __restrict__ tables) {
+                                                 const double2* __restrict__ tables, const BlkSlots* bs) {
     for (int b0 = 0; b0 < n_ops; b0 += kTileMaxOps) {
         const int nb = n_ops - b0 < kTileMaxOps ? n_ops - b0 : kTileMaxOps;
         if (b0 > 0) {
@@ -727,7 +797,7 @@ __device__ __forceinline__ void tile_run_batches(TV tile, TileOp* s_ops, const T
             tile_stage_ops(s_ops, g_ops + b0, nb, (int)threadIdx.x, (int)blockDim.x);
             __syncthreads();
         }
-        tile_run_ops<A, FUSED>(tile, s_ops, nb, k, base, tables);
+        tile_run_ops<A, FUSED>(tile, s_ops, nb, k, base, tables, bs);
     }
 }
 
@@ -789,7 +859,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile(A* __restrict__ psi, const
     // a generated (lazy-init) tile that does not hold the basis index is all zeros: every gate maps it to
     // itself, so only the one tile that owns the index runs the gates -- the others just write zeros
     const int n_ops_here = (load || (a.init_index & ~a.tile_mask) == base) ? a.n_ops : 0;
-    tile_run_batches<A, FUSED>(TileView<A, false>{tile}, s_ops, a.ops, n_ops_here, k, base, a.tables);
+    tile_run_batches<A, FUSED>(TileView<A, false>{tile}, s_ops, a.ops, n_ops_here, k, base, a.tables, nullptr);
 
     if (BULK) {
         // generic-proxy writes to shared memory must be visible to the async proxy before the copy out
@@ -829,6 +899,7 @@ __device__ __forceinline__ void tma_s2g_2d(const CUtensorMap* map, uint32_t c0, 
 struct alignas(64) TileArgsSwz {
     CUtensorMap map;  // {16 doubles (128 B), rows}, box {16, rows per chunk}, SWIZZLE_128B
     TileArgs t;
+    BlkSlots blk;     // the sweep's dense-block matrices (immediate constant-bank operands, see tile_apply_block)
 };
 
 template <typename A, bool FUSED>
@@ -881,7 +952,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile_swz(const __grid_constant_
     // a generated (lazy-init) tile that does not hold the basis index is all zeros: every gate maps it to
     // itself, so only the one tile that owns the index runs the gates -- the others just write zeros
     const int n_ops_here = (load || (a.init_index & ~a.tile_mask) == base) ? a.n_ops : 0;
-    tile_run_batches<A, FUSED>(tile, s_ops, a.ops, n_ops_here, k, base, a.tables);
+    tile_run_batches<A, FUSED>(tile, s_ops, a.ops, n_ops_here, k, base, a.tables, FUSED ? &args.blk : nullptr);
 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -891,94 +962,6 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile_swz(const __grid_constant_
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Persistent, pipelined form of the tile sweep: ONE CTA per SM walks over its tiles with a ring of
-// three shared-memory stages, so that at any time one tile is arriving (bulk-async copies tracked by
-// an mbarrier), one is being worked on by all threads, and one is leaving (bulk-async stores).  The
-// TMA engine keeps HBM busy while every thread computes, which is what lets a sweep carry several
-// full-touch gates at the copy roofline (the one-tile-per-CTA kernel above only overlaps through
-// occupancy: 3 CTAs/SM, each idle on memory half of the time).
-// ---------------------------------------------------------------------------------------------------
-constexpr int kPipeThreads = 512;
-constexpr int kPipeStages = 3;
-
-template <typename A, bool FUSED>
-__global__ void __launch_bounds__(kPipeThreads, 1) k_tile_pipe(A* __restrict__ psi, const TileArgs a, uint32_t n_tiles) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const int k = a.k, lc = a.lc;
-    const size_t tile_bytes = (size_t)sizeof(A) << k;
-    TileOp* s_ops = reinterpret_cast<TileOp*>(smem_raw + kPipeStages * tile_bytes);
-    __shared__ __align__(8) uint64_t full[kPipeStages];
-    const int tid = threadIdx.x;
-    const uint32_t n_chunks = 1u << (k - lc), chunk_elems = 1u << lc;
-    const uint32_t chunk_bytes = chunk_elems * (uint32_t)sizeof(A);
-    const bool load = a.init_mode == 0;
-
-    if (tid == 0) {
-        for (int s = 0; s < kPipeStages; ++s) mbar_init(&full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(a.ops);
-        uint4* dst = reinterpret_cast<uint4*>(s_ops);
-        const int n16 = a.n_ops * (int)(sizeof(TileOp) / 16);
-        for (int i = tid; i < n16; i += kPipeThreads) dst[i] = __ldg(src + i);
-    }
-    __syncthreads();
-
-    // the first min(n_chunks, 32) threads own the bulk copies: thread j moves chunks j, j+32, ...
-    // (bulk-store groups are per thread, so the thread that stored a stage is the one that waits for it)
-    auto issue_load = [&](uint32_t tile_id, int stage) {
-        A* tile = reinterpret_cast<A*>(smem_raw + stage * tile_bytes);
-        const uint64_t base = expand_bits((uint64_t)tile_id, a.cta_ex) | a.cta_or;
-        if (tid == 0) mbar_expect_tx(&full[stage], chunk_bytes * n_chunks);
-        __syncwarp();
-        for (uint32_t j = tid; j < n_chunks; j += 32)
-            bulk_g2s(tile + (size_t)j * chunk_elems, psi + (base | chunk_offset(j, a.tile_ex, k, lc)), chunk_bytes, &full[stage]);
-    };
-
-    uint32_t it = 0;
-    if (load && tid < 32 && blockIdx.x < n_tiles) issue_load(blockIdx.x, 0);
-    for (uint32_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x, ++it) {
-        const int stage = (int)(it % kPipeStages);
-        A* tile = reinterpret_cast<A*>(smem_raw + stage * tile_bytes);
-        const uint64_t base = expand_bits((uint64_t)tile_id, a.cta_ex) | a.cta_or;
-        // prefetch the next tile into the stage that held tile it-2: its store must have drained
-        const uint32_t next_id = tile_id + gridDim.x;
-        if (tid < 32) {
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            if (load && next_id < n_tiles) issue_load(next_id, (int)((it + 1) % kPipeStages));
-        }
-        if (load) {
-            mbar_wait(&full[stage], (it / kPipeStages) & 1u);
-        } else {
-            // not-yet-materialised basis state: generate the tile; the stage may still be draining
-            // (stores of tile it-3) -- the wait_group above only covers it-2, so wait for all but one
-            if (tid < 32) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            __syncthreads();
-            const uint32_t elems = 1u << k;
-            const A zero = from_c128<A>(make_double2(0.0, 0.0));
-            for (uint32_t l = tid; l < elems; l += kPipeThreads) tile[l] = zero;
-            __syncthreads();
-            if (tid == 0 && (a.init_index & ~a.tile_mask) == base) {
-                uint32_t l = 0;
-                for (int i = 0; i < k; ++i) l |= (uint32_t)((a.init_index >> a.tile_ex.pos[i]) & 1ull) << i;
-                tile[l] = from_c128<A>(make_double2(1.0, 0.0));
-            }
-            __syncthreads();
-        }
-        tile_run_ops<A, FUSED>(TileView<A, false>{tile}, s_ops, a.n_ops, k, base, a.tables);  // single batch (host checks)
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (tid < 32) {
-            for (uint32_t j = tid; j < n_chunks; j += 32)
-                bulk_s2g(psi + (base | chunk_offset(j, a.tile_ex, k, lc)), tile + (size_t)j * chunk_elems, chunk_bytes);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-    }
-    if (tid < 32) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1290,6 +1273,86 @@ __global__ void __launch_bounds__(kPermThreads) k_perm(const A* __restrict__ in,
 #pragma unroll
         for (int u = 0; u < 8; ++u) out[warp_base + (uint64_t)(b0 + u) * 32 + lane] = v[u];
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Distributed permutation sweep (sharded register, one process per GPU): out[j] = s_r * in_r[f^-1(rank:j)],
+// where the upper bits of the source index pick the peer shard `r` to read -- peers' shards are mapped into
+// this process with CUDA IPC, so the loads below go over NVLink.  The NVRTC-specialised form of this kernel
+// is generated by perm_jit.hpp (perm_dist_source); the interpreter below is what runs for shards too small
+// for the bit-sliced layout (< 2^13 amplitudes) or when NVRTC is not available.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kDistMaxRanks = 16;
+
+struct DistPermArgs {
+    const void* src[kDistMaxRanks];                        // current state buffer of every rank (own pointer for itself)
+    unsigned long long wmask[kDistMaxRanks], wval[kDistMaxRanks];  // live window of every source shard (0,0: all of it)
+    double sre[kDistMaxRanks], sim[kDistMaxRanks];         // pending lazy scalar of every source shard
+    void* out;
+    unsigned rank_logical;  // logical values of the global index bits of this rank's outputs
+    unsigned flip_in;       // physical source rank = logical source bits ^ flip_in
+    int has_scale;
+    int pad;
+};
+
+struct DistGate {
+    uint64_t ctrl;
+    uint8_t op, t0, t1, pad[5];
+};
+
+template <typename A>
+__global__ void __launch_bounds__(kThreads) k_dist_perm_generic(const __grid_constant__ DistPermArgs a, const DistGate* __restrict__ gates,
+                                                                int n_gates, int nl, uint64_t count) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t lmask = (1ull << nl) - 1ull;
+    A* out = reinterpret_cast<A*>(a.out);
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {
+        uint64_t idx = j | ((uint64_t)a.rank_logical << nl);
+        for (int gi = n_gates - 1; gi >= 0; --gi) {  // gather: the self-inverse gates in reverse order
+            const DistGate g = gates[gi];
+            if ((idx & g.ctrl) != g.ctrl) continue;
+            if (g.op == B2SV_OP_X) {
+                idx ^= 1ull << g.t0;
+            } else if (((idx >> g.t0) ^ (idx >> g.t1)) & 1ull) {
+                idx ^= (1ull << g.t0) | (1ull << g.t1);
+            }
+        }
+        const unsigned r = (unsigned)(idx >> nl) ^ a.flip_in;
+        const uint64_t s = idx & lmask;
+        A v = from_c128<A>(make_double2(0.0, 0.0));
+        if ((s & a.wmask[r]) == a.wval[r]) v = reinterpret_cast<const A*>(a.src[r])[s];
+        if (a.has_scale) v = from_c128<A>(cmul(make_double2(a.sre[r], a.sim[r]), to_c128(v)));
+        out[j] = v;
+    }
+}
+
+// Seeded dense test vector, generated on the device (benchmarks and full-size property tests: no 2^n host array, no
+// PCIe upload): psi_i = scale * (u(2i), u(2i+1)) for global index index_base + i < support, 0 above, with
+// u(k) = splitmix64(seed + k) mapped to [-1, 1).  tests/helpers.py restates the same hash in numpy.
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__host__ __device__ __forceinline__ double hash_unit(uint64_t seed, uint64_t k) {
+    return (double)(splitmix64(seed + k) >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+}
+template <typename A>
+__global__ void __launch_bounds__(kThreads) k_fill_random(A* __restrict__ psi, uint64_t count, uint64_t support, uint64_t seed,
+                                                          uint64_t index_base, double scale) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const uint64_t gi = index_base + i;
+        double2 v = make_double2(0.0, 0.0);
+        if (gi < support) v = make_double2(scale * hash_unit(seed, 2 * gi), scale * hash_unit(seed, 2 * gi + 1));
+        psi[i] = from_c128<A>(v);
+    }
+}
+
+template <typename A>
+__global__ void k_set_one(A* __restrict__ psi, uint64_t index) {
+    psi[index] = from_c128<A>(make_double2(1.0, 0.0));
 }
 
 // ===================================================================================================

@@ -98,6 +98,112 @@ inline std::string perm_jit_source(const std::vector<PGate>& exec_order, int n, 
     return s;
 }
 
+// ---- distributed form: the same sweep over a register sharded across GPUs -----------------------------
+//
+// The index map of a permutation run does not care where an amplitude lives: with the statevector split by the
+// top g index positions over 2^g GPUs of one NVSwitch box, output j of rank r still is in[f^-1(r:j)] -- and the
+// upper g bits of that source index say WHICH GPU holds it.  Every rank maps its peers' shards into its own
+// address space (CUDA IPC, b2sv_ipc_attach) and this kernel gathers straight out of their HBM over NVLink:
+// index arithmetic, the all-to-all and the write-out are ONE kernel, nothing is packed, staged or unpacked.
+// Multi-controlled X gates whose TARGET is a global qubit (the carry chain of an Increment that runs across
+// the rank boundary) therefore need no qubit swap at all -- almost every source is local -- and a real
+// global<->local swap of k qubits is the same kernel with SWAP gates: one pass, (1 - 2^-k) of the shard
+// crosses NVLink once.
+//
+// Words 0..nl-1 are the local index bits (as in b2sv_perm_jit), words nl..nl+g-1 the LOGICAL values of the
+// global positions on this rank (physical rank bit ^ flip flag: an uncontrolled X on a global qubit is a rank
+// relabel, unitaria_b200/distributed.py).  After the run the source rank of output b is the logical source
+// bits ^ flip_in.  Per source rank the kernel gets the shard pointer, its live window (zero outside, not even
+// materialised -- a rank that holds no amplitude at all has an empty window) and its pending lazy scalar.
+// (struct DistPermArgs: kernels.cuh; mirrored textually in the generated source)
+inline std::string perm_dist_source(const std::vector<PGate>& exec_order, int nl, int g, int dtype) {
+    std::string s;
+    s.reserve(exec_order.size() * 40 + 8192);
+    char buf[320];
+    const int n = nl + g;
+    s += dtype == B2SV_C64 ? "typedef float2 amp_t;\n" : "typedef double2 amp_t;\n";
+    s += "struct DistPermArgs { const amp_t* src[16]; unsigned long long wmask[16], wval[16]; double sre[16], sim[16]; amp_t* out; "
+         "unsigned rank_logical; unsigned flip_in; int has_scale; int pad; };\n";
+    s += "extern \"C\" __global__ void __launch_bounds__(256) b2sv_perm_dist(const __grid_constant__ DistPermArgs a) {\n";
+    s += "  const unsigned tid = threadIdx.x, lane = tid & 31u;\n";
+    s += "  const unsigned long long wg = ((unsigned long long)blockIdx.x * blockDim.x + tid) >> 5;\n";
+    s += "  const unsigned long long warp_base = wg << 10;\n";
+    static const char* pat[5] = {"0xAAAAAAAAu", "0xCCCCCCCCu", "0xF0F0F0F0u", "0xFF00FF00u", "0xFFFF0000u"};
+    for (int q = 0; q < n; ++q) {
+        if (q >= nl) snprintf(buf, sizeof(buf), "  unsigned w%d = ((a.rank_logical >> %d) & 1u) ? 0xFFFFFFFFu : 0u;\n", q, q - nl);
+        else if (q < 5) snprintf(buf, sizeof(buf), "  unsigned w%d = ((lane >> %d) & 1u) ? 0xFFFFFFFFu : 0u;\n", q, q);
+        else if (q < 10) snprintf(buf, sizeof(buf), "  unsigned w%d = %s;\n", q, pat[q - 5]);
+        else snprintf(buf, sizeof(buf), "  unsigned w%d = ((wg >> %d) & 1ull) ? 0xFFFFFFFFu : 0u;\n", q, q - 10);
+        s += buf;
+    }
+    for (size_t gi = exec_order.size(); gi-- > 0;) {  // gather: the self-inverse gates in reverse order
+        const PGate& gt = exec_order[gi];
+        std::string m;
+        for (int q = 0; q < 64; ++q)
+            if ((gt.ctrl >> q) & 1) {
+                snprintf(buf, sizeof(buf), "%sw%d", m.empty() ? "" : " & ", q);
+                m += buf;
+            }
+        if (gt.op == B2SV_OP_X) {
+            if (m.empty()) snprintf(buf, sizeof(buf), "  w%d = ~w%d;\n", (int)gt.t0, (int)gt.t0);
+            else snprintf(buf, sizeof(buf), "  w%d ^= %s;\n", (int)gt.t0, m.c_str());
+        } else if (m.empty()) {
+            snprintf(buf, sizeof(buf), "  { const unsigned d = w%d ^ w%d; w%d ^= d; w%d ^= d; }\n", (int)gt.t0, (int)gt.t1, (int)gt.t0, (int)gt.t1);
+        } else {
+            snprintf(buf, sizeof(buf), "  { const unsigned d = (w%d ^ w%d) & %s; w%d ^= d; w%d ^= d; }\n", (int)gt.t0, (int)gt.t1, m.c_str(),
+                     (int)gt.t0, (int)gt.t1);
+        }
+        s += buf;
+    }
+    s += "  unsigned t[32] = {";
+    for (int q = 0; q < 32; ++q) {
+        if (q < nl) snprintf(buf, sizeof(buf), "w%d%s", q, q == 31 ? "" : ", ");
+        else snprintf(buf, sizeof(buf), "0u%s", q == 31 ? "" : ", ");
+        s += buf;
+    }
+    s += "};\n";
+    s += "  unsigned m = 0x0000FFFFu;\n"
+         "  #pragma unroll\n"
+         "  for (int j = 16; j != 0; j >>= 1) {\n"
+         "    #pragma unroll\n"
+         "    for (int k = 0; k < 32; ++k) {\n"
+         "      if ((k & j) == 0) { const unsigned x = ((t[k] >> j) ^ t[k + j]) & m; t[k] ^= x << j; t[k + j] ^= x; }\n"
+         "    }\n"
+         "    m ^= m << (j >> 1);\n"
+         "  }\n";
+    s += "  amp_t zero; zero.x = 0; zero.y = 0;\n"
+         "  #pragma unroll\n"
+         "  for (int b0 = 0; b0 < 32; b0 += 8) {\n"
+         "    unsigned long long src[8];\n"
+         "    unsigned r[8];\n"
+         "    #pragma unroll\n"
+         "    for (int u = 0; u < 8; ++u) { src[u] = t[b0 + u]; r[u] = a.flip_in; }\n";
+    for (int q = 32; q < nl; ++q) {
+        snprintf(buf, sizeof(buf),
+                 "    #pragma unroll\n    for (int u = 0; u < 8; ++u) src[u] |= (unsigned long long)((w%d >> (b0 + u)) & 1u) << %d;\n", q, q);
+        s += buf;
+    }
+    for (int i = 0; i < g; ++i) {
+        snprintf(buf, sizeof(buf), "    #pragma unroll\n    for (int u = 0; u < 8; ++u) r[u] ^= ((w%d >> (b0 + u)) & 1u) << %d;\n", nl + i, i);
+        s += buf;
+    }
+    s += "    amp_t v[8];\n"
+         "    #pragma unroll\n"
+         "    for (int u = 0; u < 8; ++u) v[u] = ((src[u] & a.wmask[r[u]]) == a.wval[r[u]]) ? a.src[r[u]][src[u]] : zero;\n"
+         "    if (a.has_scale) {\n"
+         "      #pragma unroll\n"
+         "      for (int u = 0; u < 8; ++u) {\n"
+         "        const double sr = a.sre[r[u]], si = a.sim[r[u]], x = (double)v[u].x, y = (double)v[u].y;\n"
+         "        v[u].x = x * sr - y * si; v[u].y = x * si + y * sr;\n"
+         "      }\n"
+         "    }\n"
+         "    #pragma unroll\n"
+         "    for (int u = 0; u < 8; ++u) a.out[warp_base + (unsigned long long)(b0 + u) * 32ull + lane] = v[u];\n"
+         "  }\n"
+         "}\n";
+    return s;
+}
+
 // ---- NVRTC through dlopen: the library keeps no link-time dependency on it --------------------------
 
 struct NvrtcApi {

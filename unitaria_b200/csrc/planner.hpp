@@ -476,80 +476,149 @@ inline void gate_sources(const Plan& plan, const PGate& g, std::vector<int>& out
     else out.push_back(g.src);
 }
 
+// FP64 work of a plain gate inside a register phase, in DFMA per 8 amplitudes (`common`: controls every gate of the
+// run shares -- they scale both alternatives alike).  Register phases apply a gate to the four pairs a thread
+// holds: a complex 2x2 is 4 x 16 DFMA, a real one half of that, a diagonal 4 x 8; X and SWAP are register moves.
+inline bool gate_is_real(const PGate& g) {
+    if (g.op == B2SV_OP_MAT1) return g.m[1] == 0.0 && g.m[3] == 0.0 && g.m[5] == 0.0 && g.m[7] == 0.0;
+    if (g.op == B2SV_OP_DIAG1) return g.m[1] == 0.0 && g.m[3] == 0.0;
+    if (g.op == B2SV_OP_PHASE) return g.m[1] == 0.0;
+    return true;
+}
+inline double gate_fp64_cost(const PGate& g, uint64_t common) {
+    const double f = std::ldexp(1.0, -popcount64(g.ctrl & ~common));
+    switch (g.op) {
+        case B2SV_OP_MAT1: return f * (gate_is_real(g) ? 32.0 : 64.0);
+        case B2SV_OP_DIAG1:
+        case B2SV_OP_PHASE: return f * 32.0;
+        default: return 0.0;
+    }
+}
+// one dense block pass: 2^kb complex FMAs per amplitude (half for a real matrix) plus a shared-memory round trip of
+// its own (a register phase would have carried the gates along with its neighbours)
+inline double block_fp64_cost(int kb, bool real) { return (kb == 3 ? 256.0 : 128.0) * (real ? 0.5 : 1.0) * fuse_margin() + 96.0; }
+
+// Build the dense matrix of G[a, b) on its <= 3 qubits and append the BLOCK gate to `out`.
+inline void emit_block(Plan& plan, const std::vector<PGate>& G, size_t a, size_t b, std::vector<PGate>& out) {
+    uint64_t K = G[a].ctrl, T = gate_targets(G[a]), U = G[a].ctrl;
+    for (size_t q = a + 1; q < b; ++q) {
+        K &= G[q].ctrl;
+        T |= gate_targets(G[q]);
+        U |= G[q].ctrl;
+    }
+    const uint64_t B = T | (U & ~K);
+    BlockInfo info;
+    info.kb = popcount64(B);
+    int nb = 0;
+    for (int bit = 0; bit < 64; ++bit)
+        if ((B >> bit) & 1) info.q[nb++] = (uint8_t)bit;
+    const uint32_t dim = 1u << info.kb;
+    std::vector<double> mat((size_t)2 * dim * dim, 0.0);  // row-major, (re,im)
+    for (uint32_t col = 0; col < dim; ++col) {
+        double v[2 * 8] = {0};
+        v[2 * col] = 1.0;
+        for (size_t qg = a; qg < b; ++qg) block_apply_gate(v, info.kb, info.q, G[qg], K);
+        for (uint32_t row = 0; row < dim; ++row) {
+            mat[2 * ((size_t)row * dim + col)] = v[2 * row];
+            mat[2 * ((size_t)row * dim + col) + 1] = v[2 * row + 1];
+        }
+    }
+    while (plan.mux_tables.size() % 8) plan.mux_tables.push_back(0.0);  // keep multiplexor entries aligned
+    info.mat_off = plan.mux_tables.size() / 2;
+    plan.mux_tables.insert(plan.mux_tables.end(), mat.begin(), mat.end());
+    for (size_t qg = a; qg < b; ++qg) gate_sources(plan, G[qg], info.sources);
+    PGate f;
+    f.op = B2SV_OP_BLOCK;
+    f.t0 = info.q[0];
+    f.t1 = 0;
+    f.ctrl = K;
+    f.tmask = B;
+    f.qmask = B | K;
+    for (int e = 0; e < 8; ++e) f.m[e] = 0;
+    f.src = G[a].src;
+    f.blk = (int)plan.blocks.size();
+    plan.blocks.push_back(std::move(info));
+    out.push_back(f);
+}
+
+// A maximal run of consecutive gates confined to <= 3 qubits is cut into pieces, each either left as plain gates
+// (they ride in register phases) or multiplied out into one dense 4x4 / 8x8 block, so that the FP64 work is smallest
+// (dynamic programme over the cut points).  ncu on the BPX sweeps (profiles/ncu_r2_bpx.txt) showed what the greedy
+// "one block per run" of round 1 cost: the 2-qubit cosine-sine unitaries of circuits/generic_unitary.py (6 Ry, 9 Rz,
+// 6 phases, 6 CNOT: 672 DFMA per 8 amplitudes as plain gates, 128 as a 4x4 block) were followed by ONE SWAP with a
+// third qubit, which turned each of them into an 8x8 block at twice the work.
 inline void fuse_blocks(Plan& plan) {
     std::vector<PGate> out;
     out.reserve(plan.gates.size());
     const std::vector<PGate>& G = plan.gates;
     size_t i = 0;
     while (i < G.size()) {
-        const PGate& g = G[i];
-        if (!blockable_gate(g)) {
-            out.push_back(g);
+        if (!blockable_gate(G[i])) {
+            out.push_back(G[i]);
             ++i;
             continue;
         }
-        uint64_t K = g.ctrl, T = gate_targets(g), U = g.ctrl;
-        bool nonperm = !g.is_perm();
-        double separate = gate_sweep_fraction(g);
+        // the maximal run on <= 3 qubits starting here
         size_t j = i + 1;
-        while (j < G.size() && blockable_gate(G[j])) {
-            const uint64_t K2 = K & G[j].ctrl, T2 = T | gate_targets(G[j]), U2 = U | G[j].ctrl;
-            const uint64_t B2 = T2 | (U2 & ~K2);
-            if (popcount64(B2) > kBlockMaxQubits || (T2 & K2) != 0) break;
-            K = K2;
-            T = T2;
-            U = U2;
-            nonperm |= !G[j].is_perm();
-            separate += gate_sweep_fraction(G[j]);
-            ++j;
-        }
-        const size_t len = j - i;
-        const uint64_t B = T | (U & ~K);
-        const int kb = popcount64(B);
-        // measured on B200 (scripts/microbench_tile.py, 26 qubits): one block pass in units of a plain
-        // full-touch 2x2 gate: kb=2 ~1.5, kb=3 ~5 (DFMA-bound); a table-driven multiplexor pass ~1.7
-        static const double block_cost[4] = {0.6, 1.0, 1.6, 5.0};
-        const double scale = std::ldexp(1.0, -popcount64(K));
-        // a light sweep hides ~4 plain passes behind its HBM time, so only fuse when the win is clear
-        const bool worth = nonperm && kb >= 2 && len >= 3 && separate > fuse_margin() * block_cost[kb] * scale;
-        if (!worth) {
-            out.push_back(g);
-            ++i;
-            continue;
-        }
-        BlockInfo info;
-        info.kb = kb;
-        int nb = 0;
-        for (int b = 0; b < 64; ++b)
-            if ((B >> b) & 1) info.q[nb++] = (uint8_t)b;
-        const uint32_t dim = 1u << kb;
-        std::vector<double> mat((size_t)2 * dim * dim, 0.0);  // row-major, (re,im)
-        for (uint32_t col = 0; col < dim; ++col) {
-            double v[2 * 8] = {0};
-            v[2 * col] = 1.0;
-            for (size_t qg = i; qg < j; ++qg) block_apply_gate(v, kb, info.q, G[qg], K);
-            for (uint32_t row = 0; row < dim; ++row) {
-                mat[2 * ((size_t)row * dim + col)] = v[2 * row];
-                mat[2 * ((size_t)row * dim + col) + 1] = v[2 * row + 1];
+        {
+            uint64_t K = G[i].ctrl, T = gate_targets(G[i]), U = G[i].ctrl;
+            while (j < G.size() && blockable_gate(G[j])) {
+                const uint64_t K2 = K & G[j].ctrl, T2 = T | gate_targets(G[j]), U2 = U | G[j].ctrl;
+                if (popcount64(T2 | (U2 & ~K2)) > kBlockMaxQubits || (T2 & K2) != 0) break;
+                K = K2;
+                T = T2;
+                U = U2;
+                ++j;
             }
         }
-        while (plan.mux_tables.size() % 8) plan.mux_tables.push_back(0.0);  // keep multiplexor entries aligned
-        info.mat_off = plan.mux_tables.size() / 2;
-        plan.mux_tables.insert(plan.mux_tables.end(), mat.begin(), mat.end());
-        for (size_t qg = i; qg < j; ++qg) gate_sources(plan, G[qg], info.sources);
-        PGate f;
-        f.op = B2SV_OP_BLOCK;
-        f.t0 = info.q[0];
-        f.t1 = 0;
-        f.ctrl = K;
-        f.tmask = B;
-        f.qmask = B | K;
-        for (int e = 0; e < 8; ++e) f.m[e] = 0;
-        f.src = g.src;
-        f.blk = (int)plan.blocks.size();
-        plan.blocks.push_back(std::move(info));
-        out.push_back(f);
-        i = j;
+        const size_t L = j - i;
+        if (L < 3) {
+            out.push_back(G[i]);
+            ++i;
+            continue;
+        }
+        // dp[p]: least cost of G[i, i+p); cut[p]: start of the last piece; blk[p]: that piece is a block
+        const size_t Lc = std::min<size_t>(L, 256);  // bound the quadratic search on very long runs
+        std::vector<double> dp(Lc + 1, 0.0);
+        std::vector<size_t> cut(Lc + 1, 0);
+        std::vector<char> blk(Lc + 1, 0);
+        for (size_t p = 1; p <= Lc; ++p) {
+            // last gate alone, as a plain gate (its controls all count: nothing is common to a single gate's "run")
+            dp[p] = dp[p - 1] + gate_fp64_cost(G[i + p - 1], G[i + p - 1].ctrl);
+            cut[p] = p - 1;
+            blk[p] = 0;
+            // a block over G[i+q, i+p), q descending
+            uint64_t K = G[i + p - 1].ctrl, T = gate_targets(G[i + p - 1]), U = G[i + p - 1].ctrl;
+            bool nonperm = !G[i + p - 1].is_perm(), real = gate_is_real(G[i + p - 1]);
+            for (size_t q = p - 1; q-- > 0;) {
+                const PGate& g = G[i + q];
+                K &= g.ctrl;
+                T |= gate_targets(g);
+                U |= g.ctrl;
+                const uint64_t B = T | (U & ~K);
+                const int kb = popcount64(B);
+                if (kb > kBlockMaxQubits || (T & K) != 0) break;
+                nonperm |= !g.is_perm();
+                real = real && gate_is_real(g);
+                if (p - q < 3 || kb < 2 || !nonperm) continue;
+                const double c = dp[q] + block_fp64_cost(kb, real);
+                if (c < dp[p]) {
+                    dp[p] = c;
+                    cut[p] = q;
+                    blk[p] = 1;
+                }
+            }
+        }
+        // walk the cuts back, then emit front to back
+        std::vector<std::pair<size_t, size_t>> pieces;  // [first, last) relative to i; blocks flagged through blk[last]
+        for (size_t p = Lc; p > 0; p = cut[p]) pieces.push_back({cut[p], p});
+        for (size_t k = pieces.size(); k-- > 0;) {
+            const size_t a = i + pieces[k].first, b = i + pieces[k].second;
+            if (blk[pieces[k].second]) emit_block(plan, G, a, b, out);
+            else
+                for (size_t q = a; q < b; ++q) out.push_back(G[q]);
+        }
+        i += Lc;
     }
     plan.gates.swap(out);
 }

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -84,6 +85,10 @@ inline TileOp make_tile_op(const Plan& plan, const PGate& g, uint64_t tile_mask,
         op.blk.mat_off = bi.mat_off;
         op.blk.kb = (uint8_t)bi.kb;
         for (int i = 0; i < bi.kb; ++i) op.blk.bpos[i] = (uint8_t)local_pos(bi.q[i]);
+        op.blk.slot = 0xFF;  // build_segment_ops hands out the launch's constant-bank slots
+        bool real = true;
+        for (int e = 0; e < (1 << (2 * bi.kb)); ++e) real = real && plan.mux_tables[2 * (bi.mat_off + e) + 1] == 0.0;
+        op.blk.real = real ? 1 : 0;
     }
     if (g.op == B2SV_OP_MUX) {
         const MuxInfo& mi = plan.mux[g.mux];
@@ -408,14 +413,54 @@ inline void layout_batches(const std::vector<TileOp>& in, std::vector<TileOp>& o
     }
 }
 
+// Which dense-block matrix goes into which granule of the launch's BlkSlots (kernels.cuh).
+struct SlotFill {
+    uint8_t granule;
+    uint8_t kb;
+    size_t mat_off;  // first double2 of the matrix in Plan::mux_tables
+};
+
+// Hand the launch's 16 constant-bank granules to the segment's block ops: 8x8 matrices first (four aligned granules
+// each), 4x4 matrices into what is left; identical matrices share their slot, ops that find no room keep slot 0xFF
+// (the kernel then reads their matrix through the read-only path).
+inline void assign_block_slots(std::vector<TileOp>& ops, std::vector<SlotFill>& fills) {
+    static const bool disabled = std::getenv("B2SV_NO_BLK_SLOTS") != nullptr;  // A/B switch: matrices through __ldg as in round 1
+    if (disabled) return;
+    bool used[kBlkGranules] = {};
+    auto find = [&](const TileOp& op) -> int {
+        for (const SlotFill& f : fills)
+            if (f.mat_off == op.blk.mat_off && f.kb == op.blk.kb) return f.granule;
+        return -1;
+    };
+    for (int kb = 3; kb >= 2; --kb)
+        for (TileOp& op : ops) {
+            if (op.op != kOpBlock || op.blk.kb != kb) continue;
+            int g = find(op);
+            if (g < 0) {
+                const int need = kb == 3 ? 4 : 1;
+                for (int c = 0; c + need <= kBlkGranules && g < 0; c += need) {
+                    bool free_run = true;
+                    for (int i = 0; i < need; ++i) free_run = free_run && !used[c + i];
+                    if (free_run) g = c;
+                }
+                if (g < 0) continue;
+                for (int i = 0; i < need; ++i) used[g + i] = true;
+                fills.push_back(SlotFill{(uint8_t)g, (uint8_t)kb, (size_t)op.blk.mat_off});
+            }
+            op.blk.slot = (uint8_t)g;
+        }
+}
+
 // The complete op program of one SEG_TILE / SEG_LOW6 segment, appended to `out`.
 // Table-driven monomial phases append their walk results to plan.mux_tables.
-inline void build_segment_ops(Plan& plan, const Segment& seg, const PlanConfig& cfg, std::vector<TileOp>& out) {
+inline void build_segment_ops(Plan& plan, const Segment& seg, const PlanConfig& cfg, std::vector<TileOp>& out,
+                              std::vector<SlotFill>* slots = nullptr) {
     ExpandArgs ex;
     fill_expand(ex, seg.tile_mask);
     std::vector<TileOp> seg_ops, grouped;
     seg_ops.reserve(seg.gates.size());
     for (int gi : seg.gates) seg_ops.push_back(make_tile_op(plan, plan.gates[gi], seg.tile_mask, ex));
+    if (slots && seg.cls == SEG_TILE) assign_block_slots(seg_ops, *slots);
     const bool tile = seg.cls == SEG_TILE;
     append_with_phases(seg_ops, ex.m, cfg.phases && tile, cfg.mono && tile, seg.common_ctrl, &plan.mux_tables, grouped, &plan.mono_tables);
     if (tile) layout_batches(grouped, out);

@@ -9,18 +9,27 @@ the contiguous shard whose global position bits equal r (one process per GPU, ``
 qubits).  A logical qubit may sit at any position; ``Layout`` tracks the permutation.
 
 Per gate:
-* non-diagonal targets must be local.  Controls on global positions are free: the rank either
-  satisfies them (the control is dropped) or skips the gate.  Diagonal gates on a global target
-  become a per-rank scalar phase on the remaining controls.  An uncontrolled X on a global
-  position is a rank relabel (a flip flag), no data moves.
-* when a gate needs a global qubit as a target, the gates gathered so far are flushed to the local
-  engine (which fuses them as usual) and the qubit is swapped with a local one that is not needed
-  soon: every rank packs the half of its shard whose local bit differs from its rank bit
-  (``b2sv_swap_pack``), exchanges it with rank ``r ^ bit`` over NCCL (grouped send/recv -- the
-  pairwise case of an all-to-all) and unpacks in place.  Half a shard crosses NVLink per swap.
+* Controls on global positions are free: the rank either satisfies them (the control is dropped) or
+  skips the gate.  Diagonal gates on a global target become a per-rank scalar phase on the remaining
+  controls.  An uncontrolled X on a global position is a rank relabel (a flip flag), no data moves.
+* X / multi-controlled X / (controlled) SWAP gates with a target on a global position -- the carry chain
+  of an Increment that crosses the rank boundary -- do NOT make the qubit local first.  The whole run of
+  permutation gates around such a gate becomes ONE *distributed permutation sweep*
+  (``b2sv_dist_perm``): every rank gathers ``out[j] = in[f^-1(rank:j)]`` straight out of its peers'
+  HBM (their shards are mapped into this process with CUDA IPC), so index arithmetic, the all-to-all
+  over NVLink and the write-out are one kernel and only the amplitudes whose source really lives on
+  another GPU cross the link (a handful for an Increment).
+* dense gates (Ry, H, ...) need their target local: the global qubits needed next are swapped with
+  local ones that are not -- all of them in one distributed sweep of SWAP gates (a k-qubit all-to-all:
+  (1 - 2^-k) of the shard crosses NVLink once, nothing is packed or staged).
+* ordering between ranks is stream-ordered through interprocess CUDA events; the host side only
+  exchanges a few words per sweep over a ``gloo`` control group and never waits for the GPU.
+
+The pack / NCCL send-recv / unpack exchange of round 1 is kept as ``exchange="nccl"`` (baseline and
+fallback when peer mapping is not possible).
 
 The local engine is reached through a small backend interface so that the host logic (layout,
-gate localisation, swap planning, exchange order) is testable on CPU with ``gloo`` and a test
+gate localisation, run collection, swap planning) is testable on CPU with ``gloo`` and a test
 double; the product backend is :class:`GpuShard` (the CUDA engine, no fallback).
 """
 
@@ -123,6 +132,39 @@ class TorchComm:
         self.rank = dist.get_rank()
         self.size = dist.get_world_size()
         self.device = device
+        # host-side control plane: a gloo group, so that barriers and the few words exchanged per distributed
+        # sweep never touch a CUDA stream (an NCCL collective + .item() is a device synchronisation)
+        self.ctrl = None
+        if dist.get_backend() != "gloo":
+            self.ctrl = dist.new_group(backend="gloo")
+
+    # -- control plane (host only) ------------------------------------------------------------------
+    def host_barrier(self) -> None:
+        self.dist.barrier(group=self.ctrl)
+
+    def all_gather_bytes(self, blob: bytes) -> list:
+        out = [None] * self.size
+        self.dist.all_gather_object(out, blob, group=self.ctrl)
+        return out
+
+    def all_gather_u64(self, words: np.ndarray) -> np.ndarray:
+        """Every rank's uint64 words, in rank order: array of shape (size, len(words))."""
+        import torch
+
+        mine = torch.from_numpy(np.ascontiguousarray(words, dtype=np.uint64).view(np.int64).copy())
+        outs = [torch.empty_like(mine) for _ in range(self.size)]
+        self.dist.all_gather(outs, mine, group=self.ctrl)
+        return np.stack([o.numpy().view(np.uint64) for o in outs])
+
+    def all_gather_array(self, arr: np.ndarray) -> list:
+        """Host arrays of every rank (test doubles and small parity gathers)."""
+        import torch
+
+        flat = np.ascontiguousarray(arr).reshape(-1)
+        mine = torch.from_numpy(flat.view(np.uint8).copy())
+        outs = [torch.empty_like(mine) for _ in range(self.size)]
+        self.dist.all_gather(outs, mine, group=self.ctrl)
+        return [o.numpy().view(flat.dtype) for o in outs]
 
     def exchange(self, send, recv, partner: int) -> None:
         self.wait(self.start_exchange(send, recv, partner), send)
@@ -130,6 +172,14 @@ class TorchComm:
     def start_exchange(self, send, recv, partner: int):
         """Grouped send/recv with one peer (the pairwise case of an all-to-all); returns without waiting."""
         dist = self.dist
+        if send.is_cuda and dist.get_backend() == "gloo":
+            # gloo has no device send/recv (two ranks sharing one GPU in the tests): stage through the host
+            import torch
+
+            s_host = send.cpu()
+            r_host = torch.empty_like(s_host)
+            reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, s_host, partner), dist.P2POp(dist.irecv, r_host, partner)])
+            return [_StagedRecv(reqs, recv, r_host, s_host)]
         return dist.batch_isend_irecv([dist.P2POp(dist.isend, send, partner), dist.P2POp(dist.irecv, recv, partner)])
 
     def wait(self, reqs, tensor) -> None:
@@ -142,84 +192,95 @@ class TorchComm:
             # stream (not the whole device: later pieces of a pipelined exchange are still in flight)
             torch.cuda.current_stream(tensor.device).synchronize()
 
-    # -- peer-memory exchange: pull the partner's packed half straight out of its HBM over NVLink ------
-    def enable_peer_pull(self, send_tensor) -> bool:
-        """Map every rank's send buffer into this process (CUDA IPC through torch's storage sharing) so
-        that an exchange is ONE device-to-device copy over NVLink issued by the receiver, with no NCCL
-        channel kernels in between.  Returns False (and leaves the NCCL path active) if mapping fails."""
+    def _allreduce(self, value: float, op) -> float:
         import torch
 
-        self.peer_send = {}
-        try:
-            handle = send_tensor.untyped_storage()._share_cuda_()
-            gathered = [None] * self.size
-            self.dist.all_gather_object(gathered, (handle, int(send_tensor.storage_offset()), int(send_tensor.numel())))
-            for r, (h, off, n) in enumerate(gathered):
-                if r == self.rank:
-                    continue
-                storage = torch.UntypedStorage._new_shared_cuda(*h)
-                self.peer_send[r] = torch.empty(0, dtype=torch.uint8, device=storage.device).set_(storage, off, (n,))
-            ok = 1.0
-        except Exception as exc:  # pragma: no cover - depends on the platform
-            self.peer_error = repr(exc)
-            ok = 0.0
-        all_ok = self.allreduce_min(ok) > 0.5
-        if not all_ok:
-            self.peer_send = {}
-        return all_ok
-
-    def pull_async(self, recv_view, partner: int, first_byte: int):
-        """Enqueue recv_view <- partner's send buffer [first_byte, +len) and return an event that fires when
-        the bytes have landed (torch makes the destination device's current stream wait for a cross-device
-        copy, so an event recorded there afterwards covers it)."""
-        import torch
-
-        n = recv_view.numel()
-        recv_view.copy_(self.peer_send[partner][first_byte : first_byte + n], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(recv_view.device))
-        return ev
+        t = torch.tensor([value], dtype=torch.float64)  # host scalar over the gloo control group
+        self.dist.all_reduce(t, op=op, group=self.ctrl)
+        return float(t.item())
 
     def allreduce_min(self, value: float) -> float:
-        import torch
-
-        t = torch.tensor([value], dtype=torch.float64, device=self.device if self.device is not None else "cpu")
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
-        return float(t.item())
+        return self._allreduce(value, self.dist.ReduceOp.MIN)
 
     def allreduce_sum(self, value: float) -> float:
-        import torch
-
-        t = torch.tensor([value], dtype=torch.float64, device=self.device if self.device is not None else "cpu")
-        self.dist.all_reduce(t)
-        return float(t.item())
+        return self._allreduce(value, self.dist.ReduceOp.SUM)
 
     def allreduce_max(self, value: float) -> float:
-        import torch
-
-        t = torch.tensor([value], dtype=torch.float64, device=self.device if self.device is not None else "cpu")
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-        return float(t.item())
+        return self._allreduce(value, self.dist.ReduceOp.MAX)
 
     def barrier(self) -> None:
-        self.dist.barrier()
+        self.host_barrier()
+
+
+class _StagedRecv:
+    """A host-staged exchange in flight (gloo control plane with device buffers)."""
+
+    def __init__(self, reqs, recv, r_host, s_host):
+        self.reqs, self.recv, self.r_host, self.s_host = reqs, recv, r_host, s_host
+
+    def wait(self):
+        for r in self.reqs:
+            r.wait()
+        self.recv.copy_(self.r_host)
 
 
 class GpuShard:
-    """Product backend: the shard lives in the CUDA engine; exchange buffers are torch tensors
-    (tensor hand-off only: NCCL needs them), filled and drained by the engine's pack kernels."""
+    """Product backend: the shard lives in the CUDA engine.
 
-    def __init__(self, n_local: int, dtype: str, device: int):
-        import torch
+    ``exchange="gather"`` (default): peers' shards are mapped with CUDA IPC and every exchange is one fused
+    gather kernel (``b2sv_dist_perm``).  ``exchange="nccl"``: round 1's pack / NCCL send-recv / unpack through
+    torch exchange buffers (tensor hand-off only: NCCL needs them)."""
 
+    def __init__(self, n_local: int, dtype: str, device: int, exchange: str = "gather"):
         from .engine import StateVector
 
         self.device = device
+        self.exchange = exchange
         self.sv = StateVector(n_local, dtype=dtype, device=device)
-        half_bytes = (self.sv.size // 2) * self.sv.amp_bytes
-        self.send = torch.empty(half_bytes, dtype=torch.uint8, device=f"cuda:{device}")
-        self.recv = torch.empty(half_bytes, dtype=torch.uint8, device=f"cuda:{device}")
-        torch.cuda.synchronize(device)
+        self.send = self.recv = None
+        self.supports_gather = False
+
+    # -- peer mapping ------------------------------------------------------------------------------
+    def attach(self, comm) -> bool:
+        """Map every peer's state buffers into this process.  Returns False (nothing attached anywhere) if any
+        rank fails, so that all ranks fall back together."""
+        if self.exchange != "gather":
+            return False
+        ok, blobs, err = 1.0, None, ""
+        try:
+            blob = self.sv.ipc_export()
+        except Exception as exc:  # pragma: no cover - depends on the platform
+            blob, ok, err = b"\0" * 320, 0.0, repr(exc)
+        blobs = comm.all_gather_bytes(blob)
+        if comm.allreduce_min(ok) > 0.5:
+            try:
+                self.sv.ipc_attach(comm.rank, comm.size, blobs)
+            except Exception as exc:  # pragma: no cover
+                ok, err = 0.0, repr(exc)
+        all_ok = comm.allreduce_min(ok) > 0.5
+        if not all_ok:
+            self.attach_error = err
+            try:
+                self.sv.ipc_detach()
+            except Exception:
+                pass
+        self.supports_gather = all_ok
+        return all_ok
+
+    def detach(self, comm) -> None:
+        if self.supports_gather:
+            self.sv.sync()
+            comm.host_barrier()       # nobody is still gathering from a buffer that is about to be unmapped
+            self.sv.ipc_detach()
+            comm.host_barrier()       # ... or freed
+            self.supports_gather = False
+
+    def dist_perm(self, lowered, n_total: int, flip_in: int, flip_out: int, comm, opts=None) -> None:
+        """One distributed permutation sweep (protocol: include/b2sv.h)."""
+        states = comm.all_gather_u64(self.sv.dist_ready())
+        self.sv.dist_perm(lowered, n_total, flip_in, flip_out, states, opts)
+        comm.host_barrier()
+        self.sv.dist_done()
 
     def set_basis(self, index: int):
         self.sv.set_basis(index)
@@ -231,12 +292,31 @@ class GpuShard:
         if gates:
             self.sv.apply(gates, opts)
 
-    chunks = 8  # pack / exchange / unpack are pipelined over this many pieces of the half shard
+    def prepare_local(self, gates):
+        from .lowering import lower_gates
+
+        return lower_gates(gates, self.sv.n_qubits)
+
+    def apply_prepared(self, lowered, opts=None):
+        if len(lowered):
+            self.sv.apply_lowered(lowered, opts)
+
+    chunks = 8  # nccl exchange: pack / exchange / unpack are pipelined over this many pieces of the half shard
     min_chunk = 1 << 16
+
+    def _buffers(self):
+        if self.send is None:
+            import torch
+
+            half_bytes = (self.sv.size // 2) * self.sv.amp_bytes
+            self.send = torch.empty(half_bytes, dtype=torch.uint8, device=f"cuda:{self.device}")
+            self.recv = torch.empty(half_bytes, dtype=torch.uint8, device=f"cuda:{self.device}")
+            torch.cuda.synchronize(self.device)
 
     def pack(self, q: int, keep_bit: int, first: int = 0, count: int | None = None):
         """Pack amplitudes [first, first+count) of the moving half; returns the matching views of the
         send / receive buffers (bytes)."""
+        self._buffers()
         half = self.sv.size >> 1
         count = half - first if count is None else count
         self.sv.swap_pack(q, keep_bit, self.send.data_ptr(), first, count)
@@ -255,6 +335,7 @@ class GpuShard:
         return self.sv.amp_bytes
 
     def views(self, first: int, count: int):
+        self._buffers()
         b = self.sv.amp_bytes
         return self.send[first * b : (first + count) * b], self.recv[first * b : (first + count) * b]
 
@@ -266,6 +347,14 @@ class GpuShard:
 
     def close(self):
         self.sv.close()
+
+
+def _is_perm_gate(g) -> bool:
+    """X / multi-controlled X / (controlled) SWAP with power 1: pure index permutations."""
+    name = g.name.upper()
+    if name not in ("X", "SWAP"):
+        return False
+    return getattr(g, "power", 1) in (1, None)
 
 
 class ShardedStateVector:
@@ -283,7 +372,11 @@ class ShardedStateVector:
         self.layout = Layout(n_qubits, g)
         self.shard = shard_factory(n_qubits - g)
         self.lookahead = lookahead
-        self.stats = {"swaps": 0, "swap_bytes": 0, "swap_s": 0.0, "flushes": 0, "local_gates": 0}
+        # fused gather exchange when the backend can map its peers' shards; else pack / send-recv / unpack
+        attach = getattr(self.shard, "attach", None)
+        self.gather = bool(attach(comm)) if attach is not None else bool(getattr(self.shard, "supports_gather", False))
+        self.stats = {"swaps": 0, "swap_bytes": 0, "swap_s": 0.0, "flushes": 0, "local_gates": 0, "dist_sweeps": 0, "dist_gates": 0}
+        self._programs: dict = {}
 
     # -- state ----------------------------------------------------------------------------------
     def set_basis(self, index: int) -> None:
@@ -298,7 +391,146 @@ class ShardedStateVector:
 
     # -- gates ----------------------------------------------------------------------------------
     def apply(self, gates, opts=None) -> None:
+        if not self.gather:
+            return self._apply_swapping([g for g in gates if g.name.upper() != "I"], opts)
+        # The host work (gate localisation, run collection, lowering) depends only on the gate list, the
+        # layout at entry and the rank: verify-style callers and benchmarks apply one circuit to many
+        # inputs from the identity layout, so the compiled program is kept.
+        lay = self.layout
+        key = (id(gates), len(gates), tuple(lay.pos), tuple(lay.flip))
+        hit = self._programs.get(key)
+        if hit is None or hit[0] is not gates:
+            program, final = self._compile(gates)
+            if len(self._programs) > 8:
+                self._programs.clear()
+            hit = self._programs[key] = (gates, program, final)
+        _g, program, final = hit
+        for step in program:
+            if step[0] == "local":
+                self.shard.apply_prepared(step[1], opts) if hasattr(self.shard, "apply_prepared") else self.shard.apply(step[2], opts)
+                self.stats["flushes"] += 1
+                self.stats["local_gates"] += step[3]
+            else:
+                _kind, lowered, flip_in, flip_out, n_gates, n_swaps = step
+                self.shard.dist_perm(lowered, self.n, flip_in, flip_out, self.comm, opts)
+                self.stats["dist_sweeps"] += 1
+                self.stats["dist_gates"] += n_gates
+                self.stats["swaps"] += n_swaps
+        lay.pos, lay.at, lay.flip = list(final[0]), list(final[1]), list(final[2])
+
+    def _flip_mask(self, flips) -> int:
+        nl = self.layout.n_local
+        return sum(1 << (p - nl) for p in range(nl, self.n) if flips[p])
+
+    def _lower_positions(self, gates_pos):
+        """Gates in POSITION coordinates of the whole register (global positions included) -> b2sv_gate[];
+        a backend without the C ABI (the CPU test double) takes the records as they are."""
+        if hasattr(self.shard, "prepare_dist"):
+            return self.shard.prepare_dist(gates_pos, self.n)
+        from .lowering import lower_gates
+
+        return lower_gates(gates_pos, self.n)
+
+    def _compile(self, gates):
+        """Split the circuit into local stretches (fused by the engine as usual) and distributed permutation
+        sweeps.  Pure host logic on a copy of the layout; returns (program, final layout)."""
+        lay = Layout(self.n, self.layout.g)
+        lay.pos, lay.at, lay.flip = list(self.layout.pos), list(self.layout.at), list(self.layout.flip)
+        rank = self.rank
         gates = [g for g in gates if g.name.upper() != "I"]
+        need = _next_use_table(gates, self.n)
+        program: list = []
+        pending: list = []
+
+        def flush():
+            if pending:
+                prepared = self.shard.prepare_local(list(pending)) if hasattr(self.shard, "prepare_local") else None
+                program.append(("local", prepared, list(pending), len(pending)))
+                pending.clear()
+
+        def to_positions(g):
+            return GateRecord(g.name, tuple(lay.pos[int(t)] for t in (g.target or ())), tuple(lay.pos[int(c)] for c in (g.control or ())),
+                              float(getattr(g, "parameter", 1.0) or 1.0), 1.0)
+
+        def dist_sweep(gates_pos, flip_in, flip_out, n_swaps=0):
+            program.append(("dist", self._lower_positions(gates_pos), self._flip_mask(flip_in), self._flip_mask(flip_out), len(gates_pos), n_swaps))
+
+        run_start = None      # first gate of the current stretch of consecutive permutation gates
+        run_flip = None       # flip flags when that stretch began
+        run_mark = 0          # len(pending) when that stretch began
+        i, m = 0, len(gates)
+        while i < m:
+            g = gates[i]
+            nd = _nd_targets(g)
+            if not _is_perm_gate(g):
+                run_start = None
+                missing = [q for q in nd if not lay.is_local(q)]
+                if missing:
+                    # a dense gate needs its target local: swap it in -- together with every other global qubit
+                    # that is a dense target later and a local qubit with no further use -- in ONE all-to-all
+                    flush()
+                    swaps, taken = [], set(nd)
+                    for q in missing:
+                        victim = self._pick_victim(lay, need, i, exclude=taken, dense=True)
+                        swaps.append((q, victim))
+                        taken.add(victim)
+                    never = 1 << 60
+                    for p in range(lay.n_local, lay.n):
+                        q = lay.at[p]
+                        if q in missing or need.next_dense_after(q, i) >= never:
+                            continue
+                        victim = self._pick_victim(lay, need, i, exclude=taken, dense=True)
+                        if victim is None or need.next_dense_after(victim, i) < never:
+                            break
+                        swaps.append((q, victim))
+                        taken.add(victim)
+                    gates_pos = [GateRecord("SWAP", (lay.pos[a], lay.pos[b]), (), 1.0, 1.0) for a, b in swaps]
+                    dist_sweep(gates_pos, lay.flip, lay.flip, n_swaps=len(swaps))
+                    for a, b in swaps:
+                        lay.swap_positions(lay.pos[a], lay.pos[b])
+                lg = localise_gate(g, lay, rank)
+                if lg is not None:
+                    pending.append(lg)
+                i += 1
+                continue
+            # ---- permutation gate
+            if run_start is None:
+                run_start, run_flip, run_mark = i, list(lay.flip), len(pending)
+            if g.name.upper() == "X" and not g.control and not lay.is_local(nd[0]):
+                lay.flip[lay.pos[nd[0]]] ^= 1   # uncontrolled X on a global qubit: rank relabel, no data moves
+                i += 1
+                continue
+            if all(lay.is_local(q) for q in nd):
+                lg = localise_gate(g, lay, rank)
+                if lg is not None:
+                    pending.append(lg)
+                i += 1
+                continue
+            # a permutation gate whose target is a global qubit: the whole stretch of permutation gates around it
+            # becomes one distributed sweep (the gates of the stretch already queued for the engine come back)
+            j = i + 1
+            while j < m and _is_perm_gate(gates[j]):
+                j += 1
+            del pending[run_mark:]
+            flush()
+            lay.flip = list(run_flip)
+            flip_out = list(run_flip)
+            gates_pos = []
+            for gg in gates[run_start:j]:
+                gp = to_positions(gg)
+                if gg.name.upper() == "X" and not gg.control and gp.target[0] >= lay.n_local:
+                    flip_out[gp.target[0]] ^= 1  # stays a relabel: the kernel sees the gate AND the new flag
+                gates_pos.append(gp)
+            dist_sweep(gates_pos, run_flip, flip_out)
+            lay.flip = flip_out
+            run_start = None
+            i = j
+        flush()
+        return program, (lay.pos, lay.at, lay.flip)
+
+    def _apply_swapping(self, gates, opts=None) -> None:
+        """Round-1 schedule (exchange="nccl"): a global qubit that is a non-diagonal target is swapped with a
+        local one, half a shard per swap through pack / send-recv / unpack."""
         lay = self.layout
         pending: list = []
         # next index at which each qubit is needed as a non-diagonal target (Belady eviction)
@@ -322,7 +554,7 @@ class ShardedStateVector:
             if missing:
                 flush()
                 for q in missing:
-                    victim = self._pick_victim(need, i, exclude=set(nd))
+                    victim = self._pick_victim(lay, need, i, exclude=set(nd))
                     self._swap(q, victim)
                 # While the engine is drained anyway, also bring in every other global qubit that will be
                 # a target later, as long as a local qubit with no further use can take its place: one
@@ -332,7 +564,7 @@ class ShardedStateVector:
                     q = lay.at[p]
                     if need.next_after(q, i) >= never:
                         continue
-                    victim = self._pick_victim(need, i, exclude=set(nd))
+                    victim = self._pick_victim(lay, need, i, exclude=set(nd))
                     if victim is None or need.next_after(victim, i) < never:
                         break
                     self._swap(q, victim)
@@ -341,15 +573,16 @@ class ShardedStateVector:
                 pending.append(lg)
         flush()
 
-    def _pick_victim(self, need, i: int, exclude) -> int:
-        """Local qubit whose next use as a non-diagonal target is farthest away."""
-        lay = self.layout
+    @staticmethod
+    def _pick_victim(lay, need, i: int, exclude, dense: bool = False) -> int:
+        """Local qubit whose next use as a non-diagonal target (``dense``: as the target of a gate that is not a
+        pure permutation -- the only ones that need locality with the gather exchange) is farthest away."""
         best, best_next = None, -1
-        for p in range(lay.n_local - 1, -1, -1):  # prefer high local positions on ties (cheap, long strides)
+        for p in range(lay.n_local - 1, -1, -1):  # prefer high local positions on ties (long contiguous runs move)
             q = lay.at[p]
             if q in exclude:
                 continue
-            nxt = need.next_after(q, i)
+            nxt = need.next_dense_after(q, i) if dense else need.next_after(q, i)
             if nxt > best_next:
                 best, best_next = q, nxt
         return best
@@ -358,42 +591,19 @@ class ShardedStateVector:
         """Exchange the positions of a global and a local qubit (half a shard crosses the link)."""
         lay = self.layout
         pg, pl = lay.pos[q_global], lay.pos[q_local]
+        if self.gather:
+            flips = self._flip_mask(lay.flip)
+            self.shard.dist_perm(self._lower_positions([GateRecord("SWAP", (pg, pl), (), 1.0, 1.0)]), self.n, flips, flips, self.comm)
+            lay.swap_positions(pg, pl)
+            self.stats["swaps"] += 1
+            self.stats["dist_sweeps"] += 1
+            return
         bit = pg - lay.n_local
         my_bit = (self.rank >> bit) & 1  # PHYSICAL rank bit: data placement ignores the flip flag
         t0 = time.perf_counter()
         partner = self.rank ^ (1 << bit)
         chunks = getattr(self.shard, "chunks", 1)
-        if getattr(self.comm, "peer_send", None):
-            # peer-memory path: everybody packs, then every rank pulls its incoming half directly out of
-            # the partner's HBM -- one device-to-device copy over NVLink, no NCCL channel kernels
-            half = self.shard.half
-            b = self.shard.amp_bytes
-            ta = time.perf_counter()
-            self.shard.pack(pl, my_bit)
-            tb = time.perf_counter()
-            self.comm.allreduce_sum(0.0)              # light barrier: the partner's send buffer is complete
-            tc = time.perf_counter()
-            # all pieces are queued on the copy engine at once; piece c is unpacked while c+1.. still fly
-            step = max(1, half // max(1, chunks))
-            pending = []
-            for first in range(0, half, step):
-                count = min(step, half - first)
-                _s, recv = self.shard.views(first, count)
-                pending.append((self.comm.pull_async(recv, partner, first * b), first, count))
-            unpack_s = 0.0
-            for ev, first, count in pending:
-                ev.synchronize()
-                tu = time.perf_counter()
-                self.shard.unpack(pl, my_bit, first, count)
-                unpack_s += time.perf_counter() - tu
-            te = time.perf_counter()
-            td = te - unpack_s  # transfer time not hidden behind unpacking
-            self.comm.allreduce_sum(0.0)              # nobody re-packs while a peer is still reading
-            tf = time.perf_counter()
-            for key, dt in (("pack_s", tb - ta), ("barrier_s", tc - tb + tf - te), ("transfer_s", td - tc), ("unpack_s", te - td)):
-                self.stats[key] = self.stats.get(key, 0.0) + dt
-            send_bytes = half * b
-        elif chunks > 1 and hasattr(self.comm, "start_exchange") and self.shard.half >= chunks * getattr(self.shard, "min_chunk", 1):
+        if chunks > 1 and hasattr(self.comm, "start_exchange") and self.shard.half >= chunks * getattr(self.shard, "min_chunk", 1):
             # software pipeline: while NCCL moves piece c, the engine packs piece c+1 and unpacks c-1
             half = self.shard.half
             step = half // chunks
@@ -429,8 +639,23 @@ class ShardedStateVector:
         self.stats["swap_s"] += time.perf_counter() - t0
 
     def restore_identity_layout(self) -> None:
-        """Bring every logical qubit back to position == qubit (needed before projections / download)."""
+        """Bring every logical qubit back to position == qubit (needed before download)."""
         lay = self.layout
+        if self.gather:
+            # one sweep: the position permutation as SWAP gates, flip flags cleared through flip_out = 0
+            if all(lay.at[p] == p for p in range(lay.n)) and not any(lay.flip):
+                return
+            gates_pos = []
+            flip_in = self._flip_mask(lay.flip)
+            for p in range(lay.n):
+                while lay.at[p] != p:
+                    other = lay.pos[p]
+                    gates_pos.append(GateRecord("SWAP", (p, other), (), 1.0, 1.0))
+                    lay.swap_positions(p, other)
+            self.shard.dist_perm(self._lower_positions(gates_pos), self.n, flip_in, 0, self.comm)
+            lay.flip = [0] * lay.n
+            self.stats["dist_sweeps"] += 1
+            return
         # clear flip flags: an X on the data, done by making the qubit local once
         for p in range(lay.n_local, lay.n):
             if lay.flip[p]:
@@ -468,8 +693,12 @@ class ShardedStateVector:
 
         prog = subspace if isinstance(subspace, SubspaceProgram) else SubspaceProgram(subspace)
         lay = self.layout
-        rank_value = lambda p: ((self.rank >> (p - lay.n_local)) & 1) ^ lay.flip[p]  # noqa: E731
-        sp = ShardProgram(prog, lay.pos, lay.n_local, rank_value, self.n)
+        key = (id(prog), tuple(lay.pos), tuple(lay.flip))
+        hit = getattr(self, "_shard_prog", None)
+        if hit is None or hit[0] != key or hit[1] is not prog:
+            rank_value = lambda p: ((self.rank >> (p - lay.n_local)) & 1) ^ lay.flip[p]  # noqa: E731
+            hit = self._shard_prog = (key, prog, ShardProgram(prog, lay.pos, lay.n_local, rank_value, self.n))
+        sp = hit[2]
         local = 0.0 if sp.rejects_all else self.shard.norm2_shard(sp)
         return self.comm.allreduce_sum(local)
 
@@ -479,16 +708,16 @@ class ShardedStateVector:
         return self.shard.download()
 
     def close(self):
-        if getattr(self.comm, "peer_send", None):
-            self.comm.barrier()
-            self.comm.peer_send = {}  # drop the IPC mappings before the owners free their buffers
-            self.comm.barrier()
+        detach = getattr(self.shard, "detach", None)
+        if detach is not None:
+            detach(self.comm)
         self.shard.close()
 
 
 class _NextUse:
-    def __init__(self, uses):
+    def __init__(self, uses, dense=None):
         self.uses = uses  # per qubit: sorted gate indices where it is a non-diagonal target
+        self.dense = dense if dense is not None else uses
         self.cursor = [0] * len(uses)
 
     def next_after(self, q: int, i: int) -> int:
@@ -499,13 +728,24 @@ class _NextUse:
         self.cursor[q] = c
         return u[c] if c < len(u) else 1 << 60
 
+    def next_dense_after(self, q: int, i: int) -> int:
+        """Next use as the target of a gate that is not a pure permutation (those need the qubit local)."""
+        for k in self.dense[q]:
+            if k > i:
+                return k
+        return 1 << 60
+
 
 def _next_use_table(gates, n: int) -> _NextUse:
     uses = [[] for _ in range(n)]
+    dense = [[] for _ in range(n)]
     for i, g in enumerate(gates):
+        perm = _is_perm_gate(g)
         for q in _nd_targets(g):
             uses[q].append(i)
-    return _NextUse(uses)
+            if not perm:
+                dense[q].append(i)
+    return _NextUse(uses, dense)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -513,12 +753,12 @@ def _next_use_table(gates, n: int) -> _NextUse:
 # ---------------------------------------------------------------------------------------------
 
 
-def make_gpu_shard_factory(dtype: str, device: int):
-    return lambda n_local: GpuShard(n_local, dtype, device)
+def make_gpu_shard_factory(dtype: str, device: int, exchange: str = "gather"):
+    return lambda n_local: GpuShard(n_local, dtype, device, exchange)
 
 
 def _family_single_gpu(case1, dtype, device, jit):
-    """gates/s of the scaling family's single-GPU member (same amplitudes per GPU), 3 timed steps."""
+    """The scaling family's single-GPU member (same amplitudes per GPU): basis-input and dense-input steps."""
     from .cabi import PlanOpts
     from .engine import StateVector
     from .lowering import lower_gates
@@ -528,6 +768,7 @@ def _family_single_gpu(case1, dtype, device, jit):
     low = lower_gates(case1.gates, n1)
     prog = SubspaceProgram(case1.meta["subspace_out"])
     opts = PlanOpts.make(jit=jit)
+    out = {"workload": case1.meta["name"], "qubits": n1, "unit": "gates/s"}
     with StateVector(n1, dtype=dtype, device=device) as sv:
         for j in (1, 2, 3):
             sv.set_basis(j)
@@ -543,7 +784,59 @@ def _family_single_gpu(case1, dtype, device, jit):
         sv.mark(1)
         ms = sv.elapsed_ms(0, 1)
         live = sv.stats()["gates_live"] // (steps + 3)
-    return {"workload": case1.meta["name"], "qubits": n1, "gates_live": int(live), "ms_per_step": ms / steps, "value": live * steps / (ms * 1e-3), "unit": "gates/s"}
+        out.update({"gates_live": int(live), "ms_per_step": ms / steps, "value": live * steps / (ms * 1e-3)})
+        dense_ms = 0.0
+        for k in range(steps + 1):
+            sv.fill_random(seed=k, support_bits=n1 - 1)
+            sv.mark(2)
+            sv.apply_lowered(low, opts)
+            sv.project_norm2(prog)
+            sv.mark(3)
+            if k:
+                dense_ms += sv.elapsed_ms(2, 3)
+        out["dense_ms_per_step"] = dense_ms / steps
+    return out
+
+
+def _bench_parity(comm, dtype, device, exchange, jit, golden_dir):
+    """Before anything is timed: the sharded path on this world size against the REFERENCE's frozen columns
+    (node.compute(e_j), tests/golden/*.cols.npz) -- Increment across the rank boundary (config 5's shape) and
+    dense gates on global qubits (Laplace: Ry on the top LCU qubits).  Every rank takes part; rank 0 compares."""
+    from .cabi import PlanOpts
+    from .engine import StateVector
+    from .fixtures import column_error, load_circuit, load_columns
+    from .subspace_prog import SubspaceProgram
+
+    tol = 1e-12 if dtype == "complex128" else 1e-5
+    worst, detail = 0.0, {}
+    for name in ("cfg5_bits13", "laplace_n16"):
+        case = load_circuit(os.path.join(golden_dir, name + ".npz"))
+        cols, dim_out = load_columns(os.path.join(golden_dir, name + ".cols.npz"))
+        prog = SubspaceProgram(case.meta["subspace_out"])
+        norm = case.meta["normalization"]
+        sv = ShardedStateVector(max(1, case.n_qubits), comm, make_gpu_shard_factory(dtype, device, exchange))
+        err_case = 0.0
+        members = None
+        if comm.rank == 0:
+            with StateVector(max(1, prog.total_qubits), device=device) as tmp:
+                members = tmp.enumerate_basis(prog)
+        for basis, idx, val in cols[:3]:
+            sv.set_basis(basis)
+            sv.apply(case.gates, PlanOpts.make(jit=jit))
+            norm2 = sv.project_norm2(prog)
+            shards = comm.all_gather_array(np.asarray(sv.local_amplitudes()))
+            if comm.rank == 0:
+                full = np.concatenate(shards)
+                got = norm * full[members]
+                scale = max(1.0, float(np.abs(val).max()))
+                err = column_error(got, idx, val) / scale
+                err = max(err, abs(abs(norm) * math.sqrt(norm2) - float(np.sqrt(np.sum(np.abs(val) ** 2)))))
+                err_case = max(err_case, err)
+        detail[name] = {"max_abs_err": err_case, "swaps": sv.stats["swaps"], "dist_sweeps": sv.stats["dist_sweeps"], "columns": min(3, len(cols))}
+        worst = max(worst, err_case)
+        sv.close()
+    ok = comm.allreduce_min(1.0 if (comm.rank != 0 or worst <= tol) else 0.0) > 0.5
+    return {"parity_max_abs": worst, "tol": tol, "ok": bool(ok), "against": "reference node.compute(e_j) columns frozen in tests/golden/*.cols.npz", "cases": detail}
 
 
 def bench_main(args, case, config_dict, cpu_sample, ClockSampler, measured_peak):
@@ -561,13 +854,21 @@ def bench_main(args, case, config_dict, cpu_sample, ClockSampler, measured_peak)
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
     torch.cuda.set_device(local_rank)
-    # the exchanges are big pairwise send/recv: give NCCL enough point-to-point channels to fill NVLink 5
+    # the nccl exchange is big pairwise send/recv: give NCCL enough point-to-point channels to fill NVLink 5
     os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "32")
     os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     comm = TorchComm(device=torch.device(f"cuda:{local_rank}"))
     dtype = "complex128" if args.dtype == "c128" else "complex64"
     n = max(1, case.n_qubits)
+    golden_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+    # ---- parity first: a sharded result that differs from the reference's is not worth timing
+    check = _bench_parity(comm, dtype, local_rank, args.exchange, args.jit, golden_dir)
+    if not check["ok"]:
+        if rank == 0:
+            print(json.dumps({"error": "sharded parity check failed", "check": check}), flush=True)
+        dist.destroy_process_group()
+        raise SystemExit(3)
     # the scaling family keeps 2^(n - log2 N) amplitudes per GPU; its N = 1 member is measured here on
     # rank 0 (bench.py's own N = 1 run is BASELINE config 2, a different circuit), so that the line
     # carries what a weak-scaling efficiency has to be computed against
@@ -575,10 +876,13 @@ def bench_main(args, case, config_dict, cpu_sample, ClockSampler, measured_peak)
     if rank == 0 and getattr(args, "family_n1", None) is not None:
         family_n1 = _family_single_gpu(args.family_n1, dtype, local_rank, args.jit)
     comm.barrier()
-    sv = ShardedStateVector(n, comm, make_gpu_shard_factory(dtype, local_rank))
-    exchange = "peer-memory pull (CUDA IPC mapped send buffers, one NVLink copy per swap)"
-    if args.exchange == "nccl" or not comm.enable_peer_pull(sv.shard.send):
-        exchange = "NCCL grouped send/recv, 8-piece pack/exchange/unpack pipeline"
+    sv = ShardedStateVector(n, comm, make_gpu_shard_factory(dtype, local_rank, args.exchange))
+    exchange = (
+        "fused gather: peers' shards mapped with CUDA IPC, one b2sv_perm_dist kernel per exchange (index map + all-to-all over NVLink + write-out), "
+        "stream-ordered by interprocess events, gloo control plane"
+        if sv.gather
+        else "NCCL grouped send/recv, 8-piece pack/exchange/unpack pipeline (round-1 transport)"
+    )
     prog = SubspaceProgram(case.meta["subspace_out"])
     norm = case.meta["normalization"]
     opts = PlanOpts.make(timing=True, jit=args.jit)
@@ -586,11 +890,24 @@ def bench_main(args, case, config_dict, cpu_sample, ClockSampler, measured_peak)
     dim_in = SubspaceProgram(case.meta["subspace_in"]).dimension
     inputs = [int(i) for i in rng.integers(0, min(dim_in, 1 << 20), size=args.steps + args.warmup)]
     live = [g for g in case.gates if g.name.upper() != "I"]
+    nl = sv.layout.n_local
+    esv = sv.shard.sv
 
     def step(j):
         sv.set_basis(j)
         sv.apply(live, opts)
         return abs(norm) * math.sqrt(sv.project_norm2(prog))
+
+    def dense_step(k, timed):
+        sv.layout = Layout(n, sv.layout.g)
+        esv.fill_random(seed=100 + k, support_bits=n - 1, index_base=rank << nl)
+        if timed:
+            esv.mark(2)
+        sv.apply(live, opts)
+        r = abs(norm) * math.sqrt(sv.project_norm2(prog))
+        if timed:
+            esv.mark(3)
+        return r
 
     for j in inputs[: args.warmup]:
         step(j)
@@ -599,31 +916,65 @@ def bench_main(args, case, config_dict, cpu_sample, ClockSampler, measured_peak)
         clocks.start()
     for k in sv.stats:
         sv.stats[k] = 0
-    sv.shard.sv.stats_reset()
+    esv.stats_reset()
     comm.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    sv.shard.sv.mark(0)
+    esv.mark(0)
     norms = [step(j) for j in inputs[args.warmup :]]
-    sv.shard.sv.mark(1)
+    esv.mark(1)
     torch.cuda.synchronize()
     comm.barrier()
     wall_s = time.perf_counter() - t0
-    # every step ends in an all-reduce + host read, so the engine-stream event span is the rank's time
-    ms_rank = sv.shard.sv.elapsed_ms(0, 1)
+    # every step ends in a host reduction of the norm, so the engine-stream event span is the rank's time
+    ms_rank = esv.elapsed_ms(0, 1)
     ms = comm.allreduce_max(ms_rank)
-    st = sv.shard.sv.stats()
-    swap_s = comm.allreduce_max(sv.stats["swap_s"])
+    st = esv.stats()
+    run_stats = dict(sv.stats)
+    # ---- the same circuit on a dense register (every sweep reads and writes the whole shard)
+    dense_steps = max(1, min(args.steps, 5))
+    dense_step(0, False)
+    dense_ms_rank = 0.0
+    for k in range(dense_steps):
+        dense_step(1 + k, True)
+        dense_ms_rank += esv.elapsed_ms(2, 3)
+    dense_ms = comm.allreduce_max(dense_ms_rank)
+    # ---- exchange probe: ONE all-to-all that swaps every global qubit with a (high) local one, i.e. the
+    # worst-case exchange of the layer: (1 - 1/N) of every shard crosses NVLink once
+    probe = None
+    if sv.gather:
+        g = sv.layout.g
+        gates_pos = [GateRecord("SWAP", (nl + i, nl - 1 - i), (), 1.0, 1.0) for i in range(g)]
+        lowered = sv._lower_positions(gates_pos)
+        probe_ms = []
+        for rep in range(3):
+            comm.barrier()
+            esv.mark(4)
+            sv.shard.dist_perm(lowered, n, 0, 0, comm, PlanOpts.make(jit=args.jit))
+            esv.mark(5)
+            probe_ms.append(comm.allreduce_max(esv.elapsed_ms(4, 5)))
+        shard_bytes = (1 << nl) * esv.amp_bytes
+        moved = shard_bytes * (1.0 - 1.0 / world)
+        best = min(probe_ms[1:])
+        probe = {
+            "what": f"{g}-qubit global<->local swap as one distributed sweep (all-to-all)",
+            "bytes_received_per_rank": moved,
+            "ms": best,
+            "GBps_per_direction": moved / (best * 1e-3) / 1e9,
+            "nvlink_bound_GBps": 770.0,
+            "frac_of_nvlink_bound": moved / (best * 1e-3) / 1e9 / 770.0,
+            "nvlink_bound_ms": moved / 770e9 * 1e3,
+        }
     if rank == 0:
         clk = clocks.stop()
         gates_live = len(live)
         peak, peak_src = measured_peak()
-        cls = max(("tile", "low6", "perm", "perm_jit", "gate1q"), key=lambda c: st["ms_by_class"][c])
+        cls = max(("tile", "low6", "perm", "perm_jit", "gate1q", "dist_perm"), key=lambda c: st["ms_by_class"][c])
         L = max(1, st["launches_by_class"][cls])
         per_ms = st["ms_by_class"][cls] / L
         per_bytes = st["alg_bytes_by_class"][cls] / L
         achieved = per_bytes / (per_ms * 1e-3) / 1e9 if per_ms > 0 else 0.0
-        swap_bytes = sv.stats["swap_bytes"]
+        ms_step = ms / args.steps
         line = {
             "metric": "gates_per_sec",
             "value": gates_live * args.steps / (ms * 1e-3),
@@ -631,7 +982,7 @@ def bench_main(args, case, config_dict, cpu_sample, ClockSampler, measured_peak)
             "n_gpus": world,
             "steps": args.steps,
             "warmup": args.warmup,
-            "ms_per_step": ms / args.steps,
+            "ms_per_step": ms_step,
             "higher_is_better": True,
             "scaling": "weak",
             "vs_baseline": None,
@@ -639,6 +990,10 @@ def bench_main(args, case, config_dict, cpu_sample, ClockSampler, measured_peak)
             "data": "synthetic",
             "config": config_dict(case, world, args.dtype),
             "gates_live_per_step": gates_live,
+            "amplitude_gate_updates_per_sec": gates_live * float(1 << n) / (ms_step * 1e-3),
+            "weak_efficiency": (family_n1["ms_per_step"] / ms_step) if family_n1 else None,
+            "weak_efficiency_note": "t1 / tN with t1 = the family's single-GPU member (same 2^31 amplitudes per GPU, weak_scaling_n1) -- "
+            "`value` is gates/s of ONE circuit on the whole register and does not grow with N under weak scaling; the aggregate that does is amplitude_gate_updates_per_sec",
             "roofline": {
                 "bound": "hbm",
                 "kernel": cls,
@@ -651,16 +1006,23 @@ def bench_main(args, case, config_dict, cpu_sample, ClockSampler, measured_peak)
                 "ms_per_launch": per_ms,
                 "launches": st["launches_by_class"][cls],
                 "traffic": None,
+                "note": "rank 0's dominant kernel class; basis-state inputs make the distributed sweep write-only on most of the shard (the source window is one tile)",
+            },
+            "inputs": {
+                "basis": {"ms_per_step": ms_step},
+                "dense": {
+                    "ms_per_step": dense_ms / dense_steps,
+                    "gates_per_sec": gates_live * dense_steps / (dense_ms * 1e-3),
+                    "weak_efficiency": (family_n1["dense_ms_per_step"] / (dense_ms / dense_steps)) if family_n1 else None,
+                    "input": "b2sv_fill_random on every shard (one global dense vector), generated outside the timed region",
+                },
             },
             "exchange": {
-                "swaps_per_step": sv.stats["swaps"] / args.steps,
-                "bytes_sent_per_rank_per_step": swap_bytes / args.steps,
-                "seconds_per_step_max_rank": swap_s / args.steps,
-                "achieved_GBps_per_direction": (swap_bytes / swap_s / 1e9) if swap_s > 0 else None,
-                "nvlink_peak_GBps_per_direction": 770.0,
                 "path": exchange,
-                "breakdown_s_per_step_rank0": {k: sv.stats[k] / args.steps for k in ("pack_s", "barrier_s", "transfer_s", "unpack_s") if k in sv.stats},
-                "note": "seconds include pack + transfer + unpack",
+                "dist_sweeps_per_step": run_stats["dist_sweeps"] / args.steps,
+                "qubit_swaps_per_step": run_stats["swaps"] / args.steps,
+                "probe": probe,
+                "nccl_swap_seconds_per_step_rank0": run_stats.get("swap_s", 0.0) / args.steps,
             },
             "weak_scaling_n1": family_n1,
             "kernels_rank0": {c: {"launches": st["launches_by_class"][c], "ms": st["ms_by_class"][c]} for c in st["ms_by_class"] if st["launches_by_class"][c]},
@@ -674,7 +1036,7 @@ def bench_main(args, case, config_dict, cpu_sample, ClockSampler, measured_peak)
             },
             "gpu_launches": int(st["launches"]) * world,
             "clocks": clk,
-            "check": {"norm_first": float(norms[0]), "norm_last": float(norms[-1])},
+            "check": check | {"norm_first": float(norms[0]), "norm_last": float(norms[-1])},
         }
         print(json.dumps(line), flush=True)
     sv.close()

@@ -87,6 +87,25 @@ def _dtype_code(dtype) -> int:
         return _DTYPES[np.dtype(dtype).name]
 
 
+def random_state_hash(n_qubits: int, seed: int = 0, support_bits: int | None = None, index_base: int = 0) -> np.ndarray:
+    """Host restatement of ``b2sv_fill_random`` (splitmix64 counter hash), for parity checks at small sizes."""
+    bits = n_qubits if support_bits is None else support_bits
+    k = np.arange(2**n_qubits, dtype=np.uint64) + np.uint64(index_base)
+
+    def unit(x):
+        with np.errstate(over="ignore"):
+            x = x + np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15)
+            x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            x = x ^ (x >> np.uint64(31))
+        return (x >> np.uint64(11)).astype(np.float64) * (2.0 / 9007199254740992.0) - 1.0
+
+    scale = np.sqrt(1.5 / 2.0**bits)
+    out = scale * (unit(np.uint64(2) * k) + 1j * unit(np.uint64(2) * k + np.uint64(1)))
+    out[k >= np.uint64(2**bits)] = 0
+    return out
+
+
 class StateVector:
     """``2**n_qubits`` amplitudes on one B200, LSB order (index bit q = qubit q).
 
@@ -136,6 +155,11 @@ class StateVector:
 
     def set_zero(self) -> None:
         cabi.check(self._lib.b2sv_set_zero(self._h))
+
+    def fill_random(self, seed: int = 0, support_bits: int | None = None, index_base: int = 0) -> None:
+        """Seeded dense vector generated on the device (``random_state_hash`` below is its host restatement)."""
+        bits = self.n_qubits if support_bits is None else int(support_bits)
+        cabi.check(self._lib.b2sv_fill_random(self._h, int(seed), bits, int(index_base)))
 
     def upload(self, amplitudes: np.ndarray) -> None:
         a = np.ascontiguousarray(amplitudes, dtype=np.complex128).reshape(-1)
@@ -263,6 +287,36 @@ class StateVector:
 
     def stats_reset(self) -> None:
         cabi.check(self._lib.b2sv_stats_reset(self._h))
+
+    # -- distributed execution (unitaria_b200/distributed.py) ---------------------------------------
+    def ipc_export(self) -> bytes:
+        """Opaque blob (state buffers + hand-shake events) that peers attach with :meth:`ipc_attach`."""
+        blob = ctypes.create_string_buffer(cabi.IPC_BYTES)
+        cabi.check(self._lib.b2sv_ipc_export(self._h, blob))
+        return blob.raw
+
+    def ipc_attach(self, rank: int, world: int, blobs) -> None:
+        raw = b"".join(blobs)
+        if len(raw) != world * cabi.IPC_BYTES:
+            raise ValueError("one IPC blob per rank is needed")
+        cabi.check(self._lib.b2sv_ipc_attach(self._h, int(rank), int(world), raw))
+
+    def ipc_detach(self) -> None:
+        cabi.check(self._lib.b2sv_ipc_detach(self._h))
+
+    def dist_ready(self) -> np.ndarray:
+        state = np.zeros(cabi.DIST_STATE_WORDS, dtype=np.uint64)
+        cabi.check(self._lib.b2sv_dist_ready(self._h, state.ctypes.data))
+        return state
+
+    def dist_perm(self, lowered: np.ndarray, n_total: int, flip_in: int, flip_out: int, states: np.ndarray, opts: PlanOpts | None = None) -> None:
+        lowered = np.ascontiguousarray(lowered, dtype=GATE_DTYPE)
+        states = np.ascontiguousarray(states, dtype=np.uint64)
+        optp = ctypes.byref(opts) if opts is not None else None
+        cabi.check(self._lib.b2sv_dist_perm(self._h, lowered.ctypes.data, len(lowered), int(n_total), int(flip_in), int(flip_out), states.ctypes.data, optp))
+
+    def dist_done(self) -> None:
+        cabi.check(self._lib.b2sv_dist_done(self._h))
 
     def swap_pack(self, qubit: int, keep_bit: int, staging_ptr: int, first: int = 0, count: int | None = None) -> None:
         count = (self.size >> 1) - first if count is None else count

@@ -98,3 +98,26 @@ def load_circuit(path) -> SavedCircuit:
         meta = json.loads(str(z["meta_json"]))
         arrays = {k[2:]: z[k] for k in z.files if k.startswith("x_")}
         return SavedCircuit(gates, int(z["n_qubits"]), meta, arrays)
+
+
+def load_columns(path):
+    """Frozen columns of an encoded matrix (the reference's ``node.compute(e_j)``, written by
+    tests/golden/make_golden.py --columns): ``[(basis index of input j, nonzero indices, nonzero values)]`` and the
+    output dimension; ``(None, 0)`` if the file does not exist."""
+    import os
+
+    if not os.path.exists(path):
+        return None, 0
+    with np.load(path) as z:
+        ptr, idx, val = z["col_ptr"], z["col_index"], z["col_value"]
+        cols = [(int(b), idx[ptr[k] : ptr[k + 1]], val[ptr[k] : ptr[k + 1]]) for k, b in enumerate(z["col_basis"])]
+        return cols, int(z["dim_out"])
+
+
+def column_error(got, indices, values) -> float:
+    """max |got - column| of a dense result against a sparse expected column."""
+    err_nz = float(np.abs(got[indices] - values).max()) if len(indices) else 0.0
+    mask = np.ones(len(got), dtype=bool)
+    mask[indices] = False
+    rest = got[mask]
+    return max(err_nz, float(np.abs(rest).max()) if rest.size else 0.0)
