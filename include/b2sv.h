@@ -151,6 +151,14 @@ int b2sv_project_norm2_at(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, in
  * (= Subspace.enumerate_basis order, subspace.py:325-329); `dim` must equal the subspace dimension. */
 int b2sv_project_gather(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
                         double scale_re, double scale_im, void* host_out_c128, uint64_t dim);
+/* Pipelined form for callers that run one circuit on many inputs (the matrix case of Node.simulate,
+ * nodes/node.py:381-388; verify, verifier.py:119-126): the gather lands in one of two device buffers (`slot` 0/1)
+ * and is copied to `host_out` (page-locked memory for a real overlap) by a second stream, so the call returns at
+ * once and the next input's sweeps run while the result crosses PCIe.  `host_out` must stay valid until
+ * b2sv_gather_wait(slot) (or the next async call on the same slot) returns. */
+int b2sv_project_gather_async(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
+                              double scale_re, double scale_im, void* host_out_c128, uint64_t dim, int slot);
+int b2sv_gather_wait(b2sv_t* sv, int slot);
 /* The inverse hand-off: psi := sum_r host_in[r] |basis_r>, i.e. the members of the subspace (ascending
  * index order) take the `dim` amplitudes and every other amplitude is 0.  Replaces the 2^n-element host
  * array BlockEncoding.compute fills and uploads (nodes/block_encoding.py:45-52: full_input[basis] = input):
@@ -220,6 +228,9 @@ int b2sv_dist_source(int n_local, int n_global, int dtype, const b2sv_gate* gate
  * (a fused gate lists every caller gate it stands for; common_ctrl = controls shared by all gates
  * of a tile sweep outside its tile; n_ops = device ops after fusion), then the trailer
  * {-1, 2, 0, 0, 0, bits(scalar_re), bits(scalar_im)},
+ * then {-2, count, 0, 0, 0, count x {gate id, op, t0, t1, ctrl_mask}}: the gates the planner's SWAP frame executes
+ * on renamed qubits (a deferred SWAP renames instead of moving data) and the synthetic SWAPs (ids >= n_gates) that
+ * restore the layout -- a gate id listed here is to be replayed with THESE qubits;
  * and returns the number of words needed in *n_words. */
 int b2sv_plan_describe(int n_qubits, int dtype, const b2sv_gate* gates, size_t n_gates, const b2sv_plan_opts* opts,
                        int64_t* out_words, size_t cap, size_t* n_words);

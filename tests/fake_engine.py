@@ -96,6 +96,18 @@ class FakeStateVector:
     def close(self):
         pass
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def project_async(self, subspace, scale, out, slot):
+        out[:] = self.project(subspace, scale)
+
+    def gather_wait(self, slot):
+        pass
+
     def set_basis(self, index):
         self.psi[:] = 0
         self.psi[int(index)] = 1

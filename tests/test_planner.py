@@ -17,17 +17,38 @@ def popcount(x):
     return bin(x).count("1")
 
 
+RELABEL: dict = {}
+
+
 def plan_for(gates, n, dtype=cabi.B2SV_C128, **kw):
     live = [g for g in gates if g.name != "I"]
     low = lower_gates(live, n)
-    segs, scalar = cabi.plan_describe(max(1, n), dtype, low, cabi.PlanOpts.make(**kw))
+    segs, scalar, _common, relabel = cabi.plan_describe(max(1, n), dtype, low, cabi.PlanOpts.make(**kw), with_relabel=True)
+    RELABEL[id(segs)] = relabel
     return live, low, segs, scalar
 
 
 def replay(live, segs, scalar, n, psi0):
+    from unitaria_b200.fixtures import GateRecord
+
+    relabel = RELABEL.get(id(segs), {})
+
+    def gate(i):
+        # gates the SWAP frame runs on renamed qubits (and its synthetic layout-restoring SWAPs, ids >= len(live))
+        if i not in relabel:
+            return live[i]
+        op, t0, t1, ctrl = relabel[i]
+        controls = tuple(q for q in range(64) if (ctrl >> q) & 1)
+        if i >= len(live):
+            assert op == cabi.OP_SWAP
+            return GateRecord("SWAP", (t0, t1), controls, 1.0, 1.0)
+        g = live[i]
+        target = (t0, t1) if g.name.upper() == "SWAP" else ((t0,) if len(g.target) else ())
+        return GateRecord(g.name, target, controls, g.parameter, getattr(g, "power", 1.0))
+
     order = [gi for _cls, _mask, idx in segs for gi in idx]
-    # global phases without controls are folded into `scalar`; dropped no-ops and X.X pairs vanish
-    psi = np_oracle.simulate_gates([live[i] for i in order], n, psi0)
+    # global phases without controls are folded into `scalar`; dropped no-ops, X.X pairs and renamed SWAPs vanish
+    psi = np_oracle.simulate_gates([gate(i) for i in order], n, psi0)
     return scalar * psi
 
 
@@ -62,6 +83,16 @@ def test_plan_structure(name):
     live, low, segs, _ = plan_for(case.gates, n)
     k = 12
     seen = set()
+    relabel = RELABEL[id(segs)]
+
+    def planned(gi):
+        """(op, t0, t1, m) of the gate the plan executes under source id gi (the SWAP frame may have renamed its qubits)."""
+        if gi in relabel:
+            op, t0, t1, _ctrl = relabel[gi]
+            return op, t0, t1, (low[gi]["m"] if gi < len(low) else np.zeros(8))
+        rec = low[gi]
+        return int(rec["op"]), int(rec["t0"]), int(rec["t1"]), rec["m"]
+
     for cls, mask, idx in segs:
         assert cls in (cabi.SEG_GATE1Q, cabi.SEG_TILE, cabi.SEG_PERM, cabi.SEG_LOW6)
         assert idx and not (set(idx) & seen)
@@ -71,19 +102,17 @@ def test_plan_structure(name):
         if cls == cabi.SEG_TILE:
             assert popcount(mask) == min(k, n) and mask < (1 << n)
             for gi in idx:
-                rec = low[gi]
-                op = int(rec["op"])
+                op, t0, t1, m = planned(gi)
                 if op in (cabi.OP_MAT1, cabi.OP_X):
                     # a DIAG1-able MAT1 may sit outside the tile; a genuinely dense one may not
-                    m = rec["m"]
                     dense = op == cabi.OP_X or not (m[2] == 0 and m[3] == 0 and m[4] == 0 and m[5] == 0)
                     if dense:
-                        assert (mask >> int(rec["t0"])) & 1, (name, gi)
+                        assert (mask >> t0) & 1, (name, gi)
                 elif op == cabi.OP_SWAP:
-                    assert (mask >> int(rec["t0"])) & 1 and (mask >> int(rec["t1"])) & 1
+                    assert (mask >> t0) & 1 and (mask >> t1) & 1
         if cls == cabi.SEG_PERM:
-            assert all(int(low[gi]["op"]) in (cabi.OP_X, cabi.OP_SWAP) for gi in idx)
-    assert len(seen) <= len(live)
+            assert all(planned(gi)[0] in (cabi.OP_X, cabi.OP_SWAP) for gi in idx)
+    assert len([gi for gi in seen if gi < len(live)]) <= len(live)
 
 
 def test_headline_circuit_needs_few_sweeps():
@@ -146,7 +175,7 @@ def test_common_controls_restrict_tile_sweeps(name):
     n = case.n_qubits
     live = [g for g in case.gates if g.name != "I"]
     low = lower_gates(live, n)
-    segs, _scalar, common = cabi.plan_describe(n, cabi.B2SV_C128, low, cabi.PlanOpts.make(mux=False), with_common=True)
+    segs, _scalar, common, relabel = cabi.plan_describe(n, cabi.B2SV_C128, low, cabi.PlanOpts.make(mux=False), with_relabel=True)
     restricted = 0
     for (cls, mask, idx), (com, _n_ops) in zip(segs, common):
         if cls != cabi.SEG_TILE:
@@ -154,7 +183,8 @@ def test_common_controls_restrict_tile_sweeps(name):
             continue
         assert com & mask == 0
         for gi in idx:
-            assert int(low[gi]["ctrl_mask"]) & com == com, (name, gi)
+            ctrl = relabel[gi][3] if gi in relabel else int(low[gi]["ctrl_mask"])  # the SWAP frame may have renamed qubits
+            assert ctrl & com == com, (name, gi)
         restricted += com != 0
     if n >= 17:
         assert restricted > 0

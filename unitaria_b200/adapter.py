@@ -20,7 +20,7 @@ import numpy as np
 
 from .cabi import PlanOpts
 from .engine import StateVector
-from .lowering import lower_gates, touches_any_qubit
+from .lowering import LoweringError, lower_gates, touches_any_qubit
 from .subspace_prog import SubspaceProgram
 
 _DEFAULTS = {"dtype": "complex128", "device": 0, "opts": None}
@@ -116,6 +116,37 @@ def simulate_projected(tq_circuit, n_qubits: int, subspace_out, normalization, i
     return _run(tq_circuit, n_qubits, input).project(prog, scale=normalization)
 
 
+def simulate_columns(tq_circuit, n_qubits: int, subspace_out, normalization, inputs, keep: bool = True) -> list:
+    """``[simulate_projected(..., b) for b in inputs]`` -- the matrix case of ``Node.simulate`` (node.py:381-388) and
+    ``verify``'s loop (verifier.py:119-126) -- with the columns pipelined: one cached plan, one resident register,
+    and the device->host copy of column j (second stream, page-locked buffers) overlapping the sweeps of column
+    j+1.  ``keep=False`` recycles two result buffers and returns only the last two columns (throughput runs)."""
+    from .engine import PINNED
+
+    prog = subspace_out if isinstance(subspace_out, SubspaceProgram) else SubspaceProgram(subspace_out)
+    inputs = list(inputs)
+    if not touches_any_qubit(tq_circuit.gates) or not inputs:
+        return [simulate_projected(tq_circuit, n_qubits, prog, normalization, b) for b in inputs]
+    sv = _state(n_qubits)
+    low = _lowered(tq_circuit, n_qubits)
+    ring = [PINNED.array(prog.dimension, np.complex128) for _ in range(2)] if not keep else None
+    results = []
+    for k, b in enumerate(inputs):
+        slot = k & 1
+        sv.gather_wait(slot)  # column k-2 has landed (its buffer may be recycled)
+        if isinstance(b, np.ndarray):
+            sv.upload(b)
+        else:
+            sv.set_basis(int(b))
+        sv.apply_lowered(low, _DEFAULTS["opts"])
+        out = ring[slot] if ring is not None else PINNED.array(prog.dimension, np.complex128)
+        sv.project_async(prog, normalization, out, slot)
+        results.append(out)
+    sv.gather_wait(0)
+    sv.gather_wait(1)
+    return results if keep else results[-2:]
+
+
 def simulate_norm(tq_circuit, n_qubits: int, subspace_out, normalization, input=0) -> float:
     """``norm(normalization * project(simulate(input)))`` (node.py:390-403) as one device reduction."""
     prog = subspace_out if isinstance(subspace_out, SubspaceProgram) else SubspaceProgram(subspace_out)
@@ -134,11 +165,23 @@ def _basis_indices(prog: SubspaceProgram) -> np.ndarray:
     key = (prog.instrs.tobytes(), prog.entry)
     hit = _BASIS.get(key)
     if hit is None:
-        hit = _state(max(1, prog.total_qubits)).enumerate_basis(prog)
+        hit = _enumerate(prog)
         if len(_BASIS) > 64:
             _BASIS.clear()
         _BASIS[key] = hit
     return hit
+
+
+def _enumerate(prog: SubspaceProgram) -> np.ndarray:
+    """Member indices in ``enumerate_basis`` order.  Listing indices needs no amplitudes: members come from the
+    rank -> index map on the host when there are few of them, else from the device kernel on a throw-away handle
+    of the smallest size the ABI allows -- never by allocating (or evicting) a 2^total_qubits register."""
+    from .subspace_prog import spec_member
+
+    if prog.dimension <= 4096:
+        return np.array([spec_member(prog.spec, r) for r in range(prog.dimension)], dtype=np.int64)
+    with StateVector(1, dtype="complex64", device=_DEFAULTS["device"]) as tmp:
+        return tmp.enumerate_basis(prog)
 
 
 def block_encoding_compute(tq_circuit, n_qubits: int, subspace_in, subspace_out, normalization, input: np.ndarray) -> np.ndarray:
@@ -201,7 +244,7 @@ def estimate_norm_sampled(tq_circuit, n_qubits: int, subspace_out, normalization
         p_member = sv.project_norm2(prog)
         p_anc0 = sv.project_norm2(_all_free_program(t)) if t > 0 else p_member
     else:  # the circuit leaves |0..0> untouched
-        member0 = len(prog.instrs) > 0 and bool(_state(max(1, t)).enumerate_basis(prog)[:1] == 0) if prog.dimension else False
+        member0 = bool(_basis_indices(prog)[:1] == 0) if prog.dimension else False
         p_member, p_anc0 = (1.0 if member0 else 0.0), 1.0
     p_anc0 = min(1.0, max(0.0, p_anc0))
     p_member = min(p_anc0, max(0.0, p_member))
@@ -223,9 +266,8 @@ def _all_free_program(t: int) -> SubspaceProgram:
 
 
 def _host_project(prog: SubspaceProgram, vector: np.ndarray) -> np.ndarray:
-    # only reached for circuits that touch no qubit (tiny registers): index list from the device
-    sv = _state(max(1, prog.total_qubits))
-    return vector[sv.enumerate_basis(prog)]
+    # only reached for circuits that touch no qubit (tiny registers)
+    return vector[_basis_indices(prog)]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -245,7 +287,17 @@ def install(dtype="complex128", device: int = 0, opts: PlanOpts | None = None, p
         _ORIGINALS["Circuit.simulate"] = Circuit.simulate
 
     def simulate(self, input=0, **kwargs):
-        return simulate_circuit(self._tq_circuit, self.n_qubits, input, **kwargs)
+        # Only what the reference's own callers pass (backend="qulacs", nodes/node.py:378,386, verifier.py:123) is taken
+        # over.  Anything else tq.simulate understands (samples=, variables=, ...) and any gate outside the alphabet of
+        # unitaria_b200.lowering (Rp, ExpPauli, u3, parametrised angles, SWAP powers, ...) goes to the original
+        # tequila path, so user circuits that worked upstream keep working (and fail the way they failed upstream
+        # if tequila's backend is missing).
+        if any(k != "backend" for k in kwargs):
+            return _ORIGINALS["Circuit.simulate"](self, input, **kwargs)
+        try:
+            return simulate_circuit(self._tq_circuit, self.n_qubits, input, **kwargs)
+        except LoweringError:
+            return _ORIGINALS["Circuit.simulate"](self, input, **kwargs)
 
     simulate.__doc__ = _ORIGINALS["Circuit.simulate"].__doc__
     Circuit.simulate = simulate
@@ -259,17 +311,25 @@ def install(dtype="complex128", device: int = 0, opts: PlanOpts | None = None, p
             _ORIGINALS["Node.simulate_norm"] = Node.simulate_norm
 
         def node_simulate(self, input=None):
+            try:
+                return _node_simulate(self, input)
+            except LoweringError:  # a gate outside the engine's alphabet: the reference's own path
+                return _ORIGINALS["Node.simulate"](self, input)
+
+        def _node_simulate(self, input=None):
             if self.is_vector() and input is None:
                 input = 0
             circuit = self.circuit()
             prog = _subspace_program(self.subspace_out)
             if input is not None:
                 return simulate_projected(circuit._tq_circuit, circuit.n_qubits, prog, self.normalization, input)
-            # matrix case (node.py:381-388): one lowered plan, one resident register, dimension_in runs
-            basis_in = _state(max(1, self.subspace_in.total_qubits)).enumerate_basis(_subspace_program(self.subspace_in))
+            # matrix case (node.py:381-388): one lowered plan, one resident register, dimension_in runs whose
+            # result copies overlap the next column's sweeps (simulate_columns)
+            basis_in = _basis_indices(_subspace_program(self.subspace_in))
             output = np.zeros((self.dimension_out, self.dimension_in), dtype=np.complex128)
-            for i, b in enumerate(basis_in):
-                output[:, i] = simulate_projected(circuit._tq_circuit, circuit.n_qubits, prog, self.normalization, int(b))
+            cols = simulate_columns(circuit._tq_circuit, circuit.n_qubits, prog, self.normalization, [int(b) for b in basis_in])
+            for i, col in enumerate(cols):
+                output[:, i] = col
             return output
 
         def node_simulate_norm(self, input=None):
@@ -279,7 +339,10 @@ def install(dtype="complex128", device: int = 0, opts: PlanOpts | None = None, p
                 input = 0
             circuit = self.circuit()
             prog = _subspace_program(self.subspace_out)
-            return simulate_norm(circuit._tq_circuit, circuit.n_qubits, prog, self.normalization, input)
+            try:
+                return simulate_norm(circuit._tq_circuit, circuit.n_qubits, prog, self.normalization, input)
+            except LoweringError:
+                return _ORIGINALS["Node.simulate_norm"](self, input)
 
         try:  # sampling mode: BackendEstimator without materialised shots
             import unitaria.estimator.backend_estimator as ube

@@ -124,6 +124,11 @@ SYMBOLS = {
         ctypes.c_int,
         [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, _P, ctypes.c_uint64],
     ),
+    "b2sv_project_gather_async": (
+        ctypes.c_int,
+        [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, _P, ctypes.c_uint64, ctypes.c_int],
+    ),
+    "b2sv_gather_wait": (ctypes.c_int, [_P, ctypes.c_int]),
     "b2sv_embed": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, ctypes.c_uint64]),
     "b2sv_enumerate_basis": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, ctypes.c_uint64]),
     "b2sv_device_ptr": (ctypes.c_int, [_P, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_uint64)]),
@@ -190,9 +195,10 @@ def device_count() -> int:
     return int(load().b2sv_device_count())
 
 
-def plan_describe(n_qubits: int, dtype: int, gates: np.ndarray, opts: PlanOpts | None = None, with_common: bool = False):
+def plan_describe(n_qubits: int, dtype: int, gates: np.ndarray, opts: PlanOpts | None = None, with_common: bool = False, with_relabel: bool = False):
     """Planner introspection (host only, needs no GPU): list of (class, tile_mask, [gate indices]) and
-    the folded global scalar."""
+    the folded global scalar.  ``with_relabel``: also the {gate id: (op, t0, t1, ctrl_mask)} table of gates the
+    SWAP frame executes on renamed qubits (ids >= len(gates) are synthetic layout-restoring SWAPs)."""
     lib = load()
     gates = np.ascontiguousarray(gates, dtype=GATE_DTYPE)
     need = ctypes.c_size_t(0)
@@ -204,8 +210,15 @@ def plan_describe(n_qubits: int, dtype: int, gates: np.ndarray, opts: PlanOpts |
     scalar = 1.0 + 0.0j
     i = 0
     common = []
+    relabel = {}
     while i < len(words):
         cls, cnt, mask, com, n_ops = (int(words[i + k]) for k in range(5))
+        if cls == -2:
+            for r in range(cnt):
+                gid, op, t0, t1, ctrl = (int(words[i + 5 + 5 * r + k]) for k in range(5))
+                relabel[gid] = (op, t0, t1, ctrl & 0xFFFFFFFFFFFFFFFF)
+            i += 5 + 5 * cnt
+            continue
         if cls == -1:
             re = np.array([words[i + 5]], dtype=np.int64).view(np.float64)[0]
             im = np.array([words[i + 6]], dtype=np.int64).view(np.float64)[0]
@@ -215,6 +228,8 @@ def plan_describe(n_qubits: int, dtype: int, gates: np.ndarray, opts: PlanOpts |
         segs.append((cls, mask & 0xFFFFFFFFFFFFFFFF, [int(w) for w in words[i + 5 : i + 5 + cnt]]))
         common.append((com & 0xFFFFFFFFFFFFFFFF, n_ops))
         i += 5 + cnt
+    if with_relabel:
+        return segs, scalar, common, relabel
     if with_common:
         return segs, scalar, common
     return segs, scalar

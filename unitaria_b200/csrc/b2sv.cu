@@ -93,6 +93,13 @@ struct b2sv {
     std::vector<Peer> peers;
     void* d_dist_gates = nullptr;
     size_t d_dist_gates_cap = 0;
+    // pipelined results (b2sv_project_gather_async): two device result buffers drained by a copy stream while
+    // the next input's sweeps run on the main stream
+    void* d_col[2] = {nullptr, nullptr};
+    size_t d_col_cap[2] = {0, 0};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_col_kernel[2] = {nullptr, nullptr}, ev_col_copy[2] = {nullptr, nullptr};
+    bool col_pending[2] = {false, false};
     std::vector<unsigned char> plan_gate_copy;  // the gate list the cached plan was made from (compared on a hash hit)
     bool timing_on = false;        // last b2sv_apply asked for per-launch timing: time init/project too
     double sre = 1.0, sim = 0.0;   // pending global scalar (folded uncontrolled global phases)
@@ -773,7 +780,7 @@ double subprog_members(const b2sv_subinstr* prog, int n_instr, int entry) {
 }
 
 int upload_subprog(b2sv* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits, int* count_bits,
-                   int max_target_qubits = -1, bool* full_cover = nullptr) {
+                   int max_target_qubits = -1, bool* full_cover = nullptr, uint64_t* head_zeros = nullptr) {
     if (max_target_qubits < 0) max_target_qubits = sv->n;
     if (!prog || n_instr <= 0) return fail(B2SV_EINVAL, "empty subspace program");
     if (n_instr > kMaxSubInstr) return fail(B2SV_EINVAL, "subspace program has %d instructions (max %d)", n_instr, kMaxSubInstr);
@@ -809,6 +816,7 @@ int upload_subprog(b2sv* sv, const b2sv_subinstr* prog, int n_instr, int entry, 
             pc = prog[pc].next0;
         }
         while (bits > 0 && ((zero_mask >> (bits - 1)) & 1)) --bits;
+        if (head_zeros) *head_zeros = zero_mask & low_mask(bits);
     }
     if (count_bits) *count_bits = bits;
     if (n_instr > sv->d_sub_cap) {
@@ -912,6 +920,15 @@ int b2sv_destroy(b2sv_t* sv) {
     for (auto e : sv->marks)
         if (e) cudaEventDestroy(e);
     b2sv_ipc_detach(sv);
+    if (sv->copy_stream) {
+        cudaStreamSynchronize(sv->copy_stream);
+        cudaStreamDestroy(sv->copy_stream);
+    }
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(sv->d_col[i]);
+        if (sv->ev_col_kernel[i]) cudaEventDestroy(sv->ev_col_kernel[i]);
+        if (sv->ev_col_copy[i]) cudaEventDestroy(sv->ev_col_copy[i]);
+    }
     if (sv->ev_ready) cudaEventDestroy(sv->ev_ready);
     if (sv->ev_done) cudaEventDestroy(sv->ev_done);
     cudaFree(sv->d_dist_gates);
@@ -1214,14 +1231,19 @@ int b2sv_project_norm2_at(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, in
     if (int rc = materialise(sv)) return rc;
     int count_bits = 0;
     bool full_cover = false;
-    if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits, 64, &full_cover)) return rc;
+    uint64_t head_zeros = 0;
+    if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits, 64, &full_cover, &head_zeros)) return rc;
     if (target_qubits < 64 && (index_base >> target_qubits) != 0) {  // this shard holds ancilla != 0 only
         *out = 0.0;
         return B2SV_OK;
     }
     if (count_bits > sv->n) count_bits = sv->n;
-    const uint64_t cnt = 1ull << count_bits;
-    const bool grouped = low_free_bits(prog, entry) >= kProjectGroupBits && cnt >= (uint64_t)kProjectWarpSpan;
+    head_zeros &= low_mask(count_bits);
+    const bool grouped = head_zeros == 0 && low_free_bits(prog, entry) >= kProjectGroupBits && (1ull << count_bits) >= (uint64_t)kProjectWarpSpan;
+    ExpandArgs scan{};
+    if (!grouped) fill_expand(scan, head_zeros);
+    // grouped: the whole range; else only the indices whose always-zero bits are clear
+    const uint64_t cnt = 1ull << (count_bits - scan.m);
     const int grid = grid_for(sv, grouped ? cnt >> kProjectGroupBits : cnt);
     int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
         using A = std::remove_pointer_t<decltype(tag)>;
@@ -1231,10 +1253,10 @@ int b2sv_project_norm2_at(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, in
         LaunchTimer lt(sv, sv->timing_on, CLS_PROJECT, (double)sv->amp_bytes * members);
         if (grouped)
             k_project_norm2<A, true><<<grid, kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, index_base,
-                                                                       sv->d_partial);
+                                                                       sv->d_partial, scan);
         else
             k_project_norm2<A, false><<<grid, kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, index_base,
-                                                                        sv->d_partial);
+                                                                        sv->d_partial, scan);
         k_reduce_partials<<<1, kThreads, 0, sv->stream>>>(sv->d_partial, grid, sv->d_partial + sv->n_partial);
         sv->stats.launches++;  // the reduction is a launch too
         sv->stats.launches_by_class[CLS_PROJECT]++;
@@ -1262,9 +1284,13 @@ int b2sv_project_gather(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int 
     CU(cudaSetDevice(sv->device));
     if (int rc = materialise(sv)) return rc;
     int count_bits = 0;
-    if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits)) return rc;
+    uint64_t head_zeros = 0;
+    if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits, -1, nullptr, &head_zeros)) return rc;
     if (dim == 0) return B2SV_OK;
-    const uint64_t cnt = 1ull << count_bits;
+    const bool grouped = head_zeros == 0 && low_free_bits(prog, entry) >= kProjectGroupBits && (1ull << count_bits) >= (uint64_t)kProjectWarpSpan;
+    ExpandArgs scan{};
+    if (!grouped) fill_expand(scan, head_zeros);
+    const uint64_t cnt = 1ull << (count_bits - scan.m);
     if (int rc = ensure_gather(sv, dim * 16)) return rc;
     double2* d_out = (double2*)sv->d_gather;
     cudaMemsetAsync(d_out, 0, dim * 16, sv->stream);
@@ -1273,18 +1299,86 @@ int b2sv_project_gather(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int 
     dispatch_dtype(sv, [&](auto* tag) -> int {
         using A = std::remove_pointer_t<decltype(tag)>;
         LaunchTimer lt(sv, sv->timing_on, CLS_PROJECT, (double)sv->amp_bytes * std::min((double)cnt, (double)dim) + 16.0 * (double)dim);
-        if (low_free_bits(prog, entry) >= kProjectGroupBits && cnt >= (uint64_t)kProjectWarpSpan)
+        if (grouped)
             k_project_gather<A, true><<<grid_for(sv, cnt >> kProjectGroupBits), kThreads, 0, sv->stream>>>(
-                (const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, s, d_out, dim, prog[entry].weight);
+                (const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, s, d_out, dim, prog[entry].weight, scan);
         else
             k_project_gather<A, false><<<grid_for(sv, cnt), kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1,
-                                                                                     s, d_out, dim, 0);
+                                                                                     s, d_out, dim, 0, scan);
         return B2SV_OK;
     });
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, d_out, dim * 16, cudaMemcpyDeviceToHost, sv->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(sv->stream);
     if (e != cudaSuccess) return fail(B2SV_ECUDA, "project_gather failed: %s", cudaGetErrorString(e));
+    return B2SV_OK;
+}
+
+int b2sv_project_gather_async(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
+                              double scale_re, double scale_im, void* host_out, uint64_t dim, int slot) {
+    if (int rc = check(sv)) return rc;
+    if (slot < 0 || slot > 1) return fail(B2SV_EINVAL, "slot %d outside [0,1]", slot);
+    if (!host_out && dim > 0) return fail(B2SV_EINVAL, "host_out is null");
+    CU(cudaSetDevice(sv->device));
+    if (!sv->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&sv->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&sv->ev_col_kernel[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&sv->ev_col_copy[i], cudaEventDisableTiming));
+        }
+    }
+    if (int rc = materialise(sv)) return rc;
+    int count_bits = 0;
+    uint64_t head_zeros = 0;
+    if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits, -1, nullptr, &head_zeros)) return rc;
+    if (dim == 0) return B2SV_OK;
+    if (sv->col_pending[slot]) {
+        if (dim * 16 > sv->d_col_cap[slot]) CU(cudaEventSynchronize(sv->ev_col_copy[slot]));  // about to free the buffer
+        else CU(cudaStreamWaitEvent(sv->stream, sv->ev_col_copy[slot], 0));                      // about to overwrite it
+        sv->col_pending[slot] = false;
+    }
+    if (dim * 16 > sv->d_col_cap[slot]) {
+        CU(cudaStreamSynchronize(sv->stream));
+        cudaFree(sv->d_col[slot]);
+        sv->d_col[slot] = nullptr;
+        sv->d_col_cap[slot] = 0;
+        CU(cudaMalloc(&sv->d_col[slot], dim * 16));
+        sv->d_col_cap[slot] = dim * 16;
+    }
+    const bool grouped = head_zeros == 0 && low_free_bits(prog, entry) >= kProjectGroupBits && (1ull << count_bits) >= (uint64_t)kProjectWarpSpan;
+    ExpandArgs scan{};
+    if (!grouped) fill_expand(scan, head_zeros);
+    const uint64_t cnt = 1ull << (count_bits - scan.m);
+    double2* d_out = (double2*)sv->d_col[slot];
+    CU(cudaMemsetAsync(d_out, 0, dim * 16, sv->stream));
+    const double2 s = make_double2(scale_re * sv->sre - scale_im * sv->sim, scale_re * sv->sim + scale_im * sv->sre);
+    dispatch_dtype(sv, [&](auto* tag) -> int {
+        using A = std::remove_pointer_t<decltype(tag)>;
+        LaunchTimer lt(sv, sv->timing_on, CLS_PROJECT, (double)sv->amp_bytes * std::min((double)cnt, (double)dim) + 16.0 * (double)dim);
+        if (grouped)
+            k_project_gather<A, true><<<grid_for(sv, cnt >> kProjectGroupBits), kThreads, 0, sv->stream>>>(
+                (const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, s, d_out, dim, prog[entry].weight, scan);
+        else
+            k_project_gather<A, false><<<grid_for(sv, cnt), kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1,
+                                                                                     s, d_out, dim, 0, scan);
+        return B2SV_OK;
+    });
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(sv->ev_col_kernel[slot], sv->stream));
+    CU(cudaStreamWaitEvent(sv->copy_stream, sv->ev_col_kernel[slot], 0));
+    CU(cudaMemcpyAsync(host_out, d_out, dim * 16, cudaMemcpyDeviceToHost, sv->copy_stream));
+    CU(cudaEventRecord(sv->ev_col_copy[slot], sv->copy_stream));
+    sv->col_pending[slot] = true;
+    return B2SV_OK;
+}
+
+int b2sv_gather_wait(b2sv_t* sv, int slot) {
+    if (int rc = check(sv)) return rc;
+    if (slot < 0 || slot > 1) return fail(B2SV_EINVAL, "slot %d outside [0,1]", slot);
+    if (!sv->col_pending[slot]) return B2SV_OK;
+    CU(cudaSetDevice(sv->device));
+    CU(cudaEventSynchronize(sv->ev_col_copy[slot]));
+    sv->col_pending[slot] = false;
     return B2SV_OK;
 }
 
@@ -1323,7 +1417,8 @@ int b2sv_enumerate_basis(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int
     if (!host_out && dim > 0) return fail(B2SV_EINVAL, "host_out is null");
     CU(cudaSetDevice(sv->device));
     int count_bits = 0;
-    if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits)) return rc;
+    // listing member indices touches no amplitude: any handle will do, whatever its register size
+    if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits, 64)) return rc;
     if (dim == 0) return B2SV_OK;
     const uint64_t cnt = 1ull << count_bits;
     if (int rc = ensure_gather(sv, dim * 8)) return rc;
@@ -1774,6 +1869,20 @@ int b2sv_plan_describe(int n_qubits, int dtype, const b2sv_gate* gates, size_t n
         put(0);
         put(re_bits);
         put(im_bits);
+    }
+    {  // second trailer: gates the SWAP frame executed on renamed qubits, and the synthetic SWAPs that restore the layout
+        put(-2);
+        put((int64_t)plan.relabelled.size());
+        put(0);
+        put(0);
+        put(0);
+        for (const Plan::Relabel& r : plan.relabelled) {
+            put(r.id);
+            put(r.op);
+            put(r.t0);
+            put(r.t1);
+            put((int64_t)r.ctrl);
+        }
     }
     if (n_words) *n_words = w;
     return B2SV_OK;

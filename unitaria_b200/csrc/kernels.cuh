@@ -1405,10 +1405,13 @@ __device__ __forceinline__ bool sub_member_rank(const b2sv_subinstr* __restrict_
 constexpr int kProjectGroup = 8;        // amplitudes per group
 constexpr int kProjectWarpSpan = 256;   // amplitudes a warp handles per iteration (32 groups)
 
+// `scan`: positions below the scanned range that every member has 0 (ZEROS instructions every walk passes): the
+// non-grouped kernels enumerate only the indices with those bits clear -- a "000###...###000"-shaped subspace
+// (BASELINE config 3: 2^20 members strided by 8 in a 2^26 range) needs 2^20 walks, not 2^26.
 template <typename A, bool GROUPED>
 __global__ void __launch_bounds__(kThreads) k_project_norm2(const A* __restrict__ psi, const b2sv_subinstr* __restrict__ sub,
                                                             uint64_t count, int entry, int max_steps, uint64_t index_base,
-                                                            double* __restrict__ partial) {
+                                                            double* __restrict__ partial, const ExpandArgs scan) {
     double acc = 0.0;
     if (GROUPED) {
         const int lane = threadIdx.x & 31;
@@ -1430,7 +1433,8 @@ __global__ void __launch_bounds__(kThreads) k_project_norm2(const A* __restrict_
         }
     } else {
         const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
+            const uint64_t i = expand_bits(k, scan);
             uint64_t r;
             if (sub_member_rank(sub, entry, max_steps, index_base | i, r)) {
                 const double2 v = to_c128(psi[i]);
@@ -1466,7 +1470,8 @@ __global__ void __launch_bounds__(kThreads) k_reduce_partials(const double* __re
 template <typename A, bool GROUPED>
 __global__ void __launch_bounds__(kThreads) k_project_gather(const A* __restrict__ psi, const b2sv_subinstr* __restrict__ sub,
                                                              uint64_t count, int entry, int max_steps,
-                                                             double2 scale, double2* __restrict__ out, uint64_t dim, uint64_t weight) {
+                                                             double2 scale, double2* __restrict__ out, uint64_t dim, uint64_t weight,
+                                                             const ExpandArgs scan) {
     if (GROUPED) {
         const int lane = threadIdx.x & 31;
         const uint64_t warps = (uint64_t)gridDim.x * (kThreads / 32);
@@ -1489,7 +1494,8 @@ __global__ void __launch_bounds__(kThreads) k_project_gather(const A* __restrict
         }
     } else {
         const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
+            const uint64_t i = expand_bits(k, scan);
             uint64_t r;
             if (sub_member_rank(sub, entry, max_steps, i, r) && r < dim) out[r] = cmul(scale, to_c128(psi[i]));
         }

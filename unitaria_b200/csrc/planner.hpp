@@ -90,6 +90,7 @@ struct PlanConfig {
     bool low6 = true;                     // sweeps confined to the low 6 qubits use the warp-shuffle kernel
     bool mono = true;                     // monomial phases: runs of X / SWAP / phase gates inside a tile sweep cost
                                           // index arithmetic only, so such runs ride in tile sweeps
+    bool frame = true;                    // SWAP frame: (controlled) SWAPs relabel qubits at plan time instead of moving data
     double mono_gate_cost = 0.001;        // one gate of a monomial phase in units of one full sweep: the index walks
                                           // run on the host, the device pays per phase, not per gate
 };
@@ -131,6 +132,15 @@ struct Plan {
     std::vector<Segment> segs;
     double scalar_re = 1.0, scalar_im = 0.0;  // folded uncontrolled global phases
     uint64_t gates_in = 0, gates_live = 0;
+    // SWAP frame (make_plan): caller gates that were executed on relabelled qubits, and the synthetic SWAPs that
+    // restore the layout (source ids >= gates_in).  {id, op, t0, t1, ctrl} -- exported by b2sv_plan_describe so that a
+    // plan can be replayed gate by gate.
+    struct Relabel {
+        int64_t id;
+        uint8_t op, t0, t1;
+        uint64_t ctrl;
+    };
+    std::vector<Relabel> relabelled;
 };
 
 inline int popcount64(uint64_t x) { return __builtin_popcountll(x); }
@@ -162,6 +172,7 @@ inline PlanConfig default_config(int n, int dtype, const b2sv_plan_opts* o) {
     c.phases = !(env_ab & 2);
     c.low6 = !(env_ab & 4);
     c.mono = !(env_ab & 8);
+    c.frame = !(env_ab & 16);
     if (o) {
         c.fuse = o->fuse != 0;
         c.perm_runs = o->perm_runs != 0;
@@ -172,8 +183,10 @@ inline PlanConfig default_config(int n, int dtype, const b2sv_plan_opts* o) {
         c.phases = !(ab & 2);  // reserved bit 1: no register phases (A/B switch)
         c.low6 = !(ab & 4);    // reserved bit 2: no warp-shuffle low-qubit sweeps (A/B switch)
         c.mono = !(ab & 8);    // reserved bit 3: no monomial phases (A/B switch)
+        c.frame = !(ab & 16);  // reserved bit 4: no SWAP frame (A/B switch)
     }
     if (!c.phases) c.mono = false;
+    if (!c.fuse) c.frame = false;
     if (c.tile_qubits > 13 && c.amp_bytes == 16) c.tile_qubits = 13;
     if (c.tile_qubits > 14) c.tile_qubits = 14;
     if (c.tile_qubits < 3) c.tile_qubits = 3;
@@ -338,7 +351,10 @@ inline void fuse_multiplexors(Plan& plan) {
         // with a single entry is just another 2x2 gate
         // measured (profiles/fusion_r1.txt): the table-driven pass only pays for long multiplexor runs
         // (state preparation); short controlled runs are cheaper as plain gates
-        const bool worth = nonperm && len >= 2 && (C == 0 ? true : (len >= 6 && separate > 1.8 * scale));
+        // ... and a multiplexor with one or two index bits is cheaper as its plain gates inside ONE register phase
+        // (target + controls are <= 3 qubits): ncu on config 3's sweep (profiles/ncu_r2_cfg3.txt) had the L1 data
+        // pipe at 97 % from the per-pair table look-ups of a 2-bit multiplexor
+        const bool worth = nonperm && len >= 2 && (C == 0 ? true : (len >= 6 && popcount64(C) >= 3 && separate > 1.8 * scale));
         if (!worth) {
             out.push_back(g);
             ++i;
@@ -541,84 +557,58 @@ inline void emit_block(Plan& plan, const std::vector<PGate>& G, size_t a, size_t
     out.push_back(f);
 }
 
-// A maximal run of consecutive gates confined to <= 3 qubits is cut into pieces, each either left as plain gates
-// (they ride in register phases) or multiplied out into one dense 4x4 / 8x8 block, so that the FP64 work is smallest
-// (dynamic programme over the cut points).  ncu on the BPX sweeps (profiles/ncu_r2_bpx.txt) showed what the greedy
-// "one block per run" of round 1 cost: the 2-qubit cosine-sine unitaries of circuits/generic_unitary.py (6 Ry, 9 Rz,
-// 6 phases, 6 CNOT: 672 DFMA per 8 amplitudes as plain gates, 128 as a 4x4 block) were followed by ONE SWAP with a
-// third qubit, which turned each of them into an 8x8 block at twice the work.
+// The gate list is cut into pieces, each either left as plain gates (they ride in register phases) or multiplied out
+// into one dense 4x4 / 8x8 block, so that the FP64 work is smallest: a dynamic programme over the whole list
+// (dp[p] = least cost of the first p gates; a block may end at p and start at any q for which G[q, p) stays on <= 3
+// qubits).  Costs are DFMA per 8 amplitudes of the FULL state: a gate with c controls costs 2^-c of its uncontrolled
+// self, a block 2^-|K| with K the controls all its gates share.  ncu on the BPX sweeps (profiles/ncu_r2_bpx.txt) showed
+// what the greedy "one block per maximal run" of round 1 cost: the 2-qubit cosine-sine unitaries of
+// circuits/generic_unitary.py (6 Ry, 9 Rz, 6 phases, 6 CNOT: 672 DFMA per 8 amplitudes as plain gates, 128 as a 4x4
+// block) were followed by ONE SWAP with a third qubit, which turned each of them into an 8x8 block at twice the work.
 inline void fuse_blocks(Plan& plan) {
-    std::vector<PGate> out;
-    out.reserve(plan.gates.size());
     const std::vector<PGate>& G = plan.gates;
-    size_t i = 0;
-    while (i < G.size()) {
-        if (!blockable_gate(G[i])) {
-            out.push_back(G[i]);
-            ++i;
-            continue;
-        }
-        // the maximal run on <= 3 qubits starting here
-        size_t j = i + 1;
-        {
-            uint64_t K = G[i].ctrl, T = gate_targets(G[i]), U = G[i].ctrl;
-            while (j < G.size() && blockable_gate(G[j])) {
-                const uint64_t K2 = K & G[j].ctrl, T2 = T | gate_targets(G[j]), U2 = U | G[j].ctrl;
-                if (popcount64(T2 | (U2 & ~K2)) > kBlockMaxQubits || (T2 & K2) != 0) break;
-                K = K2;
-                T = T2;
-                U = U2;
-                ++j;
+    const size_t N = G.size();
+    if (N == 0) return;
+    std::vector<double> dp(N + 1, 0.0);
+    std::vector<uint32_t> cut(N + 1, 0);
+    std::vector<char> blk(N + 1, 0);
+    constexpr size_t kMaxBlockGates = 512;
+    for (size_t p = 1; p <= N; ++p) {
+        const PGate& last = G[p - 1];
+        dp[p] = dp[p - 1] + gate_fp64_cost(last, 0);
+        cut[p] = (uint32_t)(p - 1);
+        blk[p] = 0;
+        if (!blockable_gate(last)) continue;
+        uint64_t K = last.ctrl, T = gate_targets(last), U = last.ctrl;
+        bool nonperm = !last.is_perm(), real = gate_is_real(last);
+        for (size_t q = p - 1; q-- > 0 && p - q <= kMaxBlockGates;) {
+            const PGate& g = G[q];
+            if (!blockable_gate(g)) break;
+            K &= g.ctrl;
+            T |= gate_targets(g);
+            U |= g.ctrl;
+            const int kb = popcount64(T | (U & ~K));
+            if (kb > kBlockMaxQubits || (T & K) != 0) break;
+            nonperm |= !g.is_perm();
+            real = real && gate_is_real(g);
+            if (p - q < 3 || kb < 2 || !nonperm) continue;
+            const double c = dp[q] + std::ldexp(block_fp64_cost(kb, real), -popcount64(K));
+            if (c < dp[p]) {
+                dp[p] = c;
+                cut[p] = (uint32_t)q;
+                blk[p] = 1;
             }
         }
-        const size_t L = j - i;
-        if (L < 3) {
-            out.push_back(G[i]);
-            ++i;
-            continue;
-        }
-        // dp[p]: least cost of G[i, i+p); cut[p]: start of the last piece; blk[p]: that piece is a block
-        const size_t Lc = std::min<size_t>(L, 256);  // bound the quadratic search on very long runs
-        std::vector<double> dp(Lc + 1, 0.0);
-        std::vector<size_t> cut(Lc + 1, 0);
-        std::vector<char> blk(Lc + 1, 0);
-        for (size_t p = 1; p <= Lc; ++p) {
-            // last gate alone, as a plain gate (its controls all count: nothing is common to a single gate's "run")
-            dp[p] = dp[p - 1] + gate_fp64_cost(G[i + p - 1], G[i + p - 1].ctrl);
-            cut[p] = p - 1;
-            blk[p] = 0;
-            // a block over G[i+q, i+p), q descending
-            uint64_t K = G[i + p - 1].ctrl, T = gate_targets(G[i + p - 1]), U = G[i + p - 1].ctrl;
-            bool nonperm = !G[i + p - 1].is_perm(), real = gate_is_real(G[i + p - 1]);
-            for (size_t q = p - 1; q-- > 0;) {
-                const PGate& g = G[i + q];
-                K &= g.ctrl;
-                T |= gate_targets(g);
-                U |= g.ctrl;
-                const uint64_t B = T | (U & ~K);
-                const int kb = popcount64(B);
-                if (kb > kBlockMaxQubits || (T & K) != 0) break;
-                nonperm |= !g.is_perm();
-                real = real && gate_is_real(g);
-                if (p - q < 3 || kb < 2 || !nonperm) continue;
-                const double c = dp[q] + block_fp64_cost(kb, real);
-                if (c < dp[p]) {
-                    dp[p] = c;
-                    cut[p] = q;
-                    blk[p] = 1;
-                }
-            }
-        }
-        // walk the cuts back, then emit front to back
-        std::vector<std::pair<size_t, size_t>> pieces;  // [first, last) relative to i; blocks flagged through blk[last]
-        for (size_t p = Lc; p > 0; p = cut[p]) pieces.push_back({cut[p], p});
-        for (size_t k = pieces.size(); k-- > 0;) {
-            const size_t a = i + pieces[k].first, b = i + pieces[k].second;
-            if (blk[pieces[k].second]) emit_block(plan, G, a, b, out);
-            else
-                for (size_t q = a; q < b; ++q) out.push_back(G[q]);
-        }
-        i += Lc;
+    }
+    std::vector<std::pair<size_t, size_t>> pieces;
+    for (size_t p = N; p > 0; p = cut[p]) pieces.push_back({cut[p], p});
+    std::vector<PGate> out;
+    out.reserve(N);
+    for (size_t k = pieces.size(); k-- > 0;) {
+        const size_t a = pieces[k].first, b = pieces[k].second;
+        if (blk[b]) emit_block(plan, G, a, b, out);
+        else
+            for (size_t q = a; q < b; ++q) out.push_back(G[q]);
     }
     plan.gates.swap(out);
 }
@@ -730,17 +720,107 @@ inline Plan make_plan(const b2sv_gate* gates, size_t n_gates, const PlanConfig& 
     Plan plan;
     plan.gates_in = n_gates;
     plan.gates.reserve(n_gates);
-    for (size_t j = 0; j < n_gates; ++j) {
+    // SWAP frame.  A (controlled) SWAP does not have to move amplitudes: it renames two qubits.  While every following
+    // gate carries the SWAP's controls C (then it only acts where the SWAP did), the rename is applied to the gates
+    // instead -- phys[q] is where logical qubit q lives -- and the data moves once, when a gate without those controls
+    // arrives or the circuit ends (a few SWAPs that ride in one monomial phase).  Block-encoding circuits are full of
+    // this: nodes/permutation/permutation.py emits SWAP networks between the two-qubit unitaries of an LCU term, all
+    // under the term's selector controls; ncu / per-sweep timings of BPX L=8 showed one shared-memory pass per SWAP
+    // chain (13 ms of a 69 ms step) and, worse, the chains kept neighbouring unitaries from fusing.
+    struct Frame {
+        bool active = false;
+        uint64_t C = 0, moved = 0;
+        uint8_t phys[64];
+    } fr;
+    int64_t next_virtual = (int64_t)n_gates;
+    uint64_t absorbed = 0;  // SWAPs executed by renaming (they are live gates of the circuit all the same)
+    auto push_gate = [&](const b2sv_gate& raw, int64_t id) {
         PGate g;
-        if (!normalise_gate(gates[j], (int)j, g, plan.scalar_re, plan.scalar_im)) continue;
+        if (!normalise_gate(raw, (int)id, g, plan.scalar_re, plan.scalar_im)) return;
         // adjacent self-inverse pairs cancel (X.X, SWAP.SWAP with identical controls)
         if (g.is_perm() && !plan.gates.empty() && same_perm_gate(plan.gates.back(), g)) {
             plan.gates.pop_back();
-            continue;
+            return;
         }
         plan.gates.push_back(g);
+    };
+    auto flush_frame = [&]() {
+        if (!fr.active) return;
+        fr.active = false;
+        if (!fr.moved) return;
+        uint8_t inv[64];
+        for (int q = 0; q < 64; ++q) inv[fr.phys[q]] = (uint8_t)q;
+        for (int q = 0; q < 64; ++q) {
+            if (fr.phys[q] == q) continue;
+            const int x = fr.phys[q], other = inv[q];  // logical q lives at x; position q holds logical `other`
+            b2sv_gate sw{};
+            sw.op = B2SV_OP_SWAP;
+            sw.n_targets = 2;
+            sw.t0 = (uint8_t)q;
+            sw.t1 = (uint8_t)x;
+            sw.ctrl_mask = fr.C;
+            plan.relabelled.push_back({next_virtual, B2SV_OP_SWAP, sw.t0, sw.t1, sw.ctrl_mask});
+            push_gate(sw, next_virtual++);
+            fr.phys[q] = (uint8_t)q;
+            fr.phys[other] = (uint8_t)x;
+            inv[q] = (uint8_t)q;
+            inv[x] = (uint8_t)other;
+        }
+        fr.moved = 0;
+    };
+    for (size_t j = 0; j < n_gates; ++j) {
+        b2sv_gate raw = gates[j];
+        if (cfg.frame) {
+            const bool is_swap = raw.op == B2SV_OP_SWAP && raw.t0 != raw.t1;
+            uint64_t qm = raw.ctrl_mask;
+            if (raw.op != B2SV_OP_PHASE) qm |= 1ull << raw.t0;
+            if (raw.op == B2SV_OP_SWAP) qm |= 1ull << raw.t1;
+            for (int pass = 0; pass < 2; ++pass) {  // second pass: the same gate after a flush
+                if (!fr.active) {
+                    if (is_swap) {  // start a frame with this SWAP
+                        fr.active = true;
+                        fr.C = raw.ctrl_mask;
+                        fr.moved = 0;
+                        for (int q = 0; q < 64; ++q) fr.phys[q] = (uint8_t)q;
+                    } else {
+                        break;  // no frame, ordinary gate
+                    }
+                }
+                if (is_swap && raw.ctrl_mask == fr.C) {  // absorbed: rename
+                    std::swap(fr.phys[raw.t0], fr.phys[raw.t1]);
+                    fr.moved |= (1ull << raw.t0) | (1ull << raw.t1);
+                    bool ident = true;
+                    for (int q = 0; q < 64 && ident; ++q) ident = fr.phys[q] == q;
+                    if (ident) fr.moved = 0;
+                    ++absorbed;
+                    raw.op = 0xFF;  // nothing to emit
+                    break;
+                }
+                if ((raw.ctrl_mask & fr.C) == fr.C) {  // acts only where the deferred SWAPs did: rename its qubits
+                    if (fr.moved & qm) {
+                        uint64_t c2 = 0;
+                        for (int q = 0; q < 64; ++q)
+                            if ((raw.ctrl_mask >> q) & 1) c2 |= 1ull << fr.phys[q];
+                        raw.ctrl_mask = c2;
+                        if (raw.op != B2SV_OP_PHASE) raw.t0 = fr.phys[raw.t0];
+                        if (raw.op == B2SV_OP_SWAP) raw.t1 = fr.phys[raw.t1];
+                        plan.relabelled.push_back({(int64_t)j, raw.op, raw.t0, raw.t1, raw.ctrl_mask});
+                    }
+                    break;
+                }
+                if (((fr.moved | fr.C) & qm) == 0) break;  // touches neither the renamed qubits nor the controls: commutes
+                flush_frame();                             // the data has to move now; then look at the gate again
+            }
+            if (raw.op == 0xFF) continue;
+        }
+        push_gate(raw, (int64_t)j);
     }
-    plan.gates_live = plan.gates.size();
+    flush_frame();
+    {   // live gates of the CALLER's circuit: what survived normalisation, plus renamed SWAPs, minus synthetic ones
+        uint64_t synthetic = 0;
+        for (const PGate& g : plan.gates) synthetic += (uint64_t)g.src >= n_gates ? 1 : 0;
+        plan.gates_live = plan.gates.size() + absorbed - synthetic;
+    }
     if (cfg.fuse && cfg.mux) {
         fuse_multiplexors(plan);
         fuse_blocks(plan);

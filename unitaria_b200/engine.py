@@ -242,6 +242,20 @@ class StateVector:
         )
         return out
 
+    def project_async(self, subspace, scale: complex, out: np.ndarray, slot: int) -> None:
+        """:meth:`project` without waiting: the result lands in ``out`` once :meth:`gather_wait` (same slot) returns."""
+        p = self._program(subspace)
+        assert out.dtype == np.complex128 and out.flags.c_contiguous and out.size == p.dimension
+        s = complex(scale)
+        cabi.check(
+            self._lib.b2sv_project_gather_async(
+                self._h, p.instrs.ctypes.data, len(p.instrs), p.entry, p.total_qubits, s.real, s.imag, out.ctypes.data, p.dimension, int(slot)
+            )
+        )
+
+    def gather_wait(self, slot: int) -> None:
+        cabi.check(self._lib.b2sv_gather_wait(self._h, int(slot)))
+
     def embed(self, subspace, vector: np.ndarray) -> None:
         """psi := sum_r vector[r] |basis_r>: the inverse of :meth:`project` and the device form of the
         embedding in ``BlockEncoding.compute`` (nodes/block_encoding.py:49-52) -- only ``dimension``

@@ -69,6 +69,14 @@ def _power_matrix(name: str, power: float):
     return tuple(out)
 
 
+def _num(x, what: str) -> float:
+    """Numeric gate parameter; tequila Variables / objectives (parametrised circuits) are not lowered."""
+    try:
+        return float(x)
+    except (TypeError, ValueError) as exc:
+        raise LoweringError(f"{what}: parameter {x!r} is not a number (parametrised gates are outside this engine's alphabet)") from exc
+
+
 def _mask(qubits) -> int:
     m = 0
     for q in qubits:
@@ -100,7 +108,7 @@ def lower_gates(gates, n_qubits: int | None = None) -> np.ndarray:
         m = mats[k]
         if uname == "GLOBALPHASE":
             ops[k], nts[k] = OP_PHASE, 0
-            m[0], m[1] = _cis(float(g.parameter))
+            m[0], m[1] = _cis(_num(g.parameter, name))
         elif uname == "SWAP":
             power = getattr(g, "power", 1)
             if power not in (1, None):
@@ -119,29 +127,29 @@ def lower_gates(gates, n_qubits: int | None = None) -> np.ndarray:
                     ops[k] = OP_X
                 else:
                     ops[k] = OP_MAT1
-                    m[:] = [v for pair in _power_matrix(uname, float(power)) for v in pair]
+                    m[:] = [v for pair in _power_matrix(uname, _num(power, name)) for v in pair]
             elif uname == "Z":
                 power = getattr(g, "power", 1)
                 power = 1 if power is None else power
                 ops[k] = OP_DIAG1
                 m[0], m[1] = 1.0, 0.0
-                m[2], m[3] = _cis(math.pi * float(power))
+                m[2], m[3] = _cis(math.pi * _num(power, name))
             elif uname == "RZ":
-                t = float(g.parameter) / 2.0
+                t = _num(g.parameter, name) / 2.0
                 c, s = _cis(t)
                 ops[k] = OP_DIAG1
                 m[0], m[1], m[2], m[3] = c, -s, c, s
             elif uname == "PHASE":
                 ops[k] = OP_DIAG1
                 m[0], m[1] = 1.0, 0.0
-                m[2], m[3] = _cis(float(g.parameter))
+                m[2], m[3] = _cis(_num(g.parameter, name))
             elif uname == "RY":
-                t = float(g.parameter) / 2.0
+                t = _num(g.parameter, name) / 2.0
                 c, s = _cis(t)
                 ops[k] = OP_MAT1
                 m[:] = [c, 0.0, -s, 0.0, s, 0.0, c, 0.0]
             elif uname == "RX":
-                t = float(g.parameter) / 2.0
+                t = _num(g.parameter, name) / 2.0
                 c, s = _cis(t)
                 ops[k] = OP_MAT1
                 m[:] = [c, 0.0, 0.0, -s, 0.0, -s, c, 0.0]
