@@ -77,7 +77,9 @@ typedef struct b2sv_plan_opts {
     int32_t jit;          /* permutation runs: 0 = specialise with NVRTC in the background after first use
                              (default), 1 = never (generic kernel only), 2 = compile synchronously       */
     int32_t reserved;     /* A/B switches: bit 0 = no multiplexor / block fusion, bit 1 = no register phases,
-                             bit 2 = no warp-shuffle low-qubit sweeps, bit 3 = no monomial phases */
+                             bit 2 = no warp-shuffle low-qubit sweeps, bit 3 = no monomial phases, bit 4 = no SWAP frame;
+                             bit 5 = "a permutation sweep follows this call" (the distributed gather): a pending basis
+                             state that has only been through one tile may stay a live window */
 } b2sv_plan_opts;
 
 /* Subspace program (restates Subspace.test_basis / enumerate_basis,

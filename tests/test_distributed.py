@@ -143,7 +143,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, case_name, seed, out_dir, gather=False):
+def _worker(rank, world, port, case_name, seed, out_dir, gather=False, choose=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -158,7 +158,12 @@ def _worker(rank, world, port, case_name, seed, out_dir, gather=False):
             case = load_golden(case_name)
             n, gates, spec = case.n_qubits, case.gates, case.meta["subspace_out"]
             basis = 3
-        sv = ShardedStateVector(n, TorchComm(), NumpyGatherShard if gather else NumpyShard)
+        gq = None
+        if choose:
+            from unitaria_b200.distributed import choose_global_qubits
+
+            gq = choose_global_qubits(gates, n, int(np.log2(world)), spec)
+        sv = ShardedStateVector(n, TorchComm(), NumpyGatherShard if gather else NumpyShard, global_qubits=gq)
         assert sv.gather == gather
         sv.set_basis(basis)
         sv.apply(gates)
@@ -172,9 +177,9 @@ def _worker(rank, world, port, case_name, seed, out_dir, gather=False):
         dist.destroy_process_group()
 
 
-def run_case(tmp_path, world, case_name, seed=0, gather=False):
+def run_case(tmp_path, world, case_name, seed=0, gather=False, choose=False):
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, case_name, seed, str(tmp_path), gather), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, case_name, seed, str(tmp_path), gather, choose), nprocs=world, join=True)
     full = np.concatenate([np.load(tmp_path / f"shard{r}.npy") for r in range(world)])
     meta = np.load(tmp_path / "meta.npy")
     return full, meta
@@ -218,6 +223,34 @@ def test_cfg5_needs_no_swap_with_the_gather_exchange(tmp_path):
     want = np_oracle.simulate_gates(case.gates, case.n_qubits, 3)
     assert np.abs(full - want).max() < 1e-12
     assert meta[1] == 0 and 1 <= meta[3] <= 3, meta
+
+
+@pytest.mark.parametrize("case_name,world", [("cfg5_bits5", 4), ("bpx_L2", 2), ("random_8", 4)])
+def test_chosen_global_qubits(tmp_path, case_name, world):
+    """Initial layout picked by choose_global_qubits (no dense targets, no post-selected ancilla in the rank number):
+    same amplitudes, same norm."""
+    full, meta = run_case(tmp_path, world, case_name, seed=5, gather=True, choose=True)
+    if case_name.startswith("random"):
+        rng = np.random.default_rng(5)
+        n = 8
+        gates = random_circuit(n, 160, rng, max_controls=3).gates
+        basis = int(rng.integers(0, 2 ** (n - 1)))
+        want = np_oracle.simulate_gates(gates, n, basis)
+        members = np_oracle.enumerate_basis(to_spec("0" + "#" * (n - 1)))
+    else:
+        case = load_golden(case_name)
+        want = np_oracle.simulate_gates(case.gates, case.n_qubits, 3)
+        members = np_oracle.enumerate_basis(case.meta["subspace_out"])
+    assert np.abs(full - want).max() < 1e-12
+    assert abs(meta[0] - np.sum(np.abs(want[members]) ** 2)) < 1e-12
+
+
+def test_choose_global_qubits_rules():
+    from unitaria_b200.distributed import choose_global_qubits
+
+    case = load_golden("cfg5_bits5")  # qubits 0-5 state preparation (dense), 6-10 Increment, 11 borrowed ancilla
+    assert choose_global_qubits(case.gates, 12, 2, case.meta["subspace_out"]) == [9, 10]
+    assert choose_global_qubits(case.gates, 12, 2, None) == [10, 11]
 
 
 def test_localise_gate_rules():

@@ -58,7 +58,7 @@ class PlanOpts(ctypes.Structure):
     ]
 
     @classmethod
-    def make(cls, fuse=True, tile_qubits=0, perm_runs=True, timing=False, lookahead=0, plain_tile_io=False, jit="auto", mux=True, tile_io=None, phases=True, low6=True, mono=True):
+    def make(cls, fuse=True, tile_qubits=0, perm_runs=True, timing=False, lookahead=0, plain_tile_io=False, jit="auto", mux=True, tile_io=None, phases=True, low6=True, mono=True, frame=True, tail_window=False):
         o = cls()
         o.fuse = int(bool(fuse))
         o.tile_qubits = int(tile_qubits)
@@ -67,7 +67,14 @@ class PlanOpts(ctypes.Structure):
         o.lookahead = int(lookahead)
         o.tile_io = (1 if plain_tile_io else 0) if tile_io is None else int(tile_io)
         o.jit = {"auto": 0, "off": 1, "sync": 2}[jit]
-        o.reserved = (0 if mux else 1) | (0 if phases else 2) | (0 if low6 else 4) | (0 if mono else 8)
+        o.reserved = (0 if mux else 1) | (0 if phases else 2) | (0 if low6 else 4) | (0 if mono else 8) | (0 if frame else 16) | (32 if tail_window else 0)
+        return o
+
+    def with_tail_window(self):
+        """Copy of these options with the "a permutation sweep follows" promise set."""
+        o = type(self)()
+        ctypes.memmove(ctypes.byref(o), ctypes.byref(self), ctypes.sizeof(self))
+        o.reserved |= 32
         return o
 
 

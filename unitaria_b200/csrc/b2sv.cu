@@ -1069,6 +1069,7 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
     sv->timing_on = timing;
     const int tile_io = opts ? opts->tile_io : 0;
     const int jit_mode = opts ? opts->jit : 0;
+    const bool tail_window = opts && (opts->reserved & 32);
     if (sv->n < 13) cfg.perm_runs = false;
     // same gate list and planner options as last time: reuse the plan and what is already on the device
     uint64_t key = 1469598103934665603ull, key2 = 0;
@@ -1178,8 +1179,9 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
         const bool lazy_init = sv->pending_basis && (seg.cls == SEG_TILE || seg.cls == SEG_LOW6) && seg.common_ctrl == 0;
         // ... and if a permutation sweep comes next, only the tile that owns the index is written at all: the
         // permutation sweep reads that tile and takes zeros for everything else
-        const bool owner_only = lazy_init && s + 1 < plan.segs.size() && plan.segs[s + 1].cls == SEG_PERM && sv->n <= kMaxFixed &&
-                                !std::getenv("B2SV_NO_WINDOW");
+        // (tail_window: the caller promises that a permutation sweep comes next -- the distributed layer's gather)
+        const bool perm_next = s + 1 < plan.segs.size() ? plan.segs[s + 1].cls == SEG_PERM : tail_window;
+        const bool owner_only = lazy_init && perm_next && sv->n <= kMaxFixed && !std::getenv("B2SV_NO_WINDOW");
         if ((sv->pending_basis && !lazy_init) || (sv->window && seg.cls != SEG_PERM)) {
             rc = materialise(sv);
             if (rc) return rc;

@@ -349,6 +349,12 @@ class GpuShard:
         self.sv.close()
 
 
+def _TAIL_WINDOW_OPTS():
+    from .cabi import PlanOpts
+
+    return PlanOpts.make(tail_window=True)
+
+
 def _is_perm_gate(g) -> bool:
     """X / multi-controlled X / (controlled) SWAP with power 1: pure index permutations."""
     name = g.name.upper()
@@ -357,10 +363,39 @@ def _is_perm_gate(g) -> bool:
     return getattr(g, "power", 1) in (1, None)
 
 
-class ShardedStateVector:
-    """A 2^n_qubits-amplitude register over ``comm.size`` ranks (power of two)."""
+def choose_global_qubits(gates, n_qubits: int, n_global: int, subspace_out=None, samples: int = 64) -> list:
+    """Which logical qubits should start in the rank number (the initial relabel costs nothing).
 
-    def __init__(self, n_qubits: int, comm, shard_factory, lookahead: int = 4096):
+    Not the targets of dense gates (those need their qubit local); preferably qubits on which the members of
+    ``subspace_out`` take both values, so that every rank holds its share of the projection (a post-selected
+    ancilla in the rank number leaves half the ranks without a single member); among those the highest."""
+    dense = set()
+    for g in gates:
+        if not _is_perm_gate(g):
+            dense.update(_nd_targets(g))
+    spread = set(range(n_qubits))
+    if subspace_out is not None:
+        from .subspace_prog import SubspaceProgram, spec_member
+
+        prog = subspace_out if isinstance(subspace_out, SubspaceProgram) else SubspaceProgram(subspace_out)
+        rng = np.random.default_rng(0)
+        seen0 = seen1 = 0
+        for r in [0, prog.dimension - 1] + [int(x) for x in rng.integers(0, prog.dimension, size=samples)]:
+            m = spec_member(prog.spec, r)
+            seen1 |= m
+            seen0 |= ~m
+        spread = {q for q in range(prog.total_qubits) if (seen0 >> q) & 1 and (seen1 >> q) & 1}
+    order = [q for q in range(n_qubits - 1, -1, -1) if q not in dense and q in spread]
+    order += [q for q in range(n_qubits - 1, -1, -1) if q not in dense and q not in spread]
+    order += [q for q in range(n_qubits - 1, -1, -1) if q in dense]
+    return sorted(order[:n_global])
+
+
+class ShardedStateVector:
+    """A 2^n_qubits-amplitude register over ``comm.size`` ranks (power of two).  ``global_qubits``: the logical
+    qubits that sit in the rank number in the initial layout (default: the top ones)."""
+
+    def __init__(self, n_qubits: int, comm, shard_factory, lookahead: int = 4096, global_qubits=None):
         g = int(math.log2(comm.size))
         if 1 << g != comm.size:
             raise ValueError("world size must be a power of two")
@@ -369,7 +404,13 @@ class ShardedStateVector:
         self.n = n_qubits
         self.comm = comm
         self.rank = comm.rank
-        self.layout = Layout(n_qubits, g)
+        self.home = Layout(n_qubits, g)
+        if global_qubits is not None:
+            if len(set(global_qubits)) != g or not all(0 <= q < n_qubits for q in global_qubits):
+                raise ValueError(f"need {g} distinct global qubits")
+            for i, q in enumerate(sorted(global_qubits)):
+                self.home.swap_positions(self.home.pos[q], n_qubits - g + i)
+        self.layout = self._home_layout()
         self.shard = shard_factory(n_qubits - g)
         self.lookahead = lookahead
         # fused gather exchange when the backend can map its peers' shards; else pack / send-recv / unpack
@@ -378,12 +419,20 @@ class ShardedStateVector:
         self.stats = {"swaps": 0, "swap_bytes": 0, "swap_s": 0.0, "flushes": 0, "local_gates": 0, "dist_sweeps": 0, "dist_gates": 0}
         self._programs: dict = {}
 
+    def _home_layout(self) -> Layout:
+        lay = Layout(self.n, self.home.g)
+        lay.pos, lay.at = list(self.home.pos), list(self.home.at)
+        return lay
+
     # -- state ----------------------------------------------------------------------------------
     def set_basis(self, index: int) -> None:
-        """|index> of the LOGICAL register (identity layout is restored first)."""
-        self.layout = Layout(self.n, self.layout.g)
+        """|index> of the LOGICAL register (the initial layout is restored first)."""
+        self.layout = self._home_layout()
         nl = self.layout.n_local
-        owner, local = index >> nl, index & ((1 << nl) - 1)
+        physical = 0
+        for q in range(self.n):
+            physical |= ((index >> q) & 1) << self.layout.pos[q]
+        owner, local = physical >> nl, physical & ((1 << nl) - 1)
         if owner == self.rank:
             self.shard.set_basis(local)
         else:
@@ -405,9 +454,13 @@ class ShardedStateVector:
                 self._programs.clear()
             hit = self._programs[key] = (gates, program, final)
         _g, program, final = hit
-        for step in program:
+        for k, step in enumerate(program):
             if step[0] == "local":
-                self.shard.apply_prepared(step[1], opts) if hasattr(self.shard, "apply_prepared") else self.shard.apply(step[2], opts)
+                # a gather follows: a basis state that has only been through one tile may stay a live window
+                o = opts
+                if k + 1 < len(program) and program[k + 1][0] == "dist":
+                    o = opts.with_tail_window() if opts is not None else _TAIL_WINDOW_OPTS()
+                self.shard.apply_prepared(step[1], o) if hasattr(self.shard, "apply_prepared") else self.shard.apply(step[2], o)
                 self.stats["flushes"] += 1
                 self.stats["local_gates"] += step[3]
             else:
@@ -787,7 +840,7 @@ def _family_single_gpu(case1, dtype, device, jit):
         out.update({"gates_live": int(live), "ms_per_step": ms / steps, "value": live * steps / (ms * 1e-3)})
         dense_ms = 0.0
         for k in range(steps + 1):
-            sv.fill_random(seed=k, support_bits=n1 - 1)
+            sv.fill_random(seed=k, support_bits=n1)
             sv.mark(2)
             sv.apply_lowered(low, opts)
             sv.project_norm2(prog)
@@ -814,7 +867,8 @@ def _bench_parity(comm, dtype, device, exchange, jit, golden_dir):
         cols, dim_out = load_columns(os.path.join(golden_dir, name + ".cols.npz"))
         prog = SubspaceProgram(case.meta["subspace_out"])
         norm = case.meta["normalization"]
-        sv = ShardedStateVector(max(1, case.n_qubits), comm, make_gpu_shard_factory(dtype, device, exchange))
+        gq = choose_global_qubits(case.gates, max(1, case.n_qubits), int(math.log2(comm.size)), case.meta["subspace_out"])
+        sv = ShardedStateVector(max(1, case.n_qubits), comm, make_gpu_shard_factory(dtype, device, exchange), global_qubits=gq)
         err_case = 0.0
         members = None
         if comm.rank == 0:
@@ -876,7 +930,9 @@ def bench_main(args, case, config_dict, cpu_sample, ClockSampler, measured_peak)
     if rank == 0 and getattr(args, "family_n1", None) is not None:
         family_n1 = _family_single_gpu(args.family_n1, dtype, local_rank, args.jit)
     comm.barrier()
-    sv = ShardedStateVector(n, comm, make_gpu_shard_factory(dtype, local_rank, args.exchange))
+    live = [g for g in case.gates if g.name.upper() != "I"]
+    global_qubits = choose_global_qubits(live, n, int(math.log2(world)), case.meta["subspace_out"])
+    sv = ShardedStateVector(n, comm, make_gpu_shard_factory(dtype, local_rank, args.exchange), global_qubits=global_qubits)
     exchange = (
         "fused gather: peers' shards mapped with CUDA IPC, one b2sv_perm_dist kernel per exchange (index map + all-to-all over NVLink + write-out), "
         "stream-ordered by interprocess events, gloo control plane"
@@ -889,7 +945,6 @@ def bench_main(args, case, config_dict, cpu_sample, ClockSampler, measured_peak)
     rng = np.random.default_rng(0)
     dim_in = SubspaceProgram(case.meta["subspace_in"]).dimension
     inputs = [int(i) for i in rng.integers(0, min(dim_in, 1 << 20), size=args.steps + args.warmup)]
-    live = [g for g in case.gates if g.name.upper() != "I"]
     nl = sv.layout.n_local
     esv = sv.shard.sv
 
@@ -899,8 +954,8 @@ def bench_main(args, case, config_dict, cpu_sample, ClockSampler, measured_peak)
         return abs(norm) * math.sqrt(sv.project_norm2(prog))
 
     def dense_step(k, timed):
-        sv.layout = Layout(n, sv.layout.g)
-        esv.fill_random(seed=100 + k, support_bits=n - 1, index_base=rank << nl)
+        sv.layout = sv._home_layout()
+        esv.fill_random(seed=100 + k, support_bits=n, index_base=rank << nl)
         if timed:
             esv.mark(2)
         sv.apply(live, opts)
@@ -1019,6 +1074,7 @@ def bench_main(args, case, config_dict, cpu_sample, ClockSampler, measured_peak)
             },
             "exchange": {
                 "path": exchange,
+                "global_qubits": global_qubits,
                 "dist_sweeps_per_step": run_stats["dist_sweeps"] / args.steps,
                 "qubit_swaps_per_step": run_stats["swaps"] / args.steps,
                 "probe": probe,
