@@ -661,7 +661,62 @@ cudaKernel_t jit_lookup(b2sv* sv, const std::vector<PGate>& gates, int jit_mode,
     return it->second.second;
 }
 
+// Device copy of a permutation run as DistGate records (interpreter / scatter kernels).
+int upload_dist_gates(b2sv* sv, const std::vector<PGate>& pg) {
+    std::vector<DistGate> dg(pg.size());
+    for (size_t j = 0; j < pg.size(); ++j) {
+        std::memset(&dg[j], 0, sizeof(DistGate));
+        dg[j].ctrl = pg[j].ctrl;
+        dg[j].op = pg[j].op;
+        dg[j].t0 = pg[j].t0;
+        dg[j].t1 = pg[j].t1;
+    }
+    const size_t bytes = (dg.size() + 1) * sizeof(DistGate);
+    if (bytes > sv->d_dist_gates_cap) {
+        CU(cudaStreamSynchronize(sv->stream));
+        cudaFree(sv->d_dist_gates);
+        sv->d_dist_gates = nullptr;
+        sv->d_dist_gates_cap = 0;
+        CU(cudaMalloc(&sv->d_dist_gates, bytes * 2));
+        sv->d_dist_gates_cap = bytes * 2;
+    }
+    if (!dg.empty()) {
+        CU(cudaMemcpyAsync(sv->d_dist_gates, dg.data(), dg.size() * sizeof(DistGate), cudaMemcpyHostToDevice, sv->stream));
+        CU(cudaStreamSynchronize(sv->stream));  // dg is pageable host memory that dies with this frame
+    }
+    return B2SV_OK;
+}
+
+constexpr int kScatterMaxBits = 16;  // window sources up to 2^16 amplitudes are scattered, larger ones gathered
+
 int launch_perm(b2sv* sv, const Plan& plan, const Segment& seg, bool timing, int jit_mode) {
+    // a small live window as the source: zero-fill the output at write bandwidth and scatter the window forward
+    if (sv->window && popcount64(~sv->win_mask & low_mask(sv->n)) <= kScatterMaxBits && !std::getenv("B2SV_NO_SCATTER")) {
+        std::vector<PGate> gates;
+        gates.reserve(seg.gates.size());
+        for (int gi : seg.gates) gates.push_back(plan.gates[gi]);
+        if (int rc = upload_dist_gates(sv, gates)) return rc;
+        DistPermArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.src[0] = sv->amps;
+        a.wmask[0] = sv->win_mask;
+        a.wval[0] = sv->win_value;
+        a.out = sv->scratch;
+        const uint64_t cnt = 1ull << popcount64(~sv->win_mask & low_mask(sv->n));
+        int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
+            using A = std::remove_pointer_t<decltype(tag)>;
+            LaunchTimer lt(sv, timing, jit_mode == 1 ? CLS_PERM : CLS_PERM_JIT, 1.0 * sv->amp_bytes * (double)sv->count);
+            CU(cudaMemsetAsync(sv->scratch, 0, sv->count * sv->amp_bytes, sv->stream));
+            k_perm_scatter<A><<<dim3((unsigned)((cnt + kThreads - 1) / kThreads), 1), kThreads, 0, sv->stream>>>(a, (const DistGate*)sv->d_dist_gates,
+                                                                                                          (int)gates.size(), sv->n);
+            return B2SV_OK;
+        });
+        if (rc) return rc;
+        CU(cudaGetLastError());
+        sv->window = false;
+        std::swap(sv->amps, sv->scratch);
+        return B2SV_OK;
+    }
     // long runs on big registers: straight-line register code from NVRTC once it is ready
     if (jit_mode == 2 || (seg.gates.size() >= 64 && sv->n >= 20)) {
         std::vector<PGate> gates;
@@ -1757,43 +1812,46 @@ int b2sv_dist_perm(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, int n_tot
     // in b2sv_dist_ready -- the caller's host-side exchange of the state words guarantees they have been recorded
     for (int r = 0; r < sv->dist_world; ++r)
         if (r != sv->dist_rank) CU(cudaStreamWaitEvent(sv->stream, sv->peers[r].ready, 0));
+    // every source shard is a small live window (or holds nothing at all): zero-fill + forward scatter (k_perm_scatter)
+    bool scatter = !std::getenv("B2SV_NO_SCATTER");
+    uint64_t scatter_max = 0;
+    for (int r = 0; r < sv->dist_world && scatter; ++r) {
+        if ((a.wval[r] & ~a.wmask[r]) != 0) continue;  // empty window
+        const int bits = popcount64(~a.wmask[r] & low_mask(sv->n));
+        scatter = bits <= kScatterMaxBits;
+        scatter_max = std::max<uint64_t>(scatter_max, 1ull << bits);
+    }
     cudaKernel_t k = nullptr;
-    if (sv->n >= 13 && jit_mode != 1) k = jit_lookup(sv, pg, 2, g);
-    if (k) {
+    if (scatter) {
+        if (int rc = upload_dist_gates(sv, pg)) return rc;
+        int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
+            using A = std::remove_pointer_t<decltype(tag)>;
+            LaunchTimer lt(sv, timing, CLS_DIST, 1.0 * sv->amp_bytes * (double)sv->count);
+            CU(cudaMemsetAsync(a.out, 0, sv->count * sv->amp_bytes, sv->stream));
+            if (scatter_max)
+                k_perm_scatter<A><<<dim3((unsigned)((scatter_max + kThreads - 1) / kThreads), (unsigned)sv->dist_world), kThreads, 0, sv->stream>>>(
+                    a, (const DistGate*)sv->d_dist_gates, (int)pg.size(), sv->n);
+            return B2SV_OK;
+        });
+        if (rc) return rc;
+        CU(cudaGetLastError());
+    } else if (sv->n >= 13 && jit_mode != 1 && (k = jit_lookup(sv, pg, 2, g)) != nullptr) {
         void* args[] = {(void*)&a};
         const uint64_t blocks = sv->count / (uint64_t)(kPermThreads * 32);
         LaunchTimer lt(sv, timing, CLS_DIST, 2.0 * sv->amp_bytes * (double)sv->count);
         CU(cudaLaunchKernel((const void*)k, dim3((unsigned)blocks), dim3(kPermThreads), args, 0, sv->stream));
     } else {
         // interpreter: shards too small for the bit-sliced layout, or no NVRTC
-        std::vector<DistGate> dg(pg.size());
-        for (size_t j = 0; j < pg.size(); ++j) {
-            std::memset(&dg[j], 0, sizeof(DistGate));
-            dg[j].ctrl = pg[j].ctrl;
-            dg[j].op = pg[j].op;
-            dg[j].t0 = pg[j].t0;
-            dg[j].t1 = pg[j].t1;
-        }
-        const size_t bytes = (dg.size() + 1) * sizeof(DistGate);
-        if (bytes > sv->d_dist_gates_cap) {
-            CU(cudaStreamSynchronize(sv->stream));
-            cudaFree(sv->d_dist_gates);
-            sv->d_dist_gates = nullptr;
-            sv->d_dist_gates_cap = 0;
-            CU(cudaMalloc(&sv->d_dist_gates, bytes * 2));
-            sv->d_dist_gates_cap = bytes * 2;
-        }
-        if (!dg.empty()) CU(cudaMemcpyAsync(sv->d_dist_gates, dg.data(), dg.size() * sizeof(DistGate), cudaMemcpyHostToDevice, sv->stream));
+        if (int rc = upload_dist_gates(sv, pg)) return rc;
         int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
             using A = std::remove_pointer_t<decltype(tag)>;
             LaunchTimer lt(sv, timing, CLS_DIST, 2.0 * sv->amp_bytes * (double)sv->count);
-            k_dist_perm_generic<A><<<grid_for(sv, sv->count), kThreads, 0, sv->stream>>>(a, (const DistGate*)sv->d_dist_gates, (int)dg.size(), sv->n,
+            k_dist_perm_generic<A><<<grid_for(sv, sv->count), kThreads, 0, sv->stream>>>(a, (const DistGate*)sv->d_dist_gates, (int)pg.size(), sv->n,
                                                                                       sv->count);
             return B2SV_OK;
         });
         if (rc) return rc;
         CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(sv->stream));  // dg is pageable host memory
     }
     sv->amps = a.out;
     sv->scratch = sv->amps == sv->own_buf[0] ? sv->own_buf[1] : sv->own_buf[0];

@@ -351,10 +351,9 @@ inline void fuse_multiplexors(Plan& plan) {
         // with a single entry is just another 2x2 gate
         // measured (profiles/fusion_r1.txt): the table-driven pass only pays for long multiplexor runs
         // (state preparation); short controlled runs are cheaper as plain gates
-        // ... and a multiplexor with one or two index bits is cheaper as its plain gates inside ONE register phase
-        // (target + controls are <= 3 qubits): ncu on config 3's sweep (profiles/ncu_r2_cfg3.txt) had the L1 data
-        // pipe at 97 % from the per-pair table look-ups of a 2-bit multiplexor
-        const bool worth = nonperm && len >= 2 && (C == 0 ? true : (len >= 6 && popcount64(C) >= 3 && separate > 1.8 * scale));
+        // (tried in round 2: leaving 1-2 bit multiplexors as plain gates for a register phase -- config 3's sweep went
+        // from 2.24 ms to 2.7 ms, the per-gate loop of the phase costs more than the table look-ups)
+        const bool worth = nonperm && len >= 2 && (C == 0 ? true : (len >= 6 && separate > 1.8 * scale));
         if (!worth) {
             out.push_back(g);
             ++i;
