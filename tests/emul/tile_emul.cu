@@ -147,10 +147,16 @@ void run_reg_phase(std::vector<cplx>& tile, const TileOp& hdr, const TileOp* ops
         for (int mi = 0; mi < hdr.ph.count; ++mi) {
             const TileOp& op = ops[mi];
             if ((base & op.ext_ctrl) != op.ext_ctrl) continue;
-            const uint32_t lc = op.lctrl;
+            // the kernel reads the host's pre-decoded member fields (tileops.hpp): so does the emulator
+            const uint32_t lco = (uint32_t)op.fixpos, ok = op.nfix;
+            if ((l & lco) != lco) continue;
+            const int rp = (int)((op.fixpos >> 32) & 3u), rq = (int)((op.fixpos >> 34) & 3u);
             auto jbit = [&](uint32_t pos) { return pos == r0 ? 1 : (pos == r1 ? 2 : 4); };
+            if (op.op != B2SV_OP_PHASE && op.tpos != 0xFF && (1 << rp) != jbit(op.tpos)) std::abort();
+            if (op.op == B2SV_OP_SWAP && (1 << rq) != jbit(op.tpos2)) std::abort();
+            if (((op.fixpos >> 36) & 1u) && (op.op != B2SV_OP_MAT1 || op.m[1] != 0.0 || op.m[3] != 0.0 || op.m[5] != 0.0 || op.m[7] != 0.0)) std::abort();
             for (int j = 0; j < 8; ++j) {
-                if ((off[j] & lc) != lc) continue;
+                if (!((ok >> j) & 1u)) continue;
                 switch (op.op) {
                     case B2SV_OP_PHASE:
                         v[j] *= c_of(op.m, 0);

@@ -128,7 +128,11 @@ def test_two_ranks_on_one_gpu_round1_pack_kernels(tmp_path):
 
 def _worlds():
     n = cabi.device_count()
-    return [w for w in (2, 4, 8) if w <= n]
+    worlds = [w for w in (2, 4, 8) if w <= n]
+    only = os.environ.get("B2SV_TEST_WORLDS")  # e.g. "8": keep an 8-GPU lease short
+    if only:
+        worlds = [w for w in worlds if str(w) in only.split(",")]
+    return worlds
 
 
 @pytest.mark.parametrize("case_name,dtype,tol", [("cfg5_bits13", "complex128", 1e-12), ("laplace_n16", "complex128", 1e-12), ("bpx_L4", "complex64", 1e-5)])

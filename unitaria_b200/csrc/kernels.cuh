@@ -573,13 +573,13 @@ __device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, con
         for (int mi = 0; mi < count; ++mi) {
             const TileOp& op = ops[mi];
             if ((base & op.ext_ctrl) != op.ext_ctrl) continue;
-            const uint32_t lc = op.lctrl;
-            if ((l & lc & ~rmask) != (lc & ~rmask)) continue;
-            uint32_t ok = 0xFFu;  // bit j: element j of the group satisfies the controls that lie in R
-            if ((lc >> r0) & 1u) ok &= 0xAAu;
-            if ((lc >> r1) & 1u) ok &= 0xCCu;
-            if ((lc >> r2) & 1u) ok &= 0xF0u;
-            const int rp = op.tpos == r0 ? 0 : (op.tpos == r1 ? 1 : 2);
+            // pre-decoded by the host (tileops.hpp): controls outside R, per-element mask of the controls inside R,
+            // register position of the target(s), real-matrix flag
+            const uint64_t fx = op.fixpos;
+            const uint32_t lco = (uint32_t)fx;
+            if ((l & lco) != lco) continue;
+            const uint32_t ok = op.nfix;  // bit j: element j of the group satisfies the controls that lie in R
+            const int rp = (int)((fx >> 32) & 3u);
             switch (op.op) {
                 case B2SV_OP_X: {
 #define B2SV_F(a, b)                       \
@@ -592,6 +592,18 @@ __device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, con
 #undef B2SV_F
                 } break;
                 case B2SV_OP_MAT1: {
+                    if ((fx >> 36) & 1u) {  // real matrix: two FP64 operations per component instead of four
+                        const double r00 = op.m[0], r01 = op.m[2], r10 = op.m[4], r11 = op.m[6];
+#define B2SV_F(a, b)                                                                  \
+    if ((ok >> a) & 1u) {                                                             \
+        const double2 x_ = v[a], y_ = v[b];                                           \
+        v[a] = make_double2(fma(r01, y_.x, r00 * x_.x), fma(r01, y_.y, r00 * x_.y));  \
+        v[b] = make_double2(fma(r11, y_.x, r10 * x_.x), fma(r11, y_.y, r10 * x_.y));  \
+    }
+                        B2SV_PAIRS(rp, B2SV_F)
+#undef B2SV_F
+                        break;
+                    }
                     const double2 m00 = make_double2(op.m[0], op.m[1]), m01 = make_double2(op.m[2], op.m[3]);
                     const double2 m10 = make_double2(op.m[4], op.m[5]), m11 = make_double2(op.m[6], op.m[7]);
 #define B2SV_F(a, b)                                   \
@@ -621,7 +633,7 @@ __device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, con
                     }
                 } break;
                 case B2SV_OP_SWAP: {
-                    const int rq = op.tpos2 == r0 ? 0 : (op.tpos2 == r1 ? 1 : 2);
+                    const int rq = (int)((fx >> 34) & 3u);
                     const int pair = rp + rq;  // {0,1} -> 1, {0,2} -> 2, {1,2} -> 3
 #define B2SV_S(a, b)                       \
     if ((ok >> a) & 1u) {                  \

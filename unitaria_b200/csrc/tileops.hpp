@@ -389,7 +389,30 @@ inline void append_with_phases(const std::vector<TileOp>& ops, int k, bool enabl
                 h.nfix++;
             }
         out.push_back(h);
-        for (size_t q = i; q < jr; ++q) out.push_back(ops[q]);
+        // Members are pre-decoded for the kernel's inner loop (which runs once per 8-amplitude group: ncu on the BPX
+        // phase-only sweeps showed them instruction-issue bound, ~70 instructions per member per group): the fields
+        // a member does not need inside a phase carry
+        //   nfix          bit j: element j of a group (bit 0/1/2 of j <-> rpos[0/1/2]) satisfies the controls that lie in R
+        //   fixpos 0-31   the tile-local controls outside R (one mask test per group)
+        //   fixpos 32-33  which register position the target is (3: none), 34-35 the same for a SWAP's second target
+        //   fixpos 36     MAT1 with a real matrix (Ry, H, X powers of pi: half the FP64 work)
+        for (size_t q = i; q < jr; ++q) {
+            TileOp m = ops[q];
+            uint32_t ok = 0xFFu;
+            for (int b = 0; b < 3; ++b)
+                if ((m.lctrl >> h.ph.rpos[b]) & 1u) ok &= b == 0 ? 0xAAu : (b == 1 ? 0xCCu : 0xF0u);
+            auto reg_of = [&](uint8_t pos) -> uint64_t {
+                for (int b = 0; b < 3; ++b)
+                    if (h.ph.rpos[b] == pos) return (uint64_t)b;
+                return 3;
+            };
+            const bool has_t = m.op != B2SV_OP_PHASE && m.tpos != 0xFF;
+            const bool real = m.op == B2SV_OP_MAT1 && m.m[1] == 0.0 && m.m[3] == 0.0 && m.m[5] == 0.0 && m.m[7] == 0.0;
+            m.nfix = (uint8_t)ok;
+            m.fixpos = (uint64_t)(m.lctrl & ~R) | ((has_t ? reg_of(m.tpos) : 3ull) << 32) |
+                       ((m.op == B2SV_OP_SWAP ? reg_of(m.tpos2) : 3ull) << 34) | ((real ? 1ull : 0ull) << 36);
+            out.push_back(m);
+        }
         i = jr;
     }
 }
