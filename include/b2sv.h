@@ -161,6 +161,14 @@ int b2sv_project_gather(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int 
 int b2sv_project_gather_async(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
                               double scale_re, double scale_im, void* host_out_c128, uint64_t dim, int slot);
 int b2sv_gather_wait(b2sv_t* sv, int slot);
+/* Device-resident hand-off (chained nodes, fixed-point / Newton loops of
+ * examples/example_amplified_encodings.py:32-63 -- no host array in between): the projected vector stays in a device
+ * buffer of the handle (complex128[dim], valid until the next projection on this handle; the call returns after the
+ * kernel has finished, so any stream may read it), and a state can be loaded from a complex128 device buffer
+ * (2^n amplitudes) of the same GPU. */
+int b2sv_project_gather_device(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
+                               double scale_re, double scale_im, void** dev_out_c128, uint64_t dim);
+int b2sv_upload_device(b2sv_t* sv, const void* dev_amps_c128);
 /* The inverse hand-off: psi := sum_r host_in[r] |basis_r>, i.e. the members of the subspace (ascending
  * index order) take the `dim` amplitudes and every other amplitude is 0.  Replaces the 2^n-element host
  * array BlockEncoding.compute fills and uploads (nodes/block_encoding.py:45-52: full_input[basis] = input):

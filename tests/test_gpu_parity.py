@@ -474,3 +474,30 @@ def test_two_devices_in_one_process():
             sv.upload(psi0)
             sv.apply(case.gates)
             assert np.abs(sv.download() - want).max() < 1e-12, device
+
+
+def test_device_resident_chaining_and_pipelined_columns():
+    """results that stay on the GPU (torch tensor views), a CUDA tensor as the initial state, and
+    the pipelined matrix-case loop of Node.simulate (node.py:381-388) -- same numbers as the host path."""
+    import torch
+
+    case = load_golden("laplace_n8")
+
+    class C:
+        gates = case.gates
+
+    n, norm, spec = case.n_qubits, case.meta["normalization"], case.meta["subspace_out"]
+    inputs = [b for _c, b in golden_inputs(case, limit=9)]
+    host = [adapter.simulate_projected(C, n, spec, norm, b).copy() for b in inputs]
+    cols = adapter.simulate_columns(C, n, spec, norm, inputs)
+    for a, b in zip(host, cols):
+        assert np.array_equal(a, b)
+    recycled = adapter.simulate_columns(C, n, spec, norm, inputs, keep=False)
+    assert np.array_equal(recycled[-1], host[-1]) and np.array_equal(recycled[-2], host[-2])
+    dev = adapter.simulate_projected(C, n, spec, norm, inputs[3], out="device")
+    assert dev.is_cuda and dev.dtype == torch.complex128 and np.array_equal(dev.cpu().numpy(), host[3])
+    # chain: feed a device-resident full state back in (dense initial state that never touches the host)
+    psi0 = random_state(n, np.random.default_rng(3))
+    want = adapter.simulate_projected(C, n, spec, norm, psi0).copy()
+    got = adapter.simulate_projected(C, n, spec, norm, torch.as_tensor(psi0, device="cuda:0"), out="device")
+    assert np.abs(got.cpu().numpy() - want).max() < 1e-14

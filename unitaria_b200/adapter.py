@@ -80,9 +80,15 @@ def _lowered(tq_circuit, n_qubits: int) -> np.ndarray:
     return low
 
 
+def _is_device_tensor(x) -> bool:
+    return type(x).__module__.startswith("torch") and getattr(x, "is_cuda", False)
+
+
 def _run(tq_circuit, n_qubits: int, input) -> StateVector:
     sv = _state(n_qubits)
-    if isinstance(input, np.ndarray):
+    if _is_device_tensor(input):  # device-resident initial state
+        sv.upload_device(input)
+    elif isinstance(input, np.ndarray):
         if input.size != sv.size:
             raise ValueError(f"input has {input.size} amplitudes, circuit register has {sv.size}")
         sv.upload(input)
@@ -106,14 +112,28 @@ def simulate_circuit(tq_circuit, n_qubits: int, input=0, **kwargs) -> np.ndarray
     return _run(tq_circuit, n_qubits, input).download()
 
 
-def simulate_projected(tq_circuit, n_qubits: int, subspace_out, normalization, input=0) -> np.ndarray:
+def simulate_projected(tq_circuit, n_qubits: int, subspace_out, normalization, input=0, out: str = "host"):
     """``normalization * subspace_out.project(circuit.simulate(input))`` (node.py:378-379), with the
-    projection gathered on the device so only ``dimension_out`` amplitudes cross PCIe."""
+    projection gathered on the device so only ``dimension_out`` amplitudes cross PCIe.
+
+    ``out="device"``: nothing crosses PCIe -- the result is a torch complex128 CUDA tensor viewing the engine's result
+    buffer (valid until the next projection; ``.clone()`` to keep), and ``input`` may itself be a CUDA tensor, so
+    chained nodes and fixed-point / Newton loops (examples/example_amplified_encodings.py:32-63) stay on the GPU."""
     prog = subspace_out if isinstance(subspace_out, SubspaceProgram) else SubspaceProgram(subspace_out)
     if not touches_any_qubit(tq_circuit.gates):
+        if _is_device_tensor(input):
+            input = input.cpu().numpy()
         wavefunction = simulate_circuit(tq_circuit, n_qubits, input)
-        return normalization * _host_project(prog, wavefunction)
-    return _run(tq_circuit, n_qubits, input).project(prog, scale=normalization)
+        result = normalization * _host_project(prog, wavefunction)
+        if out == "device":
+            import torch
+
+            return torch.as_tensor(result, device=f"cuda:{_DEFAULTS['device']}")
+        return result
+    sv = _run(tq_circuit, n_qubits, input)
+    if out == "device":
+        return sv.project_device(prog, scale=normalization)
+    return sv.project(prog, scale=normalization)
 
 
 def simulate_columns(tq_circuit, n_qubits: int, subspace_out, normalization, inputs, keep: bool = True) -> list:

@@ -136,6 +136,11 @@ SYMBOLS = {
         [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, _P, ctypes.c_uint64, ctypes.c_int],
     ),
     "b2sv_gather_wait": (ctypes.c_int, [_P, ctypes.c_int]),
+    "b2sv_project_gather_device": (
+        ctypes.c_int,
+        [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.POINTER(_P), ctypes.c_uint64],
+    ),
+    "b2sv_upload_device": (ctypes.c_int, [_P, _P]),
     "b2sv_embed": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, ctypes.c_uint64]),
     "b2sv_enumerate_basis": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, ctypes.c_uint64]),
     "b2sv_device_ptr": (ctypes.c_int, [_P, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_uint64)]),

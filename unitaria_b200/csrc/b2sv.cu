@@ -1439,6 +1439,62 @@ int b2sv_gather_wait(b2sv_t* sv, int slot) {
     return B2SV_OK;
 }
 
+int b2sv_project_gather_device(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
+                               double scale_re, double scale_im, void** dev_out, uint64_t dim) {
+    if (int rc = check(sv)) return rc;
+    if (!dev_out) return fail(B2SV_EINVAL, "dev_out is null");
+    *dev_out = nullptr;
+    CU(cudaSetDevice(sv->device));
+    if (int rc = materialise(sv)) return rc;
+    int count_bits = 0;
+    uint64_t head_zeros = 0;
+    if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits, -1, nullptr, &head_zeros)) return rc;
+    if (int rc = ensure_gather(sv, (dim ? dim : 1) * 16)) return rc;
+    double2* d_out = (double2*)sv->d_gather;
+    *dev_out = d_out;
+    if (dim == 0) return B2SV_OK;
+    const bool grouped = head_zeros == 0 && low_free_bits(prog, entry) >= kProjectGroupBits && (1ull << count_bits) >= (uint64_t)kProjectWarpSpan;
+    ExpandArgs scan{};
+    if (!grouped) fill_expand(scan, head_zeros);
+    const uint64_t cnt = 1ull << (count_bits - scan.m);
+    CU(cudaMemsetAsync(d_out, 0, dim * 16, sv->stream));
+    const double2 s = make_double2(scale_re * sv->sre - scale_im * sv->sim, scale_re * sv->sim + scale_im * sv->sre);
+    dispatch_dtype(sv, [&](auto* tag) -> int {
+        using A = std::remove_pointer_t<decltype(tag)>;
+        LaunchTimer lt(sv, sv->timing_on, CLS_PROJECT, (double)sv->amp_bytes * std::min((double)cnt, (double)dim) + 16.0 * (double)dim);
+        if (grouped)
+            k_project_gather<A, true><<<grid_for(sv, cnt >> kProjectGroupBits), kThreads, 0, sv->stream>>>(
+                (const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, s, d_out, dim, prog[entry].weight, scan);
+        else
+            k_project_gather<A, false><<<grid_for(sv, cnt), kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1,
+                                                                                     s, d_out, dim, 0, scan);
+        return B2SV_OK;
+    });
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(sv->stream));  // the caller reads the buffer from its own stream
+    return B2SV_OK;
+}
+
+int b2sv_upload_device(b2sv_t* sv, const void* dev_amps_c128) {
+    if (int rc = check(sv)) return rc;
+    if (!dev_amps_c128) return fail(B2SV_EINVAL, "device buffer is null");
+    CU(cudaSetDevice(sv->device));
+    sv->sre = 1.0;
+    sv->sim = 0.0;
+    sv->pending_basis = false;
+    sv->window = false;
+    sv->zero = false;
+    if (sv->dtype == B2SV_C128) {
+        CU(cudaMemcpyAsync(sv->amps, dev_amps_c128, sv->count * 16, cudaMemcpyDeviceToDevice, sv->stream));
+    } else {
+        sv->stats.launches_by_class[CLS_INIT]++;
+        k_convert<float2, double2><<<grid_for(sv, sv->count), kThreads, 0, sv->stream>>>((float2*)sv->amps, (const double2*)dev_amps_c128, sv->count);
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(sv->stream));  // the source belongs to the caller's stream
+    return B2SV_OK;
+}
+
 int b2sv_embed(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits, const void* host_in,
                uint64_t dim) {
     if (int rc = check(sv)) return rc;

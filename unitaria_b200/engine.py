@@ -106,6 +106,14 @@ def random_state_hash(n_qubits: int, seed: int = 0, support_bits: int | None = N
     return out
 
 
+class _DeviceArray:
+    """``__cuda_array_interface__`` view of a device buffer owned by a StateVector (tensor hand-off only)."""
+
+    def __init__(self, ptr: int, count: int, owner):
+        self.owner = owner  # keeps the handle (and with it the buffer) alive
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<c16", "data": (ptr, False), "version": 2, "strides": None}
+
+
 class StateVector:
     """``2**n_qubits`` amplitudes on one B200, LSB order (index bit q = qubit q).
 
@@ -241,6 +249,34 @@ class StateVector:
             )
         )
         return out
+
+    def project_device(self, subspace, scale: complex = 1.0):
+        """:meth:`project` with the result left on the GPU: a torch complex128 tensor VIEWING the handle's result
+        buffer (valid until the next projection on this handle -- ``.clone()`` it to keep it)."""
+        import torch
+
+        p = self._program(subspace)
+        ptr = ctypes.c_void_p()
+        s = complex(scale)
+        cabi.check(
+            self._lib.b2sv_project_gather_device(
+                self._h, p.instrs.ctypes.data, len(p.instrs), p.entry, p.total_qubits, s.real, s.imag, ctypes.byref(ptr), p.dimension
+            )
+        )
+        if p.dimension == 0:
+            return torch.empty(0, dtype=torch.complex128, device=f"cuda:{self.device}")
+        view = _DeviceArray(int(ptr.value), p.dimension, self)
+        return torch.as_tensor(view, device=f"cuda:{self.device}")
+
+    def upload_device(self, tensor) -> None:
+        """Load the state from a torch CUDA tensor (complex128, 2^n amplitudes, same GPU): no host round trip."""
+        import torch
+
+        t = tensor.contiguous().reshape(-1)
+        if t.dtype != torch.complex128 or t.numel() != self.size or not t.is_cuda or t.device.index != self.device:
+            raise ValueError(f"expected a complex128 CUDA tensor with {self.size} amplitudes on cuda:{self.device}")
+        torch.cuda.current_stream(t.device).synchronize()
+        cabi.check(self._lib.b2sv_upload_device(self._h, ctypes.c_void_p(t.data_ptr())))
 
     def project_async(self, subspace, scale: complex, out: np.ndarray, slot: int) -> None:
         """:meth:`project` without waiting: the result lands in ``out`` once :meth:`gather_wait` (same slot) returns."""
