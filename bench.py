@@ -203,6 +203,9 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import c_oracle
+
+    c_oracle.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; this arm is the box's host cores
     case = load_workload(args.workload or workload_for(args.gpus))
     # the whole arm stays under ~2 minutes whatever N is: at N > 1 (32-34 qubit registers) the sample runs on 30 qubits
     per_step_budget = max(1.5, min(20.0, 100.0 / max(1, args.steps + args.warmup)))

@@ -22,7 +22,9 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    if force or not os.path.exists(_LIB_PATH):
+    src = os.path.join(_HERE, "sv_oracle.c")
+    stale = not os.path.exists(_LIB_PATH) or os.path.getmtime(src) > os.path.getmtime(_LIB_PATH)
+    if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _LIB_PATH
 
@@ -67,6 +69,11 @@ def encode_gates(gates) -> np.ndarray:
 
 def max_threads() -> int:
     return int(lib().orc_max_threads())
+
+
+def set_threads(n: int) -> None:
+    """Use ``n`` OpenMP threads (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    lib().orc_set_threads(int(n))
 
 
 def apply_encoded(psi: np.ndarray, n: int, enc: np.ndarray) -> None:

@@ -37,6 +37,11 @@ typedef struct {
     double param;        /* angle, or power for X/Y/Z/H */
 } orc_gate;
 
+/* bench.py --impl reference runs under torchrun, which exports OMP_NUM_THREADS=1: the CPU arm asks for the box's cores */
+void orc_set_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

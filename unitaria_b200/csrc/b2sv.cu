@@ -1892,8 +1892,9 @@ int b2sv_dist_perm(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, int n_tot
         if (rc) return rc;
         CU(cudaGetLastError());
     } else if (sv->n >= 13 && jit_mode != 1 && (k = jit_lookup(sv, pg, 2, g)) != nullptr) {
-        void* args[] = {(void*)&a};
         const uint64_t blocks = sv->count / (uint64_t)(kPermThreads * 32);
+        a.block_rot = (unsigned)((blocks / (uint64_t)sv->dist_world) * (uint64_t)sv->dist_rank);
+        void* args[] = {(void*)&a};
         LaunchTimer lt(sv, timing, CLS_DIST, 2.0 * sv->amp_bytes * (double)sv->count);
         CU(cudaLaunchKernel((const void*)k, dim3((unsigned)blocks), dim3(kPermThreads), args, 0, sv->stream));
     } else {

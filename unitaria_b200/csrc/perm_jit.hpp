@@ -123,10 +123,11 @@ inline std::string perm_dist_source(const std::vector<PGate>& exec_order, int nl
     const int n = nl + g;
     s += dtype == B2SV_C64 ? "typedef float2 amp_t;\n" : "typedef double2 amp_t;\n";
     s += "struct DistPermArgs { const amp_t* src[16]; unsigned long long wmask[16], wval[16]; double sre[16], sim[16]; amp_t* out; "
-         "unsigned rank_logical; unsigned flip_in; int has_scale; int pad; };\n";
+         "unsigned rank_logical; unsigned flip_in; int has_scale; unsigned block_rot; };\n";
     s += "extern \"C\" __global__ void __launch_bounds__(256) b2sv_perm_dist(const __grid_constant__ DistPermArgs a) {\n";
     s += "  const unsigned tid = threadIdx.x, lane = tid & 31u;\n";
-    s += "  const unsigned long long wg = ((unsigned long long)blockIdx.x * blockDim.x + tid) >> 5;\n";
+    s += "  unsigned blk = blockIdx.x + a.block_rot; if (blk >= gridDim.x) blk -= gridDim.x;\n";
+    s += "  const unsigned long long wg = ((unsigned long long)blk * blockDim.x + tid) >> 5;\n";
     s += "  const unsigned long long warp_base = wg << 10;\n";
     static const char* pat[5] = {"0xAAAAAAAAu", "0xCCCCCCCCu", "0xF0F0F0F0u", "0xFF00FF00u", "0xFFFF0000u"};
     for (int q = 0; q < n; ++q) {
