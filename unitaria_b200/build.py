@@ -45,7 +45,19 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > lib_mtime for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+DBG_LIB_PATH = os.path.join(_HERE, "libunitaria_b200_dbg.so")
+
+
+def build(force: bool = False, verbose: bool = False, bounds: bool = False) -> str:
+    """``bounds``: the range-checking debug build (-DB2SV_BOUNDS_CHECK -> libunitaria_b200_dbg.so; load it with
+    B2SV_LIB=<path>), the stand-in for compute-sanitizer's memcheck on pools where the tool is closed."""
+    if bounds:
+        cmd = [find_nvcc()] + NVCC_FLAGS + ["-DB2SV_BOUNDS_CHECK", "-o", DBG_LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            sys.stderr.write(proc.stdout + proc.stderr)
+            raise RuntimeError("nvcc failed building libunitaria_b200_dbg.so")
+        return DBG_LIB_PATH
     if not force and not needs_build():
         return LIB_PATH
     cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
@@ -59,4 +71,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, bounds="--bounds" in sys.argv))

@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libunitaria_b200.so")
+# B2SV_LIB: load another build of the same ABI (the range-checking debug build, unitaria_b200.build --bounds)
+LIB_PATH = os.environ.get("B2SV_LIB") or os.path.join(_HERE, "libunitaria_b200.so")
 
 B2SV_C128, B2SV_C64 = 0, 1
 OP_MAT1, OP_DIAG1, OP_X, OP_SWAP, OP_PHASE = 0, 1, 2, 3, 4

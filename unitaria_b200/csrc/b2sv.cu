@@ -334,6 +334,7 @@ int launch_gate1(b2sv* sv, const PGate& g, bool timing) {
     if (popcount64(fixed) > kMaxFixed) return fail(B2SV_EINVAL, "gate touches more than %d qubits", kMaxFixed);
     fill_expand(a.ex, fixed);
     a.count = 1ull << (sv->n - a.ex.m);
+    a.total = sv->count;
     std::memcpy(a.m, g.m, sizeof(a.m));
     return dispatch_dtype(sv, [&](auto* tag) -> int {
         using A = std::remove_pointer_t<decltype(tag)>;

@@ -14,6 +14,26 @@
 
 #include "../../include/b2sv.h"
 
+// -DB2SV_BOUNDS_CHECK (python -m unitaria_b200.build --bounds -> libunitaria_b200_dbg.so): every shared-memory tile access
+// and the global accesses whose index is computed from gate data are range-checked on the device and trap with a message.
+// compute-sanitizer is closed on the B200 pool this engine is developed on (profiles/sanitizer_r2.txt); this build plus
+// the oracle comparison of scripts/sanitize_cases.py is the memcheck stand-in.
+#ifdef B2SV_BOUNDS_CHECK
+#include <cstdio>
+#define B2SV_CHECK(cond)                                                                      \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            printf("b2sv bounds check failed: %s (kernels.cuh:%d, block %d thread %d)\n", #cond, __LINE__, (int)blockIdx.x, \
+                   (int)threadIdx.x);                                                         \
+            __trap();                                                                         \
+        }                                                                                     \
+    } while (0)
+#else
+#define B2SV_CHECK(cond) \
+    do {                 \
+    } while (0)
+#endif
+
 namespace b2svk {
 
 constexpr int kMaxFixed = 40;
@@ -65,6 +85,7 @@ struct Gate1Args {
     uint64_t ctrl;      // OR-ed into every expanded index
     uint64_t bit0, bit1;
     uint64_t count;     // number of (pairs of) amplitudes to visit
+    uint64_t total;     // amplitudes of the register (range checks)
     int op;
     double m[8];
 };
@@ -74,6 +95,7 @@ __global__ void __launch_bounds__(kThreads) k_gate1(A* __restrict__ psi, const G
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a.count; k += stride) {
         const uint64_t i0 = expand_bits(k, a.ex) | a.ctrl;
+        B2SV_CHECK((i0 | a.bit0 | a.bit1) < a.total);
         switch (a.op) {
             case B2SV_OP_X: {
                 const uint64_t i1 = i0 | a.bit0;
@@ -242,7 +264,9 @@ constexpr int kTileMaxOps = 112;  // ops of one sweep are staged in shared memor
 template <typename A, bool SWZ>
 struct TileView {
     A* p;
+    uint32_t n;  // elements of the tile (range checks of the -DB2SV_BOUNDS_CHECK build)
     __device__ __forceinline__ A& operator[](uint32_t l) const {
+        B2SV_CHECK(l < n);
         if (SWZ) {
             if (sizeof(A) == 16) l ^= (l >> 3) & 7u;
             else l ^= ((l >> 4) & 7u) << 1;
@@ -871,7 +895,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile(A* __restrict__ psi, const
     // a generated (lazy-init) tile that does not hold the basis index is all zeros: every gate maps it to
     // itself, so only the one tile that owns the index runs the gates -- the others just write zeros
     const int n_ops_here = (load || (a.init_index & ~a.tile_mask) == base) ? a.n_ops : 0;
-    tile_run_batches<A, FUSED>(TileView<A, false>{tile}, s_ops, a.ops, n_ops_here, k, base, a.tables, nullptr);
+    tile_run_batches<A, FUSED>(TileView<A, false>{tile, 1u << k}, s_ops, a.ops, n_ops_here, k, base, a.tables, nullptr);
 
     if (BULK) {
         // generic-proxy writes to shared memory must be visible to the async proxy before the copy out
@@ -919,7 +943,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile_swz(const __grid_constant_
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const TileArgs& a = args.t;
     A* tile_raw = reinterpret_cast<A*>(smem_raw);
-    const TileView<A, true> tile{tile_raw};
+    const TileView<A, true> tile{tile_raw, 1u << args.t.k};
     const int k = a.k, lc = a.lc;
     TileOp* s_ops = reinterpret_cast<TileOp*>(smem_raw + ((size_t)sizeof(A) << k));
     // the mbarrier lives in dynamic shared memory too: static shared memory would push the 1 KiB-aligned
@@ -1280,8 +1304,10 @@ __global__ void __launch_bounds__(kPermThreads) k_perm(const A* __restrict__ in,
         // (a basis state that has only been through one tile so far) and is not even materialised there
         A v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < 8; ++u) {
+            B2SV_CHECK(src[u] < (1ull << n));
             v[u] = ((src[u] & win_mask) == win_value) ? in[src[u]] : from_c128<A>(make_double2(0.0, 0.0));
+        }
 #pragma unroll
         for (int u = 0; u < 8; ++u) out[warp_base + (uint64_t)(b0 + u) * 32 + lane] = v[u];
     }
@@ -1332,6 +1358,7 @@ __global__ void __launch_bounds__(kThreads) k_dist_perm_generic(const __grid_con
             }
         }
         const unsigned r = (unsigned)(idx >> nl) ^ a.flip_in;
+        B2SV_CHECK(r < (unsigned)kDistMaxRanks && a.src[r] != nullptr);
         const uint64_t s = idx & lmask;
         A v = from_c128<A>(make_double2(0.0, 0.0));
         if ((s & a.wmask[r]) == a.wval[r]) v = reinterpret_cast<const A*>(a.src[r])[s];
@@ -1398,6 +1425,7 @@ __global__ void __launch_bounds__(kThreads) k_perm_scatter(const __grid_constant
             else if (((idx >> g.t0) ^ (idx >> g.t1)) & 1ull) idx ^= (1ull << g.t0) | (1ull << g.t1);
         }
         if ((unsigned)(idx >> nl) != a.rank_logical) continue;  // lands on another rank
+        B2SV_CHECK(src <= lmask);
         A v = in[src];
         if (a.has_scale) v = from_c128<A>(cmul(make_double2(a.sre[r], a.sim[r]), to_c128(v)));
         out[idx & lmask] = v;
