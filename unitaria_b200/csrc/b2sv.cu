@@ -450,8 +450,15 @@ int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, co
             TileArgsSwz as;
             as.map = *map;
             as.t = a;
-            for (const SlotFill& f : slots)  // the sweep's dense-block matrices ride in the kernel parameters
-                std::memcpy(&as.blk.m[(size_t)f.granule * kBlkGranuleElems], &tables[2 * f.mat_off], sizeof(double2) << (2 * f.kb));
+            for (const SlotFill& f : slots) {  // the sweep's dense-block matrices ride in the kernel parameters
+                if (sv->amp_bytes == 16) {
+                    std::memcpy(&as.blk.m[(size_t)f.granule * kBlkGranuleElems], &tables[2 * f.mat_off], sizeof(double2) << (2 * f.kb));
+                } else {  // complex64 sweeps compute in fp32: the same entries, narrowed once here
+                    float2* dst = reinterpret_cast<float2*>(as.blk.m) + (size_t)f.granule * kBlkGranuleElems;
+                    for (int e = 0; e < (1 << (2 * f.kb)); ++e)
+                        dst[e] = make_float2((float)tables[2 * (f.mat_off + e)], (float)tables[2 * (f.mat_off + e) + 1]);
+                }
+            }
             const size_t swz_smem = smem + 16;  // tile + ops + the mbarrier
             return dispatch_dtype(sv, [&](auto* tag) -> int {
                 using A = std::remove_pointer_t<decltype(tag)>;

@@ -75,6 +75,31 @@ __device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {  // a
     return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
 }
 
+// Compute type of the tile sweeps: the storage type itself.  complex64 registers are swept in fp32 arithmetic: the fp64
+// round trip (F2F conversions run at 16 per clock per SM, 4 per amplitude per shared-memory pass) made the complex64
+// sweeps of config 3 conversion-bound at 3.4x their HBM time, and every pass rounds to fp32 when it stores anyway.
+// Matrices are fused and multiplied out in fp64 on the host and rounded once.
+template <typename A>
+struct Num;
+template <>
+struct Num<double2> {
+    using C = double2;
+    using R = double;
+    static __device__ __forceinline__ C mk(double re, double im) { return make_double2(re, im); }
+};
+template <>
+struct Num<float2> {
+    using C = float2;
+    using R = float;
+    static __device__ __forceinline__ C mk(float re, float im) { return make_float2(re, im); }
+};
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cfma(float2 a, float2 b, float2 c) {
+    return make_float2(fmaf(a.x, b.x, fmaf(-a.y, b.y, c.x)), fmaf(a.x, b.y, fmaf(a.y, b.x, c.y)));
+}
+__device__ __forceinline__ float2 narrow(double2 v, float2*) { return make_float2((float)v.x, (float)v.y); }
+__device__ __forceinline__ double2 narrow(double2 v, double2*) { return v; }
+
 // ===================================================================================================
 // 1. Stand-alone multi-controlled gate: visits only the 2^(n-c[-1]) amplitudes selected by the
 //    control bits (the schedule of one qulacs update, but with all controls handled in the index).
@@ -156,6 +181,14 @@ struct __align__(16) TileOp {
             uint8_t nmux;
             uint8_t mpos[7];       // per index bit: tile-local position, or 0xFF when outside the tile
             uint8_t mq[8];         // per index bit: global qubit
+            // enumeration that keeps the table index uniform over long stretches of consecutive pairs: the index bits
+            // that lie inside the tile are enumerated LAST (as the top bits of the pair counter)
+            uint64_t mfixpos;      // fixpos plus the tile-local positions of the index bits (ascending, 4 bits each)
+            uint8_t mnfix;         // entries of mfixpos
+            uint8_t nl;            // index bits inside the tile
+            uint8_t pad_[2];
+            uint32_t lppack;       // nibble i: tile-local position of the i-th inside index bit
+            uint32_t ljpack;       // nibble i: which index bit (j) that is
         } mux;
         struct {               // op == kOpBlock: dense 2^kb x 2^kb matrix on kb <= 3 tile qubits
             uint64_t mat_off;      // first double2 of the row-major matrix in TileArgs::tables
@@ -195,6 +228,13 @@ constexpr int kMonoThreadBits = 8;         // log2(kThreads)
 constexpr int kMonoV = 8, kMonoVFac = 4;   // index walks per thread (pure permutation / with factors)
 constexpr int kMonoMaxEbits = 4;           // table-driven phases: at most 16 slices
 static_assert(sizeof(TileOp) == 96, "TileOp layout");
+// Entry i of a STAGED plain op's m[]: the complex64 kernels narrow the eight doubles to floats in place while staging
+// (tile_narrow_ops), so the sweep itself never converts.
+template <typename A>
+__device__ __forceinline__ typename Num<A>::R mval(const double* m, int i) {
+    if constexpr (sizeof(A) == 16) return m[i];
+    else return reinterpret_cast<const float*>(m)[i];
+}
 
 struct TileArgs {
     ExpandArgs cta_ex;    // tile qubits + the sweep's common outside controls: block index -> tile base
@@ -304,38 +344,49 @@ __device__ __forceinline__ void tile_for_each(uint32_t cnt, uint64_t fixpos, int
 constexpr int kBlkGranules = 16;
 constexpr int kBlkGranuleElems = 16;
 struct BlkSlots {
-    double2 m[kBlkGranules * kBlkGranuleElems];  // 4 KiB
+    double2 m[kBlkGranules * kBlkGranuleElems];  // 4 KiB (complex64 sweeps: the host stores float2 entries, same numbering)
 };
 
-template <bool REAL>
-__device__ __forceinline__ double2 bmul(double2 m, double2 v) {
-    if (REAL) return make_double2(m.x * v.x, m.x * v.y);
+template <bool REAL, typename C>
+__device__ __forceinline__ C bmul(C m, C v) {
+    if (REAL) {
+        C r;
+        r.x = m.x * v.x;
+        r.y = m.x * v.y;
+        return r;
+    }
     return cmul(m, v);
 }
-template <bool REAL>
-__device__ __forceinline__ double2 bfma(double2 m, double2 v, double2 c) {
-    if (REAL) return make_double2(fma(m.x, v.x, c.x), fma(m.x, v.y, c.y));
+template <bool REAL, typename C>
+__device__ __forceinline__ C bfma(C m, C v, C c) {
+    if (REAL) {
+        C r;
+        r.x = fma(m.x, v.x, c.x);
+        r.y = fma(m.x, v.y, c.y);
+        return r;
+    }
     return cfma(m, v, c);
 }
 
 // One dense block pass; U(i) yields entry i of the row-major matrix.
 template <typename A, int KB, bool REAL, typename TV, typename MAT>
 __device__ __forceinline__ void tile_block_pass(TV tile, const TileOp& op, int k, MAT U) {
+    using C = typename Num<A>::C;
     const uint32_t cnt = 1u << (k - op.nfix);
     if (KB == 3) {
         const uint32_t b0 = 1u << op.blk.bpos[0], b1 = 1u << op.blk.bpos[1], b2 = 1u << op.blk.bpos[2];
         tile_for_each<1>(cnt, op.fixpos, op.nfix, op.lctrl, [&](const uint32_t* l, int) {
             uint32_t off[8];
-            double2 v[8];
+            C v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 off[j] = l[0] | ((j & 1) ? b0 : 0u) | ((j & 2) ? b1 : 0u) | ((j & 4) ? b2 : 0u);
-                v[j] = to_c128(tile[off[j]]);
+                v[j] = tile[off[j]];
             }
             // four rows at a time: four independent accumulation chains hide the DFMA latency
 #pragma unroll
             for (int r0 = 0; r0 < 8; r0 += 4) {
-                double2 acc[4];
+                C acc[4];
 #pragma unroll
                 for (int r = 0; r < 4; ++r) acc[r] = bmul<REAL>(U((r0 + r) * 8), v[0]);
 #pragma unroll
@@ -343,18 +394,18 @@ __device__ __forceinline__ void tile_block_pass(TV tile, const TileOp& op, int k
 #pragma unroll
                     for (int r = 0; r < 4; ++r) acc[r] = bfma<REAL>(U((r0 + r) * 8 + c), v[c], acc[r]);
 #pragma unroll
-                for (int r = 0; r < 4; ++r) tile[off[r0 + r]] = from_c128<A>(acc[r]);
+                for (int r = 0; r < 4; ++r) tile[off[r0 + r]] = acc[r];
             }
         });
     } else {  // KB == 2
         const uint32_t b0 = 1u << op.blk.bpos[0], b1 = 1u << op.blk.bpos[1];
         tile_for_each<1>(cnt, op.fixpos, op.nfix, op.lctrl, [&](const uint32_t* l, int) {
             uint32_t off[4];
-            double2 v[4], acc[4];
+            C v[4], acc[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 off[j] = l[0] | ((j & 1) ? b0 : 0u) | ((j & 2) ? b1 : 0u);
-                v[j] = to_c128(tile[off[j]]);
+                v[j] = tile[off[j]];
             }
 #pragma unroll
             for (int r = 0; r < 4; ++r) acc[r] = bmul<REAL>(U(r * 4), v[0]);
@@ -363,14 +414,14 @@ __device__ __forceinline__ void tile_block_pass(TV tile, const TileOp& op, int k
 #pragma unroll
                 for (int r = 0; r < 4; ++r) acc[r] = bfma<REAL>(U(r * 4 + c), v[c], acc[r]);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) tile[off[r]] = from_c128<A>(acc[r]);
+            for (int r = 0; r < 4; ++r) tile[off[r]] = acc[r];
         });
     }
 }
 
 template <typename A, int KB, int G, typename TV>
 __device__ __forceinline__ void tile_block_slot(TV tile, const TileOp& op, int k, const BlkSlots* bs) {
-    auto U = [bs](int i) { return bs->m[G * kBlkGranuleElems + i]; };  // G and i are compile-time: an immediate operand
+    auto U = [bs](int i) { return reinterpret_cast<const typename Num<A>::C*>(bs->m)[G * kBlkGranuleElems + i]; };  // G and i are compile-time: an immediate operand
     if (op.blk.real) tile_block_pass<A, KB, true>(tile, op, k, U);
     else tile_block_pass<A, KB, false>(tile, op, k, U);
 }
@@ -398,7 +449,7 @@ __device__ __forceinline__ void tile_apply_block(TV tile, const TileOp& op, int 
     }
     // no slot left in this launch (or a kernel without the parameter block): the matrix comes through the read-only path
     const double2* __restrict__ Ug = tables + op.blk.mat_off;
-    auto U = [Ug](int i) { return __ldg(Ug + i); };
+    auto U = [Ug](int i) { return narrow(__ldg(Ug + i), (typename Num<A>::C*)nullptr); };
     if (op.blk.kb == 3) {
         if (op.blk.real) tile_block_pass<A, 3, true>(tile, op, k, U);
         else tile_block_pass<A, 3, false>(tile, op, k, U);
@@ -413,6 +464,8 @@ __device__ __forceinline__ void tile_apply_block(TV tile, const TileOp& op, int 
 template <typename A, bool FUSED, typename TV>
 __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, uint64_t base,
                                               const double2* __restrict__ tables, const BlkSlots* bs) {
+    using C = typename Num<A>::C;
+    using N = Num<A>;
     const uint32_t cnt = 1u << (k - op.nfix);
     const uint64_t fixpos = op.fixpos;
     const int nfix = op.nfix;
@@ -456,109 +509,122 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
         } break;
         case B2SV_OP_MAT1: {
             const uint32_t bt = 1u << op.tpos;
-            const double2 m00 = make_double2(op.m[0], op.m[1]), m01 = make_double2(op.m[2], op.m[3]);
-            const double2 m10 = make_double2(op.m[4], op.m[5]), m11 = make_double2(op.m[6], op.m[7]);
+            const C m00 = N::mk(mval<A>(op.m, 0), mval<A>(op.m, 1)), m01 = N::mk(mval<A>(op.m, 2), mval<A>(op.m, 3));
+            const C m10 = N::mk(mval<A>(op.m, 4), mval<A>(op.m, 5)), m11 = N::mk(mval<A>(op.m, 6), mval<A>(op.m, 7));
             tile_for_each<2>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
-                double2 v0[2], v1[2];
+                C v0[2], v1[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u)
                     if (u < m) {
-                        v0[u] = to_c128(tile[l[u]]);
-                        v1[u] = to_c128(tile[l[u] | bt]);
+                        v0[u] = tile[l[u]];
+                        v1[u] = tile[l[u] | bt];
                     }
 #pragma unroll
                 for (int u = 0; u < 2; ++u)
                     if (u < m) {
-                        tile[l[u]] = from_c128<A>(cfma(m01, v1[u], cmul(m00, v0[u])));
-                        tile[l[u] | bt] = from_c128<A>(cfma(m11, v1[u], cmul(m10, v0[u])));
+                        tile[l[u]] = cfma(m01, v1[u], cmul(m00, v0[u]));
+                        tile[l[u] | bt] = cfma(m11, v1[u], cmul(m10, v0[u]));
                     }
             });
         } break;
         case B2SV_OP_DIAG1: {
-            const double2 d0 = make_double2(op.m[0], op.m[1]), d1 = make_double2(op.m[2], op.m[3]);
+            const C d0 = N::mk(mval<A>(op.m, 0), mval<A>(op.m, 1)), d1 = N::mk(mval<A>(op.m, 2), mval<A>(op.m, 3));
             if (op.tpos == 0xFF) {  // target outside the tile: one CTA-uniform factor
-                const double2 d = (base & op.ext_tbit) ? d1 : d0;
-                if (d.x == 1.0 && d.y == 0.0) break;
+                const C d = (base & op.ext_tbit) ? d1 : d0;
+                if (d.x == 1 && d.y == 0) break;
                 tile_for_each<4>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
-                    double2 v[4];
+                    C v[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if (u < m) v[u] = to_c128(tile[l[u]]);
+                        if (u < m) v[u] = tile[l[u]];
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if (u < m) tile[l[u]] = from_c128<A>(cmul(d, v[u]));
+                        if (u < m) tile[l[u]] = cmul(d, v[u]);
                 });
             } else {
                 const uint32_t bt = 1u << op.tpos;
                 tile_for_each<2>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
-                    double2 v0[2], v1[2];
+                    C v0[2], v1[2];
 #pragma unroll
                     for (int u = 0; u < 2; ++u)
                         if (u < m) {
-                            v0[u] = to_c128(tile[l[u]]);
-                            v1[u] = to_c128(tile[l[u] | bt]);
+                            v0[u] = tile[l[u]];
+                            v1[u] = tile[l[u] | bt];
                         }
 #pragma unroll
                     for (int u = 0; u < 2; ++u)
                         if (u < m) {
-                            tile[l[u]] = from_c128<A>(cmul(d0, v0[u]));
-                            tile[l[u] | bt] = from_c128<A>(cmul(d1, v1[u]));
+                            tile[l[u]] = cmul(d0, v0[u]);
+                            tile[l[u] | bt] = cmul(d1, v1[u]);
                         }
                 });
             }
         } break;
         case kOpMux: if constexpr (FUSED) {
-            // one pass over all pairs of the target; the 2x2 matrix of a pair is looked up by the
-            // pair's control bits (tile-local ones per element, outside ones CTA-uniform)
+            // one pass over all pairs of the target; the 2x2 matrix of a pair is looked up by the pair's control bits
+            // (outside the tile: CTA-uniform; inside: the top bits of the pair counter, so a thread -- and for all but
+            // tiny sub-ranges its whole warp -- keeps one matrix in registers over consecutive pairs.  Fetching the
+            // matrix per pair made the complex64 state-preparation sweeps of cfg 3 L1-bound: ncu showed 67 % of the L1
+            // data-pipe wavefronts being table reads and the pipe 97 % busy.)
             const uint32_t bt = 1u << op.tpos;
             const int nmux = op.mux.nmux;
             uint32_t idx_ext = 0;
-            uint8_t lp[7];
-            int nl = 0, ljb[7];
-            for (int j = 0; j < nmux; ++j) {
+            for (int j = 0; j < nmux; ++j)
                 if (op.mux.mpos[j] == 0xFF) idx_ext |= (uint32_t)((base >> op.mux.mq[j]) & 1ull) << j;
-                else {
-                    lp[nl] = op.mux.mpos[j];
-                    ljb[nl] = j;
-                    ++nl;
+            const double2* __restrict__ tab = tables + op.mux.table_off * 4;
+            const int nl = op.mux.nl, mnfix = op.mux.mnfix;
+            const uint64_t mfixpos = op.mux.mfixpos;
+            const uint32_t lppack = op.mux.lppack, ljpack = op.mux.ljpack;
+            const uint32_t fbits = (uint32_t)(k - mnfix);
+            // threads split into nt / T groups of T = min(nt, 2^fbits); a group walks the values of the inside index bits
+            // (outer loop: matrix in registers), its threads the pairs of one value (inner loop)
+            const uint32_t nt = blockDim.x;
+            const uint32_t per = 1u << fbits, T = per < nt ? per : nt;
+            const uint32_t t = threadIdx.x & (T - 1), grp = threadIdx.x / T, ngrp = nt / T;
+            for (uint32_t il = grp; il < (1u << nl); il += ngrp) {
+                uint32_t idx = idx_ext, lbits = 0;
+                for (int i = 0; i < nl; ++i)
+                    if ((il >> i) & 1u) {
+                        idx |= 1u << ((ljpack >> (4 * i)) & 15u);
+                        lbits |= 1u << ((lppack >> (4 * i)) & 15u);
+                    }
+                const double2* M = tab + (size_t)idx * 4;
+                const C m00 = narrow(__ldg(M), (C*)nullptr), m01 = narrow(__ldg(M + 1), (C*)nullptr);
+                const C m10 = narrow(__ldg(M + 2), (C*)nullptr), m11 = narrow(__ldg(M + 3), (C*)nullptr);
+                const uint32_t lfix = lctrl | lbits;
+                uint32_t p = t;
+                for (; p + T < per; p += 2 * T) {  // two independent shared-memory round trips in flight
+                    const uint32_t la = expand_local(p, mfixpos, mnfix) | lfix;
+                    const uint32_t lb = expand_local(p + T, mfixpos, mnfix) | lfix;
+                    const C a0 = tile[la], a1 = tile[la | bt];
+                    const C b0 = tile[lb], b1 = tile[lb | bt];
+                    tile[la] = cfma(m01, a1, cmul(m00, a0));
+                    tile[la | bt] = cfma(m11, a1, cmul(m10, a0));
+                    tile[lb] = cfma(m01, b1, cmul(m00, b0));
+                    tile[lb | bt] = cfma(m11, b1, cmul(m10, b0));
+                }
+                for (; p < per; p += T) {
+                    const uint32_t la = expand_local(p, mfixpos, mnfix) | lfix;
+                    const C a0 = tile[la], a1 = tile[la | bt];
+                    tile[la] = cfma(m01, a1, cmul(m00, a0));
+                    tile[la | bt] = cfma(m11, a1, cmul(m10, a0));
                 }
             }
-            const double2* __restrict__ tab = tables + op.mux.table_off * 4;
-            tile_for_each<2>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
-                double2 v0[2], v1[2];
-                const double2* M[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-                    if (u < m) {
-                        uint32_t idx = idx_ext;
-                        for (int j = 0; j < nl; ++j) idx |= ((l[u] >> lp[j]) & 1u) << ljb[j];
-                        M[u] = tab + (size_t)idx * 4;
-                        v0[u] = to_c128(tile[l[u]]);
-                        v1[u] = to_c128(tile[l[u] | bt]);
-                    }
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-                    if (u < m) {
-                        const double2 m00 = __ldg(M[u]), m01 = __ldg(M[u] + 1), m10 = __ldg(M[u] + 2), m11 = __ldg(M[u] + 3);
-                        tile[l[u]] = from_c128<A>(cfma(m01, v1[u], cmul(m00, v0[u])));
-                        tile[l[u] | bt] = from_c128<A>(cfma(m11, v1[u], cmul(m10, v0[u])));
-                    }
-            });
         } break;
         case kOpBlock: if constexpr (FUSED) {
             // every group of 2^kb amplitudes (block bits free, predicate bits set) is multiplied by one dense matrix
             tile_apply_block<A>(tile, op, k, tables, bs);
         } break;
         default: {  // PHASE
-            const double2 w = make_double2(op.m[0], op.m[1]);
+            const C w = N::mk(mval<A>(op.m, 0), mval<A>(op.m, 1));
             tile_for_each<4>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
-                double2 v[4];
+                C v[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    if (u < m) v[u] = to_c128(tile[l[u]]);
+                    if (u < m) v[u] = tile[l[u]];
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    if (u < m) tile[l[u]] = from_c128<A>(cmul(w, v[u]));
+                    if (u < m) tile[l[u]] = cmul(w, v[u]);
             });
         } break;
     }
@@ -579,8 +645,11 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
 
 template <typename A, typename TV>
 __device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, const TileOp* ops, int k, uint64_t base) {
+    using C = typename Num<A>::C;
+    using R = typename Num<A>::R;
+    using N = Num<A>;
     const uint32_t r0 = hdr.ph.rpos[0], r1 = hdr.ph.rpos[1], r2 = hdr.ph.rpos[2];
-    const uint32_t b0 = 1u << r0, b1 = 1u << r1, b2 = 1u << r2, rmask = b0 | b1 | b2;
+    const uint32_t b0 = 1u << r0, b1 = 1u << r1, b2 = 1u << r2;
     const int count = hdr.ph.count;
     // groups are enumerated over the tile bits that are neither register bits nor controls shared by
     // every gate of the phase (hdr.lctrl): heavily controlled stretches only touch their own corner
@@ -588,14 +657,32 @@ __device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, con
     for (uint32_t g = threadIdx.x; g < cnt; g += blockDim.x) {
         const uint32_t l = expand_local(g, hdr.fixpos, hdr.nfix) | hdr.lctrl;
         uint32_t off[8];
-        double2 v[8];
+        C v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             off[j] = l | ((j & 1) ? b0 : 0u) | ((j & 2) ? b1 : 0u) | ((j & 4) ? b2 : 0u);
-            v[j] = to_c128(tile[off[j]]);
+            v[j] = tile[off[j]];
         }
         for (int mi = 0; mi < count; ++mi) {
-            const TileOp& op = ops[mi];
+            // the member's descriptor comes in as two 16-byte shared-memory loads issued back to back (field-by-field
+            // reads were a chain of dependent loads and branches); the matrix follows once the member is known to act
+            struct alignas(16) MemberWords {
+                uint4 w0, w1;
+            };
+            const MemberWords op_w = *reinterpret_cast<const MemberWords*>(&ops[mi]);
+            struct {
+                uint8_t op, tpos;
+                uint32_t nfix;
+                uint64_t fixpos, ext_ctrl, ext_tbit;
+                const double* m;
+            } op;
+            op.op = (uint8_t)(op_w.w0.x & 0xFFu);
+            op.tpos = (uint8_t)((op_w.w0.x >> 8) & 0xFFu);
+            op.nfix = op_w.w0.x >> 24;
+            op.fixpos = (uint64_t)op_w.w0.z | ((uint64_t)op_w.w0.w << 32);
+            op.ext_ctrl = (uint64_t)op_w.w1.x | ((uint64_t)op_w.w1.y << 32);
+            op.ext_tbit = (uint64_t)op_w.w1.z | ((uint64_t)op_w.w1.w << 32);
+            op.m = ops[mi].m;
             if ((base & op.ext_ctrl) != op.ext_ctrl) continue;
             // pre-decoded by the host (tileops.hpp): controls outside R, per-element mask of the controls inside R,
             // register position of the target(s), real-matrix flag
@@ -608,7 +695,7 @@ __device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, con
                 case B2SV_OP_X: {
 #define B2SV_F(a, b)                       \
     if ((ok >> a) & 1u) {                  \
-        const double2 t_ = v[a];           \
+        const C t_ = v[a];           \
         v[a] = v[b];                       \
         v[b] = t_;                         \
     }
@@ -617,22 +704,22 @@ __device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, con
                 } break;
                 case B2SV_OP_MAT1: {
                     if ((fx >> 36) & 1u) {  // real matrix: two FP64 operations per component instead of four
-                        const double r00 = op.m[0], r01 = op.m[2], r10 = op.m[4], r11 = op.m[6];
+                        const R r00 = mval<A>(op.m, 0), r01 = mval<A>(op.m, 2), r10 = mval<A>(op.m, 4), r11 = mval<A>(op.m, 6);
 #define B2SV_F(a, b)                                                                  \
     if ((ok >> a) & 1u) {                                                             \
-        const double2 x_ = v[a], y_ = v[b];                                           \
-        v[a] = make_double2(fma(r01, y_.x, r00 * x_.x), fma(r01, y_.y, r00 * x_.y));  \
-        v[b] = make_double2(fma(r11, y_.x, r10 * x_.x), fma(r11, y_.y, r10 * x_.y));  \
+        const C x_ = v[a], y_ = v[b];                                                 \
+        v[a] = N::mk(fma(r01, y_.x, r00 * x_.x), fma(r01, y_.y, r00 * x_.y));         \
+        v[b] = N::mk(fma(r11, y_.x, r10 * x_.x), fma(r11, y_.y, r10 * x_.y));         \
     }
                         B2SV_PAIRS(rp, B2SV_F)
 #undef B2SV_F
                         break;
                     }
-                    const double2 m00 = make_double2(op.m[0], op.m[1]), m01 = make_double2(op.m[2], op.m[3]);
-                    const double2 m10 = make_double2(op.m[4], op.m[5]), m11 = make_double2(op.m[6], op.m[7]);
+                    const C m00 = N::mk(mval<A>(op.m, 0), mval<A>(op.m, 1)), m01 = N::mk(mval<A>(op.m, 2), mval<A>(op.m, 3));
+                    const C m10 = N::mk(mval<A>(op.m, 4), mval<A>(op.m, 5)), m11 = N::mk(mval<A>(op.m, 6), mval<A>(op.m, 7));
 #define B2SV_F(a, b)                                   \
     if ((ok >> a) & 1u) {                              \
-        const double2 x_ = v[a], y_ = v[b];            \
+        const C x_ = v[a], y_ = v[b];                  \
         v[a] = cfma(m01, y_, cmul(m00, x_));           \
         v[b] = cfma(m11, y_, cmul(m10, x_));           \
     }
@@ -640,9 +727,9 @@ __device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, con
 #undef B2SV_F
                 } break;
                 case B2SV_OP_DIAG1: {
-                    const double2 d0 = make_double2(op.m[0], op.m[1]), d1 = make_double2(op.m[2], op.m[3]);
+                    const C d0 = N::mk(mval<A>(op.m, 0), mval<A>(op.m, 1)), d1 = N::mk(mval<A>(op.m, 2), mval<A>(op.m, 3));
                     if (op.tpos == 0xFF) {
-                        const double2 d = (base & op.ext_tbit) ? d1 : d0;
+                        const C d = (base & op.ext_tbit) ? d1 : d0;
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             if ((ok >> j) & 1u) v[j] = cmul(d, v[j]);
@@ -661,7 +748,7 @@ __device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, con
                     const int pair = rp + rq;  // {0,1} -> 1, {0,2} -> 2, {1,2} -> 3
 #define B2SV_S(a, b)                       \
     if ((ok >> a) & 1u) {                  \
-        const double2 t_ = v[a];           \
+        const C t_ = v[a];           \
         v[a] = v[b];                       \
         v[b] = t_;                         \
     }
@@ -671,7 +758,7 @@ __device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, con
 #undef B2SV_S
                 } break;
                 default: {  // PHASE
-                    const double2 w = make_double2(op.m[0], op.m[1]);
+                    const C w = N::mk(mval<A>(op.m, 0), mval<A>(op.m, 1));
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         if ((ok >> j) & 1u) v[j] = cmul(w, v[j]);
@@ -679,7 +766,7 @@ __device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, con
             }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) tile[off[j]] = from_c128<A>(v[j]);
+        for (int j = 0; j < 8; ++j) tile[off[j]] = v[j];
     }
 }
 #undef B2SV_PAIRS
@@ -716,6 +803,7 @@ __host__ __device__ __forceinline__ uint32_t mono_next_subset(uint32_t cur, uint
 template <typename A, int V, bool FAC, typename TV>
 __device__ __forceinline__ void tile_apply_mono(TV tile, const TileOp& hdr, uint64_t base, uint32_t slice,
                                                 const double2* __restrict__ tables) {
+    using C = typename Num<A>::C;
     constexpr int E = kMonoElems;
     static_assert(V == 8 || V == 4, "walks per thread");
     const uint32_t tmask = hdr.mono.tmask, qlmask = hdr.mono.qlmask, nmask = hdr.mono.nmask;
@@ -739,11 +827,11 @@ __device__ __forceinline__ void tile_apply_mono(TV tile, const TileOp& hdr, uint
         xw[0] = w.x;
         xw[1] = w.y;
     }
-    double2 fac[FAC ? V : 1];
+    C fac[FAC ? V : 1];
     if (FAC) {
         const double2* __restrict__ fm = tables + hdr.mono.fac_off + first;
 #pragma unroll
-        for (int v = 0; v < V; ++v) fac[v] = __ldg(fm + v);
+        for (int v = 0; v < V; ++v) fac[v] = narrow(__ldg(fm + v), (C*)nullptr);
     }
     // amplitude e of a round belongs to walk e mod V (E is a multiple of V); `q` runs through the walk bits,
     // `ncur` through the untouched loop bits.  The destinations are recomputed after the barrier rather
@@ -751,14 +839,14 @@ __device__ __forceinline__ void tile_apply_mono(TV tile, const TileOp& hdr, uint
     uint32_t ncur = 0;
 #pragma unroll 1
     for (uint32_t j0 = 0; j0 < per_thread; j0 += E) {
-        double2 val[E];
+        C val[E];
         {
             uint32_t q = 0, nn = ncur;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 constexpr int VM = V - 1;
                 const int v = e & VM;
-                val[e] = to_c128(tile[tpart | q | nn]);
+                val[e] = tile[tpart | q | nn];
                 if (FAC) val[e] = cmul(fac[v], val[e]);
                 q = mono_next_subset(q, qlmask);
                 if (v == VM) nn = mono_next_subset(nn, nmask);
@@ -772,7 +860,7 @@ __device__ __forceinline__ void tile_apply_mono(TV tile, const TileOp& hdr, uint
                 constexpr int VM = V - 1;
                 const int v = e & VM;
                 const uint32_t xm = (v & 1) ? (xw[v >> 1] >> 16) : (xw[v >> 1] & 0xFFFFu);
-                tile[(tpart | q | ncur) ^ xm] = from_c128<A>(val[e]);
+                tile[(tpart | q | ncur) ^ xm] = val[e];
                 q = mono_next_subset(q, qlmask);
                 if (v == VM) ncur = mono_next_subset(ncur, nmask);
             }
@@ -823,6 +911,24 @@ __device__ __forceinline__ void tile_stage_ops(TileOp* s_ops, const TileOp* g_op
     for (int i = tid; i < n16; i += nt) dst[i] = __ldg(src + i);
 }
 
+// complex64 sweeps: narrow the matrix entries of the staged plain ops (stand-alone ones and register-phase members) to
+// floats in place, once per staged batch (see mval)
+template <typename A>
+__device__ __forceinline__ void tile_narrow_ops(TileOp* s_ops, int n, int tid, int nt) {
+    if constexpr (sizeof(A) == 8) {
+        for (int o = tid; o < n; o += nt) {
+            TileOp& op = s_ops[o];
+            if (op.op > B2SV_OP_PHASE) continue;  // table-driven ops and phase headers carry no matrix here
+            double t[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = op.m[i];
+            float* f = reinterpret_cast<float*>(op.m);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = (float)t[i];
+        }
+    }
+}
+
 template <typename A, bool FUSED, typename TV>
 __device__ __forceinline__ void tile_run_batches(TV tile, TileOp* s_ops, const TileOp* g_ops, int n_ops, int k, uint64_t base,
                                                  const double2* __restrict__ tables, const BlkSlots* bs) {
@@ -831,6 +937,8 @@ __device__ __forceinline__ void tile_run_batches(TV tile, TileOp* s_ops, const T
         if (b0 > 0) {
             __syncthreads();
             tile_stage_ops(s_ops, g_ops + b0, nb, (int)threadIdx.x, (int)blockDim.x);
+            __syncthreads();
+            tile_narrow_ops<A>(s_ops, nb, (int)threadIdx.x, (int)blockDim.x);
             __syncthreads();
         }
         tile_run_ops<A, FUSED>(tile, s_ops, nb, k, base, tables, bs);
@@ -871,6 +979,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile(A* __restrict__ psi, const
             bulk_g2s(tile + (size_t)j * chunk_elems, psi + (base | chunk_offset(j, a.tile_ex, k, lc)), chunk_bytes, &bar);
     }
     tile_stage_ops(s_ops, a.ops, a.n_ops < kTileMaxOps ? a.n_ops : kTileMaxOps, tid, kThreads);
+    if constexpr (sizeof(A) == 8) {
+        __syncthreads();
+        tile_narrow_ops<A>(s_ops, a.n_ops < kTileMaxOps ? a.n_ops : kTileMaxOps, tid, kThreads);
+    }
     if (!load) {
         const uint32_t elems = 1u << k;
         const A zero = from_c128<A>(make_double2(0.0, 0.0));
@@ -970,6 +1082,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile_swz(const __grid_constant_
         }
     }
     tile_stage_ops(s_ops, a.ops, a.n_ops < kTileMaxOps ? a.n_ops : kTileMaxOps, tid, kThreads);
+    if constexpr (sizeof(A) == 8) {
+        __syncthreads();
+        tile_narrow_ops<A>(s_ops, a.n_ops < kTileMaxOps ? a.n_ops : kTileMaxOps, tid, kThreads);
+    }
     if (!load) {
         const uint32_t elems = 1u << k;
         const A zero = from_c128<A>(make_double2(0.0, 0.0));
@@ -1398,18 +1514,25 @@ __global__ void __launch_bounds__(kThreads) k_fill_random(A* __restrict__ psi, u
 // walks the few window amplitudes FORWARD through the run and drops each at its destination: out[f(i)] = s * in[i].
 // f is a bijection, so no two threads write the same amplitude.  Sharded form: blockIdx.y is the source rank; every
 // rank walks every window amplitude (read over NVLink: a few KiB) and keeps the ones that land in its own shard.
+// The walk is one dependent chain per amplitude, so its latency per gate is what counts: the gate list is staged through
+// shared memory in chunks (reading it from global memory cost ~140 ns per gate: 0.2 ms for the 1434-gate run of config
+// 2 on a 16-CTA grid) and a gate is applied branch-free.
+constexpr int kScatterChunk = 512;
 template <typename A>
 __global__ void __launch_bounds__(kThreads) k_perm_scatter(const __grid_constant__ DistPermArgs a, const DistGate* __restrict__ gates,
                                                            int n_gates, int nl) {
+    __shared__ DistGate s_gates[kScatterChunk];
     const unsigned r = blockIdx.y;
     const uint64_t lmask = (1ull << nl) - 1ull;
     const uint64_t free_mask = ~a.wmask[r] & lmask;
     const int free_bits = __popcll(free_mask);
-    if ((a.wval[r] & ~a.wmask[r]) != 0) return;  // empty window (a shard that holds no amplitude)
+    if ((a.wval[r] & ~a.wmask[r]) != 0) return;  // empty window (a shard that holds no amplitude): uniform over the CTA
     const uint64_t count = 1ull << free_bits;
     A* out = reinterpret_cast<A*>(a.out);
     const A* in = reinterpret_cast<const A*>(a.src[r]);
-    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k0 = (uint64_t)blockIdx.x * blockDim.x; k0 < count; k0 += stride) {  // uniform trip count per CTA
+        const uint64_t k = k0 + threadIdx.x;
         uint64_t src = a.wval[r], m = free_mask, kk = k;  // deposit the bits of k at the free positions
         while (m) {
             const uint64_t low = m & (0ull - m);
@@ -1418,13 +1541,24 @@ __global__ void __launch_bounds__(kThreads) k_perm_scatter(const __grid_constant
             m ^= low;
         }
         uint64_t idx = src | ((uint64_t)(r ^ a.flip_in) << nl);  // logical index of the source amplitude
-        for (int gi = 0; gi < n_gates; ++gi) {                  // forward: execution order
-            const DistGate g = gates[gi];
-            if ((idx & g.ctrl) != g.ctrl) continue;
-            if (g.op == B2SV_OP_X) idx ^= 1ull << g.t0;
-            else if (((idx >> g.t0) ^ (idx >> g.t1)) & 1ull) idx ^= (1ull << g.t0) | (1ull << g.t1);
+        for (int g0 = 0; g0 < n_gates; g0 += kScatterChunk) {    // forward: execution order
+            const int nb = n_gates - g0 < kScatterChunk ? n_gates - g0 : kScatterChunk;
+            __syncthreads();
+            for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+                const uint4 w = __ldg(reinterpret_cast<const uint4*>(gates + g0 + i));
+                *reinterpret_cast<uint4*>(&s_gates[i]) = w;
+            }
+            __syncthreads();
+#pragma unroll 4
+            for (int gi = 0; gi < nb; ++gi) {
+                const DistGate g = s_gates[gi];
+                const uint64_t b0 = 1ull << g.t0, b1 = 1ull << g.t1;
+                // X: flip t0; SWAP: flip both when they differ
+                const uint64_t flip = g.op == B2SV_OP_X ? b0 : ((((idx >> g.t0) ^ (idx >> g.t1)) & 1ull) ? (b0 | b1) : 0ull);
+                idx ^= ((idx & g.ctrl) == g.ctrl) ? flip : 0ull;
+            }
         }
-        if ((unsigned)(idx >> nl) != a.rank_logical) continue;  // lands on another rank
+        if (k >= count || (unsigned)(idx >> nl) != a.rank_logical) continue;  // beyond the window / lands on another rank
         B2SV_CHECK(src <= lmask);
         A v = in[src];
         if (a.has_scale) v = from_c128<A>(cmul(make_double2(a.sre[r], a.sim[r]), to_c128(v)));

@@ -103,6 +103,24 @@ inline TileOp make_tile_op(const Plan& plan, const PGate& g, uint64_t tile_mask,
                 op.mux.mq[j] = (uint8_t)q;
                 ++j;
             }
+        // the index bits inside the tile join the fixed positions and are enumerated last (kernels.cuh, kOpMux)
+        uint32_t mfixed = fixed;
+        op.mux.nl = 0;
+        op.mux.lppack = op.mux.ljpack = 0;
+        for (int jj = 0; jj < mi.nbits; ++jj)
+            if (op.mux.mpos[jj] != 0xFF) {
+                mfixed |= 1u << op.mux.mpos[jj];
+                op.mux.lppack |= (uint32_t)op.mux.mpos[jj] << (4 * op.mux.nl);
+                op.mux.ljpack |= (uint32_t)jj << (4 * op.mux.nl);
+                op.mux.nl++;
+            }
+        op.mux.mfixpos = 0;
+        op.mux.mnfix = 0;
+        for (int i = 0; i < ex.m; ++i)
+            if ((mfixed >> i) & 1) {
+                op.mux.mfixpos |= (uint64_t)i << (4 * op.mux.mnfix);
+                op.mux.mnfix++;
+            }
     }
     return op;
 }
