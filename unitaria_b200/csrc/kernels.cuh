@@ -318,8 +318,42 @@ struct TileView {
 // Enumerate the tile-local indices with the fixed positions cleared, UNROLL at a time, so that a
 // thread has UNROLL independent shared-memory round trips in flight (the tile phase is latency-
 // bound otherwise: 8 warps per CTA, a dependent LDS -> DFMA -> STS chain per element).
+// Element p = tid + i * nt of the enumeration (nt = CTA size, a power of two) has the bits of tid in the lowest free
+// positions and the bits of i in the free positions above them, so the deposit of tid is done ONCE per op and the
+// i part is stepped as "next subset of a mask" (3 instructions) -- depositing every p bit by bit was ~10
+// instructions per fixed position per element, a quarter of the instructions of a dense-block pass.
+__device__ __forceinline__ uint32_t subset_next(uint32_t cur, uint32_t mask) { return ((cur | ~mask) + 1u) & mask; }
+
 template <int UNROLL, typename F>
 __device__ __forceinline__ void tile_for_each(uint32_t cnt, uint64_t fixpos, int nfix, uint32_t lctrl, F&& body) {
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    if (tid >= cnt) return;
+    const uint32_t lt = expand_local(tid, fixpos, nfix) | lctrl;
+    const uint32_t himask = cnt > nt ? expand_local((cnt - 1u) & ~(nt - 1u), fixpos, nfix) : 0u;
+    const uint32_t iters = cnt > nt ? cnt / nt : 1u;  // a power of two
+    uint32_t hi = 0, i = 0;
+    uint32_t l[UNROLL];
+#pragma unroll 1
+    for (; i + UNROLL <= iters; i += UNROLL) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            l[u] = lt | hi;
+            hi = subset_next(hi, himask);
+        }
+        body(l, UNROLL);
+    }
+#pragma unroll 1
+    for (; i < iters; ++i) {
+        l[0] = lt | hi;
+        hi = subset_next(hi, himask);
+        body(l, 1);
+    }
+}
+
+// The bit-by-bit form (every element deposited on its own): kept for the dense-block passes, whose bodies sit at the
+// register limit -- the three extra live values of the stepped form made ptxas spill 1.2 KB per thread there.
+template <int UNROLL, typename F>
+__device__ __forceinline__ void tile_for_each_deposit(uint32_t cnt, uint64_t fixpos, int nfix, uint32_t lctrl, F&& body) {
     uint32_t p = threadIdx.x;
     const uint32_t nt = blockDim.x;
     for (; p + (UNROLL - 1) * nt < cnt; p += UNROLL * nt) {
@@ -375,7 +409,7 @@ __device__ __forceinline__ void tile_block_pass(TV tile, const TileOp& op, int k
     const uint32_t cnt = 1u << (k - op.nfix);
     if (KB == 3) {
         const uint32_t b0 = 1u << op.blk.bpos[0], b1 = 1u << op.blk.bpos[1], b2 = 1u << op.blk.bpos[2];
-        tile_for_each<1>(cnt, op.fixpos, op.nfix, op.lctrl, [&](const uint32_t* l, int) {
+        tile_for_each_deposit<1>(cnt, op.fixpos, op.nfix, op.lctrl, [&](const uint32_t* l, int) {
             uint32_t off[8];
             C v[8];
 #pragma unroll
@@ -399,7 +433,7 @@ __device__ __forceinline__ void tile_block_pass(TV tile, const TileOp& op, int k
         });
     } else {  // KB == 2
         const uint32_t b0 = 1u << op.blk.bpos[0], b1 = 1u << op.blk.bpos[1];
-        tile_for_each<1>(cnt, op.fixpos, op.nfix, op.lctrl, [&](const uint32_t* l, int) {
+        tile_for_each_deposit<1>(cnt, op.fixpos, op.nfix, op.lctrl, [&](const uint32_t* l, int) {
             uint32_t off[4];
             C v[4], acc[4];
 #pragma unroll
@@ -581,6 +615,8 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
             const uint32_t nt = blockDim.x;
             const uint32_t per = 1u << fbits, T = per < nt ? per : nt;
             const uint32_t t = threadIdx.x & (T - 1), grp = threadIdx.x / T, ngrp = nt / T;
+            const uint32_t lt = expand_local(t, mfixpos, mnfix);  // see tile_for_each
+            const uint32_t himask = expand_local((per - 1u) & ~(T - 1u), mfixpos, mnfix);
             for (uint32_t il = grp; il < (1u << nl); il += ngrp) {
                 uint32_t idx = idx_ext, lbits = 0;
                 for (int i = 0; i < nl; ++i)
@@ -592,10 +628,12 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
                 const C m00 = narrow(__ldg(M), (C*)nullptr), m01 = narrow(__ldg(M + 1), (C*)nullptr);
                 const C m10 = narrow(__ldg(M + 2), (C*)nullptr), m11 = narrow(__ldg(M + 3), (C*)nullptr);
                 const uint32_t lfix = lctrl | lbits;
-                uint32_t p = t;
+                uint32_t p = t, hi = 0;
                 for (; p + T < per; p += 2 * T) {  // two independent shared-memory round trips in flight
-                    const uint32_t la = expand_local(p, mfixpos, mnfix) | lfix;
-                    const uint32_t lb = expand_local(p + T, mfixpos, mnfix) | lfix;
+                    const uint32_t la = lt | hi | lfix;
+                    hi = subset_next(hi, himask);
+                    const uint32_t lb = lt | hi | lfix;
+                    hi = subset_next(hi, himask);
                     const C a0 = tile[la], a1 = tile[la | bt];
                     const C b0 = tile[lb], b1 = tile[lb | bt];
                     tile[la] = cfma(m01, a1, cmul(m00, a0));
@@ -604,7 +642,8 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
                     tile[lb | bt] = cfma(m11, b1, cmul(m10, b0));
                 }
                 for (; p < per; p += T) {
-                    const uint32_t la = expand_local(p, mfixpos, mnfix) | lfix;
+                    const uint32_t la = lt | hi | lfix;
+                    hi = subset_next(hi, himask);
                     const C a0 = tile[la], a1 = tile[la | bt];
                     tile[la] = cfma(m01, a1, cmul(m00, a0));
                     tile[la | bt] = cfma(m11, a1, cmul(m10, a0));
@@ -654,8 +693,13 @@ __device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, con
     // groups are enumerated over the tile bits that are neither register bits nor controls shared by
     // every gate of the phase (hdr.lctrl): heavily controlled stretches only touch their own corner
     const uint32_t cnt = 1u << (k - hdr.nfix);
+    if (threadIdx.x >= cnt) return;
+    const uint32_t lt = expand_local(threadIdx.x, hdr.fixpos, hdr.nfix) | hdr.lctrl;  // see tile_for_each
+    const uint32_t himask = cnt > blockDim.x ? expand_local((cnt - 1u) & ~(blockDim.x - 1u), hdr.fixpos, hdr.nfix) : 0u;
+    uint32_t hi = 0;
     for (uint32_t g = threadIdx.x; g < cnt; g += blockDim.x) {
-        const uint32_t l = expand_local(g, hdr.fixpos, hdr.nfix) | hdr.lctrl;
+        const uint32_t l = lt | hi;
+        hi = subset_next(hi, himask);
         uint32_t off[8];
         C v[8];
 #pragma unroll

@@ -500,13 +500,23 @@ inline bool gate_is_real(const PGate& g) {
     if (g.op == B2SV_OP_PHASE) return g.m[1] == 0.0;
     return true;
 }
+// What a gate costs as a register-phase member beyond its arithmetic (decode, predicates, the idle threads of a phase
+// whose members share controls): it does NOT shrink with the number of controls.  Measured on the 30-qubit BPX sweeps:
+// 29 mostly doubly-controlled gates in six phases took 6.7 ms of compute where their DFMA count predicted 1.1 ms.
+inline double member_overhead() {
+    static const double v = [] {
+        const char* e = std::getenv("B2SV_MEMBER_COST");
+        return e ? std::atof(e) : 64.0;
+    }();
+    return v;
+}
 inline double gate_fp64_cost(const PGate& g, uint64_t common) {
     const double f = std::ldexp(1.0, -popcount64(g.ctrl & ~common));
     switch (g.op) {
-        case B2SV_OP_MAT1: return f * (gate_is_real(g) ? 32.0 : 64.0);
+        case B2SV_OP_MAT1: return f * (gate_is_real(g) ? 32.0 : 64.0) + member_overhead();
         case B2SV_OP_DIAG1:
-        case B2SV_OP_PHASE: return f * 32.0;
-        default: return 0.0;
+        case B2SV_OP_PHASE: return f * 32.0 + member_overhead();
+        default: return member_overhead();
     }
 }
 // one dense block pass: 2^kb complex FMAs per amplitude (half for a real matrix) plus a shared-memory round trip of
