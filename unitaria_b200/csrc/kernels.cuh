@@ -313,6 +313,21 @@ struct TileView {
         }
         return p[l];
     }
+    // The swizzle is linear over GF(2): swz(l ^ b) = swz(l) ^ swz(b).  An op therefore swizzles an element index once
+    // and reaches its partners (l | target bit, the 2^kb corners of a block, the eight amplitudes of a register group)
+    // with ONE XOR each against a per-op constant, instead of re-deriving every address (~6 instructions apiece in
+    // passes that are instruction-issue bound).
+    __device__ __forceinline__ uint32_t swz(uint32_t l) const {
+        if (SWZ) {
+            if (sizeof(A) == 16) l ^= (l >> 3) & 7u;
+            else l ^= ((l >> 4) & 7u) << 1;
+        }
+        return l;
+    }
+    __device__ __forceinline__ A& raw(uint32_t s) const {  // s = swz(l)
+        B2SV_CHECK(s < n);
+        return p[s];
+    }
 };
 
 // Enumerate the tile-local indices with the fixed positions cleared, UNROLL at a time, so that a
@@ -324,11 +339,12 @@ struct TileView {
 // instructions per fixed position per element, a quarter of the instructions of a dense-block pass.
 __device__ __forceinline__ uint32_t subset_next(uint32_t cur, uint32_t mask) { return ((cur | ~mask) + 1u) & mask; }
 
-template <int UNROLL, typename F>
-__device__ __forceinline__ void tile_for_each(uint32_t cnt, uint64_t fixpos, int nfix, uint32_t lctrl, F&& body) {
+// The body gets SWIZZLED element indices (TileView::raw).
+template <int UNROLL, typename TV, typename F>
+__device__ __forceinline__ void tile_for_each(TV tile, uint32_t cnt, uint64_t fixpos, int nfix, uint32_t lctrl, F&& body) {
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
     if (tid >= cnt) return;
-    const uint32_t lt = expand_local(tid, fixpos, nfix) | lctrl;
+    const uint32_t lt = tile.swz(expand_local(tid, fixpos, nfix) | lctrl);
     const uint32_t himask = cnt > nt ? expand_local((cnt - 1u) & ~(nt - 1u), fixpos, nfix) : 0u;
     const uint32_t iters = cnt > nt ? cnt / nt : 1u;  // a power of two
     uint32_t hi = 0, i = 0;
@@ -337,14 +353,14 @@ __device__ __forceinline__ void tile_for_each(uint32_t cnt, uint64_t fixpos, int
     for (; i + UNROLL <= iters; i += UNROLL) {
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            l[u] = lt | hi;
+            l[u] = lt ^ tile.swz(hi);
             hi = subset_next(hi, himask);
         }
         body(l, UNROLL);
     }
 #pragma unroll 1
     for (; i < iters; ++i) {
-        l[0] = lt | hi;
+        l[0] = lt ^ tile.swz(hi);
         hi = subset_next(hi, himask);
         body(l, 1);
     }
@@ -352,19 +368,19 @@ __device__ __forceinline__ void tile_for_each(uint32_t cnt, uint64_t fixpos, int
 
 // The bit-by-bit form (every element deposited on its own): kept for the dense-block passes, whose bodies sit at the
 // register limit -- the three extra live values of the stepped form made ptxas spill 1.2 KB per thread there.
-template <int UNROLL, typename F>
-__device__ __forceinline__ void tile_for_each_deposit(uint32_t cnt, uint64_t fixpos, int nfix, uint32_t lctrl, F&& body) {
+template <int UNROLL, typename TV, typename F>
+__device__ __forceinline__ void tile_for_each_deposit(TV tile, uint32_t cnt, uint64_t fixpos, int nfix, uint32_t lctrl, F&& body) {
     uint32_t p = threadIdx.x;
     const uint32_t nt = blockDim.x;
     for (; p + (UNROLL - 1) * nt < cnt; p += UNROLL * nt) {
         uint32_t l[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) l[u] = expand_local(p + u * nt, fixpos, nfix) | lctrl;
+        for (int u = 0; u < UNROLL; ++u) l[u] = tile.swz(expand_local(p + u * nt, fixpos, nfix) | lctrl);
         body(l, UNROLL);
     }
     for (; p < cnt; p += nt) {
         uint32_t l[UNROLL];
-        l[0] = expand_local(p, fixpos, nfix) | lctrl;
+        l[0] = tile.swz(expand_local(p, fixpos, nfix) | lctrl);
         body(l, 1);
     }
 }
@@ -408,14 +424,14 @@ __device__ __forceinline__ void tile_block_pass(TV tile, const TileOp& op, int k
     using C = typename Num<A>::C;
     const uint32_t cnt = 1u << (k - op.nfix);
     if (KB == 3) {
-        const uint32_t b0 = 1u << op.blk.bpos[0], b1 = 1u << op.blk.bpos[1], b2 = 1u << op.blk.bpos[2];
-        tile_for_each_deposit<1>(cnt, op.fixpos, op.nfix, op.lctrl, [&](const uint32_t* l, int) {
+        const uint32_t b0 = tile.swz(1u << op.blk.bpos[0]), b1 = tile.swz(1u << op.blk.bpos[1]), b2 = tile.swz(1u << op.blk.bpos[2]);
+        tile_for_each_deposit<1>(tile, cnt, op.fixpos, op.nfix, op.lctrl, [&](const uint32_t* l, int) {
             uint32_t off[8];
             C v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                off[j] = l[0] | ((j & 1) ? b0 : 0u) | ((j & 2) ? b1 : 0u) | ((j & 4) ? b2 : 0u);
-                v[j] = tile[off[j]];
+                off[j] = l[0] ^ ((j & 1) ? b0 : 0u) ^ ((j & 2) ? b1 : 0u) ^ ((j & 4) ? b2 : 0u);
+                v[j] = tile.raw(off[j]);
             }
             // four rows at a time: four independent accumulation chains hide the DFMA latency
 #pragma unroll
@@ -428,18 +444,18 @@ __device__ __forceinline__ void tile_block_pass(TV tile, const TileOp& op, int k
 #pragma unroll
                     for (int r = 0; r < 4; ++r) acc[r] = bfma<REAL>(U((r0 + r) * 8 + c), v[c], acc[r]);
 #pragma unroll
-                for (int r = 0; r < 4; ++r) tile[off[r0 + r]] = acc[r];
+                for (int r = 0; r < 4; ++r) tile.raw(off[r0 + r]) = acc[r];
             }
         });
     } else {  // KB == 2
-        const uint32_t b0 = 1u << op.blk.bpos[0], b1 = 1u << op.blk.bpos[1];
-        tile_for_each_deposit<1>(cnt, op.fixpos, op.nfix, op.lctrl, [&](const uint32_t* l, int) {
+        const uint32_t b0 = tile.swz(1u << op.blk.bpos[0]), b1 = tile.swz(1u << op.blk.bpos[1]);
+        tile_for_each_deposit<1>(tile, cnt, op.fixpos, op.nfix, op.lctrl, [&](const uint32_t* l, int) {
             uint32_t off[4];
             C v[4], acc[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                off[j] = l[0] | ((j & 1) ? b0 : 0u) | ((j & 2) ? b1 : 0u);
-                v[j] = tile[off[j]];
+                off[j] = l[0] ^ ((j & 1) ? b0 : 0u) ^ ((j & 2) ? b1 : 0u);
+                v[j] = tile.raw(off[j]);
             }
 #pragma unroll
             for (int r = 0; r < 4; ++r) acc[r] = bmul<REAL>(U(r * 4), v[0]);
@@ -448,7 +464,7 @@ __device__ __forceinline__ void tile_block_pass(TV tile, const TileOp& op, int k
 #pragma unroll
                 for (int r = 0; r < 4; ++r) acc[r] = bfma<REAL>(U(r * 4 + c), v[c], acc[r]);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) tile[off[r]] = acc[r];
+            for (int r = 0; r < 4; ++r) tile.raw(off[r]) = acc[r];
         });
     }
 }
@@ -506,58 +522,58 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
     const uint32_t lctrl = op.lctrl;
     switch (op.op) {
         case B2SV_OP_X: {
-            const uint32_t bt = 1u << op.tpos;
-            tile_for_each<4>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
+            const uint32_t bt = tile.swz(1u << op.tpos);
+            tile_for_each<4>(tile, cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
                 A v0[4], v1[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                     if (u < m) {
-                        v0[u] = tile[l[u]];
-                        v1[u] = tile[l[u] | bt];
+                        v0[u] = tile.raw(l[u]);
+                        v1[u] = tile.raw(l[u] ^ bt);
                     }
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                     if (u < m) {
-                        tile[l[u]] = v1[u];
-                        tile[l[u] | bt] = v0[u];
+                        tile.raw(l[u]) = v1[u];
+                        tile.raw(l[u] ^ bt) = v0[u];
                     }
             });
         } break;
         case B2SV_OP_SWAP: {
-            const uint32_t ba = 1u << op.tpos, bb = 1u << op.tpos2;
-            tile_for_each<4>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
+            const uint32_t ba = tile.swz(1u << op.tpos), bb = tile.swz(1u << op.tpos2);
+            tile_for_each<4>(tile, cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
                 A va[4], vb[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                     if (u < m) {
-                        va[u] = tile[l[u] | ba];
-                        vb[u] = tile[l[u] | bb];
+                        va[u] = tile.raw(l[u] ^ ba);
+                        vb[u] = tile.raw(l[u] ^ bb);
                     }
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                     if (u < m) {
-                        tile[l[u] | ba] = vb[u];
-                        tile[l[u] | bb] = va[u];
+                        tile.raw(l[u] ^ ba) = vb[u];
+                        tile.raw(l[u] ^ bb) = va[u];
                     }
             });
         } break;
         case B2SV_OP_MAT1: {
-            const uint32_t bt = 1u << op.tpos;
+            const uint32_t bt = tile.swz(1u << op.tpos);
             const C m00 = N::mk(mval<A>(op.m, 0), mval<A>(op.m, 1)), m01 = N::mk(mval<A>(op.m, 2), mval<A>(op.m, 3));
             const C m10 = N::mk(mval<A>(op.m, 4), mval<A>(op.m, 5)), m11 = N::mk(mval<A>(op.m, 6), mval<A>(op.m, 7));
-            tile_for_each<2>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
+            tile_for_each<2>(tile, cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
                 C v0[2], v1[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u)
                     if (u < m) {
-                        v0[u] = tile[l[u]];
-                        v1[u] = tile[l[u] | bt];
+                        v0[u] = tile.raw(l[u]);
+                        v1[u] = tile.raw(l[u] ^ bt);
                     }
 #pragma unroll
                 for (int u = 0; u < 2; ++u)
                     if (u < m) {
-                        tile[l[u]] = cfma(m01, v1[u], cmul(m00, v0[u]));
-                        tile[l[u] | bt] = cfma(m11, v1[u], cmul(m10, v0[u]));
+                        tile.raw(l[u]) = cfma(m01, v1[u], cmul(m00, v0[u]));
+                        tile.raw(l[u] ^ bt) = cfma(m11, v1[u], cmul(m10, v0[u]));
                     }
             });
         } break;
@@ -566,30 +582,30 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
             if (op.tpos == 0xFF) {  // target outside the tile: one CTA-uniform factor
                 const C d = (base & op.ext_tbit) ? d1 : d0;
                 if (d.x == 1 && d.y == 0) break;
-                tile_for_each<4>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
+                tile_for_each<4>(tile, cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
                     C v[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if (u < m) v[u] = tile[l[u]];
+                        if (u < m) v[u] = tile.raw(l[u]);
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if (u < m) tile[l[u]] = cmul(d, v[u]);
+                        if (u < m) tile.raw(l[u]) = cmul(d, v[u]);
                 });
             } else {
-                const uint32_t bt = 1u << op.tpos;
-                tile_for_each<2>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
+                const uint32_t bt = tile.swz(1u << op.tpos);
+                tile_for_each<2>(tile, cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
                     C v0[2], v1[2];
 #pragma unroll
                     for (int u = 0; u < 2; ++u)
                         if (u < m) {
-                            v0[u] = tile[l[u]];
-                            v1[u] = tile[l[u] | bt];
+                            v0[u] = tile.raw(l[u]);
+                            v1[u] = tile.raw(l[u] ^ bt);
                         }
 #pragma unroll
                     for (int u = 0; u < 2; ++u)
                         if (u < m) {
-                            tile[l[u]] = cmul(d0, v0[u]);
-                            tile[l[u] | bt] = cmul(d1, v1[u]);
+                            tile.raw(l[u]) = cmul(d0, v0[u]);
+                            tile.raw(l[u] ^ bt) = cmul(d1, v1[u]);
                         }
                 });
             }
@@ -600,7 +616,7 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
             // tiny sub-ranges its whole warp -- keeps one matrix in registers over consecutive pairs.  Fetching the
             // matrix per pair made the complex64 state-preparation sweeps of cfg 3 L1-bound: ncu showed 67 % of the L1
             // data-pipe wavefronts being table reads and the pipe 97 % busy.)
-            const uint32_t bt = 1u << op.tpos;
+            const uint32_t bt = tile.swz(1u << op.tpos);
             const int nmux = op.mux.nmux;
             uint32_t idx_ext = 0;
             for (int j = 0; j < nmux; ++j)
@@ -630,23 +646,23 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
                 const uint32_t lfix = lctrl | lbits;
                 uint32_t p = t, hi = 0;
                 for (; p + T < per; p += 2 * T) {  // two independent shared-memory round trips in flight
-                    const uint32_t la = lt | hi | lfix;
+                    const uint32_t la = tile.swz(lt | hi | lfix);
                     hi = subset_next(hi, himask);
-                    const uint32_t lb = lt | hi | lfix;
+                    const uint32_t lb = tile.swz(lt | hi | lfix);
                     hi = subset_next(hi, himask);
-                    const C a0 = tile[la], a1 = tile[la | bt];
-                    const C b0 = tile[lb], b1 = tile[lb | bt];
-                    tile[la] = cfma(m01, a1, cmul(m00, a0));
-                    tile[la | bt] = cfma(m11, a1, cmul(m10, a0));
-                    tile[lb] = cfma(m01, b1, cmul(m00, b0));
-                    tile[lb | bt] = cfma(m11, b1, cmul(m10, b0));
+                    const C a0 = tile.raw(la), a1 = tile.raw(la ^ bt);
+                    const C b0 = tile.raw(lb), b1 = tile.raw(lb ^ bt);
+                    tile.raw(la) = cfma(m01, a1, cmul(m00, a0));
+                    tile.raw(la ^ bt) = cfma(m11, a1, cmul(m10, a0));
+                    tile.raw(lb) = cfma(m01, b1, cmul(m00, b0));
+                    tile.raw(lb ^ bt) = cfma(m11, b1, cmul(m10, b0));
                 }
                 for (; p < per; p += T) {
-                    const uint32_t la = lt | hi | lfix;
+                    const uint32_t la = tile.swz(lt | hi | lfix);
                     hi = subset_next(hi, himask);
-                    const C a0 = tile[la], a1 = tile[la | bt];
-                    tile[la] = cfma(m01, a1, cmul(m00, a0));
-                    tile[la | bt] = cfma(m11, a1, cmul(m10, a0));
+                    const C a0 = tile.raw(la), a1 = tile.raw(la ^ bt);
+                    tile.raw(la) = cfma(m01, a1, cmul(m00, a0));
+                    tile.raw(la ^ bt) = cfma(m11, a1, cmul(m10, a0));
                 }
             }
         } break;
@@ -656,14 +672,14 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
         } break;
         default: {  // PHASE
             const C w = N::mk(mval<A>(op.m, 0), mval<A>(op.m, 1));
-            tile_for_each<4>(cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
+            tile_for_each<4>(tile, cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
                 C v[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    if (u < m) v[u] = tile[l[u]];
+                    if (u < m) v[u] = tile.raw(l[u]);
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    if (u < m) tile[l[u]] = cmul(w, v[u]);
+                    if (u < m) tile.raw(l[u]) = cmul(w, v[u]);
             });
         } break;
     }
@@ -688,7 +704,7 @@ __device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, con
     using R = typename Num<A>::R;
     using N = Num<A>;
     const uint32_t r0 = hdr.ph.rpos[0], r1 = hdr.ph.rpos[1], r2 = hdr.ph.rpos[2];
-    const uint32_t b0 = 1u << r0, b1 = 1u << r1, b2 = 1u << r2;
+    const uint32_t sb0 = tile.swz(1u << r0), sb1 = tile.swz(1u << r1), sb2 = tile.swz(1u << r2);
     const int count = hdr.ph.count;
     // groups are enumerated over the tile bits that are neither register bits nor controls shared by
     // every gate of the phase (hdr.lctrl): heavily controlled stretches only touch their own corner
@@ -702,10 +718,11 @@ __device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, con
         hi = subset_next(hi, himask);
         uint32_t off[8];
         C v[8];
+        const uint32_t sl = tile.swz(l);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            off[j] = l | ((j & 1) ? b0 : 0u) | ((j & 2) ? b1 : 0u) | ((j & 4) ? b2 : 0u);
-            v[j] = tile[off[j]];
+            off[j] = sl ^ ((j & 1) ? sb0 : 0u) ^ ((j & 2) ? sb1 : 0u) ^ ((j & 4) ? sb2 : 0u);
+            v[j] = tile.raw(off[j]);
         }
         for (int mi = 0; mi < count; ++mi) {
             // the member's descriptor comes in as two 16-byte shared-memory loads issued back to back (field-by-field
@@ -810,7 +827,7 @@ __device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, con
             }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) tile[off[j]] = v[j];
+        for (int j = 0; j < 8; ++j) tile.raw(off[j]) = v[j];
     }
 }
 #undef B2SV_PAIRS
