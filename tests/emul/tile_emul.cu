@@ -396,3 +396,39 @@ extern "C" int emul_build_all(int n, int dtype, const b2sv_gate* gates, size_t n
     out3[2] = (int64_t)plan.mux_tables.size();
     return 0;
 }
+
+// Introspection for profiling scripts: every dense block of the plan as {kb, n_controls, real, real_up_to_phase}.
+extern "C" int emul_block_stats(int n, int dtype, const b2sv_gate* gates, size_t n_gates, const b2sv_plan_opts* opts, int32_t* out, int cap) {
+    PlanConfig cfg = default_config(n, dtype, opts);
+    if (n < 13) cfg.perm_runs = false;
+    Plan plan = make_plan(gates, n_gates, cfg, true);
+    int m = 0;
+    for (const PGate& g : plan.gates) {
+        if (g.op != B2SV_OP_BLOCK || 4 * m + 3 >= cap) continue;
+        const BlockInfo& bi = plan.blocks[g.blk];
+        const int dim = 1 << bi.kb;
+        const double* M = plan.mux_tables.data() + 2 * bi.mat_off;
+        bool real = true;
+        double best = 0, pre = 1, pim = 0;
+        for (int e = 0; e < dim * dim; ++e) {
+            real = real && M[2 * e + 1] == 0.0;
+            const double a = std::hypot(M[2 * e], M[2 * e + 1]);
+            if (a > best) {
+                best = a;
+                pre = M[2 * e] / a;
+                pim = M[2 * e + 1] / a;
+            }
+        }
+        bool rup = true;  // real after dividing by the phase of the largest entry
+        for (int e = 0; e < dim * dim; ++e) {
+            const double im = M[2 * e + 1] * pre - M[2 * e] * pim;
+            rup = rup && std::fabs(im) < 1e-14;
+        }
+        out[4 * m] = bi.kb;
+        out[4 * m + 1] = __builtin_popcountll(g.ctrl);
+        out[4 * m + 2] = real ? 1 : 0;
+        out[4 * m + 3] = rup ? 1 : 0;
+        ++m;
+    }
+    return m;
+}

@@ -464,9 +464,32 @@ int launch_tile(b2sv* sv, const Segment& seg, const TileOp* d_ops, int n_ops, co
                 using A = std::remove_pointer_t<decltype(tag)>;
                 int rc = set_swz_smem<A>(sv->device, swz_smem);
                 if (rc) return rc;
-                LaunchTimer lt(sv, timing, CLS_TILE, (lazy_init ? 1.0 : 2.0) * sv->amp_bytes * (double)(n_tiles << a.k));
-                if (fused_ops) k_tile_swz<A, true><<<(unsigned)n_tiles, kThreads, swz_smem, sv->stream>>>(as);
-                else k_tile_swz<A, false><<<(unsigned)n_tiles, kThreads, swz_smem, sv->stream>>>(as);
+                // B2SV_TRACE=<file> B2SV_TRACE_LAUNCH=<i>: dump the phase timestamps of every CTA of the i-th swizzled tile
+                // launch of this process (profiling aid: how load / compute / store of co-resident CTAs overlap)
+                static const char* trace_path = std::getenv("B2SV_TRACE");
+                static const long trace_launch = [] { const char* e = std::getenv("B2SV_TRACE_LAUNCH"); return e ? std::atol(e) : -1L; }();
+                static long launch_no = 0;
+                unsigned long long* d_trace = nullptr;
+                if (trace_path && launch_no++ == trace_launch) {
+                    CU(cudaMalloc(&d_trace, n_tiles * 5 * sizeof(unsigned long long)));
+                    CU(cudaMemsetAsync(d_trace, 0, n_tiles * 5 * sizeof(unsigned long long), sv->stream));
+                    as.t.trace = d_trace;
+                }
+                {
+                    LaunchTimer lt(sv, timing, CLS_TILE, (lazy_init ? 1.0 : 2.0) * sv->amp_bytes * (double)(n_tiles << a.k));
+                    if (fused_ops) k_tile_swz<A, true><<<(unsigned)n_tiles, kThreads, swz_smem, sv->stream>>>(as);
+                    else k_tile_swz<A, false><<<(unsigned)n_tiles, kThreads, swz_smem, sv->stream>>>(as);
+                }
+                if (d_trace) {
+                    std::vector<unsigned long long> h(n_tiles * 5);
+                    CU(cudaStreamSynchronize(sv->stream));
+                    CU(cudaMemcpy(h.data(), d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+                    cudaFree(d_trace);
+                    if (FILE* f = std::fopen(trace_path, "wb")) {
+                        std::fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
+                        std::fclose(f);
+                    }
+                }
                 return B2SV_OK;
             });
         }

@@ -250,6 +250,8 @@ struct TileArgs {
     int init_mode;
     uint64_t init_index;
     uint64_t tile_mask;
+    // phase trace (profiling aid, B2SV_TRACE): per CTA {smid, t_start, t_loaded, t_computed, t_stored} in ns (%globaltimer)
+    unsigned long long* trace;
 };
 
 __host__ __device__ __forceinline__ uint32_t expand_local(uint32_t p, uint64_t fixpos, int nfix) {
@@ -1129,6 +1131,19 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile_swz(const __grid_constant_
     const uint64_t base = expand_bits((uint64_t)blockIdx.x, a.cta_ex) | a.cta_or;
     const bool load = a.init_mode == 0;
 
+    auto stamp = [&](int slot) {
+        if (a.trace != nullptr && tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            a.trace[(size_t)blockIdx.x * 5 + slot] = t;
+            if (slot == 1) {
+                unsigned int smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                a.trace[(size_t)blockIdx.x * 5] = smid;
+            }
+        }
+    };
+    stamp(1);
     if (load) {
         if (tid == 0) {
             mbar_init(&bar, 1);
@@ -1161,6 +1176,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile_swz(const __grid_constant_
         mbar_wait(&bar, 0);
     }
     __syncthreads();
+    stamp(2);
 
     // a generated (lazy-init) tile that does not hold the basis index is all zeros: every gate maps it to
     // itself, so only the one tile that owns the index runs the gates -- the others just write zeros
@@ -1169,12 +1185,14 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile_swz(const __grid_constant_
 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    stamp(3);
     for (uint32_t j = tid; j < n_chunks; j += kThreads) {
         const uint64_t g = base | chunk_offset(j, a.tile_ex, k, lc);
         tma_s2g_2d(&args.map, 0u, (uint32_t)(g >> kRowShift), tile_raw + (size_t)j * chunk_elems);
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    stamp(4);
 }
 
 // ---------------------------------------------------------------------------------------------------

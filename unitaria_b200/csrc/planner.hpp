@@ -488,7 +488,7 @@ inline void block_apply_gate(double* v, int kb, const uint8_t* q, const PGate& g
 inline void gate_sources(const Plan& plan, const PGate& g, std::vector<int>& out) {
     if (g.mux >= 0) out.insert(out.end(), plan.mux[g.mux].sources.begin(), plan.mux[g.mux].sources.end());
     else if (g.blk >= 0) out.insert(out.end(), plan.blocks[g.blk].sources.begin(), plan.blocks[g.blk].sources.end());
-    else out.push_back(g.src);
+    else if (g.src >= 0) out.push_back(g.src);  // (src < 0: a phase factored out of dense blocks, see fuse_blocks)
 }
 
 // FP64 work of a plain gate inside a register phase, in DFMA per 8 amplitudes (`common`: controls every gate of the
@@ -524,7 +524,21 @@ inline double gate_fp64_cost(const PGate& g, uint64_t common) {
 inline double block_fp64_cost(int kb, bool real) { return (kb == 3 ? 256.0 : 128.0) * (real ? 0.5 : 1.0) * fuse_margin() + 96.0; }
 
 // Build the dense matrix of G[a, b) on its <= 3 qubits and append the BLOCK gate to `out`.
-inline void emit_block(Plan& plan, const std::vector<PGate>& G, size_t a, size_t b, std::vector<PGate>& out) {
+// Largest imaginary residue (after dividing by the common phase) that is treated as rounding noise of the host-side
+// matrix product and dropped.  The residues of the BPX / Pseudoinverse blocks are <= 5e-16 (products of ~25 gates).
+inline double block_phase_tol() {
+    static const double v = [] {
+        const char* e = std::getenv("B2SV_BLOCK_PHASE_TOL");
+        return e ? std::atof(e) : 2e-15;
+    }();
+    return v;
+}
+
+// Returns the unit scalar factored out of the matrix in (*ph_re, *ph_im): a block whose entries are all real multiples
+// of ONE phase e^{i phi} (the cosine-sine two-qubit unitaries of circuits/generic_unitary.py are: 46 of the 50 complex
+// 4x4 blocks of BPX L=8, all 684 of Pseudoinverse(BPX L=4)) is stored as the real matrix -- half the FP64 work of the
+// pass -- and the phase is left to the caller, who merges the phases of a whole chain of blocks into one gate.
+inline void emit_block(Plan& plan, const std::vector<PGate>& G, size_t a, size_t b, std::vector<PGate>& out, double* ph_re, double* ph_im) {
     uint64_t K = G[a].ctrl, T = gate_targets(G[a]), U = G[a].ctrl;
     for (size_t q = a + 1; q < b; ++q) {
         K &= G[q].ctrl;
@@ -548,6 +562,34 @@ inline void emit_block(Plan& plan, const std::vector<PGate>& G, size_t a, size_t
             mat[2 * ((size_t)row * dim + col) + 1] = v[2 * row + 1];
         }
     }
+    *ph_re = 1.0;
+    *ph_im = 0.0;
+    {
+        bool real = true;
+        double best = 0.0, pr = 1.0, pi = 0.0;
+        for (size_t e = 0; e < (size_t)dim * dim; ++e) {
+            real = real && mat[2 * e + 1] == 0.0;
+            const double mag = std::hypot(mat[2 * e], mat[2 * e + 1]);
+            if (mag > best) {
+                best = mag;
+                pr = mat[2 * e] / mag;
+                pi = mat[2 * e + 1] / mag;
+            }
+        }
+        if (!real && best > 0.0) {
+            bool up_to_phase = true;  // every entry * conj(phase) is real (to rounding: the entries are <= 1 in magnitude)
+            for (size_t e = 0; e < (size_t)dim * dim && up_to_phase; ++e)
+                up_to_phase = std::fabs(mat[2 * e + 1] * pr - mat[2 * e] * pi) <= block_phase_tol();
+            if (up_to_phase) {
+                for (size_t e = 0; e < (size_t)dim * dim; ++e) {
+                    mat[2 * e] = mat[2 * e] * pr + mat[2 * e + 1] * pi;
+                    mat[2 * e + 1] = 0.0;
+                }
+                *ph_re = pr;
+                *ph_im = pi;
+            }
+        }
+    }
     while (plan.mux_tables.size() % 8) plan.mux_tables.push_back(0.0);  // keep multiplexor entries aligned
     info.mat_off = plan.mux_tables.size() / 2;
     plan.mux_tables.insert(plan.mux_tables.end(), mat.begin(), mat.end());
@@ -564,6 +606,98 @@ inline void emit_block(Plan& plan, const std::vector<PGate>& G, size_t a, size_t
     f.blk = (int)plan.blocks.size();
     plan.blocks.push_back(std::move(info));
     out.push_back(f);
+}
+
+// A dense-block pass is bound by its shared-memory round trip, not by its arithmetic (ncu on the BPX chains of 4x4
+// blocks: L1 data pipe 75 % busy, FP64 pipe 48 %; storing the blocks as real matrices -- half the DFMAs -- did not move
+// the time).  Two blocks under the same controls whose qubit sets overlap in one qubit ({1,5} then {1,7}: the chains
+// of circuits/generic_unitary.py alternate between two such families) cost the same arithmetic as ONE 8x8 block on the
+// union but half the round trips.  They are rarely adjacent in the gate list, so the DP cannot see them: this pass
+// moves a block up to an earlier one when every gate in between commutes with it for the plain reason that they share
+// no qubit (control-control overlaps are fine), and multiplies the two out.
+inline void merge_commuting_blocks(Plan& plan, std::vector<PGate>& L) {
+    static const bool disabled = std::getenv("B2SV_NO_BLOCK_MERGE") != nullptr;
+    if (disabled) return;
+    auto commutes = [](const PGate& g, const PGate& b) { return (g.qmask & b.tmask) == 0 && (g.tmask & b.qmask) == 0; };
+    for (size_t j = 1; j < L.size(); ++j) {
+        if (L[j].op != B2SV_OP_BLOCK) continue;
+        // walk back over commuting gates to the nearest earlier block that can absorb L[j]
+        for (size_t i = j; i-- > 0 && j - i <= 4096;) {
+            const PGate& cand = L[i];
+            if (cand.op == B2SV_OP_BLOCK && cand.ctrl == L[j].ctrl && popcount64(cand.tmask | L[j].tmask) <= kBlockMaxQubits &&
+                (cand.tmask & L[j].tmask) != 0) {
+                const BlockInfo a = plan.blocks[cand.blk], b = plan.blocks[L[j].blk];
+                const uint64_t B = cand.tmask | L[j].tmask;
+                BlockInfo info;
+                info.kb = popcount64(B);
+                int nb = 0;
+                for (int bit = 0; bit < 64; ++bit)
+                    if ((B >> bit) & 1) info.q[nb++] = (uint8_t)bit;
+                const int dim = 1 << info.kb;
+                auto apply = [&](const BlockInfo& blk, double* v) {  // v: 2^kb complex entries indexed by info.q
+                    int pos[3];
+                    for (int t = 0; t < blk.kb; ++t)
+                        for (int u = 0; u < info.kb; ++u)
+                            if (info.q[u] == blk.q[t]) pos[t] = u;
+                    const int bd = 1 << blk.kb;
+                    const double* M = plan.mux_tables.data() + 2 * blk.mat_off;
+                    double w[16];
+                    for (int rest = 0; rest < dim; ++rest) {
+                        bool base = true;
+                        for (int t = 0; t < blk.kb; ++t) base = base && !((rest >> pos[t]) & 1);
+                        if (!base) continue;
+                        int idx[8];
+                        for (int c = 0; c < bd; ++c) {
+                            idx[c] = rest;
+                            for (int t = 0; t < blk.kb; ++t)
+                                if ((c >> t) & 1) idx[c] |= 1 << pos[t];
+                        }
+                        for (int r = 0; r < bd; ++r) {
+                            double re = 0, im = 0;
+                            for (int c = 0; c < bd; ++c) {
+                                const double mr = M[2 * (r * bd + c)], mi = M[2 * (r * bd + c) + 1];
+                                re += mr * v[2 * idx[c]] - mi * v[2 * idx[c] + 1];
+                                im += mr * v[2 * idx[c] + 1] + mi * v[2 * idx[c]];
+                            }
+                            w[2 * r] = re;
+                            w[2 * r + 1] = im;
+                        }
+                        for (int r = 0; r < bd; ++r) {
+                            v[2 * idx[r]] = w[2 * r];
+                            v[2 * idx[r] + 1] = w[2 * r + 1];
+                        }
+                    }
+                };
+                std::vector<double> mat((size_t)2 * dim * dim, 0.0);
+                for (int col = 0; col < dim; ++col) {
+                    double v[16] = {0};
+                    v[2 * col] = 1.0;
+                    apply(a, v);
+                    apply(b, v);
+                    for (int row = 0; row < dim; ++row) {
+                        mat[2 * ((size_t)row * dim + col)] = v[2 * row];
+                        mat[2 * ((size_t)row * dim + col) + 1] = v[2 * row + 1];
+                    }
+                }
+                while (plan.mux_tables.size() % 8) plan.mux_tables.push_back(0.0);
+                info.mat_off = plan.mux_tables.size() / 2;
+                plan.mux_tables.insert(plan.mux_tables.end(), mat.begin(), mat.end());
+                info.sources = a.sources;
+                info.sources.insert(info.sources.end(), b.sources.begin(), b.sources.end());
+                PGate f = cand;
+                f.t0 = info.q[0];
+                f.tmask = B;
+                f.qmask = B | f.ctrl;
+                f.blk = (int)plan.blocks.size();
+                plan.blocks.push_back(std::move(info));
+                L[i] = f;
+                L.erase(L.begin() + (long)j);
+                --j;
+                break;
+            }
+            if (!commutes(cand, L[j])) break;
+        }
+    }
 }
 
 // The gate list is cut into pieces, each either left as plain gates (they ride in register phases) or multiplied out
@@ -613,12 +747,79 @@ inline void fuse_blocks(Plan& plan) {
     for (size_t p = N; p > 0; p = cut[p]) pieces.push_back({cut[p], p});
     std::vector<PGate> out;
     out.reserve(N);
+    // Phases factored out of blocks wait here, keyed by the blocks' shared controls K: a phase on the K-controlled
+    // subspace is diagonal, so it commutes with everything that does not act non-diagonally on a qubit of K and the
+    // phases of a chain of blocks under the same selector controls merge into ONE gate (emitted with src = -1: the
+    // blocks' source lists already stand for the whole unitaries).
+    struct Pending {
+        uint64_t K;
+        double re, im;
+    };
+    std::vector<Pending> pending;
+    auto emit_phase = [&](const Pending& ph) {
+        if (ph.re == 1.0 && ph.im == 0.0) return;
+        PGate f{};
+        f.op = B2SV_OP_PHASE;
+        f.t0 = f.t1 = 0;
+        f.ctrl = ph.K;
+        f.tmask = 0;
+        f.qmask = ph.K;
+        f.m[0] = ph.re;
+        f.m[1] = ph.im;
+        f.src = -1;
+        out.push_back(f);
+    };
+    auto flush_touching = [&](uint64_t nondiag) {
+        for (size_t i = 0; i < pending.size();) {
+            if (pending[i].K & nondiag) {
+                emit_phase(pending[i]);
+                pending.erase(pending.begin() + (long)i);
+            } else {
+                ++i;
+            }
+        }
+    };
     for (size_t k = pieces.size(); k-- > 0;) {
         const size_t a = pieces[k].first, b = pieces[k].second;
-        if (blk[b]) emit_block(plan, G, a, b, out);
-        else
-            for (size_t q = a; q < b; ++q) out.push_back(G[q]);
+        if (blk[b]) {
+            double pr = 1.0, pi = 0.0;
+            const size_t at = out.size();
+            emit_block(plan, G, a, b, out, &pr, &pi);
+            const PGate blockgate = out[at];
+            if (pr != 1.0 || pi != 0.0) {
+                if (blockgate.ctrl == 0) {  // unconditioned: a global phase, folded into the lazy scalar
+                    const double r = plan.scalar_re * pr - plan.scalar_im * pi, i = plan.scalar_re * pi + plan.scalar_im * pr;
+                    plan.scalar_re = r;
+                    plan.scalar_im = i;
+                } else {
+                    // the block itself may act on a qubit of an older pending phase's K: that phase goes in FRONT of it
+                    out.pop_back();
+                    flush_touching(blockgate.tmask);
+                    out.push_back(blockgate);
+                    bool merged = false;
+                    for (Pending& ph : pending)
+                        if (ph.K == blockgate.ctrl) {
+                            const double r = ph.re * pr - ph.im * pi, i = ph.re * pi + ph.im * pr;
+                            ph.re = r;
+                            ph.im = i;
+                            merged = true;
+                        }
+                    if (!merged) pending.push_back({blockgate.ctrl, pr, pi});
+                }
+            } else if (!pending.empty()) {
+                out.pop_back();
+                flush_touching(blockgate.tmask);
+                out.push_back(blockgate);
+            }
+        } else {
+            for (size_t q = a; q < b; ++q) {
+                if (!pending.empty()) flush_touching(G[q].tmask);
+                out.push_back(G[q]);
+            }
+        }
     }
+    for (const Pending& ph : pending) emit_phase(ph);
+    merge_commuting_blocks(plan, out);
     plan.gates.swap(out);
 }
 
