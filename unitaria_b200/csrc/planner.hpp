@@ -712,15 +712,21 @@ inline void fuse_blocks(Plan& plan) {
     const std::vector<PGate>& G = plan.gates;
     const size_t N = G.size();
     if (N == 0) return;
-    std::vector<double> dp(N + 1, 0.0);
-    std::vector<uint32_t> cut(N + 1, 0);
-    std::vector<char> blk(N + 1, 0);
+    // Two states per prefix: the last piece is a plain stretch (P) or a block (B).  A plain stretch that follows a block
+    // (or starts the list) opens a shared-memory pass of its own, like every block does: without that term the DP cut
+    // "block + one left-over gate" where one register phase does the same work in one round trip (config 2's sweeps).
+    const double inf = 1e300;
+    std::vector<double> dpP(N + 1, inf), dpB(N + 1, inf);
+    std::vector<uint32_t> cutB(N + 1, 0);
+    std::vector<char> fromB_P(N + 1, 0), fromB_B(N + 1, 0);  // predecessor state of the P / B state at p (1: block)
+    dpB[0] = 0.0;
     constexpr size_t kMaxBlockGates = 512;
+    constexpr double kPassCost = 96.0;
     for (size_t p = 1; p <= N; ++p) {
         const PGate& last = G[p - 1];
-        dp[p] = dp[p - 1] + gate_fp64_cost(last, 0);
-        cut[p] = (uint32_t)(p - 1);
-        blk[p] = 0;
+        const double open = dpB[p - 1] + kPassCost;  // (not scaled by the gate's controls: barrier + latency of a pass are fixed)
+        fromB_P[p] = open < dpP[p - 1] ? 1 : 0;
+        dpP[p] = gate_fp64_cost(last, 0) + (fromB_P[p] ? open : dpP[p - 1]);
         if (!blockable_gate(last)) continue;
         uint64_t K = last.ctrl, T = gate_targets(last), U = last.ctrl;
         bool nonperm = !last.is_perm(), real = gate_is_real(last);
@@ -735,16 +741,33 @@ inline void fuse_blocks(Plan& plan) {
             nonperm |= !g.is_perm();
             real = real && gate_is_real(g);
             if (p - q < 3 || kb < 2 || !nonperm) continue;
-            const double c = dp[q] + std::ldexp(block_fp64_cost(kb, real), -popcount64(K));
-            if (c < dp[p]) {
-                dp[p] = c;
-                cut[p] = (uint32_t)q;
-                blk[p] = 1;
+            const bool prevB = dpB[q] < dpP[q];
+            const double c = (prevB ? dpB[q] : dpP[q]) + std::ldexp(block_fp64_cost(kb, real), -popcount64(K));
+            if (c < dpB[p]) {
+                dpB[p] = c;
+                cutB[p] = (uint32_t)q;
+                fromB_B[p] = prevB ? 1 : 0;
             }
         }
     }
     std::vector<std::pair<size_t, size_t>> pieces;
-    for (size_t p = N; p > 0; p = cut[p]) pieces.push_back({cut[p], p});
+    std::vector<char> blk(N + 1, 0);
+    {
+        size_t p = N;
+        bool inB = dpB[N] < dpP[N];
+        while (p > 0) {
+            if (inB) {
+                pieces.push_back({cutB[p], p});
+                blk[p] = 1;
+                inB = fromB_B[p] != 0;
+                p = cutB[p];
+            } else {
+                pieces.push_back({p - 1, p});
+                inB = fromB_P[p] != 0;
+                p = p - 1;
+            }
+        }
+    }
     std::vector<PGate> out;
     out.reserve(N);
     // Phases factored out of blocks wait here, keyed by the blocks' shared controls K: a phase on the K-controlled
