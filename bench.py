@@ -476,16 +476,38 @@ def run_single(args):
         for j in in_list[args.warmup : args.warmup + e2e_steps]:
             out = adapter.simulate_projected(Circuit, n, prog, norm, j)
         e2e_s = time.perf_counter() - t0
+        sv_e2e = adapter._state(n)
+        d2h = int(getattr(sv_e2e, "last_d2h_bytes", out.nbytes))
         e2e = {
             "value": gates_live * e2e_steps / e2e_s,
             "unit": "gates/s",
             "h2d_bytes_per_step": int(lowered.nbytes + 96 * len(lowered)),
-            "d2h_bytes_per_step": int(out.nbytes),
+            "d2h_bytes_per_step": d2h,
+            "result_bytes_on_host": int(out.nbytes),
             "steps": e2e_steps,
             "ms_per_step": 1e3 * e2e_s / e2e_steps,
             "call": "unitaria_b200.simulate_projected(circuit, n_qubits, subspace_out, normalization, j) -> host complex128[dim_out] "
-            "(= Node.simulate(j)); H2D = lowered gate program, D2H = projected vector",
+            "(= Node.simulate(j)); H2D = lowered gate program, D2H = the projected vector -- as (rank, value) pairs of its non-zeros "
+            "when they are few (b2sv_project_gather_sparse; the dense array is assembled on the host), else the whole array",
         }
+        # the same call with the compact form switched off: the whole dim_out array crosses PCIe (what a dense column costs)
+        saved_min = type(sv_e2e).SPARSE_MIN_DIM
+        type(sv_e2e).SPARSE_MIN_DIM = 1 << 62
+        try:
+            for j in in_list[:3]:  # warm: two page-locked 1 GiB result buffers end up in the pool
+                out = adapter.simulate_projected(Circuit, n, prog, norm, j)
+            t0 = time.perf_counter()
+            for j in in_list[args.warmup : args.warmup + e2e_steps]:
+                out = adapter.simulate_projected(Circuit, n, prog, norm, j)
+            dense_s = time.perf_counter() - t0
+            e2e["dense_copy"] = {
+                "value": gates_live * e2e_steps / dense_s,
+                "unit": "gates/s",
+                "ms_per_step": 1e3 * dense_s / e2e_steps,
+                "d2h_bytes_per_step": int(out.nbytes),
+            }
+        finally:
+            type(sv_e2e).SPARSE_MIN_DIM = saved_min
         # matrix case of Node.simulate (node.py:381-388): columns pipelined, the D2H of column j overlaps column j+1
         if hasattr(adapter, "simulate_columns"):
             cols = in_list[args.warmup : args.warmup + e2e_steps]
@@ -498,7 +520,7 @@ def run_single(args):
                 "unit": "gates/s",
                 "ms_per_column": 1e3 * pipe_s / len(cols),
                 "columns": len(cols),
-                "call": "unitaria_b200.simulate_columns(...): same host result per column, double-buffered D2H on a second stream",
+                "call": "unitaria_b200.simulate_columns(...): same host result per column; compact form when the column is sparse, else double-buffered D2H on a second stream",
             }
     adapter.clear_caches()
 

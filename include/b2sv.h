@@ -153,6 +153,14 @@ int b2sv_project_norm2_at(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, in
  * (= Subspace.enumerate_basis order, subspace.py:325-329); `dim` must equal the subspace dimension. */
 int b2sv_project_gather(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
                         double scale_re, double scale_im, void* host_out_c128, uint64_t dim);
+/* Sparse form of the same result (replaces the dense `normalization * subspace_out.project(...)` array of
+ * nodes/node.py:377-379 when almost all of it is zeros -- a column of the Laplacian block encoding has three non-zeros out
+ * of 2^26): up to `cap` pairs (rank, value) of the NON-ZERO projected amplitudes, in no particular order.  *nnz_out is the
+ * number of pairs written; *nnz_out >= cap means "too many, the lists are incomplete -- use b2sv_project_gather".  Only
+ * 8 + 24 * nnz bytes cross PCIe. */
+int b2sv_project_gather_sparse(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
+                               double scale_re, double scale_im, uint64_t dim, uint64_t cap, uint64_t* idx_out,
+                               void* val_out_c128, uint64_t* nnz_out);
 /* Pipelined form for callers that run one circuit on many inputs (the matrix case of Node.simulate,
  * nodes/node.py:381-388; verify, verifier.py:119-126): the gather lands in one of two device buffers (`slot` 0/1)
  * and is copied to `host_out` (page-locked memory for a real overlap) by a second stream, so the call returns at

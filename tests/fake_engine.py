@@ -142,6 +142,15 @@ class FakeStateVector:
         prog = subspace if isinstance(subspace, SubspaceProgram) else SubspaceProgram(subspace)
         return complex(scale) * self.psi[self._members(prog)]
 
+    SPARSE_MIN_DIM = 1 << 16
+
+    def project_sparse(self, subspace, scale=1.0):
+        dense = self.project(subspace, scale)
+        nz = np.flatnonzero(dense)
+        if len(nz) >= max(len(dense) >> 6, 1024):
+            return None
+        return nz.astype(np.uint64), dense[nz]
+
     def project_norm2(self, subspace):
         prog = subspace if isinstance(subspace, SubspaceProgram) else SubspaceProgram(subspace)
         return float(np.sum(np.abs(self.psi[self._members(prog)]) ** 2))

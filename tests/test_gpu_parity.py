@@ -501,3 +501,50 @@ def test_device_resident_chaining_and_pipelined_columns():
     want = adapter.simulate_projected(C, n, spec, norm, psi0).copy()
     got = adapter.simulate_projected(C, n, spec, norm, torch.as_tensor(psi0, device="cuda:0"), out="device")
     assert np.abs(got.cpu().numpy() - want).max() < 1e-14
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("name", ["laplace_n16", "laplace_n20", "cfg5_bits13"])
+def test_sparse_projection_equals_dense(name, dtype):
+    """b2sv_project_gather_sparse lists exactly the non-zeros of b2sv_project_gather (bit for bit), project() assembles
+    the same dense array from them, and a dense state makes the compact form step aside (nnz >= cap -> None)."""
+    case = load_golden(name)
+    n, norm = case.n_qubits, case.meta["normalization"]
+    prog = SubspaceProgram(case.meta["subspace_out"])
+    low = lower_gates(case.gates, n)
+    with StateVector(n, dtype) as sv:
+        for b in (0, 5):
+            sv.set_basis(b)
+            sv.apply_lowered(low)
+            saved = StateVector.SPARSE_MIN_DIM
+            StateVector.SPARSE_MIN_DIM = 1 << 62
+            try:
+                dense = sv.project(prog, scale=norm).copy()
+                assert sv.last_d2h_bytes == 16 * prog.dimension
+            finally:
+                StateVector.SPARSE_MIN_DIM = saved
+            pairs = sv.project_sparse(prog, scale=norm)
+            assert pairs is not None, "a basis-state column of these block encodings has few non-zeros"
+            idx, val = pairs
+            order = np.argsort(idx)
+            want = np.flatnonzero(dense)
+            assert np.array_equal(idx[order].astype(np.int64), want)
+            assert np.array_equal(val[order], dense[want])
+            StateVector.SPARSE_MIN_DIM = 1
+            try:
+                again = sv.project(prog, scale=norm)
+                assert sv.last_d2h_bytes == 8 + 24 * len(want)
+            finally:
+                StateVector.SPARSE_MIN_DIM = saved
+            assert np.array_equal(again, dense)
+        rng = np.random.default_rng(11)
+        sv.upload(random_state(n, rng))
+        assert sv.project_sparse("#" * n) is None
+        StateVector.SPARSE_MIN_DIM = 1
+        try:
+            full = sv.project("#" * n)
+            assert sv.last_d2h_bytes == 16 * 2**n and np.array_equal(full, sv.download())
+            sv.project("#" * n)  # (the handle skips the compact attempt for a while after a dense result)
+            assert sv.last_d2h_bytes == 16 * 2**n
+        finally:
+            StateVector.SPARSE_MIN_DIM = saved

@@ -149,8 +149,9 @@ def simulate_columns(tq_circuit, n_qubits: int, subspace_out, normalization, inp
         return [simulate_projected(tq_circuit, n_qubits, prog, normalization, b) for b in inputs]
     sv = _state(n_qubits)
     low = _lowered(tq_circuit, n_qubits)
-    ring = [PINNED.array(prog.dimension, np.complex128) for _ in range(2)] if not keep else None
+    ring = None  # keep=False: two recycled page-locked buffers, allocated when the first dense column shows up
     results = []
+    sparse_skip = 0  # columns to send densely without trying the compact form (after a column turned out dense)
     for k, b in enumerate(inputs):
         slot = k & 1
         sv.gather_wait(slot)  # column k-2 has landed (its buffer may be recycled)
@@ -159,6 +160,18 @@ def simulate_columns(tq_circuit, n_qubits: int, subspace_out, normalization, inp
         else:
             sv.set_basis(int(b))
         sv.apply_lowered(low, _DEFAULTS["opts"])
+        if prog.dimension >= sv.SPARSE_MIN_DIM and sparse_skip == 0:
+            pairs = sv.project_sparse(prog, normalization)  # a handful of non-zeros: nothing worth pipelining
+            if pairs is not None:
+                out = np.zeros(prog.dimension, dtype=np.complex128)
+                out[pairs[0]] = pairs[1]
+                results.append(out)
+                continue
+            sparse_skip = 8
+        elif sparse_skip:
+            sparse_skip -= 1
+        if not keep and ring is None:
+            ring = [PINNED.array(prog.dimension, np.complex128) for _ in range(2)]
         out = ring[slot] if ring is not None else PINNED.array(prog.dimension, np.complex128)
         sv.project_async(prog, normalization, out, slot)
         results.append(out)

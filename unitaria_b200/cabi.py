@@ -132,6 +132,10 @@ SYMBOLS = {
         ctypes.c_int,
         [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, _P, ctypes.c_uint64],
     ),
+    "b2sv_project_gather_sparse": (
+        ctypes.c_int,
+        [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_uint64, ctypes.c_uint64, _P, _P, ctypes.POINTER(ctypes.c_uint64)],
+    ),
     "b2sv_project_gather_async": (
         ctypes.c_int,
         [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, _P, ctypes.c_uint64, ctypes.c_int],

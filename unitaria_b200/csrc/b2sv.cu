@@ -1402,6 +1402,58 @@ int b2sv_project_gather(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int 
     return B2SV_OK;
 }
 
+int b2sv_project_gather_sparse(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
+                               double scale_re, double scale_im, uint64_t dim, uint64_t cap, uint64_t* idx_out, void* val_out,
+                               uint64_t* nnz_out) {
+    if (int rc = check(sv)) return rc;
+    if (!nnz_out || (cap > 0 && (!idx_out || !val_out))) return fail(B2SV_EINVAL, "null output");
+    *nnz_out = 0;
+    CU(cudaSetDevice(sv->device));
+    if (int rc = materialise(sv)) return rc;
+    int count_bits = 0;
+    uint64_t head_zeros = 0;
+    if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits, -1, nullptr, &head_zeros)) return rc;
+    if (dim == 0) return B2SV_OK;
+    if (cap == 0) {
+        *nnz_out = 1;  // ">= cap": nothing can be listed
+        return B2SV_OK;
+    }
+    const bool grouped = head_zeros == 0 && low_free_bits(prog, entry) >= kProjectGroupBits && (1ull << count_bits) >= (uint64_t)kProjectWarpSpan;
+    ExpandArgs scan{};
+    if (!grouped) fill_expand(scan, head_zeros);
+    const uint64_t cnt = 1ull << (count_bits - scan.m);
+    // device layout: values (cap * 16 B) | indices (cap * 8 B) | count (8 B)
+    if (int rc = ensure_gather(sv, cap * 24 + 8)) return rc;
+    double2* d_val = (double2*)sv->d_gather;
+    SparseOut sp;
+    sp.idx = reinterpret_cast<unsigned long long*>(d_val + cap);
+    sp.count = sp.idx + cap;
+    sp.cap = cap;
+    CU(cudaMemsetAsync(sp.count, 0, 8, sv->stream));
+    const double2 s = make_double2(scale_re * sv->sre - scale_im * sv->sim, scale_re * sv->sim + scale_im * sv->sre);
+    dispatch_dtype(sv, [&](auto* tag) -> int {
+        using A = std::remove_pointer_t<decltype(tag)>;
+        LaunchTimer lt(sv, sv->timing_on, CLS_PROJECT, (double)sv->amp_bytes * std::min((double)cnt, (double)dim));
+        if (grouped)
+            k_project_gather<A, true, true><<<grid_for(sv, cnt >> kProjectGroupBits), kThreads, 0, sv->stream>>>(
+                (const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, s, d_val, dim, prog[entry].weight, scan, sp);
+        else
+            k_project_gather<A, false, true><<<grid_for(sv, cnt), kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, entry,
+                                                                                           n_instr + 1, s, d_val, dim, 0, scan, sp);
+        return B2SV_OK;
+    });
+    CU(cudaGetLastError());
+    unsigned long long n = 0;
+    CU(cudaMemcpyAsync(&n, sp.count, 8, cudaMemcpyDeviceToHost, sv->stream));
+    CU(cudaStreamSynchronize(sv->stream));
+    *nnz_out = n;
+    if (n == 0 || n >= cap) return B2SV_OK;
+    CU(cudaMemcpyAsync(idx_out, sp.idx, n * 8, cudaMemcpyDeviceToHost, sv->stream));
+    CU(cudaMemcpyAsync(val_out, d_val, n * 16, cudaMemcpyDeviceToHost, sv->stream));
+    CU(cudaStreamSynchronize(sv->stream));
+    return B2SV_OK;
+}
+
 int b2sv_project_gather_async(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
                               double scale_re, double scale_im, void* host_out, uint64_t dim, int slot) {
     if (int rc = check(sv)) return rc;

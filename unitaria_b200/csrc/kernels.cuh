@@ -1773,11 +1773,30 @@ __global__ void __launch_bounds__(kThreads) k_reduce_partials(const double* __re
     if (threadIdx.x == 0) *out = red[0];
 }
 
-template <typename A, bool GROUPED>
+// SPARSE: instead of filling a dense result, append (rank, value) of every NON-ZERO projected amplitude to a compact list
+// (b2sv_project_gather_sparse): a column of a block encoding often has a handful of non-zeros out of 2^26 (three for the
+// Laplacian), and hauling the zeros over PCIe was 80 % of an end-to-end Node.simulate call.  Once the list is full the
+// threads stop taking slots (the host sees count >= cap and falls back to the dense path).
+struct SparseOut {
+    unsigned long long* count;
+    unsigned long long cap;
+    unsigned long long* idx;
+};
+__device__ __forceinline__ void sparse_emit(const SparseOut& sp, double2* __restrict__ val, uint64_t r, double2 v) {
+    if (v.x == 0.0 && v.y == 0.0) return;
+    if (*reinterpret_cast<volatile unsigned long long*>(sp.count) >= sp.cap) return;
+    const unsigned long long pos = atomicAdd(sp.count, 1ull);
+    if (pos < sp.cap) {
+        sp.idx[pos] = r;
+        val[pos] = v;
+    }
+}
+
+template <typename A, bool GROUPED, bool SPARSE = false>
 __global__ void __launch_bounds__(kThreads) k_project_gather(const A* __restrict__ psi, const b2sv_subinstr* __restrict__ sub,
                                                              uint64_t count, int entry, int max_steps,
                                                              double2 scale, double2* __restrict__ out, uint64_t dim, uint64_t weight,
-                                                             const ExpandArgs scan) {
+                                                             const ExpandArgs scan, const SparseOut sp = SparseOut{nullptr, 0, nullptr}) {
     if (GROUPED) {
         const int lane = threadIdx.x & 31;
         const uint64_t warps = (uint64_t)gridDim.x * (kThreads / 32);
@@ -1794,7 +1813,11 @@ __global__ void __launch_bounds__(kThreads) k_project_gather(const A* __restrict
                 const unsigned long long rg = __shfl_sync(0xffffffffu, (unsigned long long)r, group);
                 if ((members >> group) & 1u) {
                     const uint64_t rr = rg + (uint64_t)(lane & 7) * weight;
-                    if (rr < dim) out[rr] = cmul(scale, to_c128(psi[base + (uint64_t)(j * 32 + lane)]));
+                    if (rr < dim) {
+                        const double2 v = cmul(scale, to_c128(psi[base + (uint64_t)(j * 32 + lane)]));
+                        if (SPARSE) sparse_emit(sp, out, rr, v);
+                        else out[rr] = v;
+                    }
                 }
             }
         }
@@ -1803,7 +1826,11 @@ __global__ void __launch_bounds__(kThreads) k_project_gather(const A* __restrict
         for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
             const uint64_t i = expand_bits(k, scan);
             uint64_t r;
-            if (sub_member_rank(sub, entry, max_steps, i, r) && r < dim) out[r] = cmul(scale, to_c128(psi[i]));
+            if (sub_member_rank(sub, entry, max_steps, i, r) && r < dim) {
+                const double2 v = cmul(scale, to_c128(psi[i]));
+                if (SPARSE) sparse_emit(sp, out, r, v);
+                else out[r] = v;
+            }
         }
     }
 }

@@ -949,6 +949,36 @@ inline void plan_tiles(const std::vector<PGate>& G, const std::vector<int>& idx,
 
 // ---- whole plan -------------------------------------------------------------------------------
 
+// Inside a sweep the op program pays per PASS (a shared-memory round trip), and a pass is a run of like gates: a
+// monomial phase takes any number of consecutive X / SWAP / phase gates, a register phase consecutive plain gates on <=
+// 3 targets.  The arithmetic-plus-rotation stretches of the QSVT circuits alternate the two kinds gate by gate (a
+// 41-gate sweep of Pseudoinverse(BPX) became 15 passes, 3.7 x its HBM time), although most neighbours commute for the
+// plain reason that neither acts non-diagonally on a qubit the other touches.  This pass moves every gate back over such
+// commuting neighbours to the nearest earlier gate of its own kind, so the kinds cluster and the runs get long.
+inline void cluster_commuting(const std::vector<PGate>& G, Segment& seg) {
+    static const bool disabled = std::getenv("B2SV_NO_CLUSTER") != nullptr;
+    if (disabled || seg.gates.size() < 3) return;
+    auto kind = [&](const PGate& g) { return (g.op == B2SV_OP_X || g.op == B2SV_OP_SWAP || g.op == B2SV_OP_PHASE || g.op == B2SV_OP_DIAG1) ? 0 : 1; };
+    auto commutes = [](const PGate& g, const PGate& h) { return (g.tmask & h.qmask) == 0 && (h.tmask & g.qmask) == 0; };
+    std::vector<int> out;
+    out.reserve(seg.gates.size());
+    for (int gi : seg.gates) {
+        const PGate& g = G[gi];
+        const int kg = kind(g);
+        size_t at = out.size();
+        for (size_t k = out.size(); k-- > 0 && out.size() - k <= 256;) {
+            const PGate& h = G[out[k]];
+            if (kind(h) == kg) {
+                at = k + 1;
+                break;
+            }
+            if (!commutes(g, h)) break;
+        }
+        out.insert(out.begin() + (long)at, gi);
+    }
+    seg.gates.swap(out);
+}
+
 inline Plan make_plan(const b2sv_gate* gates, size_t n_gates, const PlanConfig& cfg, bool scratch_available) {
     Plan plan;
     plan.gates_in = n_gates;
@@ -1126,6 +1156,8 @@ inline Plan make_plan(const b2sv_gate* gates, size_t n_gates, const PlanConfig& 
         }
     }
     flush_stretch();
+    for (Segment& seg : plan.segs)
+        if (seg.cls == SEG_TILE) cluster_commuting(plan.gates, seg);
     return plan;
 }
 
