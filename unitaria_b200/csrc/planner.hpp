@@ -721,7 +721,7 @@ inline void fuse_blocks(Plan& plan) {
     std::vector<char> fromB_P(N + 1, 0), fromB_B(N + 1, 0);  // predecessor state of the P / B state at p (1: block)
     dpB[0] = 0.0;
     constexpr size_t kMaxBlockGates = 512;
-    constexpr double kPassCost = 96.0;
+    static const double kPassCost = [] { const char* e = std::getenv("B2SV_PASS_COST"); return e ? std::atof(e) : 48.0; }();  // A/B over 0/24/48/96: 96 cost the Pseudoinverse 3 %
     for (size_t p = 1; p <= N; ++p) {
         const PGate& last = G[p - 1];
         const double open = dpB[p - 1] + kPassCost;  // (not scaled by the gate's controls: barrier + latency of a pass are fixed)
