@@ -432,3 +432,59 @@ extern "C" int emul_block_stats(int n, int dtype, const b2sv_gate* gates, size_t
     }
     return m;
 }
+
+// Like emul_describe_segment, with the qubits each pass works on: {kind, detail, target-qubit mask lo, hi, control-qubit mask lo, hi}.
+extern "C" int emul_describe_segment_qubits(int n, int dtype, const b2sv_gate* gates, size_t n_gates, const b2sv_plan_opts* opts, int seg_index,
+                                            int64_t* out, int cap) {
+    PlanConfig cfg = default_config(n, dtype, opts);
+    if (n < 13) cfg.perm_runs = false;
+    Plan plan = make_plan(gates, n_gates, cfg, true);
+    if (seg_index < 0 || seg_index >= (int)plan.segs.size()) return -1;
+    const Segment& seg = plan.segs[seg_index];
+    if (seg.cls != SEG_TILE && seg.cls != SEG_LOW6) return 0;
+    std::vector<TileOp> ops;
+    build_segment_ops(plan, seg, cfg, ops);
+    ExpandArgs ex;
+    fill_expand(ex, seg.tile_mask);
+    auto qmask_of = [&](uint32_t local) {
+        uint64_t q = 0;
+        for (int i = 0; i < ex.m; ++i)
+            if ((local >> i) & 1u) q |= 1ull << ex.pos[i];
+        return q;
+    };
+    auto targets_of = [&](const TileOp& op) -> uint32_t {
+        uint32_t t = 0;
+        if (op.op == kOpBlock) {
+            for (int i = 0; i < op.blk.kb; ++i) t |= 1u << op.blk.bpos[i];
+        } else if (op.op != B2SV_OP_PHASE && op.op <= kOpMux) {
+            if (op.tpos != 0xFF) t |= 1u << op.tpos;
+            if (op.op == B2SV_OP_SWAP) t |= 1u << op.tpos2;
+        }
+        return t;
+    };
+    int m = 0;
+    for (size_t o = 0; o < ops.size() && 4 * m + 3 < cap; ++o) {
+        const TileOp& op = ops[o];
+        int detail = 0;
+        uint64_t tq = 0, cq = 0;
+        if (op.op == kOpPhase) {
+            detail = op.ph.count;
+            for (int i = 0; i < 3; ++i) tq |= qmask_of(1u << op.ph.rpos[i]);
+            cq = qmask_of(op.lctrl);
+        } else if (op.op == kOpMono) {
+            detail = op.mono.fac * 100 + op.mono.ebits;
+            tq = qmask_of(op.mono.tmask | op.mono.qlmask);
+        } else {
+            detail = op.op == kOpBlock ? op.blk.kb : (op.op == kOpMux ? op.mux.nmux : __builtin_popcount(op.lctrl));
+            tq = qmask_of(targets_of(op));
+            cq = qmask_of(op.lctrl) | op.ext_ctrl;
+        }
+        out[4 * m] = op.op;
+        out[4 * m + 1] = detail;
+        out[4 * m + 2] = (int64_t)tq;
+        out[4 * m + 3] = (int64_t)cq;
+        ++m;
+        if (op.op == kOpPhase) o += op.ph.count;
+    }
+    return m;
+}

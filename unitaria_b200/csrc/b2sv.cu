@@ -866,7 +866,7 @@ double subprog_members(const b2sv_subinstr* prog, int n_instr, int entry) {
 }
 
 int upload_subprog(b2sv* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits, int* count_bits,
-                   int max_target_qubits = -1, bool* full_cover = nullptr, uint64_t* head_zeros = nullptr) {
+                   int max_target_qubits = -1, bool* full_cover = nullptr, uint64_t* head_zeros = nullptr, bool* pure = nullptr) {
     if (max_target_qubits < 0) max_target_qubits = sv->n;
     if (!prog || n_instr <= 0) return fail(B2SV_EINVAL, "empty subspace program");
     if (n_instr > kMaxSubInstr) return fail(B2SV_EINVAL, "subspace program has %d instructions (max %d)", n_instr, kMaxSubInstr);
@@ -903,6 +903,8 @@ int upload_subprog(b2sv* sv, const b2sv_subinstr* prog, int n_instr, int entry, 
         }
         while (bits > 0 && ((zero_mask >> (bits - 1)) & 1)) --bits;
         if (head_zeros) *head_zeros = zero_mask & low_mask(bits);
+        // branch-free program: the straight-line head runs into END, so membership IS "the always-zero bits are clear"
+        if (pure) *pure = prog[pc].op == B2SV_SUB_END;
     }
     if (count_bits) *count_bits = bits;
     if (n_instr > sv->d_sub_cap) {
@@ -1320,26 +1322,31 @@ int b2sv_project_norm2_at(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, in
     int count_bits = 0;
     bool full_cover = false;
     uint64_t head_zeros = 0;
-    if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits, 64, &full_cover, &head_zeros)) return rc;
+    bool pure = false;
+    if (int rc = upload_subprog(sv, prog, n_instr, entry, target_qubits, &count_bits, 64, &full_cover, &head_zeros, &pure)) return rc;
     if (target_qubits < 64 && (index_base >> target_qubits) != 0) {  // this shard holds ancilla != 0 only
         *out = 0.0;
         return B2SV_OK;
     }
     if (count_bits > sv->n) count_bits = sv->n;
     head_zeros &= low_mask(count_bits);
-    const bool grouped = head_zeros == 0 && low_free_bits(prog, entry) >= kProjectGroupBits && (1ull << count_bits) >= (uint64_t)kProjectWarpSpan;
+    static const bool no_scan_kernel = std::getenv("B2SV_NO_NORM_SCAN") != nullptr;
+    if (no_scan_kernel) pure = false;
+    const bool grouped = !pure && head_zeros == 0 && low_free_bits(prog, entry) >= kProjectGroupBits && (1ull << count_bits) >= (uint64_t)kProjectWarpSpan;
     ExpandArgs scan{};
     if (!grouped) fill_expand(scan, head_zeros);
     // grouped: the whole range; else only the indices whose always-zero bits are clear
     const uint64_t cnt = 1ull << (count_bits - scan.m);
-    const int grid = grid_for(sv, grouped ? cnt >> kProjectGroupBits : cnt);
+    const int grid = grid_for(sv, grouped ? cnt >> kProjectGroupBits : (pure ? (cnt + 7) / 8 : cnt));
     int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
         using A = std::remove_pointer_t<decltype(tag)>;
         // algorithmic bytes: the member amplitudes (what has to be read), never more than the scanned range
         // (per-rank specialised programs do not mention their free bits: book the scanned range for those)
         const double members = (sv->timing_on && full_cover) ? std::min((double)cnt, subprog_members(prog, n_instr, entry)) : (double)cnt;
         LaunchTimer lt(sv, sv->timing_on, CLS_PROJECT, (double)sv->amp_bytes * members);
-        if (grouped)
+        if (pure)  // branch-free subspace: a strided streaming reduction, no membership walk
+            k_norm2_scan<A><<<grid, kThreads, 0, sv->stream>>>((const A*)sv->amps, cnt, sv->d_partial, scan);
+        else if (grouped)
             k_project_norm2<A, true><<<grid, kThreads, 0, sv->stream>>>((const A*)sv->amps, sv->d_sub, cnt, entry, n_instr + 1, index_base,
                                                                        sv->d_partial, scan);
         else

@@ -1760,6 +1760,42 @@ __global__ void __launch_bounds__(kThreads) k_project_norm2(const A* __restrict_
 }
 
 // deterministic final reduction of the per-block partial sums (one block)
+// Post-selection norm of a BRANCH-FREE subspace ("0" on some qubits, "#" on the rest: every from_dim window, every
+// one-ancilla block encoding, every per-rank program of such a subspace): the members are exactly the indices whose
+// always-zero bits are clear, so no membership walk is needed at all -- a strided streaming reduction with eight loads in
+// flight per thread.  (The general kernel walks the decision program per index or per group of 8 and was walk-bound on
+// these: 2.5-3.4 TB/s for a 30-qubit register with one ancilla anywhere but at the top, scripts/microbench_project.py.)
+template <typename A>
+__global__ void __launch_bounds__(kThreads) k_norm2_scan(const A* __restrict__ psi, uint64_t count, double* __restrict__ partial,
+                                                         const ExpandArgs scan) {
+    double acc = 0.0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; k + 7 * stride < count; k += 8 * stride) {
+        A v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = psi[expand_bits(k + (uint64_t)u * stride, scan)];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double2 w = to_c128(v[u]);
+            acc = fma(w.x, w.x, fma(w.y, w.y, acc));
+        }
+    }
+    for (; k < count; k += stride) {
+        const double2 w = to_c128(psi[expand_bits(k, scan)]);
+        acc = fma(w.x, w.x, fma(w.y, w.y, acc));
+    }
+    __shared__ double red[kThreads / 32];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < kThreads / 32 ? red[threadIdx.x] : 0.0;
+        for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) partial[blockIdx.x] = v;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) k_reduce_partials(const double* __restrict__ partial, int n, double* out) {
     __shared__ double red[kThreads];
     double acc = 0.0;
