@@ -341,10 +341,28 @@ struct TileView {
 // instructions per fixed position per element, a quarter of the instructions of a dense-block pass.
 __device__ __forceinline__ uint32_t subset_next(uint32_t cur, uint32_t mask) { return ((cur | ~mask) + 1u) & mask; }
 
+// Bank-conflict-free lane assignment.  The lanes of one shared-memory phase (8 lanes for 16-byte accesses, 16 for 8-byte
+// ones) differ in the LOWEST bits of the thread number, which the enumeration deposits into the lowest free tile
+// positions.  With the 128-byte swizzle a position p < 6 moves the 16-byte bank group by bit (p mod 3): positions 0 and 3
+// (1 and 4, 2 and 5) collide, so free positions {0, 2, 3} under the three lowest lane bits give a 2-way conflict on every
+// access of the pass (ncu on the 8x8 block passes of BPX: twice the ideal shared-memory wavefronts, L1 data pipe 85 %
+// busy).  The host picks, per op, free positions with DISTINCT bank-group bits for those lane bits (tileops.hpp:
+// assign_lane_swaps) and passes the choice as up to four bit swaps of the thread number (6 bits each: a, b).
+__device__ __forceinline__ uint32_t lane_swaps(uint32_t t, uint32_t code) {
+    if (code == 0u) return t;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const uint32_t a = (code >> (6 * s)) & 7u, b = (code >> (6 * s + 3)) & 7u;
+        const uint32_t d = ((t >> a) ^ (t >> b)) & 1u;
+        t ^= (d << a) | (d << b);
+    }
+    return t;
+}
+
 // The body gets SWIZZLED element indices (TileView::raw).
 template <int UNROLL, typename TV, typename F>
-__device__ __forceinline__ void tile_for_each(TV tile, uint32_t cnt, uint64_t fixpos, int nfix, uint32_t lctrl, F&& body) {
-    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+__device__ __forceinline__ void tile_for_each(TV tile, uint32_t cnt, uint64_t fixpos, int nfix, uint32_t lctrl, uint32_t swaps, F&& body) {
+    const uint32_t tid = lane_swaps(threadIdx.x, swaps), nt = blockDim.x;
     if (tid >= cnt) return;
     const uint32_t lt = tile.swz(expand_local(tid, fixpos, nfix) | lctrl);
     const uint32_t himask = cnt > nt ? expand_local((cnt - 1u) & ~(nt - 1u), fixpos, nfix) : 0u;
@@ -371,8 +389,8 @@ __device__ __forceinline__ void tile_for_each(TV tile, uint32_t cnt, uint64_t fi
 // The bit-by-bit form (every element deposited on its own): kept for the dense-block passes, whose bodies sit at the
 // register limit -- the three extra live values of the stepped form made ptxas spill 1.2 KB per thread there.
 template <int UNROLL, typename TV, typename F>
-__device__ __forceinline__ void tile_for_each_deposit(TV tile, uint32_t cnt, uint64_t fixpos, int nfix, uint32_t lctrl, F&& body) {
-    uint32_t p = threadIdx.x;
+__device__ __forceinline__ void tile_for_each_deposit(TV tile, uint32_t cnt, uint64_t fixpos, int nfix, uint32_t lctrl, uint32_t swaps, F&& body) {
+    uint32_t p = lane_swaps(threadIdx.x, swaps);
     const uint32_t nt = blockDim.x;
     for (; p + (UNROLL - 1) * nt < cnt; p += UNROLL * nt) {
         uint32_t l[UNROLL];
@@ -427,7 +445,7 @@ __device__ __forceinline__ void tile_block_pass(TV tile, const TileOp& op, int k
     const uint32_t cnt = 1u << (k - op.nfix);
     if (KB == 3) {
         const uint32_t b0 = tile.swz(1u << op.blk.bpos[0]), b1 = tile.swz(1u << op.blk.bpos[1]), b2 = tile.swz(1u << op.blk.bpos[2]);
-        tile_for_each_deposit<1>(tile, cnt, op.fixpos, op.nfix, op.lctrl, [&](const uint32_t* l, int) {
+        tile_for_each_deposit<1>(tile, cnt, op.fixpos, op.nfix, op.lctrl, (uint32_t)op.ext_tbit, [&](const uint32_t* l, int) {
             uint32_t off[8];
             C v[8];
 #pragma unroll
@@ -451,7 +469,7 @@ __device__ __forceinline__ void tile_block_pass(TV tile, const TileOp& op, int k
         });
     } else {  // KB == 2
         const uint32_t b0 = tile.swz(1u << op.blk.bpos[0]), b1 = tile.swz(1u << op.blk.bpos[1]);
-        tile_for_each_deposit<1>(tile, cnt, op.fixpos, op.nfix, op.lctrl, [&](const uint32_t* l, int) {
+        tile_for_each_deposit<1>(tile, cnt, op.fixpos, op.nfix, op.lctrl, (uint32_t)op.ext_tbit, [&](const uint32_t* l, int) {
             uint32_t off[4];
             C v[4], acc[4];
 #pragma unroll
@@ -522,10 +540,12 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
     const uint64_t fixpos = op.fixpos;
     const int nfix = op.nfix;
     const uint32_t lctrl = op.lctrl;
+    // lane assignment of this op (a DIAG1 whose target lies outside the tile keeps that target's bit in ext_tbit instead)
+    const uint32_t swaps = (op.op == B2SV_OP_DIAG1 && op.tpos == 0xFF) ? 0u : (uint32_t)op.ext_tbit;
     switch (op.op) {
         case B2SV_OP_X: {
             const uint32_t bt = tile.swz(1u << op.tpos);
-            tile_for_each<4>(tile, cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
+            tile_for_each<4>(tile, cnt, fixpos, nfix, lctrl, swaps, [&](const uint32_t* l, int m) {
                 A v0[4], v1[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
@@ -543,7 +563,7 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
         } break;
         case B2SV_OP_SWAP: {
             const uint32_t ba = tile.swz(1u << op.tpos), bb = tile.swz(1u << op.tpos2);
-            tile_for_each<4>(tile, cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
+            tile_for_each<4>(tile, cnt, fixpos, nfix, lctrl, swaps, [&](const uint32_t* l, int m) {
                 A va[4], vb[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
@@ -563,7 +583,7 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
             const uint32_t bt = tile.swz(1u << op.tpos);
             const C m00 = N::mk(mval<A>(op.m, 0), mval<A>(op.m, 1)), m01 = N::mk(mval<A>(op.m, 2), mval<A>(op.m, 3));
             const C m10 = N::mk(mval<A>(op.m, 4), mval<A>(op.m, 5)), m11 = N::mk(mval<A>(op.m, 6), mval<A>(op.m, 7));
-            tile_for_each<2>(tile, cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
+            tile_for_each<2>(tile, cnt, fixpos, nfix, lctrl, swaps, [&](const uint32_t* l, int m) {
                 C v0[2], v1[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u)
@@ -584,7 +604,7 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
             if (op.tpos == 0xFF) {  // target outside the tile: one CTA-uniform factor
                 const C d = (base & op.ext_tbit) ? d1 : d0;
                 if (d.x == 1 && d.y == 0) break;
-                tile_for_each<4>(tile, cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
+                tile_for_each<4>(tile, cnt, fixpos, nfix, lctrl, swaps, [&](const uint32_t* l, int m) {
                     C v[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
@@ -595,7 +615,7 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
                 });
             } else {
                 const uint32_t bt = tile.swz(1u << op.tpos);
-                tile_for_each<2>(tile, cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
+                tile_for_each<2>(tile, cnt, fixpos, nfix, lctrl, swaps, [&](const uint32_t* l, int m) {
                     C v0[2], v1[2];
 #pragma unroll
                     for (int u = 0; u < 2; ++u)
@@ -632,7 +652,7 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
             // (outer loop: matrix in registers), its threads the pairs of one value (inner loop)
             const uint32_t nt = blockDim.x;
             const uint32_t per = 1u << fbits, T = per < nt ? per : nt;
-            const uint32_t t = threadIdx.x & (T - 1), grp = threadIdx.x / T, ngrp = nt / T;
+            const uint32_t t = lane_swaps(threadIdx.x & (T - 1), swaps), grp = threadIdx.x / T, ngrp = nt / T;
             const uint32_t lt = expand_local(t, mfixpos, mnfix);  // see tile_for_each
             const uint32_t himask = expand_local((per - 1u) & ~(T - 1u), mfixpos, mnfix);
             for (uint32_t il = grp; il < (1u << nl); il += ngrp) {
@@ -674,7 +694,7 @@ __device__ __forceinline__ void tile_apply_op(TV tile, const TileOp& op, int k, 
         } break;
         default: {  // PHASE
             const C w = N::mk(mval<A>(op.m, 0), mval<A>(op.m, 1));
-            tile_for_each<4>(tile, cnt, fixpos, nfix, lctrl, [&](const uint32_t* l, int m) {
+            tile_for_each<4>(tile, cnt, fixpos, nfix, lctrl, swaps, [&](const uint32_t* l, int m) {
                 C v[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
@@ -712,7 +732,7 @@ __device__ __forceinline__ void tile_apply_phase(TV tile, const TileOp& hdr, con
     // every gate of the phase (hdr.lctrl): heavily controlled stretches only touch their own corner
     const uint32_t cnt = 1u << (k - hdr.nfix);
     if (threadIdx.x >= cnt) return;
-    const uint32_t lt = expand_local(threadIdx.x, hdr.fixpos, hdr.nfix) | hdr.lctrl;  // see tile_for_each
+    const uint32_t lt = expand_local(lane_swaps(threadIdx.x, (uint32_t)hdr.ext_tbit), hdr.fixpos, hdr.nfix) | hdr.lctrl;  // see tile_for_each
     const uint32_t himask = cnt > blockDim.x ? expand_local((cnt - 1u) & ~(blockDim.x - 1u), hdr.fixpos, hdr.nfix) : 0u;
     uint32_t hi = 0;
     for (uint32_t g = threadIdx.x; g < cnt; g += blockDim.x) {

@@ -492,6 +492,69 @@ inline void assign_block_slots(std::vector<TileOp>& ops, std::vector<SlotFill>& 
         }
 }
 
+// Lane assignment per pass (kernels.cuh: lane_swaps).  `fixed`: the tile positions the pass does NOT enumerate (targets,
+// controls).  The lowest lane bits -- 3 for 16-byte amplitudes (a shared-memory phase is 8 lanes), 4 for 8-byte ones (16
+// lanes) -- should land on free positions whose bank-group bits differ: with the 128-byte swizzle the bank group of a
+// complex128 element is (l & 7) ^ ((l >> 3) & 7), i.e. position p < 6 drives bit p mod 3; of a complex64 element
+// (l & 15) ^ (((l >> 4) & 7) << 1), i.e. positions {0}, {1,4}, {2,5}, {3,6} drive bits 0..3.
+inline uint32_t lane_swap_code(uint32_t fixed, int k, int amp_bytes) {
+    int F[16], nf = 0;
+    for (int p = 0; p < k && nf < 16; ++p)
+        if (!((fixed >> p) & 1u)) F[nf++] = p;
+    const int lane_bits = amp_bytes == 16 ? 3 : 4, lim = amp_bytes == 16 ? 6 : 7;
+    auto cls = [&](int p) { return amp_bytes == 16 ? p % 3 : (p == 0 ? 0 : 1 + (p - 1) % 3); };
+    const int m = nf < 8 ? nf : 8;  // only the low 8 bits of the thread number are permuted, and only below log2(groups)
+    int chosen[4], nc = 0;
+    bool used[8] = {}, have[4] = {};
+    for (int i = 0; i < m && nc < lane_bits; ++i)
+        if (F[i] < lim && !have[cls(F[i])]) {
+            have[cls(F[i])] = true;
+            used[i] = true;
+            chosen[nc++] = i;
+        }
+    for (int i = 0; i < m && nc < lane_bits; ++i)
+        if (!used[i]) {
+            used[i] = true;
+            chosen[nc++] = i;
+        }
+    // thread bit j normally feeds F[j]; make thread bit kk feed F[chosen[kk]] by successive swaps
+    int cur[8];
+    for (int j = 0; j < 8; ++j) cur[j] = j;
+    uint32_t code = 0;
+    int ns = 0;
+    for (int kk = 0; kk < nc; ++kk) {
+        int at = 0;
+        while (cur[at] != kk) ++at;
+        if (at == chosen[kk]) continue;
+        std::swap(cur[at], cur[chosen[kk]]);
+        code |= ((uint32_t)at | ((uint32_t)chosen[kk] << 3)) << (6 * ns);
+        ++ns;
+    }
+    return code;
+}
+
+inline void assign_lane_swaps(std::vector<TileOp>& ops, int k, int amp_bytes) {
+    static const bool disabled = std::getenv("B2SV_NO_LANE_SWAPS") != nullptr;
+    if (disabled) return;
+    auto fixed_of = [](uint64_t fixpos, int nfix) {
+        uint32_t f = 0;
+        for (int i = 0; i < nfix; ++i) f |= 1u << ((fixpos >> (4 * i)) & 15);
+        return f;
+    };
+    for (size_t o = 0; o < ops.size(); ++o) {
+        TileOp& op = ops[o];
+        if (op.op == kOpPhase) {
+            op.ext_tbit = lane_swap_code(fixed_of(op.fixpos, op.nfix), k, amp_bytes);
+            o += op.ph.count;  // members keep their fields
+            continue;
+        }
+        if (op.op == kOpMono || op.op == kOpNop) continue;
+        if (op.op == B2SV_OP_DIAG1 && op.tpos == 0xFF) continue;  // ext_tbit is that gate's target bit
+        if (op.op == kOpMux) op.ext_tbit = lane_swap_code(fixed_of(op.mux.mfixpos, op.mux.mnfix), k, amp_bytes);
+        else op.ext_tbit = lane_swap_code(fixed_of(op.fixpos, op.nfix), k, amp_bytes);
+    }
+}
+
 // The complete op program of one SEG_TILE / SEG_LOW6 segment, appended to `out`.
 // Table-driven monomial phases append their walk results to plan.mux_tables.
 inline void build_segment_ops(Plan& plan, const Segment& seg, const PlanConfig& cfg, std::vector<TileOp>& out,
@@ -504,6 +567,7 @@ inline void build_segment_ops(Plan& plan, const Segment& seg, const PlanConfig& 
     if (slots && seg.cls == SEG_TILE) assign_block_slots(seg_ops, *slots);
     const bool tile = seg.cls == SEG_TILE;
     append_with_phases(seg_ops, ex.m, cfg.phases && tile, cfg.mono && tile, seg.common_ctrl, &plan.mux_tables, grouped, &plan.mono_tables);
+    if (tile) assign_lane_swaps(grouped, ex.m, cfg.amp_bytes);
     if (tile) layout_batches(grouped, out);
     else out.insert(out.end(), grouped.begin(), grouped.end());
 }
