@@ -62,3 +62,32 @@ def test_block_encoding_compute_matches_the_columns_of_toarray(fake_engine):
     eye = np.eye(expected.shape[1], dtype=np.complex128)
     got = adapter.block_encoding_compute(_Circuit(case.gates), n, s_in, s_out, norm, eye)
     assert np.abs(got.T - expected).max() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["fourier4", "laplace_n3", "bpx_L2", "laplace_readme_n4"])
+def test_block_encoding_compute_adjoint_follows_the_reference_formula(fake_engine, name):
+    """nodes/block_encoding.py:68-80: project onto subspace_out, run the adjoint circuit on that vector as the
+    state of the whole register, normalization * project onto subspace_in -- vector and batch forms.  The
+    reference formula needs dimension_out == 2^n, so the output subspace here is the whole register."""
+    from tests.helpers import dagger_gates
+
+    case = load_golden(name)
+    n, norm = case.n_qubits, case.meta["normalization"]
+    s_in, s_out = case.meta["subspace_in"], [[[], []]] * n
+    b_in = np_oracle.enumerate_basis(s_in)
+    adjoint = _Circuit(dagger_gates(case.gates))
+    rng = np.random.default_rng(6)
+    batch = rng.normal(size=(3, 2**n)) + 1j * rng.normal(size=(3, 2**n))
+
+    def ref(vec):
+        return norm * np_oracle.simulate_gates(adjoint.gates, n, vec)[b_in]
+
+    got = adapter.block_encoding_compute_adjoint(adjoint, n, s_in, s_out, norm, batch[2])
+    assert got.shape == (len(b_in),) and np.abs(got - ref(batch[2])).max() < 1e-12
+    got = adapter.block_encoding_compute_adjoint(adjoint, n, s_in, s_out, norm, batch)
+    assert got.shape == (3, len(b_in))
+    assert np.abs(got - np.stack([ref(v) for v in batch])).max() < 1e-12
+    # a post-selected output subspace hands dimension_out < 2^n amplitudes to Circuit.simulate: an error upstream too
+    if len(np_oracle.enumerate_basis(case.meta["subspace_out"])) != 2**n:
+        with pytest.raises((ValueError, IndexError)):
+            adapter.block_encoding_compute_adjoint(adjoint, n, s_in, case.meta["subspace_out"], norm, batch[0])

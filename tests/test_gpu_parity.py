@@ -330,6 +330,34 @@ def test_block_encoding_compute_device_resident(name):
     assert got.shape == want.shape and np.abs(got - want).max() < tol("complex128", len(case.gates))
 
 
+@pytest.mark.parametrize("name", ["fourier4", "laplace_n8", "bpx_L3", "laplace_readme_n8"])
+def test_block_encoding_compute_adjoint_device_resident(name):
+    """adapter.block_encoding_compute_adjoint == the reference's BlockEncoding.compute_adjoint formula evaluated
+    with the oracle (block_encoding.py:68-80): the adjoint circuit on the projected input as the state of the whole
+    register, normalization * projection onto subspace_in gathered on the device."""
+    from tests.helpers import dagger_gates
+
+    case = load_golden(name)
+    n, norm = case.n_qubits, case.meta["normalization"]
+    s_in, s_out = case.meta["subspace_in"], [[[], []]] * n  # the formula needs dimension_out == 2^n
+    b_in = np_oracle.enumerate_basis(s_in)
+    rng = np.random.default_rng(17)
+    batch = (rng.normal(size=(2, 2**n)) + 1j * rng.normal(size=(2, 2**n))) / np.sqrt(2.0 ** (n + 1))
+
+    class Adjoint:
+        gates = dagger_gates(case.gates)
+
+    def ref(vec):
+        return norm * c_oracle.simulate_gates(Adjoint.gates, n, vec)[b_in]
+
+    got = adapter.block_encoding_compute_adjoint(Adjoint, n, s_in, s_out, norm, batch[1])
+    assert got.shape == (len(b_in),) and np.abs(got - ref(batch[1])).max() < tol("complex128", len(case.gates))
+    got = adapter.block_encoding_compute_adjoint(Adjoint, n, s_in, s_out, norm, batch)
+    want = np.stack([ref(v) for v in batch])
+    assert got.shape == want.shape and np.abs(got - want).max() < tol("complex128", len(case.gates))
+    adapter.clear_caches()
+
+
 def test_adapter_simulate_circuit_contract():
     """Circuit.simulate's contract (circuit.py:42-70) incl. quirks Q1-Q3, Q7 of SURVEY.md App. D."""
     import tequila as tq

@@ -249,6 +249,32 @@ def block_encoding_compute(tq_circuit, n_qubits: int, subspace_in, subspace_out,
     return results
 
 
+def block_encoding_compute_adjoint(tq_circuit_adjoint, n_qubits: int, subspace_in, subspace_out, normalization, input: np.ndarray) -> np.ndarray:
+    """``BlockEncoding.compute_adjoint`` (nodes/block_encoding.py:68-80):
+    ``normalization * subspace_in.project(circuit.adjoint().simulate(subspace_out.project(input)))``, vector and
+    batch forms.  ``tq_circuit_adjoint`` is the tequila circuit of ``circuit.adjoint()``.  The reference hands the
+    projected input (``dimension_out`` amplitudes) to ``Circuit.simulate`` as the initial state of the WHOLE register,
+    so it only works when ``dimension_out == 2^n_qubits``; other sizes raise here as they do there.  What changes is
+    the way back: the 2^n amplitudes stay on the device and only ``dimension_in`` of them, already scaled, return."""
+    prog_in = subspace_in if isinstance(subspace_in, SubspaceProgram) else SubspaceProgram(subspace_in)
+    prog_out = subspace_out if isinstance(subspace_out, SubspaceProgram) else SubspaceProgram(subspace_out)
+    n = max(1, int(n_qubits))
+    input = np.asarray(input)
+
+    def one(vec):
+        projected_input = np.ascontiguousarray(vec[_basis_indices(prog_out)], dtype=np.complex128)
+        if not touches_any_qubit(tq_circuit_adjoint.gates) or prog_in.total_qubits > n:
+            return normalization * simulate_circuit(tq_circuit_adjoint, n_qubits, projected_input)[_basis_indices(prog_in)]
+        return _run(tq_circuit_adjoint, n_qubits, projected_input).project(prog_in, scale=normalization)
+
+    if input.ndim == 1:
+        return one(input)
+    results = np.zeros((input.shape[0], prog_in.dimension), dtype=np.complex128)
+    for idx in np.ndindex(input.shape[:-1]):
+        results[idx] = one(input[idx])
+    return results
+
+
 _SAMPLING_RNG = np.random.default_rng()
 
 
@@ -415,6 +441,26 @@ def install(dtype="complex128", device: int = 0, opts: PlanOpts | None = None, p
 
             block_encoding_compute_patched.__doc__ = _ORIGINALS["BlockEncoding.compute"].__doc__
             ube_node.BlockEncoding.compute = block_encoding_compute_patched
+
+            if "BlockEncoding.compute_adjoint" not in _ORIGINALS:
+                _ORIGINALS["BlockEncoding.compute_adjoint"] = ube_node.BlockEncoding.compute_adjoint
+
+            def block_encoding_compute_adjoint_patched(self, input):
+                # the adjoint circuit is built once per node and kept, so its lowering and plan are cached too
+                adjoint = getattr(self, "_b2sv_adjoint_circuit", None)
+                if adjoint is None or adjoint[0] is not self._circuit_obj:
+                    adjoint = (self._circuit_obj, self._circuit_obj.adjoint())
+                    self._b2sv_adjoint_circuit = adjoint
+                try:
+                    return block_encoding_compute_adjoint(
+                        adjoint[1]._tq_circuit, adjoint[1].n_qubits, _subspace_program(self._subspace_in_obj),
+                        _subspace_program(self._subspace_out_obj), self._normalization_value, input,
+                    )
+                except LoweringError:
+                    return _ORIGINALS["BlockEncoding.compute_adjoint"](self, input)
+
+            block_encoding_compute_adjoint_patched.__doc__ = _ORIGINALS["BlockEncoding.compute_adjoint"].__doc__
+            ube_node.BlockEncoding.compute_adjoint = block_encoding_compute_adjoint_patched
         except ImportError:  # pragma: no cover
             pass
 
@@ -438,6 +484,8 @@ def uninstall() -> None:
         import unitaria.nodes.block_encoding as ube_node
 
         ube_node.BlockEncoding.compute = _ORIGINALS.pop("BlockEncoding.compute")
+        if "BlockEncoding.compute_adjoint" in _ORIGINALS:
+            ube_node.BlockEncoding.compute_adjoint = _ORIGINALS.pop("BlockEncoding.compute_adjoint")
     if "Node.simulate" in _ORIGINALS:
         import unitaria.nodes.node as unode
 
