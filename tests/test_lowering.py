@@ -159,3 +159,20 @@ def test_subspace_string_form():
     assert p.total_qubits == 5 and p.dimension == 8
     assert len(p.instrs) == 3  # END, ZEROS(3,2), FREE(0,3): runs are merged
     assert [walk(p, i) for i in range(9)] == [0, 1, 2, 3, 4, 5, 6, 7, None]
+
+
+def test_memoised_lowering_equals_gate_by_gate_lowering():
+    """lower_gates lowers each distinct gate record once and gathers (sub-circuit reuse, qsvt.py:341-359): same
+    bytes as lowering every gate on its own, I gates dropped, order kept, unhashable fields tolerated."""
+    from tests.helpers import load_golden
+    from unitaria_b200.fixtures import GateRecord
+    from unitaria_b200.lowering import _lower_each
+
+    case = load_golden("pinv_bpx_L2")
+    gates = list(case.gates)
+    gates.insert(7, GateRecord("I", (3,), (), None, 1.0))
+    gates.insert(400, GateRecord("I", (5,), (), None, 1.0))
+    gates.append(GateRecord("X", [2], [0, 1], None, 1.0))  # list-valued targets: not hashable
+    low = lower_gates(gates, case.n_qubits)
+    each = _lower_each(gates, case.n_qubits)
+    assert len(low) == len(gates) - 2 and low.tobytes() == each.tobytes()

@@ -88,14 +88,48 @@ def _mask(qubits) -> int:
 
 
 def lower_gates(gates, n_qubits: int | None = None) -> np.ndarray:
-    """Lower a sequence of tequila-like gates to a ``GATE_DTYPE`` array (one entry per non-``I`` gate)."""
+    """Lower a sequence of tequila-like gates to a ``GATE_DTYPE`` array (one entry per non-``I`` gate).
+
+    unitaria's circuits are built by repeating sub-circuits (QSVT alternates A and A^dagger,
+    nodes/qsvt/qsvt.py:341-359; amplification repeats the whole node): the 93 675 gates of
+    Pseudoinverse(BPX L=4) are 753 distinct (name, targets, controls, parameter, power) records.  Each
+    distinct record is lowered once and the output is one table gather."""
+    gates = gates if isinstance(gates, (list, tuple)) else list(gates)
+    if len(gates) < 64:
+        return _lower_each(gates, n_qubits)
+    memo: dict = {}
+    unique = []
+    which = np.empty(len(gates), dtype=np.intp)
+    for i, g in enumerate(gates):
+        try:
+            key = (g.name, g.target, g.control, getattr(g, "parameter", None), getattr(g, "power", None))
+            j = memo.get(key)
+        except TypeError:  # unhashable field (list targets, symbolic parameter): lowered on its own
+            key, j = None, None
+        if j is None:
+            j = len(unique)
+            unique.append(g)
+            if key is not None:
+                memo[key] = j
+        which[i] = j
+    table, kept = _lower_each(unique, n_qubits, keep_dropped=True)
+    return table[which[kept[which]]]
+
+
+def _lower_each(gates, n_qubits: int | None = None, keep_dropped: bool = False):
+    """One entry per gate; ``keep_dropped``: also return the mask of entries that are real gates (not ``I``),
+    with the array still holding one (zeroed) slot per input gate."""
     out = np.zeros(len(gates), dtype=GATE_DTYPE)
+    kept = np.ones(len(gates), dtype=bool)
     ops, t0s, t1s, nts, ctrls, mats = out["op"], out["t0"], out["t1"], out["n_targets"], out["ctrl_mask"], out["m"]
     k = 0
     for g in gates:
         name = str(g.name)
         uname = name.upper()
         if uname == "I":
+            if keep_dropped:
+                kept[k] = False
+                k += 1
             continue
         target = tuple(int(t) for t in (g.target or ()))
         control = tuple(int(c) for c in (g.control or ()))
@@ -156,6 +190,8 @@ def lower_gates(gates, n_qubits: int | None = None) -> np.ndarray:
             else:
                 raise LoweringError(f"gate {name!r} is outside unitaria's gate alphabet (SURVEY.md App. A)")
         k += 1
+    if keep_dropped:
+        return out, kept
     return out[:k]
 
 
