@@ -5,6 +5,7 @@
 // Circuit.simulate (/root/reference/src/unitaria/circuit.py:62-70) plus the Subspace projection and
 // norm of Node.simulate / simulate_norm (/root/reference/src/unitaria/nodes/node.py:363-403).
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <unistd.h>
 
@@ -27,6 +28,16 @@
 #include "planner.hpp"
 #include "tileops.hpp"
 #include "perm_jit.hpp"
+
+// NVTX ranges (tracing): every C-ABI entry point that launches work and every sweep of a plan is a
+// named range, so an Nsight timeline shows "b2sv_apply > plan > tile / perm / low6 ..." next to the kernels.  nvtx3 is
+// header-only and resolves to a no-op call when no tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 namespace {
 
@@ -1059,6 +1070,7 @@ int b2sv_set_zero(b2sv_t* sv) {
 }
 
 int b2sv_fill_random(b2sv_t* sv, uint64_t seed, int support_bits, uint64_t index_base) {
+    NvtxRange nvtx_range("b2sv_fill_random");
     if (int rc = check(sv)) return rc;
     if (support_bits < 0 || support_bits > 63) return fail(B2SV_EINVAL, "support_bits %d outside [0,63]", support_bits);
     CU(cudaSetDevice(sv->device));
@@ -1084,6 +1096,7 @@ int b2sv_fill_random(b2sv_t* sv, uint64_t seed, int support_bits, uint64_t index
 static const uint64_t kStageAmps = 1ull << 22;  // 64 MiB of complex128
 
 int b2sv_upload(b2sv_t* sv, const void* host) {
+    NvtxRange nvtx_range("b2sv_upload");
     if (int rc = check(sv)) return rc;
     if (!host) return fail(B2SV_EINVAL, "host buffer is null");
     CU(cudaSetDevice(sv->device));
@@ -1117,6 +1130,7 @@ int b2sv_upload(b2sv_t* sv, const void* host) {
 }
 
 int b2sv_download(b2sv_t* sv, void* host) {
+    NvtxRange nvtx_range("b2sv_download");
     if (int rc = check(sv)) return rc;
     if (!host) return fail(B2SV_EINVAL, "host buffer is null");
     CU(cudaSetDevice(sv->device));
@@ -1145,6 +1159,7 @@ int b2sv_download(b2sv_t* sv, void* host) {
 }
 
 int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_plan_opts* opts) {
+    NvtxRange nvtx_range("b2sv_apply");
     if (int rc = check(sv)) return rc;
     if (n_gates > 0 && !gates) return fail(B2SV_EINVAL, "gates is null");
     CU(cudaSetDevice(sv->device));
@@ -1203,6 +1218,7 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
             }
             if ((int)best >= cfg.perm_min) scratch_ok = ensure_scratch(sv) == B2SV_OK;
         }
+        NvtxRange nvtx_plan("b2sv plan (host)");
         sv->plan = make_plan(gates, n_gates, cfg, scratch_ok);
         Plan& np = sv->plan;
         // tile ops of all tile segments, one upload
@@ -1263,6 +1279,7 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
     for (size_t s = 0; s < plan.segs.size(); ++s) {
         const Segment& seg = plan.segs[s];
         int rc = B2SV_OK;
+        NvtxRange nvtx_seg(seg.cls == SEG_TILE ? "sweep: tile" : seg.cls == SEG_LOW6 ? "sweep: low6" : seg.cls == SEG_PERM ? "sweep: perm" : "sweep: gate1q");
         // a pending basis state is generated by the first sweep if that sweep visits every tile
         const bool lazy_init = sv->pending_basis && (seg.cls == SEG_TILE || seg.cls == SEG_LOW6) && seg.common_ctrl == 0;
         // ... and if a permutation sweep comes next, only the tile that owns the index is written at all: the
@@ -1310,6 +1327,7 @@ int b2sv_apply(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, const b2sv_pl
 
 int b2sv_project_norm2_at(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
                           uint64_t index_base, double* out) {
+    NvtxRange nvtx_range("b2sv_project_norm2_at");
     if (int rc = check(sv)) return rc;
     if (!out) return fail(B2SV_EINVAL, "out is null");
     CU(cudaSetDevice(sv->device));
@@ -1374,6 +1392,7 @@ int b2sv_project_norm2(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int e
 
 int b2sv_project_gather(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
                         double scale_re, double scale_im, void* host_out, uint64_t dim) {
+    NvtxRange nvtx_range("b2sv_project_gather");
     if (int rc = check(sv)) return rc;
     if (!host_out && dim > 0) return fail(B2SV_EINVAL, "host_out is null");
     CU(cudaSetDevice(sv->device));
@@ -1412,6 +1431,7 @@ int b2sv_project_gather(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int 
 int b2sv_project_gather_sparse(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
                                double scale_re, double scale_im, uint64_t dim, uint64_t cap, uint64_t* idx_out, void* val_out,
                                uint64_t* nnz_out) {
+    NvtxRange nvtx_range("b2sv_project_gather_sparse");
     if (int rc = check(sv)) return rc;
     if (!nnz_out || (cap > 0 && (!idx_out || !val_out))) return fail(B2SV_EINVAL, "null output");
     *nnz_out = 0;
@@ -1463,6 +1483,7 @@ int b2sv_project_gather_sparse(b2sv_t* sv, const b2sv_subinstr* prog, int n_inst
 
 int b2sv_project_gather_async(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
                               double scale_re, double scale_im, void* host_out, uint64_t dim, int slot) {
+    NvtxRange nvtx_range("b2sv_project_gather_async");
     if (int rc = check(sv)) return rc;
     if (slot < 0 || slot > 1) return fail(B2SV_EINVAL, "slot %d outside [0,1]", slot);
     if (!host_out && dim > 0) return fail(B2SV_EINVAL, "host_out is null");
@@ -1531,6 +1552,7 @@ int b2sv_gather_wait(b2sv_t* sv, int slot) {
 
 int b2sv_project_gather_device(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
                                double scale_re, double scale_im, void** dev_out, uint64_t dim) {
+    NvtxRange nvtx_range("b2sv_project_gather_device");
     if (int rc = check(sv)) return rc;
     if (!dev_out) return fail(B2SV_EINVAL, "dev_out is null");
     *dev_out = nullptr;
@@ -1566,6 +1588,7 @@ int b2sv_project_gather_device(b2sv_t* sv, const b2sv_subinstr* prog, int n_inst
 }
 
 int b2sv_upload_device(b2sv_t* sv, const void* dev_amps_c128) {
+    NvtxRange nvtx_range("b2sv_upload_device");
     if (int rc = check(sv)) return rc;
     if (!dev_amps_c128) return fail(B2SV_EINVAL, "device buffer is null");
     CU(cudaSetDevice(sv->device));
@@ -1587,6 +1610,7 @@ int b2sv_upload_device(b2sv_t* sv, const void* dev_amps_c128) {
 
 int b2sv_embed(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits, const void* host_in,
                uint64_t dim) {
+    NvtxRange nvtx_range("b2sv_embed");
     if (int rc = check(sv)) return rc;
     if (!host_in && dim > 0) return fail(B2SV_EINVAL, "host_in is null");
     CU(cudaSetDevice(sv->device));
@@ -1616,6 +1640,7 @@ int b2sv_embed(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, in
 
 int b2sv_enumerate_basis(b2sv_t* sv, const b2sv_subinstr* prog, int n_instr, int entry, int target_qubits,
                          int64_t* host_out, uint64_t dim) {
+    NvtxRange nvtx_range("b2sv_enumerate_basis");
     if (int rc = check(sv)) return rc;
     if (!host_out && dim > 0) return fail(B2SV_EINVAL, "host_out is null");
     CU(cudaSetDevice(sv->device));
@@ -1870,6 +1895,7 @@ int b2sv_ipc_attach(b2sv_t* sv, int rank, int world, const void* blobs) {
 }
 
 int b2sv_dist_ready(b2sv_t* sv, uint64_t* state_out) {
+    NvtxRange nvtx_range("b2sv_dist_ready");
     if (int rc = check(sv)) return rc;
     if (!state_out) return fail(B2SV_EINVAL, "state_out is null");
     if (sv->dist_world == 0) return fail(B2SV_ESTATE, "not attached (b2sv_ipc_attach)");
@@ -1906,6 +1932,7 @@ int b2sv_dist_ready(b2sv_t* sv, uint64_t* state_out) {
 
 int b2sv_dist_perm(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, int n_total, uint32_t flip_in, uint32_t flip_out,
                    const uint64_t* states, const b2sv_plan_opts* opts) {
+    NvtxRange nvtx_range("b2sv_dist_perm");
     if (int rc = check(sv)) return rc;
     if (sv->dist_world == 0) return fail(B2SV_ESTATE, "not attached (b2sv_ipc_attach)");
     if (n_gates > 0 && !gates) return fail(B2SV_EINVAL, "gates is null");
@@ -2012,6 +2039,7 @@ int b2sv_dist_perm(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, int n_tot
 }
 
 int b2sv_dist_done(b2sv_t* sv) {
+    NvtxRange nvtx_range("b2sv_dist_done");
     if (int rc = check(sv)) return rc;
     if (sv->dist_world == 0) return fail(B2SV_ESTATE, "not attached (b2sv_ipc_attach)");
     CU(cudaSetDevice(sv->device));
