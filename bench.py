@@ -199,6 +199,43 @@ def cpu_sample(case, budget_s=20.0, stride=4, state=None, max_qubits=30):
     }
 
 
+def effective_bytes(lowered, n, amp_bytes):
+    """SURVEY.md 8(d) "effective" traffic: what a gate-at-a-time simulator would move for this circuit,
+    sum over lowered gates of 2*B*2^(n-c) (c controls; half of that for a diagonal gate with one unit entry, which only
+    touches target = 1).  Fusion makes effective GB/s exceed the HBM peak: it is NOT a roofline fraction."""
+    from unitaria_b200 import cabi
+
+    c = np.array([bin(int(m)).count("1") for m in lowered["ctrl_mask"]], dtype=np.float64)
+    half = (lowered["op"] == cabi.OP_DIAG1) & (lowered["m"][:, 0] == 1.0) & (lowered["m"][:, 1] == 0.0)
+    c = c + half.astype(np.float64)
+    return float(np.sum(2.0 * amp_bytes * np.exp2(n - c)))
+
+
+def reference_projection_cost(spec, seconds=2.0):
+    """The reference's own projection (subspace.py:325-335) filters range(2^total_qubits) through the Python predicate
+    test_basis, one index at a time; this times the oracle's literal restatement of that predicate on a bounded sample
+    of indices (part of today's Node.simulate, reported apart from the gate sweeps as SURVEY.md 8(d) asks)."""
+    from oracle import np_oracle
+
+    total = np_oracle.spec_total_qubits(spec)
+    rng = np.random.default_rng(0)
+    idx = [int(i) for i in rng.integers(0, 1 << total, size=200000)]
+    done, t0 = 0, time.perf_counter()
+    while done < len(idx) and time.perf_counter() - t0 < seconds:
+        for i in idx[done : done + 2000]:
+            np_oracle.test_basis(spec, i)
+        done += 2000
+    dt = time.perf_counter() - t0
+    per = dt / max(1, done)
+    return {
+        "us_per_index": 1e6 * per,
+        "indices_sampled": done,
+        "total_qubits": total,
+        "enumerate_basis_seconds_at_full_size": per * float(1 << total),
+        "note": "oracle/np_oracle.test_basis (restates subspace.py:297-323) on random indices, one host thread; the reference calls it for every index of range(2^total_qubits) on each projection",
+    }
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -525,6 +562,9 @@ def run_single(args):
     adapter.clear_caches()
 
     cpu = None if args.no_cpu_baseline else cpu_sample(case, budget_s=args.cpu_seconds)
+    if cpu is not None:
+        cpu["projection"] = reference_projection_cost(case.meta["subspace_out"])
+    eff_bytes = effective_bytes(lowered, n, 16 if dtype == "c128" else 8)
     line = {
         "metric": "gates_per_sec",
         "value": m["value"],
@@ -544,7 +584,13 @@ def run_single(args):
         "kernels": m["kernels"],
         "inputs": inputs,
         "configs": configs,
-        "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "effective": {
+            "GBps": eff_bytes / (m["ms_per_step"] * 1e-3) / 1e9,
+            "bytes_per_step": eff_bytes,
+            "note": "sum over lowered gates of 2*B*2^(n-controls) / device time per step: the traffic of a gate-at-a-time simulator; "
+            "above the HBM peak because sweeps are fused -- an 'effective' figure, not a roofline fraction",
+        },
+        "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "projection")},
         "e2e": e2e,
         "gpu_launches": int(st["launches"]),
         "clocks": clk,
