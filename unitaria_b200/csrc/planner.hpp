@@ -440,9 +440,24 @@ inline uint64_t gate_targets(const PGate& g) {
     return t;
 }
 
+// A small multiplexor (target + index bits on <= 3 qubits) is a block-diagonal 4x4 / 8x8 matrix on those qubits: a dense
+// block that already covers them absorbs it for free.  Config 3's closing sweep was MUX (index bits 1, 2 -> target 0) +
+// an 8x8 block on {0,1,2} + a monomial phase: three shared-memory passes where two do (the whole Moettoenen rotation
+// tree of circuits/multiplexed_rot.py on three qubits is ONE real 8x8 matrix).  For the block DP the index bits count
+// as block qubits (they select the matrix, so they can never be "common controls").
+inline bool blockable_mux(const Plan& plan, const PGate& g) {
+    static const bool disabled = std::getenv("B2SV_NO_MUX_IN_BLOCK") != nullptr;
+    return !disabled && g.op == B2SV_OP_MUX && g.mux >= 0 && plan.mux[g.mux].nbits >= 1 && plan.mux[g.mux].nbits + 1 <= kBlockMaxQubits;
+}
+inline bool blockable_gate(const Plan& plan, const PGate& g) { return blockable_gate(g) || blockable_mux(plan, g); }
+inline uint64_t block_targets(const Plan& plan, const PGate& g) {
+    return g.op == B2SV_OP_MUX ? (1ull << g.t0) | plan.mux[g.mux].ctrl_mask : gate_targets(g);
+}
+inline bool block_gate_is_real(const Plan& plan, const PGate& g);
+
 // Apply gate g to a 2^kb vector (interleaved re,im) whose bit i stands for qubit q[i]; controls in
 // `common` are assumed satisfied.
-inline void block_apply_gate(double* v, int kb, const uint8_t* q, const PGate& g, uint64_t common) {
+inline void block_apply_gate(double* v, int kb, const uint8_t* q, const PGate& g, uint64_t common, const Plan* plan = nullptr) {
     auto local = [&](int qubit) {
         for (int i = 0; i < kb; ++i)
             if (q[i] == qubit) return i;
@@ -452,6 +467,25 @@ inline void block_apply_gate(double* v, int kb, const uint8_t* q, const PGate& g
     for (int b = 0; b < 64; ++b)
         if (((g.ctrl & ~common) >> b) & 1) lc |= 1u << local(b);
     const uint32_t dim = 1u << kb;
+    if (g.op == B2SV_OP_MUX) {  // table entry chosen by the index bits (ascending qubit order), then a plain 2x2
+        const MuxInfo& mi = plan->mux[g.mux];
+        int ipos[kMuxMaxCtrl], nb = 0;
+        for (int b = 0; b < 64; ++b)
+            if ((mi.ctrl_mask >> b) & 1) ipos[nb++] = local(b);
+        const uint32_t bt = 1u << local(g.t0);
+        for (uint32_t i = 0; i < dim; ++i)
+            if ((i & lc) == lc && !(i & bt)) {
+                uint32_t idx = 0;
+                for (int b = 0; b < nb; ++b) idx |= ((i >> ipos[b]) & 1u) << b;
+                const double* U = plan->mux_tables.data() + 8 * (mi.table_off + idx);
+                const double a0r = v[2 * i], a0i = v[2 * i + 1], a1r = v[2 * (i | bt)], a1i = v[2 * (i | bt) + 1];
+                v[2 * i] = U[0] * a0r - U[1] * a0i + U[2] * a1r - U[3] * a1i;
+                v[2 * i + 1] = U[0] * a0i + U[1] * a0r + U[2] * a1i + U[3] * a1r;
+                v[2 * (i | bt)] = U[4] * a0r - U[5] * a0i + U[6] * a1r - U[7] * a1i;
+                v[2 * (i | bt) + 1] = U[4] * a0i + U[5] * a0r + U[6] * a1i + U[7] * a1r;
+            }
+        return;
+    }
     if (g.op == B2SV_OP_PHASE) {
         for (uint32_t i = 0; i < dim; ++i)
             if ((i & lc) == lc) {
@@ -500,6 +534,14 @@ inline bool gate_is_real(const PGate& g) {
     if (g.op == B2SV_OP_PHASE) return g.m[1] == 0.0;
     return true;
 }
+inline bool block_gate_is_real(const Plan& plan, const PGate& g) {
+    if (g.op != B2SV_OP_MUX) return gate_is_real(g);
+    const MuxInfo& mi = plan.mux[g.mux];
+    const double* t = plan.mux_tables.data() + 8 * mi.table_off;
+    for (size_t e = 0; e < ((size_t)4 << mi.nbits); ++e)
+        if (t[2 * e + 1] != 0.0) return false;
+    return true;
+}
 // What a gate costs as a register-phase member beyond its arithmetic (decode, predicates, the idle threads of a phase
 // whose members share controls): it does NOT shrink with the number of controls.  Measured on the 30-qubit BPX sweeps:
 // 29 mostly doubly-controlled gates in six phases took 6.7 ms of compute where their DFMA count predicted 1.1 ms.
@@ -539,10 +581,10 @@ inline double block_phase_tol() {
 // 4x4 blocks of BPX L=8, all 684 of Pseudoinverse(BPX L=4)) is stored as the real matrix -- half the FP64 work of the
 // pass -- and the phase is left to the caller, who merges the phases of a whole chain of blocks into one gate.
 inline void emit_block(Plan& plan, const std::vector<PGate>& G, size_t a, size_t b, std::vector<PGate>& out, double* ph_re, double* ph_im) {
-    uint64_t K = G[a].ctrl, T = gate_targets(G[a]), U = G[a].ctrl;
+    uint64_t K = G[a].ctrl, T = block_targets(plan, G[a]), U = G[a].ctrl;
     for (size_t q = a + 1; q < b; ++q) {
         K &= G[q].ctrl;
-        T |= gate_targets(G[q]);
+        T |= block_targets(plan, G[q]);
         U |= G[q].ctrl;
     }
     const uint64_t B = T | (U & ~K);
@@ -556,7 +598,7 @@ inline void emit_block(Plan& plan, const std::vector<PGate>& G, size_t a, size_t
     for (uint32_t col = 0; col < dim; ++col) {
         double v[2 * 8] = {0};
         v[2 * col] = 1.0;
-        for (size_t qg = a; qg < b; ++qg) block_apply_gate(v, info.kb, info.q, G[qg], K);
+        for (size_t qg = a; qg < b; ++qg) block_apply_gate(v, info.kb, info.q, G[qg], K, &plan);
         for (uint32_t row = 0; row < dim; ++row) {
             mat[2 * ((size_t)row * dim + col)] = v[2 * row];
             mat[2 * ((size_t)row * dim + col) + 1] = v[2 * row + 1];
@@ -727,19 +769,19 @@ inline void fuse_blocks(Plan& plan) {
         const double open = dpB[p - 1] + kPassCost;  // (not scaled by the gate's controls: barrier + latency of a pass are fixed)
         fromB_P[p] = open < dpP[p - 1] ? 1 : 0;
         dpP[p] = gate_fp64_cost(last, 0) + (fromB_P[p] ? open : dpP[p - 1]);
-        if (!blockable_gate(last)) continue;
-        uint64_t K = last.ctrl, T = gate_targets(last), U = last.ctrl;
-        bool nonperm = !last.is_perm(), real = gate_is_real(last);
+        if (!blockable_gate(plan, last)) continue;
+        uint64_t K = last.ctrl, T = block_targets(plan, last), U = last.ctrl;
+        bool nonperm = !last.is_perm(), real = block_gate_is_real(plan, last);
         for (size_t q = p - 1; q-- > 0 && p - q <= kMaxBlockGates;) {
             const PGate& g = G[q];
-            if (!blockable_gate(g)) break;
+            if (!blockable_gate(plan, g)) break;
             K &= g.ctrl;
-            T |= gate_targets(g);
+            T |= block_targets(plan, g);
             U |= g.ctrl;
             const int kb = popcount64(T | (U & ~K));
             if (kb > kBlockMaxQubits || (T & K) != 0) break;
             nonperm |= !g.is_perm();
-            real = real && gate_is_real(g);
+            real = real && block_gate_is_real(plan, g);
             if (p - q < 3 || kb < 2 || !nonperm) continue;
             const bool prevB = dpB[q] < dpP[q];
             const double c = (prevB ? dpB[q] : dpP[q]) + std::ldexp(block_fp64_cost(kb, real), -popcount64(K));
