@@ -286,13 +286,27 @@ int flush_scalar(b2sv* sv, bool timing) {
     return rc;
 }
 
+// Zero `bytes` of device memory on the handle's stream with the library's own fill kernel (buffers that are not a
+// multiple of 32 bytes -- registers of one qubit -- and B2SV_MEMSET=1, the A/B baseline, take cudaMemsetAsync).
+int fill_zero(b2sv* sv, void* ptr, size_t bytes) {
+    static const bool use_memset = std::getenv("B2SV_MEMSET") != nullptr;
+    if (use_memset || (bytes & 31) != 0 || (reinterpret_cast<uintptr_t>(ptr) & 31) != 0) {
+        CU(cudaMemsetAsync(ptr, 0, bytes, sv->stream));
+        return B2SV_OK;
+    }
+    const uint64_t n32 = bytes / 32;
+    const uint64_t blocks = (n32 + 1023) / 1024;  // <= 2^21 for a 64 GiB buffer
+    k_fill_zero<<<(unsigned)blocks, 256, 0, sv->stream>>>(reinterpret_cast<unsigned char*>(ptr), n32);
+    CU(cudaGetLastError());
+    return B2SV_OK;
+}
+
 // Write the lazily requested basis state out (every reader of the amplitudes calls this first).
 int materialise(b2sv* sv) {
     if (sv->zero) {
         sv->zero = false;
         sv->stats.launches_by_class[CLS_INIT]++;
-        CU(cudaMemsetAsync(sv->amps, 0, sv->count * sv->amp_bytes, sv->stream));
-        return B2SV_OK;
+        return fill_zero(sv, sv->amps, sv->count * sv->amp_bytes);
     }
     if (sv->window) {  // write the implied zeros
         sv->window = false;
@@ -748,7 +762,7 @@ int launch_perm(b2sv* sv, const Plan& plan, const Segment& seg, bool timing, int
         int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
             using A = std::remove_pointer_t<decltype(tag)>;
             LaunchTimer lt(sv, timing, jit_mode == 1 ? CLS_PERM : CLS_PERM_JIT, 1.0 * sv->amp_bytes * (double)sv->count);
-            CU(cudaMemsetAsync(sv->scratch, 0, sv->count * sv->amp_bytes, sv->stream));
+            if (int frc = fill_zero(sv, sv->scratch, sv->count * sv->amp_bytes)) return frc;
             k_perm_scatter<A><<<dim3((unsigned)((cnt + kThreads - 1) / kThreads), 1), kThreads, 0, sv->stream>>>(a, (const DistGate*)sv->d_dist_gates,
                                                                                                           (int)gates.size(), sv->n);
             return B2SV_OK;
@@ -2000,7 +2014,7 @@ int b2sv_dist_perm(b2sv_t* sv, const b2sv_gate* gates, size_t n_gates, int n_tot
         int rc = dispatch_dtype(sv, [&](auto* tag) -> int {
             using A = std::remove_pointer_t<decltype(tag)>;
             LaunchTimer lt(sv, timing, CLS_DIST, 1.0 * sv->amp_bytes * (double)sv->count);
-            CU(cudaMemsetAsync(a.out, 0, sv->count * sv->amp_bytes, sv->stream));
+            if (int frc = fill_zero(sv, a.out, sv->count * sv->amp_bytes)) return frc;
             if (scatter_max)
                 k_perm_scatter<A><<<dim3((unsigned)((scatter_max + kThreads - 1) / kThreads), (unsigned)sv->dist_world), kThreads, 0, sv->stream>>>(
                     a, (const DistGate*)sv->d_dist_gates, (int)pg.size(), sv->n);

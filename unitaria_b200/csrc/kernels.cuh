@@ -1433,6 +1433,23 @@ __global__ void __launch_bounds__(kThreads) k_low6(A* __restrict__ psi, const Lo
     }
 }
 
+// Zero-fill of a state buffer: the write-only half of a window-mode permutation sweep (zero-fill + forward scatter) and
+// of a lazily requested zero / basis state.  256-bit stores (STG.E.256), four per thread, ONE 32 KiB block per CTA and no
+// grid-stride loop: measured on the 8 GiB scratch buffer of cfg 2 (gpurun_out/r2ai_*, r2aj_*) -- cudaMemsetAsync 1.224 ms,
+// a persistent grid (148 x 16 CTAs) of 128-bit streaming stores 1.32-1.33 ms, of plain 128-bit stores 1.36 ms, of 256-bit
+// stores 1.29 ms, TMA bulk stores from a zeroed shared-memory buffer 1.40 ms, this form 1.193 ms (7.2 TB/s): consecutive
+// CTAs write consecutive 32 KiB blocks, so the block scheduler keeps the DRAM pages in order.
+constexpr uint32_t kFillBlockBytes = 32768;
+__global__ void __launch_bounds__(256) k_fill_zero(unsigned char* __restrict__ p, uint64_t n32) {
+    const uint64_t i = (uint64_t)blockIdx.x * 1024u + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (i + (uint64_t)u * 256u < n32) {
+            const unsigned long long z = 0ull;
+            asm volatile("st.global.v4.b64 [%0], {%1, %1, %1, %1};" ::"l"(p + (i + (uint64_t)u * 256u) * 32), "l"(z) : "memory");
+        }
+}
+
 // ===================================================================================================
 // 3. Permutation run: a run of X / multi-controlled X / (controlled) SWAP gates is a bijection f on
 //    amplitude indices.  One out-of-place sweep computes out[j] = in[f^-1(j)] (writes coalesced).
