@@ -297,6 +297,7 @@ int fill_zero(b2sv* sv, void* ptr, size_t bytes) {
     const uint64_t n32 = bytes / 32;
     const uint64_t blocks = (n32 + 1023) / 1024;  // <= 2^21 for a 64 GiB buffer
     k_fill_zero<<<(unsigned)blocks, 256, 0, sv->stream>>>(reinterpret_cast<unsigned char*>(ptr), n32);
+    sv->stats.launches++;  // a kernel of this library like any other (its time is booked by the caller's LaunchTimer)
     CU(cudaGetLastError());
     return B2SV_OK;
 }
