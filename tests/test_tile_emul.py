@@ -156,3 +156,37 @@ def test_fuzz_random_shapes(emul, block):
         want = np_oracle.simulate_gates(gates, n, psi0)
         got, _ = emul(gates, n, psi0, dtype=dtype, tile_qubits=tile_qubits, perm_runs=bool(rng.integers(0, 2)), lookahead=int(rng.choice([0, 4, 32])))
         assert np.abs(got - want).max() < 1e-11, seed
+
+
+def test_small_multiplexors_ride_in_dense_blocks(emul):
+    """A uniformly controlled rotation tree on three qubits (circuits/multiplexed_rot.py: Ry / CNOT ladders, the closing
+    sweep of the Gaussian-convolution circuit) is ONE 8x8 matrix: the multiplexor fusion's table op (index bits 1, 2 ->
+    target 0) must be multiplied into the dense block on {0, 1, 2}, not run as a pass of its own -- and the result must
+    not change."""
+    from unitaria_b200.fixtures import GateRecord as G
+
+    n = 16
+    rng = np.random.default_rng(11)
+    gates = []
+    for _ in range(2):  # target 0 under the index bits 1 and 2: 8 gates -> a 2-bit multiplexor
+        for c in (2, 1, 2, 1):
+            gates += [G("Ry", (0,), (), float(rng.normal()), 1.0), G("X", (0,), (c,), None, 1.0)]
+    for c in (2, 2):  # target 1 under index bit 2: too short for a table, stays plain
+        gates += [G("Ry", (1,), (), float(rng.normal()), 1.0), G("X", (1,), (c,), None, 1.0)]
+    gates += [G("Ry", (2,), (), float(rng.normal()), 1.0)]
+    psi0 = random_state(n, rng)
+    want = np_oracle.simulate_gates(gates, n, psi0)
+
+    def passes():
+        low = np.ascontiguousarray(lower_gates(gates, n), dtype=cabi.GATE_DTYPE)
+        opts = cabi.PlanOpts.make(jit="off")
+        lib = ctypes.CDLL(_build())
+        out = np.zeros(256, dtype=np.int32)
+        m = lib.emul_describe_segment(n, cabi.B2SV_C128, low.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(low)), ctypes.byref(opts), 0,
+                                      out.ctypes.data_as(ctypes.c_void_p), len(out))
+        return [int(out[2 * i]) for i in range(m)]
+
+    got, _info = emul(gates, n, psi0)
+    assert np.abs(got - want).max() < 1e-12
+    kinds = passes()
+    assert 5 not in kinds and kinds.count(6) == 1, kinds  # no MUX pass, one BLOCK pass (op codes of kernels.cuh)
