@@ -242,9 +242,17 @@ inline void append_with_phases(const std::vector<TileOp>& ops, int k, bool enabl
         return t;
     };
     // what the op costs as a stand-alone pass, in units of one read+write pass over the whole tile
+    // Measured (scripts/microbench_passes.py, profiles/microbench_passes_r2.txt): inside a sweep that is bound by its passes
+    // a stand-alone X / SWAP pass on a QUARTER of the tile still costs 0.13 HBM sweeps and a full-tile 2x2 pass 0.23, against
+    // 0.36 for a monomial phase (= 2.5 units here): 0.8 + 0.5 * fraction.  The round-1 model (fraction + 0.08) let runs of
+    // three or four lightly controlled SWAPs / Xs go out as passes of their own; with the measured cost they ride in one
+    // monomial phase (Pseudoinverse(BPX L=4) at 30 qubits: 4857 -> 4601 passes, tile time 7553 -> 7302 ms; A/B through
+    // B2SV_LIGHT_PASS / B2SV_LIGHT_SLOPE, gpurun_out/r2am_*).
+    static const double kLightPass = [] { const char* e = std::getenv("B2SV_LIGHT_PASS"); return e ? std::atof(e) : 0.8; }();
+    static const double kLightSlope = [] { const char* e = std::getenv("B2SV_LIGHT_SLOPE"); return e ? std::atof(e) : 0.5; }();
     auto alone_cost = [](const TileOp& o) {
         const int c = __builtin_popcount(o.lctrl) + (o.op == B2SV_OP_SWAP ? 1 : 0);
-        return std::ldexp(1.0, -c) + 0.08;  // + barrier and latency of a pass of its own
+        return kLightSlope * std::ldexp(1.0, -c) + kLightPass;
     };
     auto pass_cost = [](uint32_t common) { return std::ldexp(1.0, -__builtin_popcount(common)); };
     size_t i = 0;
